@@ -1,0 +1,216 @@
+/*
+ * qcgraft.h -- C ABI of the B200-native inspection hot path (libqcgraft.so).
+ *
+ * The reference (JayDS22/Industrial-Quality-Control-Computer-Vision-System-) is pure
+ * Python and has no FFI today; its seam is the Python method surface
+ * (inference/detector.py:72, models/ensemble.py:71, models/yolo_model.py:84,
+ * inference/segmentation.py:39).  Each entry point below replaces the library
+ * routine(s) the reference executes at the cited call site; the ctypes binding a
+ * maintainer adds is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative qc_status otherwise;
+ *     qc_last_error(ctx) gives the message (the Python shim turns it into the
+ *     reference's {"error": str} convention, inference/detector.py:124-126).
+ *   - all data pointers are DEVICE pointers owned by the caller; the library
+ *     allocates nothing on the data path, never synchronises the stream and
+ *     never touches host memory.  Scratch space comes from the caller via the
+ *     *_workspace_bytes() queries.
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).
+ *   - no CPU fallback exists: every entry point launches sm_100a kernels.
+ */
+#ifndef QCGRAFT_H
+#define QCGRAFT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct qc_ctx qc_ctx;
+
+typedef enum {
+    QC_OK = 0,
+    QC_ERR_INVALID = -1,   /* bad argument */
+    QC_ERR_CUDA = -2,      /* CUDA runtime error (message holds cudaGetErrorString) */
+    QC_ERR_WORKSPACE = -3, /* workspace too small */
+    QC_ERR_UNSUPPORTED = -4
+} qc_status;
+
+/* ---- context ------------------------------------------------------------ */
+int qc_create(int device, qc_ctx** out);
+void qc_destroy(qc_ctx* ctx);
+const char* qc_last_error(const qc_ctx* ctx);
+const char* qc_version(void);
+int qc_sm_count(const qc_ctx* ctx);
+/* number of kernels this ctx has launched since creation (bench.py "gpu_launches") */
+int64_t qc_launch_count(const qc_ctx* ctx);
+/* sizeof() of the ABI structs, for bindings to self-check their layout:
+ * 0 qc_pre_plan, 1 qc_yolo_params, 2 qc_seg_region, 3 qc_seg_params */
+size_t qc_sizeof(int which);
+
+/* ---- K1: letterbox / stretch resize + normalise + NCHW pack -------------
+ * Replaces: cv2.cvtColor(BGR2RGB) inference/detector.py:233-234 and
+ * models/yolo_model.py:79-80 (-> swap_rb); cv2.resize inference/detector.py:240-242
+ * (-> QC_PRE_STRETCH); ultralytics LetterBox + [...,::-1] + NCHW + float()/255 run by
+ * models/yolo_model.py:105-110 (-> QC_PRE_LETTERBOX*); and, with a mean/std LUT, the
+ * ToTensor+Normalize of models/resent_model.py:59-66.
+ */
+typedef enum { QC_PRE_STRETCH = 0, QC_PRE_LETTERBOX = 1, QC_PRE_LETTERBOX_AUTO = 2 } qc_pre_mode;
+typedef enum { QC_DT_F32 = 0, QC_DT_BF16 = 1 } qc_dtype;
+
+typedef struct {
+    int32_t src_h, src_w;       /* source image (uint8, 3 channels, HWC)             */
+    int32_t new_h, new_w;       /* size after the bilinear resize ("new_unpad")      */
+    int32_t top, left;          /* border added before the resized image             */
+    int32_t dst_h, dst_w;       /* output plane size (new + borders)                 */
+    float gain;                 /* min(H/h0, W/w0) as float32 (scale_boxes)          */
+    int32_t pad_x, pad_y;       /* scale_boxes' pad: round((W-w0*gain)/2-0.1), ...   */
+} qc_pre_plan;
+
+/* Host-side geometry, exactly ultralytics' LetterBox / scale_boxes arithmetic
+ * (Python round() == round-half-even).  mode STRETCH: new = dst = (H,W), no border. */
+int qc_pre_make_plan(int mode, int src_h, int src_w, int H, int W, int stride, qc_pre_plan* plan);
+
+/* src: n images, uint8 HWC (3 ch), row pitch src_row_stride bytes, image pitch
+ * src_img_stride bytes.  lut: device float32 [3][256], lut[c][v] = the normalised value of
+ * byte v in OUTPUT channel c (the caller builds it with the reference's own float32 ops, so
+ * the result is bit-exact; bf16 output = RNE of that float32).  dst: [n,3,dst_h,dst_w]
+ * contiguous, dtype out_dtype.  pad_value: border byte (114).  flags: QC_PRE_SWAP_RB =
+ * output channel c reads source channel 2-c; QC_PRE_LUT_UNIFORM = the caller asserts the three
+ * LUT rows are identical (plain /255), which lets the kernel keep one shared-memory table.  */
+#define QC_PRE_SWAP_RB 1
+#define QC_PRE_LUT_UNIFORM 2
+int qc_preprocess(qc_ctx* ctx, const uint8_t* src, int n, int64_t src_img_stride,
+                  int32_t src_row_stride, const qc_pre_plan* plan, const float* lut,
+                  int pad_value, int flags, int out_dtype, void* dst, void* stream);
+
+/* ---- K2: YOLOv8 DFL decode + confidence filter + class-aware NMS ----------
+ * Replaces ultralytics Detect._inference + ops.non_max_suppression (torchvision.ops.nms on
+ * class-offset boxes) + ops.scale_boxes, all run inside the model call at
+ * models/yolo_model.py:105-110; outputs are what models/yolo_model.py:133-135 reads.
+ */
+#define QC_MAX_LEVELS 4
+typedef struct {
+    int32_t n;                  /* images                                             */
+    int32_t nc;                 /* classes (<= 80)                                     */
+    int32_t reg_max;            /* DFL bins (16)                                       */
+    int32_t num_levels;         /* <= QC_MAX_LEVELS                                    */
+    int32_t level_h[QC_MAX_LEVELS], level_w[QC_MAX_LEVELS];
+    float level_stride[QC_MAX_LEVELS];                 /* 8,16,32                      */
+    int64_t level_batch_stride[QC_MAX_LEVELS];         /* elements between images      */
+    int64_t level_chan_stride[QC_MAX_LEVELS];          /* elements between channels    */
+    int32_t in_dtype;           /* qc_dtype of the head tensors                        */
+    double conf_thres, iou_thres;  /* compared as float32 / double like the reference  */
+    int32_t max_det, max_nms;   /* 300, 30000                                          */
+    float max_wh;               /* 7680 class offset                                   */
+    /* scale_boxes: network input (H,W) -> original (h0,w0) */
+    float gain; int32_t pad_x, pad_y; int32_t orig_h, orig_w;
+    int32_t scale_boxes;        /* 0: leave boxes in network coordinates               */
+} qc_yolo_params;
+
+size_t qc_yolo_workspace_bytes(const qc_yolo_params* p);
+
+/* levels[l]: device pointer to level l, [n, 4*reg_max+nc, h_l, w_l] addressed through
+ * the strides above.  out_det [n][max_det][6] float32 rows (x1,y1,x2,y2,conf,cls) in
+ * descending score order; out_anchor [n][max_det] int32 anchor index of each kept box;
+ * out_count [n] int32 kept boxes; out_ncand [n] int32 candidates that passed conf
+ * (may be NULL).  Rows >= count are zero.                                              */
+int qc_yolo_decode_nms(qc_ctx* ctx, const void* const* levels, const qc_yolo_params* p,
+                       void* workspace, size_t workspace_bytes, float* out_det,
+                       int32_t* out_anchor, int32_t* out_count, int32_t* out_ncand, void* stream);
+
+/* NMS-only entry (the torchvision.ops.nms + [:max_det] step on caller-supplied candidates):
+ * boxes [n][cap][4] xyxy float32 (un-offset), scores [n][cap], cls [n][cap] int32,
+ * counts [n].  out_keep [n][max_det] int32 = candidate indices kept, score-descending
+ * (ties: lower index first); out_count [n].                                             */
+size_t qc_nms_workspace_bytes(int n, int cap);
+int qc_nms(qc_ctx* ctx, const float* boxes, const float* scores, const int32_t* cls,
+           const int32_t* counts, int n, int cap, double iou_thres, float max_wh, int max_det,
+           void* workspace, size_t workspace_bytes, int32_t* out_keep, int32_t* out_count,
+           void* stream);
+
+/* ---- K3: ROI-align crop-resize into classifier inputs ----------------------
+ * Implements the hand-off models/ensemble.py:129-142,181-195 only mocks: each kept box is
+ * cropped/resampled to [3,out_h,out_w] with torchvision.ops.roi_align semantics
+ * (spatial_scale=1) and normalised through the same LUT mechanism as K1.
+ * imgs: n images uint8 HWC; rois: device float32 [K][5] = (img, x1, y1, x2, y2).        */
+int qc_roi_align(qc_ctx* ctx, const uint8_t* imgs, int n, int h, int w, int64_t img_stride,
+                 int32_t row_stride, const float* rois, int K, int out_h, int out_w,
+                 int sampling_ratio, int aligned, int swap_rb, const float* norm,
+                 int out_dtype, void* dst, void* stream);
+/* norm: device float32 [3][3] rows (div, mean, std) per OUTPUT channel:
+ * out = (roi_align_value / div - mean) / std in float32, i.e. /255 then Normalize.
+ * dst: [K,3,out_h,out_w] contiguous.                                                    */
+
+/* ---- K4: Otsu + 3x3 cross morphology + union-find CCL + stats ---------------
+ * Replaces, per region: cv2.cvtColor(RGB2GRAY) inference/segmentation.py:66-69; the Otsu
+ * threshold + polarity compare of :212-234; cv2.morphologyEx CLOSE/OPEN with the 3x3 cross
+ * :284-286 (iters=2 == skimage disk(2), :458-460); cv2.connectedComponents + bincount +
+ * isin of :464-484; and np.sum(mask>0) :98 (sum of kept areas).
+ */
+typedef struct {
+    /* set by the caller */
+    int32_t img;                /* image index                                         */
+    int32_t x, y, w, h;         /* region rectangle inside the image (w,h >= 1)        */
+    int32_t polarity;           /* 1: light defects (v > T) ; 0: dark defects           */
+    int32_t min_area;           /* components with area < min_area are removed          */
+    int32_t max_comp;           /* stats rows reserved for this region (incl. row 0)    */
+    double thr_scale;           /* 1.0: cv2 BINARY / BINARY_INV (v > t | v <= t);
+                                   else the reference's float compare of :226-234,
+                                   v > t*s (light) | v < t*s (dark), s = class factor   */
+    /* filled by qc_segment_plan() -- offsets of this region in outputs / workspace      */
+    int64_t out_offset;         /* first pixel in out_mask / out_labels (pitch = w)     */
+    int32_t stats_offset;       /* first row in out_stats                               */
+    int32_t band_offset, chunk_offset, bits_offset, blk_offset;   /* internal           */
+} qc_seg_region;
+
+typedef struct {
+    /* set by the caller */
+    int32_t n, h, w, channels;  /* image batch: uint8 [n,h,w] gray or [n,h,w,3] RGB      */
+    int64_t img_stride; int32_t row_stride;            /* bytes                         */
+    int32_t morph_iters;        /* 0..4: close then open, `iters` iterations each       */
+    /* filled by qc_segment_plan() */
+    int32_t num_regions;
+    int64_t total_pixels;       /* size of out_mask / out_labels (elements)             */
+    int32_t total_stats_rows;   /* rows of out_stats                                    */
+    int32_t total_bits_words, total_blocks, total_bands, total_chunks;   /* internal    */
+    int32_t max_region_w, max_region_h;
+} qc_seg_params;
+
+/* Host-side: validates the regions against p->{n,h,w} and fills every offset/total above.
+ * The caller then uploads `regions` to the device and sizes outputs/workspace from `p`.  */
+int qc_segment_plan(qc_seg_region* regions, int num_regions, qc_seg_params* p);
+
+size_t qc_segment_workspace_bytes(const qc_seg_params* p);
+
+/* regions: DEVICE array [num_regions] (planned on the host, then uploaded).  out_mask uint8
+ * {0,255} and out_labels int32, both [total_pixels], region r occupying
+ * [out_offset, out_offset + w*h) row-major with pitch w.  Labels follow
+ * cv2.connectedComponents' numbering (8-connectivity, ordered by first 2x2 block); removed
+ * (small) components are zeroed but the numbering is NOT compacted.
+ * out_ncomp [num_regions]: number of labels incl. background (cv2's return value).
+ * out_stats [total_stats_rows][5] int32 rows (x,y,w,h,area) at stats_offset + label
+ * (label >= 1; row 0 of each region is zero); labels >= max_comp are counted but not
+ * recorded (and never removed by min_area).  out_thr [num_regions] int32 Otsu threshold;
+ * out_area [num_regions] int64 kept foreground pixels (== np.sum(mask>0)).
+ * out_mask / out_labels may be NULL to skip those writes.                               */
+int qc_segment(qc_ctx* ctx, const uint8_t* imgs, const qc_seg_params* p,
+               const qc_seg_region* regions, void* workspace, size_t workspace_bytes,
+               uint8_t* out_mask, int32_t* out_labels, int32_t* out_ncomp, int32_t* out_stats,
+               int32_t* out_thr, int64_t* out_area, void* stream);
+
+/* ---- SPC per-batch statistics (payload of the one NCCL all-reduce) ---------
+ * Device-side reduction of K2's outputs into the 9-vector derived from
+ * analytics/sec_analysis.py:105-147: [n_images, sum defects, sum defects^2, sum conf,
+ * n_detections, n_critical, n_major, n_minor, sum bbox area] (float64).  Severity follows
+ * models/yolo_model.py:162-172 on int-truncated boxes.  out9 is overwritten.            */
+int qc_spc_stats(qc_ctx* ctx, const float* det, const int32_t* count, int n, int max_det,
+                 double* out9, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QCGRAFT_H */

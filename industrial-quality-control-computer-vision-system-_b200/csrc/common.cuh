@@ -1,0 +1,90 @@
+// common.cuh -- shared host/device helpers for libqcgraft (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <atomic>
+#include "../../include/qcgraft.h"
+
+struct qc_ctx {
+    int device;
+    int sm_count;
+    int max_smem_optin;
+    std::atomic<long long> launches;
+    char err[512];
+};
+
+#define QC_FAIL(ctx, code, ...)                                   \
+    do {                                                          \
+        if (ctx) snprintf((ctx)->err, sizeof((ctx)->err), __VA_ARGS__); \
+        return (code);                                            \
+    } while (0)
+
+#define QC_CUDA(ctx, expr)                                                              \
+    do {                                                                                \
+        cudaError_t _e = (expr);                                                        \
+        if (_e != cudaSuccess)                                                          \
+            QC_FAIL(ctx, QC_ERR_CUDA, "%s failed: %s (%s:%d)", #expr,                   \
+                    cudaGetErrorString(_e), __FILE__, __LINE__);                        \
+    } while (0)
+
+// every kernel launch goes through this so qc_launch_count() is honest
+#define QC_LAUNCHED(ctx)                                                                \
+    do {                                                                                \
+        (ctx)->launches.fetch_add(1, std::memory_order_relaxed);                        \
+        QC_CUDA(ctx, cudaGetLastError());                                               \
+    } while (0)
+
+static inline size_t qc_align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+#ifdef __CUDACC__
+// ---- mbarrier + 1-D TMA bulk copy (cp.async.bulk -> SASS UBLKCP) ---------------------------
+__device__ __forceinline__ uint32_t qc_smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void qc_mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(qc_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void qc_fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void qc_fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void qc_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(qc_smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void qc_mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(ok)
+            : "r"(qc_smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+// global -> shared bulk copy; bytes % 16 == 0, both addresses 16-B aligned
+__device__ __forceinline__ void qc_bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     qc_smem_u32(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"(qc_smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ uint16_t qc_f2bf(float f) {
+    return __bfloat16_as_ushort(__float2bfloat16_rn(f));
+}
+__device__ __forceinline__ float qc_bf2f(uint16_t b) { return __uint_as_float(((uint32_t)b) << 16); }
+// streaming 128-bit store (outputs are written once, never re-read by this kernel)
+__device__ __forceinline__ void qc_st_cs(void* p, uint4 v) {
+    asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+                 : "memory");
+}
+#endif

@@ -1,0 +1,328 @@
+// k1_preprocess.cu -- K1: uint8 HWC -> (stretch | letterbox) bilinear resize -> constant
+// border -> channel swap -> LUT normalise -> NCHW bf16/f32 pack.
+//
+// Replaces (see include/qcgraft.h): cv2.cvtColor(BGR2RGB) inference/detector.py:233-234,
+// models/yolo_model.py:79-80; cv2.resize inference/detector.py:240-242; ultralytics
+// LetterBox + [...,::-1] + NCHW + float()/255 behind models/yolo_model.py:105-110.
+//
+// Two kernels:
+//   k1_pack_stream : no resize, no border, packed rows (every BASELINE config): the batch
+//                    is a flat byte stream.  Persistent CTAs pull 12 KB chunks into shared
+//                    memory with 1-D TMA bulk copies (cp.async.bulk + mbarrier, double
+//                    buffered), de-interleave the 3-byte pixels from smem with conflict-free
+//                    64-bit reads, normalise through a lane-private (bank == lane) LUT and
+//                    write each plane with fully coalesced 128-bit streaming stores.
+//   k1_generic     : any geometry/alignment.  Exact integer model of cv2's 8-bit INTER_LINEAR
+//                    (11-bit coefficients) + border + LUT.
+// HBM-bound, no tensor cores: algorithmic bytes = h0*w0*3 + 3*H*W*sizeof(out) per image.
+#include "common.cuh"
+#include <math.h>
+
+namespace {
+
+constexpr int K1_THREADS = 256;
+constexpr int K1_CHUNK_PX = 4096;                 // pixels per chunk (12288 B of input)
+constexpr int K1_CHUNK_BYTES = K1_CHUNK_PX * 3;
+constexpr int K1_LUT_WORDS = 256 * 32;            // one lane-private table
+
+template <typename T> struct OutPack;
+template <> struct OutPack<__nv_bfloat16> {
+    static __device__ __forceinline__ uint32_t enc(float f) { return qc_f2bf(f); }
+    // 8 pixels -> one uint4
+    static __device__ __forceinline__ void store8(__nv_bfloat16* p, const uint32_t* v) {
+        uint4 o;
+        o.x = v[0] | (v[1] << 16); o.y = v[2] | (v[3] << 16);
+        o.z = v[4] | (v[5] << 16); o.w = v[6] | (v[7] << 16);
+        qc_st_cs(p, o);
+    }
+};
+template <> struct OutPack<float> {
+    static __device__ __forceinline__ uint32_t enc(float f) { return __float_as_uint(f); }
+    static __device__ __forceinline__ void store8(float* p, const uint32_t* v) {
+        qc_st_cs(p, make_uint4(v[0], v[1], v[2], v[3]));
+        qc_st_cs(p + 4, make_uint4(v[4], v[5], v[6], v[7]));
+    }
+};
+
+// ------------------------------------------------------------------------------------------
+// fast path
+// ------------------------------------------------------------------------------------------
+template <typename OutT, int NT, bool SWAP>
+__global__ void __launch_bounds__(K1_THREADS)
+k1_pack_stream(const uint8_t* __restrict__ src, OutT* __restrict__ dst, const float* __restrict__ lut,
+               long long P, long long src_img_stride, int chunks_per_img, long long total_items) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint32_t* lut_s = reinterpret_cast<uint32_t*>(smem);
+    uint8_t* stage = smem + (size_t)NT * K1_LUT_WORDS * 4;
+    __shared__ __align__(8) uint64_t bar[2];
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    if (tid == 0) {
+        qc_mbar_init(&bar[0], 1);
+        qc_mbar_init(&bar[1], 1);
+        qc_fence_mbar_init();
+    }
+    // lane-private LUT: word (v*32 + lane) -> bank == lane, so 32 random lookups never conflict
+    for (int i = tid; i < NT * K1_LUT_WORDS; i += K1_THREADS) {
+        int c = i / K1_LUT_WORDS, v = (i >> 5) & 255;
+        lut_s[i] = OutPack<OutT>::enc(lut[c * 256 + v]);
+    }
+    __syncthreads();
+
+    auto issue = [&](long long item, int buf) {
+        long long img = item / chunks_per_img;
+        long long chunk = item - img * chunks_per_img;
+        long long px0 = chunk * K1_CHUNK_PX;
+        long long npx = P - px0 < K1_CHUNK_PX ? P - px0 : K1_CHUNK_PX;
+        uint32_t bytes = (uint32_t)(npx * 3);
+        qc_mbar_expect_tx(&bar[buf], bytes);
+        qc_bulk_g2s(stage + buf * K1_CHUNK_BYTES, src + img * src_img_stride + px0 * 3, bytes, &bar[buf]);
+    };
+
+    long long item = blockIdx.x;
+    if (tid == 0 && item < total_items) issue(item, 0);
+
+    for (int it = 0; item < total_items; ++it, item += gridDim.x) {
+        const int buf = it & 1;
+        const long long next = item + gridDim.x;
+        if (tid == 0 && next < total_items) issue(next, buf ^ 1);
+        qc_mbar_wait(&bar[buf], (it >> 1) & 1);
+
+        const long long img = item / chunks_per_img;
+        const long long chunk = item - img * chunks_per_img;
+        const long long px0 = chunk * K1_CHUNK_PX;
+        const int npx = (int)(P - px0 < K1_CHUNK_PX ? P - px0 : K1_CHUNK_PX);
+        const uint8_t* sbuf = stage + buf * K1_CHUNK_BYTES;
+
+#pragma unroll
+        for (int g = 0; g < K1_CHUNK_PX / (8 * K1_THREADS); ++g) {
+            const int p = (g * K1_THREADS + tid) * 8;      // first pixel of this thread's group
+            if (p < npx) {
+                const uint2* s2 = reinterpret_cast<const uint2*>(sbuf + p * 3);
+                uint2 a = s2[0], b = s2[1], c = s2[2];
+                uint32_t w[6] = {a.x, a.y, b.x, b.y, c.x, c.y};
+#pragma unroll
+                for (int oc = 0; oc < 3; ++oc) {
+                    const int sc = SWAP ? 2 - oc : oc;
+                    const uint32_t* tab = lut_s + (NT == 1 ? 0 : oc) * K1_LUT_WORDS + lane;
+                    uint32_t v[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int k = 3 * j + sc;
+                        uint32_t byte = (w[k >> 2] >> (8 * (k & 3))) & 255u;
+                        v[j] = tab[byte << 5];
+                    }
+                    OutT* o = dst + (img * 3 + oc) * P + px0 + p;
+                    OutPack<OutT>::store8(o, v);
+                }
+            }
+        }
+        __syncthreads();   // everyone is done with `buf` before it is refilled two iterations on
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// generic path (exact cv2 INTER_LINEAR integer model)
+// ------------------------------------------------------------------------------------------
+struct LinCoef { int s0, s1, a0, a1; };
+
+__device__ __forceinline__ LinCoef lin_coef(int d, int dst, int src, bool clamp_f) {
+    // cv2::resize: inv_scale = (double)dst/src; scale = 1./inv_scale;
+    // f = (float)((d+0.5)*scale - 0.5); s = cvFloor(f); f -= s; (x only: clamp -> f = 0)
+    const double inv_scale = __ddiv_rn((double)dst, (double)src);
+    const double scale = __ddiv_rn(1.0, inv_scale);
+    float f = (float)__dadd_rn(__dmul_rn((double)d + 0.5, scale), -0.5);
+    int s = (int)floorf(f);
+    f = __fsub_rn(f, (float)s);
+    if (clamp_f) {
+        if (s < 0) { s = 0; f = 0.f; }
+        if (s >= src - 1) { s = src - 1; f = 0.f; }
+    }
+    LinCoef c;
+    c.a1 = __float2int_rn(__fmul_rn(f, 2048.f));
+    c.a0 = __float2int_rn(__fmul_rn(__fsub_rn(1.f, f), 2048.f));
+    c.s0 = min(max(s, 0), src - 1);
+    c.s1 = min(max(s + 1, 0), src - 1);
+    return c;
+}
+
+template <typename OutT>
+__global__ void __launch_bounds__(256)
+k1_generic(const uint8_t* __restrict__ src, OutT* __restrict__ dst, const float* __restrict__ lut,
+           int n, long long src_img_stride, int src_row_stride, qc_pre_plan pl, int pad_value, int swap_rb) {
+    __shared__ uint32_t lut_s[3 * 256];
+    for (int i = threadIdx.x; i < 768; i += blockDim.x) lut_s[i] = OutPack<OutT>::enc(lut[i]);
+    __syncthreads();
+
+    const int groups_per_row = (pl.dst_w + 7) >> 3;
+    const long long total = (long long)n * pl.dst_h * groups_per_row;
+    const bool resize = (pl.new_h != pl.src_h) || (pl.new_w != pl.src_w);
+    const long long plane = (long long)pl.dst_h * pl.dst_w;
+
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (long long)gridDim.x * blockDim.x) {
+        const int gx = (int)(t % groups_per_row);
+        const long long r = t / groups_per_row;
+        const int y = (int)(r % pl.dst_h);
+        const int img = (int)(r / pl.dst_h);
+        const uint8_t* simg = src + (long long)img * src_img_stride;
+        const int ry = y - pl.top;
+        const bool row_in = ry >= 0 && ry < pl.new_h;
+        LinCoef cy = {0, 0, 2048, 0};
+        if (row_in) {
+            if (resize) cy = lin_coef(ry, pl.new_h, pl.src_h, false);
+            else cy.s0 = cy.s1 = ry;
+        }
+        const uint8_t* row0 = simg + (long long)cy.s0 * src_row_stride;
+        const uint8_t* row1 = simg + (long long)cy.s1 * src_row_stride;
+
+        uint32_t vals[3][8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int x = gx * 8 + j;
+            const int rx = x - pl.left;
+            int px[3] = {pad_value, pad_value, pad_value};
+            if (row_in && rx >= 0 && rx < pl.new_w && x < pl.dst_w) {
+                if (resize) {
+                    LinCoef cx = lin_coef(rx, pl.new_w, pl.src_w, true);
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        int r0 = (int)__ldg(row0 + cx.s0 * 3 + c) * cx.a0 + (int)__ldg(row0 + cx.s1 * 3 + c) * cx.a1;
+                        int r1 = (int)__ldg(row1 + cx.s0 * 3 + c) * cx.a0 + (int)__ldg(row1 + cx.s1 * 3 + c) * cx.a1;
+                        px[c] = (((cy.a0 * (r0 >> 4)) >> 16) + ((cy.a1 * (r1 >> 4)) >> 16) + 2) >> 2;
+                    }
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) px[c] = __ldg(row0 + rx * 3 + c);
+                }
+            }
+#pragma unroll
+            for (int oc = 0; oc < 3; ++oc) {
+                const int sc = swap_rb ? 2 - oc : oc;
+                vals[oc][j] = lut_s[oc * 256 + (px[sc] & 255)];
+            }
+        }
+        const int x0 = gx * 8;
+#pragma unroll
+        for (int oc = 0; oc < 3; ++oc) {
+            OutT* o = dst + ((long long)img * 3 + oc) * plane + (long long)y * pl.dst_w + x0;
+            const bool full = (x0 + 8 <= pl.dst_w) && ((reinterpret_cast<uintptr_t>(o) & 15) == 0);
+            if (full) {
+                OutPack<OutT>::store8(o, vals[oc]);
+            } else {
+                for (int j = 0; j < 8 && x0 + j < pl.dst_w; ++j) {
+                    if (sizeof(OutT) == 2) reinterpret_cast<uint16_t*>(o)[j] = (uint16_t)vals[oc][j];
+                    else reinterpret_cast<uint32_t*>(o)[j] = vals[oc][j];
+                }
+            }
+        }
+    }
+}
+
+inline long long py_round(double v) { return (long long)nearbyint(v); }  // round-half-even == Python round()
+
+}  // namespace
+
+extern "C" int qc_pre_make_plan(int mode, int src_h, int src_w, int H, int W, int stride, qc_pre_plan* pl) {
+    if (!pl || src_h <= 0 || src_w <= 0 || H <= 0 || W <= 0) return QC_ERR_INVALID;
+    memset(pl, 0, sizeof(*pl));
+    pl->src_h = src_h; pl->src_w = src_w;
+    if (mode == QC_PRE_STRETCH) {            // inference/detector.py:240-242
+        pl->new_h = pl->dst_h = H; pl->new_w = pl->dst_w = W;
+        pl->gain = 1.f; pl->pad_x = pl->pad_y = 0;
+        return QC_OK;
+    }
+    if (mode != QC_PRE_LETTERBOX && mode != QC_PRE_LETTERBOX_AUTO) return QC_ERR_INVALID;
+    // ultralytics LetterBox (scaleup=True, center=True)
+    double r = fmin((double)H / src_h, (double)W / src_w);
+    int new_w = (int)py_round(src_w * r), new_h = (int)py_round(src_h * r);
+    double dw = W - new_w, dh = H - new_h;
+    if (mode == QC_PRE_LETTERBOX_AUTO) {
+        if (stride <= 0) return QC_ERR_INVALID;
+        dw = (double)(((int)dw % stride + stride) % stride);
+        dh = (double)(((int)dh % stride + stride) % stride);
+    }
+    dw /= 2; dh /= 2;
+    int top = (int)py_round(dh - 0.1), bottom = (int)py_round(dh + 0.1);
+    int left = (int)py_round(dw - 0.1), right = (int)py_round(dw + 0.1);
+    pl->new_h = new_h; pl->new_w = new_w; pl->top = top; pl->left = left;
+    pl->dst_h = new_h + top + bottom; pl->dst_w = new_w + left + right;
+    // ultralytics scale_boxes(img1_shape = network input, img0_shape = original)
+    double gain = fmin((double)pl->dst_h / src_h, (double)pl->dst_w / src_w);
+    pl->gain = (float)gain;
+    pl->pad_x = (int)py_round((pl->dst_w - src_w * gain) / 2 - 0.1);
+    pl->pad_y = (int)py_round((pl->dst_h - src_h * gain) / 2 - 0.1);
+    return QC_OK;
+}
+
+template <typename OutT>
+static int launch_k1(qc_ctx* ctx, const uint8_t* src, int n, int64_t src_img_stride, int32_t src_row_stride,
+                     const qc_pre_plan* pl, const float* lut, bool lut_uniform, int pad_value, int swap_rb,
+                     OutT* dst, cudaStream_t st) {
+    const long long P = (long long)pl->src_h * pl->src_w;
+    const bool identity = pl->new_h == pl->src_h && pl->new_w == pl->src_w && pl->top == 0 && pl->left == 0 &&
+                          pl->dst_h == pl->src_h && pl->dst_w == pl->src_w;
+    const bool packed = src_row_stride == pl->src_w * 3 && (src_img_stride % 16) == 0 &&
+                        (reinterpret_cast<uintptr_t>(src) & 15) == 0 &&
+                        (reinterpret_cast<uintptr_t>(dst) & 15) == 0 && (P % 16) == 0;
+    if (identity && packed && lut_uniform) {
+        const int chunks = (int)((P + K1_CHUNK_PX - 1) / K1_CHUNK_PX);
+        const long long total = (long long)n * chunks;
+        const size_t smem = (size_t)K1_LUT_WORDS * 4 + 2 * K1_CHUNK_BYTES;
+        auto kern = swap_rb ? k1_pack_stream<OutT, 1, true> : k1_pack_stream<OutT, 1, false>;
+        QC_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int occ = 0;
+        QC_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, K1_THREADS, smem));
+        if (occ < 1) occ = 1;
+        long long grid = (long long)ctx->sm_count * occ;
+        if (grid > total) grid = total;
+        kern<<<(unsigned)grid, K1_THREADS, smem, st>>>(src, dst, lut, P, src_img_stride, chunks, total);
+        QC_LAUNCHED(ctx);
+        return QC_OK;
+    }
+    if (identity && packed) {   // per-channel LUT (mean/std normalisation): three lane-private tables
+        const int chunks = (int)((P + K1_CHUNK_PX - 1) / K1_CHUNK_PX);
+        const long long total = (long long)n * chunks;
+        const size_t smem = (size_t)3 * K1_LUT_WORDS * 4 + 2 * K1_CHUNK_BYTES;
+        auto kern = swap_rb ? k1_pack_stream<OutT, 3, true> : k1_pack_stream<OutT, 3, false>;
+        QC_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        long long grid = ctx->sm_count;
+        if (grid > total) grid = total;
+        kern<<<(unsigned)grid, K1_THREADS, smem, st>>>(src, dst, lut, P, src_img_stride, chunks, total);
+        QC_LAUNCHED(ctx);
+        return QC_OK;
+    }
+    const long long items = (long long)n * pl->dst_h * ((pl->dst_w + 7) / 8);
+    long long grid = (items + 255) / 256;
+    const long long cap = (long long)ctx->sm_count * 16;
+    if (grid > cap) grid = cap;
+    if (grid < 1) grid = 1;
+    k1_generic<OutT><<<(unsigned)grid, 256, 0, st>>>(src, dst, lut, n, src_img_stride, src_row_stride, *pl,
+                                                     pad_value, swap_rb);
+    QC_LAUNCHED(ctx);
+    return QC_OK;
+}
+
+extern "C" int qc_preprocess(qc_ctx* ctx, const uint8_t* src, int n, int64_t src_img_stride,
+                             int32_t src_row_stride, const qc_pre_plan* plan, const float* lut, int pad_value,
+                             int flags, int out_dtype, void* dst, void* stream) {
+    if (!ctx) return QC_ERR_INVALID;
+    if (!src || !plan || !lut || !dst || n < 0) QC_FAIL(ctx, QC_ERR_INVALID, "qc_preprocess: null/invalid argument");
+    if (n == 0) return QC_OK;
+    if (plan->src_h <= 0 || plan->src_w <= 0 || plan->dst_h <= 0 || plan->dst_w <= 0 || plan->new_h <= 0 ||
+        plan->new_w <= 0 || plan->top < 0 || plan->left < 0 || plan->top + plan->new_h > plan->dst_h ||
+        plan->left + plan->new_w > plan->dst_w || src_row_stride < plan->src_w * 3)
+        QC_FAIL(ctx, QC_ERR_INVALID, "qc_preprocess: inconsistent plan");
+    if (pad_value < 0 || pad_value > 255) QC_FAIL(ctx, QC_ERR_INVALID, "qc_preprocess: pad_value out of range");
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool lut_uniform = (flags & QC_PRE_LUT_UNIFORM) != 0;
+    const int swap = (flags & QC_PRE_SWAP_RB) ? 1 : 0;
+    if (out_dtype == QC_DT_BF16)
+        return launch_k1<__nv_bfloat16>(ctx, src, n, src_img_stride, src_row_stride, plan, lut, lut_uniform,
+                                        pad_value, swap, (__nv_bfloat16*)dst, st);
+    if (out_dtype == QC_DT_F32)
+        return launch_k1<float>(ctx, src, n, src_img_stride, src_row_stride, plan, lut, lut_uniform, pad_value,
+                                swap, (float*)dst, st);
+    QC_FAIL(ctx, QC_ERR_INVALID, "qc_preprocess: bad out_dtype %d", out_dtype);
+}

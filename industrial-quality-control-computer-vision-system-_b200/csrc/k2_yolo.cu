@@ -1,0 +1,513 @@
+// k2_yolo.cu -- K2: YOLOv8 head post-processing on device.
+//
+// Replaces what runs inside `self.model(img, conf=, iou=)` at models/yolo_model.py:105-110
+// after the conv net (ultralytics, restated in SURVEY.md App. A): Detect._inference (DFL
+// softmax.arange, dist2bbox, *stride, sigmoid), ops.non_max_suppression (conf filter,
+// class max, xywh->xyxy, class offset 7680, torchvision.ops.nms, [:max_det]) and
+// ops.scale_boxes.  Output rows are what models/yolo_model.py:133-135 reads.
+//
+// Three kernels per call:
+//   k2_filter   streams ONLY the nc class planes (5 of 69 channels): per anchor sigmoid, first
+//               max over classes, `score > (float)conf`, warp-ballot aggregated compaction into
+//               a per-image candidate list (key = score-desc | anchor | class).
+//   k2_decode   4 threads per candidate (one per box side): gathers the 16 DFL logits of its
+//               side, softmax, expectation, then the reference's exact float32 op order
+//               anchor-/+dist -> (cx,cy,w,h)*stride -> xy-/+wh/2.
+//   k2_nms      one CTA per image: bitonic sort of (key,slot) by (score desc, anchor asc) ==
+//               torch's stable descending sort; class offset boxes; greedy NMS in 64-box
+//               chunks with a shared-memory 64x64 IoU bitmask resolved by one thread and the
+//               chunk's kept boxes applied to all later boxes by the whole CTA; stops at
+//               max_det; scale_boxes epilogue.  IoU math is torchvision's CPU kernel verbatim
+//               (float32, no FMA, compared against the double threshold).
+// Streaming phase is HBM-bound; sort/NMS phase is latency-bound (reported separately).
+#include "common.cuh"
+#include <math.h>
+#include <algorithm>
+
+namespace {
+
+constexpr int K2_NMS_THREADS = 1024;
+constexpr int K2_SORT_SMEM_MAX = 4096;   // candidates sorted / held in shared memory
+constexpr int K2_REMOVED_MAX = 32768;    // removed[] byte flags in shared memory
+
+struct LevelTable {
+    const void* ptr[QC_MAX_LEVELS];
+    long long batch_stride[QC_MAX_LEVELS];
+    long long chan_stride[QC_MAX_LEVELS];
+    int h[QC_MAX_LEVELS], w[QC_MAX_LEVELS];
+    int start[QC_MAX_LEVELS + 1];   // first anchor of each level
+    float stride[QC_MAX_LEVELS];
+    int num_levels;
+    int A;
+};
+
+__device__ __forceinline__ uint32_t f2ord_desc(float f) {
+    // monotone map float -> uint32 such that larger floats give SMALLER keys
+    uint32_t u = __float_as_uint(f);
+    u ^= (u & 0x80000000u) ? 0xFFFFFFFFu : 0x80000000u;   // ascending order-preserving
+    return ~u;
+}
+__device__ __forceinline__ float ord_desc2f(uint32_t k) {
+    uint32_t u = ~k;
+    u ^= (u & 0x80000000u) ? 0x80000000u : 0xFFFFFFFFu;
+    return __uint_as_float(u);
+}
+
+template <bool BF16>
+__device__ __forceinline__ float load_elem(const void* base, long long idx) {
+    if (BF16) return qc_bf2f(__ldg(reinterpret_cast<const uint16_t*>(base) + idx));
+    return __ldg(reinterpret_cast<const float*>(base) + idx);
+}
+
+__device__ __forceinline__ float sigmoid_f32(float x) {
+    // 1/(1+exp(-x)) in float32 (torch.sigmoid); IEEE division, accurate expf
+    return __fdiv_rn(1.f, __fadd_rn(1.f, expf(-x)));
+}
+
+// ------------------------------------------------------------------------------------------
+template <bool BF16>
+__global__ void __launch_bounds__(256)
+k2_filter(LevelTable lt, int nc, int reg_max, float conf, int cap,
+          unsigned long long* __restrict__ cand_key, int* __restrict__ cand_count) {
+    const int img = blockIdx.y;
+    const int lane = threadIdx.x & 31;
+    for (int a0 = blockIdx.x * blockDim.x; a0 < lt.A; a0 += gridDim.x * blockDim.x) {
+        const int a = a0 + threadIdx.x;
+        bool is_cand = false;
+        float best = 0.f;
+        int best_c = 0;
+        if (a < lt.A) {
+            int l = 0;
+#pragma unroll
+            for (int k = 1; k < QC_MAX_LEVELS; ++k)
+                if (k < lt.num_levels && a >= lt.start[k]) l = k;
+            const long long base = (long long)img * lt.batch_stride[l] + (a - lt.start[l]);
+            const long long cs = lt.chan_stride[l];
+            const void* p = lt.ptr[l];
+            best = -1.f;
+            for (int c = 0; c < nc; ++c) {
+                float s = sigmoid_f32(load_elem<BF16>(p, base + (long long)(4 * reg_max + c) * cs));
+                if (s > best) { best = s; best_c = c; }     // first maximum wins (torch.max)
+            }
+            is_cand = best > conf;                          // float32 compare, like torch
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, is_cand);
+        if (m) {
+            int base_slot = 0;
+            const int leader = __ffs(m) - 1;
+            if (lane == leader) base_slot = atomicAdd(&cand_count[img], __popc(m));
+            base_slot = __shfl_sync(0xffffffffu, base_slot, leader);
+            if (is_cand) {
+                const int slot = base_slot + __popc(m & ((1u << lane) - 1));
+                if (slot < cap)
+                    cand_key[(long long)img * cap + slot] =
+                        ((unsigned long long)f2ord_desc(best) << 32) | ((unsigned long long)a << 8) |
+                        (unsigned long long)best_c;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+template <bool BF16, int RM>   // RM == 16: registers only; RM == 0: runtime reg_max (<= 32)
+__global__ void __launch_bounds__(256)
+k2_decode(LevelTable lt, int reg_max_rt, int cap, const unsigned long long* __restrict__ cand_key,
+          const int* __restrict__ cand_count, float4* __restrict__ cand_box) {
+    const int img = blockIdx.y;
+    int n = cand_count[img];
+    if (n > cap) n = cap;
+    const int side = threadIdx.x & 3;
+    for (int ci = (blockIdx.x * blockDim.x + threadIdx.x) >> 2; ci < ((n + 63) & ~63);
+         ci += (gridDim.x * blockDim.x) >> 2) {
+        const bool valid = ci < n;
+        float dist = 0.f, ax = 0.f, ay = 0.f, stride = 1.f;
+        if (valid) {
+            const unsigned long long key = cand_key[(long long)img * cap + ci];
+            const int a = (int)((key >> 8) & 0xFFFFFFu);
+            int l = 0;
+#pragma unroll
+            for (int k = 1; k < QC_MAX_LEVELS; ++k)
+                if (k < lt.num_levels && a >= lt.start[k]) l = k;
+            const int al = a - lt.start[l];
+            const int y = al / lt.w[l], x = al - y * lt.w[l];
+            ax = (float)x + 0.5f;
+            ay = (float)y + 0.5f;
+            stride = lt.stride[l];
+            const long long base = (long long)img * lt.batch_stride[l] + al;
+            const long long cs = lt.chan_stride[l];
+            const void* p = lt.ptr[l];
+            // softmax over reg_max bins of this side, expectation with arange weights
+            const int reg_max = RM ? RM : reg_max_rt;
+            float v[RM ? RM : 32];
+            float mx = -INFINITY;
+#pragma unroll
+            for (int k = 0; k < (RM ? RM : 32); ++k) {
+                if (k < reg_max) {
+                    v[k] = load_elem<BF16>(p, base + (long long)(side * reg_max + k) * cs);
+                    mx = fmaxf(mx, v[k]);
+                }
+            }
+            float sum = 0.f;
+#pragma unroll
+            for (int k = 0; k < (RM ? RM : 32); ++k) {
+                if (k < reg_max) {
+                    v[k] = expf(__fsub_rn(v[k], mx));
+                    sum = __fadd_rn(sum, v[k]);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < (RM ? RM : 32); ++k)
+                if (k < reg_max) dist = __fadd_rn(dist, __fmul_rn((float)k, __fdiv_rn(v[k], sum)));
+        }
+        // gather the four sides into the side-0 lane of each quad
+        const float d_t = __shfl_down_sync(0xffffffffu, dist, 1);
+        const float d_r = __shfl_down_sync(0xffffffffu, dist, 2);
+        const float d_b = __shfl_down_sync(0xffffffffu, dist, 3);
+        if (valid && side == 0) {
+            // dist2bbox(xywh=True) * stride, then ops.xywh2xyxy -- same float32 op order
+            const float x1 = __fsub_rn(ax, dist), y1 = __fsub_rn(ay, d_t);
+            const float x2 = __fadd_rn(ax, d_r), y2 = __fadd_rn(ay, d_b);
+            const float cx = __fmul_rn(__fdiv_rn(__fadd_rn(x1, x2), 2.f), stride);
+            const float cy = __fmul_rn(__fdiv_rn(__fadd_rn(y1, y2), 2.f), stride);
+            const float w = __fmul_rn(__fsub_rn(x2, x1), stride);
+            const float h = __fmul_rn(__fsub_rn(y2, y1), stride);
+            const float hw = __fdiv_rn(w, 2.f), hh = __fdiv_rn(h, 2.f);
+            cand_box[(long long)img * cap + ci] =
+                make_float4(__fsub_rn(cx, hw), __fsub_rn(cy, hh), __fadd_rn(cx, hw), __fadd_rn(cy, hh));
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// keys for the NMS-only entry point
+__global__ void k2_make_keys(const float* __restrict__ scores, const int* __restrict__ cls,
+                             const int* __restrict__ counts, int cap, unsigned long long* __restrict__ cand_key,
+                             int* __restrict__ cand_count) {
+    const int img = blockIdx.y;
+    int n = counts[img];
+    if (n > cap) n = cap;
+    if (n < 0) n = 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) cand_count[img] = n;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const long long o = (long long)img * cap + i;
+        cand_key[o] = ((unsigned long long)f2ord_desc(scores[o]) << 32) | ((unsigned long long)i << 8) |
+                      (unsigned long long)(cls[o] & 0xFF);
+    }
+}
+
+// torchvision/csrc/ops/cpu/nms_kernel.cpp inner test, verbatim in float32 (no FMA)
+__device__ __forceinline__ bool iou_gt(const float4 a, const float4 b, double thr) {
+    const float iarea = __fmul_rn(__fsub_rn(a.z, a.x), __fsub_rn(a.w, a.y));
+    const float jarea = __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
+    const float xx1 = fmaxf(a.x, b.x), yy1 = fmaxf(a.y, b.y);
+    const float xx2 = fminf(a.z, b.z), yy2 = fminf(a.w, b.w);
+    const float w = fmaxf(0.f, __fsub_rn(xx2, xx1));
+    const float h = fmaxf(0.f, __fsub_rn(yy2, yy1));
+    const float inter = __fmul_rn(w, h);
+    const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(iarea, jarea), inter));
+    return (double)ovr > thr;
+}
+
+struct NmsArgs {
+    int cap, max_det, max_nms;
+    float max_wh;
+    double iou_thres;
+    int scale_boxes;
+    float gain, pad_x, pad_y, orig_w, orig_h;
+    int mode;   // 0: full (write det rows + anchors), 1: nms-only (write kept candidate index)
+};
+
+__device__ void bitonic_sort_pairs(unsigned long long* keys, int* vals, int npow2) {
+    for (int k = 2; k <= npow2; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < npow2; i += blockDim.x) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const unsigned long long a = keys[i], b = keys[ixj];
+                    const bool up = (i & k) == 0;
+                    if ((a > b) == up) {
+                        keys[i] = b; keys[ixj] = a;
+                        const int t = vals[i]; vals[i] = vals[ixj]; vals[ixj] = t;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+__global__ void __launch_bounds__(K2_NMS_THREADS, 1)
+k2_nms(NmsArgs args, const unsigned long long* __restrict__ cand_key, const float4* __restrict__ cand_box,
+       const int* __restrict__ cand_count, unsigned long long* __restrict__ g_keys, int* __restrict__ g_vals,
+       float4* __restrict__ g_sorted, float* __restrict__ out_det, int* __restrict__ out_idx,
+       int* __restrict__ out_count, int* __restrict__ out_ncand) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    __shared__ unsigned long long M[64];
+    __shared__ unsigned long long s_rem, s_keptmask;
+    __shared__ int s_kept_total;
+
+    const int img = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int cap = args.cap;
+    int n = cand_count[img];
+    if (n > cap) n = cap;
+    if (out_ncand && tid == 0) out_ncand[img] = n;
+
+    int npow2 = 1;
+    while (npow2 < n) npow2 <<= 1;
+
+    // carve shared memory: removed flags | kept list | (keys, vals, sorted boxes if they fit)
+    uint8_t* removed = smem_raw;                                                 // K2_REMOVED_MAX
+    int* kept_list = reinterpret_cast<int*>(smem_raw + K2_REMOVED_MAX);          // max_det ints
+    uint8_t* dyn = smem_raw + K2_REMOVED_MAX + (size_t)((args.max_det + 3) & ~3) * 4;
+    dyn = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(dyn) + 15) & ~(uintptr_t)15);
+    const bool in_smem = npow2 <= K2_SORT_SMEM_MAX;
+    float4* sorted = in_smem ? reinterpret_cast<float4*>(dyn) : g_sorted + (long long)img * cap;
+    unsigned long long* keys = in_smem ? reinterpret_cast<unsigned long long*>(dyn + (size_t)K2_SORT_SMEM_MAX * 16)
+                                       : g_keys + (long long)img * 2 * cap;
+    int* vals = in_smem ? reinterpret_cast<int*>(dyn + (size_t)K2_SORT_SMEM_MAX * 24) : g_vals + (long long)img * 2 * cap;
+
+    // ---- sort (score desc, anchor asc) ---------------------------------------------------
+    for (int i = tid; i < npow2; i += blockDim.x) {
+        keys[i] = i < n ? cand_key[(long long)img * cap + i] : ~0ull;
+        vals[i] = i;
+    }
+    __syncthreads();
+    bitonic_sort_pairs(keys, vals, npow2);
+    if (n > args.max_nms) n = args.max_nms;      // top max_nms by score
+    if (n > K2_REMOVED_MAX) n = K2_REMOVED_MAX;  // (rejected on the host; belt and braces)
+
+    // ---- class-offset boxes in sorted order: x[:, :4] + cls * max_wh (float32) ------------
+    for (int i = tid; i < n; i += blockDim.x) {
+        const float4 b = cand_box[(long long)img * cap + vals[i]];
+        const float off = __fmul_rn((float)(int)(keys[i] & 0xFF), args.max_wh);
+        sorted[i] = make_float4(__fadd_rn(b.x, off), __fadd_rn(b.y, off), __fadd_rn(b.z, off), __fadd_rn(b.w, off));
+        removed[i] = 0;
+    }
+    if (tid == 0) s_kept_total = 0;
+    __syncthreads();
+
+    // ---- greedy NMS in chunks of 64 sorted boxes -------------------------------------------
+    const double thr = args.iou_thres;
+    for (int c0 = 0; c0 < n; c0 += 64) {
+        const int m = min(64, n - c0);
+        // 64x64 upper-triangular suppression bitmask of the chunk
+        for (int i = warp; i < 64; i += K2_NMS_THREADS / 32) {
+            bool b0 = false, b1 = false;
+            if (i < m) {
+                const float4 bi = sorted[c0 + i];
+                const int j0 = lane, j1 = lane + 32;
+                if (j0 > i && j0 < m) b0 = iou_gt(bi, sorted[c0 + j0], thr);
+                if (j1 > i && j1 < m) b1 = iou_gt(bi, sorted[c0 + j1], thr);
+            }
+            const unsigned lo = __ballot_sync(0xffffffffu, b0), hi = __ballot_sync(0xffffffffu, b1);
+            if (lane == 0) M[i] = ((unsigned long long)hi << 32) | lo;
+        }
+        if (warp == 0) {
+            const bool r0 = lane < m && removed[c0 + lane];
+            const bool r1 = lane + 32 < m && removed[c0 + lane + 32];
+            const unsigned lo = __ballot_sync(0xffffffffu, r0), hi = __ballot_sync(0xffffffffu, r1);
+            if (lane == 0) s_rem = ((unsigned long long)hi << 32) | lo;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            unsigned long long rem = s_rem, keptmask = 0;
+            int kt = s_kept_total;
+            for (int i = 0; i < m && kt < args.max_det; ++i) {
+                if (!((rem >> i) & 1ull)) {
+                    keptmask |= 1ull << i;
+                    rem |= M[i];
+                    kept_list[kt++] = c0 + i;
+                }
+            }
+            s_keptmask = keptmask;
+            s_kept_total = kt;
+        }
+        __syncthreads();
+        const unsigned long long keptmask = s_keptmask;
+        if (s_kept_total >= args.max_det) break;
+        if (keptmask) {
+            for (int j = c0 + 64 + tid; j < n; j += K2_NMS_THREADS) {
+                if (removed[j]) continue;
+                const float4 bj = sorted[j];
+                unsigned long long km = keptmask;
+                while (km) {
+                    const int i = __ffsll((long long)km) - 1;
+                    km &= km - 1;
+                    if (iou_gt(sorted[c0 + i], bj, thr)) { removed[j] = 1; break; }
+                }
+            }
+        }
+        __syncthreads();
+    }
+    __syncthreads();
+
+    // ---- epilogue: x[keep] (un-offset boxes) -> scale_boxes -> rows -------------------------
+    const int kt = s_kept_total;
+    if (tid == 0) out_count[img] = kt;
+    for (int r = tid; r < args.max_det; r += blockDim.x) {
+        if (args.mode == 1) {
+            out_idx[(long long)img * args.max_det + r] = r < kt ? vals[kept_list[r]] : -1;
+            continue;
+        }
+        float* row = out_det + ((long long)img * args.max_det + r) * 6;
+        if (r < kt) {
+            const int pos = kept_list[r];
+            const unsigned long long key = keys[pos];
+            float4 b = cand_box[(long long)img * cap + vals[pos]];
+            if (args.scale_boxes) {
+                b.x = __fdiv_rn(__fsub_rn(b.x, args.pad_x), args.gain);
+                b.y = __fdiv_rn(__fsub_rn(b.y, args.pad_y), args.gain);
+                b.z = __fdiv_rn(__fsub_rn(b.z, args.pad_x), args.gain);
+                b.w = __fdiv_rn(__fsub_rn(b.w, args.pad_y), args.gain);
+                b.x = fminf(fmaxf(b.x, 0.f), args.orig_w);
+                b.y = fminf(fmaxf(b.y, 0.f), args.orig_h);
+                b.z = fminf(fmaxf(b.z, 0.f), args.orig_w);
+                b.w = fminf(fmaxf(b.w, 0.f), args.orig_h);
+            }
+            row[0] = b.x; row[1] = b.y; row[2] = b.z; row[3] = b.w;
+            row[4] = ord_desc2f((uint32_t)(key >> 32));
+            row[5] = (float)(int)(key & 0xFF);
+            out_idx[(long long)img * args.max_det + r] = (int)((key >> 8) & 0xFFFFFFu);
+        } else {
+            row[0] = row[1] = row[2] = row[3] = row[4] = row[5] = 0.f;
+            out_idx[(long long)img * args.max_det + r] = -1;
+        }
+    }
+}
+
+// workspace layout (all 256-B aligned):
+//   cand_count int[n] | cand_key u64[n*cap] | cand_box float4[n*cap] |
+//   g_keys u64[n*2cap] | g_vals int[n*2cap] | g_sorted float4[n*cap]      (global-sort fallback)
+struct Ws {
+    int* count; unsigned long long* key; float4* box; unsigned long long* gkeys; int* gvals; float4* gsorted;
+    size_t total;
+};
+Ws carve(void* base, int n, int cap) {
+    Ws w;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = qc_align_up(off + bytes, 256); return o; };
+    uint8_t* b = (uint8_t*)base;
+    w.count = (int*)(b + take((size_t)n * 4));
+    w.key = (unsigned long long*)(b + take((size_t)n * cap * 8));
+    w.box = (float4*)(b + take((size_t)n * cap * 16));
+    w.gkeys = (unsigned long long*)(b + take((size_t)n * 2 * cap * 8));
+    w.gvals = (int*)(b + take((size_t)n * 2 * cap * 4));
+    w.gsorted = (float4*)(b + take((size_t)n * cap * 16));
+    w.total = off;
+    return w;
+}
+
+size_t nms_smem_bytes(int max_det) {
+    return (size_t)K2_REMOVED_MAX + (size_t)((max_det + 3) & ~3) * 4 + 16 + (size_t)K2_SORT_SMEM_MAX * (16 + 8 + 4);
+}
+
+int total_anchors(const qc_yolo_params* p) {
+    long long A = 0;
+    for (int l = 0; l < p->num_levels; ++l) A += (long long)p->level_h[l] * p->level_w[l];
+    return (int)A;
+}
+
+int launch_nms(qc_ctx* ctx, const NmsArgs& a, int n, const Ws& w, float* out_det, int* out_idx, int* out_count,
+               int* out_ncand, cudaStream_t st) {
+    const size_t smem = nms_smem_bytes(a.max_det);
+    if ((int)smem > ctx->max_smem_optin) QC_FAIL(ctx, QC_ERR_UNSUPPORTED, "k2_nms: max_det %d needs too much shared memory", a.max_det);
+    QC_CUDA(ctx, cudaFuncSetAttribute(k2_nms, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k2_nms<<<n, K2_NMS_THREADS, smem, st>>>(a, w.key, w.box, w.count, w.gkeys, w.gvals, w.gsorted, out_det, out_idx,
+                                            out_count, out_ncand);
+    QC_LAUNCHED(ctx);
+    return QC_OK;
+}
+
+}  // namespace
+
+extern "C" size_t qc_yolo_workspace_bytes(const qc_yolo_params* p) {
+    if (!p || p->n <= 0 || p->num_levels <= 0 || p->num_levels > QC_MAX_LEVELS) return 0;
+    return carve(nullptr, p->n, total_anchors(p)).total;
+}
+
+extern "C" size_t qc_nms_workspace_bytes(int n, int cap) {
+    if (n <= 0 || cap <= 0) return 0;
+    return carve(nullptr, n, cap).total;
+}
+
+extern "C" int qc_yolo_decode_nms(qc_ctx* ctx, const void* const* levels, const qc_yolo_params* p, void* workspace,
+                                  size_t workspace_bytes, float* out_det, int32_t* out_anchor, int32_t* out_count,
+                                  int32_t* out_ncand, void* stream) {
+    if (!ctx) return QC_ERR_INVALID;
+    if (!levels || !p || !out_det || !out_anchor || !out_count)
+        QC_FAIL(ctx, QC_ERR_INVALID, "qc_yolo_decode_nms: null argument");
+    if (p->n == 0) return QC_OK;
+    if (p->n < 0 || p->num_levels <= 0 || p->num_levels > QC_MAX_LEVELS || p->nc <= 0 || p->nc > 128 ||
+        p->reg_max <= 0 || p->reg_max > 32 || p->max_det <= 0 || p->max_nms <= 0)
+        QC_FAIL(ctx, QC_ERR_INVALID, "qc_yolo_decode_nms: bad params");
+    if (p->max_nms > K2_REMOVED_MAX) QC_FAIL(ctx, QC_ERR_UNSUPPORTED, "max_nms > %d unsupported", K2_REMOVED_MAX);
+    if (p->in_dtype != QC_DT_F32 && p->in_dtype != QC_DT_BF16) QC_FAIL(ctx, QC_ERR_INVALID, "bad in_dtype");
+    LevelTable lt;
+    memset(&lt, 0, sizeof(lt));
+    lt.num_levels = p->num_levels;
+    int A = 0;
+    for (int l = 0; l < p->num_levels; ++l) {
+        if (!levels[l] || p->level_h[l] <= 0 || p->level_w[l] <= 0) QC_FAIL(ctx, QC_ERR_INVALID, "bad level %d", l);
+        lt.ptr[l] = levels[l];
+        lt.batch_stride[l] = p->level_batch_stride[l];
+        lt.chan_stride[l] = p->level_chan_stride[l];
+        lt.h[l] = p->level_h[l]; lt.w[l] = p->level_w[l];
+        lt.stride[l] = p->level_stride[l];
+        lt.start[l] = A;
+        A += p->level_h[l] * p->level_w[l];
+    }
+    for (int l = p->num_levels; l <= QC_MAX_LEVELS; ++l) lt.start[l] = A;
+    lt.A = A;
+    if (A >= (1 << 24)) QC_FAIL(ctx, QC_ERR_UNSUPPORTED, "too many anchors");
+    const int cap = A;
+    Ws w = carve(workspace, p->n, cap);
+    if (!workspace || workspace_bytes < w.total) QC_FAIL(ctx, QC_ERR_WORKSPACE, "workspace %zu < %zu", workspace_bytes, w.total);
+    cudaStream_t st = (cudaStream_t)stream;
+    QC_CUDA(ctx, cudaMemsetAsync(w.count, 0, (size_t)p->n * 4, st));
+
+    const float conf = (float)p->conf_thres;
+    dim3 gf((unsigned)std::min((A + 255) / 256, 64), (unsigned)p->n);
+    if (p->in_dtype == QC_DT_BF16) k2_filter<true><<<gf, 256, 0, st>>>(lt, p->nc, p->reg_max, conf, cap, w.key, w.count);
+    else k2_filter<false><<<gf, 256, 0, st>>>(lt, p->nc, p->reg_max, conf, cap, w.key, w.count);
+    QC_LAUNCHED(ctx);
+
+    dim3 gd(8, (unsigned)p->n);
+    const bool bf = p->in_dtype == QC_DT_BF16;
+    if (p->reg_max == 16) {
+        if (bf) k2_decode<true, 16><<<gd, 256, 0, st>>>(lt, 16, cap, w.key, w.count, w.box);
+        else k2_decode<false, 16><<<gd, 256, 0, st>>>(lt, 16, cap, w.key, w.count, w.box);
+    } else {
+        if (bf) k2_decode<true, 0><<<gd, 256, 0, st>>>(lt, p->reg_max, cap, w.key, w.count, w.box);
+        else k2_decode<false, 0><<<gd, 256, 0, st>>>(lt, p->reg_max, cap, w.key, w.count, w.box);
+    }
+    QC_LAUNCHED(ctx);
+
+    NmsArgs a;
+    a.cap = cap; a.max_det = p->max_det; a.max_nms = p->max_nms; a.max_wh = p->max_wh; a.iou_thres = p->iou_thres;
+    a.scale_boxes = p->scale_boxes; a.gain = p->gain; a.pad_x = (float)p->pad_x; a.pad_y = (float)p->pad_y;
+    a.orig_w = (float)p->orig_w; a.orig_h = (float)p->orig_h; a.mode = 0;
+    return launch_nms(ctx, a, p->n, w, out_det, out_anchor, out_count, out_ncand, st);
+}
+
+extern "C" int qc_nms(qc_ctx* ctx, const float* boxes, const float* scores, const int32_t* cls, const int32_t* counts,
+                      int n, int cap, double iou_thres, float max_wh, int max_det, void* workspace,
+                      size_t workspace_bytes, int32_t* out_keep, int32_t* out_count, void* stream) {
+    if (!ctx) return QC_ERR_INVALID;
+    if (!boxes || !scores || !cls || !counts || !out_keep || !out_count || cap <= 0 || max_det <= 0 || n < 0)
+        QC_FAIL(ctx, QC_ERR_INVALID, "qc_nms: bad argument");
+    if (n == 0) return QC_OK;
+    if (cap > K2_REMOVED_MAX) QC_FAIL(ctx, QC_ERR_UNSUPPORTED, "qc_nms: cap > %d unsupported", K2_REMOVED_MAX);
+    if (reinterpret_cast<uintptr_t>(boxes) & 15) QC_FAIL(ctx, QC_ERR_INVALID, "qc_nms: boxes must be 16-byte aligned");
+    Ws w = carve(workspace, n, cap);
+    if (!workspace || workspace_bytes < w.total) QC_FAIL(ctx, QC_ERR_WORKSPACE, "workspace %zu < %zu", workspace_bytes, w.total);
+    cudaStream_t st = (cudaStream_t)stream;
+    dim3 g((unsigned)std::min((cap + 255) / 256, 32), (unsigned)n);
+    k2_make_keys<<<g, 256, 0, st>>>(scores, cls, counts, cap, w.key, w.count);
+    QC_LAUNCHED(ctx);
+    w.box = const_cast<float4*>(reinterpret_cast<const float4*>(boxes));
+    NmsArgs a;
+    a.cap = cap; a.max_det = max_det; a.max_nms = cap; a.max_wh = max_wh; a.iou_thres = iou_thres;
+    a.scale_boxes = 0; a.gain = 1.f; a.pad_x = a.pad_y = 0.f; a.orig_w = a.orig_h = 0.f; a.mode = 1;
+    return launch_nms(ctx, a, n, w, nullptr, out_keep, out_count, nullptr, st);
+}

@@ -1,0 +1,724 @@
+// k4_segment.cu -- K4: defect masking on device.
+//
+// Per region (full frame or detection ROI), replaces the reference's
+//   cv2.cvtColor(RGB2GRAY)                         inference/segmentation.py:66-69
+//   Otsu threshold + polarity compare              :212-234 (u8 Otsu == cv2.threshold OTSU)
+//   cv2.morphologyEx CLOSE, OPEN with 3x3 cross    :284-286 (iters=2 == skimage disk(2), :458-460)
+//   cv2.connectedComponents + bincount + isin      :464-484
+//   np.sum(mask > 0)                               :98
+// Output labels carry cv2.connectedComponents' numbering (8-connectivity; components ordered by
+// their first 2x2 block in block-raster order), which is exactly "rank of the minimum block
+// index of the component" -- so the union-find works on 2x2 blocks with min-index roots and a
+// raster-order prefix sum over root flags gives the label.
+//
+// Pipeline (all HBM/L2-bound integer work, no tensor cores):
+//   k4_init      zero histograms / area, sentinel-initialise stats rows
+//   k4_hist      [RGB->gray] + 256-bin histogram, lane-private shared-memory counters
+//   k4_otsu      cv2's getThreshVal_Otsu_8u recurrence in float64 (sequential, one thread/region)
+//   k4_mask      threshold -> bit-packed rows in smem -> close/open (4*iters cross steps with
+//                halo) -> global bit rows + union-find parent init (horizontal runs pre-linked)
+//   k4_merge     block-based union-find (atomicMin, roots = min block index) over L2
+//   k4_compress  path compression + per-1024-block root counts
+//   k4_scan      exclusive scan of the counts per region -> chunk bases, ncomp
+//   k4_rank      root -> label (1-based rank in block-raster order)
+//   k4_stats     parent -> label in place; per-label area / bbox via run-aggregated atomics
+//   k4_final     int32 labels + u8 mask (min-area filter applied), kept area, bbox -> (x,y,w,h)
+// Algorithmic bytes per region: w*h (gray read) + w*h (mask) + 4*w*h (labels) + 20*ncomp.
+#include "common.cuh"
+#include <math.h>
+#include <float.h>
+#include <limits.h>
+#include <algorithm>
+
+namespace {
+
+constexpr int K4_THREADS = 256;
+constexpr int K4_BAND_ROWS = 32;     // pixel rows per band (16 block rows)
+constexpr int K4_CHUNK = 1024;       // blocks per ranking chunk
+
+struct SegWs {
+    unsigned* hist;       // [R][256]
+    int* cmp;             // [R][2]  inclusive foreground interval [lo, hi]
+    uint8_t* gray;        // [total_pixels] (RGB input only)
+    unsigned* bits;       // [total_bits_words]
+    int* parent;          // [total_blocks]   union-find parent, later the label
+    int* rank;            // [total_blocks]   label of root blocks
+    int* chunk_count;     // [total_chunks]
+    int* chunk_base;      // [total_chunks]
+    size_t total;
+};
+
+SegWs carve(void* base, const qc_seg_params* p) {
+    SegWs w;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = qc_align_up(off + bytes, 256); return o; };
+    uint8_t* b = (uint8_t*)base;
+    const size_t R = (size_t)p->num_regions;
+    w.hist = (unsigned*)(b + take(R * 256 * 4));
+    w.cmp = (int*)(b + take(R * 2 * 4));
+    w.gray = (uint8_t*)(b + take(p->channels == 3 ? (size_t)p->total_pixels : 0));
+    w.bits = (unsigned*)(b + take((size_t)p->total_bits_words * 4));
+    w.parent = (int*)(b + take((size_t)p->total_blocks * 4));
+    w.rank = (int*)(b + take((size_t)p->total_blocks * 4));
+    w.chunk_count = (int*)(b + take((size_t)p->total_chunks * 4));
+    w.chunk_base = (int*)(b + take((size_t)p->total_chunks * 4));
+    w.total = off;
+    return w;
+}
+
+struct Img {
+    const uint8_t* data;
+    long long img_stride;
+    int row_stride, channels;
+};
+
+// region of work item t (band or chunk index): largest r with off(r) <= t
+template <typename F>
+__device__ __forceinline__ int find_region(int t, int R, F off) {
+    int lo = 0, hi = R - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (off(mid) <= t) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+__device__ __forceinline__ int wpr_of(const qc_seg_region& r) { return (r.w + 31) >> 5; }
+__device__ __forceinline__ int bw_of(const qc_seg_region& r) { return (r.w + 1) >> 1; }
+__device__ __forceinline__ int bh_of(const qc_seg_region& r) { return (r.h + 1) >> 1; }
+
+// gray value source for region row `y` (region-local), column x
+struct GraySrc {
+    const uint8_t* p;   // first pixel of the region row
+    int step;           // 1 (gray / workspace gray)
+};
+
+// ------------------------------------------------------------------------------------------
+__global__ void k4_init(const qc_seg_region* __restrict__ regs, int R, unsigned* __restrict__ hist,
+                        int* __restrict__ stats, long long* __restrict__ out_area, int total_stats_rows) {
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
+    for (int i = gid; i < R * 256; i += gsz) hist[i] = 0;
+    for (int i = gid; i < R; i += gsz) out_area[i] = 0;
+    for (int i = gid; i < total_stats_rows; i += gsz) {
+        int* s = stats + (long long)i * 5;
+        s[0] = INT_MAX; s[1] = INT_MAX; s[2] = -1; s[3] = -1; s[4] = 0;   // minx, miny, maxx, maxy, area
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(K4_THREADS)
+k4_hist(Img im, const qc_seg_region* __restrict__ regs, int R, int total_bands, unsigned* __restrict__ hist,
+        uint8_t* __restrict__ gray_ws) {
+    __shared__ unsigned sh[256 * 32];   // [bin][lane] -> bank == lane: no intra-warp conflicts
+    __shared__ int s_r;
+    const int tid = threadIdx.x, lane = tid & 31;
+    for (int t = blockIdx.x; t < total_bands; t += gridDim.x) {
+        if (tid == 0) s_r = find_region(t, R, [&](int i) { return regs[i].band_offset; });
+        for (int i = tid; i < 256 * 32; i += K4_THREADS) sh[i] = 0;
+        __syncthreads();
+        const qc_seg_region rg = regs[s_r];
+        const int y0 = (t - rg.band_offset) * K4_BAND_ROWS;
+        const int y1 = min(y0 + K4_BAND_ROWS, rg.h);
+        const uint8_t* ibase = im.data + (long long)rg.img * im.img_stride;
+        const int npx = (y1 - y0) * rg.w;
+        for (int i = tid; i < npx; i += K4_THREADS) {
+            const int yy = i / rg.w, xx = i - yy * rg.w;
+            const uint8_t* p = ibase + (long long)(rg.y + y0 + yy) * im.row_stride + (long long)(rg.x + xx) * im.channels;
+            unsigned g;
+            if (im.channels == 3) {
+                // cv2 RGB2GRAY fixed point: (R*9798 + G*19235 + B*3735 + 2^14) >> 15
+                g = (9798u * __ldg(p) + 19235u * __ldg(p + 1) + 3735u * __ldg(p + 2) + 16384u) >> 15;
+                gray_ws[rg.out_offset + (long long)(y0 + yy) * rg.w + xx] = (uint8_t)g;
+            } else {
+                g = __ldg(p);
+            }
+            atomicAdd(&sh[(g << 5) + lane], 1u);
+        }
+        __syncthreads();
+        // reduce the 32 lane columns of each bin, one global atomic per non-empty bin
+        {
+            unsigned s = 0;
+            const int bin = tid;    // K4_THREADS == 256
+#pragma unroll 8
+            for (int k = 0; k < 32; ++k) s += sh[(bin << 5) + ((k + lane) & 31)];
+            if (s) atomicAdd(&hist[(long long)s_r * 256 + bin], s);
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+__global__ void k4_otsu(const qc_seg_region* __restrict__ regs, int R, const unsigned* __restrict__ hist,
+                        int* __restrict__ cmp, int* __restrict__ out_thr) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    const qc_seg_region rg = regs[r];
+    const unsigned* h = hist + (long long)r * 256;
+    // cv2 getThreshVal_Otsu_8u, float64, same operation order (no FMA contraction)
+    const double scale = __ddiv_rn(1.0, (double)((long long)rg.w * rg.h));
+    double mu = 0.0;
+    for (int i = 0; i < 256; ++i) mu = __dadd_rn(mu, __dmul_rn((double)i, (double)h[i]));
+    mu = __dmul_rn(mu, scale);
+    double mu1 = 0.0, q1 = 0.0, max_sigma = 0.0;
+    int max_val = 0;
+    for (int i = 0; i < 256; ++i) {
+        const double p_i = __dmul_rn((double)h[i], scale);
+        mu1 = __dmul_rn(mu1, q1);
+        q1 = __dadd_rn(q1, p_i);
+        const double q2 = __dsub_rn(1.0, q1);
+        if (fmin(q1, q2) < (double)FLT_EPSILON || fmax(q1, q2) > 1.0 - (double)FLT_EPSILON) continue;
+        mu1 = __ddiv_rn(__dadd_rn(mu1, __dmul_rn((double)i, p_i)), q1);
+        const double mu2 = __ddiv_rn(__dsub_rn(mu, __dmul_rn(q1, mu1)), q2);
+        const double d = __dsub_rn(mu1, mu2);
+        const double sigma = __dmul_rn(__dmul_rn(__dmul_rn(q1, q2), d), d);
+        if (sigma > max_sigma) { max_sigma = sigma; max_val = i; }
+    }
+    out_thr[r] = max_val;
+    int lo, hi;
+    if (rg.thr_scale == 1.0) {
+        if (rg.polarity) { lo = max_val + 1; hi = 255; }      // cv2 THRESH_BINARY: v > t
+        else { lo = 0; hi = max_val; }                        // THRESH_BINARY_INV: v <= t
+    } else {
+        const double T = __dmul_rn((double)max_val, rg.thr_scale);   // python: threshold * factor
+        if (rg.polarity) { lo = (int)floor(T) + 1; hi = 255; }       // v > T
+        else { lo = 0; hi = (int)ceil(T) - 1; }                      // v < T
+    }
+    cmp[2 * r] = lo;
+    cmp[2 * r + 1] = hi;
+}
+
+// ------------------------------------------------------------------------------------------
+// bit-row helpers for the morphology: rows live in smem as [rows][wpr] words, bits >= w are 0.
+struct BitRows {
+    const unsigned* buf;
+    int wpr, w;
+    int row_lo, row_hi;     // region rows held in buf: [row_lo, row_hi)
+    int h;                  // region height
+    // word of region row y (border: rows/words outside the REGION read as `ob`; rows outside the
+    // buffer but inside the region are halo garbage and read as `ob` too -- they never reach the
+    // band's own rows because the halo is 4*iters deep)
+    __device__ __forceinline__ unsigned rd(int y, int wx, bool ob) const {
+        if (y < row_lo || y >= row_hi || wx < 0 || wx >= wpr) return ob ? 0xFFFFFFFFu : 0u;
+        unsigned v = buf[(y - row_lo) * wpr + wx];
+        if (ob && wx == wpr - 1 && (w & 31)) v |= ~((1u << (w & 31)) - 1u);
+        return v;
+    }
+};
+
+__global__ void __launch_bounds__(K4_THREADS)
+k4_mask(Img im, const qc_seg_region* __restrict__ regs, int R, int total_bands, int iters,
+        const int* __restrict__ cmp, const uint8_t* __restrict__ gray_ws, unsigned* __restrict__ bits,
+        int* __restrict__ parent, int buf_words) {
+    extern __shared__ unsigned sm[];
+    unsigned* bufA = sm;
+    unsigned* bufB = sm + buf_words;
+    __shared__ int s_r;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int halo = 4 * iters;
+    for (int t = blockIdx.x; t < total_bands; t += gridDim.x) {
+        __syncthreads();
+        if (tid == 0) s_r = find_region(t, R, [&](int i) { return regs[i].band_offset; });
+        __syncthreads();
+        const int r = s_r;
+        const qc_seg_region rg = regs[r];
+        const int wpr = wpr_of(rg);
+        const int y0 = (t - rg.band_offset) * K4_BAND_ROWS;
+        const int y1 = min(y0 + K4_BAND_ROWS, rg.h);
+        const int row_lo = max(y0 - halo, 0), row_hi = min(y1 + halo, rg.h);
+        const int nrows = row_hi - row_lo;
+        const int lo = cmp[2 * r], hi = cmp[2 * r + 1];
+        // ---- threshold into bit rows (warp per word: 32 pixels, one ballot) ------------------
+        const uint8_t* gbase;
+        long long gpitch;
+        if (im.channels == 3) { gbase = gray_ws + rg.out_offset; gpitch = rg.w; }
+        else { gbase = im.data + (long long)rg.img * im.img_stride + (long long)rg.y * im.row_stride + rg.x; gpitch = im.row_stride; }
+        for (int wi = warp; wi < nrows * wpr; wi += K4_THREADS / 32) {
+            const int yy = wi / wpr, wx = wi - yy * wpr;
+            const int x = wx * 32 + lane;
+            bool fg = false;
+            if (x < rg.w) {
+                const int v = im.channels == 3 ? (int)gbase[(long long)(row_lo + yy) * gpitch + x]
+                                               : (int)__ldg(gbase + (long long)(row_lo + yy) * gpitch + x);
+                fg = v >= lo && v <= hi;
+            }
+            const unsigned word = __ballot_sync(0xffffffffu, fg);
+            if (lane == 0) bufA[wi] = word;
+        }
+        __syncthreads();
+        // ---- close (dilate^k, erode^k) then open (erode^k, dilate^k), 3x3 cross ----------------
+        unsigned* src = bufA;
+        unsigned* dst = bufB;
+        for (int step = 0; step < 4 * iters; ++step) {
+            const int phase = step / iters;              // 0: dilate, 1: erode, 2: erode, 3: dilate
+            const bool erode = (phase == 1 || phase == 2);
+            BitRows br{src, wpr, rg.w, row_lo, row_hi, rg.h};
+            for (int wi = tid; wi < nrows * wpr; wi += K4_THREADS) {
+                const int yy = wi / wpr, wx = wi - yy * wpr;
+                const int y = row_lo + yy;
+                const unsigned c = br.rd(y, wx, erode);
+                const unsigned l = br.rd(y, wx - 1, erode), rr = br.rd(y, wx + 1, erode);
+                // region-border rows read as the op's border value; buffer-edge rows inside the
+                // region read the same (halo garbage, discarded)
+                const unsigned up = br.rd(y - 1, wx, erode), dn = br.rd(y + 1, wx, erode);
+                const unsigned xl = (c << 1) | (l >> 31);      // pixel x-1 aligned to x
+                const unsigned xr = (c >> 1) | (rr << 31);     // pixel x+1 aligned to x
+                unsigned o = erode ? (c & xl & xr & up & dn) : (c | xl | xr | up | dn);
+                if (wx == wpr - 1 && (rg.w & 31)) o &= (1u << (rg.w & 31)) - 1u;
+                dst[wi] = o;
+            }
+            __syncthreads();
+            unsigned* tmp = src; src = dst; dst = tmp;
+        }
+        // ---- emit the band's own rows + union-find parent init ---------------------------------
+        const int bw = bw_of(rg);
+        for (int wi = tid; wi < (y1 - y0) * wpr; wi += K4_THREADS) {
+            const int yy = wi / wpr, wx = wi - yy * wpr;
+            bits[rg.bits_offset + (long long)(y0 + yy) * wpr + wx] = src[(y0 - row_lo + yy) * wpr + wx];
+        }
+        const int by0 = y0 >> 1, by1 = (y1 + 1) >> 1;
+        for (int ci = tid; ci < (by1 - by0) * wpr; ci += K4_THREADS) {
+            const int byy = ci / wpr, wx = ci - byy * wpr;
+            const int by = by0 + byy;
+            const int ry = 2 * by - row_lo;
+            const unsigned r0 = src[ry * wpr + wx];
+            const unsigned r1 = (2 * by + 1 < rg.h) ? src[(ry + 1) * wpr + wx] : 0u;
+            const unsigned v = r0 | r1;
+            int* prow = parent + rg.blk_offset + (long long)by * bw + wx * 16;
+            int head = 0;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                if (wx * 16 + k < bw) {
+                    const unsigned bits2 = (v >> (2 * k)) & 3u;
+                    int val = -1;
+                    if (bits2) {
+                        // linked to the previous block of this word when column 2k and column 2k-1 both hold a pixel
+                        const bool link = k > 0 && ((v >> (2 * k)) & 1u) && ((v >> (2 * k - 1)) & 1u);
+                        if (!link) head = rg.blk_offset + by * bw + wx * 16 + k;
+                        val = head;
+                    }
+                    prow[k] = val;
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int uf_find(int* L, int x) {
+    int p = __ldcg(L + x);
+    while (p != x) { x = p; p = __ldcg(L + x); }
+    return x;
+}
+__device__ __forceinline__ void uf_union(int* L, int a, int b) {
+    bool done;
+    do {
+        a = uf_find(L, a);
+        b = uf_find(L, b);
+        if (a < b) { const int old = atomicMin(L + b, a); done = (old == b); b = old; }
+        else if (b < a) { const int old = atomicMin(L + a, b); done = (old == a); a = old; }
+        else done = true;
+    } while (!done);
+}
+
+__global__ void __launch_bounds__(K4_THREADS)
+k4_merge(const qc_seg_region* __restrict__ regs, int R, int total_bands, const unsigned* __restrict__ bits,
+         int* __restrict__ parent) {
+    __shared__ int s_r;
+    const int tid = threadIdx.x;
+    for (int t = blockIdx.x; t < total_bands; t += gridDim.x) {
+        __syncthreads();
+        if (tid == 0) s_r = find_region(t, R, [&](int i) { return regs[i].band_offset; });
+        __syncthreads();
+        const qc_seg_region rg = regs[s_r];
+        const int wpr = wpr_of(rg), bw = bw_of(rg);
+        const int y0 = (t - rg.band_offset) * K4_BAND_ROWS;
+        const int y1 = min(y0 + K4_BAND_ROWS, rg.h);
+        const int by0 = y0 >> 1, by1 = (y1 + 1) >> 1;
+        const unsigned* B = bits + rg.bits_offset;
+        auto word = [&](int y, int wx) -> unsigned {
+            return (y < 0 || y >= rg.h || wx < 0 || wx >= wpr) ? 0u : __ldg(B + (long long)y * wpr + wx);
+        };
+        for (int ci = tid; ci < (by1 - by0) * wpr; ci += K4_THREADS) {
+            const int byy = ci / wpr, wx = ci - byy * wpr;
+            const int by = by0 + byy;
+            const unsigned r0 = word(2 * by, wx), r1 = word(2 * by + 1, wx);
+            const unsigned v = r0 | r1;
+            if (!v) continue;
+            const unsigned u = word(2 * by - 1, wx);
+            // neighbours across the word boundary
+            const unsigned vl = (word(2 * by, wx - 1) | word(2 * by + 1, wx - 1)) >> 31;   // column x0-1 of this block row
+            const unsigned ul = word(2 * by - 1, wx - 1) >> 31;                             // pixel (2by-1, x0-1)
+            const unsigned ur = word(2 * by - 1, wx + 1) & 1u;                              // pixel (2by-1, x0+32)
+            const int base = rg.blk_offset + by * bw + wx * 16;
+            const int upbase = base - bw;
+#pragma unroll 4
+            for (int k = 0; k < 16; ++k) {
+                const unsigned a = (r0 >> (2 * k)) & 1u, b = (r0 >> (2 * k + 1)) & 1u;
+                if (!((v >> (2 * k)) & 3u)) continue;
+                const int me = base + k;
+                // left neighbour: only across the word boundary (in-word runs were pre-linked)
+                if (k == 0 && wx > 0 && (v & 1u) && vl) uf_union(parent, me, me - 1);
+                if (by > 0) {
+                    const unsigned u0 = (u >> (2 * k)) & 1u, u1 = (u >> (2 * k + 1)) & 1u;
+                    if ((a | b) && (u0 | u1)) uf_union(parent, me, upbase + k);
+                    const unsigned um = k > 0 ? (u >> (2 * k - 1)) & 1u : ul;            // pixel (2by-1, 2bx-1)
+                    if (a && um && (wx > 0 || k > 0)) uf_union(parent, me, upbase + k - 1);
+                    const unsigned up2 = k < 15 ? (u >> (2 * k + 2)) & 1u : ur;           // pixel (2by-1, 2bx+2)
+                    if (b && up2 && (wx * 16 + k + 1 < bw)) uf_union(parent, me, upbase + k + 1);
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// chunk = 1024 consecutive blocks (block-raster order) of one region
+__device__ __forceinline__ void chunk_span(const qc_seg_region* regs, int R, int c, int& r, int& b0, int& b1) {
+    r = find_region(c, R, [&](int i) { return regs[i].chunk_offset; });
+    const int nb = bw_of(regs[r]) * bh_of(regs[r]);
+    b0 = (c - regs[r].chunk_offset) * K4_CHUNK;
+    b1 = min(b0 + K4_CHUNK, nb);
+}
+
+__global__ void __launch_bounds__(K4_CHUNK)
+k4_compress(const qc_seg_region* __restrict__ regs, int R, int total_chunks, int* __restrict__ parent,
+            int* __restrict__ chunk_count) {
+    __shared__ int s_cnt[K4_CHUNK / 32];
+    __shared__ int s_r, s_b0, s_b1;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int c = blockIdx.x; c < total_chunks; c += gridDim.x) {
+        __syncthreads();
+        if (tid == 0) { int r, b0, b1; chunk_span(regs, R, c, r, b0, b1); s_r = r; s_b0 = b0; s_b1 = b1; }
+        __syncthreads();
+        const int base = regs[s_r].blk_offset;
+        const int b = s_b0 + tid;
+        bool root = false;
+        if (b < s_b1) {
+            const int g = base + b;
+            if (__ldcg(parent + g) >= 0) {
+                const int rt = uf_find(parent, g);
+                parent[g] = rt;
+                root = (rt == g);
+            }
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, root);
+        if (lane == 0) s_cnt[warp] = __popc(m);
+        __syncthreads();
+        if (warp == 0) {
+            int v = s_cnt[lane];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) chunk_count[c] = v;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(1024)
+k4_scan(const qc_seg_region* __restrict__ regs, int R, const int* __restrict__ chunk_count,
+        int* __restrict__ chunk_base, int* __restrict__ out_ncomp) {
+    __shared__ int s_w[32];
+    __shared__ int s_carry;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int r = blockIdx.x; r < R; r += gridDim.x) {
+        const int c0 = regs[r].chunk_offset;
+        const int nb = bw_of(regs[r]) * bh_of(regs[r]);
+        const int nc = (nb + K4_CHUNK - 1) / K4_CHUNK;
+        __syncthreads();
+        if (tid == 0) s_carry = 0;
+        __syncthreads();
+        for (int i0 = 0; i0 < nc; i0 += 1024) {
+            const int i = i0 + tid;
+            const int v = i < nc ? chunk_count[c0 + i] : 0;
+            int x = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+            if (lane == 31) s_w[warp] = x;
+            __syncthreads();
+            if (warp == 0) {
+                int w = s_w[lane];
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += y; }
+                s_w[lane] = w;
+            }
+            __syncthreads();
+            const int incl = x + (warp ? s_w[warp - 1] : 0);
+            const int carry = s_carry;
+            if (i < nc) chunk_base[c0 + i] = carry + incl - v;
+            __syncthreads();
+            if (tid == 1023) s_carry = carry + incl;
+            __syncthreads();
+        }
+        if (tid == 0) out_ncomp[r] = s_carry + 1;     // labels incl. background, like cv2
+    }
+}
+
+__global__ void __launch_bounds__(K4_CHUNK)
+k4_rank(const qc_seg_region* __restrict__ regs, int R, int total_chunks, const int* __restrict__ parent,
+        const int* __restrict__ chunk_base, int* __restrict__ rank) {
+    __shared__ int s_cnt[K4_CHUNK / 32];
+    __shared__ int s_r, s_b0, s_b1;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int c = blockIdx.x; c < total_chunks; c += gridDim.x) {
+        __syncthreads();
+        if (tid == 0) { int r, b0, b1; chunk_span(regs, R, c, r, b0, b1); s_r = r; s_b0 = b0; s_b1 = b1; }
+        __syncthreads();
+        const int base = regs[s_r].blk_offset;
+        const int b = s_b0 + tid;
+        bool root = false;
+        if (b < s_b1) root = (parent[base + b] == base + b);
+        const unsigned m = __ballot_sync(0xffffffffu, root);
+        if (lane == 0) s_cnt[warp] = __popc(m);
+        __syncthreads();
+        if (warp == 0) {
+            int v = s_cnt[lane], x = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+            s_cnt[lane] = x - v;    // exclusive
+        }
+        __syncthreads();
+        if (root) rank[base + b] = chunk_base[c] + s_cnt[warp] + __popc(m & ((1u << lane) - 1u)) + 1;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(K4_THREADS)
+k4_stats(const qc_seg_region* __restrict__ regs, int R, int total_bands, const unsigned* __restrict__ bits,
+         int* __restrict__ parent, const int* __restrict__ rank, int* __restrict__ stats) {
+    __shared__ int s_r;
+    const int tid = threadIdx.x;
+    for (int t = blockIdx.x; t < total_bands; t += gridDim.x) {
+        __syncthreads();
+        if (tid == 0) s_r = find_region(t, R, [&](int i) { return regs[i].band_offset; });
+        __syncthreads();
+        const qc_seg_region rg = regs[s_r];
+        const int wpr = wpr_of(rg), bw = bw_of(rg);
+        const int y0 = (t - rg.band_offset) * K4_BAND_ROWS;
+        const int y1 = min(y0 + K4_BAND_ROWS, rg.h);
+        const int by0 = y0 >> 1, by1 = (y1 + 1) >> 1;
+        const unsigned* B = bits + rg.bits_offset;
+        for (int ci = tid; ci < (by1 - by0) * wpr; ci += K4_THREADS) {
+            const int byy = ci / wpr, wx = ci - byy * wpr;
+            const int by = by0 + byy;
+            const unsigned r0 = __ldg(B + (long long)(2 * by) * wpr + wx);
+            const unsigned r1 = (2 * by + 1 < rg.h) ? __ldg(B + (long long)(2 * by + 1) * wpr + wx) : 0u;
+            const unsigned v = r0 | r1;
+            if (!v) continue;
+            int* prow = parent + rg.blk_offset + (long long)by * bw + wx * 16;
+            int cur = -1, area = 0, mnx = INT_MAX, mxx = -1, mny = INT_MAX, mxy = -1;
+            auto flush = [&]() {
+                if (cur > 0 && cur < rg.max_comp) {
+                    int* s = stats + ((long long)rg.stats_offset + cur) * 5;
+                    atomicMin(s + 0, mnx); atomicMin(s + 1, mny); atomicMax(s + 2, mxx); atomicMax(s + 3, mxy);
+                    atomicAdd(s + 4, area);
+                }
+            };
+#pragma unroll 4
+            for (int k = 0; k < 16; ++k) {
+                const unsigned a = (r0 >> (2 * k)) & 1u, b = (r0 >> (2 * k + 1)) & 1u;
+                const unsigned c = (r1 >> (2 * k)) & 1u, d = (r1 >> (2 * k + 1)) & 1u;
+                if (!(a | b | c | d)) continue;
+                const int lab = rank[prow[k]];
+                prow[k] = lab;                      // parent -> final label, in place
+                if (lab != cur) { flush(); cur = lab; area = 0; mnx = INT_MAX; mxx = -1; mny = INT_MAX; mxy = -1; }
+                const int bx = wx * 16 + k;
+                area += (int)(a + b + c + d);
+                mnx = min(mnx, 2 * bx + ((a | c) ? 0 : 1));
+                mxx = max(mxx, 2 * bx + ((b | d) ? 1 : 0));
+                mny = min(mny, 2 * by + ((a | b) ? 0 : 1));
+                mxy = max(mxy, 2 * by + ((c | d) ? 1 : 0));
+            }
+            flush();
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(K4_THREADS)
+k4_final(const qc_seg_region* __restrict__ regs, int R, int total_bands, const unsigned* __restrict__ bits,
+         const int* __restrict__ parent, int* __restrict__ stats, const int* __restrict__ ncomp,
+         uint8_t* __restrict__ out_mask, int* __restrict__ out_labels, long long* __restrict__ out_area) {
+    __shared__ int s_r;
+    __shared__ int s_area[K4_THREADS / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int t = blockIdx.x; t < total_bands; t += gridDim.x) {
+        __syncthreads();
+        if (tid == 0) s_r = find_region(t, R, [&](int i) { return regs[i].band_offset; });
+        __syncthreads();
+        const qc_seg_region rg = regs[s_r];
+        const int wpr = wpr_of(rg), bw = bw_of(rg);
+        const int y0 = (t - rg.band_offset) * K4_BAND_ROWS;
+        const int y1 = min(y0 + K4_BAND_ROWS, rg.h);
+        const unsigned* B = bits + rg.bits_offset;
+        const int* st = stats + (long long)rg.stats_offset * 5;
+        const int* P = parent + rg.blk_offset;
+        int kept = 0;
+        // 4 consecutive pixels per thread
+        const int q_per_row = (rg.w + 3) >> 2;
+        for (int i = tid; i < (y1 - y0) * q_per_row; i += K4_THREADS) {
+            const int yy = i / q_per_row, q = i - yy * q_per_row;
+            const int y = y0 + yy, x0 = q * 4;
+            const unsigned word = __ldg(B + (long long)y * wpr + (x0 >> 5));
+            const unsigned nib = (word >> (x0 & 31)) & 15u;
+            int lab[4] = {0, 0, 0, 0};
+            if (nib) {
+                const int* prow = P + (long long)(y >> 1) * bw + (x0 >> 1);
+                int l01 = 0, l23 = 0;
+                if (nib & 3u) l01 = prow[0];
+                if (nib & 12u) l23 = prow[1];
+                // min-area filter (components beyond max_comp have no recorded area: kept)
+                if (l01 > 0 && l01 < rg.max_comp && st[(long long)l01 * 5 + 4] < rg.min_area) l01 = 0;
+                if (l23 > 0 && l23 < rg.max_comp && st[(long long)l23 * 5 + 4] < rg.min_area) l23 = 0;
+                lab[0] = (nib & 1u) ? l01 : 0; lab[1] = (nib & 2u) ? l01 : 0;
+                lab[2] = (nib & 4u) ? l23 : 0; lab[3] = (nib & 8u) ? l23 : 0;
+            }
+            const long long o = rg.out_offset + (long long)y * rg.w + x0;
+            const int nvalid = min(4, rg.w - x0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) kept += (j < nvalid && lab[j] > 0) ? 1 : 0;
+            if (out_labels) {
+                if (nvalid == 4 && ((o & 3) == 0)) {
+                    qc_st_cs(out_labels + o, make_uint4((unsigned)lab[0], (unsigned)lab[1], (unsigned)lab[2], (unsigned)lab[3]));
+                } else {
+                    for (int j = 0; j < nvalid; ++j) out_labels[o + j] = lab[j];
+                }
+            }
+            if (out_mask) {
+                if (nvalid == 4 && ((o & 3) == 0)) {
+                    const unsigned m = (lab[0] > 0 ? 0xFFu : 0u) | (lab[1] > 0 ? 0xFF00u : 0u) |
+                                       (lab[2] > 0 ? 0xFF0000u : 0u) | (lab[3] > 0 ? 0xFF000000u : 0u);
+                    *reinterpret_cast<unsigned*>(out_mask + o) = m;
+                } else {
+                    for (int j = 0; j < nvalid; ++j) out_mask[o + j] = lab[j] > 0 ? 255 : 0;
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) kept += __shfl_xor_sync(0xffffffffu, kept, o);
+        if (lane == 0) s_area[warp] = kept;
+        __syncthreads();
+        if (tid == 0) {
+            long long s = 0;
+            for (int k = 0; k < K4_THREADS / 32; ++k) s += s_area[k];
+            if (s) atomicAdd(reinterpret_cast<unsigned long long*>(out_area + s_r), (unsigned long long)s);
+        }
+        // first band of each region converts (minx,miny,maxx,maxy) -> (x,y,w,h); only columns 2,3
+        // change, nobody else reads them
+        if (y0 == 0) {
+            const int rows = min(ncomp[s_r], rg.max_comp);
+            int* sw = stats + (long long)rg.stats_offset * 5;
+            for (int k = tid; k < rows; k += K4_THREADS) {
+                if (k == 0 || sw[k * 5 + 4] == 0) { sw[k * 5 + 0] = sw[k * 5 + 1] = sw[k * 5 + 2] = sw[k * 5 + 3] = 0; continue; }
+                sw[k * 5 + 2] = sw[k * 5 + 2] - sw[k * 5 + 0] + 1;
+                sw[k * 5 + 3] = sw[k * 5 + 3] - sw[k * 5 + 1] + 1;
+            }
+        }
+    }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+extern "C" int qc_segment_plan(qc_seg_region* regs, int num_regions, qc_seg_params* p) {
+    if (!regs || !p || num_regions < 0) return QC_ERR_INVALID;
+    long long px = 0, bits = 0, blocks = 0, stats = 0;
+    long long bands = 0, chunks = 0;
+    int mw = 0, mh = 0;
+    for (int i = 0; i < num_regions; ++i) {
+        qc_seg_region& r = regs[i];
+        if (r.w <= 0 || r.h <= 0 || r.x < 0 || r.y < 0 || r.img < 0 || r.img >= p->n || r.x + r.w > p->w ||
+            r.y + r.h > p->h || r.max_comp < 1)
+            return QC_ERR_INVALID;
+        const long long wpr = (r.w + 31) / 32, bw = (r.w + 1) / 2, bh = (r.h + 1) / 2;
+        r.out_offset = px;
+        r.stats_offset = (int32_t)stats;
+        r.band_offset = (int32_t)bands;
+        r.chunk_offset = (int32_t)chunks;
+        r.bits_offset = (int32_t)bits;
+        r.blk_offset = (int32_t)blocks;
+        px += (long long)r.w * r.h;
+        px = (px + 15) & ~15ll;                 // keep every region's outputs 16-byte aligned
+        stats += r.max_comp;
+        bands += (r.h + K4_BAND_ROWS - 1) / K4_BAND_ROWS;
+        chunks += (bw * bh + K4_CHUNK - 1) / K4_CHUNK;
+        bits += wpr * r.h;
+        blocks += bw * bh;
+        mw = std::max(mw, r.w);
+        mh = std::max(mh, r.h);
+        if (blocks > INT_MAX || bits > INT_MAX || stats > INT_MAX) return QC_ERR_UNSUPPORTED;
+    }
+    p->num_regions = num_regions;
+    p->total_pixels = px;
+    p->total_bits_words = (int32_t)bits;
+    p->total_blocks = (int32_t)blocks;
+    p->total_stats_rows = (int32_t)stats;
+    p->total_bands = (int32_t)bands;
+    p->total_chunks = (int32_t)chunks;
+    p->max_region_w = mw;
+    p->max_region_h = mh;
+    return QC_OK;
+}
+
+extern "C" size_t qc_segment_workspace_bytes(const qc_seg_params* p) {
+    if (!p || p->num_regions <= 0) return 0;
+    return carve(nullptr, p).total;
+}
+
+extern "C" int qc_segment(qc_ctx* ctx, const uint8_t* imgs, const qc_seg_params* p, const qc_seg_region* regions,
+                          void* workspace, size_t workspace_bytes, uint8_t* out_mask, int32_t* out_labels,
+                          int32_t* out_ncomp, int32_t* out_stats, int32_t* out_thr, int64_t* out_area, void* stream) {
+    if (!ctx) return QC_ERR_INVALID;
+    if (!p) QC_FAIL(ctx, QC_ERR_INVALID, "qc_segment: null params");
+    if (p->num_regions == 0) return QC_OK;
+    if (!imgs || !regions || !out_ncomp || !out_stats || !out_thr || !out_area)
+        QC_FAIL(ctx, QC_ERR_INVALID, "qc_segment: null argument");
+    if ((p->channels != 1 && p->channels != 3) || p->morph_iters < 0 || p->morph_iters > 4 || p->total_bands <= 0 ||
+        p->row_stride < p->w * p->channels)
+        QC_FAIL(ctx, QC_ERR_INVALID, "qc_segment: bad params (run qc_segment_plan first)");
+    SegWs w = carve(workspace, p);
+    if (!workspace || workspace_bytes < w.total) QC_FAIL(ctx, QC_ERR_WORKSPACE, "workspace %zu < %zu", workspace_bytes, w.total);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int R = p->num_regions;
+    Img im{imgs, p->img_stride, p->row_stride, p->channels};
+    const int sms = ctx->sm_count;
+
+    k4_init<<<std::min(sms * 4, std::max(1, (p->total_stats_rows + 255) / 256)), 256, 0, st>>>(
+        regions, R, w.hist, out_stats, (long long*)out_area, p->total_stats_rows);
+    QC_LAUNCHED(ctx);
+
+    const int band_grid = std::min(p->total_bands, sms * 4);
+    k4_hist<<<band_grid, K4_THREADS, 0, st>>>(im, regions, R, p->total_bands, w.hist, w.gray);
+    QC_LAUNCHED(ctx);
+
+    k4_otsu<<<(R + 31) / 32, 32, 0, st>>>(regions, R, w.hist, w.cmp, out_thr);
+    QC_LAUNCHED(ctx);
+
+    const int halo = 4 * p->morph_iters;
+    const int wpr_max = (p->max_region_w + 31) / 32;
+    const int buf_words = (K4_BAND_ROWS + 2 * halo) * wpr_max;
+    const size_t smem = (size_t)buf_words * 4 * 2;
+    if ((int)smem > ctx->max_smem_optin) QC_FAIL(ctx, QC_ERR_UNSUPPORTED, "qc_segment: region width %d too large", p->max_region_w);
+    QC_CUDA(ctx, cudaFuncSetAttribute(k4_mask, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k4_mask<<<band_grid, K4_THREADS, smem, st>>>(im, regions, R, p->total_bands, p->morph_iters, w.cmp, w.gray, w.bits,
+                                                 w.parent, buf_words);
+    QC_LAUNCHED(ctx);
+
+    k4_merge<<<std::min(p->total_bands, sms * 8), K4_THREADS, 0, st>>>(regions, R, p->total_bands, w.bits, w.parent);
+    QC_LAUNCHED(ctx);
+
+    const int chunk_grid = std::min(p->total_chunks, sms * 2);
+    k4_compress<<<chunk_grid, K4_CHUNK, 0, st>>>(regions, R, p->total_chunks, w.parent, w.chunk_count);
+    QC_LAUNCHED(ctx);
+    k4_scan<<<std::min(R, sms * 2), 1024, 0, st>>>(regions, R, w.chunk_count, w.chunk_base, out_ncomp);
+    QC_LAUNCHED(ctx);
+    k4_rank<<<chunk_grid, K4_CHUNK, 0, st>>>(regions, R, p->total_chunks, w.parent, w.chunk_base, w.rank);
+    QC_LAUNCHED(ctx);
+
+    k4_stats<<<std::min(p->total_bands, sms * 8), K4_THREADS, 0, st>>>(regions, R, p->total_bands, w.bits, w.parent,
+                                                                       w.rank, out_stats);
+    QC_LAUNCHED(ctx);
+    k4_final<<<std::min(p->total_bands, sms * 8), K4_THREADS, 0, st>>>(regions, R, p->total_bands, w.bits, w.parent,
+                                                                       out_stats, out_ncomp, out_mask, out_labels,
+                                                                       (long long*)out_area);
+    QC_LAUNCHED(ctx);
+    return QC_OK;
+}

@@ -1,0 +1,384 @@
+"""ctypes binding of include/qcgraft.h + thin tensor-level wrappers.
+
+The library is the product; this module only marshals ``tensor.data_ptr()`` and the current
+CUDA stream into the C ABI.  There is NO CPU fallback: a missing library or device raises
+``QcGraftError`` (the drop-in classes turn it into the reference's ``{"error": ...}`` dicts,
+inference/detector.py:124-126).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import build as _build
+
+QC_DT_F32, QC_DT_BF16 = 0, 1
+QC_PRE_STRETCH, QC_PRE_LETTERBOX, QC_PRE_LETTERBOX_AUTO = 0, 1, 2
+QC_PRE_SWAP_RB, QC_PRE_LUT_UNIFORM = 1, 2
+QC_MAX_LEVELS = 4
+
+
+class QcGraftError(RuntimeError):
+    pass
+
+
+class PrePlan(C.Structure):
+    _fields_ = [("src_h", C.c_int32), ("src_w", C.c_int32), ("new_h", C.c_int32), ("new_w", C.c_int32),
+                ("top", C.c_int32), ("left", C.c_int32), ("dst_h", C.c_int32), ("dst_w", C.c_int32),
+                ("gain", C.c_float), ("pad_x", C.c_int32), ("pad_y", C.c_int32)]
+
+
+class YoloParams(C.Structure):
+    _fields_ = [("n", C.c_int32), ("nc", C.c_int32), ("reg_max", C.c_int32), ("num_levels", C.c_int32),
+                ("level_h", C.c_int32 * QC_MAX_LEVELS), ("level_w", C.c_int32 * QC_MAX_LEVELS),
+                ("level_stride", C.c_float * QC_MAX_LEVELS),
+                ("level_batch_stride", C.c_int64 * QC_MAX_LEVELS),
+                ("level_chan_stride", C.c_int64 * QC_MAX_LEVELS),
+                ("in_dtype", C.c_int32), ("conf_thres", C.c_double), ("iou_thres", C.c_double),
+                ("max_det", C.c_int32), ("max_nms", C.c_int32), ("max_wh", C.c_float),
+                ("gain", C.c_float), ("pad_x", C.c_int32), ("pad_y", C.c_int32),
+                ("orig_h", C.c_int32), ("orig_w", C.c_int32), ("scale_boxes", C.c_int32)]
+
+
+class SegRegion(C.Structure):
+    _fields_ = [("img", C.c_int32), ("x", C.c_int32), ("y", C.c_int32), ("w", C.c_int32), ("h", C.c_int32),
+                ("polarity", C.c_int32), ("min_area", C.c_int32), ("max_comp", C.c_int32),
+                ("thr_scale", C.c_double),
+                ("out_offset", C.c_int64), ("stats_offset", C.c_int32), ("band_offset", C.c_int32),
+                ("chunk_offset", C.c_int32), ("bits_offset", C.c_int32), ("blk_offset", C.c_int32)]
+
+
+class SegParams(C.Structure):
+    _fields_ = [("n", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("channels", C.c_int32),
+                ("img_stride", C.c_int64), ("row_stride", C.c_int32), ("morph_iters", C.c_int32),
+                ("num_regions", C.c_int32), ("total_pixels", C.c_int64), ("total_stats_rows", C.c_int32),
+                ("total_bits_words", C.c_int32), ("total_blocks", C.c_int32), ("total_bands", C.c_int32),
+                ("total_chunks", C.c_int32), ("max_region_w", C.c_int32), ("max_region_h", C.c_int32)]
+
+
+_SIGS = {
+    "qc_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
+    "qc_destroy": (None, [C.c_void_p]),
+    "qc_last_error": (C.c_char_p, [C.c_void_p]),
+    "qc_version": (C.c_char_p, []),
+    "qc_sm_count": (C.c_int, [C.c_void_p]),
+    "qc_launch_count": (C.c_int64, [C.c_void_p]),
+    "qc_sizeof": (C.c_size_t, [C.c_int]),
+    "qc_pre_make_plan": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(PrePlan)]),
+    "qc_preprocess": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int32, C.POINTER(PrePlan),
+                                C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "qc_yolo_workspace_bytes": (C.c_size_t, [C.POINTER(YoloParams)]),
+    "qc_yolo_decode_nms": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(YoloParams), C.c_void_p,
+                                     C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "qc_nms_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
+    "qc_nms": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                         C.c_double, C.c_float, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p,
+                         C.c_void_p]),
+    "qc_roi_align": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int32,
+                               C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                               C.c_int, C.c_void_p, C.c_void_p]),
+    "qc_segment_plan": (C.c_int, [C.POINTER(SegRegion), C.c_int, C.POINTER(SegParams)]),
+    "qc_segment_workspace_bytes": (C.c_size_t, [C.POINTER(SegParams)]),
+    "qc_segment": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(SegParams), C.c_void_p, C.c_void_p, C.c_size_t,
+                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "qc_spc_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+}
+EXPORTED_SYMBOLS = tuple(_SIGS)
+
+_lib = None
+_lib_lock = threading.Lock()
+
+
+def load_library(build_if_missing: bool = True) -> C.CDLL:
+    """dlopen lib/libqcgraft.so (building it first if the sources are newer)."""
+    global _lib
+    with _lib_lock:
+        if _lib is not None:
+            return _lib
+        path = _build.LIB_PATH
+        if build_if_missing and _build.needs_build():
+            try:
+                _build.build()
+            except Exception as e:  # no nvcc on the box: use the shipped .so if there is one
+                if not os.path.exists(path):
+                    raise QcGraftError(f"libqcgraft.so missing and cannot be built: {e}") from e
+        if not os.path.exists(path):
+            raise QcGraftError(f"{path} not found: run __graft_entry__.build()")
+        lib = C.CDLL(path)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(lib, name)     # AttributeError if the .so lacks a declared symbol
+            fn.restype = res
+            fn.argtypes = args
+        for which, st in enumerate((PrePlan, YoloParams, SegRegion, SegParams)):
+            if lib.qc_sizeof(which) != C.sizeof(st):
+                raise QcGraftError(f"ABI mismatch: {st.__name__} is {C.sizeof(st)} B here, "
+                                   f"{lib.qc_sizeof(which)} B in libqcgraft.so")
+        _lib = lib
+        return lib
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _stream(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+class Context:
+    """One qc_ctx per (device, thread): the reference calls predict() from thread pools
+    (inference/detector.py:143, models/ensemble.py:88) with no locks."""
+
+    _tls = threading.local()
+
+    def __init__(self, device: int = 0):
+        if not torch.cuda.is_available():
+            raise QcGraftError("CUDA device required: qcgraft has no CPU fallback")
+        self.lib = load_library()
+        self.device = torch.device("cuda", device)
+        h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            torch.cuda.current_stream()          # make sure the primary context exists
+            rc = self.lib.qc_create(device, C.byref(h))
+        if rc != 0:
+            raise QcGraftError(f"qc_create({device}) failed with status {rc}")
+        self.h = h
+        self._lut_cache = {}
+        self._ws = {}
+
+    @classmethod
+    def current(cls, device: int = 0) -> "Context":
+        d = getattr(cls._tls, "ctxs", None)
+        if d is None:
+            d = cls._tls.ctxs = {}
+        if device not in d:
+            d[device] = Context(device)
+        return d[device]
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                self.lib.qc_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    # -- helpers ---------------------------------------------------------------------------
+    def _check(self, rc: int, what: str):
+        if rc != 0:
+            msg = self.lib.qc_last_error(self.h)
+            raise QcGraftError(f"{what}: status {rc}: {msg.decode() if msg else ''}")
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.qc_launch_count(self.h))
+
+    @property
+    def sm_count(self) -> int:
+        return int(self.lib.qc_sm_count(self.h))
+
+    def workspace(self, key: str, nbytes: int) -> torch.Tensor:
+        """Grow-only cached scratch buffer (caller-owned memory as far as the C ABI goes)."""
+        t = self._ws.get(key)
+        if t is None or t.numel() < nbytes:
+            t = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=self.device)
+            self._ws[key] = t
+        return t
+
+    def norm_lut(self, mean=None, std=None) -> Tuple[torch.Tensor, bool]:
+        """float32 [3][256] table built with the reference's own float32 ops:
+        ultralytics: v.float()/255 ; torchvision: ToTensor (/255) then (t-mean)/std."""
+        key = (tuple(mean) if mean is not None else None, tuple(std) if std is not None else None)
+        if key not in self._lut_cache:
+            t = (torch.arange(256, dtype=torch.float32) / 255).repeat(3, 1)
+            if mean is not None:
+                m = torch.tensor(mean, dtype=torch.float32).view(3, 1)
+                s = torch.tensor(std, dtype=torch.float32).view(3, 1)
+                t = (t - m) / s
+            uniform = bool(torch.equal(t[0], t[1]) and torch.equal(t[0], t[2]))
+            self._lut_cache[key] = (t.contiguous().to(self.device), uniform)
+        return self._lut_cache[key]
+
+    # -- K1 --------------------------------------------------------------------------------
+    def make_pre_plan(self, mode: int, src_h: int, src_w: int, H: int, W: int, stride: int = 32) -> PrePlan:
+        pl = PrePlan()
+        rc = self.lib.qc_pre_make_plan(mode, src_h, src_w, H, W, stride, C.byref(pl))
+        if rc != 0:
+            raise QcGraftError(f"qc_pre_make_plan failed: {rc}")
+        return pl
+
+    def preprocess(self, src: torch.Tensor, plan: PrePlan, swap_rb: bool = True, mean=None, std=None,
+                   pad_value: int = 114, out_dtype=torch.bfloat16, out: Optional[torch.Tensor] = None):
+        """src: uint8 CUDA tensor [n,h,w,3] (any row/image pitch, channel-contiguous)."""
+        assert src.is_cuda and src.dtype == torch.uint8 and src.dim() == 4 and src.shape[3] == 3
+        assert src.stride(3) == 1 and src.stride(2) == 3, "pixels must be packed RGB triplets"
+        n = src.shape[0]
+        assert (src.shape[1], src.shape[2]) == (plan.src_h, plan.src_w)
+        lut, uniform = self.norm_lut(mean, std)
+        if out is None:
+            out = torch.empty((n, 3, plan.dst_h, plan.dst_w), dtype=out_dtype, device=src.device)
+        assert out.is_contiguous() and out.dtype in (torch.bfloat16, torch.float32)
+        flags = (QC_PRE_SWAP_RB if swap_rb else 0) | (QC_PRE_LUT_UNIFORM if uniform else 0)
+        dt = QC_DT_BF16 if out.dtype == torch.bfloat16 else QC_DT_F32
+        rc = self.lib.qc_preprocess(self.h, src.data_ptr(), n, src.stride(0) if n > 1 else src.shape[1] * src.stride(1),
+                                    src.stride(1), C.byref(plan), lut.data_ptr(), pad_value, flags, dt,
+                                    out.data_ptr(), _stream(src.device))
+        self._check(rc, "qc_preprocess")
+        return out
+
+    # -- K2 --------------------------------------------------------------------------------
+    def yolo_params(self, levels: Sequence[torch.Tensor], nc: int, strides=(8, 16, 32), conf=0.7, iou=0.5,
+                    max_det=300, max_nms=30000, max_wh=7680.0, plan: Optional[PrePlan] = None,
+                    reg_max: int = 16) -> YoloParams:
+        p = YoloParams()
+        p.n = levels[0].shape[0]
+        p.nc, p.reg_max, p.num_levels = nc, reg_max, len(levels)
+        for i, l in enumerate(levels):
+            assert l.is_cuda and l.dim() == 4 and l.shape[1] == 4 * reg_max + nc
+            assert l.stride(3) == 1 and l.stride(2) == l.shape[3], "level planes must be contiguous"
+            p.level_h[i], p.level_w[i] = l.shape[2], l.shape[3]
+            p.level_stride[i] = float(strides[i])
+            p.level_batch_stride[i] = l.stride(0)
+            p.level_chan_stride[i] = l.stride(1)
+        dt = levels[0].dtype
+        assert all(l.dtype == dt for l in levels) and dt in (torch.float32, torch.bfloat16)
+        p.in_dtype = QC_DT_F32 if dt == torch.float32 else QC_DT_BF16
+        p.conf_thres, p.iou_thres = float(conf), float(iou)
+        p.max_det, p.max_nms, p.max_wh = max_det, max_nms, float(max_wh)
+        if plan is not None:
+            p.gain, p.pad_x, p.pad_y = plan.gain, plan.pad_x, plan.pad_y
+            p.orig_h, p.orig_w, p.scale_boxes = plan.src_h, plan.src_w, 1
+        else:
+            p.gain, p.scale_boxes = 1.0, 0
+        return p
+
+    def yolo_decode_nms(self, levels: Sequence[torch.Tensor], params: YoloParams, out=None):
+        n, md = params.n, params.max_det
+        dev = levels[0].device
+        if out is None:
+            det = torch.empty((n, md, 6), dtype=torch.float32, device=dev)
+            anchor = torch.empty((n, md), dtype=torch.int32, device=dev)
+            count = torch.empty((n,), dtype=torch.int32, device=dev)
+            ncand = torch.empty((n,), dtype=torch.int32, device=dev)
+        else:
+            det, anchor, count, ncand = out
+        need = self.lib.qc_yolo_workspace_bytes(C.byref(params))
+        ws = self.workspace("yolo", need)
+        ptrs = (C.c_void_p * QC_MAX_LEVELS)(*[l.data_ptr() for l in levels] + [None] * (QC_MAX_LEVELS - len(levels)))
+        rc = self.lib.qc_yolo_decode_nms(self.h, ptrs, C.byref(params), ws.data_ptr(), ws.numel(), det.data_ptr(),
+                                         anchor.data_ptr(), count.data_ptr(), ncand.data_ptr(), _stream(dev))
+        self._check(rc, "qc_yolo_decode_nms")
+        return det, anchor, count, ncand
+
+    def nms(self, boxes: torch.Tensor, scores: torch.Tensor, cls: torch.Tensor, counts: torch.Tensor,
+            iou: float = 0.5, max_wh: float = 7680.0, max_det: int = 300):
+        """boxes [n,cap,4] f32, scores [n,cap] f32, cls [n,cap] i32, counts [n] i32 -> (keep [n,max_det], count [n])."""
+        n, cap = scores.shape
+        assert boxes.is_contiguous() and scores.is_contiguous() and cls.is_contiguous()
+        assert boxes.dtype == torch.float32 and scores.dtype == torch.float32 and cls.dtype == torch.int32
+        keep = torch.empty((n, max_det), dtype=torch.int32, device=boxes.device)
+        cnt = torch.empty((n,), dtype=torch.int32, device=boxes.device)
+        need = self.lib.qc_nms_workspace_bytes(n, cap)
+        ws = self.workspace("nms", need)
+        rc = self.lib.qc_nms(self.h, boxes.data_ptr(), scores.data_ptr(), cls.data_ptr(), counts.data_ptr(), n, cap,
+                             float(iou), float(max_wh), max_det, ws.data_ptr(), ws.numel(), keep.data_ptr(),
+                             cnt.data_ptr(), _stream(boxes.device))
+        self._check(rc, "qc_nms")
+        return keep, cnt
+
+    # -- K3 --------------------------------------------------------------------------------
+    def roi_align(self, imgs: torch.Tensor, rois: torch.Tensor, out_hw=(224, 224), sampling_ratio: int = 2,
+                  aligned: bool = True, swap_rb: bool = False, mean=(0.485, 0.456, 0.406),
+                  std=(0.229, 0.224, 0.225), out_dtype=torch.bfloat16, out: Optional[torch.Tensor] = None):
+        assert imgs.is_cuda and imgs.dtype == torch.uint8 and imgs.dim() == 4 and imgs.shape[3] == 3
+        assert imgs.stride(3) == 1 and imgs.stride(2) == 3
+        assert rois.is_cuda and rois.dtype == torch.float32 and rois.is_contiguous() and rois.shape[-1] == 5
+        K = rois.shape[0]
+        key = ("norm", tuple(mean), tuple(std))
+        if key not in self._lut_cache:
+            t = torch.tensor([[255.0, m, s] for m, s in zip(mean, std)], dtype=torch.float32)
+            self._lut_cache[key] = t.to(self.device)
+        norm = self._lut_cache[key]
+        if out is None:
+            out = torch.empty((K, 3) + tuple(out_hw), dtype=out_dtype, device=imgs.device)
+        if K == 0:
+            return out
+        n, h, w = imgs.shape[:3]
+        dt = QC_DT_BF16 if out.dtype == torch.bfloat16 else QC_DT_F32
+        rc = self.lib.qc_roi_align(self.h, imgs.data_ptr(), n, h, w, imgs.stride(0) if n > 1 else h * imgs.stride(1),
+                                   imgs.stride(1), rois.data_ptr(), K, out_hw[0], out_hw[1], sampling_ratio,
+                                   int(aligned), int(swap_rb), norm.data_ptr(), dt, out.data_ptr(),
+                                   _stream(imgs.device))
+        self._check(rc, "qc_roi_align")
+        return out
+
+    # -- K4 --------------------------------------------------------------------------------
+    def segment_plan(self, regions: Sequence[dict], n: int, h: int, w: int, channels: int, img_stride: int,
+                     row_stride: int, morph_iters: int = 1):
+        """regions: dicts with img,x,y,w,h and optional polarity(1), thr_scale(1.0), min_area(20), max_comp."""
+        R = len(regions)
+        arr = (SegRegion * max(R, 1))()
+        for i, r in enumerate(regions):
+            a = arr[i]
+            a.img, a.x, a.y, a.w, a.h = int(r["img"]), int(r["x"]), int(r["y"]), int(r["w"]), int(r["h"])
+            a.polarity = int(r.get("polarity", 1))
+            a.thr_scale = float(r.get("thr_scale", 1.0))
+            a.min_area = int(r.get("min_area", 20))
+            nblk = ((a.w + 1) // 2) * ((a.h + 1) // 2)
+            a.max_comp = int(r.get("max_comp", min(nblk + 1, 1 << 16)))
+        p = SegParams()
+        p.n, p.h, p.w, p.channels = n, h, w, channels
+        p.img_stride, p.row_stride, p.morph_iters = img_stride, row_stride, morph_iters
+        rc = self.lib.qc_segment_plan(arr, R, C.byref(p))
+        if rc != 0:
+            raise QcGraftError(f"qc_segment_plan failed: {rc} (region outside the image?)")
+        return arr, p
+
+    def segment(self, imgs: torch.Tensor, regions: Sequence[dict], morph_iters: int = 1, want_mask: bool = True,
+                want_labels: bool = True):
+        """imgs: uint8 CUDA [n,h,w] (gray) or [n,h,w,3] (RGB).  Returns dict of device tensors + the plan."""
+        assert imgs.is_cuda and imgs.dtype == torch.uint8 and imgs.dim() in (3, 4)
+        n, h, w = imgs.shape[:3]
+        ch = 1 if imgs.dim() == 3 else imgs.shape[3]
+        assert imgs.stride(-1) == 1 and (ch == 1 or imgs.stride(2) == ch)
+        dev = imgs.device
+        arr, p = self.segment_plan(regions, n, h, w, ch, imgs.stride(0) if n > 1 else h * imgs.stride(1),
+                                   imgs.stride(1), morph_iters)
+        R = p.num_regions
+        if R == 0:
+            return dict(regions=arr, params=p, mask=None, labels=None,
+                        ncomp=torch.zeros(0, dtype=torch.int32, device=dev),
+                        stats=torch.zeros((0, 5), dtype=torch.int32, device=dev),
+                        thr=torch.zeros(0, dtype=torch.int32, device=dev),
+                        area=torch.zeros(0, dtype=torch.int64, device=dev))
+        host = np.frombuffer(arr, dtype=np.uint8, count=C.sizeof(SegRegion) * R)
+        regs_dev = torch.from_numpy(host.copy()).to(dev, non_blocking=False)
+        mask = torch.empty(p.total_pixels, dtype=torch.uint8, device=dev) if want_mask else None
+        labels = torch.empty(p.total_pixels, dtype=torch.int32, device=dev) if want_labels else None
+        ncomp = torch.empty(R, dtype=torch.int32, device=dev)
+        stats = torch.empty((p.total_stats_rows, 5), dtype=torch.int32, device=dev)
+        thr = torch.empty(R, dtype=torch.int32, device=dev)
+        area = torch.empty(R, dtype=torch.int64, device=dev)
+        need = self.lib.qc_segment_workspace_bytes(C.byref(p))
+        ws = self.workspace("seg", need)
+        rc = self.lib.qc_segment(self.h, imgs.data_ptr(), C.byref(p), regs_dev.data_ptr(), ws.data_ptr(), ws.numel(),
+                                 _ptr(mask), _ptr(labels), ncomp.data_ptr(), stats.data_ptr(), thr.data_ptr(),
+                                 area.data_ptr(), _stream(dev))
+        self._check(rc, "qc_segment")
+        return dict(regions=arr, params=p, regs_dev=regs_dev, mask=mask, labels=labels, ncomp=ncomp, stats=stats,
+                    thr=thr, area=area)
+
+    # -- SPC -------------------------------------------------------------------------------
+    def spc_stats(self, det: torch.Tensor, count: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        n, md = det.shape[0], det.shape[1]
+        if out is None:
+            out = torch.empty(9, dtype=torch.float64, device=det.device)
+        rc = self.lib.qc_spc_stats(self.h, det.data_ptr(), count.data_ptr(), n, md, out.data_ptr(),
+                                   _stream(det.device))
+        self._check(rc, "qc_spc_stats")
+        return out
