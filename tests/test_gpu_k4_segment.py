@@ -72,8 +72,9 @@ def test_structured_patterns(qc):
     _run_full_frames(qc, imgs, iters=1, min_area=3)
     # nested rings + spiral
     im = np.full((1, 128, 128), 30, np.uint8)
+    y2, x2 = np.mgrid[0:128, 0:128]
+    d = np.maximum(np.abs(y2 - 64), np.abs(x2 - 64))
     for r in range(4, 60, 6):
-        d = np.maximum(np.abs(yy[:128, :128] - 64), np.abs(xx[:128, :128] - 64))
         im[0][d == r] = 230
     _run_full_frames(qc, im, iters=0, min_area=1)
 
