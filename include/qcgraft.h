@@ -172,6 +172,9 @@ typedef struct {
     int32_t n, h, w, channels;  /* image batch: uint8 [n,h,w] gray or [n,h,w,3] RGB      */
     int64_t img_stride; int32_t row_stride;            /* bytes                         */
     int32_t morph_iters;        /* 0..4: close then open, `iters` iterations each       */
+    int32_t swap_rb;            /* channels==3: 1 = pixels are stored B,G,R relative to what
+                                   the reference's RGB2GRAY sees (inference/detector.py:234
+                                   swaps before inference/segmentation.py:67)            */
     /* filled by qc_segment_plan() */
     int32_t num_regions;
     int64_t total_pixels;       /* size of out_mask / out_labels (elements)             */

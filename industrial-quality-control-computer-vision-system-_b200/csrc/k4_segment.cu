@@ -69,7 +69,7 @@ SegWs carve(void* base, const qc_seg_params* p) {
 struct Img {
     const uint8_t* data;
     long long img_stride;
-    int row_stride, channels;
+    int row_stride, channels, swap_rb;
 };
 
 // region of work item t (band or chunk index): largest r with off(r) <= t
@@ -127,7 +127,8 @@ k4_hist(Img im, const qc_seg_region* __restrict__ regs, int R, int total_bands, 
             unsigned g;
             if (im.channels == 3) {
                 // cv2 RGB2GRAY fixed point: (R*9798 + G*19235 + B*3735 + 2^14) >> 15
-                g = (9798u * __ldg(p) + 19235u * __ldg(p + 1) + 3735u * __ldg(p + 2) + 16384u) >> 15;
+                const unsigned c0 = __ldg(p), c1 = __ldg(p + 1), c2 = __ldg(p + 2);
+                g = (9798u * (im.swap_rb ? c2 : c0) + 19235u * c1 + 3735u * (im.swap_rb ? c0 : c2) + 16384u) >> 15;
                 gray_ws[rg.out_offset + (long long)(y0 + yy) * rg.w + xx] = (uint8_t)g;
             } else {
                 g = __ldg(p);
@@ -678,7 +679,7 @@ extern "C" int qc_segment(qc_ctx* ctx, const uint8_t* imgs, const qc_seg_params*
     if (!workspace || workspace_bytes < w.total) QC_FAIL(ctx, QC_ERR_WORKSPACE, "workspace %zu < %zu", workspace_bytes, w.total);
     cudaStream_t st = (cudaStream_t)stream;
     const int R = p->num_regions;
-    Img im{imgs, p->img_stride, p->row_stride, p->channels};
+    Img im{imgs, p->img_stride, p->row_stride, p->channels, p->swap_rb};
     const int sms = ctx->sm_count;
 
     k4_init<<<std::min(sms * 4, std::max(1, (p->total_stats_rows + 255) / 256)), 256, 0, st>>>(

@@ -56,7 +56,7 @@ class SegRegion(C.Structure):
 class SegParams(C.Structure):
     _fields_ = [("n", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("channels", C.c_int32),
                 ("img_stride", C.c_int64), ("row_stride", C.c_int32), ("morph_iters", C.c_int32),
-                ("num_regions", C.c_int32), ("total_pixels", C.c_int64), ("total_stats_rows", C.c_int32),
+                ("swap_rb", C.c_int32), ("num_regions", C.c_int32), ("total_pixels", C.c_int64), ("total_stats_rows", C.c_int32),
                 ("total_bits_words", C.c_int32), ("total_blocks", C.c_int32), ("total_bands", C.c_int32),
                 ("total_chunks", C.c_int32), ("max_region_w", C.c_int32), ("max_region_h", C.c_int32)]
 
@@ -319,7 +319,7 @@ class Context:
 
     # -- K4 --------------------------------------------------------------------------------
     def segment_plan(self, regions: Sequence[dict], n: int, h: int, w: int, channels: int, img_stride: int,
-                     row_stride: int, morph_iters: int = 1):
+                     row_stride: int, morph_iters: int = 1, swap_rb: bool = False):
         """regions: dicts with img,x,y,w,h and optional polarity(1), thr_scale(1.0), min_area(20), max_comp."""
         R = len(regions)
         arr = (SegRegion * max(R, 1))()
@@ -334,13 +334,14 @@ class Context:
         p = SegParams()
         p.n, p.h, p.w, p.channels = n, h, w, channels
         p.img_stride, p.row_stride, p.morph_iters = img_stride, row_stride, morph_iters
+        p.swap_rb = int(swap_rb)
         rc = self.lib.qc_segment_plan(arr, R, C.byref(p))
         if rc != 0:
             raise QcGraftError(f"qc_segment_plan failed: {rc} (region outside the image?)")
         return arr, p
 
     def segment(self, imgs: torch.Tensor, regions: Sequence[dict], morph_iters: int = 1, want_mask: bool = True,
-                want_labels: bool = True):
+                want_labels: bool = True, swap_rb: bool = False):
         """imgs: uint8 CUDA [n,h,w] (gray) or [n,h,w,3] (RGB).  Returns dict of device tensors + the plan."""
         assert imgs.is_cuda and imgs.dtype == torch.uint8 and imgs.dim() in (3, 4)
         n, h, w = imgs.shape[:3]
@@ -348,7 +349,7 @@ class Context:
         assert imgs.stride(-1) == 1 and (ch == 1 or imgs.stride(2) == ch)
         dev = imgs.device
         arr, p = self.segment_plan(regions, n, h, w, ch, imgs.stride(0) if n > 1 else h * imgs.stride(1),
-                                   imgs.stride(1), morph_iters)
+                                   imgs.stride(1), morph_iters, swap_rb)
         R = p.num_regions
         if R == 0:
             return dict(regions=arr, params=p, mask=None, labels=None,

@@ -1,0 +1,162 @@
+"""Plain-torch YOLOv8 (n/s/m) and ResNet-50 graphs with random-init weights.
+
+These conv backbones are OUTSIDE the graft target (BASELINE.json north_star): torch/cuDNN runs
+them; they exist so that end-to-end images/sec is measured with the real amount of network
+work between the hand-written kernels.  ultralytics is not installed, so the YOLOv8 graph is
+rebuilt from its published yolov8.yaml; Conv = Conv2d+BN+SiLU is built
+directly in its inference-fused form (Conv2d with bias + SiLU), which is what ultralytics runs
+after ``model.fuse()``.  The detector returns the three raw Detect-head tensors
+[B, 4*reg_max+nc, Hi, Wi] -- decode/NMS is K2's job.
+
+ResNet-50 + head follows models/resent_model.py:68-83 (torchvision resnet50, fc replaced by
+Dropout-Linear(2048,512)-ReLU-Dropout-Linear(512,nc)); weights=None because there is no network.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn as nn
+import torchvision
+
+YOLO_SCALES = {"n": (0.33, 0.25, 1024), "s": (0.33, 0.50, 1024), "m": (0.67, 0.75, 768)}
+
+
+def _div8(c: float) -> int:
+    return int(math.ceil(c / 8) * 8)
+
+
+class Conv(nn.Module):
+    def __init__(self, c1, c2, k=1, s=1):
+        super().__init__()
+        self.conv = nn.Conv2d(c1, c2, k, s, k // 2, bias=True)
+        self.act = nn.SiLU(inplace=True)
+
+    def forward(self, x):
+        return self.act(self.conv(x))
+
+
+class Bottleneck(nn.Module):
+    def __init__(self, c, shortcut=True):
+        super().__init__()
+        self.cv1 = Conv(c, c, 3)
+        self.cv2 = Conv(c, c, 3)
+        self.add = shortcut
+
+    def forward(self, x):
+        y = self.cv2(self.cv1(x))
+        return x + y if self.add else y
+
+
+class C2f(nn.Module):
+    def __init__(self, c1, c2, n=1, shortcut=False):
+        super().__init__()
+        self.c = c2 // 2
+        self.cv1 = Conv(c1, 2 * self.c, 1)
+        self.cv2 = Conv((2 + n) * self.c, c2, 1)
+        self.m = nn.ModuleList(Bottleneck(self.c, shortcut) for _ in range(n))
+
+    def forward(self, x):
+        y = list(self.cv1(x).chunk(2, 1))
+        for m in self.m:
+            y.append(m(y[-1]))
+        return self.cv2(torch.cat(y, 1))
+
+
+class SPPF(nn.Module):
+    def __init__(self, c1, c2, k=5):
+        super().__init__()
+        c_ = c1 // 2
+        self.cv1 = Conv(c1, c_, 1)
+        self.cv2 = Conv(c_ * 4, c2, 1)
+        self.m = nn.MaxPool2d(k, 1, k // 2)
+
+    def forward(self, x):
+        y = [self.cv1(x)]
+        for _ in range(3):
+            y.append(self.m(y[-1]))
+        return self.cv2(torch.cat(y, 1))
+
+
+class DetectHead(nn.Module):
+    def __init__(self, nc, ch, reg_max=16, strides=(8, 16, 32)):
+        super().__init__()
+        self.nc, self.reg_max, self.strides = nc, reg_max, strides
+        c2 = max(16, ch[0] // 4, reg_max * 4)
+        c3 = max(ch[0], min(nc, 100))
+        self.cv2 = nn.ModuleList(nn.Sequential(Conv(x, c2, 3), Conv(c2, c2, 3), nn.Conv2d(c2, 4 * reg_max, 1)) for x in ch)
+        self.cv3 = nn.ModuleList(nn.Sequential(Conv(x, c3, 3), Conv(c3, c3, 3), nn.Conv2d(c3, nc, 1)) for x in ch)
+        for a, b, s in zip(self.cv2, self.cv3, strides):      # ultralytics Detect.bias_init
+            a[-1].bias.data[:] = 1.0
+            b[-1].bias.data[:nc] = math.log(5 / nc / (640 / s) ** 2)
+
+    def forward(self, feats):
+        return [torch.cat((self.cv2[i](f), self.cv3[i](f)), 1) for i, f in enumerate(feats)]
+
+
+class YOLOv8(nn.Module):
+    """yolov8.yaml with (depth, width, max_channels) scaling; forward -> [P3, P4, P5] head tensors."""
+
+    def __init__(self, scale: str = "s", nc: int = 5):
+        super().__init__()
+        d, w, mc = YOLO_SCALES[scale]
+        ch = lambda c: _div8(min(c, mc) * w)
+        n = lambda k: max(round(k * d), 1)
+        c64, c128, c256, c512, c1024 = ch(64), ch(128), ch(256), ch(512), ch(1024)
+        self.b0 = Conv(3, c64, 3, 2)
+        self.b1 = Conv(c64, c128, 3, 2)
+        self.b2 = C2f(c128, c128, n(3), True)
+        self.b3 = Conv(c128, c256, 3, 2)
+        self.b4 = C2f(c256, c256, n(6), True)
+        self.b5 = Conv(c256, c512, 3, 2)
+        self.b6 = C2f(c512, c512, n(6), True)
+        self.b7 = Conv(c512, c1024, 3, 2)
+        self.b8 = C2f(c1024, c1024, n(3), True)
+        self.b9 = SPPF(c1024, c1024, 5)
+        self.up = nn.Upsample(scale_factor=2, mode="nearest")
+        self.h12 = C2f(c1024 + c512, c512, n(3))
+        self.h15 = C2f(c512 + c256, c256, n(3))
+        self.h16 = Conv(c256, c256, 3, 2)
+        self.h18 = C2f(c256 + c512, c512, n(3))
+        self.h19 = Conv(c512, c512, 3, 2)
+        self.h21 = C2f(c512 + c1024, c1024, n(3))
+        self.detect = DetectHead(nc, (c256, c512, c1024))
+        self.nc = nc
+        self.scale = scale
+
+    def forward(self, x):
+        x = self.b2(self.b1(self.b0(x)))
+        p3 = self.b4(self.b3(x))
+        p4 = self.b6(self.b5(p3))
+        p5 = self.b9(self.b8(self.b7(p4)))
+        f12 = self.h12(torch.cat((self.up(p5), p4), 1))
+        f15 = self.h15(torch.cat((self.up(f12), p3), 1))
+        f18 = self.h18(torch.cat((self.h16(f15), f12), 1))
+        f21 = self.h21(torch.cat((self.h19(f18), p5), 1))
+        return self.detect([f15, f18, f21])
+
+
+def build_yolo(scale: str = "s", nc: int = 5, seed: int = 0) -> YOLOv8:
+    g = torch.random.get_rng_state()
+    torch.manual_seed(seed)
+    m = YOLOv8(scale, nc).eval()
+    torch.random.set_rng_state(g)
+    return m
+
+
+def build_resnet50(nc: int = 5, seed: int = 0) -> nn.Module:
+    """models/resent_model.py:68-83 (weights=None: no network for the ImageNet checkpoint)."""
+    g = torch.random.get_rng_state()
+    torch.manual_seed(seed + 1)
+    m = torchvision.models.resnet50(weights=None)
+    nf = m.fc.in_features
+    m.fc = nn.Sequential(nn.Dropout(0.5), nn.Linear(nf, 512), nn.ReLU(inplace=True), nn.Dropout(0.3),
+                         nn.Linear(512, nc))
+    torch.random.set_rng_state(g)
+    return m.eval()
+
+
+def yolo_gflops(scale: str, H: int, W: int) -> float:
+    """Published YOLOv8 forward cost at 640^2 (8.7/28.6/78.9 GFLOP), scaled by area."""
+    base = {"n": 8.7, "s": 28.6, "m": 78.9}[scale]
+    return base * (H * W) / (640 * 640)

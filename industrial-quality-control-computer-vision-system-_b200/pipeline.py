@@ -1,0 +1,212 @@
+"""Batched device pipeline for the inspection hot path:
+
+    uint8 HWC frames --K1--> bf16 NCHW --YOLOv8 (torch)--> head tensors --K2--> kept boxes
+        --K3--> 224x224 crops --ResNet-50 (torch)--> class probabilities
+        --K4--> per-detection defect masks / areas / component stats
+        --K5--> SPC 9-vector (payload of the one all-reduce per step)
+
+It is the batched form of the reference's per-image chain
+``QualityControlDetector.predict`` (inference/detector.py:72-126) ->
+``EnsemblePredictor.predict`` (models/ensemble.py:71-105) -> ``YOLODetector.predict``
+(models/yolo_model.py:84-126) / ``ResNetClassifier.predict`` (models/resent_model.py:132-179) ->
+``ImageSegmentator.segment_defects`` (inference/segmentation.py:39-146).  One device->host copy of
+the packed detections sits in the middle (the reference syncs there too, models/yolo_model.py:133)
+because the ROI tables for K3/K4 are planned on the host.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import ffi, nets
+
+CLASS_NAMES = ["crack", "scratch", "dent", "discoloration", "contamination"]   # models/yolo_model.py:59-61
+DARK_CLASSES = (0, 1)            # crack, scratch -> THRESH_BINARY_INV (inference/segmentation.py:278)
+RESNET_MEAN = (0.485, 0.456, 0.406)
+RESNET_STD = (0.229, 0.224, 0.225)
+
+
+@dataclass
+class BatchResult:
+    n: int
+    det: np.ndarray                 # [n, max_det, 6] float32 (x1,y1,x2,y2,conf,cls), original-image coords
+    count: np.ndarray               # [n] int32
+    anchor: Optional[np.ndarray]    # [n, max_det] int32
+    roi_img: np.ndarray             # [K] image index of each ROI (detections with a non-empty box)
+    roi_det: np.ndarray             # [K] detection index inside its image
+    roi_box: np.ndarray             # [K,4] int32 x1,y1,x2,y2 (int()-truncated, models/yolo_model.py:138)
+    roi_probs: Optional[np.ndarray] = None      # [K, nc] float32 softmax of the ROI classifier
+    global_probs: Optional[np.ndarray] = None   # [n, nc] whole-frame classifier
+    seg_area: Optional[np.ndarray] = None       # [K] int64 kept mask pixels (== np.sum(mask>0))
+    seg_thr: Optional[np.ndarray] = None        # [K] Otsu thresholds
+    seg_ncomp: Optional[np.ndarray] = None      # [K]
+    spc: Optional[np.ndarray] = None            # [9] float64
+    seg: Optional[dict] = None                  # device tensors of K4 (mask/labels/stats) when requested
+    timings_ms: dict = field(default_factory=dict)
+
+
+class InspectionPipeline:
+    def __init__(self, yolo_scale: str = "s", nc: int = 5, device: int = 0, conf: float = 0.7, iou: float = 0.5,
+                 imgsz: int = 640, max_det: int = 300, net_dtype=torch.bfloat16, seed: int = 0,
+                 classify_rois: bool = True, classify_global: bool = True, letterbox_auto: bool = False):
+        self.qc = ffi.Context.current(device)
+        self.dev = torch.device("cuda", device)
+        self.nc, self.conf, self.iou, self.imgsz, self.max_det = nc, conf, iou, imgsz, max_det
+        self.net_dtype = net_dtype
+        self.classify_rois, self.classify_global = classify_rois, classify_global
+        self.letterbox_mode = ffi.QC_PRE_LETTERBOX_AUTO if letterbox_auto else ffi.QC_PRE_LETTERBOX
+        torch.backends.cudnn.benchmark = True
+        self.yolo = nets.build_yolo(yolo_scale, nc, seed).to(self.dev, net_dtype).to(memory_format=torch.channels_last)
+        self.resnet = nets.build_resnet50(nc, seed).to(self.dev, net_dtype).to(memory_format=torch.channels_last)
+        self.yolo_scale = yolo_scale
+        self._plans = {}
+        self.record = False          # bench.py: CUDA-event pairs around every stage
+        self.events = {}
+
+    class _Timed:
+        def __init__(self, pipe, name):
+            self.pipe, self.name = pipe, name
+
+        def __enter__(self):
+            if self.pipe.record:
+                self.s = torch.cuda.Event(enable_timing=True)
+                self.e = torch.cuda.Event(enable_timing=True)
+                self.s.record()
+            return self
+
+        def __exit__(self, *a):
+            if self.pipe.record:
+                self.e.record()
+                self.pipe.events.setdefault(self.name, []).append((self.s, self.e))
+
+    def _timed(self, name):
+        return InspectionPipeline._Timed(self, name)
+
+    def stage_ms(self) -> dict:
+        """mean milliseconds per call of every recorded stage (call after a synchronize)."""
+        return {k: float(np.mean([s.elapsed_time(e) for s, e in v])) for k, v in self.events.items() if v}
+
+    # thresholds can change at run time (api/routes.py:354-388 -> models/yolo_model.py:252-260)
+    def update_thresholds(self, confidence: Optional[float] = None, nms: Optional[float] = None):
+        if confidence is not None:
+            self.conf = confidence
+        if nms is not None:
+            self.iou = nms
+
+    def zero_detect_bias(self):
+        """Synthetic-bench helper: remove Detect's bias_init so injected logits set the scores."""
+        for seq in list(self.yolo.detect.cv2) + list(self.yolo.detect.cv3):
+            seq[-1].bias.data.zero_()
+
+    def plan_for(self, h: int, w: int) -> ffi.PrePlan:
+        key = (h, w)
+        if key not in self._plans:
+            self._plans[key] = self.qc.make_pre_plan(self.letterbox_mode, h, w, self.imgsz, self.imgsz)
+        return self._plans[key]
+
+    # ------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def detect(self, frames: torch.Tensor, inject: Optional[Sequence[torch.Tensor]] = None,
+               head_override: Optional[Sequence[torch.Tensor]] = None):
+        """K1 -> YOLOv8 -> K2 on a same-shape uint8 [n,h,w,3] CUDA batch.  The frames are in the
+        channel order the caller handed to ``QualityControlDetector.predict``; the reference flips
+        channels three times before the net sees them (inference/detector.py:234,
+        models/yolo_model.py:80, ultralytics [..., ::-1]) = one net flip -> swap_rb=True."""
+        n, h, w = frames.shape[:3]
+        plan = self.plan_for(h, w)
+        with self._timed("k1_preprocess"):
+            x = self.qc.preprocess(frames, plan, swap_rb=True, out_dtype=self.net_dtype)
+        if head_override is not None:
+            levels = list(head_override)
+        else:
+            with self._timed("yolo_net"):
+                levels = self.yolo(x.contiguous(memory_format=torch.channels_last))
+                if inject is not None:
+                    levels = [l + j for l, j in zip(levels, inject)]
+                levels = [l.contiguous() for l in levels]
+        p = self.qc.yolo_params(levels, self.nc, conf=self.conf, iou=self.iou, max_det=self.max_det, plan=plan)
+        with self._timed("k2_decode_nms"):
+            det, anchor, count, ncand = self.qc.yolo_decode_nms(levels, p)
+        return det, anchor, count, ncand
+
+    @staticmethod
+    def rois_from_detections(det: np.ndarray, count: np.ndarray):
+        """int() truncation of models/yolo_model.py:138; empty boxes are skipped like
+        inference/segmentation.py:82-83 (roi.size == 0)."""
+        n = det.shape[0]
+        k = np.arange(det.shape[1])[None, :] < count[:, None]
+        box = det[..., :4].astype(np.int32)                       # truncation toward zero (coords >= 0)
+        ok = k & (box[..., 2] > box[..., 0]) & (box[..., 3] > box[..., 1])
+        img, di = np.nonzero(ok)
+        return img.astype(np.int32), di.astype(np.int32), box[img, di]
+
+    @torch.no_grad()
+    def run(self, frames: torch.Tensor, inject=None, head_override=None, include_segmentation: bool = True,
+            keep_seg_tensors: bool = False, morph_iters: int = 1, min_area: int = 20) -> BatchResult:
+        qc = self.qc
+        n, h, w = frames.shape[:3]
+        det_d, anchor_d, count_d, _ = self.detect(frames, inject, head_override)
+        spc_d = qc.spc_stats(det_d, count_d)
+        # ---- the one mid-pipeline device->host copy (packed detections) -------------------------
+        det = det_d.cpu().numpy()
+        count = count_d.cpu().numpy()
+        roi_img, roi_det, roi_box = self.rois_from_detections(det, count)
+        K = len(roi_img)
+        res = BatchResult(n=n, det=det, count=count, anchor=None, roi_img=roi_img, roi_det=roi_det, roi_box=roi_box)
+
+        # ---- K3 + ResNet-50: ROI hand-off (models/ensemble.py:129-142) + whole-frame classifier ----
+        crops = []
+        if self.classify_global:
+            whole = np.zeros((n, 5), np.float32)
+            whole[:, 0] = np.arange(n)
+            whole[:, 3], whole[:, 4] = w, h
+            crops.append(whole)
+        if self.classify_rois and K:
+            r = np.concatenate((roi_img[:, None].astype(np.float32), roi_box.astype(np.float32)), 1)
+            crops.append(r)
+        probs = None
+        if crops:
+            rois = torch.from_numpy(np.ascontiguousarray(np.concatenate(crops))).to(self.dev, non_blocking=True)
+            # ResNet sees the caller's channel order (two flips: detector.py:234 + resent_model.py:123)
+            with self._timed("k3_roi_align"):
+                xin = qc.roi_align(frames, rois, swap_rb=False, mean=RESNET_MEAN, std=RESNET_STD,
+                                   out_dtype=self.net_dtype)
+            self.last_num_crops = int(rois.shape[0])
+            with self._timed("resnet_net"):
+                logits = self.resnet(xin.contiguous(memory_format=torch.channels_last))
+                probs = torch.softmax(logits.float(), 1)
+
+        # ---- K4 on every detection ROI ------------------------------------------------------------
+        seg = None
+        if include_segmentation and K:
+            cls = det[roi_img, roi_det, 5].astype(np.int32)
+            regs = [dict(img=int(roi_img[i]), x=int(roi_box[i, 0]), y=int(roi_box[i, 1]),
+                         w=int(roi_box[i, 2] - roi_box[i, 0]), h=int(roi_box[i, 3] - roi_box[i, 1]),
+                         polarity=0 if int(cls[i]) in DARK_CLASSES else 1, thr_scale=1.0, min_area=min_area)
+                    for i in range(K)]
+            # K4 reads gray as the reference does AFTER inference/detector.py:234 swapped the channels
+            with self._timed("k4_segment"):
+                seg = qc.segment(frames, regs, morph_iters=morph_iters, swap_rb=True,
+                                 want_mask=keep_seg_tensors, want_labels=keep_seg_tensors)
+            self.last_seg_pixels = int(seg["params"].total_pixels)
+
+        # ---- final device->host reads -------------------------------------------------------------
+        res.spc = spc_d.cpu().numpy()
+        if probs is not None:
+            pr = probs.cpu().numpy()
+            o = 0
+            if self.classify_global:
+                res.global_probs = pr[:n]
+                o = n
+            if self.classify_rois and K:
+                res.roi_probs = pr[o:o + K]
+        if seg is not None:
+            res.seg_area = seg["area"].cpu().numpy()
+            res.seg_thr = seg["thr"].cpu().numpy()
+            res.seg_ncomp = seg["ncomp"].cpu().numpy()
+            if keep_seg_tensors:
+                res.seg = seg
+        return res
