@@ -61,6 +61,12 @@ class SegParams(C.Structure):
                 ("total_chunks", C.c_int32), ("max_region_w", C.c_int32), ("max_region_h", C.c_int32)]
 
 
+SEG_REGION_DTYPE = np.dtype([("img", "i4"), ("x", "i4"), ("y", "i4"), ("w", "i4"), ("h", "i4"),
+                             ("polarity", "i4"), ("min_area", "i4"), ("max_comp", "i4"), ("thr_scale", "f8"),
+                             ("out_offset", "i8"), ("stats_offset", "i4"), ("band_offset", "i4"),
+                             ("chunk_offset", "i4"), ("bits_offset", "i4"), ("blk_offset", "i4")], align=True)
+assert SEG_REGION_DTYPE.itemsize == C.sizeof(SegRegion)
+
 _SIGS = {
     "qc_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
     "qc_destroy": (None, [C.c_void_p]),
@@ -318,29 +324,45 @@ class Context:
         return out
 
     # -- K4 --------------------------------------------------------------------------------
-    def segment_plan(self, regions: Sequence[dict], n: int, h: int, w: int, channels: int, img_stride: int,
+    def segment_plan(self, regions, n: int, h: int, w: int, channels: int, img_stride: int,
                      row_stride: int, morph_iters: int = 1, swap_rb: bool = False):
-        """regions: dicts with img,x,y,w,h and optional polarity(1), thr_scale(1.0), min_area(20), max_comp."""
-        R = len(regions)
-        arr = (SegRegion * max(R, 1))()
-        for i, r in enumerate(regions):
-            a = arr[i]
-            a.img, a.x, a.y, a.w, a.h = int(r["img"]), int(r["x"]), int(r["y"]), int(r["w"]), int(r["h"])
-            a.polarity = int(r.get("polarity", 1))
-            a.thr_scale = float(r.get("thr_scale", 1.0))
-            a.min_area = int(r.get("min_area", 20))
-            nblk = ((a.w + 1) // 2) * ((a.h + 1) // 2)
-            a.max_comp = int(r.get("max_comp", min(nblk + 1, 1 << 16)))
+        """regions: list of dicts, or a dict of equal-length arrays, with img,x,y,w,h and optional
+        polarity(1), thr_scale(1.0), min_area(20), max_comp.  Returns (recarray of planned
+        qc_seg_region, SegParams)."""
+        if isinstance(regions, dict):
+            cols = regions
+            R = len(np.atleast_1d(cols["img"]))
+        else:
+            R = len(regions)
+            keys = ("img", "x", "y", "w", "h", "polarity", "thr_scale", "min_area", "max_comp")
+            cols = {k: [r[k] for r in regions] for k in keys if R and all(k in r for r in regions)}
+            for k in keys:                      # per-region optional keys
+                if k not in cols and R and any(k in r for r in regions):
+                    dflt = {"polarity": 1, "thr_scale": 1.0, "min_area": 20}.get(k)
+                    cols[k] = [r.get(k, dflt) for r in regions]
+        arr = np.zeros(max(R, 1), SEG_REGION_DTYPE)
+        if R:
+            for k in ("img", "x", "y", "w", "h"):
+                arr[k][:R] = np.asarray(cols[k], np.int64)
+            arr["polarity"][:R] = np.asarray(cols.get("polarity", 1), np.int64)
+            arr["thr_scale"][:R] = np.asarray(cols.get("thr_scale", 1.0), np.float64)
+            arr["min_area"][:R] = np.asarray(cols.get("min_area", 20), np.int64)
+            nblk = ((arr["w"][:R].astype(np.int64) + 1) // 2) * ((arr["h"][:R].astype(np.int64) + 1) // 2)
+            if "max_comp" in cols and cols["max_comp"] is not None and not (
+                    isinstance(cols["max_comp"], list) and any(v is None for v in cols["max_comp"])):
+                arr["max_comp"][:R] = np.asarray(cols["max_comp"], np.int64)
+            else:
+                arr["max_comp"][:R] = np.minimum(nblk + 1, 1 << 16)
         p = SegParams()
         p.n, p.h, p.w, p.channels = n, h, w, channels
         p.img_stride, p.row_stride, p.morph_iters = img_stride, row_stride, morph_iters
         p.swap_rb = int(swap_rb)
-        rc = self.lib.qc_segment_plan(arr, R, C.byref(p))
+        rc = self.lib.qc_segment_plan(arr.ctypes.data_as(C.POINTER(SegRegion)), R, C.byref(p))
         if rc != 0:
             raise QcGraftError(f"qc_segment_plan failed: {rc} (region outside the image?)")
-        return arr, p
+        return arr.view(np.recarray), p
 
-    def segment(self, imgs: torch.Tensor, regions: Sequence[dict], morph_iters: int = 1, want_mask: bool = True,
+    def segment(self, imgs: torch.Tensor, regions, morph_iters: int = 1, want_mask: bool = True,
                 want_labels: bool = True, swap_rb: bool = False):
         """imgs: uint8 CUDA [n,h,w] (gray) or [n,h,w,3] (RGB).  Returns dict of device tensors + the plan."""
         assert imgs.is_cuda and imgs.dtype == torch.uint8 and imgs.dim() in (3, 4)
@@ -357,8 +379,7 @@ class Context:
                         stats=torch.zeros((0, 5), dtype=torch.int32, device=dev),
                         thr=torch.zeros(0, dtype=torch.int32, device=dev),
                         area=torch.zeros(0, dtype=torch.int64, device=dev))
-        host = np.frombuffer(arr, dtype=np.uint8, count=C.sizeof(SegRegion) * R)
-        regs_dev = torch.from_numpy(host.copy()).to(dev, non_blocking=False)
+        regs_dev = torch.from_numpy(arr[:R].view(np.uint8).reshape(-1)).to(dev, non_blocking=False)
         mask = torch.empty(p.total_pixels, dtype=torch.uint8, device=dev) if want_mask else None
         labels = torch.empty(p.total_pixels, dtype=torch.int32, device=dev) if want_labels else None
         ncomp = torch.empty(R, dtype=torch.int32, device=dev)

@@ -160,3 +160,44 @@ def yolo_gflops(scale: str, H: int, W: int) -> float:
     """Published YOLOv8 forward cost at 640^2 (8.7/28.6/78.9 GFLOP), scaled by area."""
     base = {"n": 8.7, "s": 28.6, "m": 78.9}[scale]
     return base * (H * W) / (640 * 640)
+
+
+class GraphedNet:
+    """CUDA-graph replay of a conv net at fixed input shapes (one graph per shape, captured lazily
+    after a cuDNN-autotune warm-up).  The producer kernel writes straight into ``input_buffer(shape)``;
+    ``run(shape)`` replays and returns the static outputs (valid until the next replay)."""
+
+    def __init__(self, module: nn.Module, device, dtype, channels_last: bool = True):
+        self.module, self.device, self.dtype, self.cl = module, device, dtype, channels_last
+        self.slots = {}
+
+    def input_buffer(self, shape) -> torch.Tensor:
+        shape = tuple(int(v) for v in shape)
+        if shape not in self.slots:
+            self.slots[shape] = {"in": torch.zeros(shape, dtype=self.dtype, device=self.device), "graph": None}
+        return self.slots[shape]["in"]
+
+    def _fwd(self, x):
+        if self.cl:
+            x = x.contiguous(memory_format=torch.channels_last)
+        return self.module(x)
+
+    @torch.no_grad()
+    def run(self, shape):
+        shape = tuple(int(v) for v in shape)
+        slot = self.slots[shape]
+        if slot["graph"] is None:
+            cur = torch.cuda.current_stream(self.device)
+            side = torch.cuda.Stream(self.device)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                for _ in range(3):                     # cuDNN autotune + allocator warm-up
+                    self._fwd(slot["in"])
+            cur.wait_stream(side)
+            torch.cuda.synchronize(self.device)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                slot["out"] = self._fwd(slot["in"])
+            slot["graph"] = g
+        slot["graph"].replay()
+        return slot["out"]
