@@ -13,11 +13,12 @@
 //
 // Pipeline (all HBM/L2-bound integer work, no tensor cores):
 //   k4_init      zero histograms / area, sentinel-initialise stats rows
-//   k4_hist      [RGB->gray] + 256-bin histogram, lane-private shared-memory counters
-//   k4_otsu      cv2's getThreshVal_Otsu_8u recurrence in float64 (sequential, one thread/region)
-//   k4_mask      threshold -> bit-packed rows in smem -> close/open (4*iters cross steps with
-//                halo) -> global bit rows + union-find parent init (horizontal runs pre-linked)
-//   k4_merge     block-based union-find (atomicMin, roots = min block index) over L2
+//   k4_hist      [RGB->gray] + 256-bin histogram: 128-bit loads, per-warp lane-private u16 counters
+//   k4_otsu      parallel Otsu from exact integer prefix sums; replays cv2's sequential float64
+//                recurrence only when the maximum is not decisive (ties / plateaus)
+//   k4_mask_ccl  threshold (128-bit loads) -> bit-packed rows in smem -> close/open (4*iters cross
+//                steps with halo) -> global bit rows; band-local 2x2-block union-find in smem
+//   k4_border    unions across band borders (atomicMin in L2, roots = min block index)
 //   k4_compress  path compression + per-1024-block root counts
 //   k4_scan      exclusive scan of the counts per region -> chunk bases, ncomp
 //   k4_rank      root -> label (1-based rank in block-raster order)
@@ -106,57 +107,114 @@ __global__ void k4_init(const qc_seg_region* __restrict__ regs, int R, unsigned*
 }
 
 // ------------------------------------------------------------------------------------------
+// Histogram.  Warp per pixel row.  Big gray bands count into per-warp lane-private u16 tables
+// ([bin][lane], no atomics, no intra-warp address collisions); small bands (ROIs) use one
+// 256-bin table with shared-memory atomics so the zero/reduce overhead stays small.
+constexpr int K4_HIST_BIG_PX = 8192;
+constexpr int K4_HIST_SMEM = (K4_THREADS / 32) * 256 * 32 * 2;   // 128 KB
+
 __global__ void __launch_bounds__(K4_THREADS)
 k4_hist(Img im, const qc_seg_region* __restrict__ regs, int R, int total_bands, unsigned* __restrict__ hist,
         uint8_t* __restrict__ gray_ws) {
-    __shared__ unsigned sh[256 * 32];   // [bin][lane] -> bank == lane: no intra-warp conflicts
+    extern __shared__ __align__(16) unsigned char hsm[];
+    __shared__ unsigned sh_small[256];
     __shared__ int s_r;
-    const int tid = threadIdx.x, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    unsigned short* tab = reinterpret_cast<unsigned short*>(hsm) + warp * 8192 + lane;   // [bin*32]
     for (int t = blockIdx.x; t < total_bands; t += gridDim.x) {
-        if (tid == 0) s_r = find_region(t, R, [&](int i) { return regs[i].band_offset; });
-        for (int i = tid; i < 256 * 32; i += K4_THREADS) sh[i] = 0;
         __syncthreads();
-        const qc_seg_region rg = regs[s_r];
+        if (tid == 0) s_r = find_region(t, R, [&](int i) { return regs[i].band_offset; });
+        __syncthreads();
+        const int r = s_r;
+        const qc_seg_region rg = regs[r];
         const int y0 = (t - rg.band_offset) * K4_BAND_ROWS;
         const int y1 = min(y0 + K4_BAND_ROWS, rg.h);
+        const bool big = (y1 - y0) * rg.w > K4_HIST_BIG_PX;
+        if (big) {
+            uint4* z = reinterpret_cast<uint4*>(hsm) + warp * 1024;
+            for (int i = lane; i < 1024; i += 32) z[i] = make_uint4(0, 0, 0, 0);
+        } else {
+            sh_small[tid] = 0;
+        }
+        __syncthreads();
         const uint8_t* ibase = im.data + (long long)rg.img * im.img_stride;
-        const int npx = (y1 - y0) * rg.w;
-        for (int i = tid; i < npx; i += K4_THREADS) {
-            const int yy = i / rg.w, xx = i - yy * rg.w;
-            const uint8_t* p = ibase + (long long)(rg.y + y0 + yy) * im.row_stride + (long long)(rg.x + xx) * im.channels;
-            unsigned g;
-            if (im.channels == 3) {
-                // cv2 RGB2GRAY fixed point: (R*9798 + G*19235 + B*3735 + 2^14) >> 15
-                const unsigned c0 = __ldg(p), c1 = __ldg(p + 1), c2 = __ldg(p + 2);
-                g = (9798u * (im.swap_rb ? c2 : c0) + 19235u * c1 + 3735u * (im.swap_rb ? c0 : c2) + 16384u) >> 15;
-                gray_ws[rg.out_offset + (long long)(y0 + yy) * rg.w + xx] = (uint8_t)g;
+        for (int y = y0 + warp; y < y1; y += K4_THREADS / 32) {
+            const uint8_t* p = ibase + (long long)(rg.y + y) * im.row_stride + (long long)rg.x * im.channels;
+            if (im.channels == 1) {
+                // aligned 16-byte body + scalar head/tail
+                const int head = min(rg.w, (int)((16 - (reinterpret_cast<uintptr_t>(p) & 15)) & 15));
+                const int nvec = (rg.w - head) >> 4;
+                for (int x = lane; x < head; x += 32) {
+                    const unsigned g = __ldg(p + x);
+                    if (big) tab[g << 5]++; else atomicAdd(&sh_small[g], 1u);
+                }
+                const uint4* pv = reinterpret_cast<const uint4*>(p + head);
+                for (int s0 = 0; s0 < nvec; s0 += 128) {
+                    uint4 v[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int sidx = s0 + j * 32 + lane;
+                        v[j] = sidx < nvec ? __ldg(pv + sidx) : make_uint4(0, 0, 0, 0);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        if (s0 + j * 32 + lane < nvec) {
+                            const unsigned w4[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+#pragma unroll
+                            for (int k = 0; k < 16; ++k) {
+                                const unsigned g = (w4[k >> 2] >> (8 * (k & 3))) & 255u;
+                                if (big) tab[g << 5]++; else atomicAdd(&sh_small[g], 1u);
+                            }
+                        }
+                    }
+                }
+                for (int x = head + nvec * 16 + lane; x < rg.w; x += 32) {
+                    const unsigned g = __ldg(p + x);
+                    if (big) tab[g << 5]++; else atomicAdd(&sh_small[g], 1u);
+                }
             } else {
-                g = __ldg(p);
+                uint8_t* gq = gray_ws + rg.out_offset + (long long)y * rg.w;
+                for (int x = lane; x < rg.w; x += 32) {
+                    // cv2 RGB2GRAY fixed point: (R*9798 + G*19235 + B*3735 + 2^14) >> 15
+                    const unsigned c0 = __ldg(p + 3 * x), c1 = __ldg(p + 3 * x + 1), c2 = __ldg(p + 3 * x + 2);
+                    const unsigned g =
+                        (9798u * (im.swap_rb ? c2 : c0) + 19235u * c1 + 3735u * (im.swap_rb ? c0 : c2) + 16384u) >> 15;
+                    gq[x] = (uint8_t)g;
+                    if (big) tab[g << 5]++; else atomicAdd(&sh_small[g], 1u);
+                }
             }
-            atomicAdd(&sh[(g << 5) + lane], 1u);
         }
         __syncthreads();
-        // reduce the 32 lane columns of each bin, one global atomic per non-empty bin
         {
+            const int bin = tid;            // K4_THREADS == 256 bins
             unsigned s = 0;
-            const int bin = tid;    // K4_THREADS == 256
-#pragma unroll 8
-            for (int k = 0; k < 32; ++k) s += sh[(bin << 5) + ((k + lane) & 31)];
-            if (s) atomicAdd(&hist[(long long)s_r * 256 + bin], s);
+            if (big) {
+                const unsigned* t32 = reinterpret_cast<const unsigned*>(hsm);
+#pragma unroll
+                for (int w = 0; w < K4_THREADS / 32; ++w) {
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) {
+                        // word j of row `bin`: rotate by bin>>1 so the 32 bins of a warp hit 32 banks
+                        const unsigned v = t32[w * 4096 + bin * 16 + ((k + (bin >> 1)) & 15)];
+                        s += (v & 0xFFFFu) + (v >> 16);
+                    }
+                }
+            } else {
+                s = sh_small[bin];
+            }
+            if (s) atomicAdd(&hist[(long long)r * 256 + bin], s);
         }
-        __syncthreads();
     }
 }
 
 // ------------------------------------------------------------------------------------------
-__global__ void k4_otsu(const qc_seg_region* __restrict__ regs, int R, const unsigned* __restrict__ hist,
-                        int* __restrict__ cmp, int* __restrict__ out_thr) {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= R) return;
-    const qc_seg_region rg = regs[r];
-    const unsigned* h = hist + (long long)r * 256;
-    // cv2 getThreshVal_Otsu_8u, float64, same operation order (no FMA contraction)
-    const double scale = __ddiv_rn(1.0, (double)((long long)rg.w * rg.h));
+// Otsu threshold, bit-exact with cv2's getThreshVal_Otsu_8u.  cv2's recurrence is sequential in
+// float64; 256 threads first evaluate the between-class variance of every split from exact integer
+// prefix sums.  If the best split beats every other by a relative 1e-9 (rounding in either
+// formulation is ~1e-13) its index IS cv2's answer; otherwise (plateaus of two-level images,
+// ties, bins on the FLT_EPSILON skip boundary) one thread replays cv2's exact recurrence.
+__device__ int otsu_serial_cv2(const unsigned* h, long long npix) {
+    const double scale = __ddiv_rn(1.0, (double)npix);
     double mu = 0.0;
     for (int i = 0; i < 256; ++i) mu = __dadd_rn(mu, __dmul_rn((double)i, (double)h[i]));
     mu = __dmul_rn(mu, scale);
@@ -174,18 +232,103 @@ __global__ void k4_otsu(const qc_seg_region* __restrict__ regs, int R, const uns
         const double sigma = __dmul_rn(__dmul_rn(__dmul_rn(q1, q2), d), d);
         if (sigma > max_sigma) { max_sigma = sigma; max_val = i; }
     }
-    out_thr[r] = max_val;
-    int lo, hi;
-    if (rg.thr_scale == 1.0) {
-        if (rg.polarity) { lo = max_val + 1; hi = 255; }      // cv2 THRESH_BINARY: v > t
-        else { lo = 0; hi = max_val; }                        // THRESH_BINARY_INV: v <= t
-    } else {
-        const double T = __dmul_rn((double)max_val, rg.thr_scale);   // python: threshold * factor
-        if (rg.polarity) { lo = (int)floor(T) + 1; hi = 255; }       // v > T
-        else { lo = 0; hi = (int)ceil(T) - 1; }                      // v < T
+    return max_val;
+}
+
+__global__ void __launch_bounds__(256)
+k4_otsu(const qc_seg_region* __restrict__ regs, int R, const unsigned* __restrict__ hist,
+        int* __restrict__ cmp, int* __restrict__ out_thr) {
+    __shared__ unsigned long long sw[8], ss[8];
+    __shared__ double s_best[8];
+    __shared__ int s_bidx[8], s_close[8], s_flags[8];
+    __shared__ unsigned s_h[256];
+    __shared__ int s_result;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int r = blockIdx.x; r < R; r += gridDim.x) {
+        const qc_seg_region rg = regs[r];
+        const unsigned h = hist[(long long)r * 256 + tid];
+        __syncthreads();
+        s_h[tid] = h;
+        unsigned long long w1 = h, s1 = (unsigned long long)h * tid;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long a = __shfl_up_sync(0xffffffffu, w1, o), b = __shfl_up_sync(0xffffffffu, s1, o);
+            if (lane >= o) { w1 += a; s1 += b; }
+        }
+        if (lane == 31) { sw[warp] = w1; ss[warp] = s1; }
+        __syncthreads();
+        unsigned long long N = 0, S = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            if (k < warp) { w1 += sw[k]; s1 += ss[k]; }
+            N += sw[k]; S += ss[k];
+        }
+        double sig = -1.0;
+        int flags = 0;     // bit0: some bin not skipped, bit1: a bin sits on the skip boundary
+        if (N > 0) {
+            const double q1 = (double)w1 / (double)N, q2 = 1.0 - q1;
+            const double mn = fmin(q1, q2), mx = fmax(q1, q2);
+            const double eps = (double)FLT_EPSILON;
+            if (fabs(mn - eps) <= 1e-3 * eps || fabs(mx - (1.0 - eps)) <= 1e-3 * eps) flags |= 2;
+            if (!(mn < eps || mx > 1.0 - eps)) {
+                const double mu1 = (double)s1 / (double)w1;
+                const double mu2 = (double)(S - s1) / (double)(N - w1);
+                const double d = mu1 - mu2;
+                sig = q1 * q2 * d * d;
+                flags |= 1;
+            }
+        }
+        // first maximum over the 256 splits
+        double b = sig;
+        int bi = tid;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ob = __shfl_xor_sync(0xffffffffu, b, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ob > b || (ob == b && oi < bi)) { b = ob; bi = oi; }
+        }
+        int fl = flags;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) fl |= __shfl_xor_sync(0xffffffffu, fl, o);
+        if (lane == 0) { s_best[warp] = b; s_bidx[warp] = bi; s_flags[warp] = fl; }
+        __syncthreads();
+        b = s_best[0]; bi = s_bidx[0]; fl = s_flags[0];
+#pragma unroll
+        for (int k = 1; k < 8; ++k) {
+            if (s_best[k] > b || (s_best[k] == b && s_bidx[k] < bi)) { b = s_best[k]; bi = s_bidx[k]; }
+            fl |= s_flags[k];
+        }
+        const bool close = sig >= 0.0 && tid != bi && sig >= b * (1.0 - 1e-9);
+        const unsigned cm = __ballot_sync(0xffffffffu, close);
+        if (lane == 0) s_close[warp] = __popc(cm);
+        __syncthreads();
+        int nclose = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) nclose += s_close[k];
+        if (tid == 0) {
+            int t;
+            if (!(fl & 1) && !(fl & 2)) t = 0;                                   // every split skipped
+            else if (b > 0.0 && nclose == 0 && !(fl & 2)) t = bi;                // decisive maximum
+            else t = otsu_serial_cv2(s_h, (long long)rg.w * rg.h);               // replay cv2 exactly
+            s_result = t;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            const int max_val = s_result;
+            out_thr[r] = max_val;
+            int lo, hi;
+            if (rg.thr_scale == 1.0) {
+                if (rg.polarity) { lo = max_val + 1; hi = 255; }      // cv2 THRESH_BINARY: v > t
+                else { lo = 0; hi = max_val; }                        // THRESH_BINARY_INV: v <= t
+            } else {
+                const double T = __dmul_rn((double)max_val, rg.thr_scale);   // python: threshold * factor
+                if (rg.polarity) { lo = (int)floor(T) + 1; hi = 255; }       // v > T
+                else { lo = 0; hi = (int)ceil(T) - 1; }                      // v < T
+            }
+            cmp[2 * r] = lo;
+            cmp[2 * r + 1] = hi;
+        }
     }
-    cmp[2 * r] = lo;
-    cmp[2 * r + 1] = hi;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -194,10 +337,9 @@ struct BitRows {
     const unsigned* buf;
     int wpr, w;
     int row_lo, row_hi;     // region rows held in buf: [row_lo, row_hi)
-    int h;                  // region height
-    // word of region row y (border: rows/words outside the REGION read as `ob`; rows outside the
-    // buffer but inside the region are halo garbage and read as `ob` too -- they never reach the
-    // band's own rows because the halo is 4*iters deep)
+    // word of region row y (rows/words outside the REGION read as the op's border value `ob`; rows
+    // outside the buffer but inside the region are halo garbage and read as `ob` too -- they never
+    // reach the band's own rows because the halo is 4*iters deep)
     __device__ __forceinline__ unsigned rd(int y, int wx, bool ob) const {
         if (y < row_lo || y >= row_hi || wx < 0 || wx >= wpr) return ob ? 0xFFFFFFFFu : 0u;
         unsigned v = buf[(y - row_lo) * wpr + wx];
@@ -206,13 +348,32 @@ struct BitRows {
     }
 };
 
+// union-find on shared-memory labels (roots = minimum local index)
+__device__ __forceinline__ int suf_find(volatile int* L, int x) {
+    int p = L[x];
+    while (p != x) { x = p; p = L[x]; }
+    return x;
+}
+__device__ __forceinline__ void suf_union(int* L, int a, int b) {
+    bool done;
+    do {
+        a = suf_find(L, a);
+        b = suf_find(L, b);
+        if (a < b) { const int old = atomicMin(L + b, a); done = (old == b); b = old; }
+        else if (b < a) { const int old = atomicMin(L + a, b); done = (old == a); a = old; }
+        else done = true;
+    } while (!done);
+}
+
+// threshold -> morphology -> bit rows + band-local connected components (all in shared memory)
 __global__ void __launch_bounds__(K4_THREADS)
-k4_mask(Img im, const qc_seg_region* __restrict__ regs, int R, int total_bands, int iters,
-        const int* __restrict__ cmp, const uint8_t* __restrict__ gray_ws, unsigned* __restrict__ bits,
-        int* __restrict__ parent, int buf_words) {
-    extern __shared__ unsigned sm[];
+k4_mask_ccl(Img im, const qc_seg_region* __restrict__ regs, int R, int total_bands, int iters,
+            const int* __restrict__ cmp, const uint8_t* __restrict__ gray_ws, unsigned* __restrict__ bits,
+            int* __restrict__ parent, int buf_words) {
+    extern __shared__ __align__(16) unsigned sm[];
     unsigned* bufA = sm;
     unsigned* bufB = sm + buf_words;
+    int* lab = reinterpret_cast<int*>(sm + 2 * buf_words);
     __shared__ int s_r;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int halo = 4 * iters;
@@ -228,22 +389,40 @@ k4_mask(Img im, const qc_seg_region* __restrict__ regs, int R, int total_bands, 
         const int row_lo = max(y0 - halo, 0), row_hi = min(y1 + halo, rg.h);
         const int nrows = row_hi - row_lo;
         const int lo = cmp[2 * r], hi = cmp[2 * r + 1];
-        // ---- threshold into bit rows (warp per word: 32 pixels, one ballot) ------------------
+        // ---- threshold into bit rows: a lane turns 16 pixels into 16 bits, lane pairs form words ----
         const uint8_t* gbase;
         long long gpitch;
         if (im.channels == 3) { gbase = gray_ws + rg.out_offset; gpitch = rg.w; }
         else { gbase = im.data + (long long)rg.img * im.img_stride + (long long)rg.y * im.row_stride + rg.x; gpitch = im.row_stride; }
-        for (int wi = warp; wi < nrows * wpr; wi += K4_THREADS / 32) {
-            const int yy = wi / wpr, wx = wi - yy * wpr;
-            const int x = wx * 32 + lane;
-            bool fg = false;
-            if (x < rg.w) {
-                const int v = im.channels == 3 ? (int)gbase[(long long)(row_lo + yy) * gpitch + x]
-                                               : (int)__ldg(gbase + (long long)(row_lo + yy) * gpitch + x);
-                fg = v >= lo && v <= hi;
+        const int segs = 2 * wpr;                     // 16-pixel segments per row (last ones may be partial/empty)
+        for (int yy = warp; yy < nrows; yy += K4_THREADS / 32) {
+            const uint8_t* p = gbase + (long long)(row_lo + yy) * gpitch;
+            const bool al = (reinterpret_cast<uintptr_t>(p) & 15) == 0;
+            for (int s0 = 0; s0 < segs; s0 += 32) {
+                const int sg = s0 + lane;
+                const int x0 = sg * 16;
+                unsigned b16 = 0;
+                if (sg < segs && x0 < rg.w) {
+                    if (al && x0 + 16 <= rg.w) {
+                        const uint4 v = im.channels == 3 ? *reinterpret_cast<const uint4*>(p + x0)
+                                                         : __ldg(reinterpret_cast<const uint4*>(p + x0));
+                        const unsigned w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                        for (int k = 0; k < 16; ++k) {
+                            const int g = (int)((w4[k >> 2] >> (8 * (k & 3))) & 255u);
+                            b16 |= (unsigned)(g >= lo && g <= hi) << k;
+                        }
+                    } else {
+                        const int nv = min(16, rg.w - x0);
+                        for (int k = 0; k < nv; ++k) {
+                            const int g = (int)p[x0 + k];
+                            b16 |= (unsigned)(g >= lo && g <= hi) << k;
+                        }
+                    }
+                }
+                const unsigned hi16 = __shfl_down_sync(0xffffffffu, b16, 1);
+                if (!(lane & 1) && sg < segs) bufA[yy * wpr + (sg >> 1)] = b16 | (hi16 << 16);
             }
-            const unsigned word = __ballot_sync(0xffffffffu, fg);
-            if (lane == 0) bufA[wi] = word;
         }
         __syncthreads();
         // ---- close (dilate^k, erode^k) then open (erode^k, dilate^k), 3x3 cross ----------------
@@ -252,14 +431,12 @@ k4_mask(Img im, const qc_seg_region* __restrict__ regs, int R, int total_bands, 
         for (int step = 0; step < 4 * iters; ++step) {
             const int phase = step / iters;              // 0: dilate, 1: erode, 2: erode, 3: dilate
             const bool erode = (phase == 1 || phase == 2);
-            BitRows br{src, wpr, rg.w, row_lo, row_hi, rg.h};
+            BitRows br{src, wpr, rg.w, row_lo, row_hi};
             for (int wi = tid; wi < nrows * wpr; wi += K4_THREADS) {
                 const int yy = wi / wpr, wx = wi - yy * wpr;
                 const int y = row_lo + yy;
                 const unsigned c = br.rd(y, wx, erode);
                 const unsigned l = br.rd(y, wx - 1, erode), rr = br.rd(y, wx + 1, erode);
-                // region-border rows read as the op's border value; buffer-edge rows inside the
-                // region read the same (halo garbage, discarded)
                 const unsigned up = br.rd(y - 1, wx, erode), dn = br.rd(y + 1, wx, erode);
                 const unsigned xl = (c << 1) | (l >> 31);      // pixel x-1 aligned to x
                 const unsigned xr = (c >> 1) | (rr << 31);     // pixel x+1 aligned to x
@@ -270,36 +447,63 @@ k4_mask(Img im, const qc_seg_region* __restrict__ regs, int R, int total_bands, 
             __syncthreads();
             unsigned* tmp = src; src = dst; dst = tmp;
         }
-        // ---- emit the band's own rows + union-find parent init ---------------------------------
-        const int bw = bw_of(rg);
+        // ---- emit the band's own bit rows ---------------------------------------------------------
         for (int wi = tid; wi < (y1 - y0) * wpr; wi += K4_THREADS) {
             const int yy = wi / wpr, wx = wi - yy * wpr;
             bits[rg.bits_offset + (long long)(y0 + yy) * wpr + wx] = src[(y0 - row_lo + yy) * wpr + wx];
         }
-        const int by0 = y0 >> 1, by1 = (y1 + 1) >> 1;
-        for (int ci = tid; ci < (by1 - by0) * wpr; ci += K4_THREADS) {
-            const int byy = ci / wpr, wx = ci - byy * wpr;
-            const int by = by0 + byy;
-            const int ry = 2 * by - row_lo;
-            const unsigned r0 = src[ry * wpr + wx];
-            const unsigned r1 = (2 * by + 1 < rg.h) ? src[(ry + 1) * wpr + wx] : 0u;
-            const unsigned v = r0 | r1;
-            int* prow = parent + rg.blk_offset + (long long)by * bw + wx * 16;
-            int head = 0;
-#pragma unroll
-            for (int k = 0; k < 16; ++k) {
-                if (wx * 16 + k < bw) {
-                    const unsigned bits2 = (v >> (2 * k)) & 3u;
-                    int val = -1;
-                    if (bits2) {
-                        // linked to the previous block of this word when column 2k and column 2k-1 both hold a pixel
-                        const bool link = k > 0 && ((v >> (2 * k)) & 1u) && ((v >> (2 * k - 1)) & 1u);
-                        if (!link) head = rg.blk_offset + by * bw + wx * 16 + k;
-                        val = head;
-                    }
-                    prow[k] = val;
+        // ---- band-local CCL on 2x2 blocks (8-connectivity), shared-memory union-find -----------------
+        const int bw = bw_of(rg), bwp = wpr * 16;
+        const int by0 = y0 >> 1, nbr = ((y1 + 1) >> 1) - by0;
+        const unsigned* band = src + (y0 - row_lo) * wpr;          // band rows only: no look above y0
+        const int brows = y1 - y0;
+        auto rowword = [&](int ry, int wx) -> unsigned {           // ry relative to y0
+            return (ry < 0 || ry >= brows || wx < 0 || wx >= wpr) ? 0u : band[ry * wpr + wx];
+        };
+        for (int i = tid; i < nbr * bwp; i += K4_THREADS) {
+            const int byy = i / bwp, bx = i - byy * bwp;
+            const unsigned v = rowword(2 * byy, bx >> 4) | rowword(2 * byy + 1, bx >> 4);
+            lab[i] = ((v >> (2 * (bx & 15))) & 3u) ? i : -1;
+        }
+        __syncthreads();
+        for (int i = tid; i < nbr * bwp; i += K4_THREADS) {
+            if (lab[i] < 0) continue;
+            const int byy = i / bwp, bx = i - byy * bwp;
+            const int wx = bx >> 4, k = bx & 15;
+            const unsigned r0 = rowword(2 * byy, wx), r1 = rowword(2 * byy + 1, wx);
+            const unsigned a = (r0 >> (2 * k)) & 1u, b = (r0 >> (2 * k + 1)) & 1u;
+            const unsigned c = (r1 >> (2 * k)) & 1u;
+            // left block: its right column vs my left column
+            unsigned lcol;
+            if (k > 0) lcol = ((r0 | r1) >> (2 * k - 1)) & 1u;
+            else lcol = (rowword(2 * byy, wx - 1) | rowword(2 * byy + 1, wx - 1)) >> 31;
+            if ((a | c) && lcol) suf_union(lab, i, i - 1);
+            if (byy > 0) {
+                const unsigned u = rowword(2 * byy - 1, wx);
+                const unsigned u0 = (u >> (2 * k)) & 1u, u1 = (u >> (2 * k + 1)) & 1u;
+                if ((a | b) && (u0 | u1)) suf_union(lab, i, i - bwp);
+                // up-left / up-right only when not already implied through the upper block
+                if (a && !u0) {
+                    const unsigned um = k > 0 ? (u >> (2 * k - 1)) & 1u : rowword(2 * byy - 1, wx - 1) >> 31;
+                    if (um) suf_union(lab, i, i - bwp - 1);
+                }
+                if (b && !u1) {
+                    const unsigned up2 = k < 15 ? (u >> (2 * k + 2)) & 1u : rowword(2 * byy - 1, wx + 1) & 1u;
+                    if (up2) suf_union(lab, i, i - bwp + 1);
                 }
             }
+        }
+        __syncthreads();
+        for (int i = tid; i < nbr * bwp; i += K4_THREADS) {
+            const int byy = i / bwp, bx = i - byy * bwp;
+            if (bx >= bw) continue;
+            int g = -1;
+            if (lab[i] >= 0) {
+                const int rt = suf_find(lab, i);
+                const int rby = rt / bwp, rbx = rt - rby * bwp;
+                g = rg.blk_offset + (by0 + rby) * bw + rbx;
+            }
+            parent[rg.blk_offset + (long long)(by0 + byy) * bw + bx] = g;
         }
     }
 }
@@ -321,9 +525,11 @@ __device__ __forceinline__ void uf_union(int* L, int a, int b) {
     } while (!done);
 }
 
+// stitches bands together: the first block row of every band (except a region's first) is united
+// with the block row above it, in global memory
 __global__ void __launch_bounds__(K4_THREADS)
-k4_merge(const qc_seg_region* __restrict__ regs, int R, int total_bands, const unsigned* __restrict__ bits,
-         int* __restrict__ parent) {
+k4_border(const qc_seg_region* __restrict__ regs, int R, int total_bands, const unsigned* __restrict__ bits,
+          int* __restrict__ parent) {
     __shared__ int s_r;
     const int tid = threadIdx.x;
     for (int t = blockIdx.x; t < total_bands; t += gridDim.x) {
@@ -331,47 +537,37 @@ k4_merge(const qc_seg_region* __restrict__ regs, int R, int total_bands, const u
         if (tid == 0) s_r = find_region(t, R, [&](int i) { return regs[i].band_offset; });
         __syncthreads();
         const qc_seg_region rg = regs[s_r];
-        const int wpr = wpr_of(rg), bw = bw_of(rg);
         const int y0 = (t - rg.band_offset) * K4_BAND_ROWS;
-        const int y1 = min(y0 + K4_BAND_ROWS, rg.h);
-        const int by0 = y0 >> 1, by1 = (y1 + 1) >> 1;
+        if (y0 == 0) continue;
+        const int wpr = wpr_of(rg), bw = bw_of(rg);
+        const int by = y0 >> 1;
         const unsigned* B = bits + rg.bits_offset;
         auto word = [&](int y, int wx) -> unsigned {
             return (y < 0 || y >= rg.h || wx < 0 || wx >= wpr) ? 0u : __ldg(B + (long long)y * wpr + wx);
         };
-        for (int ci = tid; ci < (by1 - by0) * wpr; ci += K4_THREADS) {
-            const int byy = ci / wpr, wx = ci - byy * wpr;
-            const int by = by0 + byy;
-            const unsigned r0 = word(2 * by, wx), r1 = word(2 * by + 1, wx);
-            const unsigned v = r0 | r1;
-            if (!v) continue;
-            const unsigned u = word(2 * by - 1, wx);
-            // neighbours across the word boundary
-            const unsigned vl = (word(2 * by, wx - 1) | word(2 * by + 1, wx - 1)) >> 31;   // column x0-1 of this block row
-            const unsigned ul = word(2 * by - 1, wx - 1) >> 31;                             // pixel (2by-1, x0-1)
-            const unsigned ur = word(2 * by - 1, wx + 1) & 1u;                              // pixel (2by-1, x0+32)
-            const int base = rg.blk_offset + by * bw + wx * 16;
-            const int upbase = base - bw;
-#pragma unroll 4
-            for (int k = 0; k < 16; ++k) {
-                const unsigned a = (r0 >> (2 * k)) & 1u, b = (r0 >> (2 * k + 1)) & 1u;
-                if (!((v >> (2 * k)) & 3u)) continue;
-                const int me = base + k;
-                // left neighbour: only across the word boundary (in-word runs were pre-linked)
-                if (k == 0 && wx > 0 && (v & 1u) && vl) uf_union(parent, me, me - 1);
-                if (by > 0) {
-                    const unsigned u0 = (u >> (2 * k)) & 1u, u1 = (u >> (2 * k + 1)) & 1u;
-                    if ((a | b) && (u0 | u1)) uf_union(parent, me, upbase + k);
-                    const unsigned um = k > 0 ? (u >> (2 * k - 1)) & 1u : ul;            // pixel (2by-1, 2bx-1)
-                    if (a && um && (wx > 0 || k > 0)) uf_union(parent, me, upbase + k - 1);
-                    const unsigned up2 = k < 15 ? (u >> (2 * k + 2)) & 1u : ur;           // pixel (2by-1, 2bx+2)
-                    if (b && up2 && (wx * 16 + k + 1 < bw)) uf_union(parent, me, upbase + k + 1);
-                }
+        for (int bx = tid; bx < bw; bx += K4_THREADS) {
+            const int wx = bx >> 4, k = bx & 15;
+            const unsigned r0 = word(y0, wx);
+            const unsigned a = (r0 >> (2 * k)) & 1u, b = (r0 >> (2 * k + 1)) & 1u;
+            if (!(a | b)) continue;
+            const unsigned u = word(y0 - 1, wx);
+            const unsigned u0 = (u >> (2 * k)) & 1u, u1 = (u >> (2 * k + 1)) & 1u;
+            const int me = rg.blk_offset + by * bw + bx;
+            const int upb = me - bw;
+            if (u0 | u1) uf_union(parent, me, upb);
+            if (a && !u0 && bx > 0) {
+                const unsigned um = k > 0 ? (u >> (2 * k - 1)) & 1u : word(y0 - 1, wx - 1) >> 31;
+                if (um) uf_union(parent, me, upb - 1);
+            }
+            if (b && !u1 && bx + 1 < bw) {
+                const unsigned up2 = k < 15 ? (u >> (2 * k + 2)) & 1u : word(y0 - 1, wx + 1) & 1u;
+                if (up2) uf_union(parent, me, upb + 1);
             }
         }
     }
 }
 
+// ------------------------------------------------------------------------------------------
 // ------------------------------------------------------------------------------------------
 // chunk = 1024 consecutive blocks (block-raster order) of one region
 __device__ __forceinline__ void chunk_span(const qc_seg_region* regs, int R, int c, int& r, int& b0, int& b1) {
@@ -687,23 +883,27 @@ extern "C" int qc_segment(qc_ctx* ctx, const uint8_t* imgs, const qc_seg_params*
     QC_LAUNCHED(ctx);
 
     const int band_grid = std::min(p->total_bands, sms * 4);
-    k4_hist<<<band_grid, K4_THREADS, 0, st>>>(im, regions, R, p->total_bands, w.hist, w.gray);
+    QC_CUDA(ctx, cudaFuncSetAttribute(k4_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, K4_HIST_SMEM));
+    k4_hist<<<std::min(p->total_bands, sms), K4_THREADS, K4_HIST_SMEM, st>>>(im, regions, R, p->total_bands, w.hist,
+                                                                          w.gray);
     QC_LAUNCHED(ctx);
 
-    k4_otsu<<<(R + 31) / 32, 32, 0, st>>>(regions, R, w.hist, w.cmp, out_thr);
+    k4_otsu<<<std::min(R, sms * 4), 256, 0, st>>>(regions, R, w.hist, w.cmp, out_thr);
     QC_LAUNCHED(ctx);
 
     const int halo = 4 * p->morph_iters;
     const int wpr_max = (p->max_region_w + 31) / 32;
     const int buf_words = (K4_BAND_ROWS + 2 * halo) * wpr_max;
-    const size_t smem = (size_t)buf_words * 4 * 2;
-    if ((int)smem > ctx->max_smem_optin) QC_FAIL(ctx, QC_ERR_UNSUPPORTED, "qc_segment: region width %d too large", p->max_region_w);
-    QC_CUDA(ctx, cudaFuncSetAttribute(k4_mask, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k4_mask<<<band_grid, K4_THREADS, smem, st>>>(im, regions, R, p->total_bands, p->morph_iters, w.cmp, w.gray, w.bits,
-                                                 w.parent, buf_words);
+    const size_t smem = (size_t)buf_words * 4 * 2 + (size_t)(K4_BAND_ROWS / 2) * wpr_max * 16 * 4;
+    if ((int)smem > ctx->max_smem_optin)
+        QC_FAIL(ctx, QC_ERR_UNSUPPORTED, "qc_segment: region width %d needs %zu B of shared memory (max %d)",
+                p->max_region_w, smem, ctx->max_smem_optin);
+    QC_CUDA(ctx, cudaFuncSetAttribute(k4_mask_ccl, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k4_mask_ccl<<<band_grid, K4_THREADS, smem, st>>>(im, regions, R, p->total_bands, p->morph_iters, w.cmp, w.gray,
+                                                     w.bits, w.parent, buf_words);
     QC_LAUNCHED(ctx);
 
-    k4_merge<<<std::min(p->total_bands, sms * 8), K4_THREADS, 0, st>>>(regions, R, p->total_bands, w.bits, w.parent);
+    k4_border<<<std::min(p->total_bands, sms * 8), K4_THREADS, 0, st>>>(regions, R, p->total_bands, w.bits, w.parent);
     QC_LAUNCHED(ctx);
 
     const int chunk_grid = std::min(p->total_chunks, sms * 2);
