@@ -159,7 +159,7 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
-def kernel_microbench(qc, peak):
+def kernel_microbench(qc, peak, only=None):
     """Per-kernel achieved GB/s on the BASELINE config that stresses each kernel.  Every timed launch
     gets a different resident input set (rotation > L2) so nothing is served from L2."""
     from qcgraft import ffi, synth
@@ -174,8 +174,22 @@ def kernel_microbench(qc, peak):
         ts = sorted(s.elapsed_time(e) for s, e in ev)
         return ts[len(ts) // 2], ts[0]
 
-    # K1 @ cfg2: 64 x 640^2, rotating 3 batches
     rng = np.random.default_rng(0)
+    want = lambda k: only is None or k in only
+    if want("k1"):
+        _mb_k1(qc, peak, rng, time_call, out)
+    if want("k2"):
+        _mb_k2(qc, peak, rng, time_call, out)
+    if want("k3"):
+        _mb_k3(qc, peak, rng, time_call, out)
+    if want("k4"):
+        _mb_k4(qc, peak, rng, time_call, out)
+    return out
+
+
+def _mb_k1(qc, peak, rng, time_call, out):
+    from qcgraft import ffi, synth
+    # K1 @ cfg2: 64 x 640^2, rotating 3 batches
     b = [torch.from_numpy(rng.integers(0, 256, (BATCH, IMGSZ, IMGSZ, 3), dtype=np.uint8)).cuda() for _ in range(3)]
     plan = qc.make_pre_plan(ffi.QC_PRE_LETTERBOX, IMGSZ, IMGSZ, IMGSZ, IMGSZ)
     outs = [torch.empty((BATCH, 3, IMGSZ, IMGSZ), dtype=torch.bfloat16, device="cuda") for _ in range(3)]
@@ -184,8 +198,10 @@ def kernel_microbench(qc, peak):
     med, best = time_call(lambda i: qc.preprocess(b[i % 3], plan, out=outs[i % 3]), 12)
     by = BATCH * (IMGSZ * IMGSZ * 3 + 3 * IMGSZ * IMGSZ * 2)
     out["k1_preprocess_cfg2"] = {"bytes": by, "ms": med, "gbs": by / med / 1e6, "frac": by / med / 1e6 / peak}
-    del b, outs
 
+
+def _mb_k2(qc, peak, rng, time_call, out):
+    from qcgraft import ffi, synth
     # K2 @ cfg3: 32 x 1280^2 head, >= 1000 candidates/image (f32 head = reference dtype)
     heads = []
     for k in range(2):
@@ -199,8 +215,10 @@ def kernel_microbench(qc, peak):
     out["k2_decode_nms_cfg3"] = {"bytes": by, "ms": med, "gbs": by / med / 1e6, "frac": by / med / 1e6 / peak,
                                  "note": "sparse decode: only the 5 class planes are streamed, box planes are "
                                          "gathered for candidates; sort+NMS phase is latency-bound"}
-    del heads
 
+
+def _mb_k3(qc, peak, rng, time_call, out):
+    from qcgraft import ffi, synth
     # K3: 512 ROIs (~80x80) of 64 frames -> 224^2 bf16
     frames = torch.from_numpy(synth.make_frames(7, 16)).cuda()
     K = 512
@@ -214,8 +232,10 @@ def kernel_microbench(qc, peak):
     med, best = time_call(lambda i: qc.roi_align(frames, rois, out=o3), 8)
     by = int(((r[:, 3] - r[:, 1]) * (r[:, 4] - r[:, 2]) * 3).sum()) + K * 3 * 224 * 224 * 2
     out["k3_roi_align_512rois"] = {"bytes": by, "ms": med, "gbs": by / med / 1e6, "frac": by / med / 1e6 / peak}
-    del frames, o3
 
+
+def _mb_k4(qc, peak, rng, time_call, out):
+    from qcgraft import ffi, synth
     # K4 @ cfg4: 16 x 2048^2 gray line-scan frames
     ls = [torch.from_numpy(np.stack([synth.make_linescan(900 + 16 * k + (i % 4)) for i in range(16)])).cuda()
           for k in range(2)]
@@ -228,7 +248,6 @@ def kernel_microbench(qc, peak):
     out["k4_segment_cfg4"] = {"bytes": by, "ms": med, "gbs": by / med / 1e6, "frac": by / med / 1e6 / peak,
                               "components": ncomp,
                               "note": "10 launches; union-find merge/rank phases are L2/atomic-bound"}
-    return out
 
 
 def main():

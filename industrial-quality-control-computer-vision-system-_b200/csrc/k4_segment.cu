@@ -35,7 +35,7 @@ namespace {
 
 constexpr int K4_THREADS = 256;
 constexpr int K4_BAND_ROWS = 32;     // pixel rows per band (16 block rows)
-constexpr int K4_CHUNK = 1024;       // blocks per ranking chunk
+constexpr int K4_CHUNK = 256;        // word cells (16 blocks each) per ranking chunk
 
 struct SegWs {
     unsigned* hist;       // [R][256]
@@ -46,6 +46,8 @@ struct SegWs {
     int* rank;            // [total_blocks]   label of root blocks
     int* chunk_count;     // [total_chunks]
     int* chunk_base;      // [total_chunks]
+    int* band_off;        // [R+1] cumulative bands
+    int* chunk_off;       // [R+1] cumulative ranking chunks
     size_t total;
 };
 
@@ -63,6 +65,8 @@ SegWs carve(void* base, const qc_seg_params* p) {
     w.rank = (int*)(b + take((size_t)p->total_blocks * 4));
     w.chunk_count = (int*)(b + take((size_t)p->total_chunks * 4));
     w.chunk_base = (int*)(b + take((size_t)p->total_chunks * 4));
+    w.band_off = (int*)(b + take((R + 1) * 4));
+    w.chunk_off = (int*)(b + take((R + 1) * 4));
     w.total = off;
     return w;
 }
@@ -73,13 +77,20 @@ struct Img {
     int row_stride, channels, swap_rb;
 };
 
-// region of work item t (band or chunk index): largest r with off(r) <= t
-template <typename F>
-__device__ __forceinline__ int find_region(int t, int R, F off) {
+// Work item -> region.  The cumulative offset tables (R+1 ints, written by k4_init) are cached in
+// shared memory when they fit, so every thread can binary-search them without a barrier.
+constexpr int K4_LOC_MAX = 2047;
+__device__ __forceinline__ const int* loc_load(int* s_off, const int* __restrict__ g_off, int R) {
+    if (R > K4_LOC_MAX) return g_off;
+    for (int i = threadIdx.x; i <= R; i += blockDim.x) s_off[i] = g_off[i];
+    __syncthreads();
+    return s_off;
+}
+__device__ __forceinline__ int loc_find(const int* off, int R, int t) {   // largest r with off[r] <= t
     int lo = 0, hi = R - 1;
     while (lo < hi) {
         const int mid = (lo + hi + 1) >> 1;
-        if (off(mid) <= t) lo = mid; else hi = mid - 1;
+        if (off[mid] <= t) lo = mid; else hi = mid - 1;
     }
     return lo;
 }
@@ -88,16 +99,15 @@ __device__ __forceinline__ int wpr_of(const qc_seg_region& r) { return (r.w + 31
 __device__ __forceinline__ int bw_of(const qc_seg_region& r) { return (r.w + 1) >> 1; }
 __device__ __forceinline__ int bh_of(const qc_seg_region& r) { return (r.h + 1) >> 1; }
 
-// gray value source for region row `y` (region-local), column x
-struct GraySrc {
-    const uint8_t* p;   // first pixel of the region row
-    int step;           // 1 (gray / workspace gray)
-};
-
 // ------------------------------------------------------------------------------------------
 __global__ void k4_init(const qc_seg_region* __restrict__ regs, int R, unsigned* __restrict__ hist,
-                        int* __restrict__ stats, long long* __restrict__ out_area, int total_stats_rows) {
+                        int* __restrict__ stats, long long* __restrict__ out_area, int total_stats_rows,
+                        int* __restrict__ band_off, int* __restrict__ chunk_off, int total_bands, int total_chunks) {
     const int gid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
+    for (int i = gid; i <= R; i += gsz) {
+        band_off[i] = i < R ? regs[i].band_offset : total_bands;
+        chunk_off[i] = i < R ? regs[i].chunk_offset : total_chunks;
+    }
     for (int i = gid; i < R * 256; i += gsz) hist[i] = 0;
     for (int i = gid; i < R; i += gsz) out_area[i] = 0;
     for (int i = gid; i < total_stats_rows; i += gsz) {
@@ -114,18 +124,17 @@ constexpr int K4_HIST_BIG_PX = 8192;
 constexpr int K4_HIST_SMEM = (K4_THREADS / 32) * 256 * 32 * 2;   // 128 KB
 
 __global__ void __launch_bounds__(K4_THREADS)
-k4_hist(Img im, const qc_seg_region* __restrict__ regs, int R, int total_bands, unsigned* __restrict__ hist,
-        uint8_t* __restrict__ gray_ws) {
+k4_hist(Img im, const qc_seg_region* __restrict__ regs, int R, int total_bands, const int* __restrict__ g_band_off,
+        unsigned* __restrict__ hist, uint8_t* __restrict__ gray_ws) {
     extern __shared__ __align__(16) unsigned char hsm[];
     __shared__ unsigned sh_small[256];
-    __shared__ int s_r;
+    __shared__ int s_off[K4_LOC_MAX + 1];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int* off = loc_load(s_off, g_band_off, R);
     unsigned short* tab = reinterpret_cast<unsigned short*>(hsm) + warp * 8192 + lane;   // [bin*32]
     for (int t = blockIdx.x; t < total_bands; t += gridDim.x) {
-        __syncthreads();
-        if (tid == 0) s_r = find_region(t, R, [&](int i) { return regs[i].band_offset; });
-        __syncthreads();
-        const int r = s_r;
+        __syncthreads();                 // previous band's reduce is done with the tables
+        const int r = loc_find(off, R, t);
         const qc_seg_region rg = regs[r];
         const int y0 = (t - rg.band_offset) * K4_BAND_ROWS;
         const int y1 = min(y0 + K4_BAND_ROWS, rg.h);
@@ -367,21 +376,21 @@ __device__ __forceinline__ void suf_union(int* L, int a, int b) {
 
 // threshold -> morphology -> bit rows + band-local connected components (all in shared memory)
 __global__ void __launch_bounds__(K4_THREADS)
-k4_mask_ccl(Img im, const qc_seg_region* __restrict__ regs, int R, int total_bands, int iters,
-            const int* __restrict__ cmp, const uint8_t* __restrict__ gray_ws, unsigned* __restrict__ bits,
-            int* __restrict__ parent, int buf_words) {
+k4_mask_ccl(Img im, const qc_seg_region* __restrict__ regs, int R, int total_bands,
+            const int* __restrict__ g_band_off, int iters, const int* __restrict__ cmp,
+            const uint8_t* __restrict__ gray_ws, unsigned* __restrict__ bits, int* __restrict__ parent,
+            int buf_words) {
     extern __shared__ __align__(16) unsigned sm[];
     unsigned* bufA = sm;
     unsigned* bufB = sm + buf_words;
     int* lab = reinterpret_cast<int*>(sm + 2 * buf_words);
-    __shared__ int s_r;
+    __shared__ int s_off[K4_LOC_MAX + 1];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int halo = 4 * iters;
+    const int* off = loc_load(s_off, g_band_off, R);
     for (int t = blockIdx.x; t < total_bands; t += gridDim.x) {
-        __syncthreads();
-        if (tid == 0) s_r = find_region(t, R, [&](int i) { return regs[i].band_offset; });
-        __syncthreads();
-        const int r = s_r;
+        __syncthreads();                 // previous band is done with bufA/bufB/lab
+        const int r = loc_find(off, R, t);
         const qc_seg_region rg = regs[r];
         const int wpr = wpr_of(rg);
         const int y0 = (t - rg.band_offset) * K4_BAND_ROWS;
@@ -452,7 +461,8 @@ k4_mask_ccl(Img im, const qc_seg_region* __restrict__ regs, int R, int total_ban
             const int yy = wi / wpr, wx = wi - yy * wpr;
             bits[rg.bits_offset + (long long)(y0 + yy) * wpr + wx] = src[(y0 - row_lo + yy) * wpr + wx];
         }
-        // ---- band-local CCL on 2x2 blocks (8-connectivity), shared-memory union-find -----------------
+        // ---- band-local CCL on 2x2 blocks (8-connectivity): one thread per 32-pixel word cell
+        //      (16 blocks); empty words are skipped and their labels never touched ------------------
         const int bw = bw_of(rg), bwp = wpr * 16;
         const int by0 = y0 >> 1, nbr = ((y1 + 1) >> 1) - by0;
         const unsigned* band = src + (y0 - row_lo) * wpr;          // band rows only: no look above y0
@@ -460,50 +470,73 @@ k4_mask_ccl(Img im, const qc_seg_region* __restrict__ regs, int R, int total_ban
         auto rowword = [&](int ry, int wx) -> unsigned {           // ry relative to y0
             return (ry < 0 || ry >= brows || wx < 0 || wx >= wpr) ? 0u : band[ry * wpr + wx];
         };
-        for (int i = tid; i < nbr * bwp; i += K4_THREADS) {
-            const int byy = i / bwp, bx = i - byy * bwp;
-            const unsigned v = rowword(2 * byy, bx >> 4) | rowword(2 * byy + 1, bx >> 4);
-            lab[i] = ((v >> (2 * (bx & 15))) & 3u) ? i : -1;
+        const int ncell = nbr * wpr;
+        // init: label = head of the horizontal run of connected blocks inside the word
+        for (int ci = tid; ci < ncell; ci += K4_THREADS) {
+            const int byy = ci / wpr, wx = ci - byy * wpr;
+            const unsigned v = rowword(2 * byy, wx) | rowword(2 * byy + 1, wx);
+            if (!v) continue;
+            const int base = byy * bwp + wx * 16;
+            int head = 0;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                if ((v >> (2 * k)) & 3u) {
+                    const bool link = k > 0 && ((v >> (2 * k)) & 1u) && ((v >> (2 * k - 1)) & 1u);
+                    if (!link) head = base + k;
+                    lab[base + k] = head;
+                }
+            }
         }
         __syncthreads();
-        for (int i = tid; i < nbr * bwp; i += K4_THREADS) {
-            if (lab[i] < 0) continue;
-            const int byy = i / bwp, bx = i - byy * bwp;
-            const int wx = bx >> 4, k = bx & 15;
+        for (int ci = tid; ci < ncell; ci += K4_THREADS) {
+            const int byy = ci / wpr, wx = ci - byy * wpr;
             const unsigned r0 = rowword(2 * byy, wx), r1 = rowword(2 * byy + 1, wx);
-            const unsigned a = (r0 >> (2 * k)) & 1u, b = (r0 >> (2 * k + 1)) & 1u;
-            const unsigned c = (r1 >> (2 * k)) & 1u;
-            // left block: its right column vs my left column
-            unsigned lcol;
-            if (k > 0) lcol = ((r0 | r1) >> (2 * k - 1)) & 1u;
-            else lcol = (rowword(2 * byy, wx - 1) | rowword(2 * byy + 1, wx - 1)) >> 31;
-            if ((a | c) && lcol) suf_union(lab, i, i - 1);
-            if (byy > 0) {
-                const unsigned u = rowword(2 * byy - 1, wx);
-                const unsigned u0 = (u >> (2 * k)) & 1u, u1 = (u >> (2 * k + 1)) & 1u;
-                if ((a | b) && (u0 | u1)) suf_union(lab, i, i - bwp);
-                // up-left / up-right only when not already implied through the upper block
-                if (a && !u0) {
-                    const unsigned um = k > 0 ? (u >> (2 * k - 1)) & 1u : rowword(2 * byy - 1, wx - 1) >> 31;
-                    if (um) suf_union(lab, i, i - bwp - 1);
-                }
-                if (b && !u1) {
-                    const unsigned up2 = k < 15 ? (u >> (2 * k + 2)) & 1u : rowword(2 * byy - 1, wx + 1) & 1u;
-                    if (up2) suf_union(lab, i, i - bwp + 1);
+            const unsigned v = r0 | r1;
+            if (!v) continue;
+            const unsigned u = rowword(2 * byy - 1, wx);
+            const unsigned vl = (rowword(2 * byy, wx - 1) | rowword(2 * byy + 1, wx - 1)) >> 31;
+            const unsigned ul = rowword(2 * byy - 1, wx - 1) >> 31;
+            const unsigned ur = rowword(2 * byy - 1, wx + 1) & 1u;
+            const int base = byy * bwp + wx * 16;
+            if ((v & 1u) && vl) suf_union(lab, base, base - 1);          // run continues from the previous word
+            if (byy > 0 && (u | ul | ur)) {
+                unsigned m = (v | (v >> 1)) & 0x55555555u;               // one bit per foreground block
+                while (m) {
+                    const int k = (__ffs(m) - 1) >> 1;
+                    m &= m - 1;
+                    const unsigned a = (r0 >> (2 * k)) & 1u, b = (r0 >> (2 * k + 1)) & 1u;
+                    if (!(a | b)) continue;
+                    const unsigned u0 = (u >> (2 * k)) & 1u, u1 = (u >> (2 * k + 1)) & 1u;
+                    const int me = base + k;
+                    if (u0 | u1) suf_union(lab, me, me - bwp);
+                    // up-left / up-right only when not already implied through the upper block
+                    if (a && !u0) {
+                        const unsigned um = k > 0 ? (u >> (2 * k - 1)) & 1u : ul;
+                        if (um) suf_union(lab, me, me - bwp - 1);
+                    }
+                    if (b && !u1) {
+                        const unsigned up2 = k < 15 ? (u >> (2 * k + 2)) & 1u : ur;
+                        if (up2) suf_union(lab, me, me - bwp + 1);
+                    }
                 }
             }
         }
         __syncthreads();
-        for (int i = tid; i < nbr * bwp; i += K4_THREADS) {
-            const int byy = i / bwp, bx = i - byy * bwp;
-            if (bx >= bw) continue;
-            int g = -1;
-            if (lab[i] >= 0) {
-                const int rt = suf_find(lab, i);
-                const int rby = rt / bwp, rbx = rt - rby * bwp;
-                g = rg.blk_offset + (by0 + rby) * bw + rbx;
+        const float inv_bwp = 1.0f / (float)bwp;
+        for (int ci = tid; ci < ncell; ci += K4_THREADS) {
+            const int byy = ci / wpr, wx = ci - byy * wpr;
+            const unsigned v = rowword(2 * byy, wx) | rowword(2 * byy + 1, wx);
+            if (!v) continue;
+            const int base = byy * bwp + wx * 16;
+            int* prow = parent + rg.blk_offset + (long long)(by0 + byy) * bw + wx * 16;
+            unsigned m = (v | (v >> 1)) & 0x55555555u;
+            while (m) {
+                const int k = (__ffs(m) - 1) >> 1;
+                m &= m - 1;
+                const int rt = suf_find(lab, base + k);
+                const int rby = (int)(((float)rt + 0.5f) * inv_bwp);     // rt / bwp (exact: rt < 2^20)
+                prow[k] = rg.blk_offset + (by0 + rby) * bw + (rt - rby * bwp);
             }
-            parent[rg.blk_offset + (long long)(by0 + byy) * bw + bx] = g;
         }
     }
 }
@@ -526,86 +559,106 @@ __device__ __forceinline__ void uf_union(int* L, int a, int b) {
 }
 
 // stitches bands together: the first block row of every band (except a region's first) is united
-// with the block row above it, in global memory
+// with the block row above it, in global memory.  One thread per 32-pixel word of that row.
 __global__ void __launch_bounds__(K4_THREADS)
-k4_border(const qc_seg_region* __restrict__ regs, int R, int total_bands, const unsigned* __restrict__ bits,
-          int* __restrict__ parent) {
-    __shared__ int s_r;
+k4_border(const qc_seg_region* __restrict__ regs, int R, int total_bands, const int* __restrict__ g_band_off,
+          const unsigned* __restrict__ bits, int* __restrict__ parent) {
+    __shared__ int s_off[K4_LOC_MAX + 1];
     const int tid = threadIdx.x;
+    const int* off = loc_load(s_off, g_band_off, R);
     for (int t = blockIdx.x; t < total_bands; t += gridDim.x) {
-        __syncthreads();
-        if (tid == 0) s_r = find_region(t, R, [&](int i) { return regs[i].band_offset; });
-        __syncthreads();
-        const qc_seg_region rg = regs[s_r];
+        const qc_seg_region rg = regs[loc_find(off, R, t)];
         const int y0 = (t - rg.band_offset) * K4_BAND_ROWS;
         if (y0 == 0) continue;
         const int wpr = wpr_of(rg), bw = bw_of(rg);
         const int by = y0 >> 1;
         const unsigned* B = bits + rg.bits_offset;
         auto word = [&](int y, int wx) -> unsigned {
-            return (y < 0 || y >= rg.h || wx < 0 || wx >= wpr) ? 0u : __ldg(B + (long long)y * wpr + wx);
+            return (wx < 0 || wx >= wpr) ? 0u : __ldg(B + (long long)y * wpr + wx);
         };
-        for (int bx = tid; bx < bw; bx += K4_THREADS) {
-            const int wx = bx >> 4, k = bx & 15;
+        for (int wx = tid; wx < wpr; wx += K4_THREADS) {
             const unsigned r0 = word(y0, wx);
-            const unsigned a = (r0 >> (2 * k)) & 1u, b = (r0 >> (2 * k + 1)) & 1u;
-            if (!(a | b)) continue;
+            if (!r0) continue;
             const unsigned u = word(y0 - 1, wx);
-            const unsigned u0 = (u >> (2 * k)) & 1u, u1 = (u >> (2 * k + 1)) & 1u;
-            const int me = rg.blk_offset + by * bw + bx;
-            const int upb = me - bw;
-            if (u0 | u1) uf_union(parent, me, upb);
-            if (a && !u0 && bx > 0) {
-                const unsigned um = k > 0 ? (u >> (2 * k - 1)) & 1u : word(y0 - 1, wx - 1) >> 31;
-                if (um) uf_union(parent, me, upb - 1);
-            }
-            if (b && !u1 && bx + 1 < bw) {
-                const unsigned up2 = k < 15 ? (u >> (2 * k + 2)) & 1u : word(y0 - 1, wx + 1) & 1u;
-                if (up2) uf_union(parent, me, upb + 1);
+            const unsigned ul = word(y0 - 1, wx - 1) >> 31, ur = word(y0 - 1, wx + 1) & 1u;
+            if (!(u | ul | ur)) continue;
+            const int base = rg.blk_offset + by * bw + wx * 16;
+            unsigned m = (r0 | (r0 >> 1)) & 0x55555555u;
+            while (m) {
+                const int k = (__ffs(m) - 1) >> 1;
+                m &= m - 1;
+                const unsigned a = (r0 >> (2 * k)) & 1u, b = (r0 >> (2 * k + 1)) & 1u;
+                const unsigned u0 = (u >> (2 * k)) & 1u, u1 = (u >> (2 * k + 1)) & 1u;
+                const int me = base + k, upb = me - bw;
+                if (u0 | u1) uf_union(parent, me, upb);
+                if (a && !u0) {
+                    const unsigned um = k > 0 ? (u >> (2 * k - 1)) & 1u : ul;
+                    if (um) uf_union(parent, me, upb - 1);
+                }
+                if (b && !u1) {
+                    const unsigned up2 = k < 15 ? (u >> (2 * k + 2)) & 1u : ur;
+                    if (up2) uf_union(parent, me, upb + 1);
+                }
             }
         }
     }
 }
 
 // ------------------------------------------------------------------------------------------
-// ------------------------------------------------------------------------------------------
-// chunk = 1024 consecutive blocks (block-raster order) of one region
-__device__ __forceinline__ void chunk_span(const qc_seg_region* regs, int R, int c, int& r, int& b0, int& b1) {
-    r = find_region(c, R, [&](int i) { return regs[i].chunk_offset; });
-    const int nb = bw_of(regs[r]) * bh_of(regs[r]);
-    b0 = (c - regs[r].chunk_offset) * K4_CHUNK;
-    b1 = min(b0 + K4_CHUNK, nb);
+// Ranking chunk = K4_CHUNK consecutive word cells (block-row major) of one region; one thread per
+// cell.  Block-raster order == (cell order, then block order inside the word).
+struct Cell {
+    unsigned r0, r1;      // the two pixel rows of the cell
+    int base;             // global block index of the cell's first block
+    bool valid;
+};
+__device__ __forceinline__ Cell load_cell(const qc_seg_region& rg, const unsigned* __restrict__ bits, int cell) {
+    Cell c;
+    const int wpr = wpr_of(rg), ncell = bh_of(rg) * wpr;
+    c.valid = cell < ncell;
+    c.r0 = c.r1 = 0u;
+    c.base = 0;
+    if (c.valid) {
+        const int by = cell / wpr, wx = cell - by * wpr;
+        const unsigned* B = bits + rg.bits_offset;
+        c.r0 = __ldg(B + (long long)(2 * by) * wpr + wx);
+        c.r1 = (2 * by + 1 < rg.h) ? __ldg(B + (long long)(2 * by + 1) * wpr + wx) : 0u;
+        c.base = rg.blk_offset + by * bw_of(rg) + wx * 16;
+    }
+    return c;
 }
 
 __global__ void __launch_bounds__(K4_CHUNK)
-k4_compress(const qc_seg_region* __restrict__ regs, int R, int total_chunks, int* __restrict__ parent,
-            int* __restrict__ chunk_count) {
+k4_compress(const qc_seg_region* __restrict__ regs, int R, int total_chunks, const int* __restrict__ g_chunk_off,
+            const unsigned* __restrict__ bits, int* __restrict__ parent, int* __restrict__ chunk_count) {
+    __shared__ int s_off[K4_LOC_MAX + 1];
     __shared__ int s_cnt[K4_CHUNK / 32];
-    __shared__ int s_r, s_b0, s_b1;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int* off = loc_load(s_off, g_chunk_off, R);
     for (int c = blockIdx.x; c < total_chunks; c += gridDim.x) {
-        __syncthreads();
-        if (tid == 0) { int r, b0, b1; chunk_span(regs, R, c, r, b0, b1); s_r = r; s_b0 = b0; s_b1 = b1; }
-        __syncthreads();
-        const int base = regs[s_r].blk_offset;
-        const int b = s_b0 + tid;
-        bool root = false;
-        if (b < s_b1) {
-            const int g = base + b;
-            if (__ldcg(parent + g) >= 0) {
-                const int rt = uf_find(parent, g);
-                parent[g] = rt;
-                root = (rt == g);
-            }
+        const int r = loc_find(off, R, c);
+        const qc_seg_region rg = regs[r];
+        const Cell ce = load_cell(rg, bits, (c - rg.chunk_offset) * K4_CHUNK + tid);
+        int cnt = 0;
+        unsigned m = ((ce.r0 | ce.r1) | ((ce.r0 | ce.r1) >> 1)) & 0x55555555u;
+        while (m) {
+            const int k = (__ffs(m) - 1) >> 1;
+            m &= m - 1;
+            const int g = ce.base + k;
+            const int rt = uf_find(parent, g);
+            parent[g] = rt;
+            cnt += (rt == g);
         }
-        const unsigned m = __ballot_sync(0xffffffffu, root);
-        if (lane == 0) s_cnt[warp] = __popc(m);
-        __syncthreads();
-        if (warp == 0) {
-            int v = s_cnt[lane];
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            if (lane == 0) chunk_count[c] = v;
+        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        __syncthreads();
+        if (lane == 0) s_cnt[warp] = cnt;
+        __syncthreads();
+        if (tid == 0) {
+            int v = 0;
+#pragma unroll
+            for (int k = 0; k < K4_CHUNK / 32; ++k) v += s_cnt[k];
+            chunk_count[c] = v;
         }
     }
 }
@@ -618,8 +671,8 @@ k4_scan(const qc_seg_region* __restrict__ regs, int R, const int* __restrict__ c
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int r = blockIdx.x; r < R; r += gridDim.x) {
         const int c0 = regs[r].chunk_offset;
-        const int nb = bw_of(regs[r]) * bh_of(regs[r]);
-        const int nc = (nb + K4_CHUNK - 1) / K4_CHUNK;
+        const int ncell = bh_of(regs[r]) * wpr_of(regs[r]);
+        const int nc = (ncell + K4_CHUNK - 1) / K4_CHUNK;
         __syncthreads();
         if (tid == 0) s_carry = 0;
         __syncthreads();
@@ -650,44 +703,53 @@ k4_scan(const qc_seg_region* __restrict__ regs, int R, const int* __restrict__ c
 }
 
 __global__ void __launch_bounds__(K4_CHUNK)
-k4_rank(const qc_seg_region* __restrict__ regs, int R, int total_chunks, const int* __restrict__ parent,
-        const int* __restrict__ chunk_base, int* __restrict__ rank) {
+k4_rank(const qc_seg_region* __restrict__ regs, int R, int total_chunks, const int* __restrict__ g_chunk_off,
+        const unsigned* __restrict__ bits, const int* __restrict__ parent, const int* __restrict__ chunk_base,
+        int* __restrict__ rank) {
+    __shared__ int s_off[K4_LOC_MAX + 1];
     __shared__ int s_cnt[K4_CHUNK / 32];
-    __shared__ int s_r, s_b0, s_b1;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int* off = loc_load(s_off, g_chunk_off, R);
     for (int c = blockIdx.x; c < total_chunks; c += gridDim.x) {
-        __syncthreads();
-        if (tid == 0) { int r, b0, b1; chunk_span(regs, R, c, r, b0, b1); s_r = r; s_b0 = b0; s_b1 = b1; }
-        __syncthreads();
-        const int base = regs[s_r].blk_offset;
-        const int b = s_b0 + tid;
-        bool root = false;
-        if (b < s_b1) root = (parent[base + b] == base + b);
-        const unsigned m = __ballot_sync(0xffffffffu, root);
-        if (lane == 0) s_cnt[warp] = __popc(m);
-        __syncthreads();
-        if (warp == 0) {
-            int v = s_cnt[lane], x = v;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
-            s_cnt[lane] = x - v;    // exclusive
+        const int r = loc_find(off, R, c);
+        const qc_seg_region rg = regs[r];
+        const Cell ce = load_cell(rg, bits, (c - rg.chunk_offset) * K4_CHUNK + tid);
+        unsigned rootmask = 0;                                   // bit k: block k of the cell is a root
+        unsigned m = ((ce.r0 | ce.r1) | ((ce.r0 | ce.r1) >> 1)) & 0x55555555u;
+        while (m) {
+            const int k = (__ffs(m) - 1) >> 1;
+            m &= m - 1;
+            if (parent[ce.base + k] == ce.base + k) rootmask |= 1u << k;
         }
+        const int cnt = __popc(rootmask);
+        int x = cnt;                                             // inclusive scan over the 256 cells
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
         __syncthreads();
-        if (root) rank[base + b] = chunk_base[c] + s_cnt[warp] + __popc(m & ((1u << lane) - 1u)) + 1;
+        if (lane == 31) s_cnt[warp] = x;
+        __syncthreads();
+        int prev = 0;
+#pragma unroll
+        for (int k = 0; k < K4_CHUNK / 32; ++k) prev += (k < warp) ? s_cnt[k] : 0;
+        int next = chunk_base[c] + prev + x - cnt;               // labels before this cell
+        while (rootmask) {
+            const int k = __ffs(rootmask) - 1;
+            rootmask &= rootmask - 1;
+            rank[ce.base + k] = ++next;
+        }
     }
 }
 
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(K4_THREADS)
-k4_stats(const qc_seg_region* __restrict__ regs, int R, int total_bands, const unsigned* __restrict__ bits,
-         int* __restrict__ parent, const int* __restrict__ rank, int* __restrict__ stats) {
-    __shared__ int s_r;
+k4_stats(const qc_seg_region* __restrict__ regs, int R, int total_bands, const int* __restrict__ g_band_off,
+         const unsigned* __restrict__ bits, int* __restrict__ parent, const int* __restrict__ rank,
+         int* __restrict__ stats) {
+    __shared__ int s_off[K4_LOC_MAX + 1];
     const int tid = threadIdx.x;
+    const int* off = loc_load(s_off, g_band_off, R);
     for (int t = blockIdx.x; t < total_bands; t += gridDim.x) {
-        __syncthreads();
-        if (tid == 0) s_r = find_region(t, R, [&](int i) { return regs[i].band_offset; });
-        __syncthreads();
-        const qc_seg_region rg = regs[s_r];
+        const qc_seg_region rg = regs[loc_find(off, R, t)];
         const int wpr = wpr_of(rg), bw = bw_of(rg);
         const int y0 = (t - rg.band_offset) * K4_BAND_ROWS;
         const int y1 = min(y0 + K4_BAND_ROWS, rg.h);
@@ -731,16 +793,17 @@ k4_stats(const qc_seg_region* __restrict__ regs, int R, int total_bands, const u
 
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(K4_THREADS)
-k4_final(const qc_seg_region* __restrict__ regs, int R, int total_bands, const unsigned* __restrict__ bits,
+k4_final(const qc_seg_region* __restrict__ regs, int R, int total_bands, const int* __restrict__ g_band_off,
+         const unsigned* __restrict__ bits,
          const int* __restrict__ parent, int* __restrict__ stats, const int* __restrict__ ncomp,
          uint8_t* __restrict__ out_mask, int* __restrict__ out_labels, long long* __restrict__ out_area) {
-    __shared__ int s_r;
+    __shared__ int s_off[K4_LOC_MAX + 1];
     __shared__ int s_area[K4_THREADS / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int* off = loc_load(s_off, g_band_off, R);
     for (int t = blockIdx.x; t < total_bands; t += gridDim.x) {
-        __syncthreads();
-        if (tid == 0) s_r = find_region(t, R, [&](int i) { return regs[i].band_offset; });
-        __syncthreads();
+        __syncthreads();                 // s_area of the previous band has been consumed
+        const int s_r = loc_find(off, R, t);
         const qc_seg_region rg = regs[s_r];
         const int wpr = wpr_of(rg), bw = bw_of(rg);
         const int y0 = (t - rg.band_offset) * K4_BAND_ROWS;
@@ -836,7 +899,7 @@ extern "C" int qc_segment_plan(qc_seg_region* regs, int num_regions, qc_seg_para
         px = (px + 15) & ~15ll;                 // keep every region's outputs 16-byte aligned
         stats += r.max_comp;
         bands += (r.h + K4_BAND_ROWS - 1) / K4_BAND_ROWS;
-        chunks += (bw * bh + K4_CHUNK - 1) / K4_CHUNK;
+        chunks += (wpr * bh + K4_CHUNK - 1) / K4_CHUNK;
         bits += wpr * r.h;
         blocks += bw * bh;
         mw = std::max(mw, r.w);
@@ -879,13 +942,16 @@ extern "C" int qc_segment(qc_ctx* ctx, const uint8_t* imgs, const qc_seg_params*
     const int sms = ctx->sm_count;
 
     k4_init<<<std::min(sms * 4, std::max(1, (p->total_stats_rows + 255) / 256)), 256, 0, st>>>(
-        regions, R, w.hist, out_stats, (long long*)out_area, p->total_stats_rows);
+        regions, R, w.hist, out_stats, (long long*)out_area, p->total_stats_rows, w.band_off, w.chunk_off,
+        p->total_bands, p->total_chunks);
     QC_LAUNCHED(ctx);
 
-    const int band_grid = std::min(p->total_bands, sms * 4);
+    // per-warp u16 histogram tables only when some band can exceed K4_HIST_BIG_PX pixels
+    const bool big_hist = (long long)p->max_region_w * K4_BAND_ROWS > K4_HIST_BIG_PX;
+    const int hist_smem = big_hist ? K4_HIST_SMEM : 0;
     QC_CUDA(ctx, cudaFuncSetAttribute(k4_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, K4_HIST_SMEM));
-    k4_hist<<<std::min(p->total_bands, sms), K4_THREADS, K4_HIST_SMEM, st>>>(im, regions, R, p->total_bands, w.hist,
-                                                                          w.gray);
+    k4_hist<<<std::min(p->total_bands, big_hist ? sms : sms * 6), K4_THREADS, hist_smem, st>>>(
+        im, regions, R, p->total_bands, w.band_off, w.hist, w.gray);
     QC_LAUNCHED(ctx);
 
     k4_otsu<<<std::min(R, sms * 4), 256, 0, st>>>(regions, R, w.hist, w.cmp, out_thr);
@@ -895,31 +961,35 @@ extern "C" int qc_segment(qc_ctx* ctx, const uint8_t* imgs, const qc_seg_params*
     const int wpr_max = (p->max_region_w + 31) / 32;
     const int buf_words = (K4_BAND_ROWS + 2 * halo) * wpr_max;
     const size_t smem = (size_t)buf_words * 4 * 2 + (size_t)(K4_BAND_ROWS / 2) * wpr_max * 16 * 4;
-    if ((int)smem > ctx->max_smem_optin)
+    if ((long long)smem + (K4_LOC_MAX + 1) * 4 + 1024 > ctx->max_smem_optin)
         QC_FAIL(ctx, QC_ERR_UNSUPPORTED, "qc_segment: region width %d needs %zu B of shared memory (max %d)",
                 p->max_region_w, smem, ctx->max_smem_optin);
     QC_CUDA(ctx, cudaFuncSetAttribute(k4_mask_ccl, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k4_mask_ccl<<<band_grid, K4_THREADS, smem, st>>>(im, regions, R, p->total_bands, p->morph_iters, w.cmp, w.gray,
-                                                     w.bits, w.parent, buf_words);
+    int occ = 1;
+    QC_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k4_mask_ccl, K4_THREADS, smem));
+    k4_mask_ccl<<<std::min(p->total_bands, sms * std::max(occ, 1)), K4_THREADS, smem, st>>>(
+        im, regions, R, p->total_bands, w.band_off, p->morph_iters, w.cmp, w.gray, w.bits, w.parent, buf_words);
     QC_LAUNCHED(ctx);
 
-    k4_border<<<std::min(p->total_bands, sms * 8), K4_THREADS, 0, st>>>(regions, R, p->total_bands, w.bits, w.parent);
+    const int band_grid = std::min(p->total_bands, sms * 8);
+    k4_border<<<band_grid, K4_THREADS, 0, st>>>(regions, R, p->total_bands, w.band_off, w.bits, w.parent);
     QC_LAUNCHED(ctx);
 
-    const int chunk_grid = std::min(p->total_chunks, sms * 2);
-    k4_compress<<<chunk_grid, K4_CHUNK, 0, st>>>(regions, R, p->total_chunks, w.parent, w.chunk_count);
+    const int chunk_grid = std::min(p->total_chunks, sms * 8);
+    k4_compress<<<chunk_grid, K4_CHUNK, 0, st>>>(regions, R, p->total_chunks, w.chunk_off, w.bits, w.parent,
+                                                 w.chunk_count);
     QC_LAUNCHED(ctx);
     k4_scan<<<std::min(R, sms * 2), 1024, 0, st>>>(regions, R, w.chunk_count, w.chunk_base, out_ncomp);
     QC_LAUNCHED(ctx);
-    k4_rank<<<chunk_grid, K4_CHUNK, 0, st>>>(regions, R, p->total_chunks, w.parent, w.chunk_base, w.rank);
+    k4_rank<<<chunk_grid, K4_CHUNK, 0, st>>>(regions, R, p->total_chunks, w.chunk_off, w.bits, w.parent, w.chunk_base,
+                                             w.rank);
     QC_LAUNCHED(ctx);
 
-    k4_stats<<<std::min(p->total_bands, sms * 8), K4_THREADS, 0, st>>>(regions, R, p->total_bands, w.bits, w.parent,
-                                                                       w.rank, out_stats);
+    k4_stats<<<band_grid, K4_THREADS, 0, st>>>(regions, R, p->total_bands, w.band_off, w.bits, w.parent, w.rank,
+                                               out_stats);
     QC_LAUNCHED(ctx);
-    k4_final<<<std::min(p->total_bands, sms * 8), K4_THREADS, 0, st>>>(regions, R, p->total_bands, w.bits, w.parent,
-                                                                       out_stats, out_ncomp, out_mask, out_labels,
-                                                                       (long long*)out_area);
+    k4_final<<<band_grid, K4_THREADS, 0, st>>>(regions, R, p->total_bands, w.band_off, w.bits, w.parent, out_stats,
+                                               out_ncomp, out_mask, out_labels, (long long*)out_area);
     QC_LAUNCHED(ctx);
     return QC_OK;
 }

@@ -13,4 +13,5 @@ from qcgraft import ffi  # noqa: E402
 if __name__ == "__main__":
     qc = ffi.Context.current(0)
     peak, _ = bench.measured_peaks()
-    print(json.dumps(bench.kernel_microbench(qc, peak), indent=1))
+    only = set(sys.argv[1:]) or None
+    print(json.dumps(bench.kernel_microbench(qc, peak, only), indent=1))
