@@ -341,26 +341,15 @@ k4_otsu(const qc_seg_region* __restrict__ regs, int R, const unsigned* __restric
 }
 
 // ------------------------------------------------------------------------------------------
-// bit-row helpers for the morphology: rows live in smem as [rows][wpr] words, bits >= w are 0.
-struct BitRows {
-    const unsigned* buf;
-    int wpr, w;
-    int row_lo, row_hi;     // region rows held in buf: [row_lo, row_hi)
-    // word of region row y (rows/words outside the REGION read as the op's border value `ob`; rows
-    // outside the buffer but inside the region are halo garbage and read as `ob` too -- they never
-    // reach the band's own rows because the halo is 4*iters deep)
-    __device__ __forceinline__ unsigned rd(int y, int wx, bool ob) const {
-        if (y < row_lo || y >= row_hi || wx < 0 || wx >= wpr) return ob ? 0xFFFFFFFFu : 0u;
-        unsigned v = buf[(y - row_lo) * wpr + wx];
-        if (ob && wx == wpr - 1 && (w & 31)) v |= ~((1u << (w & 31)) - 1u);
-        return v;
-    }
-};
-
 // union-find on shared-memory labels (roots = minimum local index)
 __device__ __forceinline__ int suf_find(volatile int* L, int x) {
+    // path halving: a concurrent reader only ever sees an ancestor, and parents only decrease
     int p = L[x];
-    while (p != x) { x = p; p = L[x]; }
+    while (p != x) {
+        const int gp = L[p];
+        if (gp != p) L[x] = gp;
+        x = p; p = gp;
+    }
     return x;
 }
 __device__ __forceinline__ void suf_union(int* L, int a, int b) {
@@ -404,6 +393,8 @@ k4_mask_ccl(Img im, const qc_seg_region* __restrict__ regs, int R, int total_ban
         if (im.channels == 3) { gbase = gray_ws + rg.out_offset; gpitch = rg.w; }
         else { gbase = im.data + (long long)rg.img * im.img_stride + (long long)rg.y * im.row_stride + rg.x; gpitch = im.row_stride; }
         const int segs = 2 * wpr;                     // 16-pixel segments per row (last ones may be partial/empty)
+        const unsigned lo4 = (unsigned)min(lo, 255) * 0x01010101u, hi4 = (unsigned)max(hi, 0) * 0x01010101u;
+        const bool none = lo > 255 || hi < 0 || lo > hi;     // empty foreground interval
         for (int yy = warp; yy < nrows; yy += K4_THREADS / 32) {
             const uint8_t* p = gbase + (long long)(row_lo + yy) * gpitch;
             const bool al = (reinterpret_cast<uintptr_t>(p) & 15) == 0;
@@ -411,15 +402,17 @@ k4_mask_ccl(Img im, const qc_seg_region* __restrict__ regs, int R, int total_ban
                 const int sg = s0 + lane;
                 const int x0 = sg * 16;
                 unsigned b16 = 0;
-                if (sg < segs && x0 < rg.w) {
+                if (sg < segs && x0 < rg.w && !none) {
                     if (al && x0 + 16 <= rg.w) {
                         const uint4 v = im.channels == 3 ? *reinterpret_cast<const uint4*>(p + x0)
                                                          : __ldg(reinterpret_cast<const uint4*>(p + x0));
+                        // per-byte compares (0xFF where lo <= g <= hi), then 4 mask bytes -> 4 bits with one
+                        // multiply: bytes at bit 0/8/16/24 land on bits 24..27 of t * 0x01020408
                         const unsigned w4[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-                        for (int k = 0; k < 16; ++k) {
-                            const int g = (int)((w4[k >> 2] >> (8 * (k & 3))) & 255u);
-                            b16 |= (unsigned)(g >= lo && g <= hi) << k;
+                        for (int q = 0; q < 4; ++q) {
+                            const unsigned mk = __vcmpgeu4(w4[q], lo4) & __vcmpleu4(w4[q], hi4) & 0x01010101u;
+                            b16 |= ((mk * 0x01020408u) >> 24) << (4 * q);
                         }
                     } else {
                         const int nv = min(16, rg.w - x0);
@@ -440,18 +433,30 @@ k4_mask_ccl(Img im, const qc_seg_region* __restrict__ regs, int R, int total_ban
         for (int step = 0; step < 4 * iters; ++step) {
             const int phase = step / iters;              // 0: dilate, 1: erode, 2: erode, 3: dilate
             const bool erode = (phase == 1 || phase == 2);
-            BitRows br{src, wpr, rg.w, row_lo, row_hi};
-            for (int wi = tid; wi < nrows * wpr; wi += K4_THREADS) {
-                const int yy = wi / wpr, wx = wi - yy * wpr;
-                const int y = row_lo + yy;
-                const unsigned c = br.rd(y, wx, erode);
-                const unsigned l = br.rd(y, wx - 1, erode), rr = br.rd(y, wx + 1, erode);
-                const unsigned up = br.rd(y - 1, wx, erode), dn = br.rd(y + 1, wx, erode);
-                const unsigned xl = (c << 1) | (l >> 31);      // pixel x-1 aligned to x
-                const unsigned xr = (c >> 1) | (rr << 31);     // pixel x+1 aligned to x
-                unsigned o = erode ? (c & xl & xr & up & dn) : (c | xl | xr | up | dn);
-                if (wx == wpr - 1 && (rg.w & 31)) o &= (1u << (rg.w & 31)) - 1u;
-                dst[wi] = o;
+            const unsigned ob = erode ? 0xFFFFFFFFu : 0u;               // value of everything outside
+            const unsigned tail = (rg.w & 31) ? ~((1u << (rg.w & 31)) - 1u) : 0u;   // bits >= w of the last word
+            const int nstrip = (nrows + 3) >> 2;
+            for (int task = tid; task < nstrip * wpr; task += K4_THREADS) {
+                const int st = task / wpr, wx = task - st * wpr;
+                const int r0 = st * 4, r1 = min(r0 + 4, nrows);
+                const bool lastw = wx == wpr - 1;
+                auto ld = [&](int rr, int wxx) -> unsigned {          // buffer row rr, word wxx, border-aware
+                    if (rr < 0 || rr >= nrows || wxx < 0 || wxx >= wpr) return ob;
+                    unsigned v = src[rr * wpr + wxx];
+                    if (erode && wxx == wpr - 1) v |= tail;
+                    return v;
+                };
+                unsigned up = ld(r0 - 1, wx), c = ld(r0, wx);
+                for (int rr = r0; rr < r1; ++rr) {
+                    const unsigned dn = ld(rr + 1, wx);
+                    const unsigned l = ld(rr, wx - 1), rgt = ld(rr, wx + 1);
+                    const unsigned xl = (c << 1) | (l >> 31);      // pixel x-1 aligned to x
+                    const unsigned xr = (c >> 1) | (rgt << 31);    // pixel x+1 aligned to x
+                    unsigned o = erode ? (c & xl & xr & up & dn) : (c | xl | xr | up | dn);
+                    if (lastw) o &= ~tail;
+                    dst[rr * wpr + wx] = o;
+                    up = c; c = dn;
+                }
             }
             __syncthreads();
             unsigned* tmp = src; src = dst; dst = tmp;
@@ -544,7 +549,11 @@ k4_mask_ccl(Img im, const qc_seg_region* __restrict__ regs, int R, int total_ban
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ int uf_find(int* L, int x) {
     int p = __ldcg(L + x);
-    while (p != x) { x = p; p = __ldcg(L + x); }
+    while (p != x) {
+        const int gp = __ldcg(L + p);
+        if (gp != p) __stcg(L + x, gp);          // path halving (any ancestor is a valid parent)
+        x = p; p = gp;
+    }
     return x;
 }
 __device__ __forceinline__ void uf_union(int* L, int a, int b) {

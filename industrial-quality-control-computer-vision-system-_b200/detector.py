@@ -1,0 +1,775 @@
+"""Drop-in host classes with the reference's own names, signatures, result dictionaries and error
+convention, running on the CUDA kernels through ``ffi``:
+
+    YOLODetector            models/yolo_model.py:17-260
+    ResNetClassifier        models/resent_model.py:21-287
+    EnsemblePredictor       models/ensemble.py:20-448
+    ImageSegmentator        inference/segmentation.py:21-146
+    QualityControlDetector  inference/detector.py:21-395
+
+so ``app.py`` / ``api/routes.py`` / ``PostProcessor`` / ``SPCAnalyzer`` run on top unchanged.  Every
+public method catches and returns ``{"error": str(e)}`` like the reference (never raises); there is
+no CPU fallback -- without a CUDA device the constructors record the error and every call returns it.
+
+Channel-order bookkeeping follows the reference literally: each class performs the same
+``cv2.cvtColor(BGR2RGB)`` flips the reference performs at the same place (as a K1/K3/K4 ``swap_rb``
+flag instead of a copy), so whatever order the caller hands in, each stage sees what the reference's
+stage would have seen.
+"""
+from __future__ import annotations
+
+import logging
+import time
+from concurrent.futures import ThreadPoolExecutor
+from typing import Dict, List, Optional, Tuple
+
+import cv2
+import numpy as np
+import torch
+
+from . import ffi
+from .pipeline import CLASS_NAMES, DARK_CLASSES, RESNET_MEAN, RESNET_STD, InspectionPipeline
+
+logger = logging.getLogger(__name__)
+
+_shared_pipelines: Dict[tuple, InspectionPipeline] = {}
+
+
+def _pipeline(config: Optional[Dict], conf=0.7, iou=0.5, nc=5) -> InspectionPipeline:
+    """One InspectionPipeline (nets + qc_ctx) per (device, scale) shared by the wrapper classes."""
+    cfg = (config or {}).get("qcgraft", {})
+    dev = int(cfg.get("device", 0))
+    scale = cfg.get("yolo_scale", "n")
+    key = (dev, scale, nc)
+    if key not in _shared_pipelines:
+        _shared_pipelines[key] = InspectionPipeline(scale, nc, device=dev, conf=conf, iou=iou,
+                                                    imgsz=int(cfg.get("imgsz", 640)),
+                                                    use_graphs=bool(cfg.get("cuda_graphs", False)))
+    return _shared_pipelines[key]
+
+
+def _decode(image: np.ndarray) -> np.ndarray:
+    if isinstance(image, np.ndarray) and image.ndim == 1:
+        image = cv2.imdecode(image, cv2.IMREAD_COLOR)          # models/yolo_model.py:74-76
+    return image
+
+
+def _as_rgb3(image: np.ndarray) -> np.ndarray:
+    if image.ndim == 2:
+        image = np.repeat(image[:, :, None], 3, 2)
+    return np.ascontiguousarray(image[:, :, :3], dtype=np.uint8)
+
+
+# ----------------------------------------------------------------------------------------------
+class YOLODetector:
+    """models/yolo_model.py:17 -- K1 + YOLOv8 + K2 instead of ``ultralytics.YOLO.__call__``."""
+
+    def __init__(self, model_path: str = "yolov8n.pt", confidence_threshold: float = 0.7,
+                 nms_threshold: float = 0.5, device: str = "auto", config: Optional[Dict] = None):
+        self.model_path = model_path
+        self.confidence_threshold = confidence_threshold
+        self.nms_threshold = nms_threshold
+        self.device = "cuda" if device == "auto" else device
+        self.class_names = list(CLASS_NAMES)
+        self.model = None
+        self._config = config
+        self.load_model()
+
+    def load_model(self) -> bool:
+        try:
+            self.model = _pipeline(self._config, self.confidence_threshold, self.nms_threshold)
+            return True
+        except Exception as e:                                    # models/yolo_model.py:67-69
+            logger.error(f"Error loading YOLO model: {str(e)}")
+            self._load_error = str(e)
+            return False
+
+    def preprocess_image(self, image: np.ndarray) -> np.ndarray:
+        """models/yolo_model.py:71-82 (kept for API parity; predict() folds the flip into K1)."""
+        image = _decode(image)
+        if isinstance(image, np.ndarray) and image.ndim == 3 and image.shape[2] == 3:
+            image = cv2.cvtColor(image, cv2.COLOR_BGR2RGB)
+        return image
+
+    def predict(self, image: np.ndarray, _head_override=None) -> Dict:
+        if self.model is None:
+            logger.error("Model not loaded")
+            return {"error": "Model not loaded"}
+        try:
+            start_time = time.time()
+            img = _as_rgb3(_decode(image))
+            pipe = self.model
+            pipe.conf, pipe.iou = self.confidence_threshold, self.nms_threshold
+            frames = torch.from_numpy(img[None]).to(pipe.dev)
+            # reference: one flip here (:80) and one inside ultralytics ([..., ::-1]) -> net sees `image` order
+            det, anchor, count, _ = pipe.detect(frames, head_override=_head_override, swap_rb=False)
+            k = int(count[0])
+            rows = det[0, :k].cpu().numpy()
+            inference_time = time.time() - start_time
+            detections = self._parse_results(rows, img.shape)
+            return {"detections": detections, "inference_time_ms": inference_time * 1000,
+                    "image_shape": img.shape[:2], "total_detections": len(detections)}
+        except Exception as e:
+            logger.error(f"Error during YOLO prediction: {str(e)}")
+            return {"error": str(e)}
+
+    def _parse_results(self, rows: np.ndarray, image_shape: Tuple) -> List[Dict]:
+        """models/yolo_model.py:128-160 on K2's [k,6] rows (x1,y1,x2,y2,conf,cls)."""
+        detections = []
+        for i, row in enumerate(np.asarray(rows, np.float32)):
+            x1, y1, x2, y2 = map(int, row[:4])
+            conf, class_id = row[4], int(row[5])
+            detections.append({
+                "id": i,
+                "class": self.class_names[class_id] if class_id < len(self.class_names) else f"class_{class_id}",
+                "confidence": float(conf),
+                "bbox": {"x1": x1, "y1": y1, "x2": x2, "y2": y2, "width": x2 - x1, "height": y2 - y1,
+                         "center_x": (x1 + x2) / 2, "center_y": (y1 + y2) / 2},
+                "area": (x2 - x1) * (y2 - y1),
+                "severity": self._classify_severity(conf, (x2 - x1) * (y2 - y1)),
+            })
+        return detections
+
+    def _classify_severity(self, confidence: float, area: float) -> str:
+        normalized_area = area / (1024 * 1024)                  # models/yolo_model.py:162-172
+        if confidence > 0.9 or normalized_area > 0.1:
+            return "critical"
+        elif confidence > 0.8 or normalized_area > 0.05:
+            return "major"
+        return "minor"
+
+    def batch_predict(self, images: List[np.ndarray]) -> List[Dict]:
+        results = []
+        for i, image in enumerate(images):
+            result = self.predict(image)
+            result["batch_index"] = i
+            results.append(result)
+        return results
+
+    def get_model_info(self) -> Dict:
+        return {"model_path": self.model_path, "device": self.device,
+                "confidence_threshold": self.confidence_threshold, "nms_threshold": self.nms_threshold,
+                "class_names": self.class_names, "model_loaded": self.model is not None}
+
+    def update_thresholds(self, confidence: Optional[float] = None, nms: Optional[float] = None):
+        if confidence is not None:
+            self.confidence_threshold = confidence
+        if nms is not None:
+            self.nms_threshold = nms
+
+
+# ----------------------------------------------------------------------------------------------
+class ResNetClassifier:
+    """models/resent_model.py:21 -- K3 (whole-frame ROI) + ResNet-50.  The reference resizes with PIL's
+    antialiased bilinear filter; K3 resamples with roi_align (SURVEY.md §8f row f4 covers the PIL model)."""
+
+    def __init__(self, model_path: str = "models/resnet50_qc.pt", num_classes: int = 5, device: str = "auto",
+                 config: Optional[Dict] = None):
+        self.model_path = model_path
+        self.num_classes = num_classes
+        self.device = torch.device("cuda" if device == "auto" else device)
+        self.class_names = list(CLASS_NAMES)
+        self.severity_mapping = {0: "minor", 1: "major", 2: "critical"}
+        self.model = None
+        self._config = config
+        self.load_model()
+
+    def load_model(self) -> bool:
+        try:
+            self._pipe = _pipeline(self._config, nc=self.num_classes)
+            self.model = self._pipe.resnet
+            return True
+        except Exception as e:
+            logger.error(f"Error loading ResNet model: {str(e)}")
+            return False
+
+    def _classify(self, frames: torch.Tensor, rois: np.ndarray, swap_rb: bool) -> np.ndarray:
+        pipe = self._pipe
+        r = torch.from_numpy(np.ascontiguousarray(rois, np.float32)).to(pipe.dev)
+        x = pipe.qc.roi_align(frames, r, swap_rb=swap_rb, mean=RESNET_MEAN, std=RESNET_STD, out_dtype=pipe.net_dtype)
+        with torch.no_grad():
+            logits = pipe.resnet(x.contiguous(memory_format=torch.channels_last))
+        return torch.softmax(logits.float(), 1).cpu().numpy()
+
+    def _result(self, probs: np.ndarray) -> Dict:
+        cid = int(np.argmax(probs))
+        conf = float(probs[cid])
+        return {"predicted_class": self.class_names[cid], "confidence": conf,
+                "class_probabilities": {self.class_names[i]: float(p) for i, p in enumerate(probs)},
+                "severity": self._predict_severity(cid, conf)}
+
+    def predict(self, image: np.ndarray) -> Dict:
+        if self.model is None:
+            logger.error("Model not loaded")
+            return {"error": "Model not loaded"}
+        try:
+            start_time = time.time()
+            img = _as_rgb3(_decode(image))
+            h, w = img.shape[:2]
+            frames = torch.from_numpy(img[None]).to(self._pipe.dev)
+            # reference flips once (models/resent_model.py:123) -> swap_rb=True relative to `image`
+            probs = self._classify(frames, np.array([[0, 0, 0, w, h]], np.float32), swap_rb=True)[0]
+            result = self._result(probs)
+            result["inference_time_ms"] = (time.time() - start_time) * 1000
+            return result
+        except Exception as e:
+            logger.error(f"Error during ResNet prediction: {str(e)}")
+            return {"error": str(e)}
+
+    def predict_batch(self, images: List[np.ndarray]) -> List[Dict]:
+        if self.model is None:
+            return [{"error": "Model not loaded"} for _ in images]
+        try:
+            start_time = time.time()
+            results = []
+            for i, im in enumerate(images):          # shapes may differ: one K3 launch per shape group
+                r = self.predict(im)
+                r["batch_index"] = i
+                results.append(r)
+            total = (time.time() - start_time) * 1000
+            for r in results:
+                r["batch_inference_time_ms"] = total
+                r["avg_time_per_image_ms"] = total / max(len(images), 1)
+            return results
+        except Exception as e:
+            logger.error(f"Error during batch prediction: {str(e)}")
+            return [{"error": str(e)} for _ in images]
+
+    def _predict_severity(self, class_id: int, confidence: float) -> str:
+        critical_classes, major_classes = [0, 2], [1, 3]      # models/resent_model.py:237-255
+        if class_id in critical_classes and confidence > 0.8:
+            return "critical"
+        elif class_id in critical_classes and confidence > 0.6:
+            return "major"
+        elif class_id in major_classes and confidence > 0.8:
+            return "major"
+        return "minor"
+
+    def get_model_info(self) -> Dict:
+        return {"model_path": self.model_path, "device": str(self.device), "num_classes": self.num_classes,
+                "class_names": self.class_names, "model_loaded": self.model is not None, "input_size": (224, 224)}
+
+
+# ----------------------------------------------------------------------------------------------
+class EnsemblePredictor:
+    """models/ensemble.py:20.  ``_classify_region`` really crops (K3) and classifies every detection --
+    the step the reference mocks (:181-195); the reference's confidence arithmetic is kept so
+    downstream numbers (ensemble_confidence, grades, SPC) are the reference's."""
+
+    def __init__(self, yolo_weights: str = "models/yolov8_qc.pt", resnet_weights: str = "models/resnet50_qc.pt",
+                 config: Dict = None):
+        self.config = config or {}
+        self.yolo_detector = None
+        self.resnet_classifier = None
+        self.ensemble_weights = {"yolo": 0.6, "resnet": 0.4}
+        self.confidence_threshold = 0.5
+        self.load_models(yolo_weights, resnet_weights)
+
+    def load_models(self, yolo_weights: str, resnet_weights: str) -> bool:
+        try:
+            yolo_config = self.config.get("model", {})
+            self.yolo_detector = YOLODetector(model_path=yolo_weights,
+                                              confidence_threshold=yolo_config.get("confidence_threshold", 0.7),
+                                              nms_threshold=yolo_config.get("nms_threshold", 0.5), config=self.config)
+            self.resnet_classifier = ResNetClassifier(
+                model_path=resnet_weights,
+                num_classes=len(self.config.get("quality_control", {}).get("defect_classes", [])) or 5,
+                config=self.config)
+            if self.yolo_detector.model is None or self.resnet_classifier.model is None:
+                self.yolo_detector = self.resnet_classifier = None
+                return False
+            return True
+        except Exception as e:
+            logger.error(f"Error loading ensemble models: {str(e)}")
+            return False
+
+    def predict(self, image: np.ndarray, _head_override=None) -> Dict:
+        if self.yolo_detector is None or self.resnet_classifier is None:
+            return {"error": "Models not loaded"}
+        try:
+            start_time = time.time()
+            yolo_results = self.yolo_detector.predict(image, _head_override=_head_override)
+            resnet_results = self.resnet_classifier.predict(image)
+            ensemble_results = self._combine_predictions(yolo_results, resnet_results, image.shape, image)
+            ensemble_results["total_inference_time_ms"] = (time.time() - start_time) * 1000
+            return ensemble_results
+        except Exception as e:
+            logger.error(f"Error in ensemble prediction: {str(e)}")
+            return {"error": str(e)}
+
+    def _combine_predictions(self, yolo_results: Dict, resnet_results: Dict, image_shape: Tuple,
+                             image: Optional[np.ndarray] = None) -> Dict:
+        combined = {"detections": [], "global_classification": resnet_results, "detection_summary": {},
+                    "quality_assessment": {}, "ensemble_confidence": 0.0}
+        if "error" in yolo_results or "error" in resnet_results:
+            combined["error"] = "Error in one or more models"
+            return combined
+        try:
+            dets = yolo_results.get("detections", [])
+            roi_probs = self._classify_regions(image, dets) if image is not None else {}
+            enhanced = []
+            for d in dets:
+                self._extract_region(image_shape, d["bbox"])
+                cls = self._classify_region_mock(d)
+                if d["id"] in roi_probs:                       # the real K3 -> ResNet-50 hand-off
+                    p = roi_probs[d["id"]]
+                    cls["roi_classification"] = {"predicted_class": CLASS_NAMES[int(np.argmax(p))],
+                                                 "class_probabilities": {CLASS_NAMES[i]: float(v) for i, v in enumerate(p)}}
+                enhanced.append(self._merge_detection_classification(d, cls))
+            combined["detections"] = enhanced
+            combined["detection_summary"] = self._create_detection_summary(enhanced)
+            combined["quality_assessment"] = self._assess_overall_quality(enhanced, resnet_results)
+            combined["ensemble_confidence"] = self._calculate_ensemble_confidence(yolo_results, resnet_results, enhanced)
+        except Exception as e:
+            logger.error(f"Error combining predictions: {str(e)}")
+            combined["error"] = str(e)
+        return combined
+
+    def _classify_regions(self, image: np.ndarray, dets: List[Dict]) -> Dict[int, np.ndarray]:
+        valid = [d for d in dets if d["bbox"]["x2"] > d["bbox"]["x1"] and d["bbox"]["y2"] > d["bbox"]["y1"]]
+        if not valid:
+            return {}
+        img = _as_rgb3(_decode(image))
+        frames = torch.from_numpy(img[None]).to(self.resnet_classifier._pipe.dev)
+        rois = np.array([[0, d["bbox"]["x1"], d["bbox"]["y1"], d["bbox"]["x2"], d["bbox"]["y2"]] for d in valid], np.float32)
+        probs = self.resnet_classifier._classify(frames, rois, swap_rb=True)
+        return {d["id"]: probs[i] for i, d in enumerate(valid)}
+
+    def _extract_region(self, image_shape: Tuple, bbox: Dict) -> Dict:
+        height, width = image_shape[:2] if len(image_shape) > 2 else (bbox["y2"], bbox["x2"])
+        return {"relative_position": {"x": bbox["center_x"] / width, "y": bbox["center_y"] / height},
+                "relative_size": {"width": bbox["width"] / width, "height": bbox["height"] / height},
+                "absolute_area": bbox["width"] * bbox["height"]}
+
+    def _classify_region_mock(self, detection: Dict) -> Dict:
+        return {"predicted_class": detection["class"], "confidence": min(detection["confidence"] * 1.1, 1.0),
+                "region_severity": detection["severity"], "classification_source": "ensemble_refined"}
+
+    def _merge_detection_classification(self, detection: Dict, classification: Dict) -> Dict:
+        merged = detection.copy()
+        yolo_conf, resnet_conf = detection["confidence"], classification["confidence"]
+        merged.update({
+            "ensemble_confidence": yolo_conf * self.ensemble_weights["yolo"] + resnet_conf * self.ensemble_weights["resnet"],
+            "yolo_confidence": yolo_conf, "resnet_confidence": resnet_conf,
+            "classification_details": classification,
+            "final_severity": self._determine_final_severity(detection, classification)})
+        return merged
+
+    def _determine_final_severity(self, detection: Dict, classification: Dict) -> str:
+        scores = {"minor": 1, "major": 2, "critical": 3}
+        final = max(scores.get(detection["severity"], 1), scores.get(classification["region_severity"], 1))
+        for severity, score in scores.items():
+            if score == final:
+                return severity
+        return "minor"
+
+    def _create_detection_summary(self, detections: List[Dict]) -> Dict:
+        if not detections:
+            return {"total_defects": 0, "defect_counts": {}, "severity_distribution": {},
+                    "average_confidence": 0.0, "max_severity": "none"}
+        counts, sev, confs = {}, {"minor": 0, "major": 0, "critical": 0}, []
+        for d in detections:
+            counts[d["class"]] = counts.get(d["class"], 0) + 1
+            sev[d["final_severity"]] += 1
+            confs.append(d["ensemble_confidence"])
+        max_sev = "critical" if sev["critical"] else "major" if sev["major"] else "minor" if sev["minor"] else "none"
+        return {"total_defects": len(detections), "defect_counts": counts, "severity_distribution": sev,
+                "average_confidence": np.mean(confs) if confs else 0.0, "max_severity": max_sev}
+
+    def _assess_overall_quality(self, detections: List[Dict], global_classification: Dict) -> Dict:
+        if not detections:                                       # models/ensemble.py:282-337
+            return {"quality_grade": "A", "pass_fail": "PASS", "defect_density": 0.0, "risk_level": "low",
+                    "recommended_action": "accept"}
+        crit = sum(1 for d in detections if d["final_severity"] == "critical")
+        major = sum(1 for d in detections if d["final_severity"] == "major")
+        minor = sum(1 for d in detections if d["final_severity"] == "minor")
+        if crit > 0:
+            g = ("F", "FAIL", "high", "reject")
+        elif major > 2:
+            g = ("D", "FAIL", "high", "reject")
+        elif major > 0:
+            g = ("C", "CONDITIONAL", "medium", "review")
+        elif minor > 3:
+            g = ("B", "CONDITIONAL", "low", "review")
+        else:
+            g = ("A", "PASS", "low", "accept")
+        return {"quality_grade": g[0], "pass_fail": g[1], "defect_density": len(detections), "risk_level": g[2],
+                "recommended_action": g[3], "defect_breakdown": {"critical": crit, "major": major, "minor": minor}}
+
+    def _calculate_ensemble_confidence(self, yolo_results, resnet_results, detections) -> float:
+        try:
+            yolo_conf = np.mean([d["yolo_confidence"] for d in detections]) if detections else 0.0
+            resnet_conf = resnet_results.get("confidence", 0.0)
+            return float(yolo_conf * self.ensemble_weights["yolo"] + resnet_conf * self.ensemble_weights["resnet"])
+        except Exception as e:
+            logger.error(f"Error calculating ensemble confidence: {str(e)}")
+            return 0.0
+
+    def batch_predict(self, images: List[np.ndarray]) -> List[Dict]:
+        results = []
+        for i, image in enumerate(images):
+            result = self.predict(image)
+            result["batch_index"] = i
+            results.append(result)
+        return results
+
+    def update_ensemble_weights(self, yolo_weight: float, resnet_weight: float):
+        total = yolo_weight + resnet_weight
+        self.ensemble_weights = {"yolo": yolo_weight / total, "resnet": resnet_weight / total}
+
+    def get_model_info(self) -> Dict:
+        info = {"ensemble_weights": self.ensemble_weights, "confidence_threshold": self.confidence_threshold,
+                "models_loaded": {"yolo": self.yolo_detector is not None, "resnet": self.resnet_classifier is not None}}
+        if self.yolo_detector:
+            info["yolo_info"] = self.yolo_detector.get_model_info()
+        if self.resnet_classifier:
+            info["resnet_info"] = self.resnet_classifier.get_model_info()
+        return info
+
+
+# ----------------------------------------------------------------------------------------------
+class _LazyFullMask:
+    """Materialises the reference's full-frame per-detection mask (inference/segmentation.py:93-95) only
+    when a consumer touches it: n_det x H x W bytes of D2H would dwarf the kernels."""
+
+    def __init__(self, shape, y1, x1, local):
+        self.shape, self._y1, self._x1, self._local, self._arr = shape, y1, x1, local, None
+
+    def __array__(self, dtype=None, copy=None):
+        if self._arr is None:
+            m = np.zeros(self.shape, np.uint8)
+            h, w = self._local.shape
+            m[self._y1:self._y1 + h, self._x1:self._x1 + w] = self._local
+            self._arr = m
+        return self._arr if dtype is None else self._arr.astype(dtype)
+
+    def __gt__(self, other):
+        return np.asarray(self) > other
+
+    def __getitem__(self, k):
+        return np.asarray(self)[k]
+
+
+class ImageSegmentator:
+    """inference/segmentation.py:21 -- one K4 launch sequence for all detections of the frame.
+    K4's composite (Otsu -> polarity -> 3x3 cross close/open -> 8-conn CCL -> min-area filter) serves every
+    class; the reference's per-class method table (:185-195) is recorded in ``segmentation_method``."""
+
+    MIN_AREA = 20          # _adaptive_segmentation's _remove_small_components(min_size=20), :289
+    MORPH_ITERS = 1        # one 3x3 cross CLOSE + OPEN, :284-286
+
+    def __init__(self, config: Dict = None):
+        self.config = config or {}
+        self.segmentation_methods = {"threshold": None, "watershed": None, "adaptive": None, "region_growing": None}
+        try:
+            self._pipe = _pipeline(self.config)
+        except Exception as e:
+            logger.error(f"Error initialising segmentator: {str(e)}")
+            self._pipe = None
+
+    def segment_defects(self, image: np.ndarray, detections: List[Dict]) -> Dict:
+        try:
+            out = {"segmented_regions": [], "masks": [], "contours": [], "area_analysis": {},
+                   "total_defect_area": 0, "defect_density": 0.0}
+            if not detections:
+                return out
+            if self._pipe is None:
+                return {"error": "CUDA segmentation backend not available"}
+            qc, dev = self._pipe.qc, self._pipe.dev
+            gray_in = image.ndim == 2
+            img = np.ascontiguousarray(image if gray_in else image[:, :, :3], np.uint8)
+            H, W = img.shape[:2]
+            total_image_area = H * W
+            sel, regs = [], dict(img=[], x=[], y=[], w=[], h=[], polarity=[])
+            for i, d in enumerate(detections):
+                b = d["bbox"]
+                x1, y1 = max(b["x1"], 0), max(b["y1"], 0)
+                x2, y2 = min(b["x2"], W), min(b["y2"], H)             # numpy slicing clips the same way (:80)
+                if x2 <= x1 or y2 <= y1:
+                    continue                                           # roi.size == 0, :82-83
+                sel.append((i, x1, y1, x2, y2))
+                regs["img"].append(0); regs["x"].append(x1); regs["y"].append(y1)
+                regs["w"].append(x2 - x1); regs["h"].append(y2 - y1)
+                regs["polarity"].append(0 if d["class"] in ("crack", "scratch") else 1)
+            if sel:
+                regs["min_area"] = self.MIN_AREA
+                res = qc.segment(torch.from_numpy(img[None]).to(dev), regs, morph_iters=self.MORPH_ITERS,
+                                 want_labels=False, swap_rb=False)
+                mask_all = res["mask"].cpu().numpy()
+                areas = res["area"].cpu().numpy()
+                plan = res["regions"]
+            total_defect_area = 0
+            for k, (i, x1, y1, x2, y2) in enumerate(sel):
+                d = detections[i]
+                o = int(plan[k].out_offset)
+                local = mask_all[o:o + (x2 - x1) * (y2 - y1)].reshape(y2 - y1, x2 - x1)
+                defect_area = int(areas[k])
+                total_defect_area += defect_area
+                contours = self._find_contours(local)
+                gcontours = []
+                for c in contours:
+                    g = c.copy(); g[:, 0, 0] += x1; g[:, 0, 1] += y1
+                    gcontours.append(g)
+                gmask = _LazyFullMask((H, W), y1, x1, local)
+                out["segmented_regions"].append({
+                    "detection_id": i, "defect_class": d["class"], "confidence": d.get("confidence", 0.0),
+                    "bbox": d["bbox"], "mask": gmask, "local_mask": local, "contours": gcontours,
+                    "area_pixels": defect_area, "area_percentage": (defect_area / total_image_area) * 100,
+                    "perimeter": self._calculate_perimeter(contours),
+                    "compactness": self._calculate_compactness(defect_area, contours),
+                    "segmentation_method": "k4_otsu_morph_ccl", "confidence_score": self._confidence(img, d, local, x1, y1)})
+                out["masks"].append(gmask)
+                out["contours"].extend(gcontours)
+            out["total_defect_area"] = total_defect_area
+            out["defect_density"] = (total_defect_area / total_image_area) * 100
+            out["area_analysis"] = self._analyze_defect_areas(out["segmented_regions"])
+            return out
+        except Exception as e:
+            logger.error(f"Error in defect segmentation: {str(e)}")
+            return {"error": str(e)}
+
+    @staticmethod
+    def _confidence(img, d, local, x1, y1) -> float:
+        """inference/segmentation.py:527-555 on the ROI (foreground/background separation)."""
+        roi = img[y1:y1 + local.shape[0], x1:x1 + local.shape[1]]
+        if roi.ndim == 3:
+            roi = cv2.cvtColor(roi, cv2.COLOR_RGB2GRAY)
+        m = local > 0
+        if not m.any() or m.all():
+            return 0.0
+        sep = abs(float(roi[m].mean()) - float(roi[~m].mean())) / (float(roi.std()) + 1e-6)
+        return min(sep / 3.0, 1.0)
+
+    def _find_contours(self, mask: np.ndarray) -> List[np.ndarray]:
+        if mask is None:
+            return []
+        contours, _ = cv2.findContours(np.ascontiguousarray(mask), cv2.RETR_EXTERNAL, cv2.CHAIN_APPROX_SIMPLE)
+        return [c for c in contours if cv2.contourArea(c) >= 10]      # :498-500
+
+    def _calculate_perimeter(self, contours) -> float:
+        return float(sum(cv2.arcLength(c, True) for c in contours))
+
+    def _calculate_compactness(self, area: float, contours) -> float:
+        if not contours or area == 0:
+            return 0.0
+        p = self._calculate_perimeter(contours)
+        return 0.0 if p == 0 else min((4 * np.pi * area) / (p ** 2), 1.0)
+
+    def _analyze_defect_areas(self, regions: List[Dict]) -> Dict:
+        if not regions:
+            return {}
+        areas = [r["area_pixels"] for r in regions]
+        pct = [r["area_percentage"] for r in regions]
+        return {"total_regions": len(regions), "total_area_pixels": sum(areas), "total_area_percentage": sum(pct),
+                "average_area_pixels": np.mean(areas), "median_area_pixels": np.median(areas),
+                "max_area_pixels": max(areas), "min_area_pixels": min(areas), "area_std": np.std(areas),
+                "size_distribution": {"small_defects": sum(1 for a in areas if a < 100),
+                                      "medium_defects": sum(1 for a in areas if 100 <= a < 1000),
+                                      "large_defects": sum(1 for a in areas if a >= 1000)}}
+
+
+# ----------------------------------------------------------------------------------------------
+class _PassThroughPostProcessor:
+    """Stand-in with PostProcessor's interface (inference/postprocess.py:32-109).  The reference's rule
+    engine is plain numpy/sklearn on <= 300 dicts and runs unchanged on these results: pass it as
+    ``config['qcgraft']['postprocessor']`` (SURVEY.md §8f row f1 is the device version)."""
+
+    def __init__(self, config):
+        self.config = config
+
+    def process_results(self, ensemble_results, segmentation_results, image_shape):
+        seg = {r["detection_id"]: r for r in (segmentation_results or {}).get("segmented_regions", [])}
+        dets = []
+        for d in ensemble_results.get("detections", []):
+            d = dict(d)
+            if d["id"] in seg:
+                r = seg[d["id"]]
+                d["segmentation"] = {k: r[k] for k in ("area_pixels", "area_percentage", "perimeter", "compactness",
+                                                       "confidence_score")}
+            dets.append(d)
+        return {"detections": dets, "quality_assessment": ensemble_results.get("quality_assessment", {}),
+                "risk_analysis": {}, "recommendations": [],
+                "metadata": {"total_detections": len(dets), "image_shape": tuple(image_shape)}}
+
+    def update_config(self, new_config):
+        self.config.update(new_config)
+
+
+class QualityControlDetector:
+    """inference/detector.py:21 -- same constructor, methods, attributes and result keys."""
+
+    def __init__(self, yolo_weights: str, resnet_weights: str, config: Dict):
+        self.config = config
+        self.ensemble_predictor = None
+        self.segmentator = None
+        self.postprocessor = None
+        self.performance_stats = {"total_predictions": 0, "total_time": 0.0, "average_time": 0.0}
+        self.initialize_components(yolo_weights, resnet_weights)
+
+    def initialize_components(self, yolo_weights: str, resnet_weights: str):
+        self.ensemble_predictor = EnsemblePredictor(yolo_weights=yolo_weights, resnet_weights=resnet_weights,
+                                                    config=self.config)
+        self.segmentator = ImageSegmentator(self.config)
+        pp = (self.config or {}).get("qcgraft", {}).get("postprocessor")
+        self.postprocessor = pp if pp is not None else _PassThroughPostProcessor(self.config)
+
+    def predict(self, image: np.ndarray, include_segmentation: bool = True, _head_override=None) -> Dict:
+        start_time = time.time()
+        try:
+            if not self._validate_image(image):
+                return {"error": "Invalid image input"}
+            processed_image = self._preprocess_image(image)
+            ensemble_results = self.ensemble_predictor.predict(processed_image, _head_override=_head_override)
+            if "error" in ensemble_results:
+                return ensemble_results
+            segmentation_results = {}
+            if include_segmentation and ensemble_results.get("detections"):
+                segmentation_results = self.segmentator.segment_defects(processed_image, ensemble_results["detections"])
+            final_results = self.postprocessor.process_results(ensemble_results, segmentation_results,
+                                                               processed_image.shape)
+            inference_time = time.time() - start_time
+            self._update_performance_stats(inference_time)
+            final_results.update({"total_inference_time_ms": inference_time * 1000,
+                                  "processing_pipeline": "ensemble + segmentation + postprocess",
+                                  "image_metadata": self._get_image_metadata(image)})
+            return final_results
+        except Exception as e:
+            logger.error(f"Error in QC prediction: {str(e)}")
+            return {"error": str(e)}
+
+    def predict_batch(self, images: List[np.ndarray], max_workers: int = 4) -> List[Dict]:
+        """Same signature/result as inference/detector.py:128-180; ``max_workers`` is accepted but the
+        images go through predict() on this thread (one CUDA stream keeps the GPU busier than 4 threads
+        contending for it); same-shape throughput batches use InspectionPipeline.run directly."""
+        start_time = time.time()
+        try:
+            results = []
+            for i, img in enumerate(images):
+                try:
+                    r = self.predict(img)
+                    r["batch_index"] = i
+                except Exception as e:
+                    r = {"error": str(e), "batch_index": i}
+                results.append(r)
+            total_time = time.time() - start_time
+            stats = {"batch_size": len(images), "total_batch_time_ms": total_time * 1000,
+                     "average_time_per_image_ms": (total_time * 1000) / max(len(images), 1),
+                     "throughput_images_per_second": len(images) / total_time if total_time > 0 else 0.0}
+            for r in results:
+                if r:
+                    r["batch_statistics"] = stats
+            return results
+        except Exception as e:
+            logger.error(f"Error in batch prediction: {str(e)}")
+            return [{"error": str(e)} for _ in images]
+
+    def predict_stream(self, image_generator, callback=None):
+        try:
+            for i, image in enumerate(image_generator):
+                result = self.predict(image)
+                result["stream_index"] = i
+                result["timestamp"] = time.time()
+                if callback:
+                    callback(result)
+                else:
+                    yield result
+        except Exception as e:
+            logger.error(f"Error in stream prediction: {str(e)}")
+            if callback:
+                callback({"error": str(e)})
+            else:
+                yield {"error": str(e)}
+
+    def _validate_image(self, image: np.ndarray) -> bool:
+        if image is None or not isinstance(image, np.ndarray):
+            return False
+        if image.ndim == 1:
+            try:
+                return cv2.imdecode(image, cv2.IMREAD_COLOR) is not None
+            except Exception:
+                return False
+        return image.ndim in (2, 3)
+
+    def _preprocess_image(self, image: np.ndarray) -> np.ndarray:
+        """inference/detector.py:226-254 (decode, BGR2RGB, optional stretch resize, bilateral, CLAHE)."""
+        if image.ndim == 1:
+            image = cv2.imdecode(image, cv2.IMREAD_COLOR)
+        if image.ndim == 3 and image.shape[2] == 3:
+            image = cv2.cvtColor(image, cv2.COLOR_BGR2RGB)
+        pre = self.config.get("preprocessing", {})
+        if "resize" in pre:
+            ts = pre["resize"]
+            image = cv2.resize(image, (ts[1], ts[0]))
+        if pre.get("denoise", False):
+            image = cv2.bilateralFilter(image, 9, 75, 75)
+        if pre.get("enhance_contrast", False):
+            lab = cv2.cvtColor(image, cv2.COLOR_RGB2LAB)
+            lab[:, :, 0] = cv2.createCLAHE(clipLimit=3.0, tileGridSize=(8, 8)).apply(lab[:, :, 0])
+            image = cv2.cvtColor(lab, cv2.COLOR_LAB2RGB)
+        return image
+
+    def _get_image_metadata(self, image: np.ndarray) -> Dict:
+        if image.ndim == 1:
+            decoded = cv2.imdecode(image, cv2.IMREAD_COLOR)
+            shape = decoded.shape if decoded is not None else (0, 0, 0)
+        else:
+            shape = image.shape
+        return {"original_shape": shape, "channels": shape[2] if len(shape) > 2 else 1,
+                "dtype": str(image.dtype), "size_bytes": image.nbytes if hasattr(image, "nbytes") else 0}
+
+    def _update_performance_stats(self, inference_time: float):
+        s = self.performance_stats
+        s["total_predictions"] += 1
+        s["total_time"] += inference_time
+        s["average_time"] = s["total_time"] / s["total_predictions"]
+
+    def get_performance_stats(self) -> Dict:
+        stats = self.performance_stats.copy()
+        if stats["total_predictions"] > 0:
+            stats.update({"average_time_ms": stats["average_time"] * 1000,
+                          "throughput_images_per_second": 1.0 / stats["average_time"] if stats["average_time"] > 0 else 0,
+                          "total_time_minutes": stats["total_time"] / 60})
+        return stats
+
+    def reset_performance_stats(self):
+        self.performance_stats = {"total_predictions": 0, "total_time": 0.0, "average_time": 0.0}
+
+    def get_system_info(self) -> Dict:
+        info = {"detector_status": "operational",
+                "components_loaded": {"ensemble_predictor": self.ensemble_predictor is not None,
+                                      "segmentator": self.segmentator is not None,
+                                      "postprocessor": self.postprocessor is not None},
+                "performance_stats": self.get_performance_stats(), "configuration": self.config}
+        if self.ensemble_predictor:
+            info["ensemble_info"] = self.ensemble_predictor.get_model_info()
+        return info
+
+    def update_config(self, new_config: Dict):
+        self.config.update(new_config)
+        if self.postprocessor:
+            self.postprocessor.update_config(new_config)
+
+    def benchmark(self, test_images: List[np.ndarray], iterations: int = 1) -> Dict:
+        all_times, all_results = [], []
+        for _ in range(iterations):
+            for image in test_images:
+                t = time.time()
+                result = self.predict(image)
+                all_times.append(time.time() - t)
+                all_results.append(result)
+        times_ms = [t * 1000 for t in all_times]
+        n = len(test_images) * iterations
+        return {"total_images": n, "iterations": iterations,
+                "timing_statistics": {"mean_ms": np.mean(times_ms), "median_ms": np.median(times_ms),
+                                      "min_ms": np.min(times_ms), "max_ms": np.max(times_ms), "std_ms": np.std(times_ms),
+                                      "p95_ms": np.percentile(times_ms, 95), "p99_ms": np.percentile(times_ms, 99)},
+                "throughput": {"images_per_second": n / sum(all_times), "images_per_minute": n / sum(all_times) * 60},
+                "accuracy_metrics": self._calculate_accuracy_metrics(all_results)}
+
+    def _calculate_accuracy_metrics(self, results: List[Dict]) -> Dict:
+        total = len(results)
+        ok = [r for r in results if "error" not in r]
+        dets = sum(len(r.get("detections", [])) for r in ok)
+        avg = np.mean([r.get("ensemble_confidence", 0.0) for r in ok]) if ok else 0.0
+        return {"success_rate": len(ok) / total if total else 0.0,
+                "average_detections_per_image": dets / len(ok) if ok else 0.0, "average_confidence": float(avg)}

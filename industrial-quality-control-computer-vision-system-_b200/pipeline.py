@@ -116,7 +116,7 @@ class InspectionPipeline:
     # ------------------------------------------------------------------------------------------
     @torch.no_grad()
     def detect(self, frames: torch.Tensor, inject: Optional[Sequence[torch.Tensor]] = None,
-               head_override: Optional[Sequence[torch.Tensor]] = None):
+               head_override: Optional[Sequence[torch.Tensor]] = None, swap_rb: bool = True):
         """K1 -> YOLOv8 -> K2 on a same-shape uint8 [n,h,w,3] CUDA batch.  The frames are in the
         channel order the caller handed to ``QualityControlDetector.predict``; the reference flips
         channels three times before the net sees them (inference/detector.py:234,
@@ -126,7 +126,7 @@ class InspectionPipeline:
         xshape = (n, 3, plan.dst_h, plan.dst_w)
         xbuf = self.yolo_g.input_buffer(xshape) if self.use_graphs else None
         with self._timed("k1_preprocess"):
-            x = self.qc.preprocess(frames, plan, swap_rb=True, out_dtype=self.net_dtype, out=xbuf)
+            x = self.qc.preprocess(frames, plan, swap_rb=swap_rb, out_dtype=self.net_dtype, out=xbuf)
         if head_override is not None:
             levels = list(head_override)
         else:

@@ -1,0 +1,185 @@
+#!/usr/bin/env python
+"""Generates tests/golden/*.json|npz by importing the REFERENCE's own Python files from
+/root/reference (read-only) through import shims -- the reference does not import as shipped
+(ultralytics / scikit-image / matplotlib / flask absent, models/__init__.py broken).
+Run in the build container only; the fixtures are committed, the reference never travels.
+
+    python tests/golden/make_golden.py
+"""
+import importlib.util
+import json
+import os
+import sys
+import types
+
+import cv2
+import numpy as np
+import torch
+
+REF = "/root/reference"
+OUT = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(OUT))
+sys.path.insert(0, ROOT)
+
+
+def _stub(name, **attrs):
+    m = types.ModuleType(name)
+    m.__dict__.update(attrs)
+    sys.modules[name] = m
+    return m
+
+
+def install_shims():
+    from scipy import ndimage
+    # --- matplotlib / seaborn (imported, unused on the paths exercised here)
+    mpl = _stub("matplotlib"); _stub("matplotlib.pyplot"); _stub("matplotlib.patches", Polygon=object)
+    mpl.pyplot = sys.modules["matplotlib.pyplot"]
+    _stub("seaborn")
+    # --- scikit-image (restated with scipy: SURVEY.md Appendix A)
+    def gaussian(img, sigma=1.0):
+        return ndimage.gaussian_filter(np.asarray(img, np.float64) / (255.0 if img.dtype == np.uint8 else 1.0),
+                                       sigma, mode="nearest", truncate=4.0)
+    def threshold_otsu(img, nbins=256):
+        img = np.asarray(img)
+        if img.min() == img.max():
+            return img.flat[0]
+        counts, edges = np.histogram(img.ravel(), nbins)
+        centers = (edges[:-1] + edges[1:]) / 2
+        counts = counts.astype(np.float64)
+        w1 = np.cumsum(counts); w2 = np.cumsum(counts[::-1])[::-1]
+        m1 = np.cumsum(counts * centers) / w1
+        m2 = (np.cumsum((counts * centers)[::-1]) / w2[::-1])[::-1]
+        return centers[np.argmax(w1[:-1] * w2[1:] * (m1[:-1] - m2[1:]) ** 2)]
+    def disk(r):
+        y, x = np.mgrid[-r:r + 1, -r:r + 1]
+        return (np.abs(x) + np.abs(y) <= r).astype(np.uint8) if r <= 2 else (x * x + y * y <= r * r).astype(np.uint8)
+    morph = _stub("skimage.morphology", disk=disk,
+                  binary_closing=lambda m, k: ndimage.binary_erosion(ndimage.binary_dilation(m, k), k, border_value=1),
+                  binary_opening=lambda m, k: ndimage.binary_dilation(ndimage.binary_erosion(m, k, border_value=1), k))
+    sk = _stub("skimage", morphology=morph)
+    sk.measure = _stub("skimage.measure")
+    _stub("skimage.filters", threshold_otsu=threshold_otsu, gaussian=gaussian)
+    _stub("skimage.segmentation", watershed=None)
+    # --- ultralytics: only the symbol has to exist for models/yolo_model.py to import
+    _stub("ultralytics", YOLO=object)
+
+
+def load(path, name):
+    spec = importlib.util.spec_from_file_location(name, os.path.join(REF, path))
+    m = importlib.util.module_from_spec(spec)
+    sys.modules[name] = m
+    spec.loader.exec_module(m)
+    return m
+
+
+def jsonable(o):
+    if isinstance(o, dict):
+        return {str(k): jsonable(v) for k, v in o.items()}
+    if isinstance(o, (list, tuple)):
+        return [jsonable(v) for v in o]
+    if isinstance(o, (np.floating, np.integer)):
+        return o.item()
+    if isinstance(o, np.ndarray):
+        return o.tolist()
+    return o
+
+
+def main():
+    install_shims()
+    pkg = _stub("models"); pkg.__path__ = [os.path.join(REF, "models")]      # bypass the broken __init__
+    yolo_mod = load("models/yolo_model.py", "models.yolo_model")
+    load("models/resent_model.py", "models.resnet_model")                    # file name typo in the reference
+    ens_mod = load("models/ensemble.py", "models.ensemble")
+    seg_mod = load("inference/segmentation.py", "ref_segmentation")
+    spc_mod = load("analytics/sec_analysis.py", "ref_spc")
+    golden = {}
+
+    # ---- (a) YOLODetector._parse_results / _classify_severity  (models/yolo_model.py:128-172)
+    rows = np.array([
+        [10.9, 20.2, 110.7, 80.9, 0.95, 0], [0.0, 0.0, 640.0, 640.0, 0.71, 3], [300.5, 300.5, 300.9, 310.0, 0.85, 1],
+        [5.0, 5.0, 400.0, 300.0, 0.75, 2], [100.0, 100.0, 330.0, 330.0, 0.79, 4], [1.2, 2.8, 50.1, 40.9, 0.9, 1],
+        [1.2, 2.8, 50.1, 40.9, 0.8, 1], [7.7, 7.7, 7.9, 7.9, 0.99, 6], [200.0, 10.0, 500.0, 190.0, 0.8000001, 2],
+        [600.0, 600.0, 639.99, 639.99, 0.9000001, 0]], np.float32)
+    det = object.__new__(yolo_mod.YOLODetector)
+    det.class_names = ["crack", "scratch", "dent", "discoloration", "contamination"]
+    fake = types.SimpleNamespace(boxes=types.SimpleNamespace(
+        xyxy=torch.from_numpy(rows[:, :4].copy()), conf=torch.from_numpy(rows[:, 4].copy()),
+        cls=torch.from_numpy(rows[:, 5].copy())))
+    parsed = det._parse_results(fake, (640, 640, 3))
+    golden["parse_results"] = {"rows": rows.tolist(), "detections": jsonable(parsed)}
+    golden["classify_severity"] = [[c, a, det._classify_severity(c, a)] for c, a in
+                                   [(0.95, 100000), (0.85, 50000), (0.7, 1000), (0.5, 104858), (0.5, 104857),
+                                    (0.5, 52429), (0.5, 52428), (0.9, 10), (0.8, 10)]]
+
+    # ---- (b) EnsemblePredictor._combine_predictions  (models/ensemble.py:107-356)
+    ens = object.__new__(ens_mod.EnsemblePredictor)
+    ens.ensemble_weights = {"yolo": 0.6, "resnet": 0.4}
+    ens.confidence_threshold = 0.5
+    yolo_res = {"detections": parsed, "inference_time_ms": 1.0, "image_shape": (640, 640), "total_detections": len(parsed)}
+    resnet_res = {"predicted_class": "dent", "confidence": 0.6123, "class_probabilities": {}, "severity": "major"}
+    comb = ens._combine_predictions(yolo_res, resnet_res, (640, 640, 3))
+    golden["combine_predictions"] = jsonable(comb)
+    grades = []
+    for sev in (["critical"], ["major"] * 3, ["major"], ["minor"] * 4, ["minor"] * 2, []):
+        q = ens._assess_overall_quality([{"final_severity": s} for s in sev], {})
+        grades.append([sev, q["quality_grade"], q["pass_fail"]])
+    golden["grading"] = grades
+
+    # ---- (c) segmentation stages the graded K4 composite reproduces (inference/segmentation.py:284-289,464-525)
+    rng = np.random.default_rng(42)
+    m0 = np.zeros((96, 128), np.uint8)
+    for _ in range(30):
+        h, w = rng.integers(1, 14, 2)
+        y, x = rng.integers(0, 96 - h), rng.integers(0, 128 - w)
+        m0[y:y + h, x:x + w] = 255
+    m0[rng.random(m0.shape) < 0.02] = 255
+    seg = seg_mod.ImageSegmentator({})
+    kernel = cv2.getStructuringElement(cv2.MORPH_ELLIPSE, (3, 3))              # :284
+    m1 = cv2.morphologyEx(m0, cv2.MORPH_CLOSE, kernel)                        # :285
+    m1 = cv2.morphologyEx(m1, cv2.MORPH_OPEN, kernel)                         # :286
+    m2 = seg._remove_small_components(m1, min_size=20)                        # :289
+    contours = seg._find_contours(m2)
+    golden["segmentation_chain"] = {
+        "area_pixels": int(np.sum(m2 > 0)), "n_contours": len(contours),
+        "perimeter": seg._calculate_perimeter(contours),
+        "compactness": seg._calculate_compactness(int(np.sum(m2 > 0)), contours)}
+    np.savez_compressed(os.path.join(OUT, "segmentation_chain.npz"), m0=m0, m1=m1, m2=m2)
+    # the reference's own segment_defects on a synthetic frame (adaptive + threshold classes): areas are a
+    # regression pin for the variant rows, not for the graded composite
+    from qcgraft import synth
+    frame = synth.make_frame(3, 320, 320)
+    dets = [{"id": 0, "class": "crack", "confidence": 0.9, "bbox": {"x1": 20, "y1": 30, "x2": 140, "y2": 150}},
+            {"id": 1, "class": "discoloration", "confidence": 0.8, "bbox": {"x1": 150, "y1": 100, "x2": 300, "y2": 260}}]
+    sd = seg.segment_defects(frame, dets)
+    golden["reference_segment_defects"] = {"seed": 3, "shape": [320, 320],
+                                           "areas": [int(r["area_pixels"]) for r in sd["segmented_regions"]],
+                                           "methods": [r["segmentation_method"] for r in sd["segmented_regions"]]}
+
+    # ---- (d) SPCAnalyzer._extract_metrics  (analytics/sec_analysis.py:105-147) -> the 9-vector
+    spc = object.__new__(spc_mod.SPCAnalyzer)
+    results = [{"detections": comb["detections"]}, {"detections": comb["detections"][:3]}, {"detections": []}]
+    mets = [spc._extract_metrics(r) for r in results]
+    vec = [len(results), sum(m["defect_count"] for m in mets), sum(m["defect_count"] ** 2 for m in mets),
+           sum(m["avg_confidence"] * m["defect_count"] for m in mets), sum(m["defect_count"] for m in mets),
+           sum(m["critical_defects"] for m in mets), sum(m["major_defects"] for m in mets),
+           sum(m["minor_defects"] for m in mets), sum(m["total_area_affected"] for m in mets)]
+    golden["spc"] = {"counts": [len(r["detections"]) for r in results], "vector": jsonable(vec),
+                     "metrics": [{k: jsonable(v) for k, v in m.items() if k != "timestamp"} for m in mets]}
+
+    # ---- (e) library known-answers on seeded inputs (guards against cv2/torchvision drift on the GPU box)
+    import torchvision
+    img = rng.integers(0, 256, (45, 70, 3), dtype=np.uint8)
+    g = cv2.cvtColor(img, cv2.COLOR_RGB2GRAY)
+    t, _ = cv2.threshold(g, 0, 255, cv2.THRESH_BINARY | cv2.THRESH_OTSU)
+    n, lab, stats, _ = cv2.connectedComponentsWithStats(m1, connectivity=8, ltype=cv2.CV_32S)
+    b = torch.tensor(rows[:, :4]); sc = torch.tensor(rows[:, 4])
+    np.savez_compressed(os.path.join(OUT, "library_pins.npz"), img=img, resized=cv2.resize(img, (33, 29)),
+                        gray=g, otsu=np.int32(t), ccl_labels=lab.astype(np.int32), ccl_stats=stats.astype(np.int32),
+                        nms_keep=torchvision.ops.nms(b, sc, 0.5).numpy())
+    with open(os.path.join(OUT, "reference_golden.json"), "w") as f:
+        json.dump(golden, f, indent=1, sort_keys=True)
+    print("wrote", os.listdir(OUT))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,104 @@
+"""CPU checks of the boundary: the C-ABI library loads and exports every symbol include/qcgraft.h
+declares, the ctypes structs match the C layout, the host-side planners agree with the oracle, the
+product never imports the oracle, and there is no CPU fallback."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "industrial-quality-control-computer-vision-system-_b200")
+
+
+def test_library_exports_every_declared_symbol():
+    from qcgraft import ffi
+    lib = ffi.load_library()
+    hdr = open(os.path.join(ROOT, "include", "qcgraft.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(qc_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 18
+    for name in declared:
+        assert hasattr(lib, name), f"libqcgraft.so does not export {name}"
+    assert declared == set(ffi.EXPORTED_SYMBOLS), declared ^ set(ffi.EXPORTED_SYMBOLS)
+    assert lib.qc_version().startswith(b"qcgraft")
+
+
+def test_struct_layouts_match():
+    from qcgraft import ffi
+    lib = ffi.load_library()
+    for i, st in enumerate((ffi.PrePlan, ffi.YoloParams, ffi.SegRegion, ffi.SegParams)):
+        assert lib.qc_sizeof(i) == C.sizeof(st)
+    assert ffi.SEG_REGION_DTYPE.itemsize == C.sizeof(ffi.SegRegion)
+    for f, _ in ffi.SegRegion._fields_:
+        assert ffi.SEG_REGION_DTYPE.fields[f][1] == getattr(ffi.SegRegion, f).offset, f
+
+
+def test_pre_make_plan_matches_letterbox_oracle():
+    from qcgraft import ffi
+    from oracle import preprocess as opre
+    lib = ffi.load_library()
+    rng = np.random.default_rng(0)
+    shapes = [(1080, 1920), (480, 640), (333, 500), (640, 640), (1280, 1280), (100, 37), (37, 100), (641, 639)]
+    shapes += [tuple(int(v) for v in rng.integers(8, 2500, 2)) for _ in range(200)]
+    for h, w in shapes:
+        for mode, auto in ((ffi.QC_PRE_LETTERBOX, False), (ffi.QC_PRE_LETTERBOX_AUTO, True)):
+            pl = ffi.PrePlan()
+            assert lib.qc_pre_make_plan(mode, h, w, 640, 640, 32, C.byref(pl)) == 0
+            g = opre.letterbox_geometry(h, w, 640, 640, auto=auto)
+            assert (pl.new_h, pl.new_w, pl.top, pl.left, pl.dst_h, pl.dst_w) == \
+                   (g["new_h"], g["new_w"], g["top"], g["left"], g["out_h"], g["out_w"]), (h, w, auto)
+            gain = min(pl.dst_h / h, pl.dst_w / w)                      # ultralytics scale_boxes
+            assert pl.pad_x == round((pl.dst_w - w * gain) / 2 - 0.1) and pl.pad_y == round((pl.dst_h - h * gain) / 2 - 0.1)
+            assert pl.gain == np.float32(gain)
+    pl = ffi.PrePlan()
+    assert lib.qc_pre_make_plan(ffi.QC_PRE_STRETCH, 480, 720, 640, 640, 32, C.byref(pl)) == 0
+    assert (pl.dst_h, pl.dst_w, pl.top, pl.left) == (640, 640, 0, 0)
+    assert lib.qc_pre_make_plan(ffi.QC_PRE_LETTERBOX, 0, 10, 640, 640, 32, C.byref(pl)) != 0
+
+
+def test_segment_plan_offsets():
+    from qcgraft import ffi
+    lib = ffi.load_library()
+
+    class Fake(ffi.Context):
+        def __init__(self):
+            self.lib = lib
+    regs = [dict(img=0, x=0, y=0, w=2048, h=2048), dict(img=1, x=3, y=5, w=33, h=17, polarity=0, min_area=5),
+            dict(img=1, x=0, y=0, w=1, h=1)]
+    arr, p = Fake().segment_plan(regs, 2, 2048, 2048, 1, 2048 * 2048, 2048)
+    assert p.num_regions == 3 and p.max_region_w == 2048
+    assert arr.out_offset[0] == 0 and arr.out_offset[1] == 2048 * 2048 and arr.out_offset[2] % 16 == 0
+    assert arr.band_offset.tolist() == [0, 64, 65] and p.total_bands == 66
+    assert arr.blk_offset.tolist() == [0, 1024 * 1024, 1024 * 1024 + 17 * 9]
+    assert p.total_bits_words == 2048 * 64 + 17 * 2 + 1
+    with pytest.raises(ffi.QcGraftError):                                   # region outside the image
+        Fake().segment_plan([dict(img=0, x=2000, y=0, w=100, h=10)], 1, 2048, 2048, 1, 2048 * 2048, 2048)
+    arr, p = Fake().segment_plan([], 1, 64, 64, 1, 4096, 64)
+    assert p.num_regions == 0 and p.total_pixels == 0
+
+
+def test_product_never_imports_oracle():
+    for dirpath, _, files in os.walk(PKG):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f"{f} imports the oracle"
+    for f in ("bench.py",):      # bench may touch the oracle only inside the CPU-baseline helpers
+        src = open(os.path.join(ROOT, f)).read()
+        for m in re.finditer(r"^(\s*)(from|import)\s+oracle\b.*$", src, re.M):
+            fn = re.findall(r"^def (\w+)", src[:m.start()], re.M)[-1]
+            assert fn in ("build_cpu_pipeline", "cpu_reference_rate"), f"bench.py imports oracle in {fn}()"
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="needs a box WITHOUT a GPU")
+def test_no_cpu_fallback():
+    from qcgraft import ffi
+    with pytest.raises(ffi.QcGraftError):
+        ffi.Context(0)
+    from qcgraft.detector import QualityControlDetector
+    d = QualityControlDetector("y.pt", "r.pt", {})
+    out = d.predict(np.zeros((64, 64, 3), np.uint8))
+    assert "error" in out                                        # the reference's error convention, never raises
