@@ -65,17 +65,43 @@ __device__ __forceinline__ float sigmoid_f32(float x) {
 }
 
 // ------------------------------------------------------------------------------------------
+constexpr int K2_NC_MAX = 16;    // classes held in registers by the vector path
+
+// Candidate test for one anchor given its nc class logits.  torch: s_c = sigmoid(x_c) (float32), first
+// maximum over c, candidate iff s > (float)conf.  sigmoid is monotone, so only logits within a hair of
+// the maximum logit can hold the maximum sigmoid (they get the exact first-max treatment), and an anchor
+// whose maximum logit is clearly below logit(conf) needs no sigmoid at all.
+__device__ __forceinline__ bool anchor_candidate(const float* x, int nc, float conf, float logit_lo, float& best,
+                                                 int& best_c) {
+    float m = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < K2_NC_MAX; ++c)
+        if (c < nc) m = fmaxf(m, x[c]);
+    if (!(m >= logit_lo)) return false;                 // sigmoid(m) < conf with a wide margin (NaN -> false)
+    const float near = m - 1e-3f * fmaxf(1.f, fabsf(m));
+    best = -1.f; best_c = 0;
+#pragma unroll
+    for (int c = 0; c < K2_NC_MAX; ++c) {
+        if (c < nc && x[c] >= near) {
+            const float sg = sigmoid_f32(x[c]);
+            if (sg > best) { best = sg; best_c = c; }   // first maximum wins (torch.max)
+        }
+    }
+    return best > conf;                                 // float32 compare, like torch
+}
+
 template <bool BF16>
 __global__ void __launch_bounds__(256)
-k2_filter(LevelTable lt, int nc, int reg_max, float conf, int cap,
+k2_filter(LevelTable lt, int nc, int reg_max, float conf, float logit_lo, int cap, int vec_ok,
           unsigned long long* __restrict__ cand_key, int* __restrict__ cand_count) {
     const int img = blockIdx.y;
     const int lane = threadIdx.x & 31;
-    for (int a0 = blockIdx.x * blockDim.x; a0 < lt.A; a0 += gridDim.x * blockDim.x) {
-        const int a = a0 + threadIdx.x;
-        bool is_cand = false;
-        float best = 0.f;
-        int best_c = 0;
+    const int step = vec_ok ? 4 : 1;                    // anchors per thread per iteration
+    for (int a0 = blockIdx.x * blockDim.x * step; a0 < lt.A; a0 += gridDim.x * blockDim.x * step) {
+        const int a = a0 + threadIdx.x * step;
+        bool is_cand[4] = {false, false, false, false};
+        float best[4];
+        int best_c[4];
         if (a < lt.A) {
             int l = 0;
 #pragma unroll
@@ -84,25 +110,58 @@ k2_filter(LevelTable lt, int nc, int reg_max, float conf, int cap,
             const long long base = (long long)img * lt.batch_stride[l] + (a - lt.start[l]);
             const long long cs = lt.chan_stride[l];
             const void* p = lt.ptr[l];
-            best = -1.f;
-            for (int c = 0; c < nc; ++c) {
-                float s = sigmoid_f32(load_elem<BF16>(p, base + (long long)(4 * reg_max + c) * cs));
-                if (s > best) { best = s; best_c = c; }     // first maximum wins (torch.max)
+            if (vec_ok) {
+                // 4 consecutive anchors x nc classes: one 128-bit (f32) / 64-bit (bf16) load per class plane
+                float x[4][K2_NC_MAX];
+#pragma unroll
+                for (int c = 0; c < K2_NC_MAX; ++c) {
+                    if (c < nc) {
+                        const long long e = base + (long long)(4 * reg_max + c) * cs;
+                        if (BF16) {
+                            const uint2 v = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(p) + e));
+                            x[0][c] = qc_bf2f((uint16_t)(v.x & 0xFFFF)); x[1][c] = qc_bf2f((uint16_t)(v.x >> 16));
+                            x[2][c] = qc_bf2f((uint16_t)(v.y & 0xFFFF)); x[3][c] = qc_bf2f((uint16_t)(v.y >> 16));
+                        } else {
+                            const float4 v = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p) + e));
+                            x[0][c] = v.x; x[1][c] = v.y; x[2][c] = v.z; x[3][c] = v.w;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) is_cand[j] = anchor_candidate(x[j], nc, conf, logit_lo, best[j], best_c[j]);
+            } else {
+                float m = -INFINITY;
+                for (int c = 0; c < nc; ++c) m = fmaxf(m, load_elem<BF16>(p, base + (long long)(4 * reg_max + c) * cs));
+                if (m >= logit_lo) {
+                    const float near = m - 1e-3f * fmaxf(1.f, fabsf(m));
+                    best[0] = -1.f; best_c[0] = 0;
+                    for (int c = 0; c < nc; ++c) {
+                        const float xv = load_elem<BF16>(p, base + (long long)(4 * reg_max + c) * cs);
+                        if (xv >= near) {
+                            const float sg = sigmoid_f32(xv);
+                            if (sg > best[0]) { best[0] = sg; best_c[0] = c; }
+                        }
+                    }
+                    is_cand[0] = best[0] > conf;
+                }
             }
-            is_cand = best > conf;                          // float32 compare, like torch
         }
-        const unsigned m = __ballot_sync(0xffffffffu, is_cand);
-        if (m) {
-            int base_slot = 0;
-            const int leader = __ffs(m) - 1;
-            if (lane == leader) base_slot = atomicAdd(&cand_count[img], __popc(m));
-            base_slot = __shfl_sync(0xffffffffu, base_slot, leader);
-            if (is_cand) {
-                const int slot = base_slot + __popc(m & ((1u << lane) - 1));
-                if (slot < cap)
-                    cand_key[(long long)img * cap + slot] =
-                        ((unsigned long long)f2ord_desc(best) << 32) | ((unsigned long long)a << 8) |
-                        (unsigned long long)best_c;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (j >= step) break;
+            const unsigned m = __ballot_sync(0xffffffffu, is_cand[j]);
+            if (m) {
+                int base_slot = 0;
+                const int leader = __ffs(m) - 1;
+                if (lane == leader) base_slot = atomicAdd(&cand_count[img], __popc(m));
+                base_slot = __shfl_sync(0xffffffffu, base_slot, leader);
+                if (is_cand[j]) {
+                    const int slot = base_slot + __popc(m & ((1u << lane) - 1));
+                    if (slot < cap)
+                        cand_key[(long long)img * cap + slot] =
+                            ((unsigned long long)f2ord_desc(best[j]) << 32) | ((unsigned long long)(a + j) << 8) |
+                            (unsigned long long)best_c[j];
+                }
             }
         }
     }
@@ -195,17 +254,26 @@ __global__ void k2_make_keys(const float* __restrict__ scores, const int* __rest
     }
 }
 
-// torchvision/csrc/ops/cpu/nms_kernel.cpp inner test, verbatim in float32 (no FMA)
-__device__ __forceinline__ bool iou_gt(const float4 a, const float4 b, double thr) {
+// torchvision/csrc/ops/cpu/nms_kernel.cpp inner test, verbatim in float32 (no FMA):
+//   ovr = inter / (iarea + jarea - inter);  suppress iff (double)ovr > thr
+// Disjoint boxes (other class offsets, far apart) leave early with inter == 0; the IEEE division is
+// only executed when inter/den is within 1e-4 of the threshold -- outside that band the comparison of
+// inter against den*(thr -/+ 1e-4) already decides (float32 rounding is ~1e-7 relative).
+__device__ __forceinline__ bool iou_gt(const float4 a, const float4 b, double thr, float thr_lo, float thr_hi,
+                                       bool fast) {
+    const float w = __fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x));
+    if (fast && !(w > 0.f)) return false;               // inter == 0 -> ovr = 0 (or NaN): never > thr >= 0
+    const float h = __fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y));
+    if (fast && !(h > 0.f)) return false;
     const float iarea = __fmul_rn(__fsub_rn(a.z, a.x), __fsub_rn(a.w, a.y));
     const float jarea = __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
-    const float xx1 = fmaxf(a.x, b.x), yy1 = fmaxf(a.y, b.y);
-    const float xx2 = fminf(a.z, b.z), yy2 = fminf(a.w, b.w);
-    const float w = fmaxf(0.f, __fsub_rn(xx2, xx1));
-    const float h = fmaxf(0.f, __fsub_rn(yy2, yy1));
-    const float inter = __fmul_rn(w, h);
-    const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(iarea, jarea), inter));
-    return (double)ovr > thr;
+    const float inter = __fmul_rn(fmaxf(0.f, w), fmaxf(0.f, h));
+    const float den = __fsub_rn(__fadd_rn(iarea, jarea), inter);
+    if (fast && den > 0.f) {
+        if (inter < __fmul_rn(den, thr_lo)) return false;
+        if (inter > __fmul_rn(den, thr_hi)) return true;
+    }
+    return (double)__fdiv_rn(inter, den) > thr;
 }
 
 struct NmsArgs {
@@ -289,6 +357,9 @@ k2_nms(NmsArgs args, const unsigned long long* __restrict__ cand_key, const floa
 
     // ---- greedy NMS in chunks of 64 sorted boxes -------------------------------------------
     const double thr = args.iou_thres;
+    // fast paths are valid for thresholds in (1e-3, 1): widen the decision band by 1e-4 on both sides
+    const bool fast = thr > 1e-3 && thr < 1.0;
+    const float thr_lo = (float)(thr - 1e-4), thr_hi = (float)(thr + 1e-4);
     for (int c0 = 0; c0 < n; c0 += 64) {
         const int m = min(64, n - c0);
         // 64x64 upper-triangular suppression bitmask of the chunk
@@ -297,8 +368,8 @@ k2_nms(NmsArgs args, const unsigned long long* __restrict__ cand_key, const floa
             if (i < m) {
                 const float4 bi = sorted[c0 + i];
                 const int j0 = lane, j1 = lane + 32;
-                if (j0 > i && j0 < m) b0 = iou_gt(bi, sorted[c0 + j0], thr);
-                if (j1 > i && j1 < m) b1 = iou_gt(bi, sorted[c0 + j1], thr);
+                if (j0 > i && j0 < m) b0 = iou_gt(bi, sorted[c0 + j0], thr, thr_lo, thr_hi, fast);
+                if (j1 > i && j1 < m) b1 = iou_gt(bi, sorted[c0 + j1], thr, thr_lo, thr_hi, fast);
             }
             const unsigned lo = __ballot_sync(0xffffffffu, b0), hi = __ballot_sync(0xffffffffu, b1);
             if (lane == 0) M[i] = ((unsigned long long)hi << 32) | lo;
@@ -310,18 +381,24 @@ k2_nms(NmsArgs args, const unsigned long long* __restrict__ cand_key, const floa
             if (lane == 0) s_rem = ((unsigned long long)hi << 32) | lo;
         }
         __syncthreads();
-        if (tid == 0) {
+        if (warp == 0) {
+            // serial greedy pass over the chunk, executed redundantly by every lane of warp 0: lane l holds
+            // mask rows l and l+32, row i is broadcast by shuffle (independent of the running state, so the
+            // shuffles pipeline ahead of the dependent chain on `rem`)
+            const unsigned long long m_lo = M[lane], m_hi = M[lane + 32];
             unsigned long long rem = s_rem, keptmask = 0;
             int kt = s_kept_total;
-            for (int i = 0; i < m && kt < args.max_det; ++i) {
-                if (!((rem >> i) & 1ull)) {
-                    keptmask |= 1ull << i;
-                    rem |= M[i];
-                    kept_list[kt++] = c0 + i;
-                }
+#pragma unroll
+            for (int i = 0; i < 64; ++i) {
+                const unsigned long long mi = __shfl_sync(0xffffffffu, i < 32 ? m_lo : m_hi, i & 31);
+                const bool k = !((rem >> i) & 1ull) && i < m && kt < args.max_det;
+                keptmask |= (unsigned long long)k << i;
+                rem |= k ? mi : 0ull;
+                if (k && lane == 0) kept_list[kt] = c0 + i;
+                kt += k;
             }
-            s_keptmask = keptmask;
-            s_kept_total = kt;
+            __syncwarp();
+            if (lane == 0) { s_keptmask = keptmask; s_kept_total = kt; }
         }
         __syncthreads();
         const unsigned long long keptmask = s_keptmask;
@@ -334,7 +411,7 @@ k2_nms(NmsArgs args, const unsigned long long* __restrict__ cand_key, const floa
                 while (km) {
                     const int i = __ffsll((long long)km) - 1;
                     km &= km - 1;
-                    if (iou_gt(sorted[c0 + i], bj, thr)) { removed[j] = 1; break; }
+                    if (iou_gt(sorted[c0 + i], bj, thr, thr_lo, thr_hi, fast)) { removed[j] = 1; break; }
                 }
             }
         }
@@ -467,13 +544,30 @@ extern "C" int qc_yolo_decode_nms(qc_ctx* ctx, const void* const* levels, const 
     QC_CUDA(ctx, cudaMemsetAsync(w.count, 0, (size_t)p->n * 4, st));
 
     const float conf = (float)p->conf_thres;
-    dim3 gf((unsigned)std::min((A + 255) / 256, 64), (unsigned)p->n);
-    if (p->in_dtype == QC_DT_BF16) k2_filter<true><<<gf, 256, 0, st>>>(lt, p->nc, p->reg_max, conf, cap, w.key, w.count);
-    else k2_filter<false><<<gf, 256, 0, st>>>(lt, p->nc, p->reg_max, conf, cap, w.key, w.count);
+    // logit(conf) minus a wide margin: anchors whose best logit is below it cannot reach conf
+    float logit_lo = -INFINITY;
+    if (p->conf_thres > 0.0 && p->conf_thres < 1.0) {
+        const double lg = log(p->conf_thres / (1.0 - p->conf_thres));
+        logit_lo = (float)(lg - 1e-2 - 1e-3 * fabs(lg));
+    } else if (p->conf_thres >= 1.0) {
+        logit_lo = 8.0f;          // sigmoid(8) = 0.99966 < 1: nothing below can exceed conf >= 1
+    }
+    const bool bf = p->in_dtype == QC_DT_BF16;
+    // vector path: every level plane starts 16-byte (f32) / 8-byte (bf16) aligned and holds a multiple of 4 anchors
+    int vec_ok = p->nc <= K2_NC_MAX;
+    const size_t esz = bf ? 2 : 4;
+    for (int l = 0; l < p->num_levels && vec_ok; ++l) {
+        if ((p->level_h[l] * p->level_w[l]) % 4 || (lt.chan_stride[l] % 4) || (lt.batch_stride[l] % 4) ||
+            (reinterpret_cast<uintptr_t>(levels[l]) % (4 * esz)))
+            vec_ok = 0;
+    }
+    const int per_cta = 256 * (vec_ok ? 4 : 1);
+    dim3 gf((unsigned)std::min((A + per_cta - 1) / per_cta, 64), (unsigned)p->n);
+    if (bf) k2_filter<true><<<gf, 256, 0, st>>>(lt, p->nc, p->reg_max, conf, logit_lo, cap, vec_ok, w.key, w.count);
+    else k2_filter<false><<<gf, 256, 0, st>>>(lt, p->nc, p->reg_max, conf, logit_lo, cap, vec_ok, w.key, w.count);
     QC_LAUNCHED(ctx);
 
-    dim3 gd(8, (unsigned)p->n);
-    const bool bf = p->in_dtype == QC_DT_BF16;
+    dim3 gd(32, (unsigned)p->n);
     if (p->reg_max == 16) {
         if (bf) k2_decode<true, 16><<<gd, 256, 0, st>>>(lt, 16, cap, w.key, w.count, w.box);
         else k2_decode<false, 16><<<gd, 256, 0, st>>>(lt, 16, cap, w.key, w.count, w.box);

@@ -6,9 +6,13 @@
 // on the uint8 HWC frame, followed by /255 and Normalize(mean,std) of
 // models/resent_model.py:59-66, written as bf16 (RNE) or f32 NCHW.
 //
-// One thread per output pixel (all 3 channels share the bilinear weights); a warp covers 32
-// consecutive output columns so plane stores are contiguous.  Source taps come through the
-// read-only path; a ROI's source window is small and stays in L1/L2.
+// k3_roi_sep (sampling_ratio 1..4): roi_align's sample lattice is separable, so each CTA takes one ROI x
+// 8 output rows, (1) builds the per-column x-tap table once, (2) runs the horizontal interpolation of the
+// few source rows the band touches into shared memory (float32, [row][channel][column]), (3) runs the
+// vertical interpolation + /255 + Normalize from shared memory and stores bf16 pairs.  12 shared-memory
+// loads per output pixel instead of 48 global byte loads.  Bands that do not fit (oversized / inverted
+// boxes, adaptive sampling) fall back to the direct per-pixel form (k3_roi_align, torchvision's loop
+// order verbatim).
 // Algorithmic bytes per ROI: roi_w*roi_h*3 (read) + 3*out_h*out_w*sizeof(out) (write).
 #include "common.cuh"
 #include <math.h>
@@ -88,6 +92,186 @@ k3_roi_align(const uint8_t* __restrict__ imgs, int n, int H, int W, long long im
     }
 }
 
+
+constexpr int K3_BH = 8;         // output rows per CTA
+constexpr int K3_SR_MAX = 4;
+
+template <typename OutT>
+__global__ void __launch_bounds__(256)
+k3_roi_sep(const uint8_t* __restrict__ imgs, int n, int H, int W, long long img_stride, int row_stride,
+           const float* __restrict__ rois, int K, int PH, int PW, int sr, int aligned, int swap_rb,
+           const float* __restrict__ norm, OutT* __restrict__ dst, int rows_max) {
+    extern __shared__ __align__(16) float k3sm[];
+    float* Hs = k3sm;                                        // [rows_max][3][PW]
+    int* xlo = reinterpret_cast<int*>(Hs + (size_t)rows_max * 3 * PW);   // [PW*sr]
+    int* xhi = xlo + PW * sr;
+    float* wlo = reinterpret_cast<float*>(xhi + PW * sr);
+    float* whi = wlo + PW * sr;
+
+    const int k = blockIdx.y;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float* r = rois + (long long)k * 5;
+    const int img = (int)r[0];
+    const float offset = aligned ? 0.5f : 0.f;
+    const float x1 = __fsub_rn(r[1], offset), y1 = __fsub_rn(r[2], offset);
+    const float x2 = __fsub_rn(r[3], offset), y2 = __fsub_rn(r[4], offset);
+    float roi_w = __fsub_rn(x2, x1), roi_h = __fsub_rn(y2, y1);
+    if (!aligned) { roi_w = fmaxf(roi_w, 1.f); roi_h = fmaxf(roi_h, 1.f); }
+    const float bin_h = __fdiv_rn(roi_h, (float)PH), bin_w = __fdiv_rn(roi_w, (float)PW);
+    const float count = (float)(sr * sr);
+    const bool img_ok = img >= 0 && img < n;
+    const uint8_t* base = imgs + (long long)(img_ok ? img : 0) * img_stride;
+    const int ph0 = blockIdx.x * K3_BH, ph1 = min(ph0 + K3_BH, PH);
+    const int total = PH * PW;
+
+    auto ysample = [&](int ph, int iy) -> float {           // torchvision's expression, same op order
+        return __fadd_rn(__fadd_rn(y1, __fmul_rn((float)ph, bin_h)), __fdiv_rn(__fmul_rn((float)iy + 0.5f, bin_h), (float)sr));
+    };
+    float nd[3], nm[3], ns[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { nd[c] = norm[c * 3 + 0]; nm[c] = norm[c * 3 + 1]; ns[c] = norm[c * 3 + 2]; }
+    auto finish = [&](float acc, int c) -> float {
+        const float v = __fdiv_rn(acc, count);
+        return __fdiv_rn(__fsub_rn(__fdiv_rn(v, nd[c]), nm[c]), ns[c]);
+    };
+    auto store = [&](int c, int o, float v) {
+        OutT* q = dst + ((long long)k * 3 + c) * total + o;
+        if (sizeof(OutT) == 2) *reinterpret_cast<uint16_t*>(q) = qc_f2bf(v);
+        else *reinterpret_cast<float*>(q) = v;
+    };
+
+    // source rows touched by this band (samples are monotone in (ph, iy) when bin_h >= 0)
+    const float yf = ysample(ph0, 0), yl_ = ysample(ph1 - 1, sr - 1);
+    const int r_lo = min(max((int)fmaxf(yf, 0.f), 0), H - 1);
+    const int r_hi = min(max((int)fmaxf(yl_, 0.f) + 1, 0), H - 1);
+    const int nrows = r_hi - r_lo + 1;
+    const bool sep = img_ok && bin_h >= 0.f && bin_w >= 0.f && nrows <= rows_max && yf == yf && yl_ == yl_;
+
+    if (!sep) {
+        // direct form for this band (rare): identical to k3_roi_align
+        for (int o = ph0 * PW + tid; o < ph1 * PW; o += blockDim.x) {
+            const int ph = o / PW, pw = o - ph * PW;
+            float acc[3] = {0.f, 0.f, 0.f};
+            if (img_ok) {
+                for (int iy = 0; iy < sr; ++iy) {
+                    const float yy = ysample(ph, iy);
+                    for (int ix = 0; ix < sr; ++ix) {
+                        const float xx = __fadd_rn(__fadd_rn(x1, __fmul_rn((float)pw, bin_w)),
+                                                   __fdiv_rn(__fmul_rn((float)ix + 0.5f, bin_w), (float)sr));
+                        float y = yy, x = xx;
+                        if (y < -1.f || y > (float)H || x < -1.f || x > (float)W) continue;
+                        if (y <= 0.f) y = 0.f;
+                        if (x <= 0.f) x = 0.f;
+                        int yl = (int)y, xl = (int)x, yh, xh;
+                        if (yl >= H - 1) { yh = yl = H - 1; y = (float)yl; } else yh = yl + 1;
+                        if (xl >= W - 1) { xh = xl = W - 1; x = (float)xl; } else xh = xl + 1;
+                        const float ly = __fsub_rn(y, (float)yl), lx = __fsub_rn(x, (float)xl);
+                        const float hy = __fsub_rn(1.f, ly), hx = __fsub_rn(1.f, lx);
+                        const float w1 = __fmul_rn(hy, hx), w2 = __fmul_rn(hy, lx), w3 = __fmul_rn(ly, hx), w4 = __fmul_rn(ly, lx);
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) {
+                            const int sc = swap_rb ? 2 - c : c;
+                            float v = __fmul_rn(w1, (float)__ldg(base + (long long)yl * row_stride + xl * 3 + sc));
+                            v = __fadd_rn(v, __fmul_rn(w2, (float)__ldg(base + (long long)yl * row_stride + xh * 3 + sc)));
+                            v = __fadd_rn(v, __fmul_rn(w3, (float)__ldg(base + (long long)yh * row_stride + xl * 3 + sc)));
+                            v = __fadd_rn(v, __fmul_rn(w4, (float)__ldg(base + (long long)yh * row_stride + xh * 3 + sc)));
+                            acc[c] = __fadd_rn(acc[c], v);
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 3; ++c) store(c, o, finish(acc[c], c));
+        }
+        return;
+    }
+
+    // (1) x taps: sample ix of output column pw -> (xl, xh, hx, lx); invalid samples get zero weights
+    for (int t = tid; t < PW * sr; t += blockDim.x) {
+        const int pw = t / sr, ix = t - pw * sr;
+        float x = __fadd_rn(__fadd_rn(x1, __fmul_rn((float)pw, bin_w)), __fdiv_rn(__fmul_rn((float)ix + 0.5f, bin_w), (float)sr));
+        int xl = 0, xh = 0;
+        float lx = 0.f, hx = 0.f;
+        if (!(x < -1.f || x > (float)W)) {
+            if (x <= 0.f) x = 0.f;
+            xl = (int)x;
+            if (xl >= W - 1) { xh = xl = W - 1; x = (float)xl; } else xh = xl + 1;
+            lx = __fsub_rn(x, (float)xl);
+            hx = __fsub_rn(1.f, lx);
+        }
+        xlo[t] = xl * 3; xhi[t] = xh * 3; wlo[t] = hx; whi[t] = lx;
+    }
+    __syncthreads();
+    // (2) horizontal pass over the band's source rows
+    for (int rr = warp; rr < nrows; rr += 8) {
+        const uint8_t* row = base + (long long)(r_lo + rr) * row_stride;
+        float* hrow = Hs + (size_t)rr * 3 * PW;
+        for (int pw = lane; pw < PW; pw += 32) {
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+            for (int ix = 0; ix < sr; ++ix) {
+                const int t = pw * sr + ix;
+                const uint8_t* pl = row + xlo[t];
+                const uint8_t* ph_ = row + xhi[t];
+                const float wl = wlo[t], wh = whi[t];
+                a0 += wl * (float)__ldg(pl + 0) + wh * (float)__ldg(ph_ + 0);
+                a1 += wl * (float)__ldg(pl + 1) + wh * (float)__ldg(ph_ + 1);
+                a2 += wl * (float)__ldg(pl + 2) + wh * (float)__ldg(ph_ + 2);
+            }
+            hrow[(swap_rb ? 2 : 0) * PW + pw] = a0;
+            hrow[PW + pw] = a1;
+            hrow[(swap_rb ? 0 : 2) * PW + pw] = a2;
+        }
+    }
+    __syncthreads();
+    // (3) vertical pass + normalise + store (pairs of columns -> 32-bit bf16x2 stores)
+    const int pairs = (PW + 1) >> 1;
+    for (int phl = warp; phl < ph1 - ph0; phl += 8) {
+        const int ph = ph0 + phl;
+        int yl[K3_SR_MAX], yh[K3_SR_MAX];
+        float wyl[K3_SR_MAX], wyh[K3_SR_MAX];
+#pragma unroll
+        for (int iy = 0; iy < K3_SR_MAX; ++iy) {
+            yl[iy] = yh[iy] = 0; wyl[iy] = wyh[iy] = 0.f;
+            if (iy < sr) {
+                float y = ysample(ph, iy);
+                if (!(y < -1.f || y > (float)H)) {
+                    if (y <= 0.f) y = 0.f;
+                    int a = (int)y, b;
+                    if (a >= H - 1) { b = a = H - 1; y = (float)a; } else b = a + 1;
+                    const float ly = __fsub_rn(y, (float)a);
+                    yl[iy] = a - r_lo; yh[iy] = b - r_lo; wyl[iy] = __fsub_rn(1.f, ly); wyh[iy] = ly;
+                }
+            }
+        }
+        for (int pp = lane; pp < pairs; pp += 32) {
+            const int pw = pp * 2;
+            const bool two = pw + 1 < PW;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+                for (int iy = 0; iy < K3_SR_MAX; ++iy) {
+                    if (iy < sr) {
+                        const float* ha = Hs + ((size_t)yl[iy] * 3 + c) * PW + pw;
+                        const float* hb = Hs + ((size_t)yh[iy] * 3 + c) * PW + pw;
+                        s0 += wyl[iy] * ha[0] + wyh[iy] * hb[0];
+                        if (two) s1 += wyl[iy] * ha[1] + wyh[iy] * hb[1];
+                    }
+                }
+                const float v0 = finish(s0, c), v1 = finish(s1, c);
+                const int o = ph * PW + pw;
+                OutT* q = dst + ((long long)k * 3 + c) * total + o;
+                if (sizeof(OutT) == 2 && two && ((reinterpret_cast<uintptr_t>(q) & 3) == 0)) {
+                    *reinterpret_cast<uint32_t*>(q) = (uint32_t)qc_f2bf(v0) | ((uint32_t)qc_f2bf(v1) << 16);
+                } else {
+                    store(c, o, v0);
+                    if (two) store(c, o + 1, v1);
+                }
+            }
+        }
+    }
+}
+
 }  // namespace
 
 extern "C" int qc_roi_align(qc_ctx* ctx, const uint8_t* imgs, int n, int h, int w, int64_t img_stride,
@@ -101,6 +285,33 @@ extern "C" int qc_roi_align(qc_ctx* ctx, const uint8_t* imgs, int n, int h, int 
     if (K > 65535) QC_FAIL(ctx, QC_ERR_UNSUPPORTED, "qc_roi_align: K > 65535 (split the call)");
     cudaStream_t st = (cudaStream_t)stream;
     const int total = out_h * out_w;
+    if (sampling_ratio >= 1 && sampling_ratio <= K3_SR_MAX) {
+        // rows one 8-row band can touch for boxes inside the frame (+ slack); larger bands fall back in-kernel
+        long long rows_max = (long long)K3_BH * ((h + out_h - 1) / out_h) + 4;
+        const size_t tap_bytes = (size_t)out_w * sampling_ratio * 16;
+        const size_t budget = (size_t)ctx->max_smem_optin - 2048;
+        const size_t per_row = (size_t)3 * out_w * 4;
+        if (tap_bytes + 8 * per_row <= budget) {
+            if (tap_bytes + rows_max * per_row > budget) rows_max = (long long)((budget - tap_bytes) / per_row);
+            const size_t smem = tap_bytes + (size_t)rows_max * per_row;
+            dim3 grid((unsigned)((out_h + K3_BH - 1) / K3_BH), (unsigned)K);
+            if (out_dtype == QC_DT_BF16) {
+                QC_CUDA(ctx, cudaFuncSetAttribute(k3_roi_sep<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                k3_roi_sep<__nv_bfloat16><<<grid, 256, smem, st>>>(imgs, n, h, w, img_stride, row_stride, rois, K, out_h,
+                                                                   out_w, sampling_ratio, aligned, swap_rb, norm,
+                                                                   (__nv_bfloat16*)dst, (int)rows_max);
+            } else if (out_dtype == QC_DT_F32) {
+                QC_CUDA(ctx, cudaFuncSetAttribute(k3_roi_sep<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                k3_roi_sep<float><<<grid, 256, smem, st>>>(imgs, n, h, w, img_stride, row_stride, rois, K, out_h, out_w,
+                                                           sampling_ratio, aligned, swap_rb, norm, (float*)dst,
+                                                           (int)rows_max);
+            } else {
+                QC_FAIL(ctx, QC_ERR_INVALID, "qc_roi_align: bad out_dtype");
+            }
+            QC_LAUNCHED(ctx);
+            return QC_OK;
+        }
+    }
     dim3 grid((unsigned)((total + 255) / 256), (unsigned)K);
     if (out_dtype == QC_DT_BF16)
         k3_roi_align<__nv_bfloat16><<<grid, 256, 0, st>>>(imgs, n, h, w, img_stride, row_stride, rois, K, out_h, out_w,
