@@ -137,6 +137,12 @@ def run_reference(args, rank):
     if rank != 0:
         return
     per_step = 4
+    # torchrun exports OMP_NUM_THREADS=1; the reference arm uses every host core it can
+    try:
+        ncpu = len(os.sched_getaffinity(0))
+    except AttributeError:
+        ncpu = os.cpu_count() or 1
+    torch.set_num_threads(ncpu)
     cores = torch.get_num_threads()
     for _ in range(max(args.warmup, 0) and 1):
         cpu_reference_rate(1, warm=1)
@@ -350,6 +356,7 @@ def main():
     e2e_value = imgs_total / (max(e2e_ms, e2e_wall_ms) / 1000)
 
     if rank != 0:
+        qdist.shutdown()
         return
 
     k1_bytes = BATCH * (IMGSZ * IMGSZ * 3 + 3 * IMGSZ * IMGSZ * 2)
@@ -380,12 +387,17 @@ def main():
         except Exception as e:   # the headline line must still be printed
             line["kernels"] = {"error": str(e)}
     if world == 1 and not args.no_cpu_baseline:
+        try:
+            torch.set_num_threads(len(os.sched_getaffinity(0)))
+        except AttributeError:
+            pass
         t0 = time.time()
         v, ts = cpu_reference_rate(args.cpu_sample, warm=1)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                                 "sample": f"{len(ts)} frames of cfg2 (+1 warm-up), sequential predict() loop, "
                                           f"{time.time() - t0:.1f}s wall, host cpu_count={os.cpu_count()}"}
     print(json.dumps(line), flush=True)
+    qdist.shutdown()
 
 
 if __name__ == "__main__":
