@@ -283,6 +283,7 @@ struct NmsArgs {
     int scale_boxes;
     float gain, pad_x, pad_y, orig_w, orig_h;
     int mode;   // 0: full (write det rows + anchors), 1: nms-only (write kept candidate index)
+    int class_prune;   // 1: boxes of different classes can never overlap after the offset (host-checked)
 };
 
 __device__ void bitonic_sort_pairs(unsigned long long* keys, int* vals, int npow2) {
@@ -311,6 +312,8 @@ k2_nms(NmsArgs args, const unsigned long long* __restrict__ cand_key, const floa
        int* __restrict__ out_count, int* __restrict__ out_ncand) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     __shared__ unsigned long long M[64];
+    __shared__ unsigned long long cmask2[2][256];  // per class: which boxes of the current chunk have it
+                                                   // (double-buffered by chunk parity: reset races with nothing)
     __shared__ unsigned long long s_rem, s_keptmask;
     __shared__ int s_kept_total;
 
@@ -353,6 +356,7 @@ k2_nms(NmsArgs args, const unsigned long long* __restrict__ cand_key, const floa
         removed[i] = 0;
     }
     if (tid == 0) s_kept_total = 0;
+    if (tid < 512) cmask2[tid >> 8][tid & 255] = 0ull;
     __syncthreads();
 
     // ---- greedy NMS in chunks of 64 sorted boxes -------------------------------------------
@@ -362,6 +366,7 @@ k2_nms(NmsArgs args, const unsigned long long* __restrict__ cand_key, const floa
     const float thr_lo = (float)(thr - 1e-4), thr_hi = (float)(thr + 1e-4);
     for (int c0 = 0; c0 < n; c0 += 64) {
         const int m = min(64, n - c0);
+        unsigned long long* cmask = cmask2[(c0 >> 6) & 1];
         // 64x64 upper-triangular suppression bitmask of the chunk
         for (int i = warp; i < 64; i += K2_NMS_THREADS / 32) {
             bool b0 = false, b1 = false;
@@ -374,6 +379,8 @@ k2_nms(NmsArgs args, const unsigned long long* __restrict__ cand_key, const floa
             const unsigned lo = __ballot_sync(0xffffffffu, b0), hi = __ballot_sync(0xffffffffu, b1);
             if (lane == 0) M[i] = ((unsigned long long)hi << 32) | lo;
         }
+        if (args.class_prune && tid >= 64 && tid < 64 + m)
+            atomicOr(&cmask[keys[c0 + tid - 64] & 0xFF], 1ull << (tid - 64));
         if (warp == 0) {
             const bool r0 = lane < m && removed[c0 + lane];
             const bool r1 = lane + 32 < m && removed[c0 + lane + 32];
@@ -407,7 +414,8 @@ k2_nms(NmsArgs args, const unsigned long long* __restrict__ cand_key, const floa
             for (int j = c0 + 64 + tid; j < n; j += K2_NMS_THREADS) {
                 if (removed[j]) continue;
                 const float4 bj = sorted[j];
-                unsigned long long km = keptmask;
+                // cross-class pairs cannot overlap: only kept boxes of this box's class are tested
+                unsigned long long km = args.class_prune ? (keptmask & cmask[keys[j] & 0xFF]) : keptmask;
                 while (km) {
                     const int i = __ffsll((long long)km) - 1;
                     km &= km - 1;
@@ -416,6 +424,7 @@ k2_nms(NmsArgs args, const unsigned long long* __restrict__ cand_key, const floa
             }
         }
         __syncthreads();
+        if (args.class_prune && tid < m) cmask[keys[c0 + tid] & 0xFF] = 0ull;    // reset only the touched entries
     }
     __syncthreads();
 
@@ -581,6 +590,14 @@ extern "C" int qc_yolo_decode_nms(qc_ctx* ctx, const void* const* levels, const 
     a.cap = cap; a.max_det = p->max_det; a.max_nms = p->max_nms; a.max_wh = p->max_wh; a.iou_thres = p->iou_thres;
     a.scale_boxes = p->scale_boxes; a.gain = p->gain; a.pad_x = (float)p->pad_x; a.pad_y = (float)p->pad_y;
     a.orig_w = (float)p->orig_w; a.orig_h = (float)p->orig_h; a.mode = 0;
+    // decoded coordinates lie within [-(reg_max-1)*stride, extent + (reg_max-1)*stride]: if max_wh exceeds that
+    // span, boxes of different classes never intersect after the +cls*max_wh offset (IoU == 0 exactly)
+    float span = 0.f, smax = 0.f;
+    for (int l = 0; l < p->num_levels; ++l) {
+        span = fmaxf(span, fmaxf((float)p->level_w[l], (float)p->level_h[l]) * p->level_stride[l]);
+        smax = fmaxf(smax, p->level_stride[l]);
+    }
+    a.class_prune = (p->max_wh > span + 2.f * p->reg_max * smax + 2.f) ? 1 : 0;
     return launch_nms(ctx, a, p->n, w, out_det, out_anchor, out_count, out_ncand, st);
 }
 
@@ -603,5 +620,6 @@ extern "C" int qc_nms(qc_ctx* ctx, const float* boxes, const float* scores, cons
     NmsArgs a;
     a.cap = cap; a.max_det = max_det; a.max_nms = cap; a.max_wh = max_wh; a.iou_thres = iou_thres;
     a.scale_boxes = 0; a.gain = 1.f; a.pad_x = a.pad_y = 0.f; a.orig_w = a.orig_h = 0.f; a.mode = 1;
+    a.class_prune = 0;            // arbitrary caller boxes: no span guarantee
     return launch_nms(ctx, a, n, w, nullptr, out_keep, out_count, nullptr, st);
 }
