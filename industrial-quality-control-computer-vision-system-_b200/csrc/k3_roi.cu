@@ -130,61 +130,25 @@ k3_roi_sep(const uint8_t* __restrict__ imgs, int n, int H, int W, long long img_
     float nd[3], nm[3], ns[3];
 #pragma unroll
     for (int c = 0; c < 3; ++c) { nd[c] = norm[c * 3 + 0]; nm[c] = norm[c * 3 + 1]; ns[c] = norm[c * 3 + 2]; }
+    float ri[3], rs[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { ri[c] = __fdiv_rn(__fdiv_rn(1.f, count), nd[c]); rs[c] = __fdiv_rn(1.f, ns[c]); }
+    // out = ((acc/count)/div - mean)/std.  Reciprocal multiplies differ from the reference's divisions by a few
+    // float32 ulps, harmless except where q - mean cancels; there (|d| < 2^-10, ~0.05% of values) the exact
+    // divisions are replayed so the result stays within 1 bf16 ulp of the reference's rounding sequence.
     auto finish = [&](float acc, int c) -> float {
-        const float v = __fdiv_rn(acc, count);
-        return __fdiv_rn(__fsub_rn(__fdiv_rn(v, nd[c]), nm[c]), ns[c]);
+        float d = __fsub_rn(__fmul_rn(acc, ri[c]), nm[c]);
+        if (fabsf(d) < 9.765625e-4f) d = __fsub_rn(__fdiv_rn(__fdiv_rn(acc, count), nd[c]), nm[c]);
+        return __fmul_rn(d, rs[c]);
+    };
+    auto finish_exact = [&](float acc, int c) -> float {
+        return __fdiv_rn(__fsub_rn(__fdiv_rn(__fdiv_rn(acc, count), nd[c]), nm[c]), ns[c]);
     };
     auto store = [&](int c, int o, float v) {
         OutT* q = dst + ((long long)k * 3 + c) * total + o;
         if (sizeof(OutT) == 2) *reinterpret_cast<uint16_t*>(q) = qc_f2bf(v);
         else *reinterpret_cast<float*>(q) = v;
     };
-
-    // source rows touched by this band (samples are monotone in (ph, iy) when bin_h >= 0)
-    const float yf = ysample(ph0, 0), yl_ = ysample(ph1 - 1, sr - 1);
-    const int r_lo = min(max((int)fmaxf(yf, 0.f), 0), H - 1);
-    const int r_hi = min(max((int)fmaxf(yl_, 0.f) + 1, 0), H - 1);
-    const int nrows = r_hi - r_lo + 1;
-    const bool sep = img_ok && bin_h >= 0.f && bin_w >= 0.f && nrows <= rows_max && yf == yf && yl_ == yl_;
-
-    if (!sep) {
-        // direct form for this band (rare): identical to k3_roi_align
-        for (int o = ph0 * PW + tid; o < ph1 * PW; o += blockDim.x) {
-            const int ph = o / PW, pw = o - ph * PW;
-            float acc[3] = {0.f, 0.f, 0.f};
-            if (img_ok) {
-                for (int iy = 0; iy < sr; ++iy) {
-                    const float yy = ysample(ph, iy);
-                    for (int ix = 0; ix < sr; ++ix) {
-                        const float xx = __fadd_rn(__fadd_rn(x1, __fmul_rn((float)pw, bin_w)),
-                                                   __fdiv_rn(__fmul_rn((float)ix + 0.5f, bin_w), (float)sr));
-                        float y = yy, x = xx;
-                        if (y < -1.f || y > (float)H || x < -1.f || x > (float)W) continue;
-                        if (y <= 0.f) y = 0.f;
-                        if (x <= 0.f) x = 0.f;
-                        int yl = (int)y, xl = (int)x, yh, xh;
-                        if (yl >= H - 1) { yh = yl = H - 1; y = (float)yl; } else yh = yl + 1;
-                        if (xl >= W - 1) { xh = xl = W - 1; x = (float)xl; } else xh = xl + 1;
-                        const float ly = __fsub_rn(y, (float)yl), lx = __fsub_rn(x, (float)xl);
-                        const float hy = __fsub_rn(1.f, ly), hx = __fsub_rn(1.f, lx);
-                        const float w1 = __fmul_rn(hy, hx), w2 = __fmul_rn(hy, lx), w3 = __fmul_rn(ly, hx), w4 = __fmul_rn(ly, lx);
-#pragma unroll
-                        for (int c = 0; c < 3; ++c) {
-                            const int sc = swap_rb ? 2 - c : c;
-                            float v = __fmul_rn(w1, (float)__ldg(base + (long long)yl * row_stride + xl * 3 + sc));
-                            v = __fadd_rn(v, __fmul_rn(w2, (float)__ldg(base + (long long)yl * row_stride + xh * 3 + sc)));
-                            v = __fadd_rn(v, __fmul_rn(w3, (float)__ldg(base + (long long)yh * row_stride + xl * 3 + sc)));
-                            v = __fadd_rn(v, __fmul_rn(w4, (float)__ldg(base + (long long)yh * row_stride + xh * 3 + sc)));
-                            acc[c] = __fadd_rn(acc[c], v);
-                        }
-                    }
-                }
-            }
-#pragma unroll
-            for (int c = 0; c < 3; ++c) store(c, o, finish(acc[c], c));
-        }
-        return;
-    }
 
     // (1) x taps: sample ix of output column pw -> (xl, xh, hx, lx); invalid samples get zero weights
     for (int t = tid; t < PW * sr; t += blockDim.x) {
@@ -202,73 +166,139 @@ k3_roi_sep(const uint8_t* __restrict__ imgs, int n, int H, int W, long long img_
         xlo[t] = xl * 3; xhi[t] = xh * 3; wlo[t] = hx; whi[t] = lx;
     }
     __syncthreads();
-    // (2) horizontal pass over the band's source rows
-    for (int rr = warp; rr < nrows; rr += 8) {
-        const uint8_t* row = base + (long long)(r_lo + rr) * row_stride;
-        float* hrow = Hs + (size_t)rr * 3 * PW;
-        for (int pw = lane; pw < PW; pw += 32) {
-            float a0 = 0.f, a1 = 0.f, a2 = 0.f;
-            for (int ix = 0; ix < sr; ++ix) {
-                const int t = pw * sr + ix;
-                const uint8_t* pl = row + xlo[t];
-                const uint8_t* ph_ = row + xhi[t];
-                const float wl = wlo[t], wh = whi[t];
-                a0 += wl * (float)__ldg(pl + 0) + wh * (float)__ldg(ph_ + 0);
-                a1 += wl * (float)__ldg(pl + 1) + wh * (float)__ldg(ph_ + 1);
-                a2 += wl * (float)__ldg(pl + 2) + wh * (float)__ldg(ph_ + 2);
-            }
-            hrow[(swap_rb ? 2 : 0) * PW + pw] = a0;
-            hrow[PW + pw] = a1;
-            hrow[(swap_rb ? 0 : 2) * PW + pw] = a2;
-        }
-    }
-    __syncthreads();
-    // (3) vertical pass + normalise + store (pairs of columns -> 32-bit bf16x2 stores)
-    const int pairs = (PW + 1) >> 1;
-    for (int phl = warp; phl < ph1 - ph0; phl += 8) {
-        const int ph = ph0 + phl;
-        int yl[K3_SR_MAX], yh[K3_SR_MAX];
-        float wyl[K3_SR_MAX], wyh[K3_SR_MAX];
-#pragma unroll
-        for (int iy = 0; iy < K3_SR_MAX; ++iy) {
-            yl[iy] = yh[iy] = 0; wyl[iy] = wyh[iy] = 0.f;
-            if (iy < sr) {
-                float y = ysample(ph, iy);
-                if (!(y < -1.f || y > (float)H)) {
-                    if (y <= 0.f) y = 0.f;
-                    int a = (int)y, b;
-                    if (a >= H - 1) { b = a = H - 1; y = (float)a; } else b = a + 1;
-                    const float ly = __fsub_rn(y, (float)a);
-                    yl[iy] = a - r_lo; yh[iy] = b - r_lo; wyl[iy] = __fsub_rn(1.f, ly); wyh[iy] = ly;
-                }
-            }
-        }
-        for (int pp = lane; pp < pairs; pp += 32) {
-            const int pw = pp * 2;
-            const bool two = pw + 1 < PW;
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                float s0 = 0.f, s1 = 0.f;
-#pragma unroll
-                for (int iy = 0; iy < K3_SR_MAX; ++iy) {
-                    if (iy < sr) {
-                        const float* ha = Hs + ((size_t)yl[iy] * 3 + c) * PW + pw;
-                        const float* hb = Hs + ((size_t)yh[iy] * 3 + c) * PW + pw;
-                        s0 += wyl[iy] * ha[0] + wyh[iy] * hb[0];
-                        if (two) s1 += wyl[iy] * ha[1] + wyh[iy] * hb[1];
+    // the band is processed in sub-bands small enough for their source rows to fit in shared memory
+    const bool geom_ok = img_ok && bin_h >= 0.f && bin_w >= 0.f;
+    int pb = ph0;
+    for (int pa = ph0; pa < ph1; pa = pb) {
+        int nb = 1;
+        if (geom_ok) nb = (int)fminf(fmaxf((float)(rows_max - 3) / fmaxf(bin_h, 1e-6f), 1.f), (float)(ph1 - pa));
+        pb = pa + nb;
+        // source rows touched (samples are monotone in (ph, iy) when bin_h >= 0)
+        const float yf = ysample(pa, 0), yl_ = ysample(pb - 1, sr - 1);
+        const int r_lo = min(max((int)fmaxf(yf, 0.f), 0), H - 1);
+        const int r_hi = min(max((int)fmaxf(yl_, 0.f) + 1, 0), H - 1);
+        const int nrows = r_hi - r_lo + 1;
+        const bool sep = geom_ok && nrows <= rows_max && yf == yf && yl_ == yl_;
+        if (!sep) {
+            // direct form for this band (rare): identical to k3_roi_align
+            for (int o = pa * PW + tid; o < pb * PW; o += blockDim.x) {
+                const int ph = o / PW, pw = o - ph * PW;
+                float acc[3] = {0.f, 0.f, 0.f};
+                if (img_ok) {
+                    for (int iy = 0; iy < sr; ++iy) {
+                        const float yy = ysample(ph, iy);
+                        for (int ix = 0; ix < sr; ++ix) {
+                            const float xx = __fadd_rn(__fadd_rn(x1, __fmul_rn((float)pw, bin_w)),
+                                                       __fdiv_rn(__fmul_rn((float)ix + 0.5f, bin_w), (float)sr));
+                            float y = yy, x = xx;
+                            if (y < -1.f || y > (float)H || x < -1.f || x > (float)W) continue;
+                            if (y <= 0.f) y = 0.f;
+                            if (x <= 0.f) x = 0.f;
+                            int yl = (int)y, xl = (int)x, yh, xh;
+                            if (yl >= H - 1) { yh = yl = H - 1; y = (float)yl; } else yh = yl + 1;
+                            if (xl >= W - 1) { xh = xl = W - 1; x = (float)xl; } else xh = xl + 1;
+                            const float ly = __fsub_rn(y, (float)yl), lx = __fsub_rn(x, (float)xl);
+                            const float hy = __fsub_rn(1.f, ly), hx = __fsub_rn(1.f, lx);
+                            const float w1 = __fmul_rn(hy, hx), w2 = __fmul_rn(hy, lx), w3 = __fmul_rn(ly, hx), w4 = __fmul_rn(ly, lx);
+    #pragma unroll
+                            for (int c = 0; c < 3; ++c) {
+                                const int sc = swap_rb ? 2 - c : c;
+                                float v = __fmul_rn(w1, (float)__ldg(base + (long long)yl * row_stride + xl * 3 + sc));
+                                v = __fadd_rn(v, __fmul_rn(w2, (float)__ldg(base + (long long)yl * row_stride + xh * 3 + sc)));
+                                v = __fadd_rn(v, __fmul_rn(w3, (float)__ldg(base + (long long)yh * row_stride + xl * 3 + sc)));
+                                v = __fadd_rn(v, __fmul_rn(w4, (float)__ldg(base + (long long)yh * row_stride + xh * 3 + sc)));
+                                acc[c] = __fadd_rn(acc[c], v);
+                            }
+                        }
                     }
                 }
-                const float v0 = finish(s0, c), v1 = finish(s1, c);
-                const int o = ph * PW + pw;
-                OutT* q = dst + ((long long)k * 3 + c) * total + o;
-                if (sizeof(OutT) == 2 && two && ((reinterpret_cast<uintptr_t>(q) & 3) == 0)) {
-                    *reinterpret_cast<uint32_t*>(q) = (uint32_t)qc_f2bf(v0) | ((uint32_t)qc_f2bf(v1) << 16);
-                } else {
-                    store(c, o, v0);
-                    if (two) store(c, o + 1, v1);
+    #pragma unroll
+                for (int c = 0; c < 3; ++c) store(c, o, finish_exact(acc[c], c));
+            }
+            continue;
+        }
+            __syncthreads();      // previous sub-band is done with Hs
+            // (2) horizontal pass over the sub-band's source rows
+        for (int rr = warp; rr < nrows; rr += 8) {
+            const uint8_t* row = base + (long long)(r_lo + rr) * row_stride;
+            float* hrow = Hs + (size_t)rr * 3 * PW;
+            for (int pw = lane; pw < PW; pw += 32) {
+                float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+                for (int ix = 0; ix < sr; ++ix) {
+                    const int t = pw * sr + ix;
+                    const uint8_t* pl = row + xlo[t];
+                    const uint8_t* ph_ = row + xhi[t];
+                    const float wl = wlo[t], wh = whi[t];
+                    a0 = __fmaf_rn(wl, (float)__ldg(pl + 0), __fmaf_rn(wh, (float)__ldg(ph_ + 0), a0));
+                    a1 = __fmaf_rn(wl, (float)__ldg(pl + 1), __fmaf_rn(wh, (float)__ldg(ph_ + 1), a1));
+                    a2 = __fmaf_rn(wl, (float)__ldg(pl + 2), __fmaf_rn(wh, (float)__ldg(ph_ + 2), a2));
+                }
+                hrow[(swap_rb ? 2 : 0) * PW + pw] = a0;
+                hrow[PW + pw] = a1;
+                hrow[(swap_rb ? 0 : 2) * PW + pw] = a2;
+            }
+        }
+        __syncthreads();
+        // (3) vertical pass + normalise + store (pairs of columns -> 32-bit bf16x2 stores)
+        const int pairs = (PW + 1) >> 1;
+        for (int phl = warp; phl < pb - pa; phl += 8) {
+            const int ph = pa + phl;
+            int yl[K3_SR_MAX], yh[K3_SR_MAX];
+            float wyl[K3_SR_MAX], wyh[K3_SR_MAX];
+    #pragma unroll
+            for (int iy = 0; iy < K3_SR_MAX; ++iy) {
+                yl[iy] = yh[iy] = 0; wyl[iy] = wyh[iy] = 0.f;
+                if (iy < sr) {
+                    float y = ysample(ph, iy);
+                    if (!(y < -1.f || y > (float)H)) {
+                        if (y <= 0.f) y = 0.f;
+                        int a = (int)y, b;
+                        if (a >= H - 1) { b = a = H - 1; y = (float)a; } else b = a + 1;
+                        const float ly = __fsub_rn(y, (float)a);
+                        yl[iy] = a - r_lo; yh[iy] = b - r_lo; wyl[iy] = __fsub_rn(1.f, ly); wyh[iy] = ly;
+                    }
+                }
+            }
+            // row offsets of the taps (floats), hoisted out of the column loop
+            int oa[K3_SR_MAX], ob[K3_SR_MAX];
+    #pragma unroll
+            for (int iy = 0; iy < K3_SR_MAX; ++iy) { oa[iy] = yl[iy] * 3 * PW; ob[iy] = yh[iy] * 3 * PW; }
+            const bool vec2 = (PW & 1) == 0;                    // float2 loads need 8-byte alignment of every row
+            for (int pp = lane; pp < pairs; pp += 32) {
+                const int pw = pp * 2;
+                const bool two = pw + 1 < PW;
+    #pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    float s0 = 0.f, s1 = 0.f;
+                    const float* hc = Hs + c * PW + pw;
+    #pragma unroll
+                    for (int iy = 0; iy < K3_SR_MAX; ++iy) {
+                        if (iy < sr) {
+                            float2 a, b;
+                            if (vec2) {
+                                a = *reinterpret_cast<const float2*>(hc + oa[iy]);
+                                b = *reinterpret_cast<const float2*>(hc + ob[iy]);
+                            } else {
+                                a.x = hc[oa[iy]]; b.x = hc[ob[iy]];
+                                a.y = two ? hc[oa[iy] + 1] : 0.f; b.y = two ? hc[ob[iy] + 1] : 0.f;
+                            }
+                            s0 = __fmaf_rn(wyl[iy], a.x, __fmaf_rn(wyh[iy], b.x, s0));
+                            s1 = __fmaf_rn(wyl[iy], a.y, __fmaf_rn(wyh[iy], b.y, s1));
+                        }
+                    }
+                    const float v0 = finish(s0, c), v1 = finish(s1, c);
+                    const int o = ph * PW + pw;
+                    OutT* q = dst + ((long long)k * 3 + c) * total + o;
+                    if (sizeof(OutT) == 2 && two && ((reinterpret_cast<uintptr_t>(q) & 3) == 0)) {
+                        *reinterpret_cast<uint32_t*>(q) = (uint32_t)qc_f2bf(v0) | ((uint32_t)qc_f2bf(v1) << 16);
+                    } else {
+                        store(c, o, v0);
+                        if (two) store(c, o + 1, v1);
+                    }
                 }
             }
         }
+
     }
 }
 
@@ -287,7 +317,7 @@ extern "C" int qc_roi_align(qc_ctx* ctx, const uint8_t* imgs, int n, int h, int 
     const int total = out_h * out_w;
     if (sampling_ratio >= 1 && sampling_ratio <= K3_SR_MAX) {
         // rows one 8-row band can touch for boxes inside the frame (+ slack); larger bands fall back in-kernel
-        long long rows_max = (long long)K3_BH * ((h + out_h - 1) / out_h) + 4;
+        long long rows_max = 12;       // source rows per sub-band (bands needing more are split in-kernel)
         const size_t tap_bytes = (size_t)out_w * sampling_ratio * 16;
         const size_t budget = (size_t)ctx->max_smem_optin - 2048;
         const size_t per_row = (size_t)3 * out_w * 4;

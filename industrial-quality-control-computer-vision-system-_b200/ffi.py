@@ -219,7 +219,8 @@ class Context:
         return pl
 
     def preprocess(self, src: torch.Tensor, plan: PrePlan, swap_rb: bool = True, mean=None, std=None,
-                   pad_value: int = 114, out_dtype=torch.bfloat16, out: Optional[torch.Tensor] = None):
+                   pad_value: int = 114, out_dtype=torch.bfloat16, out: Optional[torch.Tensor] = None,
+                   events=None):
         """src: uint8 CUDA tensor [n,h,w,3] (any row/image pitch, channel-contiguous)."""
         assert src.is_cuda and src.dtype == torch.uint8 and src.dim() == 4 and src.shape[3] == 3
         assert src.stride(3) == 1 and src.stride(2) == 3, "pixels must be packed RGB triplets"
@@ -231,9 +232,14 @@ class Context:
         assert out.is_contiguous() and out.dtype in (torch.bfloat16, torch.float32)
         flags = (QC_PRE_SWAP_RB if swap_rb else 0) | (QC_PRE_LUT_UNIFORM if uniform else 0)
         dt = QC_DT_BF16 if out.dtype == torch.bfloat16 else QC_DT_F32
-        rc = self.lib.qc_preprocess(self.h, src.data_ptr(), n, src.stride(0) if n > 1 else src.shape[1] * src.stride(1),
-                                    src.stride(1), C.byref(plan), lut.data_ptr(), pad_value, flags, dt,
-                                    out.data_ptr(), _stream(src.device))
+        args = (self.h, src.data_ptr(), n, src.stride(0) if n > 1 else src.shape[1] * src.stride(1),
+                src.stride(1), C.byref(plan), lut.data_ptr(), pad_value, flags, dt, out.data_ptr(),
+                _stream(src.device))
+        if events is not None:          # CUDA events hugging the launch itself (bench.py roofline)
+            events[0].record()
+        rc = self.lib.qc_preprocess(*args)
+        if events is not None:
+            events[1].record()
         self._check(rc, "qc_preprocess")
         return out
 

@@ -125,8 +125,11 @@ class InspectionPipeline:
         plan = self.plan_for(h, w)
         xshape = (n, 3, plan.dst_h, plan.dst_w)
         xbuf = self.yolo_g.input_buffer(xshape) if self.use_graphs else None
-        with self._timed("k1_preprocess"):
-            x = self.qc.preprocess(frames, plan, swap_rb=swap_rb, out_dtype=self.net_dtype, out=xbuf)
+        ev = None
+        if self.record:
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            self.events.setdefault("k1_preprocess", []).append(ev)
+        x = self.qc.preprocess(frames, plan, swap_rb=swap_rb, out_dtype=self.net_dtype, out=xbuf, events=ev)
         if head_override is not None:
             levels = list(head_override)
         else:
