@@ -156,6 +156,25 @@ def build_resnet50(nc: int = 5, seed: int = 0) -> nn.Module:
     return m.eval()
 
 
+def fold_batchnorm(m: nn.Module) -> nn.Module:
+    """Inference-time Conv+BN folding (same function, fewer elementwise passes over the activations):
+    every (convN, bnN) / downsample (conv, bn) pair of a torchvision ResNet becomes one biased conv."""
+    from torch.nn.utils.fusion import fuse_conv_bn_eval
+    m.eval()
+    m.conv1 = fuse_conv_bn_eval(m.conv1, m.bn1)
+    m.bn1 = nn.Identity()
+    for layer in (m.layer1, m.layer2, m.layer3, m.layer4):
+        for blk in layer:
+            for i in (1, 2, 3):
+                conv, bn = getattr(blk, f"conv{i}", None), getattr(blk, f"bn{i}", None)
+                if conv is not None and isinstance(bn, nn.BatchNorm2d):
+                    setattr(blk, f"conv{i}", fuse_conv_bn_eval(conv, bn))
+                    setattr(blk, f"bn{i}", nn.Identity())
+            if blk.downsample is not None and isinstance(blk.downsample[1], nn.BatchNorm2d):
+                blk.downsample = nn.Sequential(fuse_conv_bn_eval(blk.downsample[0], blk.downsample[1]))
+    return m
+
+
 def yolo_gflops(scale: str, H: int, W: int) -> float:
     """Published YOLOv8 forward cost at 640^2 (8.7/28.6/78.9 GFLOP), scaled by area."""
     base = {"n": 8.7, "s": 28.6, "m": 78.9}[scale]

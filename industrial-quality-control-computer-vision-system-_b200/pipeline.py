@@ -61,7 +61,8 @@ class InspectionPipeline:
         self.letterbox_mode = ffi.QC_PRE_LETTERBOX_AUTO if letterbox_auto else ffi.QC_PRE_LETTERBOX
         torch.backends.cudnn.benchmark = True
         self.yolo = nets.build_yolo(yolo_scale, nc, seed).to(self.dev, net_dtype).to(memory_format=torch.channels_last)
-        self.resnet = nets.build_resnet50(nc, seed).to(self.dev, net_dtype).to(memory_format=torch.channels_last)
+        self.resnet = nets.fold_batchnorm(nets.build_resnet50(nc, seed)).to(self.dev, net_dtype).to(
+            memory_format=torch.channels_last)
         self.yolo_scale = yolo_scale
         self._plans = {}
         # nets replay as CUDA graphs at static shapes; K1 / K3 write straight into the graph inputs
