@@ -16,8 +16,9 @@
 //   k4_hist      [RGB->gray] + 256-bin histogram: 128-bit loads, per-warp lane-private u16 counters
 //   k4_otsu      parallel Otsu from exact integer prefix sums; replays cv2's sequential float64
 //                recurrence only when the maximum is not decisive (ties / plateaus)
-//   k4_mask_ccl  threshold (128-bit loads) -> bit-packed rows in smem -> close/open (4*iters cross
-//                steps with halo) -> global bit rows; band-local 2x2-block union-find in smem
+//   k4_mask      threshold (128-bit loads, SIMD byte compares) -> bit-packed rows in smem -> close/open
+//                (4*iters cross steps with halo) -> global bit rows (1 bit/pixel)
+//   k4_ccl_local band-local 2x2-block union-find in shared memory (one thread per 32-px word)
 //   k4_border    unions across band borders (atomicMin in L2, roots = min block index)
 //   k4_compress  path compression + per-1024-block root counts
 //   k4_scan      exclusive scan of the counts per region -> chunk bases, ncomp
@@ -363,22 +364,20 @@ __device__ __forceinline__ void suf_union(int* L, int a, int b) {
     } while (!done);
 }
 
-// threshold -> morphology -> bit rows + band-local connected components (all in shared memory)
+// threshold -> morphology -> global bit rows (small shared-memory footprint: many CTAs per SM)
 __global__ void __launch_bounds__(K4_THREADS)
-k4_mask_ccl(Img im, const qc_seg_region* __restrict__ regs, int R, int total_bands,
+k4_mask(Img im, const qc_seg_region* __restrict__ regs, int R, int total_bands,
             const int* __restrict__ g_band_off, int iters, const int* __restrict__ cmp,
-            const uint8_t* __restrict__ gray_ws, unsigned* __restrict__ bits, int* __restrict__ parent,
-            int buf_words) {
+            const uint8_t* __restrict__ gray_ws, unsigned* __restrict__ bits, int buf_words) {
     extern __shared__ __align__(16) unsigned sm[];
     unsigned* bufA = sm;
     unsigned* bufB = sm + buf_words;
-    int* lab = reinterpret_cast<int*>(sm + 2 * buf_words);
     __shared__ int s_off[K4_LOC_MAX + 1];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int halo = 4 * iters;
     const int* off = loc_load(s_off, g_band_off, R);
     for (int t = blockIdx.x; t < total_bands; t += gridDim.x) {
-        __syncthreads();                 // previous band is done with bufA/bufB/lab
+        __syncthreads();                 // previous band is done with bufA/bufB
         const int r = loc_find(off, R, t);
         const qc_seg_region rg = regs[r];
         const int wpr = wpr_of(rg);
@@ -411,7 +410,10 @@ k4_mask_ccl(Img im, const qc_seg_region* __restrict__ regs, int R, int total_ban
                         const unsigned w4[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
-                            const unsigned mk = __vcmpgeu4(w4[q], lo4) & __vcmpleu4(w4[q], hi4) & 0x01010101u;
+                            // the interval is one-sided in practice ([lo,255] light, [0,hi] dark): one compare
+                            unsigned mk = hi >= 255 ? __vsetgeu4(w4[q], lo4)
+                                        : lo <= 0   ? __vsetleu4(w4[q], hi4)
+                                                    : (__vsetgeu4(w4[q], lo4) & __vsetleu4(w4[q], hi4));
                             b16 |= ((mk * 0x01020408u) >> 24) << (4 * q);
                         }
                     } else {
@@ -466,82 +468,123 @@ k4_mask_ccl(Img im, const qc_seg_region* __restrict__ regs, int R, int total_ban
             const int yy = wi / wpr, wx = wi - yy * wpr;
             bits[rg.bits_offset + (long long)(y0 + yy) * wpr + wx] = src[(y0 - row_lo + yy) * wpr + wx];
         }
-        // ---- band-local CCL on 2x2 blocks (8-connectivity): one thread per 32-pixel word cell
-        //      (16 blocks); empty words are skipped and their labels never touched ------------------
-        const int bw = bw_of(rg), bwp = wpr * 16;
-        const int by0 = y0 >> 1, nbr = ((y1 + 1) >> 1) - by0;
-        const unsigned* band = src + (y0 - row_lo) * wpr;          // band rows only: no look above y0
+    }
+}
+
+// band-local CCL on 2x2 blocks (8-connectivity): bit rows of the band -> shared memory (zero-padded by one
+// row/word on every side so neighbour reads need no bounds checks), union-find on shared-memory labels.
+// Non-empty 32-pixel word cells are compacted first; then every foreground block gets its own thread
+// (16 threads per non-empty cell), which keeps warps busy whatever the sparsity.
+__global__ void __launch_bounds__(K4_THREADS)
+k4_ccl_local(const qc_seg_region* __restrict__ regs, int R, int total_bands, const int* __restrict__ g_band_off,
+             const unsigned* __restrict__ bits, int* __restrict__ parent, int band_words, int lab_words) {
+    extern __shared__ __align__(16) unsigned sm[];
+    unsigned* band_s = sm;                                         // [34][wpr+2], zero border
+    int* lab = reinterpret_cast<int*>(sm + band_words);            // [16][wpr*16]
+    unsigned short* cell_list = reinterpret_cast<unsigned short*>(lab + lab_words);   // [16*wpr] (row<<11 | word)
+    __shared__ int s_off[K4_LOC_MAX + 1];
+    __shared__ int s_ncell;
+    const int tid = threadIdx.x;
+    const int* off = loc_load(s_off, g_band_off, R);
+    for (int t = blockIdx.x; t < total_bands; t += gridDim.x) {
+        __syncthreads();                 // previous band is done with band_s/lab/cell_list
+        const qc_seg_region rg = regs[loc_find(off, R, t)];
+        const int wpr = wpr_of(rg), pw = wpr + 2;
+        const int y0 = (t - rg.band_offset) * K4_BAND_ROWS;
+        const int y1 = min(y0 + K4_BAND_ROWS, rg.h);
         const int brows = y1 - y0;
-        auto rowword = [&](int ry, int wx) -> unsigned {           // ry relative to y0
-            return (ry < 0 || ry >= brows || wx < 0 || wx >= wpr) ? 0u : band[ry * wpr + wx];
-        };
+        {
+            const unsigned* B = bits + rg.bits_offset + (long long)y0 * wpr;
+            for (int i = tid; i < (K4_BAND_ROWS + 2) * pw; i += K4_THREADS) {
+                const int rr = i / pw - 1, wx = i - (rr + 1) * pw - 1;      // band row, word (both may be -1 / past the end)
+                band_s[i] = (rr >= 0 && rr < brows && wx >= 0 && wx < wpr) ? __ldg(B + rr * wpr + wx) : 0u;
+            }
+            if (tid == 0) s_ncell = 0;
+        }
+        __syncthreads();
+        // padded accessor: ry in [-1, 32], wx in [-1, wpr]
+        auto rowword = [&](int ry, int wx) -> unsigned { return band_s[(ry + 1) * pw + wx + 1]; };
+        const int bw = bw_of(rg), bwp = wpr * 16;
+        const int by0 = y0 >> 1, nbr = (brows + 1) >> 1;
+        // (1) per cell: run-head labels, and compaction of the non-empty cells into cell_list
         const int ncell = nbr * wpr;
-        // init: label = head of the horizontal run of connected blocks inside the word
-        for (int ci = tid; ci < ncell; ci += K4_THREADS) {
+        for (int c0 = 0; c0 < ncell; c0 += K4_THREADS) {
+            const int ci = c0 + tid;
             const int byy = ci / wpr, wx = ci - byy * wpr;
-            const unsigned v = rowword(2 * byy, wx) | rowword(2 * byy + 1, wx);
-            if (!v) continue;
-            const int base = byy * bwp + wx * 16;
-            int head = 0;
+            unsigned v = 0;
+            if (ci < ncell) v = rowword(2 * byy, wx) | rowword(2 * byy + 1, wx);
+            if (v) {
+                const int base = byy * bwp + wx * 16;
+                int head = 0;
 #pragma unroll
-            for (int k = 0; k < 16; ++k) {
-                if ((v >> (2 * k)) & 3u) {
-                    const bool link = k > 0 && ((v >> (2 * k)) & 1u) && ((v >> (2 * k - 1)) & 1u);
-                    if (!link) head = base + k;
-                    lab[base + k] = head;
+                for (int k = 0; k < 16; ++k) {
+                    if ((v >> (2 * k)) & 3u) {
+                        const bool link = k > 0 && ((v >> (2 * k)) & 1u) && ((v >> (2 * k - 1)) & 1u);
+                        if (!link) head = base + k;
+                        lab[base + k] = head;
+                    }
                 }
+            }
+            const unsigned bm = __ballot_sync(0xffffffffu, v != 0);
+            if (bm) {
+                int basei = 0;
+                const int leader = __ffs(bm) - 1;
+                if ((tid & 31) == leader) basei = atomicAdd(&s_ncell, __popc(bm));
+                basei = __shfl_sync(0xffffffffu, basei, leader);
+                if (v) cell_list[basei + __popc(bm & ((1u << (tid & 31)) - 1u))] = (unsigned short)((byy << 11) | wx);
             }
         }
         __syncthreads();
-        for (int ci = tid; ci < ncell; ci += K4_THREADS) {
-            const int byy = ci / wpr, wx = ci - byy * wpr;
+        const int nne = s_ncell;
+        // (2) unions: one thread per block of every non-empty cell
+        for (int it = tid; it < nne * 16; it += K4_THREADS) {
+            const int ce = cell_list[it >> 4], k = it & 15;
+            const int byy = ce >> 11, wx = ce & 2047;
             const unsigned r0 = rowword(2 * byy, wx), r1 = rowword(2 * byy + 1, wx);
             const unsigned v = r0 | r1;
-            if (!v) continue;
+            if (!((v >> (2 * k)) & 3u)) continue;
+            const int me = byy * bwp + wx * 16 + k;
+            if (k == 0 && (v & 1u)) {                                    // run continues from the previous word
+                const unsigned vl = (rowword(2 * byy, wx - 1) | rowword(2 * byy + 1, wx - 1)) >> 31;
+                if (vl) suf_union(lab, me, me - 1);
+            }
+            if (byy == 0) continue;                                      // the band above is stitched by k4_border
+            const unsigned a = (r0 >> (2 * k)) & 1u, b = (r0 >> (2 * k + 1)) & 1u;
+            if (!(a | b)) continue;
             const unsigned u = rowword(2 * byy - 1, wx);
-            const unsigned vl = (rowword(2 * byy, wx - 1) | rowword(2 * byy + 1, wx - 1)) >> 31;
-            const unsigned ul = rowword(2 * byy - 1, wx - 1) >> 31;
-            const unsigned ur = rowword(2 * byy - 1, wx + 1) & 1u;
-            const int base = byy * bwp + wx * 16;
-            if ((v & 1u) && vl) suf_union(lab, base, base - 1);          // run continues from the previous word
-            if (byy > 0 && (u | ul | ur)) {
-                unsigned m = (v | (v >> 1)) & 0x55555555u;               // one bit per foreground block
-                while (m) {
-                    const int k = (__ffs(m) - 1) >> 1;
-                    m &= m - 1;
-                    const unsigned a = (r0 >> (2 * k)) & 1u, b = (r0 >> (2 * k + 1)) & 1u;
-                    if (!(a | b)) continue;
-                    const unsigned u0 = (u >> (2 * k)) & 1u, u1 = (u >> (2 * k + 1)) & 1u;
-                    const int me = base + k;
-                    if (u0 | u1) suf_union(lab, me, me - bwp);
-                    // up-left / up-right only when not already implied through the upper block
-                    if (a && !u0) {
-                        const unsigned um = k > 0 ? (u >> (2 * k - 1)) & 1u : ul;
-                        if (um) suf_union(lab, me, me - bwp - 1);
-                    }
-                    if (b && !u1) {
-                        const unsigned up2 = k < 15 ? (u >> (2 * k + 2)) & 1u : ur;
-                        if (up2) suf_union(lab, me, me - bwp + 1);
-                    }
+            const unsigned u0 = (u >> (2 * k)) & 1u, u1 = (u >> (2 * k + 1)) & 1u;
+            if (u0 | u1) {
+                // redundant when block k-1 is in my run (pre-linked), is itself connected upwards, and the two upper
+                // blocks are linked (columns 2k-1 and 2k of the upper row both set): connectivity follows by induction
+                bool skip = false;
+                if (k > 0 && ((v >> (2 * k)) & 1u) && ((v >> (2 * k - 1)) & 1u) && u0 && ((u >> (2 * k - 1)) & 1u)) {
+                    const unsigned pa = (r0 >> (2 * k - 2)) & 3u, pu = (u >> (2 * k - 2)) & 3u;
+                    skip = pa && pu;
                 }
+                if (!skip) suf_union(lab, me, me - bwp);
+            }
+            // up-left / up-right only when not already implied through the upper block
+            if (a && !u0) {
+                const unsigned um = k > 0 ? (u >> (2 * k - 1)) & 1u : rowword(2 * byy - 1, wx - 1) >> 31;
+                if (um) suf_union(lab, me, me - bwp - 1);
+            }
+            if (b && !u1) {
+                const unsigned up2 = k < 15 ? (u >> (2 * k + 2)) & 1u : rowword(2 * byy - 1, wx + 1) & 1u;
+                if (up2) suf_union(lab, me, me - bwp + 1);
             }
         }
         __syncthreads();
+        // (3) flatten to global block indices (foreground blocks only)
         const float inv_bwp = 1.0f / (float)bwp;
-        for (int ci = tid; ci < ncell; ci += K4_THREADS) {
-            const int byy = ci / wpr, wx = ci - byy * wpr;
+        for (int it = tid; it < nne * 16; it += K4_THREADS) {
+            const int ce = cell_list[it >> 4], k = it & 15;
+            const int byy = ce >> 11, wx = ce & 2047;
             const unsigned v = rowword(2 * byy, wx) | rowword(2 * byy + 1, wx);
-            if (!v) continue;
-            const int base = byy * bwp + wx * 16;
-            int* prow = parent + rg.blk_offset + (long long)(by0 + byy) * bw + wx * 16;
-            unsigned m = (v | (v >> 1)) & 0x55555555u;
-            while (m) {
-                const int k = (__ffs(m) - 1) >> 1;
-                m &= m - 1;
-                const int rt = suf_find(lab, base + k);
-                const int rby = (int)(((float)rt + 0.5f) * inv_bwp);     // rt / bwp (exact: rt < 2^20)
-                prow[k] = rg.blk_offset + (by0 + rby) * bw + (rt - rby * bwp);
-            }
+            if (!((v >> (2 * k)) & 3u)) continue;
+            const int rt = suf_find(lab, byy * bwp + wx * 16 + k);
+            const int rby = (int)(((float)rt + 0.5f) * inv_bwp);         // rt / bwp (exact: rt < 2^20)
+            parent[rg.blk_offset + (long long)(by0 + byy) * bw + wx * 16 + k] =
+                rg.blk_offset + (by0 + rby) * bw + (rt - rby * bwp);
         }
     }
 }
@@ -821,43 +864,40 @@ k4_final(const qc_seg_region* __restrict__ regs, int R, int total_bands, const i
         const int* st = stats + (long long)rg.stats_offset * 5;
         const int* P = parent + rg.blk_offset;
         int kept = 0;
-        // 4 consecutive pixels per thread
-        const int q_per_row = (rg.w + 3) >> 2;
-        for (int i = tid; i < (y1 - y0) * q_per_row; i += K4_THREADS) {
-            const int yy = i / q_per_row, q = i - yy * q_per_row;
-            const int y = y0 + yy, x0 = q * 4;
-            const unsigned word = __ldg(B + (long long)y * wpr + (x0 >> 5));
-            const unsigned nib = (word >> (x0 & 31)) & 15u;
-            int lab[4] = {0, 0, 0, 0};
-            if (nib) {
-                const int* prow = P + (long long)(y >> 1) * bw + (x0 >> 1);
-                int l01 = 0, l23 = 0;
-                if (nib & 3u) l01 = prow[0];
-                if (nib & 12u) l23 = prow[1];
-                // min-area filter (components beyond max_comp have no recorded area: kept)
-                if (l01 > 0 && l01 < rg.max_comp && st[(long long)l01 * 5 + 4] < rg.min_area) l01 = 0;
-                if (l23 > 0 && l23 < rg.max_comp && st[(long long)l23 * 5 + 4] < rg.min_area) l23 = 0;
-                lab[0] = (nib & 1u) ? l01 : 0; lab[1] = (nib & 2u) ? l01 : 0;
-                lab[2] = (nib & 4u) ? l23 : 0; lab[3] = (nib & 8u) ? l23 : 0;
-            }
-            const long long o = rg.out_offset + (long long)y * rg.w + x0;
-            const int nvalid = min(4, rg.w - x0);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) kept += (j < nvalid && lab[j] > 0) ? 1 : 0;
-            if (out_labels) {
-                if (nvalid == 4 && ((o & 3) == 0)) {
-                    qc_st_cs(out_labels + o, make_uint4((unsigned)lab[0], (unsigned)lab[1], (unsigned)lab[2], (unsigned)lab[3]));
-                } else {
-                    for (int j = 0; j < nvalid; ++j) out_labels[o + j] = lab[j];
+        // warp per pixel row, 4 consecutive pixels per lane; background quads (the vast majority) take a
+        // branch-light path that only stores zeros
+        const bool al = ((rg.out_offset & 3) == 0) && ((rg.w & 3) == 0);
+        for (int y = y0 + warp; y < y1; y += K4_THREADS / 32) {
+            const unsigned* Brow = B + (long long)y * wpr;
+            const int* prow_y = P + (long long)(y >> 1) * bw;
+            const long long orow = rg.out_offset + (long long)y * rg.w;
+            for (int x0 = lane * 4; x0 < rg.w; x0 += 128) {
+                const unsigned nib = (__ldg(Brow + (x0 >> 5)) >> (x0 & 31)) & 15u;
+                int l0 = 0, l1 = 0, l2 = 0, l3 = 0;
+                if (nib) {
+                    int l01 = 0, l23 = 0;
+                    if (nib & 3u) l01 = prow_y[x0 >> 1];
+                    if (nib & 12u) l23 = prow_y[(x0 >> 1) + 1];
+                    // min-area filter (components beyond max_comp have no recorded area: kept)
+                    if (l01 > 0 && l01 < rg.max_comp && st[(long long)l01 * 5 + 4] < rg.min_area) l01 = 0;
+                    if (l23 > 0 && l23 < rg.max_comp && st[(long long)l23 * 5 + 4] < rg.min_area) l23 = 0;
+                    l0 = (nib & 1u) ? l01 : 0; l1 = (nib & 2u) ? l01 : 0;
+                    l2 = (nib & 4u) ? l23 : 0; l3 = (nib & 8u) ? l23 : 0;
+                    kept += (l0 > 0) + (l1 > 0) + (l2 > 0) + (l3 > 0);
                 }
-            }
-            if (out_mask) {
-                if (nvalid == 4 && ((o & 3) == 0)) {
-                    const unsigned m = (lab[0] > 0 ? 0xFFu : 0u) | (lab[1] > 0 ? 0xFF00u : 0u) |
-                                       (lab[2] > 0 ? 0xFF0000u : 0u) | (lab[3] > 0 ? 0xFF000000u : 0u);
-                    *reinterpret_cast<unsigned*>(out_mask + o) = m;
+                const long long o = orow + x0;
+                if (al) {
+                    if (out_labels) qc_st_cs(out_labels + o, make_uint4((unsigned)l0, (unsigned)l1, (unsigned)l2, (unsigned)l3));
+                    if (out_mask)
+                        *reinterpret_cast<unsigned*>(out_mask + o) = (l0 > 0 ? 0xFFu : 0u) | (l1 > 0 ? 0xFF00u : 0u) |
+                                                                      (l2 > 0 ? 0xFF0000u : 0u) | (l3 > 0 ? 0xFF000000u : 0u);
                 } else {
-                    for (int j = 0; j < nvalid; ++j) out_mask[o + j] = lab[j] > 0 ? 255 : 0;
+                    const int lab[4] = {l0, l1, l2, l3};
+                    const int nvalid = min(4, rg.w - x0);
+                    for (int j = 0; j < nvalid; ++j) {
+                        if (out_labels) out_labels[o + j] = lab[j];
+                        if (out_mask) out_mask[o + j] = lab[j] > 0 ? 255 : 0;
+                    }
                 }
             }
         }
@@ -969,15 +1009,24 @@ extern "C" int qc_segment(qc_ctx* ctx, const uint8_t* imgs, const qc_seg_params*
     const int halo = 4 * p->morph_iters;
     const int wpr_max = (p->max_region_w + 31) / 32;
     const int buf_words = (K4_BAND_ROWS + 2 * halo) * wpr_max;
-    const size_t smem = (size_t)buf_words * 4 * 2 + (size_t)(K4_BAND_ROWS / 2) * wpr_max * 16 * 4;
-    if ((long long)smem + (K4_LOC_MAX + 1) * 4 + 1024 > ctx->max_smem_optin)
+    const size_t smem_mask = (size_t)buf_words * 4 * 2;
+    const int band_words = ((K4_BAND_ROWS + 2) * (wpr_max + 2) + 3) & ~3;
+    const int lab_words = (K4_BAND_ROWS / 2) * wpr_max * 16;
+    const size_t smem_ccl = (size_t)band_words * 4 + (size_t)lab_words * 4 + (size_t)(K4_BAND_ROWS / 2) * wpr_max * 2;
+    const size_t smem_need = std::max(smem_mask, smem_ccl);
+    if ((long long)smem_need + (K4_LOC_MAX + 1) * 4 + 1024 > ctx->max_smem_optin)
         QC_FAIL(ctx, QC_ERR_UNSUPPORTED, "qc_segment: region width %d needs %zu B of shared memory (max %d)",
-                p->max_region_w, smem, ctx->max_smem_optin);
-    QC_CUDA(ctx, cudaFuncSetAttribute(k4_mask_ccl, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                p->max_region_w, smem_need, ctx->max_smem_optin);
     int occ = 1;
-    QC_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k4_mask_ccl, K4_THREADS, smem));
-    k4_mask_ccl<<<std::min(p->total_bands, sms * std::max(occ, 1)), K4_THREADS, smem, st>>>(
-        im, regions, R, p->total_bands, w.band_off, p->morph_iters, w.cmp, w.gray, w.bits, w.parent, buf_words);
+    QC_CUDA(ctx, cudaFuncSetAttribute(k4_mask, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_mask));
+    QC_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k4_mask, K4_THREADS, smem_mask));
+    k4_mask<<<std::min(p->total_bands, sms * std::max(occ, 1)), K4_THREADS, smem_mask, st>>>(
+        im, regions, R, p->total_bands, w.band_off, p->morph_iters, w.cmp, w.gray, w.bits, buf_words);
+    QC_LAUNCHED(ctx);
+    QC_CUDA(ctx, cudaFuncSetAttribute(k4_ccl_local, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ccl));
+    QC_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k4_ccl_local, K4_THREADS, smem_ccl));
+    k4_ccl_local<<<std::min(p->total_bands, sms * std::max(occ, 1)), K4_THREADS, smem_ccl, st>>>(
+        regions, R, p->total_bands, w.band_off, w.bits, w.parent, band_words, lab_words);
     QC_LAUNCHED(ctx);
 
     const int band_grid = std::min(p->total_bands, sms * 8);
