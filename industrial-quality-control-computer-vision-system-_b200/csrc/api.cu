@@ -14,6 +14,7 @@ int qc_create(int device, qc_ctx** out) {
     c->device = device;
     c->launches = 0;
     c->err[0] = 0;
+    c->n_attr = 0;
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete c; return QC_ERR_CUDA; }
     c->sm_count = prop.multiProcessorCount;

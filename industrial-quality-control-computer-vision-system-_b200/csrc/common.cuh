@@ -8,12 +8,15 @@
 #include <atomic>
 #include "../../include/qcgraft.h"
 
+struct qc_attr_entry { const void* func; int smem; int occ; int threads; };
 struct qc_ctx {
     int device;
     int sm_count;
     int max_smem_optin;
     std::atomic<long long> launches;
     char err[512];
+    qc_attr_entry attr[48];     // per-kernel cache of the opt-in smem limit / occupancy (one ctx per thread)
+    int n_attr;
 };
 
 #define QC_FAIL(ctx, code, ...)                                   \
@@ -36,6 +39,27 @@ struct qc_ctx {
         (ctx)->launches.fetch_add(1, std::memory_order_relaxed);                        \
         QC_CUDA(ctx, cudaGetLastError());                                               \
     } while (0)
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) + occupancy query, cached per (kernel, smem, threads):
+// both are host-side driver calls worth several microseconds, too slow to repeat on every launch.
+template <typename F>
+static inline int qc_prepare(qc_ctx* ctx, F func, int smem, int threads, int* occ_out) {
+    const void* key = reinterpret_cast<const void*>(func);
+    for (int i = 0; i < ctx->n_attr; ++i) {
+        qc_attr_entry& e = ctx->attr[i];
+        if (e.func == key && e.smem == smem && e.threads == threads) {
+            if (occ_out) *occ_out = e.occ;
+            return QC_OK;
+        }
+    }
+    if (smem > 48 * 1024) QC_CUDA(ctx, cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    int occ = 1;
+    QC_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, func, threads, (size_t)smem));
+    if (occ < 1) occ = 1;
+    if (ctx->n_attr < 48) ctx->attr[ctx->n_attr++] = qc_attr_entry{key, smem, occ, threads};
+    if (occ_out) *occ_out = occ;
+    return QC_OK;
+}
 
 static inline size_t qc_align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 

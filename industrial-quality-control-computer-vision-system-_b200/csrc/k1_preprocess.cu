@@ -271,10 +271,8 @@ static int launch_k1(qc_ctx* ctx, const uint8_t* src, int n, int64_t src_img_str
         const long long total = (long long)n * chunks;
         const size_t smem = (size_t)K1_LUT_WORDS * 4 + 2 * K1_CHUNK_BYTES;
         auto kern = swap_rb ? k1_pack_stream<OutT, 1, true> : k1_pack_stream<OutT, 1, false>;
-        QC_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        int occ = 0;
-        QC_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, K1_THREADS, smem));
-        if (occ < 1) occ = 1;
+        int occ = 1;
+        if (int rc = qc_prepare(ctx, kern, (int)smem, K1_THREADS, &occ)) return rc;
         long long grid = (long long)ctx->sm_count * occ;
         if (grid > total) grid = total;
         kern<<<(unsigned)grid, K1_THREADS, smem, st>>>(src, dst, lut, P, src_img_stride, chunks, total);
@@ -286,7 +284,7 @@ static int launch_k1(qc_ctx* ctx, const uint8_t* src, int n, int64_t src_img_str
         const long long total = (long long)n * chunks;
         const size_t smem = (size_t)3 * K1_LUT_WORDS * 4 + 2 * K1_CHUNK_BYTES;
         auto kern = swap_rb ? k1_pack_stream<OutT, 3, true> : k1_pack_stream<OutT, 3, false>;
-        QC_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (int rc = qc_prepare(ctx, kern, (int)smem, K1_THREADS, nullptr)) return rc;
         long long grid = ctx->sm_count;
         if (grid > total) grid = total;
         kern<<<(unsigned)grid, K1_THREADS, smem, st>>>(src, dst, lut, P, src_img_stride, chunks, total);

@@ -498,7 +498,7 @@ int launch_nms(qc_ctx* ctx, const NmsArgs& a, int n, const Ws& w, float* out_det
                int* out_ncand, cudaStream_t st) {
     const size_t smem = nms_smem_bytes(a.max_det);
     if ((int)smem > ctx->max_smem_optin) QC_FAIL(ctx, QC_ERR_UNSUPPORTED, "k2_nms: max_det %d needs too much shared memory", a.max_det);
-    QC_CUDA(ctx, cudaFuncSetAttribute(k2_nms, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (int rc = qc_prepare(ctx, k2_nms, (int)smem, K2_NMS_THREADS, nullptr)) return rc;
     k2_nms<<<n, K2_NMS_THREADS, smem, st>>>(a, w.key, w.box, w.count, w.gkeys, w.gvals, w.gsorted, out_det, out_idx,
                                             out_count, out_ncand);
     QC_LAUNCHED(ctx);

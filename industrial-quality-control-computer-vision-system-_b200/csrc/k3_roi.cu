@@ -326,12 +326,12 @@ extern "C" int qc_roi_align(qc_ctx* ctx, const uint8_t* imgs, int n, int h, int 
             const size_t smem = tap_bytes + (size_t)rows_max * per_row;
             dim3 grid((unsigned)((out_h + K3_BH - 1) / K3_BH), (unsigned)K);
             if (out_dtype == QC_DT_BF16) {
-                QC_CUDA(ctx, cudaFuncSetAttribute(k3_roi_sep<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                if (int rc = qc_prepare(ctx, k3_roi_sep<__nv_bfloat16>, (int)smem, 256, nullptr)) return rc;
                 k3_roi_sep<__nv_bfloat16><<<grid, 256, smem, st>>>(imgs, n, h, w, img_stride, row_stride, rois, K, out_h,
                                                                    out_w, sampling_ratio, aligned, swap_rb, norm,
                                                                    (__nv_bfloat16*)dst, (int)rows_max);
             } else if (out_dtype == QC_DT_F32) {
-                QC_CUDA(ctx, cudaFuncSetAttribute(k3_roi_sep<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                if (int rc = qc_prepare(ctx, k3_roi_sep<float>, (int)smem, 256, nullptr)) return rc;
                 k3_roi_sep<float><<<grid, 256, smem, st>>>(imgs, n, h, w, img_stride, row_stride, rois, K, out_h, out_w,
                                                            sampling_ratio, aligned, swap_rb, norm, (float*)dst,
                                                            (int)rows_max);

@@ -35,7 +35,7 @@
 namespace {
 
 constexpr int K4_THREADS = 256;
-constexpr int K4_BAND_ROWS = 32;     // pixel rows per band (16 block rows)
+constexpr int K4_BAND_ROWS = 16;     // pixel rows per band (8 block rows)
 constexpr int K4_CHUNK = 256;        // word cells (16 blocks each) per ranking chunk
 
 struct SegWs {
@@ -998,7 +998,7 @@ extern "C" int qc_segment(qc_ctx* ctx, const uint8_t* imgs, const qc_seg_params*
     // per-warp u16 histogram tables only when some band can exceed K4_HIST_BIG_PX pixels
     const bool big_hist = (long long)p->max_region_w * K4_BAND_ROWS > K4_HIST_BIG_PX;
     const int hist_smem = big_hist ? K4_HIST_SMEM : 0;
-    QC_CUDA(ctx, cudaFuncSetAttribute(k4_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, K4_HIST_SMEM));
+    if (int rc = qc_prepare(ctx, k4_hist, K4_HIST_SMEM, K4_THREADS, nullptr)) return rc;
     k4_hist<<<std::min(p->total_bands, big_hist ? sms : sms * 6), K4_THREADS, hist_smem, st>>>(
         im, regions, R, p->total_bands, w.band_off, w.hist, w.gray);
     QC_LAUNCHED(ctx);
@@ -1018,13 +1018,11 @@ extern "C" int qc_segment(qc_ctx* ctx, const uint8_t* imgs, const qc_seg_params*
         QC_FAIL(ctx, QC_ERR_UNSUPPORTED, "qc_segment: region width %d needs %zu B of shared memory (max %d)",
                 p->max_region_w, smem_need, ctx->max_smem_optin);
     int occ = 1;
-    QC_CUDA(ctx, cudaFuncSetAttribute(k4_mask, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_mask));
-    QC_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k4_mask, K4_THREADS, smem_mask));
+    if (int rc = qc_prepare(ctx, k4_mask, (int)smem_mask, K4_THREADS, &occ)) return rc;
     k4_mask<<<std::min(p->total_bands, sms * std::max(occ, 1)), K4_THREADS, smem_mask, st>>>(
         im, regions, R, p->total_bands, w.band_off, p->morph_iters, w.cmp, w.gray, w.bits, buf_words);
     QC_LAUNCHED(ctx);
-    QC_CUDA(ctx, cudaFuncSetAttribute(k4_ccl_local, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ccl));
-    QC_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k4_ccl_local, K4_THREADS, smem_ccl));
+    if (int rc = qc_prepare(ctx, k4_ccl_local, (int)smem_ccl, K4_THREADS, &occ)) return rc;
     k4_ccl_local<<<std::min(p->total_bands, sms * std::max(occ, 1)), K4_THREADS, smem_ccl, st>>>(
         regions, R, p->total_bands, w.band_off, w.bits, w.parent, band_words, lab_words);
     QC_LAUNCHED(ctx);

@@ -175,6 +175,38 @@ def fold_batchnorm(m: nn.Module) -> nn.Module:
     return m
 
 
+class _FusedBottleneck(nn.Module):
+    """torchvision Bottleneck (BN already folded) with cuDNN's fused conv+bias+ReLU / conv+bias+add+ReLU
+    epilogues instead of separate elementwise kernels (same arithmetic, fewer passes over the activations)."""
+
+    def __init__(self, blk):
+        super().__init__()
+        self.c1, self.c2, self.c3 = blk.conv1, blk.conv2, blk.conv3
+        self.down = blk.downsample[0] if blk.downsample is not None else None
+
+    @staticmethod
+    def _cr(x, c):
+        return torch.cudnn_convolution_relu(x, c.weight, c.bias, c.stride, c.padding, c.dilation, c.groups)
+
+    def forward(self, x):
+        idt = x
+        if self.down is not None:
+            d = self.down
+            idt = torch.nn.functional.conv2d(x, d.weight, d.bias, d.stride, d.padding, d.dilation, d.groups)
+        out = self._cr(self._cr(x, self.c1), self.c2)
+        c = self.c3
+        return torch.cudnn_convolution_add_relu(out, c.weight, idt, 1.0, c.bias, c.stride, c.padding, c.dilation,
+                                                c.groups)
+
+
+def fuse_resnet_epilogues(m: nn.Module) -> nn.Module:
+    """Call after fold_batchnorm() and after moving the model to CUDA."""
+    for name in ("layer1", "layer2", "layer3", "layer4"):
+        layer = getattr(m, name)
+        setattr(m, name, nn.Sequential(*[_FusedBottleneck(b) for b in layer]))
+    return m
+
+
 def yolo_gflops(scale: str, H: int, W: int) -> float:
     """Published YOLOv8 forward cost at 640^2 (8.7/28.6/78.9 GFLOP), scaled by area."""
     base = {"n": 8.7, "s": 28.6, "m": 78.9}[scale]

@@ -63,6 +63,8 @@ class InspectionPipeline:
         self.yolo = nets.build_yolo(yolo_scale, nc, seed).to(self.dev, net_dtype).to(memory_format=torch.channels_last)
         self.resnet = nets.fold_batchnorm(nets.build_resnet50(nc, seed)).to(self.dev, net_dtype).to(
             memory_format=torch.channels_last)
+        if net_dtype in (torch.bfloat16, torch.float16):
+            self.resnet = nets.fuse_resnet_epilogues(self.resnet)      # cuDNN conv+bias(+add)+ReLU
         self.yolo_scale = yolo_scale
         self._plans = {}
         # nets replay as CUDA graphs at static shapes; K1 / K3 write straight into the graph inputs
