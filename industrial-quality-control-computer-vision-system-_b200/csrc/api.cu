@@ -2,6 +2,11 @@
 #include "common.cuh"
 #include <new>
 
+qc_attr_table& qc_attrs() {
+    static qc_attr_table t;
+    return t;
+}
+
 extern "C" {
 
 int qc_create(int device, qc_ctx** out) {
@@ -14,7 +19,6 @@ int qc_create(int device, qc_ctx** out) {
     c->device = device;
     c->launches = 0;
     c->err[0] = 0;
-    c->n_attr = 0;
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete c; return QC_ERR_CUDA; }
     c->sm_count = prop.multiProcessorCount;

@@ -15,8 +15,6 @@ struct qc_ctx {
     int max_smem_optin;
     std::atomic<long long> launches;
     char err[512];
-    qc_attr_entry attr[48];     // per-kernel cache of the opt-in smem limit / occupancy (one ctx per thread)
-    int n_attr;
 };
 
 #define QC_FAIL(ctx, code, ...)                                   \
@@ -41,22 +39,37 @@ struct qc_ctx {
     } while (0)
 
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) + occupancy query, cached per (kernel, smem, threads):
-// both are host-side driver calls worth several microseconds, too slow to repeat on every launch.
+// both are host-side driver calls worth several microseconds, too slow to repeat on every launch.  The
+// attribute is per-function PROCESS state (last value wins), so the table is process-global (api.cu) and
+// the limit is only ever raised.
+#include <mutex>
+struct qc_attr_table {
+    std::mutex mu;
+    qc_attr_entry e[96];
+    int n = 0;
+};
+qc_attr_table& qc_attrs();      // defined in api.cu
+
 template <typename F>
 static inline int qc_prepare(qc_ctx* ctx, F func, int smem, int threads, int* occ_out) {
     const void* key = reinterpret_cast<const void*>(func);
-    for (int i = 0; i < ctx->n_attr; ++i) {
-        qc_attr_entry& e = ctx->attr[i];
-        if (e.func == key && e.smem == smem && e.threads == threads) {
-            if (occ_out) *occ_out = e.occ;
+    qc_attr_table& t = qc_attrs();
+    std::lock_guard<std::mutex> lock(t.mu);
+    int prev_max = 0;
+    for (int i = 0; i < t.n; ++i) {
+        if (t.e[i].func != key) continue;
+        if (t.e[i].smem == smem && t.e[i].threads == threads) {
+            if (occ_out) *occ_out = t.e[i].occ;
             return QC_OK;
         }
+        if (t.e[i].smem > prev_max) prev_max = t.e[i].smem;
     }
-    if (smem > 48 * 1024) QC_CUDA(ctx, cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    if (smem > 48 * 1024 && smem > prev_max)
+        QC_CUDA(ctx, cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     int occ = 1;
     QC_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, func, threads, (size_t)smem));
     if (occ < 1) occ = 1;
-    if (ctx->n_attr < 48) ctx->attr[ctx->n_attr++] = qc_attr_entry{key, smem, occ, threads};
+    if (t.n < 96) t.e[t.n++] = qc_attr_entry{key, smem, occ, threads};
     if (occ_out) *occ_out = occ;
     return QC_OK;
 }
