@@ -71,7 +71,8 @@ def test_segment_plan_offsets():
     arr, p = Fake().segment_plan(regs, 2, 2048, 2048, 1, 2048 * 2048, 2048)
     assert p.num_regions == 3 and p.max_region_w == 2048
     assert arr.out_offset[0] == 0 and arr.out_offset[1] == 2048 * 2048 and arr.out_offset[2] % 16 == 0
-    assert arr.band_offset.tolist() == [0, 64, 65] and p.total_bands == 66
+    band = 16                                                    # K4_BAND_ROWS
+    assert arr.band_offset.tolist() == [0, 2048 // band, 2048 // band + 2] and p.total_bands == 2048 // band + 3
     assert arr.blk_offset.tolist() == [0, 1024 * 1024, 1024 * 1024 + 17 * 9]
     assert p.total_bits_words == 2048 * 64 + 17 * 2 + 1
     with pytest.raises(ffi.QcGraftError):                                   # region outside the image
