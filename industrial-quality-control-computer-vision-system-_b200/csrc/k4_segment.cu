@@ -170,10 +170,28 @@ k4_hist(Img im, const qc_seg_region* __restrict__ regs, int R, int total_bands, 
                     for (int j = 0; j < 4; ++j) {
                         if (s0 + j * 32 + lane < nvec) {
                             const unsigned w4[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+                            if (big) {
+                                // 4 pixels per round: the four counter loads are issued together and duplicates
+                                // inside the group are merged in registers, so the smem latency is paid once
+                                // per 4 pixels instead of once per pixel (every duplicate stores the same total)
 #pragma unroll
-                            for (int k = 0; k < 16; ++k) {
-                                const unsigned g = (w4[k >> 2] >> (8 * (k & 3))) & 255u;
-                                if (big) tab[g << 5]++; else atomicAdd(&sh_small[g], 1u);
+                                for (int q = 0; q < 4; ++q) {
+                                    const unsigned g0 = w4[q] & 255u, g1 = (w4[q] >> 8) & 255u;
+                                    const unsigned g2 = (w4[q] >> 16) & 255u, g3 = w4[q] >> 24;
+                                    const unsigned c0 = tab[g0 << 5], c1 = tab[g1 << 5], c2 = tab[g2 << 5], c3 = tab[g3 << 5];
+                                    const unsigned e01 = g0 == g1, e02 = g0 == g2, e03 = g0 == g3;
+                                    const unsigned e12 = g1 == g2, e13 = g1 == g3, e23 = g2 == g3;
+                                    tab[g0 << 5] = (unsigned short)(c0 + 1 + e01 + e02 + e03);
+                                    tab[g1 << 5] = (unsigned short)(c1 + 1 + e01 + e12 + e13);
+                                    tab[g2 << 5] = (unsigned short)(c2 + 1 + e02 + e12 + e23);
+                                    tab[g3 << 5] = (unsigned short)(c3 + 1 + e03 + e13 + e23);
+                                }
+                            } else {
+#pragma unroll
+                                for (int k = 0; k < 16; ++k) {
+                                    const unsigned g = (w4[k >> 2] >> (8 * (k & 3))) & 255u;
+                                    atomicAdd(&sh_small[g], 1u);
+                                }
                             }
                         }
                     }
