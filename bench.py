@@ -363,7 +363,9 @@ def main():
     k1_ms = stage_ms.get("k1_preprocess")
     roofline = {"bound": "hbm", "kernel": "k1_pack_stream (K1 preprocess, most bytes of the step)",
                 "achieved": k1_bytes / k1_ms / 1e6 if k1_ms else None, "peak": peak, "unit": "GB/s",
-                "frac": (k1_bytes / k1_ms / 1e6 / peak) if k1_ms else None, "traffic": None,
+                "frac": (k1_bytes / k1_ms / 1e6 / peak) if k1_ms else None,
+                # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full (profiles/r01_c_k1_full.txt)
+                "traffic": 177480960,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": k1_bytes,
                 "ms_per_launch": k1_ms}
     d2h = int(last.det.nbytes + last.count.nbytes + 72 + (last.roi_probs.nbytes if last.roi_probs is not None else 0)
