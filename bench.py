@@ -162,7 +162,7 @@ def run_reference(args, rank):
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": f"{len(all_t)} frames of cfg2, sequential predict() loop, {total:.1f}s wall"},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def kernel_microbench(qc, peak, only=None):
@@ -256,7 +256,30 @@ def _mb_k4(qc, peak, rng, time_call, out):
                               "note": "10 launches; union-find merge/rank phases are L2/atomic-bound"}
 
 
+_REAL_STDOUT = None
+
+
+def _capture_stdout():
+    """Everything libraries print to fd 1 (NCCL's version banner, cuDNN notices) goes to stderr; the one JSON
+    line is written to the real stdout by emit()."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, data)
+    else:
+        os.write(1, data)
+
+
 def main():
+    _capture_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -398,7 +421,7 @@ def main():
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                                 "sample": f"{len(ts)} frames of cfg2 (+1 warm-up), sequential predict() loop, "
                                           f"{time.time() - t0:.1f}s wall, host cpu_count={os.cpu_count()}"}
-    print(json.dumps(line), flush=True)
+    emit(line)
     qdist.shutdown()
 
 
