@@ -93,14 +93,15 @@ k3_roi_align(const uint8_t* __restrict__ imgs, int n, int H, int W, long long im
 }
 
 
-constexpr int K3_BH = 8;         // output rows per CTA
+constexpr int K3_BH = 32;        // output rows per CTA (processed in sub-bands that fit the smem row budget)
 constexpr int K3_SR_MAX = 4;
 
-template <typename OutT>
+template <typename OutT, int SR>
 __global__ void __launch_bounds__(256)
 k3_roi_sep(const uint8_t* __restrict__ imgs, int n, int H, int W, long long img_stride, int row_stride,
-           const float* __restrict__ rois, int K, int PH, int PW, int sr, int aligned, int swap_rb,
+           const float* __restrict__ rois, int K, int PH, int PW, int /*sr_rt*/, int aligned, int swap_rb,
            const float* __restrict__ norm, OutT* __restrict__ dst, int rows_max) {
+    constexpr int sr = SR;
     extern __shared__ __align__(16) float k3sm[];
     float* Hs = k3sm;                                        // [rows_max][3][PW]
     int* xlo = reinterpret_cast<int*>(Hs + (size_t)rows_max * 3 * PW);   // [PW*sr]
@@ -325,19 +326,24 @@ extern "C" int qc_roi_align(qc_ctx* ctx, const uint8_t* imgs, int n, int h, int 
             if (tap_bytes + rows_max * per_row > budget) rows_max = (long long)((budget - tap_bytes) / per_row);
             const size_t smem = tap_bytes + (size_t)rows_max * per_row;
             dim3 grid((unsigned)((out_h + K3_BH - 1) / K3_BH), (unsigned)K);
-            if (out_dtype == QC_DT_BF16) {
-                if (int rc = qc_prepare(ctx, k3_roi_sep<__nv_bfloat16>, (int)smem, 256, nullptr)) return rc;
-                k3_roi_sep<__nv_bfloat16><<<grid, 256, smem, st>>>(imgs, n, h, w, img_stride, row_stride, rois, K, out_h,
-                                                                   out_w, sampling_ratio, aligned, swap_rb, norm,
-                                                                   (__nv_bfloat16*)dst, (int)rows_max);
-            } else if (out_dtype == QC_DT_F32) {
-                if (int rc = qc_prepare(ctx, k3_roi_sep<float>, (int)smem, 256, nullptr)) return rc;
-                k3_roi_sep<float><<<grid, 256, smem, st>>>(imgs, n, h, w, img_stride, row_stride, rois, K, out_h, out_w,
-                                                           sampling_ratio, aligned, swap_rb, norm, (float*)dst,
-                                                           (int)rows_max);
-            } else {
-                QC_FAIL(ctx, QC_ERR_INVALID, "qc_roi_align: bad out_dtype");
-            }
+#define K3_LAUNCH(T, S)                                                                                        \
+    do {                                                                                                       \
+        if (int rc = qc_prepare(ctx, k3_roi_sep<T, S>, (int)smem, 256, nullptr)) return rc;                    \
+        k3_roi_sep<T, S><<<grid, 256, smem, st>>>(imgs, n, h, w, img_stride, row_stride, rois, K, out_h, out_w, \
+                                                  sampling_ratio, aligned, swap_rb, norm, (T*)dst, (int)rows_max); \
+    } while (0)
+#define K3_LAUNCH_SR(T)                                  \
+    do {                                                 \
+        switch (sampling_ratio) {                        \
+            case 1: K3_LAUNCH(T, 1); break;              \
+            case 2: K3_LAUNCH(T, 2); break;              \
+            case 3: K3_LAUNCH(T, 3); break;              \
+            default: K3_LAUNCH(T, 4); break;             \
+        }                                                \
+    } while (0)
+            if (out_dtype == QC_DT_BF16) K3_LAUNCH_SR(__nv_bfloat16);
+            else if (out_dtype == QC_DT_F32) K3_LAUNCH_SR(float);
+            else QC_FAIL(ctx, QC_ERR_INVALID, "qc_roi_align: bad out_dtype");
             QC_LAUNCHED(ctx);
             return QC_OK;
         }
