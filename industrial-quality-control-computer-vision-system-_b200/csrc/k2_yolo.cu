@@ -71,17 +71,18 @@ constexpr int K2_NC_MAX = 16;    // classes held in registers by the vector path
 // maximum over c, candidate iff s > (float)conf.  sigmoid is monotone, so only logits within a hair of
 // the maximum logit can hold the maximum sigmoid (they get the exact first-max treatment), and an anchor
 // whose maximum logit is clearly below logit(conf) needs no sigmoid at all.
+template <int NCM>
 __device__ __forceinline__ bool anchor_candidate(const float* x, int nc, float conf, float logit_lo, float& best,
                                                  int& best_c) {
     float m = -INFINITY;
 #pragma unroll
-    for (int c = 0; c < K2_NC_MAX; ++c)
+    for (int c = 0; c < NCM; ++c)
         if (c < nc) m = fmaxf(m, x[c]);
     if (!(m >= logit_lo)) return false;                 // sigmoid(m) < conf with a wide margin (NaN -> false)
     const float near = m - 1e-3f * fmaxf(1.f, fabsf(m));
     best = -1.f; best_c = 0;
 #pragma unroll
-    for (int c = 0; c < K2_NC_MAX; ++c) {
+    for (int c = 0; c < NCM; ++c) {
         if (c < nc && x[c] >= near) {
             const float sg = sigmoid_f32(x[c]);
             if (sg > best) { best = sg; best_c = c; }   // first maximum wins (torch.max)
@@ -90,7 +91,7 @@ __device__ __forceinline__ bool anchor_candidate(const float* x, int nc, float c
     return best > conf;                                 // float32 compare, like torch
 }
 
-template <bool BF16>
+template <bool BF16, int NCM>
 __global__ void __launch_bounds__(256)
 k2_filter(LevelTable lt, int nc, int reg_max, float conf, float logit_lo, int cap, int vec_ok,
           unsigned long long* __restrict__ cand_key, int* __restrict__ cand_count) {
@@ -112,9 +113,9 @@ k2_filter(LevelTable lt, int nc, int reg_max, float conf, float logit_lo, int ca
             const void* p = lt.ptr[l];
             if (vec_ok) {
                 // 4 consecutive anchors x nc classes: one 128-bit (f32) / 64-bit (bf16) load per class plane
-                float x[4][K2_NC_MAX];
+                float x[4][NCM];
 #pragma unroll
-                for (int c = 0; c < K2_NC_MAX; ++c) {
+                for (int c = 0; c < NCM; ++c) {
                     if (c < nc) {
                         const long long e = base + (long long)(4 * reg_max + c) * cs;
                         if (BF16) {
@@ -128,7 +129,7 @@ k2_filter(LevelTable lt, int nc, int reg_max, float conf, float logit_lo, int ca
                     }
                 }
 #pragma unroll
-                for (int j = 0; j < 4; ++j) is_cand[j] = anchor_candidate(x[j], nc, conf, logit_lo, best[j], best_c[j]);
+                for (int j = 0; j < 4; ++j) is_cand[j] = anchor_candidate<NCM>(x[j], nc, conf, logit_lo, best[j], best_c[j]);
             } else {
                 float m = -INFINITY;
                 for (int c = 0; c < nc; ++c) m = fmaxf(m, load_elem<BF16>(p, base + (long long)(4 * reg_max + c) * cs));
@@ -287,17 +288,19 @@ struct NmsArgs {
 };
 
 __device__ void bitonic_sort_pairs(unsigned long long* keys, int* vals, int npow2) {
+    // one compare-exchange per thread per pass: thread t owns the pair (i, i | j), i = t with a zero bit spliced
+    // in at position log2(j)
+    const int half = npow2 >> 1;
     for (int k = 2; k <= npow2; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = threadIdx.x; i < npow2; i += blockDim.x) {
-                const int ixj = i ^ j;
-                if (ixj > i) {
-                    const unsigned long long a = keys[i], b = keys[ixj];
-                    const bool up = (i & k) == 0;
-                    if ((a > b) == up) {
-                        keys[i] = b; keys[ixj] = a;
-                        const int t = vals[i]; vals[i] = vals[ixj]; vals[ixj] = t;
-                    }
+            for (int t = threadIdx.x; t < half; t += blockDim.x) {
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const int ixj = i | j;
+                const unsigned long long a = keys[i], b = keys[ixj];
+                const bool up = (i & k) == 0;
+                if ((a > b) == up) {
+                    keys[i] = b; keys[ixj] = a;
+                    const int tv = vals[i]; vals[i] = vals[ixj]; vals[ixj] = tv;
                 }
             }
             __syncthreads();
@@ -311,10 +314,9 @@ k2_nms(NmsArgs args, const unsigned long long* __restrict__ cand_key, const floa
        float4* __restrict__ g_sorted, float* __restrict__ out_det, int* __restrict__ out_idx,
        int* __restrict__ out_count, int* __restrict__ out_ncand) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
-    __shared__ unsigned long long M[64];
     __shared__ unsigned long long cmask2[2][256];  // per class: which boxes of the current chunk have it
                                                    // (double-buffered by chunk parity: reset races with nothing)
-    __shared__ unsigned long long s_rem, s_keptmask;
+    __shared__ unsigned long long s_keptmask;
     __shared__ int s_kept_total;
 
     const int img = blockIdx.x;
@@ -337,6 +339,9 @@ k2_nms(NmsArgs args, const unsigned long long* __restrict__ cand_key, const floa
     unsigned long long* keys = in_smem ? reinterpret_cast<unsigned long long*>(dyn + (size_t)K2_SORT_SMEM_MAX * 16)
                                        : g_keys + (long long)img * 2 * cap;
     int* vals = in_smem ? reinterpret_cast<int*>(dyn + (size_t)K2_SORT_SMEM_MAX * 24) : g_vals + (long long)img * 2 * cap;
+    // per-box intra-chunk suppression rows; the global path reuses the upper half of the sort buffer (free after the sort)
+    unsigned long long* Mall = in_smem ? reinterpret_cast<unsigned long long*>(dyn + (size_t)K2_SORT_SMEM_MAX * 28)
+                                       : g_keys + (long long)img * 2 * cap + cap;
 
     // ---- sort (score desc, anchor asc) ---------------------------------------------------
     for (int i = tid; i < npow2; i += blockDim.x) {
@@ -364,36 +369,34 @@ k2_nms(NmsArgs args, const unsigned long long* __restrict__ cand_key, const floa
     // fast paths are valid for thresholds in (1e-3, 1): widen the decision band by 1e-4 on both sides
     const bool fast = thr > 1e-3 && thr < 1.0;
     const float thr_lo = (float)(thr - 1e-4), thr_hi = (float)(thr + 1e-4);
+    // The 64x64 upper-triangular suppression bitmask of every chunk depends only on the boxes, not on the
+    // running state: all of them are computed up front by the whole CTA, so the sequential loop below is just
+    // {resolve (warp 0) | barrier | apply kept boxes to later chunks | barrier}.
+    for (int i = warp; i < n; i += K2_NMS_THREADS / 32) {
+        const int cb = i & ~63, mm = min(64, n - cb), il = i - cb;
+        const float4 bi = sorted[i];
+        const int j0 = lane, j1 = lane + 32;
+        const bool b0 = j0 > il && j0 < mm && iou_gt(bi, sorted[cb + j0], thr, thr_lo, thr_hi, fast);
+        const bool b1 = j1 > il && j1 < mm && iou_gt(bi, sorted[cb + j1], thr, thr_lo, thr_hi, fast);
+        const unsigned lo = __ballot_sync(0xffffffffu, b0), hi = __ballot_sync(0xffffffffu, b1);
+        if (lane == 0) Mall[i] = ((unsigned long long)hi << 32) | lo;
+    }
+    __syncthreads();
     for (int c0 = 0; c0 < n; c0 += 64) {
         const int m = min(64, n - c0);
         unsigned long long* cmask = cmask2[(c0 >> 6) & 1];
-        // 64x64 upper-triangular suppression bitmask of the chunk
-        for (int i = warp; i < 64; i += K2_NMS_THREADS / 32) {
-            bool b0 = false, b1 = false;
-            if (i < m) {
-                const float4 bi = sorted[c0 + i];
-                const int j0 = lane, j1 = lane + 32;
-                if (j0 > i && j0 < m) b0 = iou_gt(bi, sorted[c0 + j0], thr, thr_lo, thr_hi, fast);
-                if (j1 > i && j1 < m) b1 = iou_gt(bi, sorted[c0 + j1], thr, thr_lo, thr_hi, fast);
-            }
-            const unsigned lo = __ballot_sync(0xffffffffu, b0), hi = __ballot_sync(0xffffffffu, b1);
-            if (lane == 0) M[i] = ((unsigned long long)hi << 32) | lo;
-        }
         if (args.class_prune && tid >= 64 && tid < 64 + m)
             atomicOr(&cmask[keys[c0 + tid - 64] & 0xFF], 1ull << (tid - 64));
-        if (warp == 0) {
-            const bool r0 = lane < m && removed[c0 + lane];
-            const bool r1 = lane + 32 < m && removed[c0 + lane + 32];
-            const unsigned lo = __ballot_sync(0xffffffffu, r0), hi = __ballot_sync(0xffffffffu, r1);
-            if (lane == 0) s_rem = ((unsigned long long)hi << 32) | lo;
-        }
-        __syncthreads();
         if (warp == 0) {
             // serial greedy pass over the chunk, executed redundantly by every lane of warp 0: lane l holds
             // mask rows l and l+32, row i is broadcast by shuffle (independent of the running state, so the
             // shuffles pipeline ahead of the dependent chain on `rem`)
-            const unsigned long long m_lo = M[lane], m_hi = M[lane + 32];
-            unsigned long long rem = s_rem, keptmask = 0;
+            const bool r0 = lane < m && removed[c0 + lane];
+            const bool r1 = lane + 32 < m && removed[c0 + lane + 32];
+            const unsigned rlo = __ballot_sync(0xffffffffu, r0), rhi = __ballot_sync(0xffffffffu, r1);
+            const unsigned long long m_lo = lane < m ? Mall[c0 + lane] : 0ull;
+            const unsigned long long m_hi = lane + 32 < m ? Mall[c0 + lane + 32] : 0ull;
+            unsigned long long rem = ((unsigned long long)rhi << 32) | rlo, keptmask = 0;
             int kt = s_kept_total;
 #pragma unroll
             for (int i = 0; i < 64; ++i) {
@@ -485,7 +488,7 @@ Ws carve(void* base, int n, int cap) {
 }
 
 size_t nms_smem_bytes(int max_det) {
-    return (size_t)K2_REMOVED_MAX + (size_t)((max_det + 3) & ~3) * 4 + 16 + (size_t)K2_SORT_SMEM_MAX * (16 + 8 + 4);
+    return (size_t)K2_REMOVED_MAX + (size_t)((max_det + 3) & ~3) * 4 + 16 + (size_t)K2_SORT_SMEM_MAX * (16 + 8 + 4 + 8);
 }
 
 int total_anchors(const qc_yolo_params* p) {
@@ -572,8 +575,13 @@ extern "C" int qc_yolo_decode_nms(qc_ctx* ctx, const void* const* levels, const 
     }
     const int per_cta = 256 * (vec_ok ? 4 : 1);
     dim3 gf((unsigned)std::min((A + per_cta - 1) / per_cta, 64), (unsigned)p->n);
-    if (bf) k2_filter<true><<<gf, 256, 0, st>>>(lt, p->nc, p->reg_max, conf, logit_lo, cap, vec_ok, w.key, w.count);
-    else k2_filter<false><<<gf, 256, 0, st>>>(lt, p->nc, p->reg_max, conf, logit_lo, cap, vec_ok, w.key, w.count);
+    if (p->nc <= 8) {
+        if (bf) k2_filter<true, 8><<<gf, 256, 0, st>>>(lt, p->nc, p->reg_max, conf, logit_lo, cap, vec_ok, w.key, w.count);
+        else k2_filter<false, 8><<<gf, 256, 0, st>>>(lt, p->nc, p->reg_max, conf, logit_lo, cap, vec_ok, w.key, w.count);
+    } else {
+        if (bf) k2_filter<true, K2_NC_MAX><<<gf, 256, 0, st>>>(lt, p->nc, p->reg_max, conf, logit_lo, cap, vec_ok, w.key, w.count);
+        else k2_filter<false, K2_NC_MAX><<<gf, 256, 0, st>>>(lt, p->nc, p->reg_max, conf, logit_lo, cap, vec_ok, w.key, w.count);
+    }
     QC_LAUNCHED(ctx);
 
     dim3 gd(32, (unsigned)p->n);
