@@ -166,6 +166,33 @@ def main():
     golden["spc"] = {"counts": [len(r["detections"]) for r in results], "vector": jsonable(vec),
                      "metrics": [{k: jsonable(v) for k, v in m.items() if k != "timestamp"} for m in mets]}
 
+    # ---- (d2) SPCAnalyzer.analyze over a 45-image series (control limits, run rules, Cp/Cpk)
+    an = spc_mod.SPCAnalyzer()
+    srng = np.random.default_rng(7)
+    series = []
+    snaps = {}
+    for t in range(45):
+        k = int(srng.integers(0, 9)) if t < 30 else t - 29          # the tail trends upwards -> rule 3
+        rr = np.zeros((k, 6), np.float32)
+        xy = srng.uniform(0, 500, (k, 2)); wh = srng.uniform(5, 400, (k, 2))
+        rr[:, :2] = xy; rr[:, 2:4] = xy + wh; rr[:, 4] = srng.uniform(0.7, 0.99, k); rr[:, 5] = srng.integers(0, 5, k)
+        series.append(rr.tolist())
+        fake_t = types.SimpleNamespace(boxes=types.SimpleNamespace(
+            xyxy=torch.from_numpy(rr[:, :4].copy()), conf=torch.from_numpy(rr[:, 4].copy()), cls=torch.from_numpy(rr[:, 5].copy())))
+        dets_t = det._parse_results(fake_t, (640, 640, 3))
+        comb_t = ens._combine_predictions({"detections": dets_t}, resnet_res, (640, 640, 3))
+        res_t = an.analyze({"detections": comb_t["detections"]})
+        if t in (8, 12, 29, 44):
+            snaps[str(t)] = jsonable({"metrics": {k2: v for k2, v in res_t["current_metrics"].items() if k2 != "timestamp"},
+                                      "control_limits": res_t["control_limits"],
+                                      "rule_violations": [v["rule"] for v in res_t["control_status"].get("rule_violations", [])],
+                                      "in_control": res_t["control_status"]["in_control"],
+                                      "n_violations": len(res_t["control_status"]["violations"]),
+                                      "n_warnings": len(res_t["control_status"]["warnings"]),
+                                      "capability": {k2: v for k2, v in res_t["process_capability"].items()
+                                                     if k2 in ("cp", "cpk", "cpm", "cpu", "cpl", "mean", "std", "insufficient_data")}})
+    golden["spc_series"] = {"rows": series, "snapshots": snaps}
+
     # ---- (e) library known-answers on seeded inputs (guards against cv2/torchvision drift on the GPU box)
     import torchvision
     img = rng.integers(0, 256, (45, 70, 3), dtype=np.uint8)
