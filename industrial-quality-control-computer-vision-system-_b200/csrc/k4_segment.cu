@@ -646,29 +646,28 @@ k4_border(const qc_seg_region* __restrict__ regs, int R, int total_bands, const 
         auto word = [&](int y, int wx) -> unsigned {
             return (wx < 0 || wx >= wpr) ? 0u : __ldg(B + (long long)y * wpr + wx);
         };
-        for (int wx = tid; wx < wpr; wx += K4_THREADS) {
+        for (int it = tid; it < wpr * 16; it += K4_THREADS) {            // one thread per block of the band's top row
+            const int wx = it >> 4, k = it & 15;
             const unsigned r0 = word(y0, wx);
-            if (!r0) continue;
+            const unsigned a = (r0 >> (2 * k)) & 1u, b = (r0 >> (2 * k + 1)) & 1u;
+            if (!(a | b)) continue;
             const unsigned u = word(y0 - 1, wx);
-            const unsigned ul = word(y0 - 1, wx - 1) >> 31, ur = word(y0 - 1, wx + 1) & 1u;
-            if (!(u | ul | ur)) continue;
-            const int base = rg.blk_offset + by * bw + wx * 16;
-            unsigned m = (r0 | (r0 >> 1)) & 0x55555555u;
-            while (m) {
-                const int k = (__ffs(m) - 1) >> 1;
-                m &= m - 1;
-                const unsigned a = (r0 >> (2 * k)) & 1u, b = (r0 >> (2 * k + 1)) & 1u;
-                const unsigned u0 = (u >> (2 * k)) & 1u, u1 = (u >> (2 * k + 1)) & 1u;
-                const int me = base + k, upb = me - bw;
-                if (u0 | u1) uf_union(parent, me, upb);
-                if (a && !u0) {
-                    const unsigned um = k > 0 ? (u >> (2 * k - 1)) & 1u : ul;
-                    if (um) uf_union(parent, me, upb - 1);
-                }
-                if (b && !u1) {
-                    const unsigned up2 = k < 15 ? (u >> (2 * k + 2)) & 1u : ur;
-                    if (up2) uf_union(parent, me, upb + 1);
-                }
+            const unsigned u0 = (u >> (2 * k)) & 1u, u1 = (u >> (2 * k + 1)) & 1u;
+            const int me = rg.blk_offset + by * bw + wx * 16 + k, upb = me - bw;
+            if (u0 | u1) {
+                // same redundancy rule as the band-local pass: skip when the left neighbour is in my run, is itself
+                // connected upwards and the two upper blocks are linked
+                bool skip = false;
+                if (k > 0 && a && ((r0 >> (2 * k - 1)) & 1u) && u0 && ((u >> (2 * k - 1)) & 1u)) skip = true;
+                if (!skip) uf_union(parent, me, upb);
+            }
+            if (a && !u0) {
+                const unsigned um = k > 0 ? (u >> (2 * k - 1)) & 1u : word(y0 - 1, wx - 1) >> 31;
+                if (um) uf_union(parent, me, upb - 1);
+            }
+            if (b && !u1) {
+                const unsigned up2 = k < 15 ? (u >> (2 * k + 2)) & 1u : word(y0 - 1, wx + 1) & 1u;
+                if (up2) uf_union(parent, me, upb + 1);
             }
         }
     }
@@ -702,34 +701,37 @@ __global__ void __launch_bounds__(K4_CHUNK)
 k4_compress(const qc_seg_region* __restrict__ regs, int R, int total_chunks, const int* __restrict__ g_chunk_off,
             const unsigned* __restrict__ bits, int* __restrict__ parent, int* __restrict__ chunk_count) {
     __shared__ int s_off[K4_LOC_MAX + 1];
-    __shared__ int s_cnt[K4_CHUNK / 32];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    __shared__ unsigned s_v[K4_CHUNK];          // r0|r1 of every cell of the chunk
+    __shared__ int s_base[K4_CHUNK];
+    __shared__ int s_cnt;
+    const int tid = threadIdx.x;
     const int* off = loc_load(s_off, g_chunk_off, R);
     for (int c = blockIdx.x; c < total_chunks; c += gridDim.x) {
         const int r = loc_find(off, R, c);
         const qc_seg_region rg = regs[r];
-        const Cell ce = load_cell(rg, bits, (c - rg.chunk_offset) * K4_CHUNK + tid);
+        __syncthreads();
+        {
+            const Cell ce = load_cell(rg, bits, (c - rg.chunk_offset) * K4_CHUNK + tid);
+            s_v[tid] = ce.r0 | ce.r1;
+            s_base[tid] = ce.base;
+            if (tid == 0) s_cnt = 0;
+        }
+        __syncthreads();
+        // one thread per block (16 per cell): the pointer chases of a cell run in parallel, not in sequence
         int cnt = 0;
-        unsigned m = ((ce.r0 | ce.r1) | ((ce.r0 | ce.r1) >> 1)) & 0x55555555u;
-        while (m) {
-            const int k = (__ffs(m) - 1) >> 1;
-            m &= m - 1;
-            const int g = ce.base + k;
+        for (int it = tid; it < K4_CHUNK * 16; it += K4_CHUNK) {
+            const int cell = it >> 4, k = it & 15;
+            if (!((s_v[cell] >> (2 * k)) & 3u)) continue;
+            const int g = s_base[cell] + k;
             const int rt = uf_find(parent, g);
             parent[g] = rt;
             cnt += (rt == g);
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        if ((tid & 31) == 0 && cnt) atomicAdd(&s_cnt, cnt);
         __syncthreads();
-        if (lane == 0) s_cnt[warp] = cnt;
-        __syncthreads();
-        if (tid == 0) {
-            int v = 0;
-#pragma unroll
-            for (int k = 0; k < K4_CHUNK / 32; ++k) v += s_cnt[k];
-            chunk_count[c] = v;
-        }
+        if (tid == 0) chunk_count[c] = s_cnt;
     }
 }
 
@@ -841,12 +843,18 @@ k4_stats(const qc_seg_region* __restrict__ regs, int R, int total_bands, const i
                     atomicAdd(s + 4, area);
                 }
             };
-#pragma unroll 4
+            // the two dependent loads per block (parent, then rank of the root) are issued for all 16 blocks first
+            int labs[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) labs[k] = ((v >> (2 * k)) & 3u) ? prow[k] : -1;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) labs[k] = labs[k] >= 0 ? rank[labs[k]] : 0;
+#pragma unroll
             for (int k = 0; k < 16; ++k) {
                 const unsigned a = (r0 >> (2 * k)) & 1u, b = (r0 >> (2 * k + 1)) & 1u;
                 const unsigned c = (r1 >> (2 * k)) & 1u, d = (r1 >> (2 * k + 1)) & 1u;
                 if (!(a | b | c | d)) continue;
-                const int lab = rank[prow[k]];
+                const int lab = labs[k];
                 prow[k] = lab;                      // parent -> final label, in place
                 if (lab != cur) { flush(); cur = lab; area = 0; mnx = INT_MAX; mxx = -1; mny = INT_MAX; mxy = -1; }
                 const int bx = wx * 16 + k;
