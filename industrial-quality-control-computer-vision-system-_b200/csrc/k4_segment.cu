@@ -128,9 +128,10 @@ __global__ void __launch_bounds__(K4_THREADS)
 k4_hist(Img im, const qc_seg_region* __restrict__ regs, int R, int total_bands, const int* __restrict__ g_band_off,
         unsigned* __restrict__ hist, uint8_t* __restrict__ gray_ws) {
     extern __shared__ __align__(16) unsigned char hsm[];
-    __shared__ unsigned sh_small[256];
+    __shared__ unsigned sh_small_all[K4_THREADS / 32][256];   // per-warp tables: 8x less same-address contention
     __shared__ int s_off[K4_LOC_MAX + 1];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    unsigned* sh_small = sh_small_all[warp];
     const int* off = loc_load(s_off, g_band_off, R);
     unsigned short* tab = reinterpret_cast<unsigned short*>(hsm) + warp * 8192 + lane;   // [bin*32]
     for (int t = blockIdx.x; t < total_bands; t += gridDim.x) {
@@ -144,7 +145,8 @@ k4_hist(Img im, const qc_seg_region* __restrict__ regs, int R, int total_bands, 
             uint4* z = reinterpret_cast<uint4*>(hsm) + warp * 1024;
             for (int i = lane; i < 1024; i += 32) z[i] = make_uint4(0, 0, 0, 0);
         } else {
-            sh_small[tid] = 0;
+#pragma unroll
+            for (int w = 0; w < K4_THREADS / 32; ++w) sh_small_all[w][tid] = 0;
         }
         __syncthreads();
         const uint8_t* ibase = im.data + (long long)rg.img * im.img_stride;
@@ -228,7 +230,8 @@ k4_hist(Img im, const qc_seg_region* __restrict__ regs, int R, int total_bands, 
                     }
                 }
             } else {
-                s = sh_small[bin];
+#pragma unroll
+                for (int w = 0; w < K4_THREADS / 32; ++w) s += sh_small_all[w][bin];
             }
             if (s) atomicAdd(&hist[(long long)r * 256 + bin], s);
         }
@@ -263,86 +266,78 @@ __device__ int otsu_serial_cv2(const unsigned* h, long long npix) {
     return max_val;
 }
 
+// one WARP per region (8 regions per CTA): lane l owns bins 8l..8l+7.  Small ROIs have sparse histograms whose
+// empty bins create exact ties, so the serial replay is common there; with a warp per region all replays of a
+// batch run concurrently instead of queueing behind one another.
 __global__ void __launch_bounds__(256)
 k4_otsu(const qc_seg_region* __restrict__ regs, int R, const unsigned* __restrict__ hist,
         int* __restrict__ cmp, int* __restrict__ out_thr) {
-    __shared__ unsigned long long sw[8], ss[8];
-    __shared__ double s_best[8];
-    __shared__ int s_bidx[8], s_close[8], s_flags[8];
-    __shared__ unsigned s_h[256];
-    __shared__ int s_result;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int r = blockIdx.x; r < R; r += gridDim.x) {
+    __shared__ unsigned s_h[8][256];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int r = blockIdx.x * 8 + warp; r < R; r += gridDim.x * 8) {
         const qc_seg_region rg = regs[r];
-        const unsigned h = hist[(long long)r * 256 + tid];
-        __syncthreads();
-        s_h[tid] = h;
-        unsigned long long w1 = h, s1 = (unsigned long long)h * tid;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const unsigned long long a = __shfl_up_sync(0xffffffffu, w1, o), b = __shfl_up_sync(0xffffffffu, s1, o);
-            if (lane >= o) { w1 += a; s1 += b; }
-        }
-        if (lane == 31) { sw[warp] = w1; ss[warp] = s1; }
-        __syncthreads();
-        unsigned long long N = 0, S = 0;
+        unsigned h[8];
+        unsigned long long w1 = 0, s1 = 0;
+        __syncwarp();
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-            if (k < warp) { w1 += sw[k]; s1 += ss[k]; }
-            N += sw[k]; S += ss[k];
+            h[k] = hist[(long long)r * 256 + lane * 8 + k];
+            s_h[warp][lane * 8 + k] = h[k];
+            w1 += h[k];
+            s1 += (unsigned long long)h[k] * (unsigned)(lane * 8 + k);
         }
-        double sig = -1.0;
-        int flags = 0;     // bit0: some bin not skipped, bit1: a bin sits on the skip boundary
-        if (N > 0) {
-            const double q1 = (double)w1 / (double)N, q2 = 1.0 - q1;
-            const double mn = fmin(q1, q2), mx = fmax(q1, q2);
-            const double eps = (double)FLT_EPSILON;
-            if (fabs(mn - eps) <= 1e-3 * eps || fabs(mx - (1.0 - eps)) <= 1e-3 * eps) flags |= 2;
-            if (!(mn < eps || mx > 1.0 - eps)) {
-                const double mu1 = (double)s1 / (double)w1;
-                const double mu2 = (double)(S - s1) / (double)(N - w1);
-                const double d = mu1 - mu2;
-                sig = q1 * q2 * d * d;
-                flags |= 1;
+        __syncwarp();
+        unsigned long long pw = w1, ps = s1;                   // inclusive prefix over lanes
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long a = __shfl_up_sync(0xffffffffu, pw, o), b = __shfl_up_sync(0xffffffffu, ps, o);
+            if (lane >= o) { pw += a; ps += b; }
+        }
+        const unsigned long long N = __shfl_sync(0xffffffffu, pw, 31), S = __shfl_sync(0xffffffffu, ps, 31);
+        unsigned long long cw = pw - w1, cs = ps - s1;        // totals of the bins before this lane's first bin
+        double best = -1.0;
+        int bidx = 0, flags = 0;       // bit0: some bin not skipped, bit1: a bin sits on the skip boundary
+        double sig[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            cw += h[k];
+            cs += (unsigned long long)h[k] * (unsigned)(lane * 8 + k);
+            sig[k] = -1.0;
+            if (N > 0) {
+                const double q1 = (double)cw / (double)N, q2 = 1.0 - q1;
+                const double mn = fmin(q1, q2), mx = fmax(q1, q2);
+                const double eps = (double)FLT_EPSILON;
+                if (fabs(mn - eps) <= 1e-3 * eps || fabs(mx - (1.0 - eps)) <= 1e-3 * eps) flags |= 2;
+                if (!(mn < eps || mx > 1.0 - eps)) {
+                    const double mu1 = (double)cs / (double)cw;
+                    const double mu2 = (double)(S - cs) / (double)(N - cw);
+                    const double d = mu1 - mu2;
+                    sig[k] = q1 * q2 * d * d;
+                    flags |= 1;
+                    if (sig[k] > best) { best = sig[k]; bidx = lane * 8 + k; }   // first maximum inside the lane
+                }
             }
         }
-        // first maximum over the 256 splits
-        double b = sig;
-        int bi = tid;
+        double b = best;
+        int bi = bidx;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             const double ob = __shfl_xor_sync(0xffffffffu, b, o);
             const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
             if (ob > b || (ob == b && oi < bi)) { b = ob; bi = oi; }
+            flags |= __shfl_xor_sync(0xffffffffu, flags, o);
         }
-        int fl = flags;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) fl |= __shfl_xor_sync(0xffffffffu, fl, o);
-        if (lane == 0) { s_best[warp] = b; s_bidx[warp] = bi; s_flags[warp] = fl; }
-        __syncthreads();
-        b = s_best[0]; bi = s_bidx[0]; fl = s_flags[0];
-#pragma unroll
-        for (int k = 1; k < 8; ++k) {
-            if (s_best[k] > b || (s_best[k] == b && s_bidx[k] < bi)) { b = s_best[k]; bi = s_bidx[k]; }
-            fl |= s_flags[k];
-        }
-        const bool close = sig >= 0.0 && tid != bi && sig >= b * (1.0 - 1e-9);
-        const unsigned cm = __ballot_sync(0xffffffffu, close);
-        if (lane == 0) s_close[warp] = __popc(cm);
-        __syncthreads();
         int nclose = 0;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) nclose += s_close[k];
-        if (tid == 0) {
-            int t;
-            if (!(fl & 1) && !(fl & 2)) t = 0;                                   // every split skipped
-            else if (b > 0.0 && nclose == 0 && !(fl & 2)) t = bi;                // decisive maximum
-            else t = otsu_serial_cv2(s_h, (long long)rg.w * rg.h);               // replay cv2 exactly
-            s_result = t;
-        }
-        __syncthreads();
-        if (tid == 0) {
-            const int max_val = s_result;
+        for (int k = 0; k < 8; ++k)
+            nclose += (sig[k] >= 0.0 && lane * 8 + k != bi && sig[k] >= b * (1.0 - 1e-9)) ? 1 : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) nclose += __shfl_xor_sync(0xffffffffu, nclose, o);
+        if (lane == 0) {
+            int max_val;
+            if (!(flags & 1) && !(flags & 2)) max_val = 0;                              // every split skipped
+            else if (b > 0.0 && nclose == 0 && !(flags & 2)) max_val = bi;              // decisive maximum
+            else max_val = otsu_serial_cv2(s_h[warp], (long long)rg.w * rg.h);          // replay cv2 exactly
             out_thr[r] = max_val;
             int lo, hi;
             if (rg.thr_scale == 1.0) {
@@ -1029,7 +1024,7 @@ extern "C" int qc_segment(qc_ctx* ctx, const uint8_t* imgs, const qc_seg_params*
         im, regions, R, p->total_bands, w.band_off, w.hist, w.gray);
     QC_LAUNCHED(ctx);
 
-    k4_otsu<<<std::min(R, sms * 4), 256, 0, st>>>(regions, R, w.hist, w.cmp, out_thr);
+    k4_otsu<<<std::min((R + 7) / 8, sms * 8), 256, 0, st>>>(regions, R, w.hist, w.cmp, out_thr);
     QC_LAUNCHED(ctx);
 
     const int halo = 4 * p->morph_iters;

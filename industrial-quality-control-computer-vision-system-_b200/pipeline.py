@@ -72,6 +72,7 @@ class InspectionPipeline:
         self.yolo_g = nets.GraphedNet(self.yolo, self.dev, net_dtype)
         self.resnet_g = nets.GraphedNet(self.resnet, self.dev, net_dtype)
         self.crop_chunks = (256, 64, 8)      # static ResNet batch sizes (largest first)
+        self.seg_max_comp = 1024             # first-pass stats rows per ROI (overflowing ROIs are redone)
         self.record = False          # bench.py: CUDA-event pairs around every stage
         self.events = {}
 
@@ -223,6 +224,12 @@ class InspectionPipeline:
                         h=roi_box[:, 3] - roi_box[:, 1], polarity=(~np.isin(cls, DARK_CLASSES)).astype(np.int32),
                         thr_scale=1.0, min_area=min_area)
             # K4 reads gray as the reference does AFTER inference/detector.py:234 swapped the channels
+            # stats rows are reserved per region; a first pass with a small reservation avoids initialising
+            # ~100 MB of rows that almost never exist, regions that overflow it are redone below
+            nblk = ((regs["w"].astype(np.int64) + 1) // 2) * ((regs["h"].astype(np.int64) + 1) // 2)
+            seg_cap = None if keep_seg_tensors else np.minimum(nblk + 1, self.seg_max_comp)
+            if seg_cap is not None:
+                regs["max_comp"] = seg_cap
             with self._timed("k4_segment"):
                 seg = qc.segment(frames, regs, morph_iters=morph_iters, swap_rb=True,
                                  want_mask=keep_seg_tensors, want_labels=keep_seg_tensors)
@@ -242,6 +249,13 @@ class InspectionPipeline:
             res.seg_area = seg["area"].cpu().numpy()
             res.seg_thr = seg["thr"].cpu().numpy()
             res.seg_ncomp = seg["ncomp"].cpu().numpy()
+            if seg_cap is not None:
+                over = np.nonzero(res.seg_ncomp > seg_cap)[0]
+                if len(over):       # components beyond the reservation escaped the min-area filter: redo exactly
+                    sub = {k: (v[over] if isinstance(v, np.ndarray) else v) for k, v in regs.items() if k != "max_comp"}
+                    seg2 = qc.segment(frames, sub, morph_iters=morph_iters, swap_rb=True, want_mask=False,
+                                      want_labels=False)
+                    res.seg_area[over] = seg2["area"].cpu().numpy()
             if keep_seg_tensors:
                 res.seg = seg
         return res
