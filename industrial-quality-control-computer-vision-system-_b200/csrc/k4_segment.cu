@@ -13,7 +13,8 @@
 //
 // Pipeline (all HBM/L2-bound integer work, no tensor cores):
 //   k4_init      zero histograms / area, sentinel-initialise stats rows
-//   k4_hist      [RGB->gray] + 256-bin histogram: 128-bit loads, per-warp lane-private u16 counters
+//   k4_gray      RGB -> gray (cv2 fixed point) into a region-packed copy (RGB input only)
+//   k4_hist      256-bin histogram: 128-bit loads, per-warp lane-private u16 counters, per-region flush
 //   k4_otsu      parallel Otsu from exact integer prefix sums; replays cv2's sequential float64
 //                recurrence only when the maximum is not decisive (ties / plateaus)
 //   k4_mask      threshold (128-bit loads, SIMD byte compares) -> bit-packed rows in smem -> close/open
@@ -118,125 +119,166 @@ __global__ void k4_init(const qc_seg_region* __restrict__ regs, int R, unsigned*
 }
 
 // ------------------------------------------------------------------------------------------
-// Histogram.  Warp per pixel row.  Big gray bands count into per-warp lane-private u16 tables
-// ([bin][lane], no atomics, no intra-warp address collisions); small bands (ROIs) use one
-// 256-bin table with shared-memory atomics so the zero/reduce overhead stays small.
-constexpr int K4_HIST_BIG_PX = 8192;
+// Histogram.  Warp per pixel row, 128-bit loads, per-warp lane-private u16 counters ([bin][lane]: no atomics, no
+// intra-warp address collisions; counter updates are issued four at a time with duplicates merged in
+// registers).  Every CTA owns a CONTIGUOUS range of bands and flushes its tables to the global histogram only
+// when the region changes (or before a counter could overflow), so the zero/reduce cost is paid per region,
+// not per band -- which matters for detection ROIs (thousands of tiny bands).
 constexpr int K4_HIST_SMEM = (K4_THREADS / 32) * 256 * 32 * 2;   // 128 KB
+constexpr int K4_HIST_FLUSH_PX = 4 << 20;                        // u16 safety: <= 16K pixels per lane between flushes
 
+// RGB -> gray (cv2 fixed point) into the region-packed gray workspace; plain high-occupancy kernel so the
+// histogram and threshold passes can stream contiguous bytes whatever the ROI alignment in the frame
 __global__ void __launch_bounds__(K4_THREADS)
-k4_hist(Img im, const qc_seg_region* __restrict__ regs, int R, int total_bands, const int* __restrict__ g_band_off,
-        unsigned* __restrict__ hist, uint8_t* __restrict__ gray_ws) {
-    extern __shared__ __align__(16) unsigned char hsm[];
-    __shared__ unsigned sh_small_all[K4_THREADS / 32][256];   // per-warp tables: 8x less same-address contention
+k4_gray(Img im, const qc_seg_region* __restrict__ regs, int R, int total_bands, const int* __restrict__ g_band_off,
+        uint8_t* __restrict__ gray_ws) {
     __shared__ int s_off[K4_LOC_MAX + 1];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    unsigned* sh_small = sh_small_all[warp];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int* off = loc_load(s_off, g_band_off, R);
-    unsigned short* tab = reinterpret_cast<unsigned short*>(hsm) + warp * 8192 + lane;   // [bin*32]
     for (int t = blockIdx.x; t < total_bands; t += gridDim.x) {
-        __syncthreads();                 // previous band's reduce is done with the tables
-        const int r = loc_find(off, R, t);
-        const qc_seg_region rg = regs[r];
+        const qc_seg_region rg = regs[loc_find(off, R, t)];
         const int y0 = (t - rg.band_offset) * K4_BAND_ROWS;
         const int y1 = min(y0 + K4_BAND_ROWS, rg.h);
-        const bool big = (y1 - y0) * rg.w > K4_HIST_BIG_PX;
-        if (big) {
-            uint4* z = reinterpret_cast<uint4*>(hsm) + warp * 1024;
-            for (int i = lane; i < 1024; i += 32) z[i] = make_uint4(0, 0, 0, 0);
-        } else {
-#pragma unroll
-            for (int w = 0; w < K4_THREADS / 32; ++w) sh_small_all[w][tid] = 0;
-        }
-        __syncthreads();
         const uint8_t* ibase = im.data + (long long)rg.img * im.img_stride;
         for (int y = y0 + warp; y < y1; y += K4_THREADS / 32) {
-            const uint8_t* p = ibase + (long long)(rg.y + y) * im.row_stride + (long long)rg.x * im.channels;
-            if (im.channels == 1) {
-                // aligned 16-byte body + scalar head/tail
-                const int head = min(rg.w, (int)((16 - (reinterpret_cast<uintptr_t>(p) & 15)) & 15));
-                const int nvec = (rg.w - head) >> 4;
-                for (int x = lane; x < head; x += 32) {
-                    const unsigned g = __ldg(p + x);
-                    if (big) tab[g << 5]++; else atomicAdd(&sh_small[g], 1u);
-                }
-                const uint4* pv = reinterpret_cast<const uint4*>(p + head);
-                for (int s0 = 0; s0 < nvec; s0 += 128) {
-                    uint4 v[4];
+            const uint8_t* p = ibase + (long long)(rg.y + y) * im.row_stride + (long long)rg.x * 3;
+            uint8_t* gq = gray_ws + rg.out_offset + (long long)y * rg.w;
+            // pixel h = (address mod 4) is the first one whose 3 bytes start 4-byte aligned; from there every group
+            // of 4 pixels is three aligned 32-bit words
+            const int head = min(rg.w, (int)(reinterpret_cast<uintptr_t>(p) & 3));
+            auto gray_of = [&](unsigned c0, unsigned c1, unsigned c2) -> uint8_t {
+                // cv2 RGB2GRAY fixed point: (R*9798 + G*19235 + B*3735 + 2^14) >> 15
+                return (uint8_t)((9798u * (im.swap_rb ? c2 : c0) + 19235u * c1 + 3735u * (im.swap_rb ? c0 : c2) + 16384u) >> 15);
+            };
+            if (lane < head) gq[lane] = gray_of(__ldg(p + 3 * lane), __ldg(p + 3 * lane + 1), __ldg(p + 3 * lane + 2));
+            const int ngrp = (rg.w - head) >> 2;
+            const unsigned* pw = reinterpret_cast<const unsigned*>(p + 3 * head);
+            for (int g0 = lane; g0 < ngrp; g0 += 64) {                 // two groups (24 bytes) in flight per lane
+                unsigned wv[2][3];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int sidx = s0 + j * 32 + lane;
-                        v[j] = sidx < nvec ? __ldg(pv + sidx) : make_uint4(0, 0, 0, 0);
+                for (int j = 0; j < 2; ++j) {
+                    const int g = g0 + 32 * j;
+                    if (g < ngrp) { wv[j][0] = __ldg(pw + 3 * g); wv[j][1] = __ldg(pw + 3 * g + 1); wv[j][2] = __ldg(pw + 3 * g + 2); }
+                }
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const int g = g0 + 32 * j;
+                    if (g < ngrp) {
+                        const unsigned a = wv[j][0], b = wv[j][1], c = wv[j][2];
+                        uint8_t* o = gq + head + 4 * g;
+                        o[0] = gray_of(a & 255u, (a >> 8) & 255u, (a >> 16) & 255u);
+                        o[1] = gray_of(a >> 24, b & 255u, (b >> 8) & 255u);
+                        o[2] = gray_of((b >> 16) & 255u, b >> 24, c & 255u);
+                        o[3] = gray_of((c >> 8) & 255u, (c >> 16) & 255u, c >> 24);
                     }
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        if (s0 + j * 32 + lane < nvec) {
-                            const unsigned w4[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
-                            if (big) {
-                                // 4 pixels per round: the four counter loads are issued together and duplicates
-                                // inside the group are merged in registers, so the smem latency is paid once
-                                // per 4 pixels instead of once per pixel (every duplicate stores the same total)
-#pragma unroll
-                                for (int q = 0; q < 4; ++q) {
-                                    const unsigned g0 = w4[q] & 255u, g1 = (w4[q] >> 8) & 255u;
-                                    const unsigned g2 = (w4[q] >> 16) & 255u, g3 = w4[q] >> 24;
-                                    const unsigned c0 = tab[g0 << 5], c1 = tab[g1 << 5], c2 = tab[g2 << 5], c3 = tab[g3 << 5];
-                                    const unsigned e01 = g0 == g1, e02 = g0 == g2, e03 = g0 == g3;
-                                    const unsigned e12 = g1 == g2, e13 = g1 == g3, e23 = g2 == g3;
-                                    tab[g0 << 5] = (unsigned short)(c0 + 1 + e01 + e02 + e03);
-                                    tab[g1 << 5] = (unsigned short)(c1 + 1 + e01 + e12 + e13);
-                                    tab[g2 << 5] = (unsigned short)(c2 + 1 + e02 + e12 + e23);
-                                    tab[g3 << 5] = (unsigned short)(c3 + 1 + e03 + e13 + e23);
-                                }
-                            } else {
-#pragma unroll
-                                for (int k = 0; k < 16; ++k) {
-                                    const unsigned g = (w4[k >> 2] >> (8 * (k & 3))) & 255u;
-                                    atomicAdd(&sh_small[g], 1u);
-                                }
-                            }
-                        }
-                    }
-                }
-                for (int x = head + nvec * 16 + lane; x < rg.w; x += 32) {
-                    const unsigned g = __ldg(p + x);
-                    if (big) tab[g << 5]++; else atomicAdd(&sh_small[g], 1u);
-                }
-            } else {
-                uint8_t* gq = gray_ws + rg.out_offset + (long long)y * rg.w;
-                for (int x = lane; x < rg.w; x += 32) {
-                    // cv2 RGB2GRAY fixed point: (R*9798 + G*19235 + B*3735 + 2^14) >> 15
-                    const unsigned c0 = __ldg(p + 3 * x), c1 = __ldg(p + 3 * x + 1), c2 = __ldg(p + 3 * x + 2);
-                    const unsigned g =
-                        (9798u * (im.swap_rb ? c2 : c0) + 19235u * c1 + 3735u * (im.swap_rb ? c0 : c2) + 16384u) >> 15;
-                    gq[x] = (uint8_t)g;
-                    if (big) tab[g << 5]++; else atomicAdd(&sh_small[g], 1u);
                 }
             }
-        }
-        __syncthreads();
-        {
-            const int bin = tid;            // K4_THREADS == 256 bins
-            unsigned s = 0;
-            if (big) {
-                const unsigned* t32 = reinterpret_cast<const unsigned*>(hsm);
-#pragma unroll
-                for (int w = 0; w < K4_THREADS / 32; ++w) {
-#pragma unroll
-                    for (int k = 0; k < 16; ++k) {
-                        // word j of row `bin`: rotate by bin>>1 so the 32 bins of a warp hit 32 banks
-                        const unsigned v = t32[w * 4096 + bin * 16 + ((k + (bin >> 1)) & 15)];
-                        s += (v & 0xFFFFu) + (v >> 16);
-                    }
-                }
-            } else {
-#pragma unroll
-                for (int w = 0; w < K4_THREADS / 32; ++w) s += sh_small_all[w][bin];
-            }
-            if (s) atomicAdd(&hist[(long long)r * 256 + bin], s);
+            for (int x = head + 4 * ngrp + lane; x < rg.w; x += 32)
+                gq[x] = gray_of(__ldg(p + 3 * x), __ldg(p + 3 * x + 1), __ldg(p + 3 * x + 2));
         }
     }
 }
+
+// one warp counts a contiguous byte span into its lane-private table: scalar head/tail, 128-bit body
+__device__ __forceinline__ void hist_span(const uint8_t* __restrict__ p, int len, unsigned short* tab, int lane) {
+    const int head = min(len, (int)((16 - (reinterpret_cast<uintptr_t>(p) & 15)) & 15));
+    const int nvec = (len - head) >> 4;
+    for (int x = lane; x < head; x += 32) tab[(unsigned)__ldg(p + x) << 5]++;
+    const uint4* pv = reinterpret_cast<const uint4*>(p + head);
+    for (int s0 = 0; s0 < nvec; s0 += 128) {
+        uint4 v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int sidx = s0 + j * 32 + lane;
+            v[j] = sidx < nvec ? __ldg(pv + sidx) : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (s0 + j * 32 + lane < nvec) {
+                const unsigned w4[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+                // 4 pixels per round: the four counter loads are issued together and duplicates inside the group
+                // are merged in registers (every duplicate stores the same total)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const unsigned g0 = w4[q] & 255u, g1 = (w4[q] >> 8) & 255u;
+                    const unsigned g2 = (w4[q] >> 16) & 255u, g3 = w4[q] >> 24;
+                    const unsigned c0 = tab[g0 << 5], c1 = tab[g1 << 5], c2 = tab[g2 << 5], c3 = tab[g3 << 5];
+                    const unsigned e01 = g0 == g1, e02 = g0 == g2, e03 = g0 == g3;
+                    const unsigned e12 = g1 == g2, e13 = g1 == g3, e23 = g2 == g3;
+                    tab[g0 << 5] = (unsigned short)(c0 + 1 + e01 + e02 + e03);
+                    tab[g1 << 5] = (unsigned short)(c1 + 1 + e01 + e12 + e13);
+                    tab[g2 << 5] = (unsigned short)(c2 + 1 + e02 + e12 + e23);
+                    tab[g3 << 5] = (unsigned short)(c3 + 1 + e03 + e13 + e23);
+                }
+            }
+        }
+    }
+    for (int x = head + nvec * 16 + lane; x < len; x += 32) tab[(unsigned)__ldg(p + x) << 5]++;
+}
+
+__global__ void __launch_bounds__(K4_THREADS)
+k4_hist(Img im, const qc_seg_region* __restrict__ regs, int R, int total_bands, const int* __restrict__ g_band_off,
+        unsigned* __restrict__ hist, const uint8_t* __restrict__ gray_ws) {
+    extern __shared__ __align__(16) unsigned char hsm[];
+    __shared__ int s_off[K4_LOC_MAX + 1];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int* off = loc_load(s_off, g_band_off, R);
+    unsigned short* tab = reinterpret_cast<unsigned short*>(hsm) + warp * 8192 + lane;   // [bin*32]
+    auto zero = [&]() {
+        uint4* z = reinterpret_cast<uint4*>(hsm) + warp * 1024;
+        for (int i = lane; i < 1024; i += 32) z[i] = make_uint4(0, 0, 0, 0);
+    };
+    auto flush = [&](int r) {          // all threads; tables -> global histogram of region r, then cleared
+        __syncthreads();
+        const int bin = tid;           // K4_THREADS == 256 bins
+        unsigned sum = 0;
+        const unsigned* t32 = reinterpret_cast<const unsigned*>(hsm);
+#pragma unroll
+        for (int w = 0; w < K4_THREADS / 32; ++w) {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                // word j of row `bin`: rotate by bin>>1 so the 32 bins of a warp hit 32 banks
+                const unsigned v = t32[w * 4096 + bin * 16 + ((k + (bin >> 1)) & 15)];
+                sum += (v & 0xFFFFu) + (v >> 16);
+            }
+        }
+        if (sum) atomicAdd(&hist[(long long)r * 256 + bin], sum);
+        __syncthreads();
+        zero();
+        __syncthreads();
+    };
+    // contiguous band range of this CTA
+    const int per = (total_bands + gridDim.x - 1) / gridDim.x;
+    const int t_begin = blockIdx.x * per, t_end = min(t_begin + per, total_bands);
+    if (t_begin >= t_end) return;
+    zero();
+    __syncthreads();
+    // consecutive bands of one region are processed as one group (rows / contiguous span shared by all 8 warps)
+    for (int t = t_begin; t < t_end;) {
+        const int r = loc_find(off, R, t);
+        const qc_seg_region rg = regs[r];
+        const int nb_region = (rg.h + K4_BAND_ROWS - 1) / K4_BAND_ROWS;
+        const int b0 = t - rg.band_offset;
+        // cap the group so a lane never counts more than 64K pixels between flushes
+        const int max_b = max(1, (int)(K4_HIST_FLUSH_PX / ((long long)K4_BAND_ROWS * rg.w)));
+        const int b1 = min(min(nb_region, b0 + (t_end - t)), b0 + max_b);
+        const int y0 = b0 * K4_BAND_ROWS, y1 = min(b1 * K4_BAND_ROWS, rg.h);
+        if (im.channels == 1) {
+            const uint8_t* ibase = im.data + (long long)rg.img * im.img_stride;
+            for (int y = y0 + warp; y < y1; y += K4_THREADS / 32)
+                hist_span(ibase + (long long)(rg.y + y) * im.row_stride + rg.x, rg.w, tab, lane);
+        } else {
+            // region-packed gray copy: the rows are one contiguous span, cut into 2 KB pieces for the 8 warps
+            const uint8_t* p = gray_ws + rg.out_offset + (long long)y0 * rg.w;
+            const long long len = (long long)(y1 - y0) * rg.w;
+            for (long long c0 = (long long)warp * 2048; c0 < len; c0 += (K4_THREADS / 32) * 2048)
+                hist_span(p + c0, (int)min(2048ll, len - c0), tab, lane);
+        }
+        flush(r);
+        t += b1 - b0;
+    }
+}
+
 
 // ------------------------------------------------------------------------------------------
 // Otsu threshold, bit-exact with cv2's getThreshVal_Otsu_8u.  cv2's recurrence is sequential in
@@ -1016,12 +1058,13 @@ extern "C" int qc_segment(qc_ctx* ctx, const uint8_t* imgs, const qc_seg_params*
         p->total_bands, p->total_chunks);
     QC_LAUNCHED(ctx);
 
-    // per-warp u16 histogram tables only when some band can exceed K4_HIST_BIG_PX pixels
-    const bool big_hist = (long long)p->max_region_w * K4_BAND_ROWS > K4_HIST_BIG_PX;
-    const int hist_smem = big_hist ? K4_HIST_SMEM : 0;
+    if (p->channels == 3) {
+        k4_gray<<<std::min(p->total_bands, sms * 8), K4_THREADS, 0, st>>>(im, regions, R, p->total_bands, w.band_off, w.gray);
+        QC_LAUNCHED(ctx);
+    }
     if (int rc = qc_prepare(ctx, k4_hist, K4_HIST_SMEM, K4_THREADS, nullptr)) return rc;
-    k4_hist<<<std::min(p->total_bands, big_hist ? sms : sms * 6), K4_THREADS, hist_smem, st>>>(
-        im, regions, R, p->total_bands, w.band_off, w.hist, w.gray);
+    k4_hist<<<std::min(p->total_bands, sms), K4_THREADS, K4_HIST_SMEM, st>>>(im, regions, R, p->total_bands, w.band_off,
+                                                                          w.hist, w.gray);
     QC_LAUNCHED(ctx);
 
     k4_otsu<<<std::min((R + 7) / 8, sms * 8), 256, 0, st>>>(regions, R, w.hist, w.cmp, out_thr);
