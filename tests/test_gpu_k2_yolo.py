@@ -173,3 +173,18 @@ def test_noncontiguous_concatenated_head(qc):
     for i in range(B):
         k = len(rdets[i])
         assert int(count[i]) == k and torch.equal(anchor[i, :k].cpu().long(), ridx[i])
+
+
+def test_cfg3_full_batch_32(qc):
+    """BASELINE cfg3 at its full size: 32 images x 1280^2 x >= 1000 candidates, every image index-exact."""
+    from qcgraft import synth
+    levels = synth.make_head(300, 32, 1280, 1280, 1200)
+    det, count = _compare_full(qc, levels, 1280, 1280)
+    assert int(count.min()) >= 100
+
+
+def test_cfg2_full_batch_64_bf16(qc):
+    """BASELINE cfg2 head shape (64 x 640^2, bf16 head as the bf16 net emits it)."""
+    from qcgraft import synth
+    levels = synth.make_head(301, 64, 640, 640, 30)
+    _compare_full(qc, levels, 640, 640, dtype=torch.bfloat16)

@@ -140,3 +140,25 @@ def test_idempotence_property(qc):
     pairs = torch.unique(torch.stack((l1[l1 > 0], l2[l1 > 0])), dim=1)
     assert torch.equal(pairs[1], torch.arange(1, pairs.shape[1] + 1, device=pairs.device, dtype=pairs.dtype))
     assert (pairs[0][1:] > pairs[0][:-1]).all()
+
+
+def test_cfg4_full_batch_16(qc):
+    """BASELINE cfg4 at its full size: 16 line-scan frames of 2048^2 in one call, all exact vs cv2."""
+    from qcgraft import synth
+    imgs = synth.make_linescans(600, 16)
+    _run_full_frames(qc, imgs, iters=1, min_area=20)
+
+
+def test_dense_noise_rois(qc):
+    """The pathological case of the bench: ROIs on a flat noisy surface (Otsu splits the noise, ~50% foreground)."""
+    rng = np.random.default_rng(77)
+    imgs = np.clip(rng.normal(150, 10, (2, 400, 600)), 0, 255).astype(np.uint8)
+    regs = []
+    for k in range(12):
+        w, h = int(rng.integers(17, 300)), int(rng.integers(17, 300))
+        regs.append(dict(img=k % 2, x=int(rng.integers(0, 600 - w)), y=int(rng.integers(0, 400 - h)), w=w, h=h,
+                         polarity=k % 2, min_area=20))
+    res = qc.segment(torch.from_numpy(imgs).cuda(), regs, morph_iters=1)
+    for i, r in enumerate(regs):
+        roi = np.ascontiguousarray(imgs[r["img"], r["y"]:r["y"] + r["h"], r["x"]:r["x"] + r["w"]])
+        _check_region(res, i, r, oseg.segment_k4(roi, r["polarity"], 1.0, 1, 20))
