@@ -162,9 +162,10 @@ class InspectionPipeline:
         return img.astype(np.int32), di.astype(np.int32), box[img, di]
 
     @torch.no_grad()
-    def run(self, frames: torch.Tensor, inject=None, head_override=None, include_segmentation: bool = True,
-            keep_seg_tensors: bool = False, morph_iters: int = 1, min_area: int = 20) -> BatchResult:
+    def run_async(self, frames: torch.Tensor, inject=None, head_override=None, include_segmentation: bool = True,
+                  keep_seg_tensors: bool = False, morph_iters: int = 1, min_area: int = 20) -> "PendingResult":
         qc = self.qc
+        seg_cap = regs = None
         n, h, w = frames.shape[:3]
         det_d, anchor_d, count_d, _ = self.detect(frames, inject, head_override)
         spc_d = qc.spc_stats(det_d, count_d)
@@ -235,27 +236,64 @@ class InspectionPipeline:
                                  want_mask=keep_seg_tensors, want_labels=keep_seg_tensors)
             self.last_seg_pixels = int(seg["params"].total_pixels)
 
-        # ---- final device->host reads -------------------------------------------------------------
-        res.spc = spc_d.cpu().numpy()
+        # ---- final device->host reads: asynchronous copies into pinned buffers, finalised by .result() ------
+        def stage(t):
+            hbuf = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            hbuf.copy_(t, non_blocking=True)
+            return hbuf
+        host = {"spc": stage(spc_d)}
         if probs is not None:
-            pr = probs.cpu().numpy()
-            o = 0
-            if self.classify_global:
-                res.global_probs = pr[:n]
-                o = n
-            if self.classify_rois and K:
-                res.roi_probs = pr[o:o + K]
+            host["probs"] = stage(probs)
         if seg is not None:
-            res.seg_area = seg["area"].cpu().numpy()
-            res.seg_thr = seg["thr"].cpu().numpy()
-            res.seg_ncomp = seg["ncomp"].cpu().numpy()
+            host["area"], host["thr"], host["ncomp"] = stage(seg["area"]), stage(seg["thr"]), stage(seg["ncomp"])
+        done = torch.cuda.Event()
+        done.record()
+        return PendingResult(self, res, frames, host, done, dict(K=K, n=n, seg=seg, seg_cap=seg_cap if seg is not None else None,
+                                                                 regs=regs if seg is not None else None,
+                                                                 morph_iters=morph_iters, keep=keep_seg_tensors))
+
+    def run(self, frames: torch.Tensor, **kw) -> BatchResult:
+        """Synchronous form: one batch in, host-side BatchResult out."""
+        return self.run_async(frames, **kw).result()
+
+
+class PendingResult:
+    """Handle of a batch whose result copies are still in flight; ``result()`` waits for them.  Letting the host
+    run ahead (submit batch i+1, then finalise batch i) keeps the GPU busy between steps."""
+
+    def __init__(self, pipe, res, frames, host, done, meta):
+        self.pipe, self.res, self.frames, self.host, self.done, self.meta = pipe, res, frames, host, done, meta
+        self._final = None
+
+    def result(self) -> BatchResult:
+        if self._final is not None:
+            return self._final
+        self.done.synchronize()
+        res, m, pipe = self.res, self.meta, self.pipe
+        n, K = m["n"], m["K"]
+        res.spc = self.host["spc"].numpy().copy()
+        if "probs" in self.host:
+            pr = self.host["probs"].numpy()
+            o = 0
+            if pipe.classify_global:
+                res.global_probs = pr[:n].copy()
+                o = n
+            if pipe.classify_rois and K:
+                res.roi_probs = pr[o:o + K].copy()
+        if m["seg"] is not None:
+            res.seg_area = self.host["area"].numpy().copy()
+            res.seg_thr = self.host["thr"].numpy().copy()
+            res.seg_ncomp = self.host["ncomp"].numpy().copy()
+            seg_cap, regs = m["seg_cap"], m["regs"]
             if seg_cap is not None:
                 over = np.nonzero(res.seg_ncomp > seg_cap)[0]
                 if len(over):       # components beyond the reservation escaped the min-area filter: redo exactly
                     sub = {k: (v[over] if isinstance(v, np.ndarray) else v) for k, v in regs.items() if k != "max_comp"}
-                    seg2 = qc.segment(frames, sub, morph_iters=morph_iters, swap_rb=True, want_mask=False,
-                                      want_labels=False)
+                    seg2 = pipe.qc.segment(self.frames, sub, morph_iters=m["morph_iters"], swap_rb=True,
+                                           want_mask=False, want_labels=False)
                     res.seg_area[over] = seg2["area"].cpu().numpy()
-            if keep_seg_tensors:
-                res.seg = seg
+            if m["keep"]:
+                res.seg = m["seg"]
+        self.frames = None
+        self._final = res
         return res
