@@ -188,6 +188,8 @@ def kernel_microbench(qc, peak, only=None):
         _mb_k2(qc, peak, rng, time_call, out)
     if want("k3"):
         _mb_k3(qc, peak, rng, time_call, out)
+    if want("k3b"):
+        _mb_k3b(qc, peak, rng, time_call, out)
     if want("k4"):
         _mb_k4(qc, peak, rng, time_call, out)
     return out
@@ -249,6 +251,18 @@ def _mb_k3(qc, peak, rng, time_call, out):
     med, best = time_call(lambda i: qc.roi_align(frames, rois, out=o3), 8)
     by = int(((r[:, 3] - r[:, 1]) * (r[:, 4] - r[:, 2]) * 3).sum()) + K * 3 * 224 * 224 * 2
     out["k3_roi_align_512rois"] = {"bytes": by, "ms": med, "gbs": by / med / 1e6, "frac": by / med / 1e6 / peak}
+
+
+def _mb_k3b(qc, peak, rng, time_call, out):
+    from qcgraft import synth
+    # K3b: 64 whole 640^2 frames -> 224^2 bf16 (PIL-exact antialiased resize + ToTensor + Normalize), rotating 3 batches
+    b = [torch.from_numpy(rng.integers(0, 256, (BATCH, IMGSZ, IMGSZ, 3), dtype=np.uint8)).cuda() for _ in range(3)]
+    o = torch.empty((BATCH, 3, 224, 224), dtype=torch.bfloat16, device="cuda")
+    for i in range(3):
+        qc.pil_resize(b[i], out=o)
+    med, best = time_call(lambda i: qc.pil_resize(b[i % 3], out=o), 9)
+    by = BATCH * (IMGSZ * IMGSZ * 3 + 3 * 224 * 224 * 2)
+    out["k3b_pil_resize_cfg2"] = {"bytes": by, "ms": med, "gbs": by / med / 1e6, "frac": by / med / 1e6 / peak}
 
 
 def _mb_k4(qc, peak, rng, time_call, out):

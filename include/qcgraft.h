@@ -145,6 +145,23 @@ int qc_roi_align(qc_ctx* ctx, const uint8_t* imgs, int n, int h, int w, int64_t 
  * out = (roi_align_value / div - mean) / std in float32, i.e. /255 then Normalize.
  * dst: [K,3,out_h,out_w] contiguous.                                                    */
 
+/* ---- K3b: whole-frame classifier input, PIL-exact ------------------------------
+ * Replaces models/resent_model.py:57-66,114-130: Image.fromarray -> transforms.Resize((224,224))
+ * (Pillow's antialiased BILINEAR resampler: 22-bit integer coefficients, horizontal then vertical
+ * pass, uint8 intermediates) -> ToTensor -> Normalize.  The resized bytes are bit-exact with
+ * Pillow; the float32 output is bit-exact with torchvision's transform (bf16: its RNE rounding).
+ * Tables depend only on the geometry: build them once on the host, keep one copy on the device.
+ *   qc_pil_resize_table_bytes   size of the int32 table for (src_h,src_w)->(dst_h,dst_w)
+ *   qc_pil_resize_make_tables   fills a HOST buffer of that size (Pillow's precompute_coeffs +
+ *                               normalize_coeffs_8bpc, float64)
+ *   qc_pil_resize               imgs: n images uint8 HWC (strides in bytes); dev_tables = device copy
+ *                               of host_tables; norm as for qc_roi_align; dst [n,3,dst_h,dst_w].   */
+size_t qc_pil_resize_table_bytes(int src_h, int src_w, int dst_h, int dst_w);
+int qc_pil_resize_make_tables(int src_h, int src_w, int dst_h, int dst_w, int32_t* host_tables);
+int qc_pil_resize(qc_ctx* ctx, const uint8_t* imgs, int n, int h, int w, int64_t img_stride,
+                  int32_t row_stride, const int32_t* dev_tables, const int32_t* host_tables,
+                  int swap_rb, const float* norm, int out_dtype, void* dst, void* stream);
+
 /* ---- K4: Otsu + 3x3 cross morphology + union-find CCL + stats ---------------
  * Replaces, per region: cv2.cvtColor(RGB2GRAY) inference/segmentation.py:66-69; the Otsu
  * threshold + polarity compare of :212-234; cv2.morphologyEx CLOSE/OPEN with the 3x3 cross

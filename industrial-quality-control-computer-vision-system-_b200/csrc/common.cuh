@@ -64,7 +64,8 @@ static inline int qc_prepare(qc_ctx* ctx, F func, int smem, int threads, int* oc
         }
         if (t.e[i].smem > prev_max) prev_max = t.e[i].smem;
     }
-    if (smem > 48 * 1024 && smem > prev_max)
+    // static + dynamic shared memory above 48 KB needs the opt-in; kernels here carry up to 8 KB of static tables
+    if (smem > 32 * 1024 && smem > prev_max)
         QC_CUDA(ctx, cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     int occ = 1;
     QC_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, func, threads, (size_t)smem));

@@ -465,24 +465,311 @@ k2_nms(NmsArgs args, const unsigned long long* __restrict__ cand_key, const floa
     }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Class-parallel NMS (the decode path, when the host has verified that boxes of different classes cannot
+// intersect after the +cls*max_wh offset): torchvision's greedy pass over the score-sorted list then factorises
+// into nc independent greedy passes, so one CTA takes one (image, class) -- nc times more CTAs in flight and
+// nc times shorter sequential chains than one CTA per image.  Each CTA: pick its class out of the image's
+// candidate list, bitonic sort, offset boxes (same float32 rounding as the reference), 64x64 chunk bitmasks,
+// greedy resolve, first max_det kept boxes -> per-class kept list in global memory.  The LAST class CTA of an
+// image to finish (ticket counter) merges the nc sorted kept lists by rank (keys are unique) and writes the
+// first max_det rows -- identical to x[keep][:max_det] of the single sorted pass.
+constexpr int K2C_THREADS = 512;
+constexpr int K2C_SMEM_N = 1024;         // candidates of one class sorted / held in shared memory
+
+__device__ __forceinline__ int lower_bound_cg(const unsigned long long* __restrict__ a, int n, unsigned long long k) {
+    int lo = 0, hi = n;                   // first index with a[idx] >= k  (== number of keys < k)
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldcg(a + mid) < k) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+// k-th smallest (1-based) of n unique 64-bit keys by MSB-first 8-bit radix select; all threads of the CTA call it
+// and get the same value.  Only used when an image holds more than max_nms candidates (the reference keeps the
+// max_nms best-scoring ones before NMS).
+__device__ unsigned long long kth_smallest_key(const unsigned long long* __restrict__ ck, int n, int k, int* s_hist,
+                                               unsigned long long* s_prefix, int* s_rem) {
+    if (threadIdx.x == 0) { *s_prefix = 0ull; *s_rem = k; }
+    for (int pass = 0; pass < 8; ++pass) {
+        const int shift = 56 - 8 * pass;
+        for (int i = threadIdx.x; i < 256; i += blockDim.x) s_hist[i] = 0;
+        __syncthreads();
+        const unsigned long long prefix = *s_prefix;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const unsigned long long key = ck[i];
+            if (pass == 0 || (key >> (shift + 8)) == (prefix >> (shift + 8))) atomicAdd(&s_hist[(int)((key >> shift) & 255ull)], 1);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int rem = *s_rem, b = 0;
+            while (b < 255 && rem > s_hist[b]) { rem -= s_hist[b]; ++b; }
+            *s_rem = rem;
+            *s_prefix = prefix | ((unsigned long long)b << shift);
+        }
+        __syncthreads();
+    }
+    return *s_prefix;
+}
+
+__global__ void __launch_bounds__(K2C_THREADS, 2)
+k2_nms_class(NmsArgs args, int nc, const unsigned long long* __restrict__ cand_key,
+             const float4* __restrict__ cand_box, const int* __restrict__ cand_count,
+             unsigned long long* __restrict__ g_keys, int* __restrict__ g_vals, float4* __restrict__ g_sorted,
+             unsigned long long* __restrict__ g_mall, unsigned long long* __restrict__ kept_key,
+             float4* __restrict__ kept_box, int* __restrict__ kept_count, int* __restrict__ ticket,
+             float* __restrict__ out_det, int* __restrict__ out_idx, int* __restrict__ out_count,
+             int* __restrict__ out_ncand) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    __shared__ int s_hist[256];              // candidates per class of this image
+    __shared__ float4 s_kb[64];              // kept boxes of the current chunk
+    __shared__ int s_fill;
+    __shared__ unsigned long long s_keptmask;
+    __shared__ int s_kept_total, s_ticket;
+
+    const int cls = blockIdx.x, img = blockIdx.y;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int cap = args.cap;
+    int ntot = cand_count[img];
+    if (ntot > cap) ntot = cap;
+    if (out_ncand && tid == 0 && cls == 0) out_ncand[img] = ntot;
+    const unsigned long long* ck = cand_key + (long long)img * cap;
+
+    // more than max_nms candidates: only the max_nms best keys (score desc, anchor asc) take part
+    unsigned long long key_max = ~0ull;
+    if (ntot > args.max_nms) key_max = kth_smallest_key(ck, ntot, args.max_nms, s_hist, &s_keptmask, &s_ticket);
+    // ---- class histogram of the image's candidates (every class CTA derives the same table) --------
+    __syncthreads();
+    for (int i = tid; i < 256; i += K2C_THREADS) s_hist[i] = 0;
+    if (tid == 0) { s_fill = 0; s_kept_total = 0; }
+    __syncthreads();
+    for (int i = tid; i < ntot; i += K2C_THREADS) {
+        const unsigned long long k = ck[i];
+        if (k <= key_max) atomicAdd(&s_hist[(int)(k & 0xFF)], 1);
+    }
+    __syncthreads();
+    int n = s_hist[cls];
+    int npow2 = 1;
+    while (npow2 < n) npow2 <<= 1;
+    const bool in_smem = npow2 <= K2C_SMEM_N;
+    // global fallback regions of this class: classes partition the candidates, so sum(npow2_c) <= 2*cap
+    long long koff = 0, boff = 0;
+    if (!in_smem) {
+        for (int c = 0; c < cls; ++c) {
+            const int m = s_hist[c];
+            int p2 = m ? 1 : 0;
+            while (p2 < m) p2 <<= 1;
+            koff += p2; boff += m;
+        }
+    }
+    // carve shared memory: removed bitmask | kept list | sorted boxes, keys, vals, chunk masks
+    unsigned* removed = reinterpret_cast<unsigned*>(smem_raw);                           // K2_REMOVED_MAX bits
+    int* kept_list = reinterpret_cast<int*>(smem_raw + K2_REMOVED_MAX / 8);              // max_det ints
+    uint8_t* dyn = smem_raw + K2_REMOVED_MAX / 8 + (size_t)((args.max_det + 3) & ~3) * 4;
+    dyn = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(dyn) + 15) & ~(uintptr_t)15);
+    float4* sorted = in_smem ? reinterpret_cast<float4*>(dyn) : g_sorted + (long long)img * cap + boff;
+    unsigned long long* keys = in_smem ? reinterpret_cast<unsigned long long*>(dyn + (size_t)K2C_SMEM_N * 16)
+                                       : g_keys + (long long)img * 2 * cap + koff;
+    int* vals = in_smem ? reinterpret_cast<int*>(dyn + (size_t)K2C_SMEM_N * 24) : g_vals + (long long)img * 2 * cap + koff;
+    unsigned long long* Mall = in_smem ? reinterpret_cast<unsigned long long*>(dyn + (size_t)K2C_SMEM_N * 28)
+                                       : g_mall + (long long)img * cap + boff;
+
+    // ---- gather this class (any order: the sort fixes it) ---------------------------------------------
+    if (n > 0) {
+        for (int i0 = 0; i0 < ntot; i0 += K2C_THREADS) {
+            const int i = i0 + tid;
+            unsigned long long k = 0;
+            const bool mine = i < ntot && (int)((k = ck[i]) & 0xFF) == cls && k <= key_max;
+            const unsigned bm = __ballot_sync(0xffffffffu, mine);
+            if (bm) {
+                int base = 0;
+                const int leader = __ffs(bm) - 1;
+                if (lane == leader) base = atomicAdd(&s_fill, __popc(bm));
+                base = __shfl_sync(0xffffffffu, base, leader);
+                if (mine) {
+                    const int slot = base + __popc(bm & ((1u << lane) - 1u));
+                    keys[slot] = k; vals[slot] = i;
+                }
+            }
+        }
+        for (int i = n + tid; i < npow2; i += K2C_THREADS) { keys[i] = ~0ull; vals[i] = 0; }
+        __syncthreads();
+        bitonic_sort_pairs(keys, vals, npow2);
+        if (n > K2_REMOVED_MAX) n = K2_REMOVED_MAX;  // (max_nms <= K2_REMOVED_MAX is checked on the host)
+        const float off = __fmul_rn((float)cls, args.max_wh);
+        for (int i = tid; i < n; i += K2C_THREADS) {
+            const float4 b = cand_box[(long long)img * cap + vals[i]];
+            sorted[i] = make_float4(__fadd_rn(b.x, off), __fadd_rn(b.y, off), __fadd_rn(b.z, off), __fadd_rn(b.w, off));
+        }
+        for (int i = tid; i < (n + 31) / 32 + 2; i += K2C_THREADS) removed[i] = 0u;
+        __syncthreads();
+
+        const double thr = args.iou_thres;
+        const bool fast = thr > 1e-3 && thr < 1.0;
+        const float thr_lo = (float)(thr - 1e-4), thr_hi = (float)(thr + 1e-4);
+        for (int i = warp; i < n; i += K2C_THREADS / 32) {
+            const int cb = i & ~63, mm = min(64, n - cb), il = i - cb;
+            const float4 bi = sorted[i];
+            const int j0 = lane, j1 = lane + 32;
+            const bool b0 = j0 > il && j0 < mm && iou_gt(bi, sorted[cb + j0], thr, thr_lo, thr_hi, fast);
+            const bool b1 = j1 > il && j1 < mm && iou_gt(bi, sorted[cb + j1], thr, thr_lo, thr_hi, fast);
+            const unsigned lo = __ballot_sync(0xffffffffu, b0), hi = __ballot_sync(0xffffffffu, b1);
+            if (lane == 0) Mall[i] = ((unsigned long long)hi << 32) | lo;
+        }
+        __syncthreads();
+        for (int c0 = 0; c0 < n; c0 += 64) {
+            const int m = min(64, n - c0);
+            if (warp == 0) {
+                const unsigned long long m_lo = lane < m ? Mall[c0 + lane] : 0ull;
+                const unsigned long long m_hi = lane + 32 < m ? Mall[c0 + lane + 32] : 0ull;
+                unsigned long long rem = ((unsigned long long)removed[(c0 >> 5) + 1] << 32) | removed[c0 >> 5], keptmask = 0;
+                int kt = s_kept_total;
+#pragma unroll
+                for (int i = 0; i < 64; ++i) {
+                    const unsigned long long mi = __shfl_sync(0xffffffffu, i < 32 ? m_lo : m_hi, i & 31);
+                    const bool k = !((rem >> i) & 1ull) && i < m && kt < args.max_det;
+                    keptmask |= (unsigned long long)k << i;
+                    rem |= k ? mi : 0ull;
+                    if (k && lane == 0) kept_list[kt] = c0 + i;
+                    kt += k;
+                }
+                __syncwarp();
+                if (lane == 0) { s_keptmask = keptmask; s_kept_total = kt; }
+            }
+            __syncthreads();
+            const unsigned long long keptmask = s_keptmask;
+            if (s_kept_total >= args.max_det) break;
+            const int nk = __popcll(keptmask);
+            if (nk && c0 + 64 < n) {
+                // the chunk's kept boxes, densely packed: the apply loop below reads them at warp-uniform
+                // addresses with no dependency between iterations
+                if (tid < 64 && ((keptmask >> tid) & 1ull))
+                    s_kb[__popcll(keptmask & ((1ull << tid) - 1ull))] = sorted[c0 + tid];
+                __syncthreads();
+                for (int j = c0 + 64 + tid; j < n; j += K2C_THREADS) {
+                    if ((removed[j >> 5] >> (j & 31)) & 1u) continue;
+                    const float4 bj = sorted[j];
+                    bool sup = false;
+                    for (int i = 0; i < nk; ++i) sup |= iou_gt(s_kb[i], bj, thr, thr_lo, thr_hi, fast);
+                    if (sup) atomicOr(&removed[j >> 5], 1u << (j & 31));
+                }
+            }
+            __syncthreads();
+        }
+        __syncthreads();
+    }
+
+    // ---- publish this class's kept list, take a ticket ------------------------------------------------
+    const int kt = s_kept_total;
+    const long long kbase = ((long long)img * nc + cls) * args.max_det;
+    for (int r = tid; r < kt; r += K2C_THREADS) {
+        const int pos = kept_list[r];
+        __stcg(kept_key + kbase + r, keys[pos]);
+        __stcg(kept_box + kbase + r, cand_box[(long long)img * cap + vals[pos]]);      // un-offset box
+    }
+    if (tid == 0) __stcg(kept_count + img * nc + cls, kt);
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_ticket = atomicAdd(&ticket[img], 1);
+    __syncthreads();
+    if (s_ticket != nc - 1) return;
+    __threadfence();
+
+    // ---- last CTA of the image: rank-merge the nc kept lists, scale_boxes epilogue ----------------------
+    int* s_cnt = s_hist;                                  // reuse: kept count per class
+    for (int c = tid; c < nc; c += K2C_THREADS) s_cnt[c] = __ldcg(kept_count + img * nc + c);
+    __syncthreads();
+    int total = 0;
+    for (int c = 0; c < nc; ++c) total += s_cnt[c];
+    const int nout = min(total, args.max_det);
+    if (tid == 0) { out_count[img] = nout; ticket[img] = 0; }
+    // the kept lists go to shared memory (the sort buffers are free now) so the binary searches chase
+    // shared-memory, not L2, latency; oversized (nc * max_det) tables are searched in global memory
+    unsigned long long* mk = reinterpret_cast<unsigned long long*>(dyn);
+    const bool merge_smem = (size_t)nc * args.max_det * 8 <= (size_t)K2C_SMEM_N * 36;
+    if (merge_smem) {
+        for (int e = tid; e < nc * args.max_det; e += K2C_THREADS) {
+            const int c = e / args.max_det, r = e - c * args.max_det;
+            if (r < s_cnt[c]) mk[e] = __ldcg(kept_key + (long long)img * nc * args.max_det + e);
+        }
+        __syncthreads();
+    }
+    for (int e = tid; e < nc * args.max_det; e += K2C_THREADS) {
+        const int c = e / args.max_det, r = e - c * args.max_det;
+        if (r >= s_cnt[c]) continue;
+        const long long eb = ((long long)img * nc + c) * args.max_det;
+        const unsigned long long key = merge_smem ? mk[e] : __ldcg(kept_key + eb + r);
+        int rank = r;
+        for (int c2 = 0; c2 < nc && rank < args.max_det; ++c2) {
+            if (c2 == c || s_cnt[c2] == 0) continue;
+            if (merge_smem) {
+                const unsigned long long* a = mk + c2 * args.max_det;
+                int lo = 0, hi = s_cnt[c2];
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (a[mid] < key) lo = mid + 1; else hi = mid;
+                }
+                rank += lo;
+            } else {
+                rank += lower_bound_cg(kept_key + ((long long)img * nc + c2) * args.max_det, s_cnt[c2], key);
+            }
+        }
+        if (rank >= args.max_det) continue;
+        float4 b = __ldcg(kept_box + eb + r);
+        if (args.scale_boxes) {
+            b.x = __fdiv_rn(__fsub_rn(b.x, args.pad_x), args.gain);
+            b.y = __fdiv_rn(__fsub_rn(b.y, args.pad_y), args.gain);
+            b.z = __fdiv_rn(__fsub_rn(b.z, args.pad_x), args.gain);
+            b.w = __fdiv_rn(__fsub_rn(b.w, args.pad_y), args.gain);
+            b.x = fminf(fmaxf(b.x, 0.f), args.orig_w);
+            b.y = fminf(fmaxf(b.y, 0.f), args.orig_h);
+            b.z = fminf(fmaxf(b.z, 0.f), args.orig_w);
+            b.w = fminf(fmaxf(b.w, 0.f), args.orig_h);
+        }
+        float* row = out_det + ((long long)img * args.max_det + rank) * 6;
+        row[0] = b.x; row[1] = b.y; row[2] = b.z; row[3] = b.w;
+        row[4] = ord_desc2f((uint32_t)(key >> 32));
+        row[5] = (float)(int)(key & 0xFF);
+        out_idx[(long long)img * args.max_det + rank] = (int)((key >> 8) & 0xFFFFFFu);
+    }
+    for (int r = nout + tid; r < args.max_det; r += K2C_THREADS) {
+        float* row = out_det + ((long long)img * args.max_det + r) * 6;
+        row[0] = row[1] = row[2] = row[3] = row[4] = row[5] = 0.f;
+        out_idx[(long long)img * args.max_det + r] = -1;
+    }
+}
+
+size_t nms_class_smem_bytes(int max_det) {
+    return (size_t)K2_REMOVED_MAX / 8 + (size_t)((max_det + 3) & ~3) * 4 + 16 + (size_t)K2C_SMEM_N * (16 + 8 + 4 + 8);
+}
+
 // workspace layout (all 256-B aligned):
-//   cand_count int[n] | cand_key u64[n*cap] | cand_box float4[n*cap] |
+//   cand_count int[n] + ticket int[n] (zeroed together) | cand_key u64[n*cap] | cand_box float4[n*cap] |
 //   g_keys u64[n*2cap] | g_vals int[n*2cap] | g_sorted float4[n*cap]      (global-sort fallback)
+//   g_mall u64[n*cap] | kept_key u64[n*nc*max_det] | kept_box float4[n*nc*max_det] | kept_count int[n*nc]   (per-class NMS)
 struct Ws {
-    int* count; unsigned long long* key; float4* box; unsigned long long* gkeys; int* gvals; float4* gsorted;
+    int* count; int* ticket; unsigned long long* key; float4* box; unsigned long long* gkeys; int* gvals; float4* gsorted;
+    unsigned long long* gmall; unsigned long long* kept_key; float4* kept_box; int* kept_count;
     size_t total;
 };
-Ws carve(void* base, int n, int cap) {
+Ws carve(void* base, int n, int cap, int nc = 0, int max_det = 0) {
     Ws w;
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = qc_align_up(off + bytes, 256); return o; };
     uint8_t* b = (uint8_t*)base;
-    w.count = (int*)(b + take((size_t)n * 4));
+    w.count = (int*)(b + take((size_t)n * 8));
+    w.ticket = w.count + n;
     w.key = (unsigned long long*)(b + take((size_t)n * cap * 8));
     w.box = (float4*)(b + take((size_t)n * cap * 16));
     w.gkeys = (unsigned long long*)(b + take((size_t)n * 2 * cap * 8));
     w.gvals = (int*)(b + take((size_t)n * 2 * cap * 4));
     w.gsorted = (float4*)(b + take((size_t)n * cap * 16));
+    w.gmall = (unsigned long long*)(b + take((size_t)n * cap * 8 * (nc > 0)));
+    w.kept_key = (unsigned long long*)(b + take((size_t)n * nc * max_det * 8));
+    w.kept_box = (float4*)(b + take((size_t)n * nc * max_det * 16));
+    w.kept_count = (int*)(b + take((size_t)n * nc * 4));
     w.total = off;
     return w;
 }
@@ -512,7 +799,7 @@ int launch_nms(qc_ctx* ctx, const NmsArgs& a, int n, const Ws& w, float* out_det
 
 extern "C" size_t qc_yolo_workspace_bytes(const qc_yolo_params* p) {
     if (!p || p->n <= 0 || p->num_levels <= 0 || p->num_levels > QC_MAX_LEVELS) return 0;
-    return carve(nullptr, p->n, total_anchors(p)).total;
+    return carve(nullptr, p->n, total_anchors(p), p->nc, p->max_det).total;
 }
 
 extern "C" size_t qc_nms_workspace_bytes(int n, int cap) {
@@ -550,10 +837,10 @@ extern "C" int qc_yolo_decode_nms(qc_ctx* ctx, const void* const* levels, const 
     lt.A = A;
     if (A >= (1 << 24)) QC_FAIL(ctx, QC_ERR_UNSUPPORTED, "too many anchors");
     const int cap = A;
-    Ws w = carve(workspace, p->n, cap);
+    Ws w = carve(workspace, p->n, cap, p->nc, p->max_det);
     if (!workspace || workspace_bytes < w.total) QC_FAIL(ctx, QC_ERR_WORKSPACE, "workspace %zu < %zu", workspace_bytes, w.total);
     cudaStream_t st = (cudaStream_t)stream;
-    QC_CUDA(ctx, cudaMemsetAsync(w.count, 0, (size_t)p->n * 4, st));
+    QC_CUDA(ctx, cudaMemsetAsync(w.count, 0, (size_t)p->n * 8, st));      // candidate counts + merge tickets
 
     const float conf = (float)p->conf_thres;
     // logit(conf) minus a wide margin: anchors whose best logit is below it cannot reach conf
@@ -606,6 +893,18 @@ extern "C" int qc_yolo_decode_nms(qc_ctx* ctx, const void* const* levels, const 
         smax = fmaxf(smax, p->level_stride[l]);
     }
     a.class_prune = (p->max_wh > span + 2.f * p->reg_max * smax + 2.f) ? 1 : 0;
+    if (a.class_prune && p->nc <= 256) {
+        // classes are independent: one CTA per (image, class), merged by the last CTA of each image
+        const size_t smem = nms_class_smem_bytes(a.max_det);
+        if ((int)smem + 4096 <= ctx->max_smem_optin) {
+            if (int rc = qc_prepare(ctx, k2_nms_class, (int)smem, K2C_THREADS, nullptr)) return rc;
+            k2_nms_class<<<dim3((unsigned)p->nc, (unsigned)p->n), K2C_THREADS, smem, st>>>(
+                a, p->nc, w.key, w.box, w.count, w.gkeys, w.gvals, w.gsorted, w.gmall, w.kept_key, w.kept_box,
+                w.kept_count, w.ticket, out_det, out_anchor, out_count, out_ncand);
+            QC_LAUNCHED(ctx);
+            return QC_OK;
+        }
+    }
     return launch_nms(ctx, a, p->n, w, out_det, out_anchor, out_count, out_ncand, st);
 }
 

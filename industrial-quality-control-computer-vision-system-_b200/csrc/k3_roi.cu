@@ -151,6 +151,8 @@ k3_roi_sep(const uint8_t* __restrict__ imgs, int n, int H, int W, long long img_
         else *reinterpret_cast<float*>(q) = v;
     };
 
+    // quad path: rows of Hs and of the output are 16-byte / (4 * sizeof(OutT))-byte aligned
+    const bool quad_ok = (PW & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0;
     // (1) x taps: sample ix of output column pw -> (xl, xh, hx, lx); invalid samples get zero weights
     for (int t = tid; t < PW * sr; t += blockDim.x) {
         const int pw = t / sr, ix = t - pw * sr;
@@ -264,6 +266,39 @@ k3_roi_sep(const uint8_t* __restrict__ imgs, int n, int H, int W, long long img_
             int oa[K3_SR_MAX], ob[K3_SR_MAX];
     #pragma unroll
             for (int iy = 0; iy < K3_SR_MAX; ++iy) { oa[iy] = yl[iy] * 3 * PW; ob[iy] = yh[iy] * 3 * PW; }
+            if (quad_ok) {
+                // 4 consecutive columns of one channel per lane: 128-bit shared-memory loads, one 64-bit (bf16) or
+                // 128-bit (f32) store
+                const int quads = PW >> 2;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    for (int q = lane; q < quads; q += 32) {
+                        const float* hc = Hs + c * PW + 4 * q;
+                        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                        for (int iy = 0; iy < K3_SR_MAX; ++iy) {
+                            if (iy < sr) {
+                                const float4 a = *reinterpret_cast<const float4*>(hc + oa[iy]);
+                                const float4 b = *reinterpret_cast<const float4*>(hc + ob[iy]);
+                                acc.x = __fmaf_rn(wyl[iy], a.x, __fmaf_rn(wyh[iy], b.x, acc.x));
+                                acc.y = __fmaf_rn(wyl[iy], a.y, __fmaf_rn(wyh[iy], b.y, acc.y));
+                                acc.z = __fmaf_rn(wyl[iy], a.z, __fmaf_rn(wyh[iy], b.z, acc.z));
+                                acc.w = __fmaf_rn(wyl[iy], a.w, __fmaf_rn(wyh[iy], b.w, acc.w));
+                            }
+                        }
+                        const float v0 = finish(acc.x, c), v1 = finish(acc.y, c), v2 = finish(acc.z, c), v3 = finish(acc.w, c);
+                        OutT* q4 = dst + ((long long)k * 3 + c) * total + ph * PW + 4 * q;
+                        if (sizeof(OutT) == 2) {
+                            const __nv_bfloat162 p0 = __floats2bfloat162_rn(v0, v1), p1 = __floats2bfloat162_rn(v2, v3);
+                            *reinterpret_cast<uint2*>(q4) = make_uint2(*reinterpret_cast<const unsigned*>(&p0),
+                                                                       *reinterpret_cast<const unsigned*>(&p1));
+                        } else {
+                            *reinterpret_cast<float4*>(q4) = make_float4(v0, v1, v2, v3);
+                        }
+                    }
+                }
+                continue;
+            }
             const bool vec2 = (PW & 1) == 0;                    // float2 loads need 8-byte alignment of every row
             for (int pp = lane; pp < pairs; pp += 32) {
                 const int pw = pp * 2;

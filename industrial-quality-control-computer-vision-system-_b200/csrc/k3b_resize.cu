@@ -1,0 +1,236 @@
+// k3b_resize.cu -- K3b: the whole-frame classifier input of the reference, bit-exact.
+//
+// models/resent_model.py:57-66,114-130 feeds ResNet-50 with
+//     PIL.Image.fromarray(rgb) -> transforms.Resize((224,224)) -> ToTensor() -> Normalize(mean,std)
+// transforms.Resize on a PIL image is Pillow's antialiased separable resampler (Image.resize BILINEAR):
+// float64 triangle coefficients normalised per output index, quantised to 22-bit integers, a horizontal pass
+// then a vertical pass, each accumulated in int32 from 2^21 and clipped to uint8.
+//
+//   qc_pil_resize_make_tables   host: Pillow's precompute_coeffs + normalize_coeffs_8bpc for both axes
+//   k3b_resize                  one CTA per (image, band of output rows): horizontal pass of the source rows the
+//                               band taps into a shared-memory uint8 tile, vertical pass from that tile, then
+//                               ToTensor + Normalize through a 256x3 table built with the reference's float32
+//                               ops (x/255, -mean, /std: IEEE divisions), bf16 (RNE) or f32 NCHW stores.
+// Integer work, HBM-bound: algorithmic bytes per image = h*w*3 (read once) + 3*out_h*out_w*sizeof(out).
+#include "common.cuh"
+#include <math.h>
+#include <algorithm>
+#include <vector>
+
+namespace {
+
+constexpr int K3B_THREADS = 256;
+constexpr int K3B_PREC = 32 - 8 - 2;          // Pillow PRECISION_BITS
+constexpr int K3B_HDR = 8;                    // table header ints
+
+// table layout (int32): [0]=src_h [1]=src_w [2]=dst_h [3]=dst_w [4]=ksize_x [5]=ksize_y [6]=band_rows [7]=max_src_rows
+//   bounds_x[dst_w][2] | kk_x[dst_w][ksize_x] | bounds_y[dst_h][2] | kk_y[dst_h][ksize_y]
+struct Tables {
+    int src_h, src_w, dst_h, dst_w, kx, ky, band_rows, max_src_rows;
+    size_t off_bx, off_kx, off_by, off_ky, total_ints;
+};
+
+int ksize_of(int in_size, int out_size) {
+    const double scale = (double)in_size / (double)out_size;
+    const double filterscale = scale < 1.0 ? 1.0 : scale;
+    return (int)ceil(filterscale) * 2 + 1;       // support = 1.0 * filterscale (bilinear)
+}
+
+Tables layout(int src_h, int src_w, int dst_h, int dst_w) {
+    Tables t;
+    t.src_h = src_h; t.src_w = src_w; t.dst_h = dst_h; t.dst_w = dst_w;
+    t.kx = ksize_of(src_w, dst_w);
+    t.ky = ksize_of(src_h, dst_h);
+    t.band_rows = 0; t.max_src_rows = 0;
+    size_t o = K3B_HDR;
+    t.off_bx = o; o += (size_t)dst_w * 2;
+    t.off_kx = o; o += (size_t)dst_w * t.kx;
+    t.off_by = o; o += (size_t)dst_h * 2;
+    t.off_ky = o; o += (size_t)dst_h * t.ky;
+    t.total_ints = o;
+    return t;
+}
+
+// Pillow Resample.c precompute_coeffs (bilinear filter, box = whole axis) + normalize_coeffs_8bpc
+void axis_coeffs(int in_size, int out_size, int ksize, int* bounds, int* kk) {
+    const double scale = (double)in_size / (double)out_size;
+    const double filterscale = scale < 1.0 ? 1.0 : scale;
+    const double support = 1.0 * filterscale;
+    const double ss = 1.0 / filterscale;
+    std::vector<double> w((size_t)ksize);
+    for (int xx = 0; xx < out_size; ++xx) {
+        const double center = (xx + 0.5) * scale;
+        int xmin = (int)(center - support + 0.5);
+        if (xmin < 0) xmin = 0;
+        int xmax = (int)(center + support + 0.5);
+        if (xmax > in_size) xmax = in_size;
+        xmax -= xmin;
+        double ww = 0.0;
+        for (int x = 0; x < xmax; ++x) {
+            double a = (x + xmin - center + 0.5) * ss;
+            if (a < 0.0) a = -a;
+            const double v = a < 1.0 ? 1.0 - a : 0.0;
+            w[x] = v;
+            ww += v;
+        }
+        for (int x = 0; x < ksize; ++x) {
+            double v = 0.0;
+            if (x < xmax) v = ww != 0.0 ? w[x] / ww : w[x];
+            kk[(size_t)xx * ksize + x] = v < 0 ? (int)(-0.5 + v * (1 << K3B_PREC)) : (int)(0.5 + v * (1 << K3B_PREC));
+        }
+        bounds[xx * 2] = xmin;
+        bounds[xx * 2 + 1] = xmax;
+    }
+}
+
+template <typename OutT>
+__global__ void __launch_bounds__(K3B_THREADS)
+k3b_resize(const uint8_t* __restrict__ imgs, long long img_stride, int row_stride, const int* __restrict__ tab,
+           int swap_rb, const float* __restrict__ norm, OutT* __restrict__ dst) {
+    extern __shared__ __align__(16) uint8_t k3b_sm[];
+    __shared__ float s_lut[3][256];
+    const int src_w = tab[1], dst_h = tab[2], dst_w = tab[3], kx = tab[4], ky = tab[5];
+    const int band_rows = tab[6], max_src_rows = tab[7];
+    const int* __restrict__ bx = tab + K3B_HDR;
+    const int* __restrict__ kkx = bx + dst_w * 2;
+    const int* __restrict__ by = kkx + dst_w * kx;
+    const int* __restrict__ kky = by + dst_h * 2;
+    const int tid = threadIdx.x;
+    const int img = blockIdx.y;
+    const int oy0 = blockIdx.x * band_rows, oy1 = min(oy0 + band_rows, dst_h);
+    const int pitch = (dst_w + 3) & ~3;                    // bytes per channel row of the tile
+    uint8_t* tile = k3b_sm;                                // [max_src_rows][3][pitch]
+
+    // ToTensor + Normalize per OUTPUT channel: ((float)v / div - mean) / std with the reference's float32 ops
+    for (int i = tid; i < 768; i += K3B_THREADS) {
+        const int c = i >> 8, v = i & 255;
+        s_lut[c][v] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)v, norm[c * 3 + 0]), norm[c * 3 + 1]), norm[c * 3 + 2]);
+    }
+    // source rows this band taps (bounds are monotone in the output index)
+    const int sy0 = by[oy0 * 2], sy1 = by[(oy1 - 1) * 2] + by[(oy1 - 1) * 2 + 1];
+    const int nsrc = min(sy1 - sy0, max_src_rows);
+    const uint8_t* ibase = imgs + (long long)img * img_stride;
+
+    // ---- horizontal pass: (source row, output column) -> 3 channel bytes of the tile -----------------
+    for (int it = tid; it < nsrc * dst_w; it += K3B_THREADS) {
+        const int rr = it / dst_w, ox = it - rr * dst_w;
+        const int x0 = bx[ox * 2], cnt = bx[ox * 2 + 1];
+        const uint8_t* p = ibase + (long long)(sy0 + rr) * row_stride + (long long)x0 * 3;
+        const int* k = kkx + ox * kx;
+        int a0 = 1 << (K3B_PREC - 1), a1 = a0, a2 = a0;
+        for (int x = 0; x < cnt; ++x) {
+            const int kv = __ldg(k + x);
+            a0 += (int)__ldg(p + 3 * x) * kv;
+            a1 += (int)__ldg(p + 3 * x + 1) * kv;
+            a2 += (int)__ldg(p + 3 * x + 2) * kv;
+        }
+        uint8_t* t = tile + (size_t)rr * 3 * pitch + ox;
+        t[0] = (uint8_t)min(max(a0 >> K3B_PREC, 0), 255);
+        t[pitch] = (uint8_t)min(max(a1 >> K3B_PREC, 0), 255);
+        t[2 * pitch] = (uint8_t)min(max(a2 >> K3B_PREC, 0), 255);
+    }
+    __syncthreads();
+
+    // ---- vertical pass + ToTensor + Normalize: 4 consecutive columns of one (row, channel) per thread -----
+    const int quads = pitch >> 2;
+    const int per_row = 3 * quads;
+    const long long plane = (long long)dst_h * dst_w;
+    const bool vec_ok = (dst_w & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0;
+    for (int it = tid; it < (oy1 - oy0) * per_row; it += K3B_THREADS) {
+        const int ry = it / per_row, rem = it - ry * per_row;
+        const int c = rem / quads, q = rem - c * quads;
+        const int oy = oy0 + ry;
+        const int y0 = by[oy * 2] - sy0, cnt = by[oy * 2 + 1];
+        const int* k = kky + oy * ky;
+        int a0 = 1 << (K3B_PREC - 1), a1 = a0, a2 = a0, a3 = a0;
+        const uint8_t* t = tile + (size_t)y0 * 3 * pitch + c * pitch + 4 * q;
+        for (int y = 0; y < cnt; ++y) {
+            const int kv = __ldg(k + y);
+            const unsigned v4 = *reinterpret_cast<const unsigned*>(t + (size_t)y * 3 * pitch);
+            a0 += (int)(v4 & 255u) * kv;
+            a1 += (int)((v4 >> 8) & 255u) * kv;
+            a2 += (int)((v4 >> 16) & 255u) * kv;
+            a3 += (int)(v4 >> 24) * kv;
+        }
+        const int oc = swap_rb ? 2 - c : c;                 // tile channel c is source byte c
+        const float* lut = s_lut[oc];
+        const float f0 = lut[min(max(a0 >> K3B_PREC, 0), 255)], f1 = lut[min(max(a1 >> K3B_PREC, 0), 255)];
+        const float f2 = lut[min(max(a2 >> K3B_PREC, 0), 255)], f3 = lut[min(max(a3 >> K3B_PREC, 0), 255)];
+        OutT* o = dst + ((long long)img * 3 + oc) * plane + (long long)oy * dst_w + 4 * q;
+        if (vec_ok) {
+            if (sizeof(OutT) == 2) {
+                const __nv_bfloat162 p0 = __floats2bfloat162_rn(f0, f1), p1 = __floats2bfloat162_rn(f2, f3);
+                *reinterpret_cast<uint2*>(o) = make_uint2(*reinterpret_cast<const unsigned*>(&p0),
+                                                          *reinterpret_cast<const unsigned*>(&p1));
+            } else {
+                *reinterpret_cast<float4*>(o) = make_float4(f0, f1, f2, f3);
+            }
+        } else {
+            const float f[4] = {f0, f1, f2, f3};
+            for (int j = 0; j < 4 && 4 * q + j < dst_w; ++j) {
+                if (sizeof(OutT) == 2) reinterpret_cast<uint16_t*>(o)[j] = qc_f2bf(f[j]);
+                else reinterpret_cast<float*>(o)[j] = f[j];
+            }
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" size_t qc_pil_resize_table_bytes(int src_h, int src_w, int dst_h, int dst_w) {
+    if (src_h <= 0 || src_w <= 0 || dst_h <= 0 || dst_w <= 0) return 0;
+    return layout(src_h, src_w, dst_h, dst_w).total_ints * sizeof(int32_t);
+}
+
+extern "C" int qc_pil_resize_make_tables(int src_h, int src_w, int dst_h, int dst_w, int32_t* host_tables) {
+    if (src_h <= 0 || src_w <= 0 || dst_h <= 0 || dst_w <= 0 || !host_tables) return QC_ERR_INVALID;
+    Tables t = layout(src_h, src_w, dst_h, dst_w);
+    axis_coeffs(src_w, dst_w, t.kx, host_tables + t.off_bx, host_tables + t.off_kx);
+    axis_coeffs(src_h, dst_h, t.ky, host_tables + t.off_by, host_tables + t.off_ky);
+    // output rows per CTA: as many as keep the uint8 tile of tapped source rows within ~64 KB (at least one)
+    const int* by = host_tables + t.off_by;
+    const int pitch = (dst_w + 3) & ~3;
+    const int budget_rows = std::max(1, (64 * 1024) / (3 * pitch));
+    int band = std::min(dst_h, 16), max_rows = 0;
+    for (;; --band) {
+        max_rows = 0;
+        for (int o0 = 0; o0 < dst_h; o0 += band) {
+            const int o1 = std::min(o0 + band, dst_h) - 1;
+            max_rows = std::max(max_rows, by[o1 * 2] + by[o1 * 2 + 1] - by[o0 * 2]);
+        }
+        if (max_rows <= budget_rows || band == 1) break;
+    }
+    host_tables[0] = src_h; host_tables[1] = src_w; host_tables[2] = dst_h; host_tables[3] = dst_w;
+    host_tables[4] = t.kx; host_tables[5] = t.ky; host_tables[6] = band; host_tables[7] = max_rows;
+    return QC_OK;
+}
+
+extern "C" int qc_pil_resize(qc_ctx* ctx, const uint8_t* imgs, int n, int h, int w, int64_t img_stride,
+                             int32_t row_stride, const int32_t* dev_tables, const int32_t* host_tables, int swap_rb,
+                             const float* norm, int out_dtype, void* dst, void* stream) {
+    if (!ctx) return QC_ERR_INVALID;
+    if (n == 0) return QC_OK;
+    if (!imgs || !dev_tables || !host_tables || !norm || !dst || n < 0 || h <= 0 || w <= 0 || row_stride < w * 3)
+        QC_FAIL(ctx, QC_ERR_INVALID, "qc_pil_resize: bad argument");
+    if (host_tables[0] != h || host_tables[1] != w) QC_FAIL(ctx, QC_ERR_INVALID, "qc_pil_resize: tables are for %dx%d", host_tables[0], host_tables[1]);
+    if (n > 65535) QC_FAIL(ctx, QC_ERR_UNSUPPORTED, "qc_pil_resize: n > 65535 (split the call)");
+    const int dst_h = host_tables[2], dst_w = host_tables[3], band = host_tables[6], max_rows = host_tables[7];
+    const int pitch = (dst_w + 3) & ~3;
+    const size_t smem = (size_t)max_rows * 3 * pitch;
+    if ((long long)smem + 4096 > ctx->max_smem_optin)
+        QC_FAIL(ctx, QC_ERR_UNSUPPORTED, "qc_pil_resize: %dx%d -> %dx%d needs %zu B of shared memory", h, w, dst_h, dst_w, smem);
+    cudaStream_t st = (cudaStream_t)stream;
+    dim3 grid((unsigned)((dst_h + band - 1) / band), (unsigned)n);
+    if (out_dtype == QC_DT_BF16) {
+        if (int rc = qc_prepare(ctx, k3b_resize<__nv_bfloat16>, (int)smem, K3B_THREADS, nullptr)) return rc;
+        k3b_resize<__nv_bfloat16><<<grid, K3B_THREADS, smem, st>>>(imgs, img_stride, row_stride, dev_tables, swap_rb, norm,
+                                                                   (__nv_bfloat16*)dst);
+    } else if (out_dtype == QC_DT_F32) {
+        if (int rc = qc_prepare(ctx, k3b_resize<float>, (int)smem, K3B_THREADS, nullptr)) return rc;
+        k3b_resize<float><<<grid, K3B_THREADS, smem, st>>>(imgs, img_stride, row_stride, dev_tables, swap_rb, norm, (float*)dst);
+    } else {
+        QC_FAIL(ctx, QC_ERR_INVALID, "qc_pil_resize: bad out_dtype");
+    }
+    QC_LAUNCHED(ctx);
+    return QC_OK;
+}

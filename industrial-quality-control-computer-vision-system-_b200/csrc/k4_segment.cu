@@ -36,7 +36,15 @@
 namespace {
 
 constexpr int K4_THREADS = 256;
-constexpr int K4_BAND_ROWS = 16;     // pixel rows per band (8 block rows)
+// Pixel rows per band, chosen per region so rows x words-per-row stays ~1024 (constant shared-memory footprint):
+// 16 rows for a 2048-px-wide frame, 96 rows for a 300-px ROI, the whole ROI for most detections -- the per-band
+// fixed costs (barriers, region lookup, flushes) are paid once per ~32K pixels whatever the region shape.
+constexpr int K4_BAND_RW = 1024;
+__host__ __device__ inline int k4_band_rows(int w) {
+    const int wpr = (w + 31) >> 5;
+    const int r = (K4_BAND_RW / wpr) & ~15;
+    return r < 16 ? 16 : (r > 512 ? 512 : r);
+}
 constexpr int K4_CHUNK = 256;        // word cells (16 blocks each) per ranking chunk
 
 struct SegWs {
@@ -137,8 +145,9 @@ k4_gray(Img im, const qc_seg_region* __restrict__ regs, int R, int total_bands, 
     const int* off = loc_load(s_off, g_band_off, R);
     for (int t = blockIdx.x; t < total_bands; t += gridDim.x) {
         const qc_seg_region rg = regs[loc_find(off, R, t)];
-        const int y0 = (t - rg.band_offset) * K4_BAND_ROWS;
-        const int y1 = min(y0 + K4_BAND_ROWS, rg.h);
+        const int BR = k4_band_rows(rg.w);
+        const int y0 = (t - rg.band_offset) * BR;
+        const int y1 = min(y0 + BR, rg.h);
         const uint8_t* ibase = im.data + (long long)rg.img * im.img_stride;
         for (int y = y0 + warp; y < y1; y += K4_THREADS / 32) {
             const uint8_t* p = ibase + (long long)(rg.y + y) * im.row_stride + (long long)rg.x * 3;
@@ -257,12 +266,13 @@ k4_hist(Img im, const qc_seg_region* __restrict__ regs, int R, int total_bands, 
     for (int t = t_begin; t < t_end;) {
         const int r = loc_find(off, R, t);
         const qc_seg_region rg = regs[r];
-        const int nb_region = (rg.h + K4_BAND_ROWS - 1) / K4_BAND_ROWS;
+        const int BR = k4_band_rows(rg.w);
+        const int nb_region = (rg.h + BR - 1) / BR;
         const int b0 = t - rg.band_offset;
         // cap the group so a lane never counts more than 64K pixels between flushes
-        const int max_b = max(1, (int)(K4_HIST_FLUSH_PX / ((long long)K4_BAND_ROWS * rg.w)));
+        const int max_b = max(1, (int)(K4_HIST_FLUSH_PX / ((long long)BR * rg.w)));
         const int b1 = min(min(nb_region, b0 + (t_end - t)), b0 + max_b);
-        const int y0 = b0 * K4_BAND_ROWS, y1 = min(b1 * K4_BAND_ROWS, rg.h);
+        const int y0 = b0 * BR, y1 = min(b1 * BR, rg.h);
         if (im.channels == 1) {
             const uint8_t* ibase = im.data + (long long)rg.img * im.img_stride;
             for (int y = y0 + warp; y < y1; y += K4_THREADS / 32)
@@ -286,26 +296,48 @@ k4_hist(Img im, const qc_seg_region* __restrict__ regs, int R, int total_bands, 
 // prefix sums.  If the best split beats every other by a relative 1e-9 (rounding in either
 // formulation is ~1e-13) its index IS cv2's answer; otherwise (plateaus of two-level images,
 // ties, bins on the FLT_EPSILON skip boundary) one thread replays cv2's exact recurrence.
-__device__ int otsu_serial_cv2(const unsigned* h, long long npix) {
+// Warp-cooperative replay of cv2's recurrence.  Only the (q1, mu1) chain is inherently sequential; lane 0 runs it
+// and parks the state of every bin in shared memory, then all lanes evaluate sigma for their 8 bins with cv2's
+// expression and the warp takes the first strict maximum (max_sigma starts at 0, updated on `>`).  The total mean
+// is a sum of exact integers below 2^53, so its summation order is irrelevant.
+__device__ int otsu_replay_cv2(const unsigned* h, long long npix, double mu_sum, double* s_q, double* s_m, int lane) {
     const double scale = __ddiv_rn(1.0, (double)npix);
-    double mu = 0.0;
-    for (int i = 0; i < 256; ++i) mu = __dadd_rn(mu, __dmul_rn((double)i, (double)h[i]));
-    mu = __dmul_rn(mu, scale);
-    double mu1 = 0.0, q1 = 0.0, max_sigma = 0.0;
-    int max_val = 0;
-    for (int i = 0; i < 256; ++i) {
-        const double p_i = __dmul_rn((double)h[i], scale);
-        mu1 = __dmul_rn(mu1, q1);
-        q1 = __dadd_rn(q1, p_i);
-        const double q2 = __dsub_rn(1.0, q1);
-        if (fmin(q1, q2) < (double)FLT_EPSILON || fmax(q1, q2) > 1.0 - (double)FLT_EPSILON) continue;
-        mu1 = __ddiv_rn(__dadd_rn(mu1, __dmul_rn((double)i, p_i)), q1);
+    const double mu = __dmul_rn(mu_sum, scale);
+    if (lane == 0) {
+        double mu1 = 0.0, q1 = 0.0;
+        for (int i = 0; i < 256; ++i) {
+            const double p_i = __dmul_rn((double)h[i], scale);
+            mu1 = __dmul_rn(mu1, q1);
+            q1 = __dadd_rn(q1, p_i);
+            const double q2 = __dsub_rn(1.0, q1);
+            const bool skip = fmin(q1, q2) < (double)FLT_EPSILON || fmax(q1, q2) > 1.0 - (double)FLT_EPSILON;
+            if (!skip) mu1 = __ddiv_rn(__dadd_rn(mu1, __dmul_rn((double)i, p_i)), q1);
+            s_q[i] = skip ? -1.0 : q1;
+            s_m[i] = mu1;
+        }
+    }
+    __syncwarp();
+    double best = 0.0;
+    int bidx = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int i = lane * 8 + k;
+        const double q1 = s_q[i];
+        if (q1 < 0.0) continue;
+        const double q2 = __dsub_rn(1.0, q1), mu1 = s_m[i];
         const double mu2 = __ddiv_rn(__dsub_rn(mu, __dmul_rn(q1, mu1)), q2);
         const double d = __dsub_rn(mu1, mu2);
         const double sigma = __dmul_rn(__dmul_rn(__dmul_rn(q1, q2), d), d);
-        if (sigma > max_sigma) { max_sigma = sigma; max_val = i; }
+        if (sigma > best) { best = sigma; bidx = i; }              // first maximum inside the lane
     }
-    return max_val;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+        if (ob > best || (ob == best && oi < bidx)) { best = ob; bidx = oi; }
+    }
+    __syncwarp();
+    return best > 0.0 ? bidx : 0;
 }
 
 // one WARP per region (8 regions per CTA): lane l owns bins 8l..8l+7.  Small ROIs have sparse histograms whose
@@ -315,6 +347,7 @@ __global__ void __launch_bounds__(256)
 k4_otsu(const qc_seg_region* __restrict__ regs, int R, const unsigned* __restrict__ hist,
         int* __restrict__ cmp, int* __restrict__ out_thr) {
     __shared__ unsigned s_h[8][256];
+    __shared__ double s_q[8][256], s_m[8][256];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int r = blockIdx.x * 8 + warp; r < R; r += gridDim.x * 8) {
         const qc_seg_region rg = regs[r];
@@ -375,11 +408,11 @@ k4_otsu(const qc_seg_region* __restrict__ regs, int R, const unsigned* __restric
             nclose += (sig[k] >= 0.0 && lane * 8 + k != bi && sig[k] >= b * (1.0 - 1e-9)) ? 1 : 0;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) nclose += __shfl_xor_sync(0xffffffffu, nclose, o);
+        int max_val;
+        if (!(flags & 1) && !(flags & 2)) max_val = 0;                              // every split skipped
+        else if (b > 0.0 && nclose == 0 && !(flags & 2)) max_val = bi;              // decisive maximum
+        else max_val = otsu_replay_cv2(s_h[warp], (long long)rg.w * rg.h, (double)S, s_q[warp], s_m[warp], lane);
         if (lane == 0) {
-            int max_val;
-            if (!(flags & 1) && !(flags & 2)) max_val = 0;                              // every split skipped
-            else if (b > 0.0 && nclose == 0 && !(flags & 2)) max_val = bi;              // decisive maximum
-            else max_val = otsu_serial_cv2(s_h[warp], (long long)rg.w * rg.h);          // replay cv2 exactly
             out_thr[r] = max_val;
             int lo, hi;
             if (rg.thr_scale == 1.0) {
@@ -436,8 +469,9 @@ k4_mask(Img im, const qc_seg_region* __restrict__ regs, int R, int total_bands,
         const int r = loc_find(off, R, t);
         const qc_seg_region rg = regs[r];
         const int wpr = wpr_of(rg);
-        const int y0 = (t - rg.band_offset) * K4_BAND_ROWS;
-        const int y1 = min(y0 + K4_BAND_ROWS, rg.h);
+        const int BR = k4_band_rows(rg.w);
+        const int y0 = (t - rg.band_offset) * BR;
+        const int y1 = min(y0 + BR, rg.h);
         const int row_lo = max(y0 - halo, 0), row_hi = min(y1 + halo, rg.h);
         const int nrows = row_hi - row_lo;
         const int lo = cmp[2 * r], hi = cmp[2 * r + 1];
@@ -536,7 +570,7 @@ k4_ccl_local(const qc_seg_region* __restrict__ regs, int R, int total_bands, con
     extern __shared__ __align__(16) unsigned sm[];
     unsigned* band_s = sm;                                         // [34][wpr+2], zero border
     int* lab = reinterpret_cast<int*>(sm + band_words);            // [16][wpr*16]
-    unsigned short* cell_list = reinterpret_cast<unsigned short*>(lab + lab_words);   // [16*wpr] (row<<11 | word)
+    unsigned short* cell_list = reinterpret_cast<unsigned short*>(lab + lab_words);   // (block row << 8 | word)
     __shared__ int s_off[K4_LOC_MAX + 1];
     __shared__ int s_ncell;
     const int tid = threadIdx.x;
@@ -545,12 +579,13 @@ k4_ccl_local(const qc_seg_region* __restrict__ regs, int R, int total_bands, con
         __syncthreads();                 // previous band is done with band_s/lab/cell_list
         const qc_seg_region rg = regs[loc_find(off, R, t)];
         const int wpr = wpr_of(rg), pw = wpr + 2;
-        const int y0 = (t - rg.band_offset) * K4_BAND_ROWS;
-        const int y1 = min(y0 + K4_BAND_ROWS, rg.h);
+        const int BR = k4_band_rows(rg.w);
+        const int y0 = (t - rg.band_offset) * BR;
+        const int y1 = min(y0 + BR, rg.h);
         const int brows = y1 - y0;
         {
             const unsigned* B = bits + rg.bits_offset + (long long)y0 * wpr;
-            for (int i = tid; i < (K4_BAND_ROWS + 2) * pw; i += K4_THREADS) {
+            for (int i = tid; i < (BR + 2) * pw; i += K4_THREADS) {
                 const int rr = i / pw - 1, wx = i - (rr + 1) * pw - 1;      // band row, word (both may be -1 / past the end)
                 band_s[i] = (rr >= 0 && rr < brows && wx >= 0 && wx < wpr) ? __ldg(B + rr * wpr + wx) : 0u;
             }
@@ -586,46 +621,61 @@ k4_ccl_local(const qc_seg_region* __restrict__ regs, int R, int total_bands, con
                 const int leader = __ffs(bm) - 1;
                 if ((tid & 31) == leader) basei = atomicAdd(&s_ncell, __popc(bm));
                 basei = __shfl_sync(0xffffffffu, basei, leader);
-                if (v) cell_list[basei + __popc(bm & ((1u << (tid & 31)) - 1u))] = (unsigned short)((byy << 11) | wx);
+                if (v) cell_list[basei + __popc(bm & ((1u << (tid & 31)) - 1u))] = (unsigned short)((byy << 8) | wx);
             }
         }
         __syncthreads();
         const int nne = s_ncell;
-        // (2) unions: one thread per block of every non-empty cell
-        for (int it = tid; it < nne * 16; it += K4_THREADS) {
-            const int ce = cell_list[it >> 4], k = it & 15;
-            const int byy = ce >> 11, wx = ce & 2047;
+        // (2) unions: one thread per non-empty cell, one union per (run, upper run) contact.  Everything is bit
+        // arithmetic on the cell's words in the "even-bit" domain (bit 2k <-> block k): FB = foreground blocks,
+        // LK = block k linked to block k-1, heads = FB & ~LK.  For a run, the top-row pixels m are dilated by
+        // one pixel and intersected with the row above (u): every maximal group of contacted upper blocks that
+        // are themselves linked belongs to one upper run and costs a single union.
+        for (int it = tid; it < nne; it += K4_THREADS) {
+            const int ce = cell_list[it];
+            const int byy = ce >> 8, wx = ce & 255;
             const unsigned r0 = rowword(2 * byy, wx), r1 = rowword(2 * byy + 1, wx);
             const unsigned v = r0 | r1;
-            if (!((v >> (2 * k)) & 3u)) continue;
-            const int me = byy * bwp + wx * 16 + k;
-            if (k == 0 && (v & 1u)) {                                    // run continues from the previous word
-                const unsigned vl = (rowword(2 * byy, wx - 1) | rowword(2 * byy + 1, wx - 1)) >> 31;
-                if (vl) suf_union(lab, me, me - 1);
+            const unsigned FB = (v | (v >> 1)) & 0x55555555u;
+            const unsigned LK = v & (v << 1) & 0x55555555u;
+            unsigned HB = FB & ~LK;
+            const int base = byy * bwp + wx * 16;
+            unsigned u = 0, ULK = 0, uL = 0, uR = 0, vuL = 0, vuR = 0, vu = 0;
+            if (byy > 0) {                                               // the band above is stitched by k4_border
+                u = rowword(2 * byy - 1, wx);
+                vu = rowword(2 * byy - 2, wx) | u;
+                ULK = vu & (vu << 1) & 0x55555555u;
+                uL = rowword(2 * byy - 1, wx - 1) >> 31;
+                uR = rowword(2 * byy - 1, wx + 1) & 1u;
+                vuL = (rowword(2 * byy - 2, wx - 1) | rowword(2 * byy - 1, wx - 1)) >> 31;
+                vuR = (rowword(2 * byy - 2, wx + 1) | rowword(2 * byy - 1, wx + 1)) & 1u;
             }
-            if (byy == 0) continue;                                      // the band above is stitched by k4_border
-            const unsigned a = (r0 >> (2 * k)) & 1u, b = (r0 >> (2 * k + 1)) & 1u;
-            if (!(a | b)) continue;
-            const unsigned u = rowword(2 * byy - 1, wx);
-            const unsigned u0 = (u >> (2 * k)) & 1u, u1 = (u >> (2 * k + 1)) & 1u;
-            if (u0 | u1) {
-                // redundant when block k-1 is in my run (pre-linked), is itself connected upwards, and the two upper
-                // blocks are linked (columns 2k-1 and 2k of the upper row both set): connectivity follows by induction
-                bool skip = false;
-                if (k > 0 && ((v >> (2 * k)) & 1u) && ((v >> (2 * k - 1)) & 1u) && u0 && ((u >> (2 * k - 1)) & 1u)) {
-                    const unsigned pa = (r0 >> (2 * k - 2)) & 3u, pu = (u >> (2 * k - 2)) & 3u;
-                    skip = pa && pu;
+            while (HB) {
+                const int b0 = __ffs(HB) - 1;                            // even bit of the run's first block
+                HB &= HB - 1;
+                const unsigned below_next = HB ? ((HB & (0u - HB)) - 1u) : 0xFFFFFFFFu;
+                const unsigned RB = FB & below_next & ~((1u << b0) - 1u);    // blocks of this run
+                const int head = base + (b0 >> 1);
+                if (b0 == 0 && (v & 1u)) {                               // run continues from the previous word
+                    const unsigned vl = (rowword(2 * byy, wx - 1) | rowword(2 * byy + 1, wx - 1)) >> 31;
+                    if (vl) suf_union(lab, head, head - 1);
                 }
-                if (!skip) suf_union(lab, me, me - bwp);
-            }
-            // up-left / up-right only when not already implied through the upper block
-            if (a && !u0) {
-                const unsigned um = k > 0 ? (u >> (2 * k - 1)) & 1u : rowword(2 * byy - 1, wx - 1) >> 31;
-                if (um) suf_union(lab, me, me - bwp - 1);
-            }
-            if (b && !u1) {
-                const unsigned up2 = k < 15 ? (u >> (2 * k + 2)) & 1u : rowword(2 * byy - 1, wx + 1) & 1u;
-                if (up2) suf_union(lab, me, me - bwp + 1);
+                if (byy == 0) continue;
+                const unsigned m = r0 & (RB * 3u);                       // top-row pixels of the run
+                if (!m) continue;
+                const unsigned c = (m | (m << 1) | (m >> 1)) & u;
+                const unsigned CB = (c | (c >> 1)) & 0x55555555u;       // contacted upper blocks
+                unsigned CN = CB & ~((CB << 2) & ULK);                   // first block of every linked group
+                const int upb = base - bwp;
+                while (CN) {
+                    const int kk = (__ffs(CN) - 1) >> 1;
+                    CN &= CN - 1;
+                    suf_union(lab, head, upb + kk);
+                }
+                // contacts in the neighbouring words (pixel -1 / pixel 32 of the row above), unless the upper block
+                // next to them is contacted too and linked to them
+                if ((m & 1u) && uL && !((CB & 1u) && (vu & 1u) && vuL)) suf_union(lab, head, upb - 1);
+                if ((m >> 31) && uR && !((CB >> 30) && (vu >> 31) && vuR)) suf_union(lab, head, upb + 16);
             }
         }
         __syncthreads();
@@ -633,7 +683,7 @@ k4_ccl_local(const qc_seg_region* __restrict__ regs, int R, int total_bands, con
         const float inv_bwp = 1.0f / (float)bwp;
         for (int it = tid; it < nne * 16; it += K4_THREADS) {
             const int ce = cell_list[it >> 4], k = it & 15;
-            const int byy = ce >> 11, wx = ce & 2047;
+            const int byy = ce >> 8, wx = ce & 255;
             const unsigned v = rowword(2 * byy, wx) | rowword(2 * byy + 1, wx);
             if (!((v >> (2 * k)) & 3u)) continue;
             const int rt = suf_find(lab, byy * bwp + wx * 16 + k);
@@ -675,7 +725,7 @@ k4_border(const qc_seg_region* __restrict__ regs, int R, int total_bands, const 
     const int* off = loc_load(s_off, g_band_off, R);
     for (int t = blockIdx.x; t < total_bands; t += gridDim.x) {
         const qc_seg_region rg = regs[loc_find(off, R, t)];
-        const int y0 = (t - rg.band_offset) * K4_BAND_ROWS;
+        const int y0 = (t - rg.band_offset) * k4_band_rows(rg.w);
         if (y0 == 0) continue;
         const int wpr = wpr_of(rg), bw = bw_of(rg);
         const int by = y0 >> 1;
@@ -860,8 +910,9 @@ k4_stats(const qc_seg_region* __restrict__ regs, int R, int total_bands, const i
     for (int t = blockIdx.x; t < total_bands; t += gridDim.x) {
         const qc_seg_region rg = regs[loc_find(off, R, t)];
         const int wpr = wpr_of(rg), bw = bw_of(rg);
-        const int y0 = (t - rg.band_offset) * K4_BAND_ROWS;
-        const int y1 = min(y0 + K4_BAND_ROWS, rg.h);
+        const int BR = k4_band_rows(rg.w);
+        const int y0 = (t - rg.band_offset) * BR;
+        const int y1 = min(y0 + BR, rg.h);
         const int by0 = y0 >> 1, by1 = (y1 + 1) >> 1;
         const unsigned* B = bits + rg.bits_offset;
         for (int ci = tid; ci < (by1 - by0) * wpr; ci += K4_THREADS) {
@@ -921,8 +972,9 @@ k4_final(const qc_seg_region* __restrict__ regs, int R, int total_bands, const i
         const int s_r = loc_find(off, R, t);
         const qc_seg_region rg = regs[s_r];
         const int wpr = wpr_of(rg), bw = bw_of(rg);
-        const int y0 = (t - rg.band_offset) * K4_BAND_ROWS;
-        const int y1 = min(y0 + K4_BAND_ROWS, rg.h);
+        const int BR = k4_band_rows(rg.w);
+        const int y0 = (t - rg.band_offset) * BR;
+        const int y1 = min(y0 + BR, rg.h);
         const unsigned* B = bits + rg.bits_offset;
         const int* st = stats + (long long)rg.stats_offset * 5;
         const int* P = parent + rg.blk_offset;
@@ -1010,7 +1062,7 @@ extern "C" int qc_segment_plan(qc_seg_region* regs, int num_regions, qc_seg_para
         px += (long long)r.w * r.h;
         px = (px + 15) & ~15ll;                 // keep every region's outputs 16-byte aligned
         stats += r.max_comp;
-        bands += (r.h + K4_BAND_ROWS - 1) / K4_BAND_ROWS;
+        bands += (r.h + k4_band_rows(r.w) - 1) / k4_band_rows(r.w);
         chunks += (wpr * bh + K4_CHUNK - 1) / K4_CHUNK;
         bits += wpr * r.h;
         blocks += bw * bh;
@@ -1072,11 +1124,15 @@ extern "C" int qc_segment(qc_ctx* ctx, const uint8_t* imgs, const qc_seg_params*
 
     const int halo = 4 * p->morph_iters;
     const int wpr_max = (p->max_region_w + 31) / 32;
-    const int buf_words = (K4_BAND_ROWS + 2 * halo) * wpr_max;
+    if (wpr_max > 256)      // k4_ccl_local packs (block row, word) of a cell into 8+8 bits
+        QC_FAIL(ctx, QC_ERR_UNSUPPORTED, "qc_segment: region width %d > 8192", p->max_region_w);
+    // conservative bounds over every region: rows x words <= RW whatever the region width
+    const int RW = std::max(K4_BAND_RW, 16 * wpr_max);
+    const int buf_words = RW + 2 * halo * wpr_max;
     const size_t smem_mask = (size_t)buf_words * 4 * 2;
-    const int band_words = ((K4_BAND_ROWS + 2) * (wpr_max + 2) + 3) & ~3;
-    const int lab_words = (K4_BAND_ROWS / 2) * wpr_max * 16;
-    const size_t smem_ccl = (size_t)band_words * 4 + (size_t)lab_words * 4 + (size_t)(K4_BAND_ROWS / 2) * wpr_max * 2;
+    const int band_words = (RW + 2 * 512 + 2 * wpr_max + 4 + 3) & ~3;
+    const int lab_words = 8 * RW;
+    const size_t smem_ccl = (size_t)band_words * 4 + (size_t)lab_words * 4 + (size_t)(RW / 2) * 2;
     const size_t smem_need = std::max(smem_mask, smem_ccl);
     if ((long long)smem_need + (K4_LOC_MAX + 1) * 4 + 1024 > ctx->max_smem_optin)
         QC_FAIL(ctx, QC_ERR_UNSUPPORTED, "qc_segment: region width %d needs %zu B of shared memory (max %d)",

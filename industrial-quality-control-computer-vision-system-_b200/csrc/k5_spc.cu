@@ -12,40 +12,39 @@
 
 namespace {
 
-__global__ void __launch_bounds__(256)
+constexpr int K5_THREADS = 1024;
+
+// one warp per image, lanes over that image's valid rows only (no per-slot division, no reads of empty rows)
+__global__ void __launch_bounds__(K5_THREADS)
 k5_spc(const float* __restrict__ det, const int* __restrict__ count, int n, int max_det, double* __restrict__ out9) {
     double acc[9];
 #pragma unroll
     for (int k = 0; k < 9; ++k) acc[k] = 0.0;
-    const int tid = threadIdx.x;
-    for (int i = tid; i < n; i += blockDim.x) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = warp; i < n; i += K5_THREADS / 32) {
         int c = count[i];
         c = c < 0 ? 0 : (c > max_det ? max_det : c);
-        acc[0] += 1.0;
-        acc[1] += (double)c;
-        acc[2] += (double)c * (double)c;
+        if (lane == 0) {
+            acc[0] += 1.0;
+            acc[1] += (double)c;
+            acc[2] += (double)c * (double)c;
+        }
+        for (int r = lane; r < c; r += 32) {
+            const float* row = det + ((long long)i * max_det + r) * 6;
+            const int x1 = (int)row[0], y1 = (int)row[1], x2 = (int)row[2], y2 = (int)row[3];
+            const float conf = row[4];
+            const long long area = (long long)(x2 - x1) * (long long)(y2 - y1);
+            const double na = (double)area / (1024.0 * 1024.0);
+            const double cd = (double)conf;
+            acc[3] += cd * 0.6 + fmin(cd * 1.1, 1.0) * 0.4;
+            acc[4] += 1.0;
+            if (conf > 0.9f || na > 0.1) acc[5] += 1.0;
+            else if (conf > 0.8f || na > 0.05) acc[6] += 1.0;
+            else acc[7] += 1.0;
+            acc[8] += (double)area;
+        }
     }
-    const long long total = (long long)n * max_det;
-    for (long long t = tid; t < total; t += blockDim.x) {
-        const int i = (int)(t / max_det), r = (int)(t - (long long)i * max_det);
-        int c = count[i];
-        c = c > max_det ? max_det : c;
-        if (r >= c) continue;
-        const float* row = det + t * 6;
-        const int x1 = (int)row[0], y1 = (int)row[1], x2 = (int)row[2], y2 = (int)row[3];
-        const float conf = row[4];
-        const long long area = (long long)(x2 - x1) * (long long)(y2 - y1);
-        const double na = (double)area / (1024.0 * 1024.0);
-        const double cd = (double)conf;
-        acc[3] += cd * 0.6 + fmin(cd * 1.1, 1.0) * 0.4;
-        acc[4] += 1.0;
-        if (conf > 0.9f || na > 0.1) acc[5] += 1.0;
-        else if (conf > 0.8f || na > 0.05) acc[6] += 1.0;
-        else acc[7] += 1.0;
-        acc[8] += (double)area;
-    }
-    __shared__ double sh[8][9];
-    const int lane = tid & 31, warp = tid >> 5;
+    __shared__ double sh[K5_THREADS / 32][9];
 #pragma unroll
     for (int k = 0; k < 9; ++k) {
         double v = acc[k];
@@ -56,7 +55,7 @@ k5_spc(const float* __restrict__ det, const int* __restrict__ count, int n, int 
     __syncthreads();
     if (tid < 9) {
         double v = 0.0;
-        for (int w = 0; w < 8; ++w) v += sh[w][tid];
+        for (int w = 0; w < K5_THREADS / 32; ++w) v += sh[w][tid];
         out9[tid] = v;
     }
 }
@@ -67,7 +66,7 @@ extern "C" int qc_spc_stats(qc_ctx* ctx, const float* det, const int32_t* count,
                             void* stream) {
     if (!ctx) return QC_ERR_INVALID;
     if (!det || !count || !out9 || n < 0 || max_det <= 0) QC_FAIL(ctx, QC_ERR_INVALID, "qc_spc_stats: bad argument");
-    k5_spc<<<1, 256, 0, (cudaStream_t)stream>>>(det, count, n, max_det, out9);
+    k5_spc<<<1, K5_THREADS, 0, (cudaStream_t)stream>>>(det, count, n, max_det, out9);
     QC_LAUNCHED(ctx);
     return QC_OK;
 }

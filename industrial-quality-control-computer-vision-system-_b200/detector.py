@@ -160,8 +160,8 @@ class YOLODetector:
 
 # ----------------------------------------------------------------------------------------------
 class ResNetClassifier:
-    """models/resent_model.py:21 -- K3 (whole-frame ROI) + ResNet-50.  The reference resizes with PIL's
-    antialiased bilinear filter; K3 resamples with roi_align (SURVEY.md §8f row f4 covers the PIL model)."""
+    """models/resent_model.py:21 -- K3b + ResNet-50.  The whole-frame input is the reference's own transform chain
+    (PIL antialiased BILINEAR Resize((224,224)) -> ToTensor -> Normalize, :57-66) computed bit-exactly on device."""
 
     def __init__(self, model_path: str = "models/resnet50_qc.pt", num_classes: int = 5, device: str = "auto",
                  config: Optional[Dict] = None):
@@ -191,6 +191,13 @@ class ResNetClassifier:
             logits = pipe.resnet(x.contiguous(memory_format=torch.channels_last))
         return torch.softmax(logits.float(), 1).cpu().numpy()
 
+    def _classify_whole(self, frames: torch.Tensor, swap_rb: bool) -> np.ndarray:
+        pipe = self._pipe
+        x = pipe.qc.pil_resize(frames, swap_rb=swap_rb, mean=RESNET_MEAN, std=RESNET_STD, out_dtype=pipe.net_dtype)
+        with torch.no_grad():
+            logits = pipe.resnet(x.contiguous(memory_format=torch.channels_last))
+        return torch.softmax(logits.float(), 1).cpu().numpy()
+
     def _result(self, probs: np.ndarray) -> Dict:
         cid = int(np.argmax(probs))
         conf = float(probs[cid])
@@ -208,7 +215,7 @@ class ResNetClassifier:
             h, w = img.shape[:2]
             frames = torch.from_numpy(img[None]).to(self._pipe.dev)
             # reference flips once (models/resent_model.py:123) -> swap_rb=True relative to `image`
-            probs = self._classify(frames, np.array([[0, 0, 0, w, h]], np.float32), swap_rb=True)[0]
+            probs = self._classify_whole(frames, swap_rb=True)[0]
             result = self._result(probs)
             result["inference_time_ms"] = (time.time() - start_time) * 1000
             return result

@@ -89,6 +89,10 @@ _SIGS = {
                                C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                C.c_int, C.c_void_p, C.c_void_p]),
     "qc_segment_plan": (C.c_int, [C.POINTER(SegRegion), C.c_int, C.POINTER(SegParams)]),
+    "qc_pil_resize_table_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    "qc_pil_resize_make_tables": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "qc_pil_resize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int32, C.c_void_p,
+                                C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "qc_segment_workspace_bytes": (C.c_size_t, [C.POINTER(SegParams)]),
     "qc_segment": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(SegParams), C.c_void_p, C.c_void_p, C.c_size_t,
                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -327,6 +331,43 @@ class Context:
                                    int(aligned), int(swap_rb), norm.data_ptr(), dt, out.data_ptr(),
                                    _stream(imgs.device))
         self._check(rc, "qc_roi_align")
+        return out
+
+    # -- K3b -------------------------------------------------------------------------------
+    def pil_resize_tables(self, h: int, w: int, out_hw=(224, 224)):
+        """(host int32 table, device copy) of Pillow's resampling coefficients for h x w -> out_hw, cached."""
+        key = ("pil", h, w, tuple(out_hw))
+        if key not in self._lut_cache:
+            nb = self.lib.qc_pil_resize_table_bytes(h, w, out_hw[0], out_hw[1])
+            host = torch.empty(nb // 4, dtype=torch.int32)
+            rc = self.lib.qc_pil_resize_make_tables(h, w, out_hw[0], out_hw[1], host.data_ptr())
+            self._check(rc, "qc_pil_resize_make_tables")
+            self._lut_cache[key] = (host, host.to(self.device))
+        return self._lut_cache[key]
+
+    def pil_resize(self, imgs: torch.Tensor, out_hw=(224, 224), swap_rb: bool = False, mean=(0.485, 0.456, 0.406),
+                   std=(0.229, 0.224, 0.225), out_dtype=torch.bfloat16, out: Optional[torch.Tensor] = None):
+        """uint8 [n,h,w,3] CUDA frames -> [n,3,oh,ow]: PIL BILINEAR (antialiased) resize + ToTensor + Normalize,
+        the whole-frame input of models/resent_model.py:114-130."""
+        assert imgs.is_cuda and imgs.dtype == torch.uint8 and imgs.dim() == 4 and imgs.shape[3] == 3
+        assert imgs.stride(3) == 1 and imgs.stride(2) == 3
+        n, h, w = imgs.shape[:3]
+        key = ("norm", tuple(mean), tuple(std))
+        if key not in self._lut_cache:
+            t = torch.tensor([[255.0, m, s] for m, s in zip(mean, std)], dtype=torch.float32)
+            self._lut_cache[key] = t.to(self.device)
+        norm = self._lut_cache[key]
+        host, dev = self.pil_resize_tables(h, w, out_hw)
+        if out is None:
+            out = torch.empty((n, 3) + tuple(out_hw), dtype=out_dtype, device=imgs.device)
+        if n == 0:
+            return out
+        assert out.is_contiguous() and tuple(out.shape) == (n, 3) + tuple(out_hw)
+        dt = QC_DT_BF16 if out.dtype == torch.bfloat16 else QC_DT_F32
+        rc = self.lib.qc_pil_resize(self.h, imgs.data_ptr(), n, h, w, imgs.stride(0) if n > 1 else h * imgs.stride(1),
+                                    imgs.stride(1), dev.data_ptr(), host.data_ptr(), int(swap_rb), norm.data_ptr(), dt,
+                                    out.data_ptr(), _stream(imgs.device))
+        self._check(rc, "qc_pil_resize")
         return out
 
     # -- K4 --------------------------------------------------------------------------------

@@ -176,31 +176,40 @@ class InspectionPipeline:
         K = len(roi_img)
         res = BatchResult(n=n, det=det, count=count, anchor=None, roi_img=roi_img, roi_det=roi_det, roi_box=roi_box)
 
-        # ---- K3 + ResNet-50: ROI hand-off (models/ensemble.py:129-142) + whole-frame classifier ----
-        crops = []
-        if self.classify_global:
-            whole = np.zeros((n, 5), np.float32)
-            whole[:, 0] = np.arange(n)
-            whole[:, 3], whole[:, 4] = w, h
-            crops.append(whole)
-        if self.classify_rois and K:
-            r = np.concatenate((roi_img[:, None].astype(np.float32), roi_box.astype(np.float32)), 1)
-            crops.append(r)
+        # ---- K3b/K3 + ResNet-50: whole-frame classifier (models/resent_model.py:114-130, PIL-exact resize) and
+        # ROI hand-off (models/ensemble.py:129-142).  Classifier rows: the n whole frames first, then the K ROIs.
+        n_whole = n if self.classify_global else 0
+        n_roi = K if self.classify_rois else 0
+        nro = n_whole + n_roi
+        self.last_num_crops = nro
         probs = None
-        if crops:
-            rois = torch.from_numpy(np.ascontiguousarray(np.concatenate(crops))).to(self.dev, non_blocking=True)
+        if nro:
+            rois = None
+            if n_roi:
+                r = np.concatenate((roi_img[:, None].astype(np.float32), roi_box.astype(np.float32)), 1)
+                rois = torch.from_numpy(np.ascontiguousarray(r)).to(self.dev, non_blocking=True)
+
             # ResNet sees the caller's channel order (two flips: detector.py:234 + resent_model.py:123)
-            nro = int(rois.shape[0])
-            self.last_num_crops = nro
+            def fill(buf, o, k):
+                """classifier rows [o, o+k) -> buf[:k]"""
+                a = min(o + k, n_whole)
+                if o < a:
+                    with self._timed("k3b_pil_resize"):
+                        qc.pil_resize(frames[o:a], swap_rb=False, mean=RESNET_MEAN, std=RESNET_STD, out=buf[:a - o])
+                if o + k > a:
+                    lo = max(o, n_whole)
+                    with self._timed("k3_roi_align"):
+                        qc.roi_align(frames, rois[lo - n_whole:o + k - n_whole], swap_rb=False, mean=RESNET_MEAN,
+                                     std=RESNET_STD, out=buf[lo - o:k])
+
             if not self.use_graphs:
-                with self._timed("k3_roi_align"):
-                    xin = qc.roi_align(frames, rois, swap_rb=False, mean=RESNET_MEAN, std=RESNET_STD,
-                                       out_dtype=self.net_dtype)
+                xin = torch.empty((nro, 3, 224, 224), dtype=self.net_dtype, device=self.dev)
+                fill(xin, 0, nro)
                 with self._timed("resnet_net"):
                     logits = self.resnet(xin.contiguous(memory_format=torch.channels_last))
                     probs = torch.softmax(logits.float(), 1)
             else:
-                # static-shape chunks: K3 writes each chunk straight into the graph's input buffer
+                # static-shape chunks: K3b/K3 write each chunk straight into the graph's input buffer
                 parts, o = [], 0
                 while o < nro:
                     rem = nro - o
@@ -208,9 +217,7 @@ class InspectionPipeline:
                     k = min(cs, rem)
                     shape = (cs, 3, 224, 224)
                     buf = self.resnet_g.input_buffer(shape)
-                    with self._timed("k3_roi_align"):
-                        qc.roi_align(frames, rois[o:o + k], swap_rb=False, mean=RESNET_MEAN, std=RESNET_STD,
-                                     out=buf[:k])
+                    fill(buf, o, k)
                     with self._timed("resnet_net"):
                         logits = self.resnet_g.run(shape)
                         parts.append(torch.softmax(logits[:k].float(), 1))

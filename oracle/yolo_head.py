@@ -146,10 +146,10 @@ def scale_boxes(net_shape, boxes, orig_shape):
 
 
 def yolo_postprocess(levels, nc, net_shape, orig_shape, conf=0.7, iou=0.5, max_det=300,
-                     strides=(8, 16, 32), return_idx=False):
+                     strides=(8, 16, 32), return_idx=False, max_nms=30000):
     """a3+a4+a5: decode -> NMS -> scale_boxes.  Returns list of [k,6] float32 tensors."""
     y = detect_decode(levels, nc, strides=strides)
-    dets, idxs = non_max_suppression(y, conf, iou, max_det=max_det, return_idx=True)
+    dets, idxs = non_max_suppression(y, conf, iou, max_det=max_det, max_nms=max_nms, return_idx=True)
     dets = [torch.cat((scale_boxes(net_shape, d[:, :4], orig_shape), d[:, 4:]), 1) if len(d) else d
             for d in dets]
     return (dets, idxs) if return_idx else dets

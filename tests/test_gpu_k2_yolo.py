@@ -87,7 +87,7 @@ def test_t1_near_threshold_offset_rounding(qc):
     assert torch.equal(keep[0, :len(ref)].cpu().long(), ref)
 
 
-def _compare_full(qc, levels, H, W, orig=None, conf=0.7, iou=0.5, max_det=300, dtype=torch.float32):
+def _compare_full(qc, levels, H, W, orig=None, conf=0.7, iou=0.5, max_det=300, dtype=torch.float32, max_nms=30000):
     from qcgraft import ffi
     nc = 5
     n = levels[0].shape[0]
@@ -95,12 +95,13 @@ def _compare_full(qc, levels, H, W, orig=None, conf=0.7, iou=0.5, max_det=300, d
     plan = qc.make_pre_plan(ffi.QC_PRE_LETTERBOX, orig[0], orig[1], H, W)
     assert (plan.dst_h, plan.dst_w) == (H, W)
     dev = [l.to(dtype).cuda().contiguous() for l in levels]
-    p = qc.yolo_params(dev, nc, conf=conf, iou=iou, max_det=max_det, plan=plan)
+    p = qc.yolo_params(dev, nc, conf=conf, iou=iou, max_det=max_det, max_nms=max_nms, plan=plan)
     det, anchor, count, ncand = qc.yolo_decode_nms(dev, p)
     torch.cuda.synchronize()
     det, anchor, count, ncand = det.cpu(), anchor.cpu(), count.cpu(), ncand.cpu()
     ref_in = [l.to(dtype).float() for l in levels]          # bf16 mode: oracle sees the rounded values
-    rdets, ridx = oyh.yolo_postprocess(ref_in, nc, (H, W), orig, conf=conf, iou=iou, max_det=max_det, return_idx=True)
+    rdets, ridx = oyh.yolo_postprocess(ref_in, nc, (H, W), orig, conf=conf, iou=iou, max_det=max_det, return_idx=True,
+                                       max_nms=max_nms)
     y = oyh.detect_decode(ref_in, nc)
     for i in range(n):
         k = len(rdets[i])
@@ -188,3 +189,37 @@ def test_cfg2_full_batch_64_bf16(qc):
     from qcgraft import synth
     levels = synth.make_head(301, 64, 640, 640, 30)
     _compare_full(qc, levels, 640, 640, dtype=torch.bfloat16)
+
+
+def test_one_class_dominates_global_sort_path(qc):
+    """> 1024 candidates of ONE class in an image: the per-class NMS CTA leaves its shared-memory sort for the
+    global-memory regions; the other classes of the same image stay in shared memory."""
+    from qcgraft import synth
+    levels = synth.make_head(302, 2, 1280, 1280, 2600)
+    for l in levels:
+        cls = l[:, 64:69]
+        top = cls.amax(1)
+        move = torch.rand(top.shape, generator=torch.Generator().manual_seed(5)) < 0.8   # 80% of anchors -> class 2
+        newc = cls.clone()
+        newc[:, 2] = torch.where(move, top, cls[:, 2])
+        for c in (0, 1, 3, 4):
+            newc[:, c] = torch.where(move, torch.full_like(top, -8.0), cls[:, c])
+        l[:, 64:69] = newc
+    det, count = _compare_full(qc, levels, 1280, 1280)
+    assert int(count.min()) >= 100
+
+
+def test_max_det_cut_across_classes(qc):
+    """max_det smaller than the kept total: the rank merge must return the global top-max_det by score."""
+    from qcgraft import synth
+    levels = synth.make_head(303, 3, 640, 640, 600, n_centres=300)
+    for md in (7, 64, 300):
+        _compare_full(qc, levels, 640, 640, max_det=md)
+
+
+def test_max_nms_cut(qc):
+    """More candidates than max_nms: only the max_nms best-scoring ones enter NMS (ultralytics' pre-NMS cut)."""
+    from qcgraft import synth
+    levels = synth.make_head(304, 2, 640, 640, 700, n_centres=120)
+    for mn in (650, 257, 64):
+        _compare_full(qc, levels, 640, 640, max_nms=mn)

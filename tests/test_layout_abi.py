@@ -71,8 +71,8 @@ def test_segment_plan_offsets():
     arr, p = Fake().segment_plan(regs, 2, 2048, 2048, 1, 2048 * 2048, 2048)
     assert p.num_regions == 3 and p.max_region_w == 2048
     assert arr.out_offset[0] == 0 and arr.out_offset[1] == 2048 * 2048 and arr.out_offset[2] % 16 == 0
-    band = 16                                                    # K4_BAND_ROWS
-    assert arr.band_offset.tolist() == [0, 2048 // band, 2048 // band + 2] and p.total_bands == 2048 // band + 3
+    band = 16                 # k4_band_rows(2048); narrow regions get taller bands (33x17 and 1x1: one band each)
+    assert arr.band_offset.tolist() == [0, 2048 // band, 2048 // band + 1] and p.total_bands == 2048 // band + 2
     assert arr.blk_offset.tolist() == [0, 1024 * 1024, 1024 * 1024 + 17 * 9]
     assert p.total_bits_words == 2048 * 64 + 17 * 2 + 1
     with pytest.raises(ffi.QcGraftError):                                   # region outside the image
@@ -103,3 +103,31 @@ def test_no_cpu_fallback():
     d = QualityControlDetector("y.pt", "r.pt", {})
     out = d.predict(np.zeros((64, 64, 3), np.uint8))
     assert "error" in out                                        # the reference's error convention, never raises
+
+
+def test_pil_resize_tables_match_pillow_coefficients():
+    """qc_pil_resize_make_tables (host C++, float64) == the oracle's restatement of Pillow's precompute_coeffs +
+    normalize_coeffs_8bpc, which tests/test_oracle_pins.py pins against Pillow itself."""
+    from qcgraft import ffi
+    from oracle import pil_resize as pr
+    lib = ffi.load_library()
+    for (h, w, oh, ow) in [(640, 640, 224, 224), (1080, 1920, 224, 224), (333, 500, 224, 224), (100, 150, 224, 224),
+                           (224, 224, 224, 224), (2048, 2048, 224, 224), (7, 9, 224, 224), (480, 640, 96, 128)]:
+        nb = lib.qc_pil_resize_table_bytes(h, w, oh, ow)
+        t = np.zeros(nb // 4, np.int32)
+        assert lib.qc_pil_resize_make_tables(h, w, oh, ow, t.ctypes.data) == 0
+        kx, bx, kkx = pr.precompute_coeffs(w, ow)
+        ky, by, kky = pr.precompute_coeffs(h, oh)
+        assert t[:6].tolist() == [h, w, oh, ow, kx, ky]
+        o = 8
+        assert np.array_equal(t[o:o + ow * 2].reshape(ow, 2), bx); o += ow * 2
+        assert np.array_equal(t[o:o + ow * kx].reshape(ow, kx), kkx); o += ow * kx
+        assert np.array_equal(t[o:o + oh * 2].reshape(oh, 2), by); o += oh * 2
+        assert np.array_equal(t[o:o + oh * ky].reshape(oh, ky), kky); o += oh * ky
+        assert o == len(t)
+        band, max_rows = int(t[6]), int(t[7])
+        assert 1 <= band <= oh and max_rows * 3 * ((ow + 3) & ~3) <= 200 * 1024
+        for o0 in range(0, oh, band):
+            o1 = min(o0 + band, oh) - 1
+            assert by[o1, 0] + by[o1, 1] - by[o0, 0] <= max_rows
+    assert lib.qc_pil_resize_make_tables(0, 5, 224, 224, t.ctypes.data) != 0

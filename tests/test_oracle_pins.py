@@ -148,3 +148,20 @@ def test_decode_shapes_and_anchor_order():
     assert torch.allclose(y[0, 2:4, 0], torch.tensor([120.0, 120.0]))
     assert torch.allclose(y[0, :2, 64], torch.tensor([8.0, 8.0]))   # first P4 anchor
     assert torch.allclose(y[0, 4:, 0], torch.full((nc,), 0.5))
+
+
+# ---- K3b: Pillow's antialiased BILINEAR resize + torchvision ToTensor/Normalize ---------------------
+@pytest.mark.parametrize("hw", [(640, 640), (480, 640), (333, 500), (224, 224), (100, 150), (224, 500), (7, 9),
+                                (1080, 1920)])
+def test_pil_resize_restatement_is_bit_exact(hw):
+    from PIL import Image
+    import torchvision.transforms as T
+    from oracle import pil_resize as pr
+    rng = np.random.default_rng(hw[0] * 7 + hw[1])
+    img = rng.integers(0, 256, hw + (3,), dtype=np.uint8)
+    ref = np.asarray(Image.fromarray(img).resize((224, 224), Image.BILINEAR))
+    assert np.array_equal(pr.pil_resize_bilinear(img), ref)
+    # the reference's transform chain (models/resent_model.py:57-66)
+    tf = T.Compose([T.Resize((224, 224)), T.ToTensor(),
+                    T.Normalize(mean=[0.485, 0.456, 0.406], std=[0.229, 0.224, 0.225])])
+    assert np.array_equal(pr.resnet_input(img), tf(Image.fromarray(img)).numpy())
