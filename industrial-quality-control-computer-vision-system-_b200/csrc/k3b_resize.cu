@@ -83,10 +83,18 @@ void axis_coeffs(int in_size, int out_size, int ksize, int* bounds, int* kk) {
     }
 }
 
-template <typename OutT>
+// Horizontal taps of one output column cover 3*cnt CONTIGUOUS source bytes.  The CTA stages source rows in shared
+// memory with 128-bit loads (smem offset == global address mod 16), and a thread (= output column) reads its window
+// as 32-bit words: four taps = 12 bytes = three words after one funnel shift per word, so a row costs 3-4 LDS.32 per
+// four taps instead of 12 byte loads -- the byte-load form is LSU-bound.  Coefficient rows are padded with zeros to
+// a multiple of four taps (NG groups); for NG <= 2 they live in registers.
+// staged row: 3*w data bytes + 16 B alignment slack + the words the zero-coefficient taps of the last group may reach
+__host__ __device__ inline int k3b_row_buf(int src_w, int ng) { return (src_w * 3 + 32 + 12 * ng + 15) & ~15; }
+
+template <typename OutT, int NG>              // NG: 4-tap groups per output column (0 = runtime, coefficients in smem)
 __global__ void __launch_bounds__(K3B_THREADS)
 k3b_resize(const uint8_t* __restrict__ imgs, long long img_stride, int row_stride, const int* __restrict__ tab,
-           int swap_rb, const float* __restrict__ norm, OutT* __restrict__ dst) {
+           int swap_rb, const float* __restrict__ norm, OutT* __restrict__ dst, int stage_rows, int ng_rt) {
     extern __shared__ __align__(16) uint8_t k3b_sm[];
     __shared__ float s_lut[3][256];
     const int src_w = tab[1], dst_h = tab[2], dst_w = tab[3], kx = tab[4], ky = tab[5];
@@ -95,41 +103,108 @@ k3b_resize(const uint8_t* __restrict__ imgs, long long img_stride, int row_strid
     const int* __restrict__ kkx = bx + dst_w * 2;
     const int* __restrict__ by = kkx + dst_w * kx;
     const int* __restrict__ kky = by + dst_h * 2;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int img = blockIdx.y;
     const int oy0 = blockIdx.x * band_rows, oy1 = min(oy0 + band_rows, dst_h);
     const int pitch = (dst_w + 3) & ~3;                    // bytes per channel row of the tile
+    const int ng = NG ? NG : ng_rt;
+    const int row_buf = k3b_row_buf(src_w, ng);
     uint8_t* tile = k3b_sm;                                // [max_src_rows][3][pitch]
+    uint8_t* stage = tile + (((size_t)max_src_rows * 3 * pitch + 15) & ~(size_t)15);   // [2][stage_rows][row_buf]
+    int* kx_s = reinterpret_cast<int*>(stage + (size_t)2 * stage_rows * row_buf);        // [dst_w][ng*4] (NG == 0)
 
     // ToTensor + Normalize per OUTPUT channel: ((float)v / div - mean) / std with the reference's float32 ops
     for (int i = tid; i < 768; i += K3B_THREADS) {
         const int c = i >> 8, v = i & 255;
         s_lut[c][v] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)v, norm[c * 3 + 0]), norm[c * 3 + 1]), norm[c * 3 + 2]);
     }
+    if (NG == 0) {
+        for (int i = tid; i < dst_w * ng * 4; i += K3B_THREADS) {
+            const int ox = i / (ng * 4), x = i - ox * ng * 4;
+            kx_s[i] = x < kx ? __ldg(kkx + ox * kx + x) : 0;
+        }
+    }
     // source rows this band taps (bounds are monotone in the output index)
     const int sy0 = by[oy0 * 2], sy1 = by[(oy1 - 1) * 2] + by[(oy1 - 1) * 2 + 1];
     const int nsrc = min(sy1 - sy0, max_src_rows);
     const uint8_t* ibase = imgs + (long long)img * img_stride;
 
-    // ---- horizontal pass: (source row, output column) -> 3 channel bytes of the tile -----------------
-    for (int it = tid; it < nsrc * dst_w; it += K3B_THREADS) {
-        const int rr = it / dst_w, ox = it - rr * dst_w;
-        const int x0 = bx[ox * 2], cnt = bx[ox * 2 + 1];
-        const uint8_t* p = ibase + (long long)(sy0 + rr) * row_stride + (long long)x0 * 3;
-        const int* k = kkx + ox * kx;
-        int a0 = 1 << (K3B_PREC - 1), a1 = a0, a2 = a0;
-        for (int x = 0; x < cnt; ++x) {
-            const int kv = __ldg(k + x);
-            a0 += (int)__ldg(p + 3 * x) * kv;
-            a1 += (int)__ldg(p + 3 * x + 1) * kv;
-            a2 += (int)__ldg(p + 3 * x + 2) * kv;
+    // ---- horizontal pass: source rows are staged stage_rows at a time, double-buffered with cp.async so the
+    // next rows stream in while the current ones are filtered ---------------------------------------------
+    auto issue_stage = [&](int r0, uint8_t* buf) {
+        const int nr = min(stage_rows, nsrc - r0);
+        // warp per row; 16-byte async copies for the aligned interior, bytes for the ragged ends; the tail is
+        // zero-filled so the zero-coefficient taps of the last group read defined bytes
+        for (int rr = warp; rr < nr; rr += K3B_THREADS / 32) {
+            const uint8_t* p = ibase + (long long)(sy0 + r0 + rr) * row_stride;
+            const int off = (int)(reinterpret_cast<uintptr_t>(p) & 15);
+            uint8_t* sb = buf + (size_t)rr * row_buf;              // sb[off + i] = p[i]
+            const int nbytes = src_w * 3;
+            const int head = min(nbytes, (16 - off) & 15);
+            const int nvec = (nbytes - head) >> 4;
+            for (int i = lane; i < head; i += 32) sb[off + i] = __ldg(p + i);
+            const uint8_t* pv = p + head;
+            const uint32_t sv = qc_smem_u32(sb + off + head);
+            for (int i = lane; i < nvec; i += 32)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sv + 16u * i), "l"(pv + 16 * (size_t)i) : "memory");
+            for (int i = head + nvec * 16 + lane; i < nbytes; i += 32) sb[off + i] = __ldg(p + i);
+            for (int i = off + nbytes + lane; i < row_buf; i += 32) sb[i] = 0;
         }
-        uint8_t* t = tile + (size_t)rr * 3 * pitch + ox;
-        t[0] = (uint8_t)min(max(a0 >> K3B_PREC, 0), 255);
-        t[pitch] = (uint8_t)min(max(a1 >> K3B_PREC, 0), 255);
-        t[2 * pitch] = (uint8_t)min(max(a2 >> K3B_PREC, 0), 255);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    const int nstage = (nsrc + stage_rows - 1) / stage_rows;
+    issue_stage(0, stage);
+    for (int sti = 0; sti < nstage; ++sti) {
+        const int r0 = sti * stage_rows;
+        const int nr = min(stage_rows, nsrc - r0);
+        uint8_t* cur = stage + (size_t)(sti & 1) * stage_rows * row_buf;
+        if (sti + 1 < nstage) {
+            issue_stage(r0 + stage_rows, stage + (size_t)((sti + 1) & 1) * stage_rows * row_buf);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncthreads();                                   // stage sti landed (and tables / LUT written)
+        for (int ox = tid; ox < dst_w; ox += K3B_THREADS) {
+            const int x0 = bx[ox * 2];
+            int kreg[NG ? NG * 4 : 1];
+            if (NG) {
+#pragma unroll
+                for (int x = 0; x < NG * 4; ++x) kreg[x] = x < kx ? __ldg(kkx + ox * kx + x) : 0;
+            }
+            for (int rr = 0; rr < nr; ++rr) {
+                const uint8_t* p = ibase + (long long)(sy0 + r0 + rr) * row_stride;
+                const int s = (int)(reinterpret_cast<uintptr_t>(p) & 15) + x0 * 3;      // window start in the staged row
+                const unsigned* wp = reinterpret_cast<const unsigned*>(cur + (size_t)rr * row_buf) + (s >> 2);
+                const unsigned sh = (unsigned)(s & 3) * 8u;
+                int a0 = 1 << (K3B_PREC - 1), a1 = a0, a2 = a0;
+                unsigned wprev = wp[0];
+#pragma unroll
+                for (int g = 0; g < (NG ? NG : 1); ++g) {
+                    for (int gg = g; gg < (NG ? g + 1 : ng); ++gg) {
+                        const unsigned w1 = wp[3 * gg + 1], w2 = wp[3 * gg + 2], w3 = wp[3 * gg + 3];
+                        const unsigned A0 = __funnelshift_r(wprev, w1, sh), A1 = __funnelshift_r(w1, w2, sh),
+                                       A2 = __funnelshift_r(w2, w3, sh);
+                        wprev = w3;
+                        int k0, k1, k2, k3;
+                        if (NG) { k0 = kreg[4 * g]; k1 = kreg[4 * g + 1]; k2 = kreg[4 * g + 2]; k3 = kreg[4 * g + 3]; }
+                        else {
+                            const int4 kv = *reinterpret_cast<const int4*>(kx_s + (ox * ng + gg) * 4);
+                            k0 = kv.x; k1 = kv.y; k2 = kv.z; k3 = kv.w;
+                        }
+                        a0 += (int)(A0 & 255u) * k0 + (int)(A0 >> 24) * k1 + (int)((A1 >> 16) & 255u) * k2 + (int)((A2 >> 8) & 255u) * k3;
+                        a1 += (int)((A0 >> 8) & 255u) * k0 + (int)(A1 & 255u) * k1 + (int)(A1 >> 24) * k2 + (int)((A2 >> 16) & 255u) * k3;
+                        a2 += (int)((A0 >> 16) & 255u) * k0 + (int)((A1 >> 8) & 255u) * k1 + (int)(A2 & 255u) * k2 + (int)(A2 >> 24) * k3;
+                    }
+                }
+                uint8_t* t = tile + (size_t)(r0 + rr) * 3 * pitch + ox;
+                t[0] = (uint8_t)min(max(a0 >> K3B_PREC, 0), 255);
+                t[pitch] = (uint8_t)min(max(a1 >> K3B_PREC, 0), 255);
+                t[2 * pitch] = (uint8_t)min(max(a2 >> K3B_PREC, 0), 255);
+            }
+        }
+        __syncthreads();                                   // done with `cur` before stage sti+2 overwrites it
     }
-    __syncthreads();
 
     // ---- vertical pass + ToTensor + Normalize: 4 consecutive columns of one (row, channel) per thread -----
     const int quads = pitch >> 2;
@@ -214,23 +289,37 @@ extern "C" int qc_pil_resize(qc_ctx* ctx, const uint8_t* imgs, int n, int h, int
         QC_FAIL(ctx, QC_ERR_INVALID, "qc_pil_resize: bad argument");
     if (host_tables[0] != h || host_tables[1] != w) QC_FAIL(ctx, QC_ERR_INVALID, "qc_pil_resize: tables are for %dx%d", host_tables[0], host_tables[1]);
     if (n > 65535) QC_FAIL(ctx, QC_ERR_UNSUPPORTED, "qc_pil_resize: n > 65535 (split the call)");
-    const int dst_h = host_tables[2], dst_w = host_tables[3], band = host_tables[6], max_rows = host_tables[7];
+    const int dst_h = host_tables[2], dst_w = host_tables[3], kx = host_tables[4], band = host_tables[6],
+              max_rows = host_tables[7];
     const int pitch = (dst_w + 3) & ~3;
-    const size_t smem = (size_t)max_rows * 3 * pitch;
+    const int ng = (kx + 3) / 4;
+    const int row_buf = k3b_row_buf(w, ng);
+    const size_t tile_bytes = ((size_t)max_rows * 3 * pitch + 15) & ~(size_t)15;
+    const size_t coef_bytes = ng <= 2 ? 0 : (size_t)dst_w * ng * 16;
+    // rows per staging buffer (two buffers): 4 unless the frame is so wide that the budget only allows fewer
+    int stage_rows = 4;
+    while (stage_rows > 1 && tile_bytes + (size_t)2 * stage_rows * row_buf + coef_bytes + 4096 > (size_t)ctx->max_smem_optin / 2)
+        stage_rows >>= 1;
+    const size_t smem = tile_bytes + (size_t)2 * stage_rows * row_buf + coef_bytes;
     if ((long long)smem + 4096 > ctx->max_smem_optin)
         QC_FAIL(ctx, QC_ERR_UNSUPPORTED, "qc_pil_resize: %dx%d -> %dx%d needs %zu B of shared memory", h, w, dst_h, dst_w, smem);
     cudaStream_t st = (cudaStream_t)stream;
     dim3 grid((unsigned)((dst_h + band - 1) / band), (unsigned)n);
-    if (out_dtype == QC_DT_BF16) {
-        if (int rc = qc_prepare(ctx, k3b_resize<__nv_bfloat16>, (int)smem, K3B_THREADS, nullptr)) return rc;
-        k3b_resize<__nv_bfloat16><<<grid, K3B_THREADS, smem, st>>>(imgs, img_stride, row_stride, dev_tables, swap_rb, norm,
-                                                                   (__nv_bfloat16*)dst);
-    } else if (out_dtype == QC_DT_F32) {
-        if (int rc = qc_prepare(ctx, k3b_resize<float>, (int)smem, K3B_THREADS, nullptr)) return rc;
-        k3b_resize<float><<<grid, K3B_THREADS, smem, st>>>(imgs, img_stride, row_stride, dev_tables, swap_rb, norm, (float*)dst);
-    } else {
-        QC_FAIL(ctx, QC_ERR_INVALID, "qc_pil_resize: bad out_dtype");
-    }
+#define K3B_LAUNCH(T, G)                                                                                          \
+    do {                                                                                                          \
+        if (int rc = qc_prepare(ctx, k3b_resize<T, G>, (int)smem, K3B_THREADS, nullptr)) return rc;               \
+        k3b_resize<T, G><<<grid, K3B_THREADS, smem, st>>>(imgs, img_stride, row_stride, dev_tables, swap_rb, norm, \
+                                                          (T*)dst, stage_rows, ng);                               \
+    } while (0)
+#define K3B_LAUNCH_NG(T)                          \
+    do {                                          \
+        if (ng == 1) K3B_LAUNCH(T, 1);            \
+        else if (ng == 2) K3B_LAUNCH(T, 2);       \
+        else K3B_LAUNCH(T, 0);                    \
+    } while (0)
+    if (out_dtype == QC_DT_BF16) K3B_LAUNCH_NG(__nv_bfloat16);
+    else if (out_dtype == QC_DT_F32) K3B_LAUNCH_NG(float);
+    else QC_FAIL(ctx, QC_ERR_INVALID, "qc_pil_resize: bad out_dtype");
     QC_LAUNCHED(ctx);
     return QC_OK;
 }

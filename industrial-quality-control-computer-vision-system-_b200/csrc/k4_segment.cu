@@ -486,17 +486,28 @@ k4_mask(Img im, const qc_seg_region* __restrict__ regs, int R, int total_bands,
         for (int yy = warp; yy < nrows; yy += K4_THREADS / 32) {
             const uint8_t* p = gbase + (long long)(row_lo + yy) * gpitch;
             const bool al = (reinterpret_cast<uintptr_t>(p) & 15) == 0;
-            for (int s0 = 0; s0 < segs; s0 += 32) {
-                const int sg = s0 + lane;
-                const int x0 = sg * 16;
-                unsigned b16 = 0;
-                if (sg < segs && x0 < rg.w && !none) {
-                    if (al && x0 + 16 <= rg.w) {
-                        const uint4 v = im.channels == 3 ? *reinterpret_cast<const uint4*>(p + x0)
-                                                         : __ldg(reinterpret_cast<const uint4*>(p + x0));
+            // four 16-pixel segments per lane per round: all 128-bit loads of the round are issued before the first
+            // compare, so a warp keeps 2 KB in flight instead of waiting out one DRAM latency per 512 B
+            for (int s0 = 0; s0 < segs; s0 += 128) {
+                uint4 v[4];
+                bool fastp[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int sg = s0 + 32 * j + lane, x0 = sg * 16;
+                    fastp[j] = sg < segs && !none && al && x0 + 16 <= rg.w;
+                    if (fastp[j])
+                        v[j] = im.channels == 3 ? *reinterpret_cast<const uint4*>(p + x0)
+                                                : __ldg(reinterpret_cast<const uint4*>(p + x0));
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int sg = s0 + 32 * j + lane, x0 = sg * 16;
+                    if (s0 + 32 * j >= segs) break;            // warp-uniform
+                    unsigned b16 = 0;
+                    if (fastp[j]) {
                         // per-byte compares (0xFF where lo <= g <= hi), then 4 mask bytes -> 4 bits with one
                         // multiply: bytes at bit 0/8/16/24 land on bits 24..27 of t * 0x01020408
-                        const unsigned w4[4] = {v.x, v.y, v.z, v.w};
+                        const unsigned w4[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
                             // the interval is one-sided in practice ([lo,255] light, [0,hi] dark): one compare
@@ -505,16 +516,16 @@ k4_mask(Img im, const qc_seg_region* __restrict__ regs, int R, int total_bands,
                                                     : (__vsetgeu4(w4[q], lo4) & __vsetleu4(w4[q], hi4));
                             b16 |= ((mk * 0x01020408u) >> 24) << (4 * q);
                         }
-                    } else {
+                    } else if (sg < segs && x0 < rg.w && !none) {
                         const int nv = min(16, rg.w - x0);
                         for (int k = 0; k < nv; ++k) {
                             const int g = (int)p[x0 + k];
                             b16 |= (unsigned)(g >= lo && g <= hi) << k;
                         }
                     }
+                    const unsigned hi16 = __shfl_down_sync(0xffffffffu, b16, 1);
+                    if (!(lane & 1) && sg < segs) bufA[yy * wpr + (sg >> 1)] = b16 | (hi16 << 16);
                 }
-                const unsigned hi16 = __shfl_down_sync(0xffffffffu, b16, 1);
-                if (!(lane & 1) && sg < segs) bufA[yy * wpr + (sg >> 1)] = b16 | (hi16 << 16);
             }
         }
         __syncthreads();
