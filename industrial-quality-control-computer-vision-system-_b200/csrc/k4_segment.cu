@@ -690,14 +690,30 @@ k4_ccl_local(const qc_seg_region* __restrict__ regs, int R, int total_bands, con
             }
         }
         __syncthreads();
-        // (3) flatten to global block indices (foreground blocks only)
+        // (3a) compress the run heads (one thread per non-empty cell): every ancestor of a block is a run head, so
+        // after this pass a block reaches its root in two hops and the per-block pass below needs no loop
+        for (int it = tid; it < nne; it += K4_THREADS) {
+            const int ce = cell_list[it];
+            const int byy = ce >> 8, wx = ce & 255;
+            const unsigned v = rowword(2 * byy, wx) | rowword(2 * byy + 1, wx);
+            unsigned HB = ((v | (v >> 1)) & 0x55555555u) & ~(v & (v << 1) & 0x55555555u);
+            const int base = byy * bwp + wx * 16;
+            while (HB) {
+                const int h = base + ((__ffs(HB) - 1) >> 1);
+                HB &= HB - 1;
+                const int rt = suf_find(lab, h);
+                lab[h] = rt;
+            }
+        }
+        __syncthreads();
+        // (3b) flatten to global block indices (foreground blocks only)
         const float inv_bwp = 1.0f / (float)bwp;
         for (int it = tid; it < nne * 16; it += K4_THREADS) {
             const int ce = cell_list[it >> 4], k = it & 15;
             const int byy = ce >> 8, wx = ce & 255;
             const unsigned v = rowword(2 * byy, wx) | rowword(2 * byy + 1, wx);
             if (!((v >> (2 * k)) & 3u)) continue;
-            const int rt = suf_find(lab, byy * bwp + wx * 16 + k);
+            const int rt = lab[lab[byy * bwp + wx * 16 + k]];
             const int rby = (int)(((float)rt + 0.5f) * inv_bwp);         // rt / bwp (exact: rt < 2^20)
             parent[rg.blk_offset + (long long)(by0 + byy) * bw + wx * 16 + k] =
                 rg.blk_offset + (by0 + rby) * bw + (rt - rby * bwp);
