@@ -262,19 +262,20 @@ __global__ void k2_make_keys(const float* __restrict__ scores, const int* __rest
 // inter against den*(thr -/+ 1e-4) already decides (float32 rounding is ~1e-7 relative).
 __device__ __forceinline__ bool iou_gt(const float4 a, const float4 b, double thr, float thr_lo, float thr_hi,
                                        bool fast) {
+    // Branch-light form: every lane computes inter and den (a dozen float ops, no early exits, so a warp whose lanes
+    // meet different cases does not serialise them); only lanes the +-1e-4 band cannot decide run the division.
+    // Disjoint boxes give inter == 0: decided "false" by inter < den*thr_lo when den > 0, and 0/den (<= 0 or NaN)
+    // through the exact path otherwise -- the same answers as torchvision's expression.
     const float w = __fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x));
-    if (fast && !(w > 0.f)) return false;               // inter == 0 -> ovr = 0 (or NaN): never > thr >= 0
     const float h = __fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y));
-    if (fast && !(h > 0.f)) return false;
     const float iarea = __fmul_rn(__fsub_rn(a.z, a.x), __fsub_rn(a.w, a.y));
     const float jarea = __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
     const float inter = __fmul_rn(fmaxf(0.f, w), fmaxf(0.f, h));
     const float den = __fsub_rn(__fadd_rn(iarea, jarea), inter);
-    if (fast && den > 0.f) {
-        if (inter < __fmul_rn(den, thr_lo)) return false;
-        if (inter > __fmul_rn(den, thr_hi)) return true;
-    }
-    return (double)__fdiv_rn(inter, den) > thr;
+    const bool lo = inter < __fmul_rn(den, thr_lo), hi = inter > __fmul_rn(den, thr_hi);
+    bool res = hi;
+    if (!(fast && den > 0.f && (lo || hi))) res = (double)__fdiv_rn(inter, den) > thr;
+    return res;
 }
 
 struct NmsArgs {
@@ -376,8 +377,9 @@ k2_nms(NmsArgs args, const unsigned long long* __restrict__ cand_key, const floa
         const int cb = i & ~63, mm = min(64, n - cb), il = i - cb;
         const float4 bi = sorted[i];
         const int j0 = lane, j1 = lane + 32;
-        const bool b0 = j0 > il && j0 < mm && iou_gt(bi, sorted[cb + j0], thr, thr_lo, thr_hi, fast);
-        const bool b1 = j1 > il && j1 < mm && iou_gt(bi, sorted[cb + j1], thr, thr_lo, thr_hi, fast);
+        const bool r0 = iou_gt(bi, sorted[cb + min(j0, mm - 1)], thr, thr_lo, thr_hi, fast);
+        const bool r1 = iou_gt(bi, sorted[cb + min(j1, mm - 1)], thr, thr_lo, thr_hi, fast);
+        const bool b0 = j0 > il && j0 < mm && r0, b1 = j1 > il && j1 < mm && r1;
         const unsigned lo = __ballot_sync(0xffffffffu, b0), hi = __ballot_sync(0xffffffffu, b1);
         if (lane == 0) Mall[i] = ((unsigned long long)hi << 32) | lo;
     }
@@ -569,15 +571,14 @@ k2_nms_class(NmsArgs args, int nc, const unsigned long long* __restrict__ cand_k
     int* kept_list = reinterpret_cast<int*>(smem_raw + K2_REMOVED_MAX / 8);              // max_det ints
     uint8_t* dyn = smem_raw + K2_REMOVED_MAX / 8 + (size_t)((args.max_det + 3) & ~3) * 4;
     dyn = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(dyn) + 15) & ~(uintptr_t)15);
-    float4* sorted = in_smem ? reinterpret_cast<float4*>(dyn) : g_sorted + (long long)img * cap + boff;
-    unsigned long long* keys = in_smem ? reinterpret_cast<unsigned long long*>(dyn + (size_t)K2C_SMEM_N * 16)
-                                       : g_keys + (long long)img * 2 * cap + koff;
-    int* vals = in_smem ? reinterpret_cast<int*>(dyn + (size_t)K2C_SMEM_N * 24) : g_vals + (long long)img * 2 * cap + koff;
-    unsigned long long* Mall = in_smem ? reinterpret_cast<unsigned long long*>(dyn + (size_t)K2C_SMEM_N * 28)
-                                       : g_mall + (long long)img * cap + boff;
+    const double thr = args.iou_thres;
+    const bool fast = thr > 1e-3 && thr < 1.0;
+    const float thr_lo = (float)(thr - 1e-4), thr_hi = (float)(thr + 1e-4);
 
-    // ---- gather this class (any order: the sort fixes it) ---------------------------------------------
-    if (n > 0) {
+    // The body is instantiated twice -- shared-memory buffers (the normal case) and the global-memory regions of an
+    // oversized class -- so that the compiler knows the address space of every access (LDS/STS instead of generic).
+    auto core = [&](float4* sorted, unsigned long long* keys, int* vals, unsigned long long* Mall) {
+        // ---- gather this class (any order: the sort fixes it) -----------------------------------------
         for (int i0 = 0; i0 < ntot; i0 += K2C_THREADS) {
             const int i = i0 + tid;
             unsigned long long k = 0;
@@ -606,15 +607,14 @@ k2_nms_class(NmsArgs args, int nc, const unsigned long long* __restrict__ cand_k
         for (int i = tid; i < (n + 31) / 32 + 2; i += K2C_THREADS) removed[i] = 0u;
         __syncthreads();
 
-        const double thr = args.iou_thres;
-        const bool fast = thr > 1e-3 && thr < 1.0;
-        const float thr_lo = (float)(thr - 1e-4), thr_hi = (float)(thr + 1e-4);
+        // 64x64 upper-triangular suppression bitmask of every chunk (depends only on the boxes)
         for (int i = warp; i < n; i += K2C_THREADS / 32) {
             const int cb = i & ~63, mm = min(64, n - cb), il = i - cb;
             const float4 bi = sorted[i];
             const int j0 = lane, j1 = lane + 32;
-            const bool b0 = j0 > il && j0 < mm && iou_gt(bi, sorted[cb + j0], thr, thr_lo, thr_hi, fast);
-            const bool b1 = j1 > il && j1 < mm && iou_gt(bi, sorted[cb + j1], thr, thr_lo, thr_hi, fast);
+            const bool r0 = iou_gt(bi, sorted[cb + min(j0, mm - 1)], thr, thr_lo, thr_hi, fast);
+            const bool r1 = iou_gt(bi, sorted[cb + min(j1, mm - 1)], thr, thr_lo, thr_hi, fast);
+            const bool b0 = j0 > il && j0 < mm && r0, b1 = j1 > il && j1 < mm && r1;
             const unsigned lo = __ballot_sync(0xffffffffu, b0), hi = __ballot_sync(0xffffffffu, b1);
             if (lane == 0) Mall[i] = ((unsigned long long)hi << 32) | lo;
         }
@@ -622,53 +622,85 @@ k2_nms_class(NmsArgs args, int nc, const unsigned long long* __restrict__ cand_k
         for (int c0 = 0; c0 < n; c0 += 64) {
             const int m = min(64, n - c0);
             if (warp == 0) {
+                // Greedy pass over the chunk, redundantly in every lane of warp 0.  Row i only holds bits > i, so bit i
+                // of `rem` is final once row i-1 has been applied: the chain per step is {test bit i, OR row i} and the
+                // kept set falls out as ~rem at the end.
                 const unsigned long long m_lo = lane < m ? Mall[c0 + lane] : 0ull;
                 const unsigned long long m_hi = lane + 32 < m ? Mall[c0 + lane + 32] : 0ull;
-                unsigned long long rem = ((unsigned long long)removed[(c0 >> 5) + 1] << 32) | removed[c0 >> 5], keptmask = 0;
-                int kt = s_kept_total;
+                unsigned long long rem = ((unsigned long long)removed[(c0 >> 5) + 1] << 32) | removed[c0 >> 5];
+                if (m < 64) rem |= ~0ull << m;
 #pragma unroll
                 for (int i = 0; i < 64; ++i) {
                     const unsigned long long mi = __shfl_sync(0xffffffffu, i < 32 ? m_lo : m_hi, i & 31);
-                    const bool k = !((rem >> i) & 1ull) && i < m && kt < args.max_det;
-                    keptmask |= (unsigned long long)k << i;
-                    rem |= k ? mi : 0ull;
-                    if (k && lane == 0) kept_list[kt] = c0 + i;
-                    kt += k;
+                    if (!((rem >> i) & 1ull)) rem |= mi;
                 }
+                unsigned long long keptmask = ~rem;
+                const int kt0 = s_kept_total;
+                int room = args.max_det - kt0;                 // only the first max_det kept boxes count
+                while (__popcll(keptmask) > room) keptmask &= ~(1ull << (63 - __clzll((long long)keptmask)));
+                if ((keptmask >> lane) & 1ull) kept_list[kt0 + __popcll(keptmask & ((1ull << lane) - 1ull))] = c0 + lane;
+                if ((keptmask >> (lane + 32)) & 1ull)
+                    kept_list[kt0 + __popcll(keptmask & ((1ull << (lane + 32)) - 1ull))] = c0 + lane + 32;
                 __syncwarp();
-                if (lane == 0) { s_keptmask = keptmask; s_kept_total = kt; }
+                if (lane == 0) { s_keptmask = keptmask; s_kept_total = kt0 + __popcll(keptmask); }
             }
             __syncthreads();
             const unsigned long long keptmask = s_keptmask;
             if (s_kept_total >= args.max_det) break;
             const int nk = __popcll(keptmask);
             if (nk && c0 + 64 < n) {
-                // the chunk's kept boxes, densely packed: the apply loop below reads them at warp-uniform
-                // addresses with no dependency between iterations
+                // the chunk's kept boxes, densely packed, then into registers: lanes hold <= 2 kept boxes each and
+                // every warp walks the later boxes four at a time (loads first, eight branch-light IoU tests, four
+                // votes) -- no dependent chain between boxes
                 if (tid < 64 && ((keptmask >> tid) & 1ull))
                     s_kb[__popcll(keptmask & ((1ull << tid) - 1ull))] = sorted[c0 + tid];
                 __syncthreads();
-                for (int j = c0 + 64 + tid; j < n; j += K2C_THREADS) {
-                    if ((removed[j >> 5] >> (j & 31)) & 1u) continue;
-                    const float4 bj = sorted[j];
-                    bool sup = false;
-                    for (int i = 0; i < nk; ++i) sup |= iou_gt(s_kb[i], bj, thr, thr_lo, thr_hi, fast);
-                    if (sup) atomicOr(&removed[j >> 5], 1u << (j & 31));
+                const bool h0 = lane < nk, h1 = lane + 32 < nk;
+                const float4 k0 = h0 ? s_kb[lane] : make_float4(0.f, 0.f, 0.f, 0.f);
+                const float4 k1 = h1 ? s_kb[lane + 32] : make_float4(0.f, 0.f, 0.f, 0.f);
+                constexpr int NW = K2C_THREADS / 32;
+                for (int j0 = c0 + 64 + warp; j0 < n; j0 += 4 * NW) {
+                    float4 bj[4];
+                    bool live[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int j = j0 + u * NW;
+                        live[u] = j < n && !((removed[j >> 5] >> (j & 31)) & 1u);      // warp-uniform
+                        bj[u] = sorted[min(j, n - 1)];
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const bool s0 = iou_gt(k0, bj[u], thr, thr_lo, thr_hi, fast);
+                        const bool s1 = iou_gt(k1, bj[u], thr, thr_lo, thr_hi, fast);
+                        const bool sup = live[u] && ((h0 && s0) || (h1 && s1));
+                        const int j = j0 + u * NW;
+                        if (__any_sync(0xffffffffu, sup) && lane == 0) atomicOr(&removed[j >> 5], 1u << (j & 31));
+                    }
                 }
             }
             __syncthreads();
         }
         __syncthreads();
+        // ---- publish this class's kept list ------------------------------------------------------------
+        const int kt = s_kept_total;
+        const long long kbase = ((long long)img * nc + cls) * args.max_det;
+        for (int r = tid; r < kt; r += K2C_THREADS) {
+            const int pos = kept_list[r];
+            __stcg(kept_key + kbase + r, keys[pos]);
+            __stcg(kept_box + kbase + r, cand_box[(long long)img * cap + vals[pos]]);      // un-offset box
+        }
+    };
+    if (n > 0) {
+        if (in_smem)
+            core(reinterpret_cast<float4*>(dyn), reinterpret_cast<unsigned long long*>(dyn + (size_t)K2C_SMEM_N * 16),
+                 reinterpret_cast<int*>(dyn + (size_t)K2C_SMEM_N * 24),
+                 reinterpret_cast<unsigned long long*>(dyn + (size_t)K2C_SMEM_N * 28));
+        else
+            core(g_sorted + (long long)img * cap + boff, g_keys + (long long)img * 2 * cap + koff,
+                 g_vals + (long long)img * 2 * cap + koff, g_mall + (long long)img * cap + boff);
     }
-
-    // ---- publish this class's kept list, take a ticket ------------------------------------------------
     const int kt = s_kept_total;
-    const long long kbase = ((long long)img * nc + cls) * args.max_det;
-    for (int r = tid; r < kt; r += K2C_THREADS) {
-        const int pos = kept_list[r];
-        __stcg(kept_key + kbase + r, keys[pos]);
-        __stcg(kept_box + kbase + r, cand_box[(long long)img * cap + vals[pos]]);      // un-offset box
-    }
+    // ---- take a ticket ----------------------------------------------------------------------------------
     if (tid == 0) __stcg(kept_count + img * nc + cls, kt);
     __threadfence();
     __syncthreads();

@@ -71,7 +71,7 @@ class InspectionPipeline:
         self.use_graphs = use_graphs
         self.yolo_g = nets.GraphedNet(self.yolo, self.dev, net_dtype)
         self.resnet_g = nets.GraphedNet(self.resnet, self.dev, net_dtype)
-        self.crop_chunks = (256, 64, 8)      # static ResNet batch sizes (largest first)
+        self.crop_chunks = (256, 128, 64, 32, 16, 8)      # static ResNet batch sizes (largest first)
         self.seg_max_comp = 1024             # first-pass stats rows per ROI (overflowing ROIs are redone)
         self.record = False          # bench.py: CUDA-event pairs around every stage
         self.events = {}
@@ -213,7 +213,8 @@ class InspectionPipeline:
                 parts, o = [], 0
                 while o < nro:
                     rem = nro - o
-                    cs = next((c for c in reversed(self.crop_chunks) if c >= rem), self.crop_chunks[0])
+                    # largest static size that is filled completely; the last few rows round up to the smallest
+                    cs = next((c for c in self.crop_chunks if c <= rem), self.crop_chunks[-1])
                     k = min(cs, rem)
                     shape = (cs, 3, 224, 224)
                     buf = self.resnet_g.input_buffer(shape)
