@@ -95,6 +95,7 @@ template <bool BF16, int NCM>
 __global__ void __launch_bounds__(256)
 k2_filter(LevelTable lt, int nc, int reg_max, float conf, float logit_lo, int cap, int vec_ok,
           unsigned long long* __restrict__ cand_key, int* __restrict__ cand_count) {
+    __shared__ int s_cnt, s_gbase;
     const int img = blockIdx.y;
     const int lane = threadIdx.x & 31;
     const int step = vec_ok ? 4 : 1;                    // anchors per thread per iteration
@@ -147,22 +148,34 @@ k2_filter(LevelTable lt, int nc, int reg_max, float conf, float logit_lo, int ca
                 }
             }
         }
+        // Slot allocation, aggregated per CTA: ballots give every candidate its offset inside the warp, one
+        // shared-memory atomic per warp its offset inside the CTA, and ONE global atomic per CTA the base in the
+        // image's list.  (A returning atomic per warp on the image's single counter serialises ~1000 L2 round trips.)
+        unsigned bm[4];
+        int woff[4], wtot = 0;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            if (j >= step) break;
-            const unsigned m = __ballot_sync(0xffffffffu, is_cand[j]);
-            if (m) {
-                int base_slot = 0;
-                const int leader = __ffs(m) - 1;
-                if (lane == leader) base_slot = atomicAdd(&cand_count[img], __popc(m));
-                base_slot = __shfl_sync(0xffffffffu, base_slot, leader);
-                if (is_cand[j]) {
-                    const int slot = base_slot + __popc(m & ((1u << lane) - 1));
-                    if (slot < cap)
-                        cand_key[(long long)img * cap + slot] =
-                            ((unsigned long long)f2ord_desc(best[j]) << 32) | ((unsigned long long)(a + j) << 8) |
-                            (unsigned long long)best_c[j];
-                }
+            bm[j] = j < step ? __ballot_sync(0xffffffffu, is_cand[j]) : 0u;
+            woff[j] = wtot;
+            wtot += __popc(bm[j]);
+        }
+        if (threadIdx.x == 0) s_cnt = 0;
+        __syncthreads();
+        int wbase = 0;
+        if (lane == 0 && wtot) wbase = atomicAdd(&s_cnt, wtot);
+        wbase = __shfl_sync(0xffffffffu, wbase, 0);
+        __syncthreads();
+        if (threadIdx.x == 0) s_gbase = s_cnt ? atomicAdd(&cand_count[img], s_cnt) : 0;
+        __syncthreads();
+        const int gbase = s_gbase;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (j < step && is_cand[j]) {
+                const int slot = gbase + wbase + woff[j] + __popc(bm[j] & ((1u << lane) - 1));
+                if (slot < cap)
+                    cand_key[(long long)img * cap + slot] =
+                        ((unsigned long long)f2ord_desc(best[j]) << 32) | ((unsigned long long)(a + j) << 8) |
+                        (unsigned long long)best_c[j];
             }
         }
     }

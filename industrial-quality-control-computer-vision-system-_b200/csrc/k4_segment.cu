@@ -452,6 +452,26 @@ __device__ __forceinline__ void suf_union(int* L, int a, int b) {
     } while (!done);
 }
 
+// 16 bytes from an arbitrary address inside the gray workspace: two aligned 128-bit loads, a 4-way word select and
+// one funnel shift per word.  Reads up to 31 bytes past p -- always inside the workspace (rows are contiguous and the
+// carve rounds the gray region up to 256 bytes in front of the next array).
+__device__ __forceinline__ uint4 ld16_any(const uint8_t* p) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const uint4* q = reinterpret_cast<const uint4*>(a & ~(uintptr_t)15);
+    const unsigned off = (unsigned)(a & 15);
+    const uint4 v0 = q[0];
+    if (off == 0) return v0;
+    const uint4 v1 = q[1];
+    const unsigned ws = off >> 2, bs = (off & 3u) * 8u;
+    const unsigned s0 = ws == 0 ? v0.x : ws == 1 ? v0.y : ws == 2 ? v0.z : v0.w;
+    const unsigned s1 = ws == 0 ? v0.y : ws == 1 ? v0.z : ws == 2 ? v0.w : v1.x;
+    const unsigned s2 = ws == 0 ? v0.z : ws == 1 ? v0.w : ws == 2 ? v1.x : v1.y;
+    const unsigned s3 = ws == 0 ? v0.w : ws == 1 ? v1.x : ws == 2 ? v1.y : v1.z;
+    const unsigned s4 = ws == 0 ? v1.x : ws == 1 ? v1.y : ws == 2 ? v1.z : v1.w;
+    return make_uint4(__funnelshift_r(s0, s1, bs), __funnelshift_r(s1, s2, bs), __funnelshift_r(s2, s3, bs),
+                      __funnelshift_r(s3, s4, bs));
+}
+
 // threshold -> morphology -> global bit rows (small shared-memory footprint: many CTAs per SM)
 __global__ void __launch_bounds__(K4_THREADS)
 k4_mask(Img im, const qc_seg_region* __restrict__ regs, int R, int total_bands,
@@ -483,49 +503,58 @@ k4_mask(Img im, const qc_seg_region* __restrict__ regs, int R, int total_bands,
         const int segs = 2 * wpr;                     // 16-pixel segments per row (last ones may be partial/empty)
         const unsigned lo4 = (unsigned)min(lo, 255) * 0x01010101u, hi4 = (unsigned)max(hi, 0) * 0x01010101u;
         const bool none = lo > 255 || hi < 0 || lo > hi;     // empty foreground interval
-        for (int yy = warp; yy < nrows; yy += K4_THREADS / 32) {
-            const uint8_t* p = gbase + (long long)(row_lo + yy) * gpitch;
-            const bool al = (reinterpret_cast<uintptr_t>(p) & 15) == 0;
-            // four 16-pixel segments per lane per round: all 128-bit loads of the round are issued before the first
-            // compare, so a warp keeps 2 KB in flight instead of waiting out one DRAM latency per 512 B
-            for (int s0 = 0; s0 < segs; s0 += 128) {
-                uint4 v[4];
-                bool fastp[4];
+        // work items = (row, 16-pixel segment), flattened so that narrow regions (a 150-px ROI row is 10 segments)
+        // still fill the warp; a warp takes 128 consecutive items per round and issues its four 128-bit loads
+        // before the first compare.  segs is even, so the two halves of a 32-pixel word sit in adjacent lanes.
+        const int nitems = nrows * segs;
+        const float inv_segs = 1.0f / (float)segs;
+        for (int t0 = warp * 128; t0 < nitems; t0 += (K4_THREADS / 32) * 128) {
+            uint4 v[4];
+            bool fastp[4];
+            int yy_[4], sg_[4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int sg = s0 + 32 * j + lane, x0 = sg * 16;
-                    fastp[j] = sg < segs && !none && al && x0 + 16 <= rg.w;
-                    if (fastp[j])
-                        v[j] = im.channels == 3 ? *reinterpret_cast<const uint4*>(p + x0)
-                                                : __ldg(reinterpret_cast<const uint4*>(p + x0));
-                }
+            for (int j = 0; j < 4; ++j) {
+                const int t = t0 + 32 * j + lane;
+                int yy = (int)(((float)t + 0.5f) * inv_segs);                // t / segs (exact: t < 2^20)
+                const int sg = t - yy * segs, x0 = sg * 16;
+                yy_[j] = yy; sg_[j] = sg;
+                const uint8_t* p = gbase + (long long)(row_lo + yy) * gpitch;
+                const bool al = (reinterpret_cast<uintptr_t>(p) & 15) == 0;
+                // gray workspace rows (RGB input): any alignment, partial tail segments included (the bits past
+                // the row end are cleared below); caller's gray image: aligned full segments only
+                fastp[j] = t < nitems && !none && x0 < rg.w && (im.channels == 3 || (al && x0 + 16 <= rg.w));
+                if (fastp[j])
+                    v[j] = im.channels == 3 ? ld16_any(p + x0) : __ldg(reinterpret_cast<const uint4*>(p + x0));
+            }
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int sg = s0 + 32 * j + lane, x0 = sg * 16;
-                    if (s0 + 32 * j >= segs) break;            // warp-uniform
-                    unsigned b16 = 0;
-                    if (fastp[j]) {
-                        // per-byte compares (0xFF where lo <= g <= hi), then 4 mask bytes -> 4 bits with one
-                        // multiply: bytes at bit 0/8/16/24 land on bits 24..27 of t * 0x01020408
-                        const unsigned w4[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+            for (int j = 0; j < 4; ++j) {
+                if (t0 + 32 * j >= nitems) break;            // warp-uniform
+                const int t = t0 + 32 * j + lane;
+                const int yy = yy_[j], sg = sg_[j], x0 = sg * 16;
+                unsigned b16 = 0;
+                if (fastp[j]) {
+                    // per-byte compares (0xFF where lo <= g <= hi), then 4 mask bytes -> 4 bits with one
+                    // multiply: bytes at bit 0/8/16/24 land on bits 24..27 of t * 0x01020408
+                    const unsigned w4[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            // the interval is one-sided in practice ([lo,255] light, [0,hi] dark): one compare
-                            unsigned mk = hi >= 255 ? __vsetgeu4(w4[q], lo4)
-                                        : lo <= 0   ? __vsetleu4(w4[q], hi4)
-                                                    : (__vsetgeu4(w4[q], lo4) & __vsetleu4(w4[q], hi4));
-                            b16 |= ((mk * 0x01020408u) >> 24) << (4 * q);
-                        }
-                    } else if (sg < segs && x0 < rg.w && !none) {
-                        const int nv = min(16, rg.w - x0);
-                        for (int k = 0; k < nv; ++k) {
-                            const int g = (int)p[x0 + k];
-                            b16 |= (unsigned)(g >= lo && g <= hi) << k;
-                        }
+                    for (int q = 0; q < 4; ++q) {
+                        // the interval is one-sided in practice ([lo,255] light, [0,hi] dark): one compare
+                        unsigned mk = hi >= 255 ? __vsetgeu4(w4[q], lo4)
+                                    : lo <= 0   ? __vsetleu4(w4[q], hi4)
+                                                : (__vsetgeu4(w4[q], lo4) & __vsetleu4(w4[q], hi4));
+                        b16 |= ((mk * 0x01020408u) >> 24) << (4 * q);
                     }
-                    const unsigned hi16 = __shfl_down_sync(0xffffffffu, b16, 1);
-                    if (!(lane & 1) && sg < segs) bufA[yy * wpr + (sg >> 1)] = b16 | (hi16 << 16);
+                    if (x0 + 16 > rg.w) b16 &= (1u << (rg.w - x0)) - 1u;
+                } else if (t < nitems && x0 < rg.w && !none) {
+                    const uint8_t* p = gbase + (long long)(row_lo + yy) * gpitch;
+                    const int nv = min(16, rg.w - x0);
+                    for (int k = 0; k < nv; ++k) {
+                        const int g = (int)p[x0 + k];
+                        b16 |= (unsigned)(g >= lo && g <= hi) << k;
+                    }
                 }
+                const unsigned hi16 = __shfl_down_sync(0xffffffffu, b16, 1);
+                if (!(lane & 1) && t < nitems) bufA[yy * wpr + (sg >> 1)] = b16 | (hi16 << 16);
             }
         }
         __syncthreads();
