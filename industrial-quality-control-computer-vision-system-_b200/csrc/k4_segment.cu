@@ -36,14 +36,16 @@
 namespace {
 
 constexpr int K4_THREADS = 256;
-// Pixel rows per band, chosen per region so rows x words-per-row stays ~1024 (constant shared-memory footprint):
-// 16 rows for a 2048-px-wide frame, 96 rows for a 300-px ROI, the whole ROI for most detections -- the per-band
-// fixed costs (barriers, region lookup, flushes) are paid once per ~32K pixels whatever the region shape.
-constexpr int K4_BAND_RW = 1024;
+// Pixel rows per band, chosen per region so rows x words-per-row stays ~512 (bounded shared-memory footprint):
+// 16 rows for a 2048-px-wide frame, 48 rows for a 300-px ROI, 96 rows for a 150-px ROI -- the per-band fixed costs
+// (barriers, region lookup, flushes) are paid once per ~16K pixels whatever the region shape, and the band-local
+// union-find trees stay shallow enough for 8 CTAs per SM to hide their shared-memory latency.
+constexpr int K4_BAND_RW = 512;
+constexpr int K4_MIN_ROWS = 16;      // (32 was tried for wide frames: mask and border gain what ccl_local loses to occupancy)
 __host__ __device__ inline int k4_band_rows(int w) {
     const int wpr = (w + 31) >> 5;
     const int r = (K4_BAND_RW / wpr) & ~15;
-    return r < 16 ? 16 : (r > 512 ? 512 : r);
+    return r < K4_MIN_ROWS ? K4_MIN_ROWS : (r > 512 ? 512 : r);
 }
 constexpr int K4_CHUNK = 256;        // word cells (16 blocks each) per ranking chunk
 
@@ -666,12 +668,13 @@ k4_ccl_local(const qc_seg_region* __restrict__ regs, int R, int total_bands, con
         }
         __syncthreads();
         const int nne = s_ncell;
-        // (2) unions: one thread per non-empty cell, one union per (run, upper run) contact.  Everything is bit
-        // arithmetic on the cell's words in the "even-bit" domain (bit 2k <-> block k): FB = foreground blocks,
-        // LK = block k linked to block k-1, heads = FB & ~LK.  For a run, the top-row pixels m are dilated by
-        // one pixel and intersected with the row above (u): every maximal group of contacted upper blocks that
-        // are themselves linked belongs to one upper run and costs a single union.
-        for (int it = tid; it < nne; it += K4_THREADS) {
+        // (2) links: one thread per non-empty cell, one contact per (run, upper run).  Everything is bit arithmetic
+        // on the cell's words in the "even-bit" domain (bit 2k <-> block k): FB = foreground blocks, LK = block k
+        // linked to block k-1, heads = FB & ~LK.  For a run, the top-row pixels m are dilated by one pixel and
+        // intersected with the row above (u): every maximal group of contacted upper blocks that are themselves
+        // linked belongs to one upper run and yields a single contact.  visit(it, fn) calls fn(head, target, first)
+        // for every contact of every run of cell `it` (targets always have a smaller index than the head).
+        auto visit = [&](int it, auto&& fn) {
             const int ce = cell_list[it];
             const int byy = ce >> 8, wx = ce & 255;
             const unsigned r0 = rowword(2 * byy, wx), r1 = rowword(2 * byy + 1, wx);
@@ -696,9 +699,10 @@ k4_ccl_local(const qc_seg_region* __restrict__ regs, int R, int total_bands, con
                 const unsigned below_next = HB ? ((HB & (0u - HB)) - 1u) : 0xFFFFFFFFu;
                 const unsigned RB = FB & below_next & ~((1u << b0) - 1u);    // blocks of this run
                 const int head = base + (b0 >> 1);
+                bool first = true;
                 if (b0 == 0 && (v & 1u)) {                               // run continues from the previous word
                     const unsigned vl = (rowword(2 * byy, wx - 1) | rowword(2 * byy + 1, wx - 1)) >> 31;
-                    if (vl) suf_union(lab, head, head - 1);
+                    if (vl) { fn(head, head - 1, first); first = false; }
                 }
                 if (byy == 0) continue;
                 const unsigned m = r0 & (RB * 3u);                       // top-row pixels of the run
@@ -710,14 +714,43 @@ k4_ccl_local(const qc_seg_region* __restrict__ regs, int R, int total_bands, con
                 while (CN) {
                     const int kk = (__ffs(CN) - 1) >> 1;
                     CN &= CN - 1;
-                    suf_union(lab, head, upb + kk);
+                    fn(head, upb + kk, first);
+                    first = false;
                 }
                 // contacts in the neighbouring words (pixel -1 / pixel 32 of the row above), unless the upper block
                 // next to them is contacted too and linked to them
-                if ((m & 1u) && uL && !((CB & 1u) && (vu & 1u) && vuL)) suf_union(lab, head, upb - 1);
-                if ((m >> 31) && uR && !((CB >> 30) && (vu >> 31) && vuR)) suf_union(lab, head, upb + 16);
+                if ((m & 1u) && uL && !((CB & 1u) && (vu & 1u) && vuL)) { fn(head, upb - 1, first); first = false; }
+                if ((m >> 31) && uR && !((CB >> 30) && (vu >> 31) && vuR)) { fn(head, upb + 16, first); first = false; }
             }
+        };
+        // (2a) every run adopts its first contact as parent with a plain store (targets have smaller indices: a
+        // forest) -- in dense regions this already links almost everything, without a single atomic
+        for (int it = tid; it < nne; it += K4_THREADS)
+            visit(it, [&](int head, int target, bool first) { if (first) lab[head] = target; });
+        __syncthreads();
+        // (2b) pointer jumping over the run heads until every head points at a root (chains are as long as the band
+        // is tall; each round halves them)
+        for (;;) {
+            int changed = 0;
+            for (int it = tid; it < nne; it += K4_THREADS) {
+                const int ce = cell_list[it];
+                const int byy = ce >> 8, wx = ce & 255;
+                const unsigned v = rowword(2 * byy, wx) | rowword(2 * byy + 1, wx);
+                unsigned HB = ((v | (v >> 1)) & 0x55555555u) & ~(v & (v << 1) & 0x55555555u);
+                const int base = byy * bwp + wx * 16;
+                while (HB) {
+                    const int h = base + ((__ffs(HB) - 1) >> 1);
+                    HB &= HB - 1;
+                    const int pp = lab[h];
+                    const int g = lab[pp];
+                    if (g != pp) { lab[h] = g; changed = 1; }
+                }
+            }
+            if (!__syncthreads_or(changed)) break;
         }
+        // (2c) the remaining contacts: unions on trees that are now one or two levels deep; most find equal roots
+        for (int it = tid; it < nne; it += K4_THREADS)
+            visit(it, [&](int head, int target, bool first) { if (!first) suf_union(lab, head, target); });
         __syncthreads();
         // (3a) compress the run heads (one thread per non-empty cell): every ancestor of a block is a run head, so
         // after this pass a block reaches its root in two hops and the per-block pass below needs no loop
@@ -1035,10 +1068,22 @@ k4_final(const qc_seg_region* __restrict__ regs, int R, int total_bands, const i
         const int* st = stats + (long long)rg.stats_offset * 5;
         const int* P = parent + rg.blk_offset;
         int kept = 0;
+        // No pixel outputs wanted and every component has a stats row: the kept area is the sum of the recorded
+        // areas that pass the min-area filter -- one CTA per region sums <= max_comp rows instead of every band
+        // re-reading its pixels (the detection-ROI mode of the pipeline).
+        const bool light = !out_mask && !out_labels && ncomp[s_r] <= rg.max_comp;
+        if (light) {
+            if (y0 != 0) continue;
+            const int rows = ncomp[s_r];
+            for (int k = 1 + tid; k < rows; k += K4_THREADS) {
+                const int a = st[(long long)k * 5 + 4];
+                kept += a >= rg.min_area ? a : 0;
+            }
+        }
         // warp per pixel row, 4 consecutive pixels per lane; background quads (the vast majority) take a
         // branch-light path that only stores zeros
         const bool al = ((rg.out_offset & 3) == 0) && ((rg.w & 3) == 0);
-        for (int y = y0 + warp; y < y1; y += K4_THREADS / 32) {
+        for (int y = y0 + warp; y < y1 && !light; y += K4_THREADS / 32) {
             const unsigned* Brow = B + (long long)y * wpr;
             const int* prow_y = P + (long long)(y >> 1) * bw;
             const long long orow = rg.out_offset + (long long)y * rg.w;
@@ -1183,7 +1228,7 @@ extern "C" int qc_segment(qc_ctx* ctx, const uint8_t* imgs, const qc_seg_params*
     if (wpr_max > 256)      // k4_ccl_local packs (block row, word) of a cell into 8+8 bits
         QC_FAIL(ctx, QC_ERR_UNSUPPORTED, "qc_segment: region width %d > 8192", p->max_region_w);
     // conservative bounds over every region: rows x words <= RW whatever the region width
-    const int RW = std::max(K4_BAND_RW, 16 * wpr_max);
+    const int RW = std::max(K4_BAND_RW, K4_MIN_ROWS * wpr_max);
     const int buf_words = RW + 2 * halo * wpr_max;
     const size_t smem_mask = (size_t)buf_words * 4 * 2;
     const int band_words = (RW + 2 * 512 + 2 * wpr_max + 4 + 3) & ~3;
