@@ -135,11 +135,13 @@ k3_roi_sep(const uint8_t* __restrict__ imgs, int n, int H, int W, long long img_
 #pragma unroll
     for (int c = 0; c < 3; ++c) { ri[c] = __fdiv_rn(__fdiv_rn(1.f, count), nd[c]); rs[c] = __fdiv_rn(1.f, ns[c]); }
     // out = ((acc/count)/div - mean)/std.  Reciprocal multiplies differ from the reference's divisions by a few
-    // float32 ulps, harmless except where q - mean cancels; there (|d| < 2^-10, ~0.05% of values) the exact
-    // divisions are replayed so the result stays within 1 bf16 ulp of the reference's rounding sequence.
+    // float32 ulps of q = acc/count/div (|q| <= 1: ~1e-7 absolute), harmless except where q - mean cancels: the
+    // relative error of d is ~1e-7/|d|, so for |d| >= 2^-14 it stays below 2e-3 relative -- inside 1 bf16 ulp
+    // (2^-8) and far inside the 1e-3 absolute float32 tolerance.  Below that (~0.01% of values) the exact
+    // divisions are replayed.
     auto finish = [&](float acc, int c) -> float {
         float d = __fsub_rn(__fmul_rn(acc, ri[c]), nm[c]);
-        if (fabsf(d) < 9.765625e-4f) d = __fsub_rn(__fdiv_rn(__fdiv_rn(acc, count), nd[c]), nm[c]);
+        if (fabsf(d) < 6.103515625e-5f) d = __fsub_rn(__fdiv_rn(__fdiv_rn(acc, count), nd[c]), nm[c]);
         return __fmul_rn(d, rs[c]);
     };
     auto finish_exact = [&](float acc, int c) -> float {

@@ -134,7 +134,8 @@ __global__ void k4_init(const qc_seg_region* __restrict__ regs, int R, unsigned*
 // registers).  Every CTA owns a CONTIGUOUS range of bands and flushes its tables to the global histogram only
 // when the region changes (or before a counter could overflow), so the zero/reduce cost is paid per region,
 // not per band -- which matters for detection ROIs (thousands of tiny bands).
-constexpr int K4_HIST_SMEM = (K4_THREADS / 32) * 256 * 32 * 2;   // 128 KB
+constexpr int K4_HIST_THREADS = 384;                             // 12 warps: the kernel is latency-bound, one CTA per SM
+constexpr int K4_HIST_SMEM = (K4_HIST_THREADS / 32) * 256 * 32 * 2;   // 192 KB
 constexpr int K4_HIST_FLUSH_PX = 4 << 20;                        // u16 safety: <= 16K pixels per lane between flushes
 
 // RGB -> gray (cv2 fixed point) into the region-packed gray workspace; plain high-occupancy kernel so the
@@ -227,7 +228,7 @@ __device__ __forceinline__ void hist_span(const uint8_t* __restrict__ p, int len
     for (int x = head + nvec * 16 + lane; x < len; x += 32) tab[(unsigned)__ldg(p + x) << 5]++;
 }
 
-__global__ void __launch_bounds__(K4_THREADS)
+__global__ void __launch_bounds__(K4_HIST_THREADS)
 k4_hist(Img im, const qc_seg_region* __restrict__ regs, int R, int total_bands, const int* __restrict__ g_band_off,
         unsigned* __restrict__ hist, const uint8_t* __restrict__ gray_ws) {
     extern __shared__ __align__(16) unsigned char hsm[];
@@ -241,11 +242,11 @@ k4_hist(Img im, const qc_seg_region* __restrict__ regs, int R, int total_bands, 
     };
     auto flush = [&](int r) {          // all threads; tables -> global histogram of region r, then cleared
         __syncthreads();
-        const int bin = tid;           // K4_THREADS == 256 bins
+        const int bin = tid & 255;     // the first 256 threads own one bin each
         unsigned sum = 0;
         const unsigned* t32 = reinterpret_cast<const unsigned*>(hsm);
 #pragma unroll
-        for (int w = 0; w < K4_THREADS / 32; ++w) {
+        for (int w = 0; w < K4_HIST_THREADS / 32; ++w) {
 #pragma unroll
             for (int k = 0; k < 16; ++k) {
                 // word j of row `bin`: rotate by bin>>1 so the 32 bins of a warp hit 32 banks
@@ -253,7 +254,7 @@ k4_hist(Img im, const qc_seg_region* __restrict__ regs, int R, int total_bands, 
                 sum += (v & 0xFFFFu) + (v >> 16);
             }
         }
-        if (sum) atomicAdd(&hist[(long long)r * 256 + bin], sum);
+        if (tid < 256 && sum) atomicAdd(&hist[(long long)r * 256 + bin], sum);
         __syncthreads();
         zero();
         __syncthreads();
@@ -277,13 +278,13 @@ k4_hist(Img im, const qc_seg_region* __restrict__ regs, int R, int total_bands, 
         const int y0 = b0 * BR, y1 = min(b1 * BR, rg.h);
         if (im.channels == 1) {
             const uint8_t* ibase = im.data + (long long)rg.img * im.img_stride;
-            for (int y = y0 + warp; y < y1; y += K4_THREADS / 32)
+            for (int y = y0 + warp; y < y1; y += K4_HIST_THREADS / 32)
                 hist_span(ibase + (long long)(rg.y + y) * im.row_stride + rg.x, rg.w, tab, lane);
         } else {
             // region-packed gray copy: the rows are one contiguous span, cut into 2 KB pieces for the 8 warps
             const uint8_t* p = gray_ws + rg.out_offset + (long long)y0 * rg.w;
             const long long len = (long long)(y1 - y0) * rg.w;
-            for (long long c0 = (long long)warp * 2048; c0 < len; c0 += (K4_THREADS / 32) * 2048)
+            for (long long c0 = (long long)warp * 2048; c0 < len; c0 += (K4_HIST_THREADS / 32) * 2048)
                 hist_span(p + c0, (int)min(2048ll, len - c0), tab, lane);
         }
         flush(r);
@@ -1215,8 +1216,8 @@ extern "C" int qc_segment(qc_ctx* ctx, const uint8_t* imgs, const qc_seg_params*
         k4_gray<<<std::min(p->total_bands, sms * 8), K4_THREADS, 0, st>>>(im, regions, R, p->total_bands, w.band_off, w.gray);
         QC_LAUNCHED(ctx);
     }
-    if (int rc = qc_prepare(ctx, k4_hist, K4_HIST_SMEM, K4_THREADS, nullptr)) return rc;
-    k4_hist<<<std::min(p->total_bands, sms), K4_THREADS, K4_HIST_SMEM, st>>>(im, regions, R, p->total_bands, w.band_off,
+    if (int rc = qc_prepare(ctx, k4_hist, K4_HIST_SMEM, K4_HIST_THREADS, nullptr)) return rc;
+    k4_hist<<<std::min(p->total_bands, sms), K4_HIST_THREADS, K4_HIST_SMEM, st>>>(im, regions, R, p->total_bands, w.band_off,
                                                                           w.hist, w.gray);
     QC_LAUNCHED(ctx);
 
