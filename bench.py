@@ -6,8 +6,8 @@
         --master-port P bench.py --gpus N --steps K --warmup W
 
 Workload (BASELINE.json configs[1], "cfg2"): YOLOv8s + ResNet-50, 64 synthetic 640x640 RGB frames
-per GPU per step; a step = K1 preprocess -> YOLOv8s -> K2 decode+NMS -> K3 ROI-align -> ResNet-50 on
-the whole frames and every kept ROI -> K4 segmentation of every kept ROI -> K5 SPC vector
+per GPU per step; a step = K1 preprocess -> YOLOv8s -> K2 decode+NMS -> K3b PIL-exact whole-frame resize +
+K3 ROI-align of every kept box -> ResNet-50 on both -> K4 segmentation of every kept ROI -> K5 SPC vector
 (+ NCCL all-reduce of that 72-byte vector when N > 1).  Detections come from injected head logits
 (random-init Detect heads fire nothing).  Weak scaling: every rank processes its own
 64 frames per step, no data-path collective.
@@ -19,7 +19,7 @@ One JSON line on stdout (rank 0):
             step's frames and the D2H reads of its results are inside the timed region
   roofline  the dominant hand-written kernel of the step (K1: most bytes), algorithmic bytes /
             its CUDA-event duration measured in the timed region, vs MEASURED_PEAKS.json
-  kernels   per-kernel achieved GB/s on their own BASELINE configs (K1 cfg2, K2 cfg3, K3, K4 cfg4),
+  kernels   per-kernel achieved GB/s on their own BASELINE configs (K1 cfg2, K2 cfg3, K3, K3b, K4 cfg4),
             measured after the timed region with L2-defeating rotation
   cpu_baseline  the oracle port of the reference CPU path on the host cores (bounded sample)
 --impl reference times only that CPU path (rank 0; other ranks exit).
@@ -49,7 +49,7 @@ IMGSZ = 640
 CANDS_PER_IMAGE = 30
 NC = 5
 WORKLOAD = ("cfg2: YOLOv8s + ResNet-50, 64 synthetic 640x640 RGB frames per GPU per step, "
-            "~30 injected candidates/image, K1->YOLOv8s->K2->K3->ResNet-50->K4->K5")
+            "~30 injected candidates/image, K1->YOLOv8s->K2->K3b+K3->ResNet-50->K4->K5")
 
 
 def measured_peaks():
@@ -278,7 +278,7 @@ def _mb_k4(qc, peak, rng, time_call, out):
     by = 16 * 6 * 2048 * 2048 + 20 * ncomp
     out["k4_segment_cfg4"] = {"bytes": by, "ms": med, "gbs": by / med / 1e6, "frac": by / med / 1e6 / peak,
                               "components": ncomp,
-                              "note": "10 launches; union-find merge/rank phases are L2/atomic-bound"}
+                              "note": "11 launches; union-find merge/rank phases are L2 / shared-memory latency bound"}
 
 
 _REAL_STDOUT = None
