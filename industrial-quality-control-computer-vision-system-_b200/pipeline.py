@@ -75,6 +75,10 @@ class InspectionPipeline:
         self.seg_max_comp = 1024             # first-pass stats rows per ROI (overflowing ROIs are redone)
         self.record = False          # bench.py: CUDA-event pairs around every stage
         self.events = {}
+        # host frames: H2D on a copy stream into one of two staging buffers, so the copy of batch i+1 overlaps the
+        # compute of batch i (run_async is called before the previous batch is finalised)
+        self.copy_stream = torch.cuda.Stream(self.dev)
+        self._stage = {}             # (shape) -> [buffers, free events, next index]
 
     class _Timed:
         def __init__(self, pipe, name):
@@ -166,6 +170,9 @@ class InspectionPipeline:
                   keep_seg_tensors: bool = False, morph_iters: int = 1, min_area: int = 20) -> "PendingResult":
         qc = self.qc
         seg_cap = regs = None
+        stage_slot = None
+        if not frames.is_cuda:
+            frames, stage_slot = self._upload(frames)
         n, h, w = frames.shape[:3]
         det_d, anchor_d, count_d, _ = self.detect(frames, inject, head_override)
         spc_d = qc.spc_stats(det_d, count_d)
@@ -256,9 +263,31 @@ class InspectionPipeline:
             host["area"], host["thr"], host["ncomp"] = stage(seg["area"]), stage(seg["thr"]), stage(seg["ncomp"])
         done = torch.cuda.Event()
         done.record()
+        if stage_slot is not None:
+            stage_slot[1] = done         # the staging buffer may be overwritten once this batch's kernels are done
         return PendingResult(self, res, frames, host, done, dict(K=K, n=n, seg=seg, seg_cap=seg_cap if seg is not None else None,
                                                                  regs=regs if seg is not None else None,
                                                                  morph_iters=morph_iters, keep=keep_seg_tensors))
+
+    def _upload(self, host_frames: torch.Tensor):
+        """uint8 [n,h,w,3] host tensor (pinned for a truly asynchronous copy) -> device staging buffer; the compute
+        stream waits for the copy, the copy waits for the last batch that read the buffer."""
+        key = tuple(host_frames.shape)
+        st = self._stage.get(key)
+        if st is None:
+            st = self._stage[key] = {"slots": [[torch.empty(key, dtype=torch.uint8, device=self.dev), None]
+                                               for _ in range(2)], "next": 0}
+        slot = st["slots"][st["next"]]
+        st["next"] ^= 1
+        cur = torch.cuda.current_stream(self.dev)
+        with torch.cuda.stream(self.copy_stream):
+            if slot[1] is not None:
+                self.copy_stream.wait_event(slot[1])
+            slot[0].copy_(host_frames, non_blocking=True)
+            ready = torch.cuda.Event()
+            ready.record(self.copy_stream)
+        cur.wait_event(ready)
+        return slot[0], slot
 
     def run(self, frames: torch.Tensor, **kw) -> BatchResult:
         """Synchronous form: one batch in, host-side BatchResult out."""

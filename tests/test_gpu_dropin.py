@@ -139,4 +139,28 @@ def test_batched_pipeline_matches_cpu_reference_pipeline(graphs):
             p_ref = ref["detections"][r["detection_id"]]["roi_class_probabilities"]
             assert np.abs(res.roi_probs[kk] - p_ref).max() < 2e-2
         k0 += len(sel)
+        # whole-frame classifier: K3b feeds the net the reference's exact PIL/ToTensor/Normalize tensor (bit-exact in
+        # tests/test_gpu_k3b_resize.py); the probabilities differ by the GPU conv arithmetic (TF32) only
+        gref = np.array([ref["global_classification"]["class_probabilities"][c] for c in oyh.CLASS_NAMES])
+        assert np.abs(res.global_probs[i] - gref).max() < 2e-2
     assert res.spc[0] == n and res.spc[1] == res.count.sum()
+
+
+def test_pipeline_host_frames_and_stats_only_area():
+    """The public call with pinned HOST frames (H2D on the pipeline's copy stream, two staging buffers) and without
+    pixel outputs (kept area from the stats rows) returns what the resident / full-output form returns."""
+    from qcgraft import synth
+    from qcgraft.pipeline import InspectionPipeline
+    pipe = InspectionPipeline("n", 5, device=0, use_graphs=False, net_dtype=torch.float32)
+    batches = [synth.make_frames(710 + 10 * b, 4) for b in range(3)]
+    heads = [synth.make_head(720 + b, 4, 640, 640, 25) for b in range(3)]
+    full = [pipe.run(torch.from_numpy(f).cuda(), head_override=[l.cuda() for l in h], keep_seg_tensors=True)
+            for f, h in zip(batches, heads)]
+    pend = [pipe.run_async(torch.from_numpy(f).pin_memory(), head_override=[l.cuda() for l in h])
+            for f, h in zip(batches, heads)]                     # three batches in flight over two staging buffers
+    for a, p in zip(full, pend):
+        b = p.result()
+        assert np.array_equal(a.det, b.det) and np.array_equal(a.count, b.count)
+        assert np.array_equal(a.seg_area, b.seg_area) and np.array_equal(a.seg_thr, b.seg_thr)
+        assert np.array_equal(a.seg_ncomp, b.seg_ncomp) and np.allclose(a.roi_probs, b.roi_probs, atol=1e-6)
+        assert np.array_equal(a.spc, b.spc)
