@@ -122,9 +122,11 @@ __global__ void k4_init(const qc_seg_region* __restrict__ regs, int R, unsigned*
     }
     for (int i = gid; i < R * 256; i += gsz) hist[i] = 0;
     for (int i = gid; i < R; i += gsz) out_area[i] = 0;
-    for (int i = gid; i < total_stats_rows; i += gsz) {
-        int* s = stats + (long long)i * 5;
-        s[0] = INT_MAX; s[1] = INT_MAX; s[2] = -1; s[3] = -1; s[4] = 0;   // minx, miny, maxx, maxy, area
+    // rows of (minx, miny, maxx, maxy, area) = (INT_MAX, INT_MAX, -1, -1, 0), written as one coalesced int stream
+    const long long nints = (long long)total_stats_rows * 5;
+    for (long long i = gid; i < nints; i += gsz) {
+        const int c = (int)(i % 5);
+        stats[i] = c < 2 ? INT_MAX : (c < 4 ? -1 : 0);
     }
 }
 
