@@ -104,10 +104,9 @@ k3_roi_sep(const uint8_t* __restrict__ imgs, int n, int H, int W, long long img_
     constexpr int sr = SR;
     extern __shared__ __align__(16) float k3sm[];
     float* Hs = k3sm;                                        // [rows_max][3][PW]
-    int* xlo = reinterpret_cast<int*>(Hs + (size_t)rows_max * 3 * PW);   // [PW*sr]
-    int* xhi = xlo + PW * sr;
-    float* wlo = reinterpret_cast<float*>(xhi + PW * sr);
-    float* whi = wlo + PW * sr;
+    // x taps, one 16-byte entry per (output column, sample): (byte offset of xl, byte offset of xh, 1-lx, lx)
+    float4* tap4 = reinterpret_cast<float4*>(                                     // [PW*sr], 16-byte aligned
+        (reinterpret_cast<uintptr_t>(Hs + (size_t)rows_max * 3 * PW) + 15) & ~(uintptr_t)15);
 
     const int k = blockIdx.y;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -168,7 +167,7 @@ k3_roi_sep(const uint8_t* __restrict__ imgs, int n, int H, int W, long long img_
             lx = __fsub_rn(x, (float)xl);
             hx = __fsub_rn(1.f, lx);
         }
-        xlo[t] = xl * 3; xhi[t] = xh * 3; wlo[t] = hx; whi[t] = lx;
+        tap4[t] = make_float4(__int_as_float(xl * 3), __int_as_float(xh * 3), hx, lx);
     }
     __syncthreads();
     // the band is processed in sub-bands small enough for their source rows to fit in shared memory
@@ -230,10 +229,10 @@ k3_roi_sep(const uint8_t* __restrict__ imgs, int n, int H, int W, long long img_
             for (int pw = lane; pw < PW; pw += 32) {
                 float a0 = 0.f, a1 = 0.f, a2 = 0.f;
                 for (int ix = 0; ix < sr; ++ix) {
-                    const int t = pw * sr + ix;
-                    const uint8_t* pl = row + xlo[t];
-                    const uint8_t* ph_ = row + xhi[t];
-                    const float wl = wlo[t], wh = whi[t];
+                    const float4 tp = tap4[pw * sr + ix];
+                    const uint8_t* pl = row + __float_as_int(tp.x);
+                    const uint8_t* ph_ = row + __float_as_int(tp.y);
+                    const float wl = tp.z, wh = tp.w;
                     a0 = __fmaf_rn(wl, (float)__ldg(pl + 0), __fmaf_rn(wh, (float)__ldg(ph_ + 0), a0));
                     a1 = __fmaf_rn(wl, (float)__ldg(pl + 1), __fmaf_rn(wh, (float)__ldg(ph_ + 1), a1));
                     a2 = __fmaf_rn(wl, (float)__ldg(pl + 2), __fmaf_rn(wh, (float)__ldg(ph_ + 2), a2));
@@ -361,7 +360,7 @@ extern "C" int qc_roi_align(qc_ctx* ctx, const uint8_t* imgs, int n, int h, int 
         const size_t per_row = (size_t)3 * out_w * 4;
         if (tap_bytes + 8 * per_row <= budget) {
             if (tap_bytes + rows_max * per_row > budget) rows_max = (long long)((budget - tap_bytes) / per_row);
-            const size_t smem = tap_bytes + (size_t)rows_max * per_row;
+            const size_t smem = tap_bytes + (size_t)rows_max * per_row + 16;    // + alignment slack of the tap table
             dim3 grid((unsigned)((out_h + K3_BH - 1) / K3_BH), (unsigned)K);
 #define K3_LAUNCH(T, S)                                                                                        \
     do {                                                                                                       \
