@@ -19,13 +19,15 @@
 //                recurrence only when the maximum is not decisive (ties / plateaus)
 //   k4_mask      threshold (128-bit loads, SIMD byte compares) -> bit-packed rows in smem -> close/open
 //                (4*iters cross steps with halo) -> global bit rows (1 bit/pixel)
-//   k4_ccl_local band-local 2x2-block union-find in shared memory (one thread per 32-px word)
+//   k4_ccl_local band-local 2x2-block union-find in shared memory: bit-parallel run contacts per 32-px word,
+//                first-contact links + pointer jumping, unions only for the remaining contacts
 //   k4_border    unions across band borders (atomicMin in L2, roots = min block index)
 //   k4_compress  path compression + per-1024-block root counts
 //   k4_scan      exclusive scan of the counts per region -> chunk bases, ncomp
 //   k4_rank      root -> label (1-based rank in block-raster order)
 //   k4_stats     parent -> label in place; per-label area / bbox via run-aggregated atomics
-//   k4_final     int32 labels + u8 mask (min-area filter applied), kept area, bbox -> (x,y,w,h)
+//   k4_final     int32 labels + u8 mask (min-area filter applied), kept area (from the stats rows alone when no
+//                pixel output is wanted), bbox -> (x,y,w,h)
 // Algorithmic bytes per region: w*h (gray read) + w*h (mask) + 4*w*h (labels) + 20*ncomp.
 #include "common.cuh"
 #include <math.h>
@@ -613,8 +615,8 @@ __global__ void __launch_bounds__(K4_THREADS)
 k4_ccl_local(const qc_seg_region* __restrict__ regs, int R, int total_bands, const int* __restrict__ g_band_off,
              const unsigned* __restrict__ bits, int* __restrict__ parent, int band_words, int lab_words) {
     extern __shared__ __align__(16) unsigned sm[];
-    unsigned* band_s = sm;                                         // [34][wpr+2], zero border
-    int* lab = reinterpret_cast<int*>(sm + band_words);            // [16][wpr*16]
+    unsigned* band_s = sm;                                         // [rows+2][wpr+2], zero border
+    int* lab = reinterpret_cast<int*>(sm + band_words);            // [rows/2][wpr*16]
     unsigned short* cell_list = reinterpret_cast<unsigned short*>(lab + lab_words);   // (block row << 8 | word)
     __shared__ int s_off[K4_LOC_MAX + 1];
     __shared__ int s_ncell;
@@ -637,7 +639,7 @@ k4_ccl_local(const qc_seg_region* __restrict__ regs, int R, int total_bands, con
             if (tid == 0) s_ncell = 0;
         }
         __syncthreads();
-        // padded accessor: ry in [-1, 32], wx in [-1, wpr]
+        // padded accessor: ry in [-1, rows], wx in [-1, wpr]
         auto rowword = [&](int ry, int wx) -> unsigned { return band_s[(ry + 1) * pw + wx + 1]; };
         const int bw = bw_of(rg), bwp = wpr * 16;
         const int by0 = y0 >> 1, nbr = (brows + 1) >> 1;
