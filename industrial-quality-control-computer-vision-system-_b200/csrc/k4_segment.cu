@@ -133,14 +133,10 @@ __global__ void k4_init(const qc_seg_region* __restrict__ regs, int R, unsigned*
 }
 
 // ------------------------------------------------------------------------------------------
-// Histogram.  Warp per pixel row, 128-bit loads, per-warp lane-private u16 counters ([bin][lane]: no atomics, no
-// intra-warp address collisions; counter updates are issued four at a time with duplicates merged in
-// registers).  Every CTA owns a CONTIGUOUS range of bands and flushes its tables to the global histogram only
-// when the region changes (or before a counter could overflow), so the zero/reduce cost is paid per region,
-// not per band -- which matters for detection ROIs (thousands of tiny bands).
+// Histogram.  128-bit loads, per-warp lane-private u16 counters ([bin][lane]: no atomics, no intra-warp address
+// collisions; counter updates are issued four at a time with duplicates merged in registers).
 constexpr int K4_HIST_THREADS = 384;                             // 12 warps: the kernel is latency-bound, one CTA per SM
 constexpr int K4_HIST_SMEM = (K4_HIST_THREADS / 32) * 256 * 32 * 2;   // 192 KB
-constexpr int K4_HIST_FLUSH_PX = 4 << 20;                        // u16 safety: <= 16K pixels per lane between flushes
 
 // RGB -> gray (cv2 fixed point) into the region-packed gray workspace; plain high-occupancy kernel so the
 // histogram and threshold passes can stream contiguous bytes whatever the ROI alignment in the frame
@@ -195,23 +191,28 @@ k4_gray(Img im, const qc_seg_region* __restrict__ regs, int R, int total_bands, 
     }
 }
 
-// one warp counts a contiguous byte span into its lane-private table: scalar head/tail, 128-bit body
+// one warp counts a contiguous byte span into its lane-private table: scalar head/tail, 128-bit body in batches of
+// four vectors per lane (2 KB per warp), the next batch loaded before the current one is counted
 __device__ __forceinline__ void hist_span(const uint8_t* __restrict__ p, int len, unsigned short* tab, int lane) {
     const int head = min(len, (int)((16 - (reinterpret_cast<uintptr_t>(p) & 15)) & 15));
     const int nvec = (len - head) >> 4;
     for (int x = lane; x < head; x += 32) tab[(unsigned)__ldg(p + x) << 5]++;
     const uint4* pv = reinterpret_cast<const uint4*>(p + head);
-    for (int s0 = 0; s0 < nvec; s0 += 128) {
-        uint4 v[4];
+    uint4 cur[4], nxt[4];
+    auto load = [&](uint4* v, int s0) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int sidx = s0 + j * 32 + lane;
             v[j] = sidx < nvec ? __ldg(pv + sidx) : make_uint4(0, 0, 0, 0);
         }
+    };
+    load(cur, 0);
+    for (int s0 = 0; s0 < nvec; s0 += 128) {
+        if (s0 + 128 < nvec) load(nxt, s0 + 128);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             if (s0 + j * 32 + lane < nvec) {
-                const unsigned w4[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+                const unsigned w4[4] = {cur[j].x, cur[j].y, cur[j].z, cur[j].w};
                 // 4 pixels per round: the four counter loads are issued together and duplicates inside the group
                 // are merged in registers (every duplicate stores the same total)
 #pragma unroll
@@ -228,74 +229,88 @@ __device__ __forceinline__ void hist_span(const uint8_t* __restrict__ p, int len
                 }
             }
         }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) cur[j] = nxt[j];
     }
     for (int x = head + nvec * 16 + lane; x < len; x += 32) tab[(unsigned)__ldg(p + x) << 5]++;
 }
+
+// Work items are quarter-bands (~4K pixels of a detection ROI, 8K of a 2048-px frame); every WARP takes a contiguous
+// range of them, counts into its own lane-private table and flushes (reduce + atomicAdd of the non-zero bins + clear)
+// only when the region changes.  No CTA barrier, a dozen independent streams per SM whatever the region sizes, an
+// even split of the pixels, and only the few warps that share a region ever meet on the same global counters.
+constexpr int K4_HIST_SPLIT = 4;
+constexpr int K4_HIST_FLUSH_PX = 1 << 20;        // forced flush: a lane never counts more than 32K pixels in between
 
 __global__ void __launch_bounds__(K4_HIST_THREADS)
 k4_hist(Img im, const qc_seg_region* __restrict__ regs, int R, int total_bands, const int* __restrict__ g_band_off,
         unsigned* __restrict__ hist, const uint8_t* __restrict__ gray_ws) {
     extern __shared__ __align__(16) unsigned char hsm[];
     __shared__ int s_off[K4_LOC_MAX + 1];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int* off = loc_load(s_off, g_band_off, R);
     unsigned short* tab = reinterpret_cast<unsigned short*>(hsm) + warp * 8192 + lane;   // [bin*32]
-    auto zero = [&]() {
-        uint4* z = reinterpret_cast<uint4*>(hsm) + warp * 1024;
+    uint4* z = reinterpret_cast<uint4*>(hsm) + warp * 1024;
+    const unsigned* t32 = reinterpret_cast<const unsigned*>(hsm) + warp * 4096;
+    const int nw = K4_HIST_THREADS / 32;
+    const int nitems = total_bands * K4_HIST_SPLIT;
+    const int per = (nitems + gridDim.x * nw - 1) / (gridDim.x * nw);
+    const int i0 = (blockIdx.x * nw + warp) * per, i1 = min(i0 + per, nitems);
+    if (i0 >= i1) return;
+    auto clear = [&]() {
         for (int i = lane; i < 1024; i += 32) z[i] = make_uint4(0, 0, 0, 0);
+        __syncwarp();
     };
-    auto flush = [&](int r) {          // all threads; tables -> global histogram of region r, then cleared
-        __syncthreads();
-        const int bin = tid & 255;     // the first 256 threads own one bin each
-        unsigned sum = 0;
-        const unsigned* t32 = reinterpret_cast<const unsigned*>(hsm);
+    auto flush = [&](int r) {
+        __syncwarp();
+        // lane owns bins lane, lane+32, ...: sum the 32 lane-private u16 counters of each (16 words, rotated start
+        // so the 32 bins of a round hit 32 banks)
 #pragma unroll
-        for (int w = 0; w < K4_HIST_THREADS / 32; ++w) {
+        for (int b = 0; b < 8; ++b) {
+            const int bin = lane + 32 * b;
+            unsigned sum = 0;
 #pragma unroll
             for (int k = 0; k < 16; ++k) {
-                // word j of row `bin`: rotate by bin>>1 so the 32 bins of a warp hit 32 banks
-                const unsigned v = t32[w * 4096 + bin * 16 + ((k + (bin >> 1)) & 15)];
+                const unsigned v = t32[bin * 16 + ((k + (bin >> 1)) & 15)];
                 sum += (v & 0xFFFFu) + (v >> 16);
             }
+            if (sum) atomicAdd(&hist[(long long)r * 256 + bin], sum);
         }
-        if (tid < 256 && sum) atomicAdd(&hist[(long long)r * 256 + bin], sum);
-        __syncthreads();
-        zero();
-        __syncthreads();
+        __syncwarp();
     };
-    // contiguous band range of this CTA
-    const int per = (total_bands + gridDim.x - 1) / gridDim.x;
-    const int t_begin = blockIdx.x * per, t_end = min(t_begin + per, total_bands);
-    if (t_begin >= t_end) return;
-    zero();
-    __syncthreads();
-    // consecutive bands of one region are processed as one group (rows / contiguous span shared by all 8 warps)
-    for (int t = t_begin; t < t_end;) {
-        const int r = loc_find(off, R, t);
-        const qc_seg_region rg = regs[r];
-        const int BR = k4_band_rows(rg.w);
-        const int nb_region = (rg.h + BR - 1) / BR;
-        const int b0 = t - rg.band_offset;
-        // cap the group so a lane never counts more than 64K pixels between flushes
-        const int max_b = max(1, (int)(K4_HIST_FLUSH_PX / ((long long)BR * rg.w)));
-        const int b1 = min(min(nb_region, b0 + (t_end - t)), b0 + max_b);
-        const int y0 = b0 * BR, y1 = min(b1 * BR, rg.h);
-        if (im.channels == 1) {
-            const uint8_t* ibase = im.data + (long long)rg.img * im.img_stride;
-            for (int y = y0 + warp; y < y1; y += K4_HIST_THREADS / 32)
-                hist_span(ibase + (long long)(rg.y + y) * im.row_stride + rg.x, rg.w, tab, lane);
-        } else {
-            // region-packed gray copy: the rows are one contiguous span, cut into 2 KB pieces for the 8 warps
-            const uint8_t* p = gray_ws + rg.out_offset + (long long)y0 * rg.w;
-            const long long len = (long long)(y1 - y0) * rg.w;
-            for (long long c0 = (long long)warp * 2048; c0 < len; c0 += (K4_HIST_THREADS / 32) * 2048)
-                hist_span(p + c0, (int)min(2048ll, len - c0), tab, lane);
+    clear();
+    int cur_r = -1, cur_t = -1, acc = 0;
+    qc_seg_region rg;
+    for (int it = i0; it < i1; ++it) {
+        const int t = it / K4_HIST_SPLIT, q = it - t * K4_HIST_SPLIT;
+        if (t != cur_t) {
+            cur_t = t;
+            const int r = loc_find(off, R, t);
+            if (r != cur_r || acc > K4_HIST_FLUSH_PX) {
+                if (cur_r >= 0) { flush(cur_r); clear(); }
+                acc = 0;
+            }
+            if (r != cur_r) { cur_r = r; rg = regs[r]; }
         }
-        flush(r);
-        t += b1 - b0;
+        const int BR = k4_band_rows(rg.w);
+        const int yb0 = (t - rg.band_offset) * BR, yb1 = min(yb0 + BR, rg.h);
+        const int qr = (yb1 - yb0 + K4_HIST_SPLIT - 1) / K4_HIST_SPLIT;
+        const int y0 = yb0 + q * qr, y1 = min(y0 + qr, yb1);
+        if (y0 >= y1) continue;
+        acc += (y1 - y0) * rg.w;
+        if (im.channels == 1 && rg.w != im.row_stride) {
+            const uint8_t* ibase = im.data + (long long)rg.img * im.img_stride + (long long)rg.y * im.row_stride + rg.x;
+            for (int y = y0; y < y1; ++y) hist_span(ibase + (long long)y * im.row_stride, rg.w, tab, lane);
+        } else {
+            // full-width rows of the caller's gray frame, or the region-packed gray copy: one contiguous span
+            const uint8_t* p = im.channels == 1
+                ? im.data + (long long)rg.img * im.img_stride + (long long)(rg.y + y0) * im.row_stride
+                : gray_ws + rg.out_offset + (long long)y0 * rg.w;
+            hist_span(p, (y1 - y0) * rg.w, tab, lane);
+        }
     }
+    if (cur_r >= 0) flush(cur_r);
 }
-
 
 // ------------------------------------------------------------------------------------------
 // Otsu threshold, bit-exact with cv2's getThreshVal_Otsu_8u.  cv2's recurrence is sequential in
@@ -1220,10 +1235,14 @@ extern "C" int qc_segment(qc_ctx* ctx, const uint8_t* imgs, const qc_seg_params*
         k4_gray<<<std::min(p->total_bands, sms * 8), K4_THREADS, 0, st>>>(im, regions, R, p->total_bands, w.band_off, w.gray);
         QC_LAUNCHED(ctx);
     }
-    if (int rc = qc_prepare(ctx, k4_hist, K4_HIST_SMEM, K4_HIST_THREADS, nullptr)) return rc;
-    k4_hist<<<std::min(p->total_bands, sms), K4_HIST_THREADS, K4_HIST_SMEM, st>>>(im, regions, R, p->total_bands, w.band_off,
-                                                                          w.hist, w.gray);
-    QC_LAUNCHED(ctx);
+    {
+        if (int rc = qc_prepare(ctx, k4_hist, K4_HIST_SMEM, K4_HIST_THREADS, nullptr)) return rc;
+        const int nw = K4_HIST_THREADS / 32;
+        const int items = p->total_bands * K4_HIST_SPLIT;
+        k4_hist<<<std::min((items + nw - 1) / nw, sms), K4_HIST_THREADS, K4_HIST_SMEM, st>>>(
+            im, regions, R, p->total_bands, w.band_off, w.hist, w.gray);
+        QC_LAUNCHED(ctx);
+    }
 
     k4_otsu<<<std::min((R + 7) / 8, sms * 8), 256, 0, st>>>(regions, R, w.hist, w.cmp, out_thr);
     QC_LAUNCHED(ctx);
