@@ -152,41 +152,42 @@ k4_gray(Img im, const qc_seg_region* __restrict__ regs, int R, int total_bands, 
         const int y0 = (t - rg.band_offset) * BR;
         const int y1 = min(y0 + BR, rg.h);
         const uint8_t* ibase = im.data + (long long)rg.img * im.img_stride;
-        for (int y = y0 + warp; y < y1; y += K4_THREADS / 32) {
+        auto gray_of = [&](unsigned c0, unsigned c1, unsigned c2) -> unsigned {
+            // cv2 RGB2GRAY fixed point: (R*9798 + G*19235 + B*3735 + 2^14) >> 15
+            return (9798u * (im.swap_rb ? c2 : c0) + 19235u * c1 + 3735u * (im.swap_rb ? c0 : c2) + 16384u) >> 15;
+        };
+        // Work items = (row, group) flattened over the band, so a 150-px ROI row (39 groups) does not leave half of
+        // a warp idle and the per-row set-up is paid per item, not per lane and row.  Per row: item 0 = the <= 3
+        // pixels in front of the first pixel whose 3 bytes start 4-byte aligned (pixel index == address mod 4),
+        // items 1..ngrp = groups of 4 pixels = three aligned 32-bit words, last item = the <= 3 tail pixels.
+        const int G = (rg.w >> 2) + 2;
+        const float inv_G = 1.0f / (float)G;
+        const int nitems = (y1 - y0) * G;
+        for (int it = threadIdx.x; it < nitems; it += K4_THREADS) {
+            const int yy = (int)(((float)it + 0.5f) * inv_G);                // it / G (exact: it < 2^20)
+            const int gi = it - yy * G, y = y0 + yy;
             const uint8_t* p = ibase + (long long)(rg.y + y) * im.row_stride + (long long)rg.x * 3;
             uint8_t* gq = gray_ws + rg.out_offset + (long long)y * rg.w;
-            // pixel h = (address mod 4) is the first one whose 3 bytes start 4-byte aligned; from there every group
-            // of 4 pixels is three aligned 32-bit words
             const int head = min(rg.w, (int)(reinterpret_cast<uintptr_t>(p) & 3));
-            auto gray_of = [&](unsigned c0, unsigned c1, unsigned c2) -> uint8_t {
-                // cv2 RGB2GRAY fixed point: (R*9798 + G*19235 + B*3735 + 2^14) >> 15
-                return (uint8_t)((9798u * (im.swap_rb ? c2 : c0) + 19235u * c1 + 3735u * (im.swap_rb ? c0 : c2) + 16384u) >> 15);
-            };
-            if (lane < head) gq[lane] = gray_of(__ldg(p + 3 * lane), __ldg(p + 3 * lane + 1), __ldg(p + 3 * lane + 2));
             const int ngrp = (rg.w - head) >> 2;
-            const unsigned* pw = reinterpret_cast<const unsigned*>(p + 3 * head);
-            for (int g0 = lane; g0 < ngrp; g0 += 64) {                 // two groups (24 bytes) in flight per lane
-                unsigned wv[2][3];
-#pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    const int g = g0 + 32 * j;
-                    if (g < ngrp) { wv[j][0] = __ldg(pw + 3 * g); wv[j][1] = __ldg(pw + 3 * g + 1); wv[j][2] = __ldg(pw + 3 * g + 2); }
+            if (gi >= 1 && gi <= ngrp) {
+                const int g = gi - 1;
+                const unsigned* pw = reinterpret_cast<const unsigned*>(p + 3 * head) + 3 * g;
+                const unsigned a = __ldg(pw), b2 = __ldg(pw + 1), c = __ldg(pw + 2);
+                const unsigned o0 = gray_of(a & 255u, (a >> 8) & 255u, (a >> 16) & 255u);
+                const unsigned o1 = gray_of(a >> 24, b2 & 255u, (b2 >> 8) & 255u);
+                const unsigned o2 = gray_of((b2 >> 16) & 255u, b2 >> 24, c & 255u);
+                const unsigned o3 = gray_of((c >> 8) & 255u, (c >> 16) & 255u, c >> 24);
+                uint8_t* o = gq + head + 4 * g;
+                if ((reinterpret_cast<uintptr_t>(o) & 3) == 0) {
+                    *reinterpret_cast<unsigned*>(o) = o0 | (o1 << 8) | (o2 << 16) | (o3 << 24);
+                } else {
+                    o[0] = (uint8_t)o0; o[1] = (uint8_t)o1; o[2] = (uint8_t)o2; o[3] = (uint8_t)o3;
                 }
-#pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    const int g = g0 + 32 * j;
-                    if (g < ngrp) {
-                        const unsigned a = wv[j][0], b = wv[j][1], c = wv[j][2];
-                        uint8_t* o = gq + head + 4 * g;
-                        o[0] = gray_of(a & 255u, (a >> 8) & 255u, (a >> 16) & 255u);
-                        o[1] = gray_of(a >> 24, b & 255u, (b >> 8) & 255u);
-                        o[2] = gray_of((b >> 16) & 255u, b >> 24, c & 255u);
-                        o[3] = gray_of((c >> 8) & 255u, (c >> 16) & 255u, c >> 24);
-                    }
-                }
+            } else if (gi == 0 || gi == ngrp + 1) {
+                const int xa = gi == 0 ? 0 : head + 4 * ngrp, xb = gi == 0 ? head : rg.w;
+                for (int x = xa; x < xb; ++x) gq[x] = (uint8_t)gray_of(__ldg(p + 3 * x), __ldg(p + 3 * x + 1), __ldg(p + 3 * x + 2));
             }
-            for (int x = head + 4 * ngrp + lane; x < rg.w; x += 32)
-                gq[x] = gray_of(__ldg(p + 3 * x), __ldg(p + 3 * x + 1), __ldg(p + 3 * x + 2));
         }
     }
 }
