@@ -427,8 +427,9 @@ def main():
     roofline = {"bound": "hbm", "kernel": "k1_pack_stream (K1 preprocess, most bytes of the step)",
                 "achieved": k1_bytes / k1_ms / 1e6 if k1_ms else None, "peak": peak, "unit": "GB/s",
                 "frac": (k1_bytes / k1_ms / 1e6 / peak) if k1_ms else None,
-                # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full (profiles/r01_c_k1_full.txt)
-                "traffic": 177480960,
+                # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full
+                # (profiles/r01_f_ncu_full_summary.md: 78.66 MB read + 102.12 MB written inside the kernel)
+                "traffic": 180780032,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": k1_bytes,
                 "ms_per_launch": k1_ms}
     d2h = int(last.det.nbytes + last.count.nbytes + 72 + (last.roi_probs.nbytes if last.roi_probs is not None else 0)
