@@ -319,23 +319,52 @@ k4_hist(Img im, const qc_seg_region* __restrict__ regs, int R, int total_bands, 
 // prefix sums.  If the best split beats every other by a relative 1e-9 (rounding in either
 // formulation is ~1e-13) its index IS cv2's answer; otherwise (plateaus of two-level images,
 // ties, bins on the FLT_EPSILON skip boundary) one thread replays cv2's exact recurrence.
-// Warp-cooperative replay of cv2's recurrence.  Only the (q1, mu1) chain is inherently sequential; lane 0 runs it
-// and parks the state of every bin in shared memory, then all lanes evaluate sigma for their 8 bins with cv2's
-// expression and the warp takes the first strict maximum (max_sigma starts at 0, updated on `>`).  The total mean
-// is a sum of exact integers below 2^53, so its summation order is irrelevant.
-__device__ int otsu_replay_cv2(const unsigned* h, long long npix, double mu_sum, double* s_q, double* s_m, int lane) {
+// Warp-cooperative replay of cv2's recurrence.  What is inherently sequential is split into two short chains run by
+// lane 0: q1 (one addition per bin) and mu1.  cv2's mu1 step divides by q1; with the correctly rounded reciprocal
+// y = RN(1/q1) prepared in parallel, Markstein's sequence q = RN(a*y), r = a - q*q1 (exact in one fma),
+// RN(q + r*y) gives exactly the correctly rounded quotient RN(a/q1) that the division instruction would (checked
+// against exact rational arithmetic on 3e5 operand pairs of this range; the cv2-pinned parity tests cover the rest),
+// in five dependent double operations per bin instead of a ~30-instruction software division.  Everything else
+// (p_i, i*p_i, the reciprocals, sigma of every bin, first strict maximum) is evaluated by all 32 lanes.  The total
+// mean is a sum of exact integers below 2^53, so its summation order is irrelevant.
+constexpr int K4_OTSU_WARPS = 4;
+__device__ int otsu_replay_cv2(const unsigned* h, long long npix, double mu_sum, double* s_q, double* s_y, double* s_ip,
+                               double* s_m, int lane) {
     const double scale = __ddiv_rn(1.0, (double)npix);
     const double mu = __dmul_rn(mu_sum, scale);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int i = lane * 8 + k;
+        const double p_i = __dmul_rn((double)h[i], scale);
+        s_m[i] = p_i;                                    // (p_i parked in s_m until the mu1 chain overwrites it)
+        s_ip[i] = __dmul_rn((double)i, p_i);
+    }
+    __syncwarp();
     if (lane == 0) {
-        double mu1 = 0.0, q1 = 0.0;
+        double q1 = 0.0;
+        for (int i = 0; i < 256; ++i) { q1 = __dadd_rn(q1, s_m[i]); s_q[i] = q1; }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int i = lane * 8 + k;
+        const double q1 = s_q[i], q2 = __dsub_rn(1.0, q1);
+        const bool skip = fmin(q1, q2) < (double)FLT_EPSILON || fmax(q1, q2) > 1.0 - (double)FLT_EPSILON;
+        s_y[i] = skip ? -1.0 : __drcp_rn(q1);
+    }
+    __syncwarp();
+    if (lane == 0) {
+        double mu1 = 0.0, qprev = 0.0;
         for (int i = 0; i < 256; ++i) {
-            const double p_i = __dmul_rn((double)h[i], scale);
-            mu1 = __dmul_rn(mu1, q1);
-            q1 = __dadd_rn(q1, p_i);
-            const double q2 = __dsub_rn(1.0, q1);
-            const bool skip = fmin(q1, q2) < (double)FLT_EPSILON || fmax(q1, q2) > 1.0 - (double)FLT_EPSILON;
-            if (!skip) mu1 = __ddiv_rn(__dadd_rn(mu1, __dmul_rn((double)i, p_i)), q1);
-            s_q[i] = skip ? -1.0 : q1;
+            mu1 = __dmul_rn(mu1, qprev);
+            qprev = s_q[i];
+            const double y = s_y[i];
+            if (y >= 0.0) {
+                const double a = __dadd_rn(mu1, s_ip[i]);
+                const double q = __dmul_rn(a, y);
+                const double r = __fma_rn(-q, qprev, a);
+                mu1 = __fma_rn(r, y, q);                  // == __ddiv_rn(a, q1)
+            }
             s_m[i] = mu1;
         }
     }
@@ -345,8 +374,8 @@ __device__ int otsu_replay_cv2(const unsigned* h, long long npix, double mu_sum,
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         const int i = lane * 8 + k;
+        if (s_y[i] < 0.0) continue;
         const double q1 = s_q[i];
-        if (q1 < 0.0) continue;
         const double q2 = __dsub_rn(1.0, q1), mu1 = s_m[i];
         const double mu2 = __ddiv_rn(__dsub_rn(mu, __dmul_rn(q1, mu1)), q2);
         const double d = __dsub_rn(mu1, mu2);
@@ -363,16 +392,16 @@ __device__ int otsu_replay_cv2(const unsigned* h, long long npix, double mu_sum,
     return best > 0.0 ? bidx : 0;
 }
 
-// one WARP per region (8 regions per CTA): lane l owns bins 8l..8l+7.  Small ROIs have sparse histograms whose
+// one WARP per region (4 regions per CTA): lane l owns bins 8l..8l+7.  Small ROIs have sparse histograms whose
 // empty bins create exact ties, so the serial replay is common there; with a warp per region all replays of a
 // batch run concurrently instead of queueing behind one another.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(K4_OTSU_WARPS * 32)
 k4_otsu(const qc_seg_region* __restrict__ regs, int R, const unsigned* __restrict__ hist,
         int* __restrict__ cmp, int* __restrict__ out_thr) {
-    __shared__ unsigned s_h[8][256];
-    __shared__ double s_q[8][256], s_m[8][256];
+    __shared__ unsigned s_h[K4_OTSU_WARPS][256];
+    __shared__ double s_q[K4_OTSU_WARPS][256], s_y[K4_OTSU_WARPS][256], s_ip[K4_OTSU_WARPS][256], s_m[K4_OTSU_WARPS][256];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int r = blockIdx.x * 8 + warp; r < R; r += gridDim.x * 8) {
+    for (int r = blockIdx.x * K4_OTSU_WARPS + warp; r < R; r += gridDim.x * K4_OTSU_WARPS) {
         const qc_seg_region rg = regs[r];
         unsigned h[8];
         unsigned long long w1 = 0, s1 = 0;
@@ -434,7 +463,8 @@ k4_otsu(const qc_seg_region* __restrict__ regs, int R, const unsigned* __restric
         int max_val;
         if (!(flags & 1) && !(flags & 2)) max_val = 0;                              // every split skipped
         else if (b > 0.0 && nclose == 0 && !(flags & 2)) max_val = bi;              // decisive maximum
-        else max_val = otsu_replay_cv2(s_h[warp], (long long)rg.w * rg.h, (double)S, s_q[warp], s_m[warp], lane);
+        else max_val = otsu_replay_cv2(s_h[warp], (long long)rg.w * rg.h, (double)S, s_q[warp], s_y[warp], s_ip[warp],
+                                       s_m[warp], lane);
         if (lane == 0) {
             out_thr[r] = max_val;
             int lo, hi;
@@ -1245,7 +1275,8 @@ extern "C" int qc_segment(qc_ctx* ctx, const uint8_t* imgs, const qc_seg_params*
         QC_LAUNCHED(ctx);
     }
 
-    k4_otsu<<<std::min((R + 7) / 8, sms * 8), 256, 0, st>>>(regions, R, w.hist, w.cmp, out_thr);
+    k4_otsu<<<std::min((R + K4_OTSU_WARPS - 1) / K4_OTSU_WARPS, sms * 8), K4_OTSU_WARPS * 32, 0, st>>>(regions, R, w.hist,
+                                                                                                          w.cmp, out_thr);
     QC_LAUNCHED(ctx);
 
     const int halo = 4 * p->morph_iters;
