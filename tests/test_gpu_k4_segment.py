@@ -162,3 +162,25 @@ def test_dense_noise_rois(qc):
     for i, r in enumerate(regs):
         roi = np.ascontiguousarray(imgs[r["img"], r["y"]:r["y"] + r["h"], r["x"]:r["x"] + r["w"]])
         _check_region(res, i, r, oseg.segment_k4(roi, r["polarity"], 1.0, 1, 20))
+
+
+def test_otsu_replay_many_sparse_histograms(qc):
+    """Thousands of small ROIs with few gray levels: sparse histograms make exact ties between neighbouring splits, so
+    nearly every region goes through the warp-cooperative replay of cv2's float64 recurrence (parallel reciprocals +
+    Markstein division chain) -- the threshold must equal cv2.threshold(OTSU) on every one of them."""
+    rng = np.random.default_rng(77)
+    frames = np.zeros((4, 256, 256), np.uint8)
+    levels = [np.array([10, 200]), np.array([0, 1, 2, 255]), np.arange(0, 256, 17), np.array([3, 4, 5, 6, 7, 250, 251])]
+    for i in range(4):
+        frames[i] = rng.choice(levels[i], size=(256, 256), p=None)
+    frames[1, :128] = rng.integers(0, 256, (128, 256))             # dense part: decisive maxima next to tie cases
+    regs = []
+    for k in range(3000):
+        w, h = int(rng.integers(3, 48)), int(rng.integers(3, 48))
+        regs.append(dict(img=int(rng.integers(0, 4)), x=int(rng.integers(0, 256 - w)), y=int(rng.integers(0, 256 - h)),
+                         w=w, h=h, polarity=int(rng.integers(0, 2)), min_area=1, max_comp=8))
+    res = qc.segment(torch.from_numpy(frames).cuda(), regs, morph_iters=0, want_mask=False, want_labels=False)
+    thr = res["thr"].cpu().numpy()
+    for k, r in enumerate(regs):
+        roi = np.ascontiguousarray(frames[r["img"], r["y"]:r["y"] + r["h"], r["x"]:r["x"] + r["w"]])
+        assert int(thr[k]) == oseg.otsu_u8(roi), (k, r)
