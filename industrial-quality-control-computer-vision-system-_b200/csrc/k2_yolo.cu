@@ -617,7 +617,7 @@ k2_nms_class(NmsArgs args, int nc, const unsigned long long* __restrict__ cand_k
             const float4 b = cand_box[(long long)img * cap + vals[i]];
             sorted[i] = make_float4(__fadd_rn(b.x, off), __fadd_rn(b.y, off), __fadd_rn(b.z, off), __fadd_rn(b.w, off));
         }
-        for (int i = tid; i < (n + 31) / 32 + 2; i += K2C_THREADS) removed[i] = 0u;
+        for (int i = tid; i < min((n + 31) / 32 + 2, K2_REMOVED_MAX / 32); i += K2C_THREADS) removed[i] = 0u;
         __syncthreads();
 
         // 64x64 upper-triangular suppression bitmask of every chunk (depends only on the boxes)
