@@ -24,6 +24,10 @@ qc.nms((b * 300).contiguous(), torch.rand(1, n).cuda(), torch.randint(0, 5, (1, 
 rois = torch.tensor([[0, 3, 4, 60, 70], [1, 0, 0, 160, 96], [0, -500, -500, 900, 900], [1, 10, 10, 11, 11]], dtype=torch.float32).cuda()
 qc.roi_align(d, rois)
 qc.roi_align(d, rois, sampling_ratio=0, out_hw=(7, 7), out_dtype=torch.float32)
+# K3b (PIL-exact resize: down-scale with runtime tap groups, up-scale, odd output)
+qc.pil_resize(d)
+qc.pil_resize(d, out_hw=(201, 333), out_dtype=torch.float32)
+qc.pil_resize(torch.from_numpy(synth.make_frames(3, 1, 700, 1300)).cuda(), out_hw=(31, 45))
 # K4 (full frame gray, RGB ROIs, odd sizes)
 g = torch.from_numpy(np.stack([synth.make_linescan(5, 130, 203), synth.make_linescan(6, 130, 203)])).cuda()
 qc.segment(g, [dict(img=0, x=0, y=0, w=203, h=130), dict(img=1, x=7, y=9, w=65, h=33, polarity=0)], morph_iters=2)
