@@ -602,6 +602,33 @@ class _PassThroughPostProcessor:
         self.config.update(new_config)
 
 
+class RulesPostProcessor(_PassThroughPostProcessor):
+    """PostProcessor.process_results (inference/postprocess.py:32-109) with the detection chain
+    refine -> filter -> merge -> validate computed by ``rules.DetectionRules`` (the array form of row f1, pinned
+    against the reference's own class).  Quality / risk / recommendation texts are not restated: plug the
+    reference's PostProcessor object for those.  Select with ``config['qcgraft']['postprocessor'] = 'rules'``."""
+
+    def __init__(self, config):
+        super().__init__(config)
+        from .rules import DetectionRules
+        self.rules = DetectionRules(config)
+
+    def process_results(self, ensemble_results, segmentation_results, image_shape):
+        try:
+            dets = self.rules.process(ensemble_results.get("detections", []), segmentation_results or {}, image_shape)
+        except Exception as e:                                    # the reference's convention: never raise
+            logger.error(f"Error in post-processing: {str(e)}")
+            return {"error": str(e)}
+        return {"detections": dets, "quality_assessment": ensemble_results.get("quality_assessment", {}),
+                "risk_analysis": {}, "recommendations": [],
+                "metadata": {"total_detections": len(dets), "image_shape": tuple(image_shape),
+                             "post_processing_version": "1.0.0"}}
+
+    def update_config(self, new_config):
+        super().update_config(new_config)
+        self.rules = type(self.rules)(self.config)
+
+
 class QualityControlDetector:
     """inference/detector.py:21 -- same constructor, methods, attributes and result keys."""
 
@@ -618,6 +645,8 @@ class QualityControlDetector:
                                                     config=self.config)
         self.segmentator = ImageSegmentator(self.config)
         pp = (self.config or {}).get("qcgraft", {}).get("postprocessor")
+        if pp == "rules":
+            pp = RulesPostProcessor(self.config)
         self.postprocessor = pp if pp is not None else _PassThroughPostProcessor(self.config)
 
     def predict(self, image: np.ndarray, include_segmentation: bool = True, _head_override=None) -> Dict:
