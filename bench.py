@@ -192,6 +192,8 @@ def kernel_microbench(qc, peak, only=None):
         _mb_k3b(qc, peak, rng, time_call, out)
     if want("k4"):
         _mb_k4(qc, peak, rng, time_call, out)
+    if want("k6"):
+        _mb_k6(qc, peak, rng, time_call, out)
     return out
 
 
@@ -263,6 +265,25 @@ def _mb_k3b(qc, peak, rng, time_call, out):
     med, best = time_call(lambda i: qc.pil_resize(b[i % 3], out=o), 9)
     by = BATCH * (IMGSZ * IMGSZ * 3 + 3 * 224 * 224 * 2)
     out["k3b_pil_resize_cfg2"] = {"bytes": by, "ms": med, "gbs": by / med / 1e6, "frac": by / med / 1e6 / peak}
+
+
+def _mb_k6(qc, peak, rng, time_call, out):
+    # K6: same-class overlap clustering of 64 images x 300 post-NMS boxes (clustered: real merge work)
+    n, cap = BATCH, 300
+    ctr = rng.uniform(50, 590, (n, 30, 2))
+    pick = rng.integers(0, 30, (n, cap))
+    xy = np.take_along_axis(ctr, pick[..., None].repeat(2, 2), 1) + rng.normal(0, 6, (n, cap, 2))
+    wh = rng.integers(8, 120, (n, cap, 2))
+    box = np.concatenate((xy, xy + wh), 2).astype(np.int32)
+    b = torch.from_numpy(np.ascontiguousarray(box)).cuda()
+    c = torch.from_numpy(rng.integers(0, NC, (n, cap)).astype(np.int32)).cuda()
+    cnt = torch.full((n,), cap, dtype=torch.int32).cuda()
+    qc.rules_cluster(b, c, cnt)
+    med, best = time_call(lambda i: qc.rules_cluster(b, c, cnt), 8)
+    by = n * cap * (16 + 4 + 4 + 4)
+    out["k6_rules_cluster_64x300"] = {"bytes": by, "ms": med, "gbs": by / med / 1e6, "frac": by / med / 1e6 / peak,
+                                      "note": "quadratic pair test + shared-memory union-find per image: latency-bound, "
+                                              "the bytes are negligible"}
 
 
 def _mb_k4(qc, peak, rng, time_call, out):

@@ -230,6 +230,19 @@ int qc_segment(qc_ctx* ctx, const uint8_t* imgs, const qc_seg_params* p,
 int qc_spc_stats(qc_ctx* ctx, const float* det, const int32_t* count, int n, int max_det,
                  double* out9, void* stream);
 
+/* ---- K6: same-class overlap clustering of the post-NMS rule engine (row f1) ------
+ * The quadratic step of inference/postprocess.py:233-303: per image, detections of one class are linked when
+ * `1.0 - IoU <= 1.0 - overlap_threshold` (IoU = integer intersection / integer union in float64, :859-877) and
+ * labelled like DBSCAN(metric='precomputed', eps = 1 - overlap_threshold, min_samples = 1) labels `1 - iou_matrix`
+ * with its zero-IoU diagonal: -1 for rows without a partner (they all share the noise label), otherwise the index
+ * of the connected component among the components of that class, in order of first member.
+ * box [n][cap][4] int32 (x1,y1,x2,y2; width/height = differences), cls [n][cap] int32 (>= 0),
+ * keep [n][cap] uint8 or NULL (rows filtered out before clustering), count [n]; out_label [n][cap] int32
+ * (-2 for rows >= count or not kept).  cap <= 2048; box 16-byte aligned.                                      */
+int qc_rules_cluster(qc_ctx* ctx, const int32_t* box, const int32_t* cls, const uint8_t* keep,
+                     const int32_t* count, int n, int cap, double overlap_threshold, int32_t* out_label,
+                     void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -97,6 +97,8 @@ _SIGS = {
     "qc_segment": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(SegParams), C.c_void_p, C.c_void_p, C.c_size_t,
                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "qc_spc_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "qc_rules_cluster": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                   C.c_double, C.c_void_p, C.c_void_p]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGS)
 
@@ -443,6 +445,23 @@ class Context:
                     thr=thr, area=area)
 
     # -- SPC -------------------------------------------------------------------------------
+    # -- K6 --------------------------------------------------------------------------------
+    def rules_cluster(self, box: torch.Tensor, cls: torch.Tensor, count: torch.Tensor,
+                      keep: Optional[torch.Tensor] = None, overlap_threshold: float = 0.3) -> torch.Tensor:
+        """box int32 [n,cap,4], cls int32 [n,cap], count int32 [n], keep uint8 [n,cap] or None -> labels int32 [n,cap]
+        (inference/postprocess.py:233-303: -1 isolated, >= 0 component of its class, -2 not clustered)."""
+        assert box.is_cuda and box.dtype == torch.int32 and box.is_contiguous() and box.shape[-1] == 4
+        assert cls.dtype == torch.int32 and cls.is_contiguous() and count.dtype == torch.int32
+        n, cap = box.shape[:2]
+        out = torch.empty((n, cap), dtype=torch.int32, device=box.device)
+        if keep is not None:
+            assert keep.dtype == torch.uint8 and keep.is_contiguous()
+        rc = self.lib.qc_rules_cluster(self.h, box.data_ptr(), cls.data_ptr(), keep.data_ptr() if keep is not None else None,
+                                       count.data_ptr(), n, cap, float(overlap_threshold), out.data_ptr(),
+                                       _stream(box.device))
+        self._check(rc, "qc_rules_cluster")
+        return out
+
     def spc_stats(self, det: torch.Tensor, count: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         n, md = det.shape[0], det.shape[1]
         if out is None:

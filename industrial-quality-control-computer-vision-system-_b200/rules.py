@@ -198,25 +198,34 @@ class DetectionRules:
         return [d for d, k in zip(detections, keep) if k]
 
     # -- :233-358 ------------------------------------------------------------------------------------
-    def _merge_overlapping_detections(self, detections: List[Dict]) -> List[Dict]:
+    def _merge_overlapping_detections(self, detections: List[Dict], labels=None) -> List[Dict]:
+        """``labels``: optional per-detection cluster labels computed elsewhere (K6 on the device: -1 isolated,
+        >= 0 component of its class); without them the IoU matrix and the clustering run here."""
         if len(detections) <= 1:
             return detections
-        groups: Dict[str, List[Dict]] = {}
-        for d in detections:
-            groups.setdefault(d["class"], []).append(d)           # classes in order of first appearance
+        groups: Dict[str, List[int]] = {}
+        for i, d in enumerate(detections):
+            groups.setdefault(d["class"], []).append(i)           # classes in order of first appearance
         merged = []
-        for members in groups.values():
+        for member_idx in groups.values():
+            members = [detections[i] for i in member_idx]
             if len(members) == 1:
                 merged.extend(members)
+                continue
+            if labels is not None:
+                lab_c = np.asarray(labels)[member_idx]
+                for lab in np.unique(lab_c):
+                    idx = np.nonzero(lab_c == lab)[0]
+                    merged.append(members[idx[0]] if len(idx) == 1 else self._merge_detection_cluster([members[i] for i in idx]))
                 continue
             box = np.array([[m["bbox"]["x1"], m["bbox"]["y1"], m["bbox"]["x1"] + m["bbox"]["width"],
                              m["bbox"]["y1"] + m["bbox"]["height"]] for m in members], np.int64)
             # the reference intersects on (x1,y1,x2,y2) and takes areas from width*height: identical while
             # width == x2-x1, which every producer on this path guarantees; keep its exact form otherwise
             xyxy = np.array([[m["bbox"]["x1"], m["bbox"]["y1"], m["bbox"]["x2"], m["bbox"]["y2"]] for m in members], np.int64)
-            labels = cluster_labels(iou_matrix(xyxy) if np.array_equal(box, xyxy) else self._iou_matrix_general(members))
-            for lab in np.unique(labels):
-                idx = np.nonzero(labels == lab)[0]
+            lab_c = cluster_labels(iou_matrix(xyxy) if np.array_equal(box, xyxy) else self._iou_matrix_general(members))
+            for lab in np.unique(lab_c):
+                idx = np.nonzero(lab_c == lab)[0]
                 merged.append(members[idx[0]] if len(idx) == 1 else self._merge_detection_cluster([members[i] for i in idx]))
         return merged
 
