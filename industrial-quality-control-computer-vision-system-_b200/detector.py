@@ -605,8 +605,8 @@ class _PassThroughPostProcessor:
 class RulesPostProcessor(_PassThroughPostProcessor):
     """PostProcessor.process_results (inference/postprocess.py:32-109) with the detection chain
     refine -> filter -> merge -> validate computed by ``rules.DetectionRules`` (the array form of row f1, pinned
-    against the reference's own class).  Quality / risk / recommendation texts are not restated: plug the
-    reference's PostProcessor object for those.  Select with ``config['qcgraft']['postprocessor'] = 'rules'``."""
+    against the reference's own class) and the numeric quality assessment (:466-599).  Risk factors and recommendation
+    texts are not restated: plug the reference's PostProcessor object for those.  Select with ``config['qcgraft']['postprocessor'] = 'rules'``."""
 
     def __init__(self, config):
         super().__init__(config)
@@ -616,11 +616,11 @@ class RulesPostProcessor(_PassThroughPostProcessor):
     def process_results(self, ensemble_results, segmentation_results, image_shape):
         try:
             dets = self.rules.process(ensemble_results.get("detections", []), segmentation_results or {}, image_shape)
+            quality = self.rules._assess_quality(dets, segmentation_results or {})
         except Exception as e:                                    # the reference's convention: never raise
             logger.error(f"Error in post-processing: {str(e)}")
             return {"error": str(e)}
-        return {"detections": dets, "quality_assessment": ensemble_results.get("quality_assessment", {}),
-                "risk_analysis": {}, "recommendations": [],
+        return {"detections": dets, "quality_assessment": quality, "risk_analysis": {}, "recommendations": [],
                 "metadata": {"total_detections": len(dets), "image_shape": tuple(image_shape),
                              "post_processing_version": "1.0.0"}}
 

@@ -290,6 +290,38 @@ class DetectionRules:
                 out.append(d)
         return out
 
+    # -- :466-599 -------------------------------------------------------------------------------------
+    GRADES = (("F", "FAIL", "high"), ("D", "FAIL", "high"), ("C", "CONDITIONAL", "medium"), ("B", "CONDITIONAL", "low"),
+              ("A", "PASS", "low"))
+    ACTIONS = {("PASS", "low"): "accept", ("CONDITIONAL", "low"): "accept_with_monitoring",
+               ("CONDITIONAL", "medium"): "review_required", ("FAIL", "high"): "reject", ("FAIL", "medium"): "rework_required"}
+    PENALTY = {"critical": 30, "major": 15, "minor": 5}
+
+    def _assess_quality(self, detections: Sequence[Dict], segmentation_results: Dict) -> Dict:
+        """Severity counts -> grade / pass-fail / risk, quality score and the per-image aggregates the SPC layer reads."""
+        counts = {"critical": 0, "major": 0, "minor": 0}
+        if not detections:
+            return {"quality_grade": "A", "pass_fail_status": "PASS", "risk_level": "low", "total_defects": 0,
+                    "severity_breakdown": counts, "total_defect_area_pixels": 0, "defect_density": 0.0,
+                    "average_confidence": 1.0, "quality_score": 100.0, "meets_requirements": True,
+                    "recommended_action": "accept"}
+        for d in detections:
+            counts[d.get("final_severity", "minor")] += 1
+        t = self.quality_thresholds
+        rule = [counts["critical"] > t.get("critical_defect_limit", 0), counts["major"] > t.get("major_defect_limit", 1),
+                counts["minor"] > t.get("minor_defect_limit", 3), counts["major"] > 0, True]
+        grade, pass_fail, risk = self.GRADES[rule.index(True)]
+        avg_conf = np.mean([_conf_of(d) if ("ensemble_confidence" in d or "confidence" in d) else 0 for d in detections])
+        base = 100.0
+        for sev, c in counts.items():
+            base -= c * self.PENALTY[sev]
+        score = max(0, base * min(avg_conf / 0.8, 1.0))
+        return {"quality_grade": grade, "pass_fail_status": pass_fail, "risk_level": risk, "total_defects": len(detections),
+                "severity_breakdown": counts, "total_defect_area_pixels": sum(d.get("area_pixels", 0) for d in detections),
+                "defect_density": (segmentation_results or {}).get("defect_density", 0.0), "average_confidence": avg_conf,
+                "quality_score": score, "meets_requirements": pass_fail == "PASS",
+                "recommended_action": self.ACTIONS.get((pass_fail, risk), "manual_inspection")}
+
     # -- :64-81 ---------------------------------------------------------------------------------------
     def process(self, raw_detections: Sequence[Dict], segmentation_results: Dict, image_shape: Tuple) -> List[Dict]:
         refined = self._refine_detections(raw_detections, segmentation_results, image_shape)

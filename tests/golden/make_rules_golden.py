@@ -36,6 +36,9 @@ def main():
         snap["merged"] = jsonable(merged)
         validated = pp._validate_detections(merged, shape)
         snap["validated"] = jsonable(validated)
+        seg_q = dict(seg, defect_density=1.25)
+        snap["quality"] = jsonable(pp._assess_quality(validated, seg_q))
+        snap["quality_refined"] = jsonable(pp._assess_quality(refined, seg_q))      # more rows: other grades
         golden[name] = snap
         print(name, len(dets), "->", len(refined), len(filtered), len(merged), len(validated))
     import gzip
