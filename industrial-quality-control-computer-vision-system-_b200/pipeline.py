@@ -29,6 +29,17 @@ RESNET_MEAN = (0.485, 0.456, 0.406)
 RESNET_STD = (0.229, 0.224, 0.225)
 
 
+def chunk_plan(total: int, sizes: Sequence[int]) -> List[tuple]:
+    """Static-shape launches for ``total`` classifier rows: [(graph batch size, rows used)].  ``sizes`` is sorted
+    largest first; every launch but the last is filled completely, the remainder rounds up to the smallest size."""
+    out, left = [], int(total)
+    while left > 0:
+        cs = next((c for c in sizes if c <= left), sizes[-1])
+        out.append((cs, min(cs, left)))
+        left -= min(cs, left)
+    return out
+
+
 @dataclass
 class BatchResult:
     n: int
@@ -218,11 +229,7 @@ class InspectionPipeline:
             else:
                 # static-shape chunks: K3b/K3 write each chunk straight into the graph's input buffer
                 parts, o = [], 0
-                while o < nro:
-                    rem = nro - o
-                    # largest static size that is filled completely; the last few rows round up to the smallest
-                    cs = next((c for c in self.crop_chunks if c <= rem), self.crop_chunks[-1])
-                    k = min(cs, rem)
+                for cs, k in chunk_plan(nro, self.crop_chunks):
                     shape = (cs, 3, 224, 224)
                     buf = self.resnet_g.input_buffer(shape)
                     fill(buf, o, k)

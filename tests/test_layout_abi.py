@@ -131,3 +131,15 @@ def test_pil_resize_tables_match_pillow_coefficients():
             o1 = min(o0 + band, oh) - 1
             assert by[o1, 0] + by[o1, 1] - by[o0, 0] <= max_rows
     assert lib.qc_pil_resize_make_tables(0, 5, 224, 224, t.ctypes.data) != 0
+
+
+def test_classifier_chunk_plan():
+    """Static ResNet batch sizes: every launch but the last is full, the tail rounds up to the smallest graph."""
+    from qcgraft.pipeline import chunk_plan
+    sizes = (256, 128, 64, 32, 16, 8)
+    assert chunk_plan(1432, sizes) == [(256, 256)] * 5 + [(128, 128), (16, 16), (8, 8)]
+    assert chunk_plan(3, sizes) == [(8, 3)] and chunk_plan(0, sizes) == [] and chunk_plan(8, sizes) == [(8, 8)]
+    assert chunk_plan(265, sizes) == [(256, 256), (8, 8), (8, 1)]
+    for total in range(0, 700, 37):
+        plan = chunk_plan(total, sizes)
+        assert sum(k for _, k in plan) == total and all(k == c for c, k in plan[:-1]) and all(c in sizes for c, _ in plan)
