@@ -605,8 +605,9 @@ class _PassThroughPostProcessor:
 class RulesPostProcessor(_PassThroughPostProcessor):
     """PostProcessor.process_results (inference/postprocess.py:32-109) with the detection chain
     refine -> filter -> merge -> validate computed by ``rules.DetectionRules`` (the array form of row f1, pinned
-    against the reference's own class) and the numeric quality assessment (:466-599).  Risk factors and recommendation
-    texts are not restated: plug the reference's PostProcessor object for those.  Select with ``config['qcgraft']['postprocessor'] = 'rules'``."""
+    against the reference's own class), the quality assessment (:466-599) and the risk analysis (:601-682).  The
+    recommendation texts are not restated (the reference emits them in the iteration order of a Python set of class
+    names, i.e. in no reproducible order): plug the reference's PostProcessor object for those.  Select with ``config['qcgraft']['postprocessor'] = 'rules'``."""
 
     def __init__(self, config):
         super().__init__(config)
@@ -615,12 +616,14 @@ class RulesPostProcessor(_PassThroughPostProcessor):
 
     def process_results(self, ensemble_results, segmentation_results, image_shape):
         try:
-            dets = self.rules.process(ensemble_results.get("detections", []), segmentation_results or {}, image_shape)
+            raw = ensemble_results.get("detections", [])
+            dets = self.rules.process(raw, segmentation_results or {}, image_shape)
             quality = self.rules._assess_quality(dets, segmentation_results or {})
+            risk = self.rules._analyze_risks(dets, quality) if raw else {}     # no raw detections: early return (:62-64)
         except Exception as e:                                    # the reference's convention: never raise
             logger.error(f"Error in post-processing: {str(e)}")
             return {"error": str(e)}
-        return {"detections": dets, "quality_assessment": quality, "risk_analysis": {}, "recommendations": [],
+        return {"detections": dets, "quality_assessment": quality, "risk_analysis": risk, "recommendations": [],
                 "metadata": {"total_detections": len(dets), "image_shape": tuple(image_shape),
                              "post_processing_version": "1.0.0"}}
 

@@ -322,6 +322,58 @@ class DetectionRules:
                 "quality_score": score, "meets_requirements": pass_fail == "PASS",
                 "recommended_action": self.ACTIONS.get((pass_fail, risk), "manual_inspection")}
 
+    # -- :601-682 -------------------------------------------------------------------------------------
+    @staticmethod
+    def _analyze_defect_clustering(detections: Sequence[Dict]) -> Dict:
+        """DBSCAN(eps=100, min_samples=2) on the box centres: with two samples per core point every point that has
+        another one within 100 px is a core point, so the clusters are the connected components of that graph and
+        the rest is noise.  (Squared distances against 100^2, like the KD-tree sklearn picks for 2-D points.)"""
+        k = len(detections)
+        if k < 3:
+            return {"has_clusters": False, "cluster_count": 0}
+        p = np.array([[d["bbox"]["center_x"], d["bbox"]["center_y"]] for d in detections], np.float64)
+        d2 = ((p[:, None, :] - p[None, :, :]) ** 2).sum(2)
+        near = d2 <= 100.0 * 100.0
+        np.fill_diagonal(near, False)
+        has_nb = near.any(1)
+        parent = np.arange(k)
+
+        def find(a):
+            while parent[a] != a:
+                parent[a] = parent[parent[a]]
+                a = parent[a]
+            return a
+        for a, b in zip(*np.nonzero(np.triu(near, 1))):
+            ra, rb = find(int(a)), find(int(b))
+            if ra != rb:
+                parent[max(ra, rb)] = min(ra, rb)
+        n_clusters = len({find(i) for i in range(k) if has_nb[i]})
+        return {"has_clusters": n_clusters > 0, "cluster_count": n_clusters, "clustered_defects": np.sum(has_nb),
+                "isolated_defects": np.sum(~has_nb)}
+
+    def _analyze_risks(self, detections: Sequence[Dict], quality_assessment: Dict) -> Dict:
+        """Risk score from clustering, large (> 1000 px) and critical defects.  The reference leaves its clustering
+        variable unset for an empty list and fails there (process_results then returns its error dict); an empty
+        list is reported here as no clusters."""
+        factors, score = [], 0.0
+        cluster = {"has_clusters": False, "cluster_count": 0}
+        if len(detections) > 0:
+            cluster = self._analyze_defect_clustering(detections)
+            if cluster["has_clusters"]:
+                factors.append("Clustered defects detected - possible systematic issue")
+                score += 0.3
+            n_large = sum(1 for d in detections if d.get("area_pixels", 0) > 1000)
+            if n_large:
+                factors.append(f"{n_large} large defects detected")
+                score += 0.2 * n_large
+            n_crit = sum(1 for d in detections if d.get("final_severity") == "critical")
+            if n_crit:
+                factors.append("Critical defects present - immediate attention required")
+                score += 0.5 * n_crit
+        level = "high" if score >= 1.0 else ("medium" if score >= 0.5 else "low")
+        return {"overall_risk_level": level, "risk_score": min(score, 1.0), "risk_factors": factors,
+                "defect_clustering": cluster, "requires_immediate_action": quality_assessment["pass_fail_status"] == "FAIL"}
+
     # -- :64-81 ---------------------------------------------------------------------------------------
     def process(self, raw_detections: Sequence[Dict], segmentation_results: Dict, image_shape: Tuple) -> List[Dict]:
         refined = self._refine_detections(raw_detections, segmentation_results, image_shape)

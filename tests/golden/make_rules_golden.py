@@ -39,6 +39,10 @@ def main():
         seg_q = dict(seg, defect_density=1.25)
         snap["quality"] = jsonable(pp._assess_quality(validated, seg_q))
         snap["quality_refined"] = jsonable(pp._assess_quality(refined, seg_q))      # more rows: other grades
+        if validated:
+            snap["risk"] = jsonable(pp._analyze_risks(validated, pp._assess_quality(validated, seg_q)))
+        if refined:
+            snap["risk_refined"] = jsonable(pp._analyze_risks(refined, pp._assess_quality(refined, seg_q)))
         golden[name] = snap
         print(name, len(dets), "->", len(refined), len(filtered), len(merged), len(validated))
     import gzip
