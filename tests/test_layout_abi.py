@@ -143,3 +143,23 @@ def test_classifier_chunk_plan():
     for total in range(0, 700, 37):
         plan = chunk_plan(total, sizes)
         assert sum(k for _, k in plan) == total and all(k == c for c, k in plan[:-1]) and all(c in sizes for c, _ in plan)
+
+
+def test_entry_points_reject_null_context_without_touching_cuda():
+    """Every compute entry point validates its context first: with a NULL qc_ctx it returns an error code and never
+    reaches a CUDA call (this runs on a box without a GPU)."""
+    from qcgraft import ffi
+    lib = ffi.load_library()
+    z = C.c_void_p(0)
+    assert lib.qc_preprocess(None, z, 1, 0, 0, C.byref(ffi.PrePlan()), z, 114, 0, 0, z, z) != 0
+    assert lib.qc_yolo_decode_nms(None, None, C.byref(ffi.YoloParams()), z, 0, z, z, z, z, z) != 0
+    assert lib.qc_nms(None, z, z, z, z, 1, 8, 0.5, 7680.0, 300, z, 0, z, z, z) != 0
+    assert lib.qc_roi_align(None, z, 1, 8, 8, 192, 24, z, 1, 224, 224, 2, 1, 0, z, 1, z, z) != 0
+    assert lib.qc_pil_resize(None, z, 1, 8, 8, 192, 24, z, z, 0, z, 1, z, z) != 0
+    assert lib.qc_segment(None, z, C.byref(ffi.SegParams()), z, z, 0, z, z, z, z, z, z, z) != 0
+    assert lib.qc_spc_stats(None, z, z, 1, 300, z, z) != 0
+    assert lib.qc_rules_cluster(None, z, z, z, z, 1, 300, 0.3, z, z) != 0
+    assert lib.qc_last_error(None) == b"null context" and lib.qc_launch_count(None) == 0 and lib.qc_sm_count(None) == 0
+    # geometry helpers are pure host code and do work without a device
+    assert lib.qc_pil_resize_table_bytes(640, 640, 224, 224) > 0 and lib.qc_pil_resize_table_bytes(0, 640, 224, 224) == 0
+    assert lib.qc_nms_workspace_bytes(2, 100) > 0 and lib.qc_nms_workspace_bytes(0, 100) == 0
