@@ -165,3 +165,17 @@ def test_pil_resize_restatement_is_bit_exact(hw):
     tf = T.Compose([T.Resize((224, 224)), T.ToTensor(),
                     T.Normalize(mean=[0.485, 0.456, 0.406], std=[0.229, 0.224, 0.225])])
     assert np.array_equal(pr.resnet_input(img), tf(Image.fromarray(img)).numpy())
+
+
+def test_fill_holes_restatement_matches_scipy():
+    """Row f3 preparation: binary_fill_holes (inference/segmentation.py:455-456) == border-reachability of the
+    4-connected background."""
+    from scipy import ndimage
+    from oracle.fill_holes import fill_holes
+    rng = np.random.default_rng(9)
+    for shape, dens in [((40, 60), 0.5), ((97, 131), 0.62), ((64, 64), 0.3), ((1, 17), 0.5), ((17, 1), 0.5), ((200, 300), 0.55)]:
+        m = rng.random(shape) < dens
+        assert np.array_equal(fill_holes(m), ndimage.binary_fill_holes(m)), shape
+    ring = np.zeros((9, 9), bool); ring[2:7, 2:7] = True; ring[4, 4] = False; ring[3, 3] = False   # diagonal hole pair
+    assert np.array_equal(fill_holes(ring), ndimage.binary_fill_holes(ring))
+    assert fill_holes(np.zeros((5, 5), bool)).sum() == 0 and fill_holes(np.ones((5, 5), bool)).all()
