@@ -144,7 +144,6 @@ __global__ void __launch_bounds__(K4_THREADS)
 k4_gray(Img im, const qc_seg_region* __restrict__ regs, int R, int total_bands, const int* __restrict__ g_band_off,
         uint8_t* __restrict__ gray_ws) {
     __shared__ int s_off[K4_LOC_MAX + 1];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int* off = loc_load(s_off, g_band_off, R);
     for (int t = blockIdx.x; t < total_bands; t += gridDim.x) {
         const qc_seg_region rg = regs[loc_find(off, R, t)];
