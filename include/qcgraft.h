@@ -222,6 +222,46 @@ int qc_segment(qc_ctx* ctx, const uint8_t* imgs, const qc_seg_params* p,
                uint8_t* out_mask, int32_t* out_labels, int32_t* out_ncomp, int32_t* out_stats,
                int32_t* out_thr, int64_t* out_area, void* stream);
 
+/* ---- K7: the reference's own per-class segmentation methods (row f3) -----------------
+ * qc_segment() above is the north-star composite (Otsu -> morphology -> CCL).  qc_segment_ref() runs, on the same
+ * region tables / workspace / outputs, the two methods inference/segmentation.py:185-195 actually routes to:
+ *
+ *   QC_SEG_REF_THRESHOLD  _threshold_segmentation :197-246 + _clean_mask :449-462, literally:
+ *       skimage gaussian(sigma=1): img_as_float (v * (1/255)) then scipy's 9-tap float64 correlate1d along axis 0,
+ *       then axis 1, mode='nearest' (operation order of ni_filters.c, no fma)
+ *       -> threshold_otsu: np.histogram(256 bins over [min,max]) with numpy's edge-corrected binning, float32
+ *          counts/weights, float64 means, first argmax, bin CENTRE; a constant image returns its value
+ *       -> x region.thr_scale (class factor) -> blurred < T (polarity 0) | blurred > T (polarity 1)
+ *       -> components with area < region.min_area removed (cv2.connectedComponents, 8-conn; reference: 10)
+ *       -> scipy.ndimage.binary_fill_holes (4-connected background reachable from the ROI border stays)
+ *       -> closing then opening with the 3x3 cross x morph_iters (skimage disk(2) == 2 iterations).
+ *     Outputs: out_area = np.sum(mask>0); out_mask; out_labels = 1 on the mask (the reference does not label the
+ *     final mask); out_ncomp = 2 if the mask is non-empty else 1; stats row 1 = extent (x,y,w,h) + area of the WHOLE
+ *     mask (what inference/postprocess.py:784-790 reads); out_thr = index of the Otsu bin.
+ *   QC_SEG_REF_ADAPTIVE   _adaptive_segmentation :248-298:
+ *       cv2.adaptiveThreshold(ADAPTIVE_THRESH_GAUSSIAN_C, polarity 0: BINARY_INV | 1: BINARY,
+ *       block = max(11, min(h,w)/10) | 1, C = adaptive_c): mean = cvRound(float32 separable Gaussian, replicate
+ *       border) with cv2's summation order (fused multiply-adds of its AVX2 path: columns < w&~7 fused in both
+ *       passes, the next group of 4 fused in the row pass only, the last w%4 columns unfused), then
+ *       src - mean > -C (<= -C for INV) -> 3x3 cross close/open x morph_iters (reference: 1) -> min-area filter
+ *       (reference: 20) with the full K4 outputs (labels in cv2 numbering, per-component stats).
+ *     akern: device float32 table of cv2.getGaussianKernel(bs, -1, CV_32F), row (bs-11)/2 holding the bs taps of
+ *     block size bs, row pitch akern_pitch floats, rows up to akern_max_block (the caller fills it with cv2's own
+ *     numbers, like the K1 LUT; only needed for QC_SEG_REF_ADAPTIVE).
+ *
+ * out_sums (may be NULL): int64 [num_regions][4] = (sum of gray over the mask, sum of gray, sum of gray^2, pixels of
+ * the ROI) -- the integers behind inference/segmentation.py:527-555's confidence (means and std of the ROI).
+ * workspace: qc_segment_ref_workspace_bytes(p, method).                                                    */
+typedef enum { QC_SEG_COMPOSITE = 0, QC_SEG_REF_THRESHOLD = 1, QC_SEG_REF_ADAPTIVE = 2 } qc_seg_method;
+
+size_t qc_segment_ref_workspace_bytes(const qc_seg_params* p, int method);
+
+int qc_segment_ref(qc_ctx* ctx, int method, const uint8_t* imgs, const qc_seg_params* p,
+                   const qc_seg_region* regions, const float* akern, int akern_pitch, int akern_max_block,
+                   int adaptive_c, void* workspace, size_t workspace_bytes, uint8_t* out_mask,
+                   int32_t* out_labels, int32_t* out_ncomp, int32_t* out_stats, int32_t* out_thr,
+                   int64_t* out_area, int64_t* out_sums, void* stream);
+
 /* ---- SPC per-batch statistics (payload of the one NCCL all-reduce) ---------
  * Device-side reduction of K2's outputs into the 9-vector derived from
  * analytics/sec_analysis.py:105-147: [n_images, sum defects, sum defects^2, sum conf,

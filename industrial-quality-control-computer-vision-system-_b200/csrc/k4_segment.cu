@@ -62,10 +62,16 @@ struct SegWs {
     int* chunk_base;      // [total_chunks]
     int* band_off;        // [R+1] cumulative bands
     int* chunk_off;       // [R+1] cumulative ranking chunks
+    // K7 (reference methods) only
+    unsigned* bits2;      // [total_bits_words]
+    unsigned* bits3;      // [total_bits_words]
+    double* blurred;      // [total_pixels]   sigma=1 float64 image (threshold method)
+    unsigned long long* minmax;   // [R][2]
+    double* thr_adj;      // [R]
     size_t total;
 };
 
-SegWs carve(void* base, const qc_seg_params* p) {
+SegWs carve(void* base, const qc_seg_params* p, int method = QC_SEG_COMPOSITE) {
     SegWs w;
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = qc_align_up(off + bytes, 256); return o; };
@@ -73,7 +79,8 @@ SegWs carve(void* base, const qc_seg_params* p) {
     const size_t R = (size_t)p->num_regions;
     w.hist = (unsigned*)(b + take(R * 256 * 4));
     w.cmp = (int*)(b + take(R * 2 * 4));
-    w.gray = (uint8_t*)(b + take(p->channels == 3 ? (size_t)p->total_pixels : 0));
+    // (+64: ld16_any and the K7 tiles may read a few bytes past the last region)
+    w.gray = (uint8_t*)(b + take(p->channels == 3 ? (size_t)p->total_pixels + 64 : 0));
     w.bits = (unsigned*)(b + take((size_t)p->total_bits_words * 4));
     w.parent = (int*)(b + take((size_t)p->total_blocks * 4));
     w.rank = (int*)(b + take((size_t)p->total_blocks * 4));
@@ -81,6 +88,12 @@ SegWs carve(void* base, const qc_seg_params* p) {
     w.chunk_base = (int*)(b + take((size_t)p->total_chunks * 4));
     w.band_off = (int*)(b + take((R + 1) * 4));
     w.chunk_off = (int*)(b + take((R + 1) * 4));
+    const bool ref = method != QC_SEG_COMPOSITE, thr = method == QC_SEG_REF_THRESHOLD;
+    w.bits2 = (unsigned*)(b + take(ref ? (size_t)p->total_bits_words * 4 : 0));
+    w.bits3 = (unsigned*)(b + take(thr ? (size_t)p->total_bits_words * 4 : 0));
+    w.blurred = (double*)(b + take(thr ? (size_t)p->total_pixels * 8 : 0));
+    w.minmax = (unsigned long long*)(b + take(thr ? R * 16 : 0));
+    w.thr_adj = (double*)(b + take(thr ? R * 8 : 0));
     w.total = off;
     return w;
 }
@@ -528,7 +541,8 @@ __device__ __forceinline__ uint4 ld16_any(const uint8_t* p) {
 __global__ void __launch_bounds__(K4_THREADS)
 k4_mask(Img im, const qc_seg_region* __restrict__ regs, int R, int total_bands,
             const int* __restrict__ g_band_off, int iters, const int* __restrict__ cmp,
-            const uint8_t* __restrict__ gray_ws, unsigned* __restrict__ bits, int buf_words) {
+            const uint8_t* __restrict__ gray_ws, unsigned* __restrict__ bits, int buf_words,
+            const unsigned* __restrict__ bits_in) {
     extern __shared__ __align__(16) unsigned sm[];
     unsigned* bufA = sm;
     unsigned* bufB = sm + buf_words;
@@ -546,7 +560,12 @@ k4_mask(Img im, const qc_seg_region* __restrict__ regs, int R, int total_bands,
         const int y1 = min(y0 + BR, rg.h);
         const int row_lo = max(y0 - halo, 0), row_hi = min(y1 + halo, rg.h);
         const int nrows = row_hi - row_lo;
-        const int lo = cmp[2 * r], hi = cmp[2 * r + 1];
+        if (bits_in) {
+            // K7: the pre-morphology mask already exists as bit rows (adaptive threshold / filled mask)
+            const unsigned* Bin = bits_in + rg.bits_offset + (long long)row_lo * wpr;
+            for (int i = tid; i < nrows * wpr; i += K4_THREADS) bufA[i] = __ldg(Bin + i);
+        }
+        const int lo = bits_in ? 0 : cmp[2 * r], hi = bits_in ? 0 : cmp[2 * r + 1];
         // ---- threshold into bit rows: a lane turns 16 pixels into 16 bits, lane pairs form words ----
         const uint8_t* gbase;
         long long gpitch;
@@ -558,7 +577,7 @@ k4_mask(Img im, const qc_seg_region* __restrict__ regs, int R, int total_bands,
         // work items = (row, 16-pixel segment), flattened so that narrow regions (a 150-px ROI row is 10 segments)
         // still fill the warp; a warp takes 128 consecutive items per round and issues its four 128-bit loads
         // before the first compare.  segs is even, so the two halves of a 32-pixel word sit in adjacent lanes.
-        const int nitems = nrows * segs;
+        const int nitems = bits_in ? 0 : nrows * segs;
         const float inv_segs = 1.0f / (float)segs;
         for (int t0 = warp * 128; t0 < nitems; t0 += (K4_THREADS / 32) * 128) {
             uint4 v[4];
@@ -925,7 +944,8 @@ __device__ __forceinline__ Cell load_cell(const qc_seg_region& rg, const unsigne
 
 __global__ void __launch_bounds__(K4_CHUNK)
 k4_compress(const qc_seg_region* __restrict__ regs, int R, int total_chunks, const int* __restrict__ g_chunk_off,
-            const unsigned* __restrict__ bits, int* __restrict__ parent, int* __restrict__ chunk_count) {
+            const unsigned* __restrict__ bits, int* __restrict__ parent, int* __restrict__ chunk_count,
+            int* __restrict__ zero_area) {
     __shared__ int s_off[K4_LOC_MAX + 1];
     __shared__ unsigned s_v[K4_CHUNK];          // r0|r1 of every cell of the chunk
     __shared__ int s_base[K4_CHUNK];
@@ -951,6 +971,7 @@ k4_compress(const qc_seg_region* __restrict__ regs, int R, int total_chunks, con
             const int g = s_base[cell] + k;
             const int rt = uf_find(parent, g);
             parent[g] = rt;
+            if (zero_area) zero_area[g] = 0;
             cnt += (rt == g);
         }
 #pragma unroll
@@ -1190,6 +1211,8 @@ k4_final(const qc_seg_region* __restrict__ regs, int R, int total_bands, const i
     }
 }
 
+#include "k7_refseg.cuh"
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------
@@ -1238,50 +1261,45 @@ extern "C" size_t qc_segment_workspace_bytes(const qc_seg_params* p) {
     return carve(nullptr, p).total;
 }
 
-extern "C" int qc_segment(qc_ctx* ctx, const uint8_t* imgs, const qc_seg_params* p, const qc_seg_region* regions,
-                          void* workspace, size_t workspace_bytes, uint8_t* out_mask, int32_t* out_labels,
-                          int32_t* out_ncomp, int32_t* out_stats, int32_t* out_thr, int64_t* out_area, void* stream) {
+extern "C" size_t qc_segment_ref_workspace_bytes(const qc_seg_params* p, int method) {
+    if (!p || p->num_regions <= 0 || method < QC_SEG_COMPOSITE || method > QC_SEG_REF_ADAPTIVE) return 0;
+    return carve(nullptr, p, method).total;
+}
+
+namespace {
+
+struct SegOut {
+    uint8_t* mask; int32_t* labels; int32_t* ncomp; int32_t* stats; int32_t* thr; int64_t* area; int64_t* sums;
+};
+struct SegAdaptive {
+    const float* akern; int pitch, max_block, c;
+};
+
+int seg_run(qc_ctx* ctx, int method, const uint8_t* imgs, const qc_seg_params* p, const qc_seg_region* regions,
+            const SegAdaptive& ad, void* workspace, size_t workspace_bytes, const SegOut& o, void* stream) {
+    const char* fn = method == QC_SEG_COMPOSITE ? "qc_segment" : "qc_segment_ref";
     if (!ctx) return QC_ERR_INVALID;
-    if (!p) QC_FAIL(ctx, QC_ERR_INVALID, "qc_segment: null params");
+    if (!p) QC_FAIL(ctx, QC_ERR_INVALID, "%s: null params", fn);
+    if (method < QC_SEG_COMPOSITE || method > QC_SEG_REF_ADAPTIVE) QC_FAIL(ctx, QC_ERR_INVALID, "%s: bad method %d", fn, method);
     if (p->num_regions == 0) return QC_OK;
-    if (!imgs || !regions || !out_ncomp || !out_stats || !out_thr || !out_area)
-        QC_FAIL(ctx, QC_ERR_INVALID, "qc_segment: null argument");
+    if (!imgs || !regions || !o.ncomp || !o.stats || !o.thr || !o.area)
+        QC_FAIL(ctx, QC_ERR_INVALID, "%s: null argument", fn);
     if ((p->channels != 1 && p->channels != 3) || p->morph_iters < 0 || p->morph_iters > 4 || p->total_bands <= 0 ||
         p->row_stride < p->w * p->channels)
-        QC_FAIL(ctx, QC_ERR_INVALID, "qc_segment: bad params (run qc_segment_plan first)");
-    SegWs w = carve(workspace, p);
+        QC_FAIL(ctx, QC_ERR_INVALID, "%s: bad params (run qc_segment_plan first)", fn);
+    SegWs w = carve(workspace, p, method);
     if (!workspace || workspace_bytes < w.total) QC_FAIL(ctx, QC_ERR_WORKSPACE, "workspace %zu < %zu", workspace_bytes, w.total);
     cudaStream_t st = (cudaStream_t)stream;
     const int R = p->num_regions;
     Img im{imgs, p->img_stride, p->row_stride, p->channels, p->swap_rb};
     const int sms = ctx->sm_count;
-
-    k4_init<<<std::min(sms * 4, std::max(1, (p->total_stats_rows + 255) / 256)), 256, 0, st>>>(
-        regions, R, w.hist, out_stats, (long long*)out_area, p->total_stats_rows, w.band_off, w.chunk_off,
-        p->total_bands, p->total_chunks);
-    QC_LAUNCHED(ctx);
-
-    if (p->channels == 3) {
-        k4_gray<<<std::min(p->total_bands, sms * 8), K4_THREADS, 0, st>>>(im, regions, R, p->total_bands, w.band_off, w.gray);
-        QC_LAUNCHED(ctx);
-    }
-    {
-        if (int rc = qc_prepare(ctx, k4_hist, K4_HIST_SMEM, K4_HIST_THREADS, nullptr)) return rc;
-        const int nw = K4_HIST_THREADS / 32;
-        const int items = p->total_bands * K4_HIST_SPLIT;
-        k4_hist<<<std::min((items + nw - 1) / nw, sms), K4_HIST_THREADS, K4_HIST_SMEM, st>>>(
-            im, regions, R, p->total_bands, w.band_off, w.hist, w.gray);
-        QC_LAUNCHED(ctx);
-    }
-
-    k4_otsu<<<std::min((R + K4_OTSU_WARPS - 1) / K4_OTSU_WARPS, sms * 8), K4_OTSU_WARPS * 32, 0, st>>>(regions, R, w.hist,
-                                                                                                          w.cmp, out_thr);
-    QC_LAUNCHED(ctx);
+    const int band_grid = std::min(p->total_bands, sms * 8);
+    const int chunk_grid = std::min(p->total_chunks, sms * 8);
 
     const int halo = 4 * p->morph_iters;
     const int wpr_max = (p->max_region_w + 31) / 32;
     if (wpr_max > 256)      // k4_ccl_local packs (block row, word) of a cell into 8+8 bits
-        QC_FAIL(ctx, QC_ERR_UNSUPPORTED, "qc_segment: region width %d > 8192", p->max_region_w);
+        QC_FAIL(ctx, QC_ERR_UNSUPPORTED, "%s: region width %d > 8192", fn, p->max_region_w);
     // conservative bounds over every region: rows x words <= RW whatever the region width
     const int RW = std::max(K4_BAND_RW, K4_MIN_ROWS * wpr_max);
     const int buf_words = RW + 2 * halo * wpr_max;
@@ -1291,37 +1309,133 @@ extern "C" int qc_segment(qc_ctx* ctx, const uint8_t* imgs, const qc_seg_params*
     const size_t smem_ccl = (size_t)band_words * 4 + (size_t)lab_words * 4 + (size_t)(RW / 2) * 2;
     const size_t smem_need = std::max(smem_mask, smem_ccl);
     if ((long long)smem_need + (K4_LOC_MAX + 1) * 4 + 1024 > ctx->max_smem_optin)
-        QC_FAIL(ctx, QC_ERR_UNSUPPORTED, "qc_segment: region width %d needs %zu B of shared memory (max %d)",
+        QC_FAIL(ctx, QC_ERR_UNSUPPORTED, "%s: region width %d needs %zu B of shared memory (max %d)", fn,
                 p->max_region_w, smem_need, ctx->max_smem_optin);
     int occ = 1;
-    if (int rc = qc_prepare(ctx, k4_mask, (int)smem_mask, K4_THREADS, &occ)) return rc;
-    k4_mask<<<std::min(p->total_bands, sms * std::max(occ, 1)), K4_THREADS, smem_mask, st>>>(
-        im, regions, R, p->total_bands, w.band_off, p->morph_iters, w.cmp, w.gray, w.bits, buf_words);
-    QC_LAUNCHED(ctx);
-    if (int rc = qc_prepare(ctx, k4_ccl_local, (int)smem_ccl, K4_THREADS, &occ)) return rc;
-    k4_ccl_local<<<std::min(p->total_bands, sms * std::max(occ, 1)), K4_THREADS, smem_ccl, st>>>(
-        regions, R, p->total_bands, w.band_off, w.bits, w.parent, band_words, lab_words);
-    QC_LAUNCHED(ctx);
 
-    const int band_grid = std::min(p->total_bands, sms * 8);
-    k4_border<<<band_grid, K4_THREADS, 0, st>>>(regions, R, p->total_bands, w.band_off, w.bits, w.parent);
-    QC_LAUNCHED(ctx);
+    // stage helpers -----------------------------------------------------------------------------------------
+    auto morph = [&](const unsigned* bits_in, unsigned* bits_out) -> int {          // (threshold |) close, open
+        if (int rc = qc_prepare(ctx, k4_mask, (int)smem_mask, K4_THREADS, &occ)) return rc;
+        k4_mask<<<std::min(p->total_bands, sms * std::max(occ, 1)), K4_THREADS, smem_mask, st>>>(
+            im, regions, R, p->total_bands, w.band_off, p->morph_iters, w.cmp, w.gray, bits_out, buf_words, bits_in);
+        QC_LAUNCHED(ctx);
+        return QC_OK;
+    };
+    auto unionfind = [&](const unsigned* bits, int* zero_area) -> int {             // parent[g] = root afterwards
+        if (int rc = qc_prepare(ctx, k4_ccl_local, (int)smem_ccl, K4_THREADS, &occ)) return rc;
+        k4_ccl_local<<<std::min(p->total_bands, sms * std::max(occ, 1)), K4_THREADS, smem_ccl, st>>>(
+            regions, R, p->total_bands, w.band_off, bits, w.parent, band_words, lab_words);
+        QC_LAUNCHED(ctx);
+        k4_border<<<band_grid, K4_THREADS, 0, st>>>(regions, R, p->total_bands, w.band_off, bits, w.parent);
+        QC_LAUNCHED(ctx);
+        k4_compress<<<chunk_grid, K4_CHUNK, 0, st>>>(regions, R, p->total_chunks, w.chunk_off, bits, w.parent,
+                                                     w.chunk_count, zero_area);
+        QC_LAUNCHED(ctx);
+        return QC_OK;
+    };
+    auto label_tail = [&](const unsigned* bits) -> int {                            // cv2 numbering, stats, outputs
+        k4_scan<<<std::min(R, sms * 2), 1024, 0, st>>>(regions, R, w.chunk_count, w.chunk_base, o.ncomp);
+        QC_LAUNCHED(ctx);
+        k4_rank<<<chunk_grid, K4_CHUNK, 0, st>>>(regions, R, p->total_chunks, w.chunk_off, bits, w.parent, w.chunk_base,
+                                                 w.rank);
+        QC_LAUNCHED(ctx);
+        k4_stats<<<band_grid, K4_THREADS, 0, st>>>(regions, R, p->total_bands, w.band_off, bits, w.parent, w.rank,
+                                                   o.stats);
+        QC_LAUNCHED(ctx);
+        k4_final<<<band_grid, K4_THREADS, 0, st>>>(regions, R, p->total_bands, w.band_off, bits, w.parent, o.stats,
+                                                   o.ncomp, o.mask, o.labels, (long long*)o.area);
+        QC_LAUNCHED(ctx);
+        return QC_OK;
+    };
 
-    const int chunk_grid = std::min(p->total_chunks, sms * 8);
-    k4_compress<<<chunk_grid, K4_CHUNK, 0, st>>>(regions, R, p->total_chunks, w.chunk_off, w.bits, w.parent,
-                                                 w.chunk_count);
+    k4_init<<<std::min(sms * 4, std::max(1, (p->total_stats_rows + 255) / 256)), 256, 0, st>>>(
+        regions, R, w.hist, o.stats, (long long*)o.area, p->total_stats_rows, w.band_off, w.chunk_off,
+        p->total_bands, p->total_chunks);
     QC_LAUNCHED(ctx);
-    k4_scan<<<std::min(R, sms * 2), 1024, 0, st>>>(regions, R, w.chunk_count, w.chunk_base, out_ncomp);
-    QC_LAUNCHED(ctx);
-    k4_rank<<<chunk_grid, K4_CHUNK, 0, st>>>(regions, R, p->total_chunks, w.chunk_off, w.bits, w.parent, w.chunk_base,
-                                             w.rank);
-    QC_LAUNCHED(ctx);
+    if (p->channels == 3) {
+        k4_gray<<<std::min(p->total_bands, sms * 8), K4_THREADS, 0, st>>>(im, regions, R, p->total_bands, w.band_off, w.gray);
+        QC_LAUNCHED(ctx);
+    }
 
-    k4_stats<<<band_grid, K4_THREADS, 0, st>>>(regions, R, p->total_bands, w.band_off, w.bits, w.parent, w.rank,
-                                               out_stats);
+    if (method == QC_SEG_COMPOSITE) {
+        if (int rc = qc_prepare(ctx, k4_hist, K4_HIST_SMEM, K4_HIST_THREADS, nullptr)) return rc;
+        const int nw = K4_HIST_THREADS / 32;
+        const int items = p->total_bands * K4_HIST_SPLIT;
+        k4_hist<<<std::min((items + nw - 1) / nw, sms), K4_HIST_THREADS, K4_HIST_SMEM, st>>>(
+            im, regions, R, p->total_bands, w.band_off, w.hist, w.gray);
+        QC_LAUNCHED(ctx);
+        k4_otsu<<<std::min((R + K4_OTSU_WARPS - 1) / K4_OTSU_WARPS, sms * 8), K4_OTSU_WARPS * 32, 0, st>>>(
+            regions, R, w.hist, w.cmp, o.thr);
+        QC_LAUNCHED(ctx);
+        if (int rc = morph(nullptr, w.bits)) return rc;
+        if (int rc = unionfind(w.bits, nullptr)) return rc;
+        return label_tail(w.bits);
+    }
+
+    if (method == QC_SEG_REF_ADAPTIVE) {
+        if (!ad.akern || ad.pitch <= 0) QC_FAIL(ctx, QC_ERR_INVALID, "%s: adaptive method needs the Gaussian kernel table", fn);
+        const int bmax = k7_block_size(p->max_region_w, p->max_region_h);       // >= every region's block size
+        if (bmax > ad.max_block || bmax > ad.pitch)
+            QC_FAIL(ctx, QC_ERR_INVALID, "%s: kernel table covers block <= %d, regions need %d", fn, ad.max_block, bmax);
+        const int pmax = bmax / 2;
+        const size_t smem_ad = (size_t)((2 * pmax + 1 + 3) & ~3) * 4 + (size_t)(32 + 2 * pmax) * 33 * 4 +
+                               (size_t)(32 + 2 * pmax) * (32 + 2 * pmax);
+        if ((long long)smem_ad + (K4_LOC_MAX + 1) * 4 + 1024 > ctx->max_smem_optin)
+            QC_FAIL(ctx, QC_ERR_UNSUPPORTED, "%s: adaptive block %d needs %zu B of shared memory", fn, bmax, smem_ad);
+        if (int rc = qc_prepare(ctx, k7_adaptive, (int)smem_ad, K4_THREADS, &occ)) return rc;
+        k7_adaptive<<<std::min(p->total_bands, sms * std::max(occ, 1)), K4_THREADS, smem_ad, st>>>(
+            im, regions, R, p->total_bands, w.band_off, w.gray, ad.akern, ad.pitch, ad.c, w.bits2, pmax);
+        QC_LAUNCHED(ctx);
+        k7_block_out<<<(R + 255) / 256, 256, 0, st>>>(regions, R, o.thr, (long long*)o.sums);
+        QC_LAUNCHED(ctx);
+        if (int rc = morph(w.bits2, w.bits)) return rc;
+        if (int rc = unionfind(w.bits, nullptr)) return rc;
+        return label_tail(w.bits);
+    }
+
+    // QC_SEG_REF_THRESHOLD
+    k7_init<<<std::max(1, std::min(sms, (R * 4 + 255) / 256)), 256, 0, st>>>(R, w.minmax, (long long*)o.sums);
     QC_LAUNCHED(ctx);
-    k4_final<<<band_grid, K4_THREADS, 0, st>>>(regions, R, p->total_bands, w.band_off, w.bits, w.parent, out_stats,
-                                               out_ncomp, out_mask, out_labels, (long long*)out_area);
+    k7_blur<<<band_grid, K4_THREADS, 0, st>>>(im, regions, R, p->total_bands, w.band_off, w.gray, w.blurred, w.minmax);
+    QC_LAUNCHED(ctx);
+    k7_hist<<<band_grid, K4_THREADS, 0, st>>>(regions, R, p->total_bands, w.band_off, w.blurred, w.minmax, w.hist);
+    QC_LAUNCHED(ctx);
+    k7_otsu<<<std::min((R + K7_OTSU_WARPS - 1) / K7_OTSU_WARPS, sms * 8), K7_OTSU_WARPS * 32, 0, st>>>(
+        regions, R, w.hist, w.minmax, w.thr_adj, o.thr);
+    QC_LAUNCHED(ctx);
+    k7_cmp<<<band_grid, K4_THREADS, 0, st>>>(regions, R, p->total_bands, w.band_off, w.blurred, w.thr_adj, w.bits);
+    QC_LAUNCHED(ctx);
+    if (int rc = unionfind(w.bits, w.rank)) return rc;                             // w.rank doubles as the area table
+    k7_area<<<band_grid, K4_THREADS, 0, st>>>(regions, R, p->total_bands, w.band_off, w.bits, w.parent, w.rank);
+    QC_LAUNCHED(ctx);
+    k7_filter<<<band_grid, K4_THREADS, 0, st>>>(regions, R, p->total_bands, w.band_off, w.bits, w.parent, w.rank, w.bits2);
+    QC_LAUNCHED(ctx);
+    k7_fill<<<std::min(R, sms * 4), K7_FILL_THREADS, 0, st>>>(regions, R, w.bits2, w.bits3);
+    QC_LAUNCHED(ctx);
+    if (int rc = morph(w.bits3, w.bits)) return rc;
+    k7_emit<<<band_grid, K4_THREADS, 0, st>>>(im, regions, R, p->total_bands, w.band_off, w.gray, w.bits, o.mask, o.labels,
+                                              o.stats, (long long*)o.area, (long long*)o.sums);
+    QC_LAUNCHED(ctx);
+    k7_finish<<<(R + 255) / 256, 256, 0, st>>>(regions, R, o.stats, (const long long*)o.area, o.ncomp, (long long*)o.sums);
     QC_LAUNCHED(ctx);
     return QC_OK;
+}
+
+}  // namespace
+
+extern "C" int qc_segment(qc_ctx* ctx, const uint8_t* imgs, const qc_seg_params* p, const qc_seg_region* regions,
+                          void* workspace, size_t workspace_bytes, uint8_t* out_mask, int32_t* out_labels,
+                          int32_t* out_ncomp, int32_t* out_stats, int32_t* out_thr, int64_t* out_area, void* stream) {
+    return seg_run(ctx, QC_SEG_COMPOSITE, imgs, p, regions, SegAdaptive{nullptr, 0, 0, 0}, workspace, workspace_bytes,
+                   SegOut{out_mask, out_labels, out_ncomp, out_stats, out_thr, out_area, nullptr}, stream);
+}
+
+extern "C" int qc_segment_ref(qc_ctx* ctx, int method, const uint8_t* imgs, const qc_seg_params* p,
+                              const qc_seg_region* regions, const float* akern, int akern_pitch, int akern_max_block,
+                              int adaptive_c, void* workspace, size_t workspace_bytes, uint8_t* out_mask,
+                              int32_t* out_labels, int32_t* out_ncomp, int32_t* out_stats, int32_t* out_thr,
+                              int64_t* out_area, int64_t* out_sums, void* stream) {
+    return seg_run(ctx, method, imgs, p, regions, SegAdaptive{akern, akern_pitch, akern_max_block, adaptive_c},
+                   workspace, workspace_bytes,
+                   SegOut{out_mask, out_labels, out_ncomp, out_stats, out_thr, out_area, out_sums}, stream);
 }

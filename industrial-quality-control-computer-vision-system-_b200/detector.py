@@ -458,12 +458,21 @@ class _LazyFullMask:
 
 
 class ImageSegmentator:
-    """inference/segmentation.py:21 -- one K4 launch sequence for all detections of the frame.
-    K4's composite (Otsu -> polarity -> 3x3 cross close/open -> 8-conn CCL -> min-area filter) serves every
-    class; the reference's per-class method table (:185-195) is recorded in ``segmentation_method``."""
+    """inference/segmentation.py:21 -- the reference's per-class methods on device (K7, csrc/k7_refseg.cuh):
 
-    MIN_AREA = 20          # _adaptive_segmentation's _remove_small_components(min_size=20), :289
-    MORPH_ITERS = 1        # one 3x3 cross CLOSE + OPEN, :284-286
+        crack / scratch          'adaptive'   cv2.adaptiveThreshold(GAUSSIAN_C) -> 3x3 close/open -> CC filter(20)   :248-298
+        discoloration / others   'threshold'  sigma=1 blur -> Otsu x class factor -> CC filter(10) -> fill holes ->
+                                              disk(2) close/open                                            :197-246,449-462
+        dent / contamination     the reference's watershed (:300-346) and region growing (:348-447) are out of scope
+                                 (SURVEY.md §2 row 3); these two classes take the reference's own fallback (:175-183):
+                                 the threshold method, reported as 'threshold_fallback'.
+
+    All detections of a frame go through at most two launch sequences (one per method)."""
+
+    METHOD_BY_CLASS = {"crack": "adaptive", "scratch": "adaptive", "dent": "watershed",
+                       "discoloration": "threshold", "contamination": "region_growing"}           # :187-193
+    THRESHOLD_FACTORS = {"crack": 0.9, "scratch": 0.9, "dent": 1.1, "discoloration": 0.8, "contamination": 0.85}  # :218-224
+    DARK = ("crack", "scratch")                                                                   # :229, :278
 
     def __init__(self, config: Dict = None):
         self.config = config or {}
@@ -474,7 +483,10 @@ class ImageSegmentator:
             logger.error(f"Error initialising segmentator: {str(e)}")
             self._pipe = None
 
-    def segment_defects(self, image: np.ndarray, detections: List[Dict]) -> Dict:
+    def _select_segmentation_method(self, defect_class: str) -> str:
+        return self.METHOD_BY_CLASS.get(defect_class, "threshold")
+
+    def segment_defects(self, image: np.ndarray, detections: List[Dict], _frames: Optional[torch.Tensor] = None) -> Dict:
         try:
             out = {"segmented_regions": [], "masks": [], "contours": [], "area_analysis": {},
                    "total_defect_area": 0, "defect_density": 0.0}
@@ -487,30 +499,48 @@ class ImageSegmentator:
             img = np.ascontiguousarray(image if gray_in else image[:, :, :3], np.uint8)
             H, W = img.shape[:2]
             total_image_area = H * W
-            sel, regs = [], dict(img=[], x=[], y=[], w=[], h=[], polarity=[])
+            sel = []                                   # (detection index, x1, y1, x2, y2, method name)
             for i, d in enumerate(detections):
                 b = d["bbox"]
                 x1, y1 = max(b["x1"], 0), max(b["y1"], 0)
                 x2, y2 = min(b["x2"], W), min(b["y2"], H)             # numpy slicing clips the same way (:80)
                 if x2 <= x1 or y2 <= y1:
                     continue                                           # roi.size == 0, :82-83
-                sel.append((i, x1, y1, x2, y2))
-                regs["img"].append(0); regs["x"].append(x1); regs["y"].append(y1)
-                regs["w"].append(x2 - x1); regs["h"].append(y2 - y1)
-                regs["polarity"].append(0 if d["class"] in ("crack", "scratch") else 1)
-            if sel:
-                regs["min_area"] = self.MIN_AREA
-                res = qc.segment(torch.from_numpy(img[None]).to(dev), regs, morph_iters=self.MORPH_ITERS,
-                                 want_labels=False, swap_rb=False)
+                m = self._select_segmentation_method(d["class"])
+                sel.append((i, x1, y1, x2, y2, m if m in ("adaptive", "threshold") else "threshold_fallback"))
+            frames = _frames if _frames is not None else torch.from_numpy(img[None]).to(dev)
+            local_masks, areas, sums = {}, {}, {}
+            for method, code, iters in (("adaptive", ffi.QC_SEG_REF_ADAPTIVE, 1), ("threshold", ffi.QC_SEG_REF_THRESHOLD, 2)):
+                grp = [k for k, s_ in enumerate(sel) if (s_[5] == "adaptive") == (method == "adaptive")]
+                if not grp:
+                    continue
+                cls = [detections[sel[k][0]]["class"] for k in grp]
+                regs = dict(img=[0] * len(grp), x=[sel[k][1] for k in grp], y=[sel[k][2] for k in grp],
+                            w=[sel[k][3] - sel[k][1] for k in grp], h=[sel[k][4] - sel[k][2] for k in grp],
+                            polarity=[0 if c in self.DARK else 1 for c in cls])
+                if method == "adaptive":
+                    regs["min_area"] = 20                                                  # :289
+                else:
+                    regs["min_area"] = 10                                                  # :452
+                    regs["thr_scale"] = [self.THRESHOLD_FACTORS.get(c, 1.0) for c in cls]
+                    regs["max_comp"] = [2] * len(grp)
+                res = qc.segment(frames, regs, morph_iters=iters, want_labels=False, swap_rb=False, method=code,
+                                 want_sums=(method == "threshold"))
                 mask_all = res["mask"].cpu().numpy()
-                areas = res["area"].cpu().numpy()
-                plan = res["regions"]
+                area = res["area"].cpu().numpy()
+                sm = res["sums"].cpu().numpy() if res["sums"] is not None else None
+                for j, k in enumerate(grp):
+                    _, x1, y1, x2, y2, _m = sel[k]
+                    o = int(res["regions"][j].out_offset)
+                    local_masks[k] = mask_all[o:o + (x2 - x1) * (y2 - y1)].reshape(y2 - y1, x2 - x1)
+                    areas[k] = int(area[j])
+                    sums[k] = sm[j] if sm is not None else None
             total_defect_area = 0
-            for k, (i, x1, y1, x2, y2) in enumerate(sel):
+            gray = None
+            for k, (i, x1, y1, x2, y2, method) in enumerate(sel):
                 d = detections[i]
-                o = int(plan[k].out_offset)
-                local = mask_all[o:o + (x2 - x1) * (y2 - y1)].reshape(y2 - y1, x2 - x1)
-                defect_area = int(areas[k])
+                local = local_masks[k]
+                defect_area = areas[k]
                 total_defect_area += defect_area
                 contours = self._find_contours(local)
                 gcontours = []
@@ -518,13 +548,19 @@ class ImageSegmentator:
                     g = c.copy(); g[:, 0, 0] += x1; g[:, 0, 1] += y1
                     gcontours.append(g)
                 gmask = _LazyFullMask((H, W), y1, x1, local)
+                if method == "adaptive":
+                    if gray is None:
+                        gray = img if gray_in else cv2.cvtColor(img, cv2.COLOR_RGB2GRAY)
+                    conf = self._adaptive_confidence(gray[y1:y2, x1:x2], local, defect_area)
+                else:
+                    conf = self._threshold_confidence(sums[k], defect_area)
                 out["segmented_regions"].append({
                     "detection_id": i, "defect_class": d["class"], "confidence": d.get("confidence", 0.0),
                     "bbox": d["bbox"], "mask": gmask, "local_mask": local, "contours": gcontours,
                     "area_pixels": defect_area, "area_percentage": (defect_area / total_image_area) * 100,
                     "perimeter": self._calculate_perimeter(contours),
                     "compactness": self._calculate_compactness(defect_area, contours),
-                    "segmentation_method": "k4_otsu_morph_ccl", "confidence_score": self._confidence(img, d, local, x1, y1)})
+                    "segmentation_method": method, "confidence_score": conf})
                 out["masks"].append(gmask)
                 out["contours"].extend(gcontours)
             out["total_defect_area"] = total_defect_area
@@ -536,16 +572,28 @@ class ImageSegmentator:
             return {"error": str(e)}
 
     @staticmethod
-    def _confidence(img, d, local, x1, y1) -> float:
-        """inference/segmentation.py:527-555 on the ROI (foreground/background separation)."""
-        roi = img[y1:y1 + local.shape[0], x1:x1 + local.shape[1]]
-        if roi.ndim == 3:
-            roi = cv2.cvtColor(roi, cv2.COLOR_RGB2GRAY)
-        m = local > 0
-        if not m.any() or m.all():
+    def _threshold_confidence(sums, area: int) -> float:
+        """inference/segmentation.py:527-555 from K7's integer sums (sum of gray over the mask, sum of gray, sum of
+        gray^2, pixels): |mean_fg - mean_bg| / (std(roi) + 1e-6) / 3, clipped to 1."""
+        s_fg, s_all, s_sq, n = (int(v) for v in sums)
+        if area == 0 or area == n:
             return 0.0
-        sep = abs(float(roi[m].mean()) - float(roi[~m].mean())) / (float(roi.std()) + 1e-6)
-        return min(sep / 3.0, 1.0)
+        fg_mean, bg_mean = s_fg / area, (s_all - s_fg) / (n - area)
+        std = float(np.sqrt(n * s_sq - s_all * s_all) / n)
+        return float(min(abs(fg_mean - bg_mean) / (std + 1e-6) / 3.0, 1.0))
+
+    @staticmethod
+    def _adaptive_confidence(roi: np.ndarray, local: np.ndarray, area: int) -> float:
+        """inference/segmentation.py:557-578 (Canny edge overlap; host cv2 on the ROI)."""
+        try:
+            ratio = area / local.size
+            if ratio < 0.01 or ratio > 0.8:
+                return 0.3
+            edges = cv2.Canny(np.ascontiguousarray(roi), 50, 150)
+            overlap = np.sum((edges > 0) & (local > 0)) / area
+            return float(min(0.5 + 0.5 * overlap, 1.0))
+        except Exception:
+            return 0.5
 
     def _find_contours(self, mask: np.ndarray) -> List[np.ndarray]:
         if mask is None:

@@ -21,6 +21,7 @@ QC_DT_F32, QC_DT_BF16 = 0, 1
 QC_PRE_STRETCH, QC_PRE_LETTERBOX, QC_PRE_LETTERBOX_AUTO = 0, 1, 2
 QC_PRE_SWAP_RB, QC_PRE_LUT_UNIFORM = 1, 2
 QC_MAX_LEVELS = 4
+QC_SEG_COMPOSITE, QC_SEG_REF_THRESHOLD, QC_SEG_REF_ADAPTIVE = 0, 1, 2
 
 
 class QcGraftError(RuntimeError):
@@ -96,6 +97,10 @@ _SIGS = {
     "qc_segment_workspace_bytes": (C.c_size_t, [C.POINTER(SegParams)]),
     "qc_segment": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(SegParams), C.c_void_p, C.c_void_p, C.c_size_t,
                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "qc_segment_ref_workspace_bytes": (C.c_size_t, [C.POINTER(SegParams), C.c_int]),
+    "qc_segment_ref": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(SegParams), C.c_void_p, C.c_void_p, C.c_int,
+                                 C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p,
+                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "qc_spc_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "qc_rules_cluster": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                    C.c_double, C.c_void_p, C.c_void_p]),
@@ -411,9 +416,26 @@ class Context:
             raise QcGraftError(f"qc_segment_plan failed: {rc} (region outside the image?)")
         return arr.view(np.recarray), p
 
+    def adaptive_kernel_table(self, max_block: int):
+        """Device float32 table of cv2.getGaussianKernel(bs, -1, CV_32F) for every odd block size 11..max_block (row
+        (bs-11)/2, pitch = max_block): cv2's own numbers, so K7's adaptive threshold sums exactly what
+        cv2.adaptiveThreshold sums (inference/segmentation.py:274-281).  Returns (tensor, pitch, max_block)."""
+        import cv2
+        max_block = max(int(max_block) | 1, 65)
+        key = ("akern", max_block)
+        if key not in self._lut_cache:
+            t = np.zeros(((max_block - 11) // 2 + 1, max_block), np.float32)
+            for bs in range(11, max_block + 1, 2):
+                t[(bs - 11) // 2, :bs] = cv2.getGaussianKernel(bs, -1, cv2.CV_32F).ravel()
+            self._lut_cache[key] = torch.from_numpy(t).to(self.device)
+        return self._lut_cache[key], max_block, max_block
+
     def segment(self, imgs: torch.Tensor, regions, morph_iters: int = 1, want_mask: bool = True,
-                want_labels: bool = True, swap_rb: bool = False):
-        """imgs: uint8 CUDA [n,h,w] (gray) or [n,h,w,3] (RGB).  Returns dict of device tensors + the plan."""
+                want_labels: bool = True, swap_rb: bool = False, method: int = QC_SEG_COMPOSITE,
+                adaptive_c: int = 2, want_sums: bool = False):
+        """imgs: uint8 CUDA [n,h,w] (gray) or [n,h,w,3] (RGB).  Returns dict of device tensors + the plan.
+        method: QC_SEG_COMPOSITE (K4: Otsu -> morphology -> CCL), QC_SEG_REF_THRESHOLD / QC_SEG_REF_ADAPTIVE (K7: the
+        reference's _threshold_segmentation / _adaptive_segmentation, see include/qcgraft.h)."""
         assert imgs.is_cuda and imgs.dtype == torch.uint8 and imgs.dim() in (3, 4)
         n, h, w = imgs.shape[:3]
         ch = 1 if imgs.dim() == 3 else imgs.shape[3]
@@ -427,7 +449,8 @@ class Context:
                         ncomp=torch.zeros(0, dtype=torch.int32, device=dev),
                         stats=torch.zeros((0, 5), dtype=torch.int32, device=dev),
                         thr=torch.zeros(0, dtype=torch.int32, device=dev),
-                        area=torch.zeros(0, dtype=torch.int64, device=dev))
+                        area=torch.zeros(0, dtype=torch.int64, device=dev),
+                        sums=torch.zeros((0, 4), dtype=torch.int64, device=dev))
         regs_dev = torch.from_numpy(arr[:R].view(np.uint8).reshape(-1)).to(dev, non_blocking=False)
         mask = torch.empty(p.total_pixels, dtype=torch.uint8, device=dev) if want_mask else None
         labels = torch.empty(p.total_pixels, dtype=torch.int32, device=dev) if want_labels else None
@@ -435,14 +458,28 @@ class Context:
         stats = torch.empty((p.total_stats_rows, 5), dtype=torch.int32, device=dev)
         thr = torch.empty(R, dtype=torch.int32, device=dev)
         area = torch.empty(R, dtype=torch.int64, device=dev)
-        need = self.lib.qc_segment_workspace_bytes(C.byref(p))
-        ws = self.workspace("seg", need)
-        rc = self.lib.qc_segment(self.h, imgs.data_ptr(), C.byref(p), regs_dev.data_ptr(), ws.data_ptr(), ws.numel(),
-                                 _ptr(mask), _ptr(labels), ncomp.data_ptr(), stats.data_ptr(), thr.data_ptr(),
-                                 area.data_ptr(), _stream(dev))
-        self._check(rc, "qc_segment")
+        sums = None
+        if method == QC_SEG_COMPOSITE:
+            need = self.lib.qc_segment_workspace_bytes(C.byref(p))
+            ws = self.workspace("seg", need)
+            rc = self.lib.qc_segment(self.h, imgs.data_ptr(), C.byref(p), regs_dev.data_ptr(), ws.data_ptr(), ws.numel(),
+                                     _ptr(mask), _ptr(labels), ncomp.data_ptr(), stats.data_ptr(), thr.data_ptr(),
+                                     area.data_ptr(), _stream(dev))
+            self._check(rc, "qc_segment")
+        else:
+            sums = torch.empty((R, 4), dtype=torch.int64, device=dev) if want_sums else None
+            ak, pitch, maxb = (None, 0, 0)
+            if method == QC_SEG_REF_ADAPTIVE:
+                ak, pitch, maxb = self.adaptive_kernel_table(max(11, min(p.max_region_w, p.max_region_h) // 10) | 1)
+            need = self.lib.qc_segment_ref_workspace_bytes(C.byref(p), method)
+            ws = self.workspace("seg", need)
+            rc = self.lib.qc_segment_ref(self.h, method, imgs.data_ptr(), C.byref(p), regs_dev.data_ptr(), _ptr(ak), pitch,
+                                         maxb, adaptive_c, ws.data_ptr(), ws.numel(), _ptr(mask), _ptr(labels),
+                                         ncomp.data_ptr(), stats.data_ptr(), thr.data_ptr(), area.data_ptr(), _ptr(sums),
+                                         _stream(dev))
+            self._check(rc, "qc_segment_ref")
         return dict(regions=arr, params=p, regs_dev=regs_dev, mask=mask, labels=labels, ncomp=ncomp, stats=stats,
-                    thr=thr, area=area)
+                    thr=thr, area=area, sums=sums)
 
     # -- SPC -------------------------------------------------------------------------------
     # -- K6 --------------------------------------------------------------------------------
