@@ -8,7 +8,7 @@
 #include <atomic>
 #include "../../include/qcgraft.h"
 
-struct qc_attr_entry { const void* func; int smem; int occ; int threads; };
+struct qc_attr_entry { const void* func; int smem; int occ; int threads; int device; };
 struct qc_ctx {
     int device;
     int sm_count;
@@ -38,14 +38,31 @@ struct qc_ctx {
         QC_CUDA(ctx, cudaGetLastError());                                               \
     } while (0)
 
-// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) + occupancy query, cached per (kernel, smem, threads):
+// Every entry point that launches kernels runs under this guard: the kernels, the stream and the pointers belong to
+// ctx->device whatever the caller's current device is (a pipeline on cuda:1 called while torch's current device is 0).
+struct qc_device_guard {
+    int prev = -1, dev = -1;
+    explicit qc_device_guard(const qc_ctx* ctx) {
+        if (!ctx) return;
+        dev = ctx->device;
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) cudaSetDevice(dev);
+    }
+    ~qc_device_guard() {
+        if (prev >= 0 && prev != dev) cudaSetDevice(prev);
+    }
+    qc_device_guard(const qc_device_guard&) = delete;
+    qc_device_guard& operator=(const qc_device_guard&) = delete;
+};
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) + occupancy query, cached per (device, kernel, smem, threads):
 // both are host-side driver calls worth several microseconds, too slow to repeat on every launch.  The
-// attribute is per-function PROCESS state (last value wins), so the table is process-global (api.cu) and
-// the limit is only ever raised.
+// attribute is per-function, per-DEVICE state (last value wins), so the table is process-global (api.cu), keyed by
+// device, and the limit is only ever raised.
 #include <mutex>
 struct qc_attr_table {
     std::mutex mu;
-    qc_attr_entry e[96];
+    qc_attr_entry e[256];
     int n = 0;
 };
 qc_attr_table& qc_attrs();      // defined in api.cu
@@ -57,7 +74,7 @@ static inline int qc_prepare(qc_ctx* ctx, F func, int smem, int threads, int* oc
     std::lock_guard<std::mutex> lock(t.mu);
     int prev_max = 0;
     for (int i = 0; i < t.n; ++i) {
-        if (t.e[i].func != key) continue;
+        if (t.e[i].func != key || t.e[i].device != ctx->device) continue;
         if (t.e[i].smem == smem && t.e[i].threads == threads) {
             if (occ_out) *occ_out = t.e[i].occ;
             return QC_OK;
@@ -70,7 +87,7 @@ static inline int qc_prepare(qc_ctx* ctx, F func, int smem, int threads, int* oc
     int occ = 1;
     QC_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, func, threads, (size_t)smem));
     if (occ < 1) occ = 1;
-    if (t.n < 96) t.e[t.n++] = qc_attr_entry{key, smem, occ, threads};
+    if (t.n < 256) t.e[t.n++] = qc_attr_entry{key, smem, occ, threads, ctx->device};
     if (occ_out) *occ_out = occ;
     return QC_OK;
 }

@@ -305,6 +305,7 @@ static int launch_k1(qc_ctx* ctx, const uint8_t* src, int n, int64_t src_img_str
 extern "C" int qc_preprocess(qc_ctx* ctx, const uint8_t* src, int n, int64_t src_img_stride,
                              int32_t src_row_stride, const qc_pre_plan* plan, const float* lut, int pad_value,
                              int flags, int out_dtype, void* dst, void* stream) {
+    qc_device_guard dev_guard(ctx);
     if (!ctx) return QC_ERR_INVALID;
     if (!src || !plan || !lut || !dst || n < 0) QC_FAIL(ctx, QC_ERR_INVALID, "qc_preprocess: null/invalid argument");
     if (n == 0) return QC_OK;

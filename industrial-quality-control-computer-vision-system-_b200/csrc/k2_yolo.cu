@@ -68,9 +68,14 @@ __device__ __forceinline__ float sigmoid_f32(float x) {
 constexpr int K2_NC_MAX = 16;    // classes held in registers by the vector path
 
 // Candidate test for one anchor given its nc class logits.  torch: s_c = sigmoid(x_c) (float32), first
-// maximum over c, candidate iff s > (float)conf.  sigmoid is monotone, so only logits within a hair of
-// the maximum logit can hold the maximum sigmoid (they get the exact first-max treatment), and an anchor
-// whose maximum logit is clearly below logit(conf) needs no sigmoid at all.
+// maximum over c, candidate iff s > (float)conf.  sigmoid is monotone, so only logits close to the maximum
+// logit can hold the maximum sigmoid (they get the exact first-max treatment), and an anchor whose maximum
+// logit is clearly below logit(conf) needs no sigmoid at all.  "Close": float32 sigmoid flattens as it
+// saturates (every logit above ~16.7 gives exactly 1.0f; 13.95 and 14.0 round to the same float), so above 10
+// the band is everything >= 10 -- torch.max then returns the FIRST class among the equal scores, which need
+// not be the class of the largest logit.  Below 10 two logits 1e-3 apart differ by >= 7 ulps of the sigmoid.
+__device__ __forceinline__ float k2_near_band(float m) { return fminf(m - 1e-3f * fmaxf(1.f, fabsf(m)), 10.f); }
+
 template <int NCM>
 __device__ __forceinline__ bool anchor_candidate(const float* x, int nc, float conf, float logit_lo, float& best,
                                                  int& best_c) {
@@ -79,7 +84,7 @@ __device__ __forceinline__ bool anchor_candidate(const float* x, int nc, float c
     for (int c = 0; c < NCM; ++c)
         if (c < nc) m = fmaxf(m, x[c]);
     if (!(m >= logit_lo)) return false;                 // sigmoid(m) < conf with a wide margin (NaN -> false)
-    const float near = m - 1e-3f * fmaxf(1.f, fabsf(m));
+    const float near = k2_near_band(m);
     best = -1.f; best_c = 0;
 #pragma unroll
     for (int c = 0; c < NCM; ++c) {
@@ -135,7 +140,7 @@ k2_filter(LevelTable lt, int nc, int reg_max, float conf, float logit_lo, int ca
                 float m = -INFINITY;
                 for (int c = 0; c < nc; ++c) m = fmaxf(m, load_elem<BF16>(p, base + (long long)(4 * reg_max + c) * cs));
                 if (m >= logit_lo) {
-                    const float near = m - 1e-3f * fmaxf(1.f, fabsf(m));
+                    const float near = k2_near_band(m);
                     best[0] = -1.f; best_c[0] = 0;
                     for (int c = 0; c < nc; ++c) {
                         const float xv = load_elem<BF16>(p, base + (long long)(4 * reg_max + c) * cs);
@@ -855,6 +860,7 @@ extern "C" size_t qc_nms_workspace_bytes(int n, int cap) {
 extern "C" int qc_yolo_decode_nms(qc_ctx* ctx, const void* const* levels, const qc_yolo_params* p, void* workspace,
                                   size_t workspace_bytes, float* out_det, int32_t* out_anchor, int32_t* out_count,
                                   int32_t* out_ncand, void* stream) {
+    qc_device_guard dev_guard(ctx);
     if (!ctx) return QC_ERR_INVALID;
     if (!levels || !p || !out_det || !out_anchor || !out_count)
         QC_FAIL(ctx, QC_ERR_INVALID, "qc_yolo_decode_nms: null argument");
@@ -956,6 +962,7 @@ extern "C" int qc_yolo_decode_nms(qc_ctx* ctx, const void* const* levels, const 
 extern "C" int qc_nms(qc_ctx* ctx, const float* boxes, const float* scores, const int32_t* cls, const int32_t* counts,
                       int n, int cap, double iou_thres, float max_wh, int max_det, void* workspace,
                       size_t workspace_bytes, int32_t* out_keep, int32_t* out_count, void* stream) {
+    qc_device_guard dev_guard(ctx);
     if (!ctx) return QC_ERR_INVALID;
     if (!boxes || !scores || !cls || !counts || !out_keep || !out_count || cap <= 0 || max_det <= 0 || n < 0)
         QC_FAIL(ctx, QC_ERR_INVALID, "qc_nms: bad argument");

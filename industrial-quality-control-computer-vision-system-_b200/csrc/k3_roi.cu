@@ -344,6 +344,7 @@ k3_roi_sep(const uint8_t* __restrict__ imgs, int n, int H, int W, long long img_
 extern "C" int qc_roi_align(qc_ctx* ctx, const uint8_t* imgs, int n, int h, int w, int64_t img_stride,
                             int32_t row_stride, const float* rois, int K, int out_h, int out_w, int sampling_ratio,
                             int aligned, int swap_rb, const float* norm, int out_dtype, void* dst, void* stream) {
+    qc_device_guard dev_guard(ctx);
     if (!ctx) return QC_ERR_INVALID;
     if (K == 0) return QC_OK;
     if (!imgs || !rois || !norm || !dst || n <= 0 || h <= 0 || w <= 0 || K < 0 || out_h <= 0 || out_w <= 0 ||

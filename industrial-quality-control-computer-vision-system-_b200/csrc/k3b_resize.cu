@@ -283,6 +283,7 @@ extern "C" int qc_pil_resize_make_tables(int src_h, int src_w, int dst_h, int ds
 extern "C" int qc_pil_resize(qc_ctx* ctx, const uint8_t* imgs, int n, int h, int w, int64_t img_stride,
                              int32_t row_stride, const int32_t* dev_tables, const int32_t* host_tables, int swap_rb,
                              const float* norm, int out_dtype, void* dst, void* stream) {
+    qc_device_guard dev_guard(ctx);
     if (!ctx) return QC_ERR_INVALID;
     if (n == 0) return QC_OK;
     if (!imgs || !dev_tables || !host_tables || !norm || !dst || n < 0 || h <= 0 || w <= 0 || row_stride < w * 3)

@@ -1279,6 +1279,7 @@ int seg_run(qc_ctx* ctx, int method, const uint8_t* imgs, const qc_seg_params* p
             const SegAdaptive& ad, void* workspace, size_t workspace_bytes, const SegOut& o, void* stream) {
     const char* fn = method == QC_SEG_COMPOSITE ? "qc_segment" : "qc_segment_ref";
     if (!ctx) return QC_ERR_INVALID;
+    qc_device_guard dev_guard(ctx);
     if (!p) QC_FAIL(ctx, QC_ERR_INVALID, "%s: null params", fn);
     if (method < QC_SEG_COMPOSITE || method > QC_SEG_REF_ADAPTIVE) QC_FAIL(ctx, QC_ERR_INVALID, "%s: bad method %d", fn, method);
     if (p->num_regions == 0) return QC_OK;

@@ -64,6 +64,7 @@ k5_spc(const float* __restrict__ det, const int* __restrict__ count, int n, int 
 
 extern "C" int qc_spc_stats(qc_ctx* ctx, const float* det, const int32_t* count, int n, int max_det, double* out9,
                             void* stream) {
+    qc_device_guard dev_guard(ctx);
     if (!ctx) return QC_ERR_INVALID;
     if (!det || !count || !out9 || n < 0 || max_det <= 0) QC_FAIL(ctx, QC_ERR_INVALID, "qc_spc_stats: bad argument");
     k5_spc<<<1, K5_THREADS, 0, (cudaStream_t)stream>>>(det, count, n, max_det, out9);

@@ -113,6 +113,7 @@ k6_cluster(const int* __restrict__ box, const int* __restrict__ cls, const uint8
 extern "C" int qc_rules_cluster(qc_ctx* ctx, const int32_t* box, const int32_t* cls, const uint8_t* keep,
                                 const int32_t* count, int n, int cap, double overlap_threshold, int32_t* out_label,
                                 void* stream) {
+    qc_device_guard dev_guard(ctx);
     if (!ctx) return QC_ERR_INVALID;
     if (n == 0) return QC_OK;
     if (!box || !cls || !count || !out_label || n < 0 || cap <= 0)

@@ -19,6 +19,7 @@ stage would have seen.
 from __future__ import annotations
 
 import logging
+import os
 import time
 from concurrent.futures import ThreadPoolExecutor
 from typing import Dict, List, Optional, Tuple
@@ -27,7 +28,7 @@ import cv2
 import numpy as np
 import torch
 
-from . import ffi
+from . import ffi, nets
 from .pipeline import CLASS_NAMES, DARK_CLASSES, RESNET_MEAN, RESNET_STD, InspectionPipeline
 
 logger = logging.getLogger(__name__)
@@ -35,17 +36,56 @@ logger = logging.getLogger(__name__)
 _shared_pipelines: Dict[tuple, InspectionPipeline] = {}
 
 
+def _qcfg(config: Optional[Dict]) -> Dict:
+    return (config or {}).get("qcgraft", {}) or {}
+
+
 def _pipeline(config: Optional[Dict], conf=0.7, iou=0.5, nc=5) -> InspectionPipeline:
-    """One InspectionPipeline (nets + qc_ctx) per (device, scale) shared by the wrapper classes."""
-    cfg = (config or {}).get("qcgraft", {})
+    """One InspectionPipeline (qc_ctx, streams, staging buffers; nets are installed by the model wrappers) per
+    (device, class count, image size, weight files) shared by the wrapper classes of one detector."""
+    cfg = _qcfg(config)
     dev = int(cfg.get("device", 0))
-    scale = cfg.get("yolo_scale", "n")
-    key = (dev, scale, nc)
+    key = (dev, nc, int(cfg.get("imgsz", 640)), cfg.get("_weights"), bool(cfg.get("synthetic_weights", False)),
+           cfg.get("yolo_scale", "n"))
     if key not in _shared_pipelines:
-        _shared_pipelines[key] = InspectionPipeline(scale, nc, device=dev, conf=conf, iou=iou,
+        _shared_pipelines[key] = InspectionPipeline(cfg.get("yolo_scale", "n"), nc, device=dev, conf=conf, iou=iou,
                                                     imgsz=int(cfg.get("imgsz", 640)),
-                                                    use_graphs=bool(cfg.get("cuda_graphs", False)))
+                                                    use_graphs=bool(cfg.get("cuda_graphs", True)), build_nets=False)
     return _shared_pipelines[key]
+
+
+def _install_yolo(pipe: InspectionPipeline, model_path: str, config: Optional[Dict], nc: int):
+    """models/yolo_model.py:45-69: the checkpoint file is loaded or load_model() fails.  Seeded random-init weights
+    only on the explicit ``config['qcgraft']['synthetic_weights'] = True`` (benchmarks / tests; no network here)."""
+    cfg = _qcfg(config)
+    if cfg.get("synthetic_weights", False):
+        src = f"synthetic:yolov8{cfg.get('yolo_scale', 'n')}"
+        if pipe.yolo_source != src:
+            pipe.install_yolo(nets.build_yolo(cfg.get("yolo_scale", "n"), nc, 0), src)
+        return
+    src = os.path.abspath(model_path)
+    if pipe.yolo_source != src:
+        if not os.path.exists(model_path):
+            raise FileNotFoundError(f"YOLO weights not found: {model_path}")
+        module, _scale, ck_nc = nets.load_yolo_checkpoint(model_path)
+        if ck_nc != nc:
+            raise ValueError(f"{model_path}: checkpoint has {ck_nc} classes, configuration has {nc}")
+        pipe.install_yolo(module, src)
+
+
+def _install_resnet(pipe: InspectionPipeline, model_path: str, config: Optional[Dict], nc: int):
+    """models/resent_model.py:85-107.  The reference falls back to ImageNet weights (a download) when the file is
+    missing; offline that does not exist, so a missing file fails unless synthetic weights are asked for."""
+    cfg = _qcfg(config)
+    if cfg.get("synthetic_weights", False):
+        if pipe.resnet_source != "synthetic:resnet50":
+            pipe.install_resnet(nets.build_resnet50(nc, 0), "synthetic:resnet50")
+        return
+    src = os.path.abspath(model_path)
+    if pipe.resnet_source != src:
+        if not os.path.exists(model_path):
+            raise FileNotFoundError(f"ResNet weights not found: {model_path} (no network for the ImageNet fallback)")
+        pipe.install_resnet(nets.load_resnet_checkpoint(model_path, nc), src)
 
 
 def _decode(image: np.ndarray) -> np.ndarray:
@@ -77,11 +117,14 @@ class YOLODetector:
 
     def load_model(self) -> bool:
         try:
-            self.model = _pipeline(self._config, self.confidence_threshold, self.nms_threshold)
+            pipe = _pipeline(self._config, self.confidence_threshold, self.nms_threshold, len(self.class_names))
+            _install_yolo(pipe, self.model_path, self._config, len(self.class_names))
+            self.model = pipe
             return True
         except Exception as e:                                    # models/yolo_model.py:67-69
             logger.error(f"Error loading YOLO model: {str(e)}")
             self._load_error = str(e)
+            self.model = None
             return False
 
     def preprocess_image(self, image: np.ndarray) -> np.ndarray:
@@ -91,7 +134,7 @@ class YOLODetector:
             image = cv2.cvtColor(image, cv2.COLOR_BGR2RGB)
         return image
 
-    def predict(self, image: np.ndarray, _head_override=None) -> Dict:
+    def predict(self, image: np.ndarray, _head_override=None, _frames: Optional[torch.Tensor] = None) -> Dict:
         if self.model is None:
             logger.error("Model not loaded")
             return {"error": "Model not loaded"}
@@ -100,7 +143,7 @@ class YOLODetector:
             img = _as_rgb3(_decode(image))
             pipe = self.model
             pipe.conf, pipe.iou = self.confidence_threshold, self.nms_threshold
-            frames = torch.from_numpy(img[None]).to(pipe.dev)
+            frames = _frames if _frames is not None else torch.from_numpy(img[None]).to(pipe.dev)
             # reference: one flip here (:80) and one inside ultralytics ([..., ::-1]) -> net sees `image` order
             det, anchor, count, _ = pipe.detect(frames, head_override=_head_override, swap_rb=False)
             k = int(count[0])
@@ -177,10 +220,12 @@ class ResNetClassifier:
     def load_model(self) -> bool:
         try:
             self._pipe = _pipeline(self._config, nc=self.num_classes)
+            _install_resnet(self._pipe, self.model_path, self._config, self.num_classes)
             self.model = self._pipe.resnet
             return True
         except Exception as e:
             logger.error(f"Error loading ResNet model: {str(e)}")
+            self.model = None
             return False
 
     def _classify(self, frames: torch.Tensor, rois: np.ndarray, swap_rb: bool) -> np.ndarray:
@@ -205,15 +250,14 @@ class ResNetClassifier:
                 "class_probabilities": {self.class_names[i]: float(p) for i, p in enumerate(probs)},
                 "severity": self._predict_severity(cid, conf)}
 
-    def predict(self, image: np.ndarray) -> Dict:
+    def predict(self, image: np.ndarray, _frames: Optional[torch.Tensor] = None) -> Dict:
         if self.model is None:
             logger.error("Model not loaded")
             return {"error": "Model not loaded"}
         try:
             start_time = time.time()
             img = _as_rgb3(_decode(image))
-            h, w = img.shape[:2]
-            frames = torch.from_numpy(img[None]).to(self._pipe.dev)
+            frames = _frames if _frames is not None else torch.from_numpy(img[None]).to(self._pipe.dev)
             # reference flips once (models/resent_model.py:123) -> swap_rb=True relative to `image`
             probs = self._classify_whole(frames, swap_rb=True)[0]
             result = self._result(probs)
@@ -275,6 +319,9 @@ class EnsemblePredictor:
     def load_models(self, yolo_weights: str, resnet_weights: str) -> bool:
         try:
             yolo_config = self.config.get("model", {})
+            # both wrappers share one pipeline: tell them about both weight files
+            self.config = dict(self.config)
+            self.config["qcgraft"] = dict(_qcfg(self.config), _weights=(str(yolo_weights), str(resnet_weights)))
             self.yolo_detector = YOLODetector(model_path=yolo_weights,
                                               confidence_threshold=yolo_config.get("confidence_threshold", 0.7),
                                               nms_threshold=yolo_config.get("nms_threshold", 0.5), config=self.config)
@@ -290,14 +337,17 @@ class EnsemblePredictor:
             logger.error(f"Error loading ensemble models: {str(e)}")
             return False
 
-    def predict(self, image: np.ndarray, _head_override=None) -> Dict:
+    def predict(self, image: np.ndarray, _head_override=None, _frames: Optional[torch.Tensor] = None) -> Dict:
         if self.yolo_detector is None or self.resnet_classifier is None:
             return {"error": "Models not loaded"}
         try:
             start_time = time.time()
-            yolo_results = self.yolo_detector.predict(image, _head_override=_head_override)
-            resnet_results = self.resnet_classifier.predict(image)
-            ensemble_results = self._combine_predictions(yolo_results, resnet_results, image.shape, image)
+            if _frames is None and isinstance(image, np.ndarray) and image.ndim != 1:
+                # one upload shared by YOLO, the whole-frame classifier and the ROI crops
+                _frames = torch.from_numpy(_as_rgb3(image)[None]).to(self.resnet_classifier._pipe.dev)
+            yolo_results = self.yolo_detector.predict(image, _head_override=_head_override, _frames=_frames)
+            resnet_results = self.resnet_classifier.predict(image, _frames=_frames)
+            ensemble_results = self._combine_predictions(yolo_results, resnet_results, image.shape, image, _frames=_frames)
             ensemble_results["total_inference_time_ms"] = (time.time() - start_time) * 1000
             return ensemble_results
         except Exception as e:
@@ -305,7 +355,8 @@ class EnsemblePredictor:
             return {"error": str(e)}
 
     def _combine_predictions(self, yolo_results: Dict, resnet_results: Dict, image_shape: Tuple,
-                             image: Optional[np.ndarray] = None) -> Dict:
+                             image: Optional[np.ndarray] = None, _frames: Optional[torch.Tensor] = None,
+                             _roi_probs: Optional[Dict[int, np.ndarray]] = None) -> Dict:
         combined = {"detections": [], "global_classification": resnet_results, "detection_summary": {},
                     "quality_assessment": {}, "ensemble_confidence": 0.0}
         if "error" in yolo_results or "error" in resnet_results:
@@ -313,7 +364,10 @@ class EnsemblePredictor:
             return combined
         try:
             dets = yolo_results.get("detections", [])
-            roi_probs = self._classify_regions(image, dets) if image is not None else {}
+            if _roi_probs is not None:
+                roi_probs = _roi_probs
+            else:
+                roi_probs = self._classify_regions(image, dets, _frames) if image is not None else {}
             enhanced = []
             for d in dets:
                 self._extract_region(image_shape, d["bbox"])
@@ -332,12 +386,13 @@ class EnsemblePredictor:
             combined["error"] = str(e)
         return combined
 
-    def _classify_regions(self, image: np.ndarray, dets: List[Dict]) -> Dict[int, np.ndarray]:
+    def _classify_regions(self, image: np.ndarray, dets: List[Dict], _frames=None) -> Dict[int, np.ndarray]:
         valid = [d for d in dets if d["bbox"]["x2"] > d["bbox"]["x1"] and d["bbox"]["y2"] > d["bbox"]["y1"]]
         if not valid:
             return {}
-        img = _as_rgb3(_decode(image))
-        frames = torch.from_numpy(img[None]).to(self.resnet_classifier._pipe.dev)
+        frames = _frames
+        if frames is None:
+            frames = torch.from_numpy(_as_rgb3(_decode(image))[None]).to(self.resnet_classifier._pipe.dev)
         rois = np.array([[0, d["bbox"]["x1"], d["bbox"]["y1"], d["bbox"]["x2"], d["bbox"]["y2"]] for d in valid], np.float32)
         probs = self.resnet_classifier._classify(frames, rois, swap_rb=True)
         return {d["id"]: probs[i] for i, d in enumerate(valid)}
@@ -453,6 +508,16 @@ class _LazyFullMask:
     def __gt__(self, other):
         return np.asarray(self) > other
 
+    def extent(self):
+        """(y_min, y_max, x_min, x_max) of mask > 0 in frame coordinates, or None -- what
+        inference/postprocess.py:784-790 reads off the full-frame mask, without materialising it."""
+        m = self._local > 0
+        rows = np.flatnonzero(m.any(1))
+        if rows.size == 0:
+            return None
+        cols = np.flatnonzero(m.any(0))
+        return rows[0] + self._y1, rows[-1] + self._y1, cols[0] + self._x1, cols[-1] + self._x1
+
     def __getitem__(self, k):
         return np.asarray(self)[k]
 
@@ -486,28 +551,30 @@ class ImageSegmentator:
     def _select_segmentation_method(self, defect_class: str) -> str:
         return self.METHOD_BY_CLASS.get(defect_class, "threshold")
 
+    def _select(self, detections: List[Dict], H: int, W: int):
+        """(detection index, x1, y1, x2, y2, method name) of every detection with a non-empty ROI."""
+        sel = []
+        for i, d in enumerate(detections):
+            b = d["bbox"]
+            x1, y1 = max(b["x1"], 0), max(b["y1"], 0)
+            x2, y2 = min(b["x2"], W), min(b["y2"], H)             # numpy slicing clips the same way (:80)
+            if x2 <= x1 or y2 <= y1:
+                continue                                           # roi.size == 0, :82-83
+            m = self._select_segmentation_method(d["class"])
+            sel.append((i, x1, y1, x2, y2, m if m in ("adaptive", "threshold") else "threshold_fallback"))
+        return sel
+
     def segment_defects(self, image: np.ndarray, detections: List[Dict], _frames: Optional[torch.Tensor] = None) -> Dict:
         try:
-            out = {"segmented_regions": [], "masks": [], "contours": [], "area_analysis": {},
-                   "total_defect_area": 0, "defect_density": 0.0}
             if not detections:
-                return out
+                return {"segmented_regions": [], "masks": [], "contours": [], "area_analysis": {},
+                        "total_defect_area": 0, "defect_density": 0.0}
             if self._pipe is None:
                 return {"error": "CUDA segmentation backend not available"}
             qc, dev = self._pipe.qc, self._pipe.dev
-            gray_in = image.ndim == 2
-            img = np.ascontiguousarray(image if gray_in else image[:, :, :3], np.uint8)
+            img = np.ascontiguousarray(image if image.ndim == 2 else image[:, :, :3], np.uint8)
             H, W = img.shape[:2]
-            total_image_area = H * W
-            sel = []                                   # (detection index, x1, y1, x2, y2, method name)
-            for i, d in enumerate(detections):
-                b = d["bbox"]
-                x1, y1 = max(b["x1"], 0), max(b["y1"], 0)
-                x2, y2 = min(b["x2"], W), min(b["y2"], H)             # numpy slicing clips the same way (:80)
-                if x2 <= x1 or y2 <= y1:
-                    continue                                           # roi.size == 0, :82-83
-                m = self._select_segmentation_method(d["class"])
-                sel.append((i, x1, y1, x2, y2, m if m in ("adaptive", "threshold") else "threshold_fallback"))
+            sel = self._select(detections, H, W)
             frames = _frames if _frames is not None else torch.from_numpy(img[None]).to(dev)
             local_masks, areas, sums = {}, {}, {}
             for method, code, iters in (("adaptive", ffi.QC_SEG_REF_ADAPTIVE, 1), ("threshold", ffi.QC_SEG_REF_THRESHOLD, 2)):
@@ -535,41 +602,51 @@ class ImageSegmentator:
                     local_masks[k] = mask_all[o:o + (x2 - x1) * (y2 - y1)].reshape(y2 - y1, x2 - x1)
                     areas[k] = int(area[j])
                     sums[k] = sm[j] if sm is not None else None
-            total_defect_area = 0
-            gray = None
-            for k, (i, x1, y1, x2, y2, method) in enumerate(sel):
-                d = detections[i]
-                local = local_masks[k]
-                defect_area = areas[k]
-                total_defect_area += defect_area
-                contours = self._find_contours(local)
-                gcontours = []
-                for c in contours:
-                    g = c.copy(); g[:, 0, 0] += x1; g[:, 0, 1] += y1
-                    gcontours.append(g)
-                gmask = _LazyFullMask((H, W), y1, x1, local)
-                if method == "adaptive":
-                    if gray is None:
-                        gray = img if gray_in else cv2.cvtColor(img, cv2.COLOR_RGB2GRAY)
-                    conf = self._adaptive_confidence(gray[y1:y2, x1:x2], local, defect_area)
-                else:
-                    conf = self._threshold_confidence(sums[k], defect_area)
-                out["segmented_regions"].append({
-                    "detection_id": i, "defect_class": d["class"], "confidence": d.get("confidence", 0.0),
-                    "bbox": d["bbox"], "mask": gmask, "local_mask": local, "contours": gcontours,
-                    "area_pixels": defect_area, "area_percentage": (defect_area / total_image_area) * 100,
-                    "perimeter": self._calculate_perimeter(contours),
-                    "compactness": self._calculate_compactness(defect_area, contours),
-                    "segmentation_method": method, "confidence_score": conf})
-                out["masks"].append(gmask)
-                out["contours"].extend(gcontours)
-            out["total_defect_area"] = total_defect_area
-            out["defect_density"] = (total_defect_area / total_image_area) * 100
-            out["area_analysis"] = self._analyze_defect_areas(out["segmented_regions"])
-            return out
+            return self._assemble(img, detections, sel, local_masks, areas, sums)
         except Exception as e:
             logger.error(f"Error in defect segmentation: {str(e)}")
             return {"error": str(e)}
+
+    def _assemble(self, img: np.ndarray, detections: List[Dict], sel, local_masks, areas, sums, bgr: bool = False) -> Dict:
+        """The reference's result dictionary (:113-138) from the device outputs of every selected ROI.  ``img`` is the
+        frame the masks were computed on (``bgr``: in the caller's channel order, i.e. before detector.py:234)."""
+        out = {"segmented_regions": [], "masks": [], "contours": [], "area_analysis": {},
+               "total_defect_area": 0, "defect_density": 0.0}
+        H, W = img.shape[:2]
+        total_image_area = H * W
+        total_defect_area = 0
+        gray = None
+        for k, (i, x1, y1, x2, y2, method) in enumerate(sel):
+            d = detections[i]
+            local = local_masks[k]
+            defect_area = areas[k]
+            total_defect_area += defect_area
+            contours = self._find_contours(local)
+            gcontours = []
+            for c in contours:
+                g = c.copy(); g[:, 0, 0] += x1; g[:, 0, 1] += y1
+                gcontours.append(g)
+            gmask = _LazyFullMask((H, W), y1, x1, local)
+            if method == "adaptive":
+                roi = img[y1:y2, x1:x2]
+                if roi.ndim == 3:            # gray of the ROI == ROI of the gray frame (per-pixel transform)
+                    roi = cv2.cvtColor(np.ascontiguousarray(roi), cv2.COLOR_BGR2GRAY if bgr else cv2.COLOR_RGB2GRAY)
+                conf = self._adaptive_confidence(roi, local, defect_area)
+            else:
+                conf = self._threshold_confidence(sums[k], defect_area)
+            out["segmented_regions"].append({
+                "detection_id": i, "defect_class": d["class"], "confidence": d.get("confidence", 0.0),
+                "bbox": d["bbox"], "mask": gmask, "local_mask": local, "contours": gcontours,
+                "area_pixels": defect_area, "area_percentage": (defect_area / total_image_area) * 100,
+                "perimeter": self._calculate_perimeter(contours),
+                "compactness": self._calculate_compactness(defect_area, contours),
+                "segmentation_method": method, "confidence_score": conf})
+            out["masks"].append(gmask)
+            out["contours"].extend(gcontours)
+        out["total_defect_area"] = total_defect_area
+        out["defect_density"] = (total_defect_area / total_image_area) * 100
+        out["area_analysis"] = self._analyze_defect_areas(out["segmented_regions"])
+        return out
 
     @staticmethod
     def _threshold_confidence(sums, area: int) -> float:
@@ -653,27 +730,71 @@ class _PassThroughPostProcessor:
 class RulesPostProcessor(_PassThroughPostProcessor):
     """PostProcessor.process_results (inference/postprocess.py:32-109) with the detection chain
     refine -> filter -> merge -> validate computed by ``rules.DetectionRules`` (the array form of row f1, pinned
-    against the reference's own class), the quality assessment (:466-599) and the risk analysis (:601-682).  The
-    recommendation texts are not restated (the reference emits them in the iteration order of a Python set of class
-    names, i.e. in no reproducible order): plug the reference's PostProcessor object for those.  Select with ``config['qcgraft']['postprocessor'] = 'rules'``."""
+    against the reference's own class), the quality assessment (:466-599), the risk analysis (:601-682) and the
+    recommendations (:684-762; the reference walks a Python *set* of class names there, i.e. in no reproducible
+    order -- here the classes come in order of first appearance).  This is the default post-processor of
+    ``QualityControlDetector``; the reference's own object can be plugged through ``config['qcgraft']['postprocessor']``."""
+
+    TYPE_RECOMMENDATIONS = {                                                                       # :737-762
+        "crack": ["Check material stress levels and handling procedures",
+                  "Verify temperature control during manufacturing"],
+        "scratch": ["Review handling and packaging procedures",
+                    "Check for abrasive contact points in production line"],
+        "dent": ["Inspect handling equipment for damage", "Review impact protection during transport"],
+        "discoloration": ["Check chemical process parameters",
+                          "Verify environmental conditions (humidity, temperature)"],
+        "contamination": ["Review cleaning procedures and protocols",
+                          "Check for foreign material sources in production area"]}
 
     def __init__(self, config):
         super().__init__(config)
         from .rules import DetectionRules
         self.rules = DetectionRules(config)
 
+    def _generate_recommendations(self, detections, quality, risk) -> List[str]:
+        rec = []
+        if quality["pass_fail_status"] == "FAIL":
+            rec.append("REJECT: Product does not meet quality standards")
+            if quality["severity_breakdown"]["critical"] > 0:
+                rec.append("Critical defects detected - investigate root cause immediately")
+            if quality["severity_breakdown"]["major"] > 2:
+                rec.append("Multiple major defects - review manufacturing process")
+        elif quality["pass_fail_status"] == "CONDITIONAL":
+            rec.append("CONDITIONAL PASS: Monitor closely and consider rework")
+            rec.append("Increase inspection frequency for similar products")
+        if risk["overall_risk_level"] == "high":
+            rec.append("High risk detected - implement immediate corrective actions")
+        if risk["defect_clustering"]["has_clusters"]:
+            rec.append("Defect clustering detected - check for systematic manufacturing issues")
+        seen = []
+        for d in detections:
+            if d["class"] not in seen:
+                seen.append(d["class"])
+                rec.extend(self.TYPE_RECOMMENDATIONS.get(d["class"], []))
+        if quality["average_confidence"] < 0.7:
+            rec.append("Low detection confidence - consider additional inspection methods")
+        if quality["defect_density"] > 5.0:
+            rec.append("High defect density - review entire manufacturing process")
+        return rec
+
     def process_results(self, ensemble_results, segmentation_results, image_shape):
         try:
+            from datetime import datetime
+            meta = {"processing_timestamp": datetime.now().isoformat(), "image_shape": image_shape,
+                    "post_processing_version": "1.0.0"}
             raw = ensemble_results.get("detections", [])
+            if not raw:                                                  # early return of :62-64
+                return {"detections": [], "quality_assessment": self.rules._assess_quality([], {}),
+                        "risk_analysis": {}, "recommendations": [], "metadata": dict(meta, total_detections=0)}
             dets = self.rules.process(raw, segmentation_results or {}, image_shape)
             quality = self.rules._assess_quality(dets, segmentation_results or {})
-            risk = self.rules._analyze_risks(dets, quality) if raw else {}     # no raw detections: early return (:62-64)
+            risk = self.rules._analyze_risks(dets, quality)
+            rec = self._generate_recommendations(dets, quality, risk)
         except Exception as e:                                    # the reference's convention: never raise
             logger.error(f"Error in post-processing: {str(e)}")
             return {"error": str(e)}
-        return {"detections": dets, "quality_assessment": quality, "risk_analysis": risk, "recommendations": [],
-                "metadata": {"total_detections": len(dets), "image_shape": tuple(image_shape),
-                             "post_processing_version": "1.0.0"}}
+        return {"detections": dets, "quality_assessment": quality, "risk_analysis": risk, "recommendations": rec,
+                "metadata": dict(meta, total_detections=len(dets))}
 
     def update_config(self, new_config):
         super().update_config(new_config)
@@ -695,18 +816,24 @@ class QualityControlDetector:
         self.ensemble_predictor = EnsemblePredictor(yolo_weights=yolo_weights, resnet_weights=resnet_weights,
                                                     config=self.config)
         self.segmentator = ImageSegmentator(self.config)
-        pp = (self.config or {}).get("qcgraft", {}).get("postprocessor")
-        if pp == "rules":
+        # the reference always runs PostProcessor (inference/detector.py:59-64): the array-form restatement is the
+        # default; 'passthrough' or any object with process_results/update_config can be plugged instead
+        pp = _qcfg(self.config).get("postprocessor", "rules")
+        if pp == "rules" or pp is None:
             pp = RulesPostProcessor(self.config)
-        self.postprocessor = pp if pp is not None else _PassThroughPostProcessor(self.config)
+        elif pp == "passthrough":
+            pp = _PassThroughPostProcessor(self.config)
+        self.postprocessor = pp
 
     def predict(self, image: np.ndarray, include_segmentation: bool = True, _head_override=None) -> Dict:
         start_time = time.time()
         try:
             if not self._validate_image(image):
                 return {"error": "Invalid image input"}
+            if self._fused():
+                return self._predict_group([image], include_segmentation, _head_override)[0]
             processed_image = self._preprocess_image(image)
-            ensemble_results = self.ensemble_predictor.predict(processed_image, _head_override=_head_override)
+            ensemble_results = self.ensemble_predictor.predict(processed_image)
             if "error" in ensemble_results:
                 return ensemble_results
             segmentation_results = {}
@@ -724,20 +851,132 @@ class QualityControlDetector:
             logger.error(f"Error in QC prediction: {str(e)}")
             return {"error": str(e)}
 
-    def predict_batch(self, images: List[np.ndarray], max_workers: int = 4) -> List[Dict]:
-        """Same signature/result as inference/detector.py:128-180; ``max_workers`` is accepted but the
-        images go through predict() on this thread (one CUDA stream keeps the GPU busier than 4 threads
-        contending for it); same-shape throughput batches use InspectionPipeline.run directly."""
+    # ---- the batched device path behind predict / predict_batch ------------------------------------------------
+    def _fused(self) -> bool:
+        """True when the stock drop-in stages are in place (a user-replaced stage keeps the staged path above)."""
+        ens = self.ensemble_predictor
+        return (type(ens) is EnsemblePredictor and type(self.segmentator) is ImageSegmentator
+                and ens.yolo_detector is not None and ens.resnet_classifier is not None
+                and ens.yolo_detector.model is not None and ens.resnet_classifier.model is not None
+                and ens.yolo_detector.model is ens.resnet_classifier._pipe)
+
+    def _predict_group(self, images: List[np.ndarray], include_segmentation: bool, head_override=None) -> List[Dict]:
+        """Same-shape validated images -> reference result dicts.  One upload of the frames, one pass of
+        InspectionPipeline (K1 -> YOLO -> K2 -> K3b/K3 -> ResNet-50 -> K7), one download of the packed results; the
+        per-image dictionaries are then built by the same host code the single-stage classes use."""
+        t0 = time.time()
+        ens, seg = self.ensemble_predictor, self.segmentator
+        ydet, rcls = ens.yolo_detector, ens.resnet_classifier
+        pipe = ydet.model
+        pipe.conf, pipe.iou = ydet.confidence_threshold, ydet.nms_threshold
+        pre = self.config.get("preprocessing", {}) if isinstance(self.config, dict) else {}
+        raw_ok = not ("resize" in pre or pre.get("denoise", False) or pre.get("enhance_contrast", False))
+        decoded = [_decode(im) for im in images]
+        if raw_ok:
+            # no optional host preprocessing: the three channel flips are folded into the kernels' swap flags
+            frames_np = [_as_rgb3(im) for im in decoded]
+            shapes = [self._processed_shape(im) for im in decoded]
+        else:
+            processed = [self._preprocess_image(im) for im in images]
+            frames_np = [_as_rgb3(im) for im in processed]
+            shapes = [im.shape for im in processed]
+        batch = torch.from_numpy(np.stack(frames_np))
+        res = pipe.run(batch.to(pipe.dev), head_override=head_override, include_segmentation=include_segmentation,
+                       keep_seg_tensors=include_segmentation, processed=not raw_ok)
+        n = len(images)
+        # ROI rows of every image; packed masks come down once per method group
+        masks_host = {}
+        if res.seg is not None:
+            for g in res.seg:
+                m = g["seg"]["mask"].cpu().numpy()
+                for j, k in enumerate(g["idx"]):
+                    r = g["seg"]["regions"][j]
+                    o = int(r.out_offset)
+                    masks_host[int(k)] = m[o:o + int(r.w) * int(r.h)].reshape(int(r.h), int(r.w))
+        per_image = (time.time() - t0) / n
+        out = []
+        for i in range(n):
+            try:
+                rows = res.det[i, :int(res.count[i])]
+                shape = shapes[i]
+                dets = ydet._parse_results(rows, shape)
+                yolo_results = {"detections": dets, "inference_time_ms": per_image * 1000,
+                                "image_shape": tuple(shape[:2]), "total_detections": len(dets)}
+                resnet_results = rcls._result(res.global_probs[i])
+                resnet_results["inference_time_ms"] = per_image * 1000
+                ks = np.nonzero(res.roi_img == i)[0]
+                roi_probs = {int(res.roi_det[k]): res.roi_probs[k] for k in ks} if res.roi_probs is not None else {}
+                ensemble_results = ens._combine_predictions(yolo_results, resnet_results, shape, None, _roi_probs=roi_probs)
+                ensemble_results["total_inference_time_ms"] = per_image * 1000
+                if "error" in ensemble_results:
+                    out.append(ensemble_results)
+                    continue
+                segmentation_results = {}
+                if include_segmentation and dets:
+                    sel, lm, ar, sm = [], {}, {}, {}
+                    for k in ks:
+                        x1, y1, x2, y2 = (int(v) for v in res.roi_box[k])
+                        code = int(res.seg_method[k])
+                        name = seg._select_segmentation_method(dets[int(res.roi_det[k])]["class"])
+                        name = name if name in ("adaptive", "threshold") else "threshold_fallback"
+                        j = len(sel)
+                        sel.append((int(res.roi_det[k]), x1, y1, x2, y2, name))
+                        lm[j], ar[j], sm[j] = masks_host[int(k)], int(res.seg_area[k]), res.seg_sums[k]
+                        assert (code == ffi.QC_SEG_REF_ADAPTIVE) == (name == "adaptive")
+                    segmentation_results = seg._assemble(frames_np[i], dets, sel, lm, ar, sm, bgr=raw_ok)
+                final = self.postprocessor.process_results(ensemble_results, segmentation_results, shape)
+                dt = per_image + 0.0
+                self._update_performance_stats(dt)
+                final.update({"total_inference_time_ms": dt * 1000,
+                              "processing_pipeline": "ensemble + segmentation + postprocess",
+                              "image_metadata": self._get_image_metadata(images[i])})
+                out.append(final)
+            except Exception as e:
+                logger.error(f"Error in QC prediction: {str(e)}")
+                out.append({"error": str(e)})
+            per_image = (time.time() - t0) / n
+        return out
+
+    @staticmethod
+    def _processed_shape(decoded: np.ndarray) -> tuple:
+        return decoded.shape
+
+    def predict_batch(self, images: List[np.ndarray], max_workers: int = 4, _head_override=None) -> List[Dict]:
+        """Same signature / result as inference/detector.py:128-180 (results in input order, ``batch_index`` and
+        ``batch_statistics`` on every result).  Instead of ``max_workers`` threads calling predict(), valid images
+        are grouped by shape and every group goes through the device pipeline as ONE batch."""
         start_time = time.time()
         try:
-            results = []
+            results: List[Optional[Dict]] = [None] * len(images)
+            groups: Dict[tuple, List[int]] = {}
+            fused = self._fused()
             for i, img in enumerate(images):
-                try:
-                    r = self.predict(img)
-                    r["batch_index"] = i
-                except Exception as e:
-                    r = {"error": str(e), "batch_index": i}
-                results.append(r)
+                if not self._validate_image(img):
+                    results[i] = {"error": "Invalid image input"}
+                elif not fused:
+                    results[i] = self.predict(img)
+                else:
+                    try:
+                        d = _decode(img)
+                        groups.setdefault(tuple(d.shape), []).append(i)
+                    except Exception as e:
+                        results[i] = {"error": str(e)}
+            chunk = int(_qcfg(self.config).get("max_batch", 64))
+            for shape, idx in groups.items():
+                for c0 in range(0, len(idx), chunk):
+                    part = idx[c0:c0 + chunk]
+                    try:
+                        ho = None
+                        if _head_override is not None:
+                            sel = torch.as_tensor(part, device=_head_override[0].device)
+                            ho = [l.index_select(0, sel) for l in _head_override]
+                        rs = self._predict_group([images[i] for i in part], True, ho)
+                    except Exception as e:
+                        rs = [{"error": str(e)} for _ in part]
+                    for i, r in zip(part, rs):
+                        results[i] = r
+            for i, r in enumerate(results):
+                r["batch_index"] = i
             total_time = time.time() - start_time
             stats = {"batch_size": len(images), "total_batch_time_ms": total_time * 1000,
                      "average_time_per_image_ms": (total_time * 1000) / max(len(images), 1),

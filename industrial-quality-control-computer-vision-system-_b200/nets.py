@@ -156,6 +156,90 @@ def build_resnet50(nc: int = 5, seed: int = 0) -> nn.Module:
     return m.eval()
 
 
+# ---- checkpoints ---------------------------------------------------------------------------------------------
+# ultralytics' DetectionModel is nn.Sequential "model.{i}"; the same layers by name here (yolov8.yaml order)
+_ULTRA_INDEX = {"b0": 0, "b1": 1, "b2": 2, "b3": 3, "b4": 4, "b5": 5, "b6": 6, "b7": 7, "b8": 8, "b9": 9,
+                "h12": 12, "h15": 15, "h16": 16, "h18": 18, "h19": 19, "h21": 21, "detect": 22}
+_SCALE_BY_STEM = {16: "n", 32: "s", 48: "m"}
+
+
+def _checkpoint_state_dict(path: str) -> dict:
+    """torch file -> flat state dict.  Accepts a plain state_dict, {'state_dict': ...} (models/resent_model.py:93-99),
+    {'model_state_dict': ...} (scripts/download_models.py:153-157), {'model': state_dict}, and -- only where the
+    ultralytics package is importable, its pickled {'model': DetectionModel} checkpoints (models/yolo_model.py:52)."""
+    try:
+        ck = torch.load(path, map_location="cpu", weights_only=True)
+    except Exception:
+        ck = torch.load(path, map_location="cpu", weights_only=False)      # pickled modules need their package
+    if isinstance(ck, dict):
+        for k in ("state_dict", "model_state_dict", "model", "ema"):
+            v = ck.get(k)
+            if isinstance(v, dict) and v and all(torch.is_tensor(t) for t in v.values()):
+                return v
+            if isinstance(v, nn.Module):
+                return v.float().state_dict()
+        if ck and all(torch.is_tensor(t) for t in ck.values()):
+            return ck
+    if isinstance(ck, nn.Module):
+        return ck.float().state_dict()
+    raise ValueError(f"{path}: no state dict found in checkpoint")
+
+
+def load_resnet_checkpoint(path: str, nc: int = 5) -> nn.Module:
+    """models/resent_model.py:85-107: resnet50 + head, state dict loaded strictly."""
+    m = torchvision.models.resnet50(weights=None)
+    nf = m.fc.in_features
+    m.fc = nn.Sequential(nn.Dropout(0.5), nn.Linear(nf, 512), nn.ReLU(inplace=True), nn.Dropout(0.3), nn.Linear(512, nc))
+    sd = {k[7:] if k.startswith("module.") else k: v for k, v in _checkpoint_state_dict(path).items()}
+    m.load_state_dict(sd, strict=True)
+    return m.eval()
+
+
+def ultralytics_state_dict(model: "YOLOv8") -> dict:
+    """This module's weights under ultralytics' key names (fused form: model.{i}...conv.weight / conv.bias)."""
+    out = {}
+    for k, v in model.state_dict().items():
+        head, rest = k.split(".", 1)
+        out[f"model.{_ULTRA_INDEX[head]}.{rest}"] = v.detach().clone()
+    return out
+
+
+def load_yolo_checkpoint(path: str):
+    """A YOLOv8 detection checkpoint in ultralytics' key layout -> (YOLOv8 module, scale, nc).  Unfused Conv+BN pairs
+    ('...conv.weight' + '...bn.*', eps 1e-3 as ultralytics builds them) are folded into the biased convs this module
+    runs -- what ``model.fuse()`` does before inference; scale and class count are read off the tensor shapes."""
+    sd = _checkpoint_state_dict(path)
+    sd = {(k[6:] if k.startswith("model.model.") else k): v.float() for k, v in sd.items()}
+    stem = sd["model.0.conv.weight"].shape[0]
+    if stem not in _SCALE_BY_STEM:
+        raise ValueError(f"{path}: unsupported YOLOv8 width (stem channels {stem}); n / s / m are built")
+    scale = _SCALE_BY_STEM[stem]
+    nc = sd["model.22.cv3.0.2.weight"].shape[0]
+    m = YOLOv8(scale, nc).eval()
+    new = {}
+    for k, ref in m.state_dict().items():
+        head, rest = k.split(".", 1)
+        src = f"model.{_ULTRA_INDEX[head]}.{rest}"
+        if src in sd:
+            t = sd[src]
+        elif rest.endswith("conv.bias") and src[:-9] + "bn.weight" in sd:
+            t = None                                                   # produced with the weight below
+        else:
+            raise KeyError(f"{path}: missing {src}")
+        if rest.endswith("conv.weight") and src[:-11] + "bn.weight" in sd:
+            pre = src[:-11] + "bn."
+            g, b, mu, var = sd[pre + "weight"], sd[pre + "bias"], sd[pre + "running_mean"], sd[pre + "running_var"]
+            sc = g / torch.sqrt(var + 1e-3)
+            new[k] = t * sc.view(-1, 1, 1, 1)
+            new[k[:-6] + "bias"] = b - mu * sc
+        elif t is not None:
+            new[k] = t
+        if k in new and new[k].shape != ref.shape:
+            raise ValueError(f"{path}: {src} has shape {tuple(new[k].shape)}, expected {tuple(ref.shape)}")
+    m.load_state_dict(new, strict=True)
+    return m, scale, nc
+
+
 def fold_batchnorm(m: nn.Module) -> nn.Module:
     """Inference-time Conv+BN folding (same function, fewer elementwise passes over the activations):
     every (convN, bnN) / downsample (conv, bn) pair of a torchvision ResNet becomes one biased conv."""

@@ -24,7 +24,10 @@ import torch
 from . import ffi, nets
 
 CLASS_NAMES = ["crack", "scratch", "dent", "discoloration", "contamination"]   # models/yolo_model.py:59-61
-DARK_CLASSES = (0, 1)            # crack, scratch -> THRESH_BINARY_INV (inference/segmentation.py:278)
+DARK_CLASSES = (0, 1)            # crack, scratch -> THRESH_BINARY_INV / '<' (inference/segmentation.py:229,278)
+ADAPTIVE_CLASSES = (0, 1)        # crack, scratch -> 'adaptive'; every other class -> 'threshold' (:187-195; dent and
+                                 # contamination through the reference's threshold fallback, :175-183)
+SEG_FACTORS = np.array([0.9, 0.9, 1.1, 0.8, 0.85], np.float64)                   # :218-224 by class id
 RESNET_MEAN = (0.485, 0.456, 0.406)
 RESNET_STD = (0.229, 0.224, 0.225)
 
@@ -52,8 +55,10 @@ class BatchResult:
     roi_probs: Optional[np.ndarray] = None      # [K, nc] float32 softmax of the ROI classifier
     global_probs: Optional[np.ndarray] = None   # [n, nc] whole-frame classifier
     seg_area: Optional[np.ndarray] = None       # [K] int64 kept mask pixels (== np.sum(mask>0))
-    seg_thr: Optional[np.ndarray] = None        # [K] Otsu thresholds
+    seg_thr: Optional[np.ndarray] = None        # [K] Otsu threshold / Otsu bin (threshold method) / block size (adaptive)
     seg_ncomp: Optional[np.ndarray] = None      # [K]
+    seg_method: Optional[np.ndarray] = None     # [K] ffi.QC_SEG_* the ROI went through
+    seg_sums: Optional[np.ndarray] = None       # [K,4] int64 confidence sums (threshold method rows)
     spc: Optional[np.ndarray] = None            # [9] float64
     seg: Optional[dict] = None                  # device tensors of K4 (mask/labels/stats) when requested
     timings_ms: dict = field(default_factory=dict)
@@ -63,7 +68,7 @@ class InspectionPipeline:
     def __init__(self, yolo_scale: str = "s", nc: int = 5, device: int = 0, conf: float = 0.7, iou: float = 0.5,
                  imgsz: int = 640, max_det: int = 300, net_dtype=torch.bfloat16, seed: int = 0,
                  classify_rois: bool = True, classify_global: bool = True, letterbox_auto: bool = False,
-                 use_graphs: bool = True):
+                 use_graphs: bool = True, seg_mode: str = "reference", build_nets: bool = True):
         self.qc = ffi.Context.current(device)
         self.dev = torch.device("cuda", device)
         self.nc, self.conf, self.iou, self.imgsz, self.max_det = nc, conf, iou, imgsz, max_det
@@ -71,25 +76,42 @@ class InspectionPipeline:
         self.classify_rois, self.classify_global = classify_rois, classify_global
         self.letterbox_mode = ffi.QC_PRE_LETTERBOX_AUTO if letterbox_auto else ffi.QC_PRE_LETTERBOX
         torch.backends.cudnn.benchmark = True
-        self.yolo = nets.build_yolo(yolo_scale, nc, seed).to(self.dev, net_dtype).to(memory_format=torch.channels_last)
-        self.resnet = nets.fold_batchnorm(nets.build_resnet50(nc, seed)).to(self.dev, net_dtype).to(
-            memory_format=torch.channels_last)
-        if net_dtype in (torch.bfloat16, torch.float16):
-            self.resnet = nets.fuse_resnet_epilogues(self.resnet)      # cuDNN conv+bias(+add)+ReLU
         self.yolo_scale = yolo_scale
         self._plans = {}
         # nets replay as CUDA graphs at static shapes; K1 / K3 write straight into the graph inputs
         self.use_graphs = use_graphs
-        self.yolo_g = nets.GraphedNet(self.yolo, self.dev, net_dtype)
-        self.resnet_g = nets.GraphedNet(self.resnet, self.dev, net_dtype)
+        self.yolo = self.resnet = self.yolo_g = self.resnet_g = None
+        self.yolo_source = self.resnet_source = None
+        if build_nets:          # seeded random-init nets (synthetic benchmarks and tests)
+            self.install_yolo(nets.build_yolo(yolo_scale, nc, seed), f"synthetic:yolov8{yolo_scale}:seed{seed}")
+            self.install_resnet(nets.build_resnet50(nc, seed), f"synthetic:resnet50:seed{seed}")
         self.crop_chunks = (256, 128, 64, 32, 16, 8)      # static ResNet batch sizes (largest first)
         self.seg_max_comp = 1024             # first-pass stats rows per ROI (overflowing ROIs are redone)
+        # "reference": per-class methods of inference/segmentation.py:185-195 (K7); "composite": the north-star K4
+        # chain (Otsu -> 3x3 morphology -> CCL) for every class
+        assert seg_mode in ("reference", "composite")
+        self.seg_mode = seg_mode
         self.record = False          # bench.py: CUDA-event pairs around every stage
         self.events = {}
         # host frames: H2D on a copy stream into one of two staging buffers, so the copy of batch i+1 overlaps the
         # compute of batch i (run_async is called before the previous batch is finalised)
         self.copy_stream = torch.cuda.Stream(self.dev)
         self._stage = {}             # (shape) -> [buffers, free events, next index]
+
+    def install_yolo(self, module, source: str):
+        """YOLOv8 module (nets.build_yolo / nets.load_yolo_checkpoint) -> device, net dtype, channels_last, graphs."""
+        self.yolo = module.eval().to(self.dev, self.net_dtype).to(memory_format=torch.channels_last)
+        self.yolo_g = nets.GraphedNet(self.yolo, self.dev, self.net_dtype)
+        self.yolo_source = source
+        self.yolo_scale = getattr(module, "scale", self.yolo_scale)
+
+    def install_resnet(self, module, source: str):
+        r = nets.fold_batchnorm(module.eval()).to(self.dev, self.net_dtype).to(memory_format=torch.channels_last)
+        if self.net_dtype in (torch.bfloat16, torch.float16):
+            r = nets.fuse_resnet_epilogues(r)          # cuDNN conv+bias(+add)+ReLU
+        self.resnet = r
+        self.resnet_g = nets.GraphedNet(self.resnet, self.dev, self.net_dtype)
+        self.resnet_source = source
 
     class _Timed:
         def __init__(self, pipe, name):
@@ -136,6 +158,8 @@ class InspectionPipeline:
     @torch.no_grad()
     def detect(self, frames: torch.Tensor, inject: Optional[Sequence[torch.Tensor]] = None,
                head_override: Optional[Sequence[torch.Tensor]] = None, swap_rb: bool = True):
+        if self.yolo is None and head_override is None:
+            raise ffi.QcGraftError("YOLO model not loaded")
         """K1 -> YOLOv8 -> K2 on a same-shape uint8 [n,h,w,3] CUDA batch.  The frames are in the
         channel order the caller handed to ``QualityControlDetector.predict``; the reference flips
         channels three times before the net sees them (inference/detector.py:234,
@@ -178,14 +202,20 @@ class InspectionPipeline:
 
     @torch.no_grad()
     def run_async(self, frames: torch.Tensor, inject=None, head_override=None, include_segmentation: bool = True,
-                  keep_seg_tensors: bool = False, morph_iters: int = 1, min_area: int = 20) -> "PendingResult":
+                  keep_seg_tensors: bool = False, morph_iters: int = 1, min_area: int = 20,
+                  processed: bool = False) -> "PendingResult":
+        """frames: uint8 [n,h,w,3], CUDA or (pinned) host.  ``processed=False``: the frames are what the caller hands to
+        ``QualityControlDetector.predict`` (the reference then flips channels at inference/detector.py:234,
+        models/yolo_model.py:80, inside ultralytics, and at models/resent_model.py:123 -- folded into the kernels'
+        swap flags); ``processed=True``: the frames are the output of ``_preprocess_image`` (already flipped once)."""
         qc = self.qc
-        seg_cap = regs = None
+        if self.resnet is None and (self.classify_global or self.classify_rois):
+            raise ffi.QcGraftError("ResNet model not loaded")
         stage_slot = None
         if not frames.is_cuda:
             frames, stage_slot = self._upload(frames)
         n, h, w = frames.shape[:3]
-        det_d, anchor_d, count_d, _ = self.detect(frames, inject, head_override)
+        det_d, anchor_d, count_d, _ = self.detect(frames, inject, head_override, swap_rb=not processed)
         spc_d = qc.spc_stats(det_d, count_d)
         # ---- the one mid-pipeline device->host copy (packed detections) -------------------------
         det = det_d.cpu().numpy()
@@ -208,16 +238,17 @@ class InspectionPipeline:
                 rois = torch.from_numpy(np.ascontiguousarray(r)).to(self.dev, non_blocking=True)
 
             # ResNet sees the caller's channel order (two flips: detector.py:234 + resent_model.py:123)
+            rswap = bool(processed)
             def fill(buf, o, k):
                 """classifier rows [o, o+k) -> buf[:k]"""
                 a = min(o + k, n_whole)
                 if o < a:
                     with self._timed("k3b_pil_resize"):
-                        qc.pil_resize(frames[o:a], swap_rb=False, mean=RESNET_MEAN, std=RESNET_STD, out=buf[:a - o])
+                        qc.pil_resize(frames[o:a], swap_rb=rswap, mean=RESNET_MEAN, std=RESNET_STD, out=buf[:a - o])
                 if o + k > a:
                     lo = max(o, n_whole)
                     with self._timed("k3_roi_align"):
-                        qc.roi_align(frames, rois[lo - n_whole:o + k - n_whole], swap_rb=False, mean=RESNET_MEAN,
+                        qc.roi_align(frames, rois[lo - n_whole:o + k - n_whole], swap_rb=rswap, mean=RESNET_MEAN,
                                      std=RESNET_STD, out=buf[lo - o:k])
 
             if not self.use_graphs:
@@ -239,24 +270,13 @@ class InspectionPipeline:
                     o += k
                 probs = torch.cat(parts)
 
-        # ---- K4 on every detection ROI ------------------------------------------------------------
+        # ---- segmentation of every detection ROI (K7 per-class methods, or the K4 composite) ------------------
         seg = None
         if include_segmentation and K:
             cls = det[roi_img, roi_det, 5].astype(np.int32)
-            regs = dict(img=roi_img, x=roi_box[:, 0], y=roi_box[:, 1], w=roi_box[:, 2] - roi_box[:, 0],
-                        h=roi_box[:, 3] - roi_box[:, 1], polarity=(~np.isin(cls, DARK_CLASSES)).astype(np.int32),
-                        thr_scale=1.0, min_area=min_area)
-            # K4 reads gray as the reference does AFTER inference/detector.py:234 swapped the channels
-            # stats rows are reserved per region; a first pass with a small reservation avoids initialising
-            # ~100 MB of rows that almost never exist, regions that overflow it are redone below
-            nblk = ((regs["w"].astype(np.int64) + 1) // 2) * ((regs["h"].astype(np.int64) + 1) // 2)
-            seg_cap = None if keep_seg_tensors else np.minimum(nblk + 1, self.seg_max_comp)
-            if seg_cap is not None:
-                regs["max_comp"] = seg_cap
-            with self._timed("k4_segment"):
-                seg = qc.segment(frames, regs, morph_iters=morph_iters, swap_rb=True,
-                                 want_mask=keep_seg_tensors, want_labels=keep_seg_tensors)
-            self.last_seg_pixels = int(seg["params"].total_pixels)
+            seg = self._segment_rois(frames, roi_img, roi_box, cls, keep_seg_tensors, morph_iters, min_area,
+                                     swap_rb=not processed)
+            self.last_seg_pixels = int(sum(int(g["seg"]["params"].total_pixels) for g in seg))
 
         # ---- final device->host reads: asynchronous copies into pinned buffers, finalised by .result() ------
         def stage(t):
@@ -267,14 +287,52 @@ class InspectionPipeline:
         if probs is not None:
             host["probs"] = stage(probs)
         if seg is not None:
-            host["area"], host["thr"], host["ncomp"] = stage(seg["area"]), stage(seg["thr"]), stage(seg["ncomp"])
+            for gi, g in enumerate(seg):
+                for k in ("area", "thr", "ncomp", "sums"):
+                    if g["seg"].get(k) is not None:
+                        host[f"{k}{gi}"] = stage(g["seg"][k])
         done = torch.cuda.Event()
         done.record()
         if stage_slot is not None:
             stage_slot[1] = done         # the staging buffer may be overwritten once this batch's kernels are done
-        return PendingResult(self, res, frames, host, done, dict(K=K, n=n, seg=seg, seg_cap=seg_cap if seg is not None else None,
-                                                                 regs=regs if seg is not None else None,
-                                                                 morph_iters=morph_iters, keep=keep_seg_tensors))
+        return PendingResult(self, res, frames, host, done, dict(K=K, n=n, seg=seg, keep=keep_seg_tensors))
+
+    def _segment_rois(self, frames, roi_img, roi_box, cls, keep: bool, morph_iters: int = 1, min_area: int = 20,
+                      swap_rb: bool = True):
+        """One launch sequence per segmentation method over all ROIs of the batch.  Returns the list of groups
+        (ROI indices, method, device results); PendingResult.result() scatters them back into ROI order."""
+        qc = self.qc
+        K = len(roi_img)
+        w, h = roi_box[:, 2] - roi_box[:, 0], roi_box[:, 3] - roi_box[:, 1]
+        if self.seg_mode == "composite":
+            specs = [("k4_segment", np.arange(K), ffi.QC_SEG_COMPOSITE, morph_iters, min_area)]
+        else:
+            ad = np.isin(cls, ADAPTIVE_CLASSES)
+            specs = [("k7_adaptive", np.nonzero(ad)[0], ffi.QC_SEG_REF_ADAPTIVE, 1, 20),       # :284-289
+                     ("k7_threshold", np.nonzero(~ad)[0], ffi.QC_SEG_REF_THRESHOLD, 2, 10)]    # :452-460
+        groups = []
+        for name, idx, code, iters, marea in specs:
+            if len(idx) == 0:
+                continue
+            regs = dict(img=roi_img[idx], x=roi_box[idx, 0], y=roi_box[idx, 1], w=w[idx], h=h[idx],
+                        polarity=(~np.isin(cls[idx], DARK_CLASSES)).astype(np.int32), thr_scale=1.0, min_area=marea)
+            cap = None
+            if code == ffi.QC_SEG_REF_THRESHOLD:
+                c = cls[idx]
+                regs["thr_scale"] = np.where((c >= 0) & (c < len(SEG_FACTORS)), SEG_FACTORS[np.clip(c, 0, len(SEG_FACTORS) - 1)], 1.0)
+                regs["max_comp"] = np.full(len(idx), 2, np.int64)
+            elif not keep:
+                # stats rows are reserved per region; a first pass with a small reservation avoids initialising
+                # ~100 MB of rows that almost never exist, regions that overflow it are redone by result()
+                nblk = ((w[idx].astype(np.int64) + 1) // 2) * ((h[idx].astype(np.int64) + 1) // 2)
+                cap = np.minimum(nblk + 1, self.seg_max_comp)
+                regs["max_comp"] = cap
+            # gray is read as the reference does AFTER inference/detector.py:234 swapped the channels
+            with self._timed(name):
+                seg = qc.segment(frames, regs, morph_iters=iters, swap_rb=swap_rb, want_mask=keep, want_labels=keep,
+                                 method=code, want_sums=(code == ffi.QC_SEG_REF_THRESHOLD))
+            groups.append(dict(name=name, idx=idx, code=code, iters=iters, seg=seg, cap=cap, regs=regs, swap_rb=swap_rb))
+        return groups
 
     def _upload(self, host_frames: torch.Tensor):
         """uint8 [n,h,w,3] host tensor (pinned for a truly asynchronous copy) -> device staging buffer; the compute
@@ -325,17 +383,28 @@ class PendingResult:
             if pipe.classify_rois and K:
                 res.roi_probs = pr[o:o + K].copy()
         if m["seg"] is not None:
-            res.seg_area = self.host["area"].numpy().copy()
-            res.seg_thr = self.host["thr"].numpy().copy()
-            res.seg_ncomp = self.host["ncomp"].numpy().copy()
-            seg_cap, regs = m["seg_cap"], m["regs"]
-            if seg_cap is not None:
-                over = np.nonzero(res.seg_ncomp > seg_cap)[0]
-                if len(over):       # components beyond the reservation escaped the min-area filter: redo exactly
-                    sub = {k: (v[over] if isinstance(v, np.ndarray) else v) for k, v in regs.items() if k != "max_comp"}
-                    seg2 = pipe.qc.segment(self.frames, sub, morph_iters=m["morph_iters"], swap_rb=True,
-                                           want_mask=False, want_labels=False)
-                    res.seg_area[over] = seg2["area"].cpu().numpy()
+            res.seg_area = np.zeros(K, np.int64)
+            res.seg_thr = np.zeros(K, np.int32)
+            res.seg_ncomp = np.zeros(K, np.int32)
+            res.seg_method = np.zeros(K, np.int32)
+            res.seg_sums = np.zeros((K, 4), np.int64)
+            for gi, g in enumerate(m["seg"]):
+                idx = g["idx"]
+                area = self.host[f"area{gi}"].numpy().copy()
+                ncomp = self.host[f"ncomp{gi}"].numpy()
+                if g["cap"] is not None:
+                    over = np.nonzero(ncomp > g["cap"])[0]
+                    if len(over):   # components beyond the reservation escaped the min-area filter: redo exactly
+                        sub = {k: (v[over] if isinstance(v, np.ndarray) else v) for k, v in g["regs"].items() if k != "max_comp"}
+                        seg2 = pipe.qc.segment(self.frames, sub, morph_iters=g["iters"], swap_rb=g["swap_rb"], want_mask=False,
+                                               want_labels=False, method=g["code"])
+                        area[over] = seg2["area"].cpu().numpy()
+                res.seg_area[idx] = area
+                res.seg_thr[idx] = self.host[f"thr{gi}"].numpy()
+                res.seg_ncomp[idx] = ncomp
+                res.seg_method[idx] = g["code"]
+                if f"sums{gi}" in self.host:
+                    res.seg_sums[idx] = self.host[f"sums{gi}"].numpy()
             if m["keep"]:
                 res.seg = m["seg"]
         self.frames = None

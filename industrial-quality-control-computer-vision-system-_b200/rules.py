@@ -159,6 +159,8 @@ class DetectionRules:
         already hold on the device."""
         if mask is None:
             return None
+        if hasattr(mask, "extent"):              # detector._LazyFullMask: same numbers from the ROI-sized mask
+            return mask.extent()
         m = np.asarray(mask) > 0
         rows = np.flatnonzero(m.any(1))
         if rows.size == 0:

@@ -13,7 +13,8 @@ One ``predict(image)`` call = what ``QualityControlDetector.predict`` does for o
   4. the ROI hand-off the reference mocks (models/ensemble.py:129-142): roi_align crops of the
      kept boxes -> ResNet-50 batch (oracle/roi.py fixes the convention)
   5. _merge_detection_classification                              models/ensemble.py:197-218
-  6. segment_defects per detection with the K4 composite          inference/segmentation.py:39-146
+  6. segment_defects per detection: the reference's per-class methods (oracle/refseg.py), or the K4
+     composite (seg_mode='composite')                             inference/segmentation.py:39-298
 The conv nets are the same random-init torch modules the GPU pipeline runs (float32 on CPU).
 The reference runs YOLO and ResNet in a 2-thread pool (models/ensemble.py:88); torch already
 uses every core for each net, so they run back to back here.
@@ -28,11 +29,12 @@ import torch
 from PIL import Image
 from torchvision import transforms
 
-from . import preprocess as opre, yolo_head as oyh, roi as oroi, segment as oseg
+from . import preprocess as opre, yolo_head as oyh, roi as oroi, segment as oseg, refseg as orefseg
 
 
 class CpuReferencePipeline:
-    def __init__(self, yolo, resnet, nc=5, conf=0.7, iou=0.5, imgsz=640, max_det=300):
+    def __init__(self, yolo, resnet, nc=5, conf=0.7, iou=0.5, imgsz=640, max_det=300, seg_mode="reference"):
+        self.seg_mode = seg_mode
         self.yolo, self.resnet = yolo.float().eval(), resnet.float().eval()
         self.nc, self.conf, self.iou, self.imgsz, self.max_det = nc, conf, iou, imgsz, max_det
         self.transform = transforms.Compose([                    # models/resent_model.py:59-66
@@ -88,6 +90,11 @@ class CpuReferencePipeline:
             for i in valid:
                 x1, y1, x2, y2 = boxes[i]
                 roi = np.ascontiguousarray(gray[y1:y2, x1:x2])
+                if self.seg_mode == "reference":
+                    m, conf, method = orefseg.segment_region(roi, detections[i]["class"])
+                    seg.append({"detection_id": i, "area_pixels": int((m > 0).sum()), "method": method,
+                                "confidence_score": conf})
+                    continue
                 dark = detections[i]["class"] in oseg.DARK_CLASSES
                 r = oseg.segment_k4(roi, 0 if dark else 1, 1.0, morph_iters, min_area)
                 seg.append({"detection_id": i, "area_pixels": int((r["mask"] > 0).sum()), "thr": r["thr"],

@@ -15,7 +15,7 @@ G = os.path.join(os.path.dirname(__file__), "golden")
 GOLD = json.load(open(os.path.join(G, "reference_golden.json")))
 CFG = {"model": {"confidence_threshold": 0.7, "nms_threshold": 0.5},
        "quality_control": {"defect_classes": ["crack", "scratch", "dent", "discoloration", "contamination"]},
-       "qcgraft": {"yolo_scale": "n", "device": 0}}
+       "qcgraft": {"yolo_scale": "n", "device": 0, "synthetic_weights": True}}
 
 
 def test_spc_kernel_matches_reference_extract_metrics(qc):
@@ -28,32 +28,42 @@ def test_spc_kernel_matches_reference_extract_metrics(qc):
     assert np.allclose(v, np.array(GOLD["spc"]["vector"], np.float64), rtol=1e-12, atol=0)
 
 
-def test_segmentator_matches_reference_chain():
-    """ImageSegmentator.segment_defects on the fixture's binary image == the reference's own
-    morphologyEx CLOSE/OPEN + _remove_small_components + contour statistics."""
-    from qcgraft.detector import ImageSegmentator
+def test_composite_matches_reference_morphology_chain(qc):
+    """K4 composite on the fixture's binary image == the reference's own morphologyEx CLOSE/OPEN +
+    _remove_small_components chain (inference/segmentation.py:284-289) recorded in the golden file."""
     z = np.load(os.path.join(G, "segmentation_chain.npz"))
     m0 = z["m0"]
     h, w = m0.shape
+    res = qc.segment(torch.from_numpy(m0[None]).cuda(), [dict(img=0, x=0, y=0, w=w, h=h, polarity=1, min_area=20)],
+                     morph_iters=1)
+    assert np.array_equal(res["mask"][:h * w].view(h, w).cpu().numpy(), z["m2"])
+    assert int(res["area"][0]) == GOLD["segmentation_chain"]["area_pixels"]
+
+
+def test_segmentator_clipping_and_empty_boxes():
+    """A box partly outside the frame is clipped like numpy slicing (:80); an empty box is skipped (:82-83); no
+    detections -> the empty result dict."""
+    from qcgraft import synth
+    from qcgraft.detector import ImageSegmentator
+    from oracle import refseg
+    import cv2
+    img = synth.make_frame(8, 300, 400)
     seg = ImageSegmentator(CFG)
-    det = [{"id": 0, "class": "dent", "confidence": 0.9, "bbox": {"x1": 0, "y1": 0, "x2": w, "y2": h}}]
-    out = seg.segment_defects(m0, det)
-    assert "error" not in out
-    r = out["segmented_regions"][0]
-    g = GOLD["segmentation_chain"]
-    assert np.array_equal(r["local_mask"], z["m2"])
-    assert r["area_pixels"] == g["area_pixels"] and len(r["contours"]) == g["n_contours"]
-    assert abs(r["perimeter"] - g["perimeter"]) < 1e-6 and abs(r["compactness"] - g["compactness"]) < 1e-9
-    assert np.array_equal(np.asarray(r["mask"]), z["m2"])                 # lazy full-frame mask
-    assert out["total_defect_area"] == g["area_pixels"]
-    assert seg.segment_defects(m0, [])["segmented_regions"] == []
-    # a box partly outside the frame is clipped like numpy slicing; an empty box is skipped
-    det2 = [{"id": 0, "class": "crack", "confidence": 0.9, "bbox": {"x1": 100, "y1": 50, "x2": 400, "y2": 300}},
-            {"id": 1, "class": "crack", "confidence": 0.9, "bbox": {"x1": 10, "y1": 10, "x2": 10, "y2": 40}}]
-    out2 = seg.segment_defects(m0, det2)
-    assert [r["detection_id"] for r in out2["segmented_regions"]] == [0]
-    ref = oseg.segment_k4(np.ascontiguousarray(m0[50:300, 100:400]), 0, 1.0, 1, 20)
-    assert np.array_equal(out2["segmented_regions"][0]["local_mask"], ref["mask"])
+    assert seg.segment_defects(img, [])["segmented_regions"] == []
+    det2 = [{"id": 0, "class": "crack", "confidence": 0.9, "bbox": {"x1": 100, "y1": 50, "x2": 500, "y2": 400}},
+            {"id": 1, "class": "crack", "confidence": 0.9, "bbox": {"x1": 10, "y1": 10, "x2": 10, "y2": 40}},
+            {"id": 2, "class": "discoloration", "confidence": 0.9, "bbox": {"x1": 300, "y1": 200, "x2": 450, "y2": 300}}]
+    out2 = seg.segment_defects(img, det2)
+    assert [r["detection_id"] for r in out2["segmented_regions"]] == [0, 2]
+    gray = cv2.cvtColor(img, cv2.COLOR_RGB2GRAY)
+    m, conf, method = refseg.segment_region(gray[50:300, 100:400], "crack")
+    r0 = out2["segmented_regions"][0]
+    assert np.array_equal(r0["local_mask"], m) and r0["segmentation_method"] == method == "adaptive"
+    assert abs(r0["confidence_score"] - conf) <= 1e-9
+    m2, conf2, method2 = refseg.segment_region(gray[200:300, 300:400], "discoloration")
+    r2 = out2["segmented_regions"][1]
+    assert np.array_equal(r2["local_mask"], m2) and abs(r2["confidence_score"] - conf2) <= 1e-9
+    assert np.asarray(r2["mask"]).shape == (300, 400) and out2["total_defect_area"] == int((m > 0).sum() + (m2 > 0).sum())
 
 
 def test_yolo_detector_dropin_matches_oracle():
@@ -94,7 +104,8 @@ def test_quality_control_detector_end_to_end_and_error_convention():
     assert abs(x0["ensemble_confidence"] - (0.6 * x0["yolo_confidence"] + 0.4 * min(x0["yolo_confidence"] * 1.1, 1.0))) < 1e-12
     assert "roi_classification" in x0["classification_details"]
     assert abs(sum(x0["classification_details"]["roi_classification"]["class_probabilities"].values()) - 1) < 1e-3
-    assert "segmentation" in x0 and x0["segmentation"]["area_pixels"] >= 0
+    assert x0["has_segmentation"] and x0["area_pixels"] >= 0 and "validation_score" in x0
+    assert out["metadata"]["post_processing_version"] == "1.0.0" and isinstance(out["recommendations"], list)
     assert d.get_performance_stats()["total_predictions"] == 1
     # error convention: never raises
     assert d.predict(None) == {"error": "Invalid image input"}
@@ -107,8 +118,8 @@ def test_quality_control_detector_end_to_end_and_error_convention():
     assert "error" not in d.predict(np.frombuffer(buf.tobytes(), np.uint8))     # 1-D encoded upload (app.py:190-194)
 
 
-@pytest.mark.parametrize("graphs", [False, True])
-def test_batched_pipeline_matches_cpu_reference_pipeline(graphs):
+@pytest.mark.parametrize("graphs,seg_mode", [(False, "reference"), (True, "reference"), (False, "composite")])
+def test_batched_pipeline_matches_cpu_reference_pipeline(graphs, seg_mode):
     """InspectionPipeline.run vs the oracle's per-image chain on identical inputs: kept boxes, classes,
     ROI tables, segmentation areas/thresholds identical; ROI class probabilities close (bf16 nets)."""
     from qcgraft import nets, synth
@@ -117,10 +128,13 @@ def test_batched_pipeline_matches_cpu_reference_pipeline(graphs):
     n = 3
     frames = synth.make_frames(700, n)
     heads = synth.make_head(701, n, 640, 640, 15)
-    pipe = InspectionPipeline("n", 5, device=0, use_graphs=graphs, net_dtype=torch.float32)
+    pipe = InspectionPipeline("n", 5, device=0, use_graphs=graphs, net_dtype=torch.float32, seg_mode=seg_mode)
     res = pipe.run(torch.from_numpy(frames).cuda(), head_override=[l.cuda() for l in heads], keep_seg_tensors=True)
     y = nets.build_yolo("n", 5, 0)
-    cp = CpuReferencePipeline(y, nets.build_resnet50(5, 0))
+    cp = CpuReferencePipeline(y, nets.build_resnet50(5, 0), seg_mode=seg_mode)
+    from qcgraft import ffi
+    code = {"adaptive": ffi.QC_SEG_REF_ADAPTIVE, "threshold": ffi.QC_SEG_REF_THRESHOLD,
+            "threshold_fallback": ffi.QC_SEG_REF_THRESHOLD}
     k0 = 0
     for i in range(n):
         ref = cp.predict(frames[i], head_override=[l[i:i + 1] for l in heads])
@@ -135,7 +149,10 @@ def test_batched_pipeline_matches_cpu_reference_pipeline(graphs):
         for kk, r in zip(sel, ref["segmented_regions"]):
             assert int(res.roi_det[kk]) == r["detection_id"]
             assert int(res.seg_area[kk]) == r["area_pixels"], (i, kk)
-            assert int(res.seg_thr[kk]) == r["thr"] and int(res.seg_ncomp[kk]) == r["ncomp"]
+            if seg_mode == "composite":
+                assert int(res.seg_thr[kk]) == r["thr"] and int(res.seg_ncomp[kk]) == r["ncomp"]
+            else:
+                assert int(res.seg_method[kk]) == code[r["method"]]
             p_ref = ref["detections"][r["detection_id"]]["roi_class_probabilities"]
             assert np.abs(res.roi_probs[kk] - p_ref).max() < 2e-2
         k0 += len(sel)
@@ -164,3 +181,82 @@ def test_pipeline_host_frames_and_stats_only_area():
         assert np.array_equal(a.seg_area, b.seg_area) and np.array_equal(a.seg_thr, b.seg_thr)
         assert np.array_equal(a.seg_ncomp, b.seg_ncomp) and np.allclose(a.roi_probs, b.roi_probs, atol=1e-6)
         assert np.array_equal(a.spc, b.spc)
+
+
+def _close(a, b, path="", tol=3e-2):
+    """dict/list equality with a float tolerance (batch-1 and batch-n convolutions pick different cuDNN kernels)."""
+    if isinstance(a, dict):
+        assert isinstance(b, dict) and set(a) == set(b), f"{path}: keys {set(a) ^ set(b)}"
+        for k in a:
+            if k in ("total_inference_time_ms", "inference_time_ms", "processing_timestamp", "batch_statistics",
+                     "batch_index", "mask", "masks"):
+                continue
+            _close(a[k], b[k], f"{path}.{k}", tol)
+    elif isinstance(a, (list, tuple)):
+        assert len(a) == len(b), path
+        for i, (x, y) in enumerate(zip(a, b)):
+            _close(x, y, f"{path}[{i}]", tol)
+    elif isinstance(a, np.ndarray):
+        assert np.array_equal(a, np.asarray(b)), path
+    elif isinstance(a, (float, np.floating)) or isinstance(b, (float, np.floating)):
+        assert abs(float(a) - float(b)) <= tol * max(1.0, abs(float(a))), f"{path}: {a} vs {b}"
+    else:
+        assert a == b, f"{path}: {a} vs {b}"
+
+
+def test_predict_batch_is_one_device_batch_and_equals_sequential_predict():
+    """predict_batch(64 frames) (inference/detector.py:128-180 signature) == 64 predict() calls, and >= 10x faster."""
+    import time
+    from qcgraft import synth
+    from qcgraft.detector import QualityControlDetector
+    n = 64
+    d = QualityControlDetector("y.pt", "r.pt", dict(CFG))
+    imgs = [synth.make_frame(900 + i) for i in range(n)]
+    heads = [l.cuda() for l in synth.make_head(950, n, 640, 640, 10)]
+    d.predict_batch(imgs[:8], _head_override=[l[:8] for l in heads])         # warm-up: graph capture, autotune
+    d.predict(imgs[0], _head_override=[l[:1] for l in heads])
+    torch.cuda.synchronize()
+    t = time.time()
+    rb = d.predict_batch(imgs, _head_override=heads)
+    tb = time.time() - t
+    t = time.time()
+    rs = [d.predict(imgs[i], _head_override=[l[i:i + 1] for l in heads]) for i in range(n)]
+    ts = time.time() - t
+    assert all("error" not in r for r in rb) and [r["batch_index"] for r in rb] == list(range(n))
+    assert rb[0]["batch_statistics"]["batch_size"] == n
+    assert sum(len(r["detections"]) for r in rs) > 0
+    for i in range(n):
+        _close(rs[i], {k: v for k, v in rb[i].items() if k not in ("batch_index", "batch_statistics")}, f"img{i}")
+    print(f"predict_batch: {tb * 1000:.1f} ms for {n} frames; {n} x predict: {ts * 1000:.1f} ms; speed-up {ts / tb:.1f}x")
+    assert ts / tb >= 10.0
+    # mixed shapes, an invalid entry and an encoded upload keep their slots
+    mix = [imgs[0], None, synth.make_frame(1, 480, 640), imgs[1]]
+    rm = d.predict_batch(mix)
+    assert "error" in rm[1] and all("error" not in rm[i] for i in (0, 2, 3)) and rm[2]["image_metadata"]["original_shape"] == (480, 640, 3)
+
+
+def test_checkpoints_are_loaded_and_missing_files_fail_like_the_reference(tmp_path):
+    """models/yolo_model.py:45-69, models/resent_model.py:85-107: weights come from the checkpoint files; without them
+    (and without the explicit synthetic flag) the models are not loaded and predict returns the reference's error."""
+    from qcgraft import nets, synth
+    from qcgraft.detector import QualityControlDetector, YOLODetector
+    cfg = {k: v for k, v in CFG.items() if k != "qcgraft"}
+    cfg["qcgraft"] = {"device": 0}
+    bad = QualityControlDetector(str(tmp_path / "missing_y.pt"), str(tmp_path / "missing_r.pt"), dict(cfg))
+    assert bad.predict(synth.make_frame(1)) == {"error": "Models not loaded"}
+    assert YOLODetector(str(tmp_path / "nope.pt"), config=dict(cfg)).predict(synth.make_frame(1)) == {"error": "Model not loaded"}
+    y = nets.build_yolo("s", 5, 7)
+    r = nets.build_resnet50(5, 7)
+    torch.save({"model": nets.ultralytics_state_dict(y)}, tmp_path / "y.pt")
+    torch.save({"state_dict": r.state_dict()}, tmp_path / "r.pt")
+    d = QualityControlDetector(str(tmp_path / "y.pt"), str(tmp_path / "r.pt"), dict(cfg))
+    info = d.get_system_info()["ensemble_info"]
+    assert info["yolo_info"]["model_loaded"] and info["resnet_info"]["model_loaded"]
+    pipe = d.ensemble_predictor.yolo_detector.model
+    assert pipe.yolo_scale == "s" and pipe.yolo_source.endswith("y.pt") and pipe.resnet_source.endswith("r.pt")
+    out = d.predict(synth.make_frame(2))
+    assert "error" not in out and "quality_assessment" in out
+    x = torch.from_numpy(synth.make_frame(2)[None]).cuda()
+    lev = pipe.yolo(pipe.qc.preprocess(x, pipe.plan_for(640, 640), swap_rb=True).contiguous(memory_format=torch.channels_last))
+    ref = y.cuda().float()(pipe.qc.preprocess(x, pipe.plan_for(640, 640), swap_rb=True, out_dtype=torch.float32))
+    assert max((a.float() - b).abs().max().item() for a, b in zip(lev, ref)) < 0.25        # bf16 net vs fp32 module

@@ -223,3 +223,25 @@ def test_max_nms_cut(qc):
     levels = synth.make_head(304, 2, 640, 640, 700, n_centres=120)
     for mn in (650, 257, 64):
         _compare_full(qc, levels, 640, 640, max_nms=mn)
+
+
+def test_saturated_sigmoid_ties_take_the_first_class(qc):
+    """float32 sigmoid saturates: logits (18, 20), (13.95, 14.0), (30, 17) ... give EQUAL scores, and torch.max returns
+    the first class, not the class of the largest logit (class label and NMS class offset depend on it)."""
+    from qcgraft import synth
+    levels = synth.make_head(31, 2, 640, 640, 0)
+    rng = np.random.default_rng(31)
+    pairs = [(18.0, 20.0), (13.95, 14.0), (30.0, 17.0), (16.8, 25.0), (12.49, 12.5), (9.0, 9.0005), (11.0, 19.0)]
+    for img in range(2):
+        for l, lev in enumerate(levels):
+            hh, ww = lev.shape[2:]
+            for k, (a, b) in enumerate(pairs):
+                y, x = int(rng.integers(0, hh)), int(rng.integers(0, ww))
+                c = rng.permutation(5)
+                lev[img, 64 + c[0], y, x] = a if c[0] < c[1] else b      # the smaller logit sits in the lower class index
+                lev[img, 64 + c[1], y, x] = b if c[0] < c[1] else a
+                for side in range(4):
+                    lev[img, side * 16 + int(rng.integers(1, 6)), y, x] += 6.0
+    det, count = _compare_full(qc, levels, 640, 640)
+    assert int(count.min()) > 0
+    _compare_full(qc, levels, 640, 640, dtype=torch.bfloat16)
