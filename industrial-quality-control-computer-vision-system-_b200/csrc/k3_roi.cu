@@ -16,6 +16,8 @@
 // Algorithmic bytes per ROI: roi_w*roi_h*3 (read) + 3*out_h*out_w*sizeof(out) (write).
 #include "common.cuh"
 #include <math.h>
+#include <limits.h>
+#include <algorithm>
 
 namespace {
 
@@ -339,6 +341,325 @@ k3_roi_sep(const uint8_t* __restrict__ imgs, int n, int H, int W, long long img_
     }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// k3_roi_tma (sampling_ratio 1..2, out_w % 4 == 0, out_w <= 224 columns per CTA pass): ONE CTA per ROI walks the
+// ROI's output rows in bands.  Per ROI, once: every thread builds the merged x taps of its output column (<= 4 source
+// pixels with summed weights, kept in registers) and the CTA builds the merged y taps of every output row.  Per band:
+//   (0) the band's source rows are staged as raw bytes in shared memory -- the 16-byte aligned superset of the row
+//       segment the ROI touches, one 1-D TMA bulk copy (cp.async.bulk + mbarrier -> SASS UBLKCP) per row when base
+//       and pitch are 16-byte aligned, plain loads otherwise; the copy of band b+1 is issued as soon as band b's
+//       horizontal pass has consumed the buffer, so it overlaps band b's vertical pass
+//   (1) horizontal pass, thread per output column: <= 4 byte taps x 3 channels from shared memory -> Hs[row][c][col]
+//   (2) vertical pass, thread per (4 columns, row slice), 3 channels: <= 4 LDS.128 + 16 FMAs per 12 outputs,
+//       /255 + Normalize, one 64-bit (bf16x4) or 128-bit (f32x4) store per channel.
+constexpr int K3T_THREADS = 224;
+constexpr int K3T_ROWS = 16;               // source rows per band held as Hs
+constexpr int K3T_RAW = 32 * 1024;         // raw byte staging buffer
+constexpr int K3T_PH_MAX = 256;
+
+struct K3Taps { int i[4]; float w[4]; int n; };
+
+// merged taps of the `sr` samples of one output coordinate: torchvision's sample positions and clamping rules; samples
+// outside [-1, size] contribute nothing; equal source indices are merged by adding their weights
+__device__ __forceinline__ K3Taps k3_taps(float start, float bin, int p, int sr, int size) {
+    K3Taps t;
+    t.n = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { t.i[j] = 0; t.w[j] = 0.f; }
+    for (int is = 0; is < sr; ++is) {
+        float v = __fadd_rn(__fadd_rn(start, __fmul_rn((float)p, bin)), __fdiv_rn(__fmul_rn((float)is + 0.5f, bin), (float)sr));
+        if (v < -1.f || v > (float)size || !(v == v)) continue;
+        if (v <= 0.f) v = 0.f;
+        int lo = (int)v, hi;
+        if (lo >= size - 1) { hi = lo = size - 1; v = (float)lo; } else hi = lo + 1;
+        const float l = __fsub_rn(v, (float)lo), h = __fsub_rn(1.f, l);
+        const int idx[2] = {lo, hi};
+        const float wt[2] = {h, l};
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            bool merged = false;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (!merged && j < t.n && t.i[j] == idx[e]) { t.w[j] = __fadd_rn(t.w[j], wt[e]); merged = true; }
+            if (!merged) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (j == t.n) { t.i[j] = idx[e]; t.w[j] = wt[e]; }
+                t.n += 1;
+            }
+        }
+    }
+    return t;
+}
+
+// one output row, 4 columns of one channel, taps straight from global memory (rare slow path)
+__device__ __noinline__ float4 k3_row_direct(const uint8_t* base, int row_stride, int4 yi, float4 yw, int yn, float x1,
+                                             float bin_w, int pw0, int sr, int W, int sc) {
+    float accv[4] = {0.f, 0.f, 0.f, 0.f};
+    const int ia[4] = {yi.x, yi.y, yi.z, yi.w};
+    const float wa[4] = {yw.x, yw.y, yw.z, yw.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const K3Taps te = k3_taps(x1, bin_w, pw0 + e, sr, W);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (j >= yn) continue;
+            const uint8_t* rowg = base + (long long)ia[j] * row_stride;
+            float hsum = 0.f;
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj)
+                if (jj < te.n) hsum = __fmaf_rn(te.w[jj], (float)__ldg(rowg + 3 * te.i[jj] + sc), hsum);
+            accv[e] = __fmaf_rn(wa[j], hsum, accv[e]);
+        }
+    }
+    return make_float4(accv[0], accv[1], accv[2], accv[3]);
+}
+
+template <typename OutT>
+__global__ void __launch_bounds__(K3T_THREADS)
+k3_roi_tma(const uint8_t* __restrict__ imgs, int n, int H, int W, long long img_stride, int row_stride,
+           const float* __restrict__ rois, int K, int PH, int PW, int sr, int aligned, int swap_rb,
+           const float* __restrict__ norm, OutT* __restrict__ dst, int tma_ok) {
+    extern __shared__ __align__(128) unsigned char k3t_sm[];
+    float* Hs = reinterpret_cast<float*>(k3t_sm);                                  // [K3T_ROWS][3][PW]
+    uint8_t* raw = k3t_sm + (((size_t)K3T_ROWS * 3 * PW * 4 + 127) & ~(size_t)127);   // [K3T_RAW]
+    __shared__ int4 s_yi[K3T_PH_MAX];
+    __shared__ float4 s_yw[K3T_PH_MAX];
+    __shared__ short s_ylo[K3T_PH_MAX], s_yhi[K3T_PH_MAX], s_yn[K3T_PH_MAX];
+    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ int s_xr[2];
+    const int tid = threadIdx.x;
+    const int total = PH * PW;
+    float nd[3], nm[3], ns[3], ri[3], rs[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { nd[c] = norm[c * 3 + 0]; nm[c] = norm[c * 3 + 1]; ns[c] = norm[c * 3 + 2]; }
+    const float count = (float)(sr * sr);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { ri[c] = __fdiv_rn(__fdiv_rn(1.f, count), nd[c]); rs[c] = __fdiv_rn(1.f, ns[c]); }
+    // out = ((acc/count)/div - mean)/std with reciprocal multiplies; where q - mean cancels (|d| < 2^-14, ~0.01 % of
+    // the values) the exact divisions are replayed (see k3_roi_sep)
+    auto finish = [&](float acc, int c) -> float {
+        float d = __fsub_rn(__fmul_rn(acc, ri[c]), nm[c]);
+        if (fabsf(d) < 6.103515625e-5f) d = __fsub_rn(__fdiv_rn(__fdiv_rn(acc, count), nd[c]), nm[c]);
+        return __fmul_rn(d, rs[c]);
+    };
+    if (tid == 0) { qc_mbar_init(&s_bar, 1); qc_fence_mbar_init(); }
+    unsigned parity = 0;
+    __syncthreads();
+
+    for (int k = blockIdx.x; k < K; k += gridDim.x) {
+        const float* r = rois + (long long)k * 5;
+        const int img = (int)r[0];
+        const float offset = aligned ? 0.5f : 0.f;
+        const float x1 = __fsub_rn(r[1], offset), y1 = __fsub_rn(r[2], offset);
+        const float x2 = __fsub_rn(r[3], offset), y2 = __fsub_rn(r[4], offset);
+        float roi_w = __fsub_rn(x2, x1), roi_h = __fsub_rn(y2, y1);
+        if (!aligned) { roi_w = fmaxf(roi_w, 1.f); roi_h = fmaxf(roi_h, 1.f); }
+        const float bin_h = __fdiv_rn(roi_h, (float)PH), bin_w = __fdiv_rn(roi_w, (float)PW);
+        const bool img_ok = img >= 0 && img < n;
+        const uint8_t* base = imgs + (long long)(img_ok ? img : 0) * img_stride;
+        OutT* dk = dst + (long long)k * 3 * total;
+        const bool geom_ok = img_ok && bin_h >= 0.f && bin_w >= 0.f;
+        __syncthreads();                                    // previous ROI is done with every shared table
+        // ---- per-ROI tables ---------------------------------------------------------------------------------
+        K3Taps tx;
+        tx.n = 0;
+        if (tid < PW) tx = k3_taps(x1, bin_w, tid, sr, W);
+        if (tid == 0) { s_xr[0] = INT_MAX; s_xr[1] = -1; }
+        for (int ph = tid; ph < PH; ph += K3T_THREADS) {
+            const K3Taps ty = k3_taps(y1, bin_h, ph, sr, H);
+            s_yi[ph] = make_int4(ty.i[0], ty.i[1], ty.i[2], ty.i[3]);
+            s_yw[ph] = make_float4(ty.w[0], ty.w[1], ty.w[2], ty.w[3]);
+            int lo = INT_MAX, hi = -1;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (j < ty.n) { lo = min(lo, ty.i[j]); hi = max(hi, ty.i[j]); }
+            s_ylo[ph] = (short)(ty.n ? lo : 0); s_yhi[ph] = (short)(ty.n ? hi : 0); s_yn[ph] = (short)ty.n;
+        }
+        __syncthreads();
+        if (tid < PW && tx.n) {
+            int lo = tx.i[0], hi = tx.i[0];
+#pragma unroll
+            for (int j = 1; j < 4; ++j)
+                if (j < tx.n) { lo = min(lo, tx.i[j]); hi = max(hi, tx.i[j]); }
+            atomicMin(&s_xr[0], lo);
+            atomicMax(&s_xr[1], hi);
+        }
+        __syncthreads();
+        const int x_lo = s_xr[0], x_hi = s_xr[1];
+        // byte window of a source row: 16-byte aligned superset of [3*x_lo, 3*x_hi + 3)
+        int b0 = 0, pitch = 16;
+        bool direct = !geom_ok || x_hi < 0 || H > 32767;
+        if (!direct) {
+            b0 = (3 * x_lo) & ~15;
+            pitch = ((3 * (x_hi + 1) + 15) & ~15) - b0;       // TMA: pitch % 16 == 0 keeps the window inside row_stride
+            if (pitch * 2 > K3T_RAW) direct = true;
+        }
+        if (direct) {
+            // inverted / oversized boxes: the direct form (torchvision's loop order), rare
+            for (int o = tid; o < total; o += K3T_THREADS) {
+                const int ph = o / PW, pw = o - ph * PW;
+                float acc[3] = {0.f, 0.f, 0.f};
+                if (img_ok) {
+                    for (int iy = 0; iy < sr; ++iy) {
+                        const float yy = __fadd_rn(__fadd_rn(y1, __fmul_rn((float)ph, bin_h)), __fdiv_rn(__fmul_rn((float)iy + 0.5f, bin_h), (float)sr));
+                        for (int ix = 0; ix < sr; ++ix) {
+                            const float xx = __fadd_rn(__fadd_rn(x1, __fmul_rn((float)pw, bin_w)), __fdiv_rn(__fmul_rn((float)ix + 0.5f, bin_w), (float)sr));
+                            float y = yy, x = xx;
+                            if (y < -1.f || y > (float)H || x < -1.f || x > (float)W) continue;
+                            if (y <= 0.f) y = 0.f;
+                            if (x <= 0.f) x = 0.f;
+                            int yl = (int)y, xl = (int)x, yh, xh;
+                            if (yl >= H - 1) { yh = yl = H - 1; y = (float)yl; } else yh = yl + 1;
+                            if (xl >= W - 1) { xh = xl = W - 1; x = (float)xl; } else xh = xl + 1;
+                            const float ly = __fsub_rn(y, (float)yl), lx = __fsub_rn(x, (float)xl);
+                            const float hy = __fsub_rn(1.f, ly), hx = __fsub_rn(1.f, lx);
+                            const float w1 = __fmul_rn(hy, hx), w2 = __fmul_rn(hy, lx), w3 = __fmul_rn(ly, hx), w4 = __fmul_rn(ly, lx);
+#pragma unroll
+                            for (int c = 0; c < 3; ++c) {
+                                const int sc = swap_rb ? 2 - c : c;
+                                float v = __fmul_rn(w1, (float)__ldg(base + (long long)yl * row_stride + xl * 3 + sc));
+                                v = __fadd_rn(v, __fmul_rn(w2, (float)__ldg(base + (long long)yl * row_stride + xh * 3 + sc)));
+                                v = __fadd_rn(v, __fmul_rn(w3, (float)__ldg(base + (long long)yh * row_stride + xl * 3 + sc)));
+                                v = __fadd_rn(v, __fmul_rn(w4, (float)__ldg(base + (long long)yh * row_stride + xh * 3 + sc)));
+                                acc[c] = __fadd_rn(acc[c], v);
+                            }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const float v = __fdiv_rn(__fsub_rn(__fdiv_rn(__fdiv_rn(acc[c], count), nd[c]), nm[c]), ns[c]);
+                    OutT* q = dk + (long long)c * total + o;
+                    if (sizeof(OutT) == 2) *reinterpret_cast<uint16_t*>(q) = qc_f2bf(v);
+                    else *reinterpret_cast<float*>(q) = v;
+                }
+            }
+            continue;
+        }
+        const int rows_cap = min(K3T_ROWS, K3T_RAW / pitch);
+        // band [pa, pb): output rows whose source rows r_lo .. r_hi fit (rows without valid samples cost nothing)
+        auto band_end = [&](int pa, int& r_lo, int& r_hi) -> int {
+            r_lo = INT_MAX; r_hi = -1;
+            int pb = pa;
+            while (pb < PH) {
+                int lo = r_lo, hi = r_hi;
+                if (s_yn[pb]) { lo = min(lo, (int)s_ylo[pb]); hi = max(hi, (int)s_yhi[pb]); }
+                if (hi >= 0 && hi - lo + 1 > rows_cap) break;
+                r_lo = lo; r_hi = hi;
+                ++pb;
+            }
+            return pb;
+        };
+        const bool use_tma = tma_ok != 0;
+        auto stage = [&](int r_lo, int r_hi) {               // rows r_lo..r_hi -> raw[rr * pitch + (byte - b0)]
+            if (r_hi < 0) return;
+            const int nrows = r_hi - r_lo + 1;
+            if (use_tma) {
+                if (tid == 0) {
+                    qc_mbar_expect_tx(&s_bar, (uint32_t)(nrows * pitch));
+                    for (int rr = 0; rr < nrows; ++rr)
+                        qc_bulk_g2s(raw + rr * pitch, base + (long long)(r_lo + rr) * row_stride + b0, (uint32_t)pitch, &s_bar);
+                }
+            } else {
+                const int valid = min(pitch, 3 * W - b0);             // never read past the row's pixels
+                for (int i = tid; i < nrows * pitch; i += K3T_THREADS) {
+                    const int rr = i / pitch, j = i - rr * pitch;
+                    raw[i] = j < valid ? __ldg(base + (long long)(r_lo + rr) * row_stride + b0 + j) : (uint8_t)0;
+                }
+            }
+        };
+        int pa = 0, r_lo, r_hi;
+        int pb = band_end(pa, r_lo, r_hi);
+        if (pb == pa) {
+            // a single output row needs more source rows than a band holds (extreme down-scaling): not this kernel's
+            // case -- the host only routes sr <= 2, and rows_cap >= 2 holds lo/hi of one sample; two far-apart samples
+            // of one row are handled by widening the band to exactly that row through the generic tap loop below
+            pb = pa + 1; r_lo = s_ylo[pa]; r_hi = s_yhi[pa];
+        }
+        if (r_hi < 0 || r_hi - r_lo + 1 <= rows_cap) stage(r_lo, r_hi);
+        while (pa < PH) {
+            const int nrows = r_hi >= 0 ? r_hi - r_lo + 1 : 0;
+            const bool fits = nrows <= rows_cap;
+            if (nrows && fits) {
+                if (use_tma) { qc_mbar_wait(&s_bar, parity); parity ^= 1u; }
+                else __syncthreads();
+                // (1) horizontal pass: thread = output column
+                if (tid < PW) {
+                    for (int rr = 0; rr < nrows; ++rr) {
+                        const uint8_t* rowp = raw + rr * pitch - b0;
+                        float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            if (j < tx.n) {
+                                const uint8_t* px = rowp + 3 * tx.i[j];
+                                a0 = __fmaf_rn(tx.w[j], (float)px[0], a0);
+                                a1 = __fmaf_rn(tx.w[j], (float)px[1], a1);
+                                a2 = __fmaf_rn(tx.w[j], (float)px[2], a2);
+                            }
+                        }
+                        float* hrow = Hs + (size_t)rr * 3 * PW;
+                        hrow[(swap_rb ? 2 : 0) * PW + tid] = a0;
+                        hrow[PW + tid] = a1;
+                        hrow[(swap_rb ? 0 : 2) * PW + tid] = a2;
+                    }
+                }
+            }
+            __syncthreads();                                 // Hs complete, raw consumed
+            // next band: its rows stream in while this band's vertical pass runs
+            const int npa = pb;
+            int nr_lo = 0, nr_hi = -1, npb = npa;
+            if (npa < PH) {
+                npb = band_end(npa, nr_lo, nr_hi);
+                if (npb == npa) { npb = npa + 1; nr_lo = s_ylo[npa]; nr_hi = s_yhi[npa]; }
+                if (nr_hi < 0 || nr_hi - nr_lo + 1 <= rows_cap) stage(nr_lo, nr_hi);
+            }
+            // (2) vertical pass
+            const int quads = PW >> 2;
+            const int nsl = K3T_THREADS / quads;             // row slices
+            const int q = tid % quads, sl = tid / quads;
+            if (sl < nsl) {
+                const int nb = pb - pa;
+                const int per = (nb + nsl - 1) / nsl;
+                const int pe = min(pa + (sl + 1) * per, pb);
+                for (int ph = pa + sl * per; ph < pe; ++ph) {
+                    const int4 yi = s_yi[ph];
+                    const float4 yw = s_yw[ph];
+                    const int yn = fits ? s_yn[ph] : 0;
+                    const int ia[4] = {yi.x, yi.y, yi.z, yi.w};
+                    const float wa[4] = {yw.x, yw.y, yw.z, yw.w};
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            if (j < yn) {
+                                const float4 a = *reinterpret_cast<const float4*>(Hs + ((size_t)(ia[j] - r_lo) * 3 + c) * PW + 4 * q);
+                                acc.x = __fmaf_rn(wa[j], a.x, acc.x); acc.y = __fmaf_rn(wa[j], a.y, acc.y);
+                                acc.z = __fmaf_rn(wa[j], a.z, acc.z); acc.w = __fmaf_rn(wa[j], a.w, acc.w);
+                            }
+                        }
+                        if (!fits)   // the row's samples are further apart than a band holds (extreme down-scaling)
+                            acc = k3_row_direct(base, row_stride, yi, yw, s_yn[ph], x1, bin_w, 4 * q, sr, W, swap_rb ? 2 - c : c);
+                        const float v0 = finish(acc.x, c), v1 = finish(acc.y, c), v2 = finish(acc.z, c), v3 = finish(acc.w, c);
+                        OutT* q4 = dk + (long long)c * total + ph * PW + 4 * q;
+                        if (sizeof(OutT) == 2) {
+                            const __nv_bfloat162 p0 = __floats2bfloat162_rn(v0, v1), p1 = __floats2bfloat162_rn(v2, v3);
+                            *reinterpret_cast<uint2*>(q4) = make_uint2(*reinterpret_cast<const unsigned*>(&p0),
+                                                                       *reinterpret_cast<const unsigned*>(&p1));
+                        } else {
+                            *reinterpret_cast<float4*>(q4) = make_float4(v0, v1, v2, v3);
+                        }
+                    }
+                }
+            }
+            __syncthreads();                                 // Hs free for the next band
+            pa = npa; pb = npb; r_lo = nr_lo; r_hi = nr_hi;
+        }
+    }
+}
+
 }  // namespace
 
 extern "C" int qc_roi_align(qc_ctx* ctx, const uint8_t* imgs, int n, int h, int w, int64_t img_stride,
@@ -353,6 +674,30 @@ extern "C" int qc_roi_align(qc_ctx* ctx, const uint8_t* imgs, int n, int h, int 
     if (K > 65535) QC_FAIL(ctx, QC_ERR_UNSUPPORTED, "qc_roi_align: K > 65535 (split the call)");
     cudaStream_t st = (cudaStream_t)stream;
     const int total = out_h * out_w;
+    if (sampling_ratio >= 1 && sampling_ratio <= 2 && (out_w & 3) == 0 && out_w <= K3T_THREADS && out_h <= K3T_PH_MAX &&
+        K3T_THREADS / (out_w >> 2) >= 1 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0 && h <= 32767) {
+        const size_t smem = (((size_t)K3T_ROWS * 3 * out_w * 4 + 127) & ~(size_t)127) + K3T_RAW;
+        // 1-D TMA bulk copies need 16-byte aligned global addresses: frame base, image pitch and row pitch
+        const int tma_ok = ((reinterpret_cast<uintptr_t>(imgs) & 15) == 0 && (img_stride & 15) == 0 && (row_stride & 15) == 0) ? 1 : 0;
+        int occ = 1;
+        const int grid = std::min(K, ctx->sm_count * 8);
+        if (out_dtype == QC_DT_BF16) {
+            if (int rc = qc_prepare(ctx, k3_roi_tma<__nv_bfloat16>, (int)smem, K3T_THREADS, &occ)) return rc;
+            k3_roi_tma<__nv_bfloat16><<<std::min(K, ctx->sm_count * std::max(occ, 1)), K3T_THREADS, smem, st>>>(
+                imgs, n, h, w, img_stride, row_stride, rois, K, out_h, out_w, sampling_ratio, aligned, swap_rb, norm,
+                (__nv_bfloat16*)dst, tma_ok);
+        } else if (out_dtype == QC_DT_F32) {
+            if (int rc = qc_prepare(ctx, k3_roi_tma<float>, (int)smem, K3T_THREADS, &occ)) return rc;
+            k3_roi_tma<float><<<std::min(K, ctx->sm_count * std::max(occ, 1)), K3T_THREADS, smem, st>>>(
+                imgs, n, h, w, img_stride, row_stride, rois, K, out_h, out_w, sampling_ratio, aligned, swap_rb, norm,
+                (float*)dst, tma_ok);
+        } else {
+            QC_FAIL(ctx, QC_ERR_INVALID, "qc_roi_align: bad out_dtype");
+        }
+        (void)grid;
+        QC_LAUNCHED(ctx);
+        return QC_OK;
+    }
     if (sampling_ratio >= 1 && sampling_ratio <= K3_SR_MAX) {
         // rows one 8-row band can touch for boxes inside the frame (+ slack); larger bands fall back in-kernel
         long long rows_max = 12;       // source rows per sub-band (bands needing more are split in-kernel)

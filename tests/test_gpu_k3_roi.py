@@ -54,3 +54,67 @@ def test_roi_align_empty(qc):
     imgs = torch.zeros((1, 32, 32, 3), dtype=torch.uint8).cuda()
     out = qc.roi_align(imgs, torch.zeros((0, 5), dtype=torch.float32).cuda())
     assert out.shape == (0, 3, 224, 224)
+
+
+def _check(qc, imgs_t, imgs_np, rois, **kw):
+    ref = oroi.roi_align_normalize(imgs_np, rois, **kw)
+    out = qc.roi_align(imgs_t, torch.from_numpy(rois).cuda(), out_dtype=torch.float32, **kw)
+    d = (out.cpu() - ref).abs()
+    assert d.max() <= 1e-3, f"max diff {d.max()} at roi {int(d.flatten(1).max(1).values.argmax())}"
+    out16 = qc.roi_align(imgs_t, torch.from_numpy(rois).cuda(), **kw)
+    # bf16: within 1 ulp of the RNE-rounded reference.  Where (v/255 - mean)/std cancels to |v| < 2^-10 a bf16 ulp
+    # (< 8e-6) is finer than float32 accumulation-order noise (~3e-7 absolute); there the absolute bar applies, 16x
+    # tighter than the float32 one.  Such elements are counted and must stay below 1e-5 of the outputs.
+    def key(t_):
+        i = t_.detach().cpu().contiguous().view(torch.int16).to(torch.int32) & 0xFFFF
+        return torch.where(i >= 0x8000, 0x8000 - i, i)
+    r16 = ref.to(torch.bfloat16)
+    far = (key(out16) - key(r16)).abs() > 1
+    if far.any():
+        assert (ref[far].abs() < 2 ** -10).all() and (out16.cpu().float()[far] - ref[far]).abs().max() <= 2 ** -14
+        assert int(far.sum()) <= 1e-5 * far.numel() + 2, int(far.sum())
+
+
+def test_roi_align_staged_path_geometries(qc):
+    """The TMA-staged kernel (sr <= 2, 224x224): up- and down-scaling, 1-2 pixel boxes, boxes on every frame border,
+    boxes partly / fully outside the frame, fractional and inverted boxes, sampling_ratio 1."""
+    from qcgraft import synth
+    rng = np.random.default_rng(23)
+    imgs = synth.make_frames(41, 4)
+    t = torch.from_numpy(imgs).cuda()
+    rois = _rois(rng, 4, 640, 640, 300)
+    extra = np.array([[0, 0, 0, 640, 640], [1, 0, 0, 2, 2], [2, 638, 638, 640, 640], [3, 0, 300, 640, 301],
+                      [0, 320, 0, 321, 640], [1, -20, -30, 50, 60], [2, 600, 610, 700, 720], [3, 700, 700, 800, 800],
+                      [0, 50.3, 60.7, 51.1, 300.2], [1, 400, 400, 380, 390], [2, 10, 10, 10, 10], [3, 5, 5, 600, 9],
+                      [0, -100, -100, -50, -50], [1, 0.5, 0.5, 639.5, 639.5]], np.float32)
+    rois = np.concatenate((extra, rois))
+    _check(qc, t, imgs, rois)
+    _check(qc, t, imgs, rois[:40], sampling_ratio=1)
+    _check(qc, t, imgs, rois[:40], swap_rb=True)
+
+
+def test_roi_align_unaligned_pitch_and_odd_width(qc):
+    """Frames whose row pitch is not a multiple of 16 bytes (333 px) and pitched views: the plain-load staging path."""
+    rng = np.random.default_rng(24)
+    imgs = rng.integers(0, 256, (2, 250, 333, 3), dtype=np.uint8)
+    rois = _rois(rng, 2, 250, 333, 60)
+    rois[0] = [0, 0, 0, 333, 250]
+    rois[1] = [1, 300, 200, 333, 250]
+    _check(qc, torch.from_numpy(imgs).cuda(), imgs, rois)
+    big = rng.integers(0, 256, (2, 300, 400, 3), dtype=np.uint8)
+    view = torch.from_numpy(big).cuda()[:, 20:270, 30:363]           # pitched, 90-byte offset: unaligned base
+    sub = np.ascontiguousarray(big[:, 20:270, 30:363])
+    _check(qc, view, sub, rois)
+
+
+def test_roi_align_large_frames(qc):
+    """2048x2048 frames: whole-frame ROI (rows wider than the staging buffer holds for a band -> per-row slow path),
+    tall and wide strips, many small boxes."""
+    rng = np.random.default_rng(25)
+    imgs = rng.integers(0, 256, (1, 2048, 2048, 3), dtype=np.uint8)
+    rois = _rois(rng, 1, 2048, 2048, 40)
+    rois[0] = [0, 0, 0, 2048, 2048]
+    rois[1] = [0, 100, 0, 140, 2048]
+    rois[2] = [0, 0, 1000, 2048, 1040]
+    rois[3] = [0, 5, 5, 1500, 1800]
+    _check(qc, torch.from_numpy(imgs).cuda(), imgs, rois)
