@@ -1,27 +1,35 @@
 #!/usr/bin/env python
 """bench.py -- end-to-end images/sec of the inspection hot path at 640^2 (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl graft|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl graft|reference] [--config cfg1|cfg2|cfg5]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
         --master-port P bench.py --gpus N --steps K --warmup W
 
-Workload (BASELINE.json configs[1], "cfg2"): YOLOv8s + ResNet-50, 64 synthetic 640x640 RGB frames
-per GPU per step; a step = K1 preprocess -> YOLOv8s -> K2 decode+NMS -> K3b PIL-exact whole-frame resize +
-K3 ROI-align of every kept box -> ResNet-50 on both -> K4 segmentation of every kept ROI -> K5 SPC vector
-(+ NCCL all-reduce of that 72-byte vector when N > 1).  Detections come from injected head logits
-(random-init Detect heads fire nothing).  Weak scaling: every rank processes its own
-64 frames per step, no data-path collective.
+Workloads (BASELINE.json configs):
+  cfg2 (default at N=1)  YOLOv8s + ResNet-50, 64 synthetic 640x640 RGB frames per GPU per step
+  cfg5 (default at N>1)  the same per-frame work, 256 frames per GPU per step (camera-stream sharding, 8 x 256 at N=8)
+  cfg1                   YOLOv8n + ResNet-50, ONE frame: latency of QualityControlDetector.predict (median / p95)
+A step = K1 preprocess -> YOLOv8 -> K2 decode+NMS -> K3b PIL-exact whole-frame resize + K3 ROI-align of every kept box
+-> ResNet-50 on both -> K7 per-class segmentation of every kept ROI (the reference's threshold / adaptive methods) ->
+K5 SPC vector (+ NCCL all-reduce of that 72-byte vector when N > 1).  Detections come from injected head logits
+(random-init Detect heads fire nothing).  Weak scaling: every rank processes its own frames, no
+data-path collective.
 
 One JSON line on stdout (rank 0):
-  value     images/s with the step's frames already resident in HBM (3 rotating batches = 236 MB,
-            larger than L2) -- CUDA events per step, max over ranks
-  e2e       images/s through the same public call with HOST (pinned) frames: the H2D copy of the
-            step's frames and the D2H reads of its results are inside the timed region
-  roofline  the dominant hand-written kernel of the step (K1: most bytes), algorithmic bytes /
-            its CUDA-event duration measured in the timed region, vs MEASURED_PEAKS.json
-  kernels   per-kernel achieved GB/s on their own BASELINE configs (K1 cfg2, K2 cfg3, K3, K3b, K4 cfg4),
-            measured after the timed region with L2-defeating rotation
-  cpu_baseline  the oracle port of the reference CPU path on the host cores (bounded sample)
+  value        images/s with the step's frames already resident in HBM (3 rotating batches, larger than L2) -- CUDA
+               events per step, max over ranks
+  e2e          images/s through the same public call with HOST (pinned) frames: the H2D copy of the step's frames and
+               the D2H reads of its results are inside the timed region
+  roofline     the DOMINANT hand-written operator of the step (largest share of own-kernel time, from CUDA events in
+               the timed region): algorithmic bytes of that call, computed from the step's actual ROI table, over its
+               measured duration, vs MEASURED_PEAKS.json; `operators` lists every C-ABI call of the step the same way
+  stage_split  GPU and CPU milliseconds per image and stage (pre | nets | decode_nms | roi | seg | rules) and
+               `prepost_ratio` = CPU / GPU over everything but the conv nets
+  kernels      per-kernel achieved GB/s on their own BASELINE configs (K1 cfg2, K2 cfg3, K3, K3b, K4 cfg4, K7),
+               measured after the timed region with L2-defeating rotation
+  cfg1_latency batch-1 latency of QualityControlDetector.predict (N=1 only)
+  cpu_baseline the oracle port of the reference CPU path on the host cores (bounded sample): the reference's work
+               (mock ROI classification, models/ensemble.py:181-195); `same_work_cpu` = with a real ResNet-50 pass per ROI
 --impl reference times only that CPU path (rank 0; other ranks exit).
 """
 from __future__ import annotations
@@ -48,8 +56,16 @@ BATCH = 64
 IMGSZ = 640
 CANDS_PER_IMAGE = 30
 NC = 5
-WORKLOAD = ("cfg2: YOLOv8s + ResNet-50, 64 synthetic 640x640 RGB frames per GPU per step, "
-            "~30 injected candidates/image, K1->YOLOv8s->K2->K3b+K3->ResNet-50->K4->K5")
+CONFIGS = {
+    "cfg1": dict(batch=1, yolo="n", name="cfg1: YOLOv8n + ResNet-50, one synthetic 640x640 RGB frame, batch=1, through "
+                                         "QualityControlDetector.predict"),
+    "cfg2": dict(batch=64, yolo="s", name="cfg2: YOLOv8s + ResNet-50, 64 synthetic 640x640 RGB frames per GPU per step, "
+                                          "~30 injected candidates/image, K1->YOLOv8s->K2->K3b+K3->ResNet-50->K7->K5"),
+    "cfg5": dict(batch=256, yolo="s", name="cfg5: camera-stream sharding, 256 synthetic 640x640 RGB frames per GPU per step "
+                                           "(8 x 256 at N=8), YOLOv8s + ResNet-50, K1->YOLOv8s->K2->K3b+K3->ResNet-50->K7->K5, "
+                                           "NCCL SPC-stats all-reduce"),
+}
+WORKLOAD = CONFIGS["cfg2"]["name"]
 
 
 def measured_peaks():
@@ -109,33 +125,40 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def build_cpu_pipeline(seed=0):
+def build_cpu_pipeline(seed=0, scale="s", classify_rois=False):
     from qcgraft import nets
+    from qcgraft.rules import DetectionRules
     from oracle.pipeline import CpuReferencePipeline
-    y = nets.build_yolo("s", NC, seed)
+    y = nets.build_yolo(scale, NC, seed)
     for seq in list(y.detect.cv2) + list(y.detect.cv3):
         seq[-1].bias.data.zero_()
-    return CpuReferencePipeline(y, nets.build_resnet50(NC, seed), nc=NC, imgsz=IMGSZ)
+    return CpuReferencePipeline(y, nets.build_resnet50(NC, seed), nc=NC, imgsz=IMGSZ, classify_rois=classify_rois,
+                                rules=DetectionRules({}))
 
 
-def cpu_reference_rate(n_images: int, warm: int = 1, seed0: int = 0):
-    """Sequential per-image loop, images_per_second = N / sum(t) (inference/detector.py:331-374)."""
+def cpu_reference_rate(n_images: int, warm: int = 1, seed0: int = 0, scale="s", classify_rois=False):
+    """Sequential per-image loop, images_per_second = N / sum(t) (inference/detector.py:331-374).  Returns
+    (images/s, per-image seconds, per-stage seconds per image)."""
     from qcgraft import synth
-    cp = build_cpu_pipeline()
+    cp = build_cpu_pipeline(scale=scale, classify_rois=classify_rois)
     imgs = synth.make_frames(seed0, n_images + warm)
     inj = synth.make_head(1000 + seed0, n_images + warm, IMGSZ, IMGSZ, CANDS_PER_IMAGE)
     times = []
     for k in range(n_images + warm):
+        if k == warm:
+            cp.stage_s = {kk: 0.0 for kk in cp.stage_s}
         t = time.time()
         cp.predict(imgs[k], inject=[l[k:k + 1] for l in inj])
         if k >= warm:
             times.append(time.time() - t)
-    return len(times) / sum(times), times
+    stages = {k: v / max(len(times), 1) for k, v in cp.stage_s.items()}
+    return len(times) / sum(times), times, stages
 
 
 def run_reference(args, rank):
     if rank != 0:
         return
+    cfg = CONFIGS[args.config]
     per_step = 4
     # torchrun exports OMP_NUM_THREADS=1; the reference arm uses every host core it can
     try:
@@ -145,22 +168,27 @@ def run_reference(args, rank):
     torch.set_num_threads(ncpu)
     cores = torch.get_num_threads()
     for _ in range(max(args.warmup, 0) and 1):
-        cpu_reference_rate(1, warm=1)
+        cpu_reference_rate(1, warm=1, scale=cfg["yolo"])
     t0 = time.time()
-    all_t = []
-    for s in range(args.steps):
-        _, ts = cpu_reference_rate(per_step, warm=0, seed0=10 * s)
+    all_t, stages = [], {}
+    for s_ in range(args.steps):
+        _, ts, stg = cpu_reference_rate(per_step, warm=0, seed0=10 * s_, scale=cfg["yolo"])
         all_t += ts
+        for k, v in stg.items():
+            stages[k] = stages.get(k, 0.0) + v / args.steps
     total = time.time() - t0
     v = len(all_t) / sum(all_t)
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000 * sum(all_t) / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "reference_arm": "oracle port of the reference CPU path "
-                       "(pure-Python reference cannot travel to the GPU box; ultralytics/skimage absent)",
+            "config": {"workload": cfg["name"], "reference_arm": "oracle port of the reference CPU path doing the "
+                       "reference's work: sequential predict(), YOLOv8 + one whole-frame ResNet-50 pass per image, "
+                       "MOCK ROI classification (models/ensemble.py:181-195), per-class segmentation, rule engine "
+                       "(the pure-Python reference cannot travel to the GPU box; ultralytics/skimage absent)",
                        "images_per_step": per_step},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": f"{len(all_t)} frames of cfg2, sequential predict() loop, {total:.1f}s wall"},
+                             "sample": f"{len(all_t)} frames of {args.config}, sequential predict() loop, {total:.1f}s wall",
+                             "stage_ms_per_image": {k: 1000 * x for k, x in stages.items()}},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
 
@@ -194,6 +222,8 @@ def kernel_microbench(qc, peak, only=None):
         _mb_k4(qc, peak, rng, time_call, out)
     if want("k6"):
         _mb_k6(qc, peak, rng, time_call, out)
+    if want("k7"):
+        _mb_k7(qc, peak, rng, time_call, out)
     return out
 
 
@@ -302,6 +332,37 @@ def _mb_k4(qc, peak, rng, time_call, out):
                               "note": "11 launches; union-find merge/rank phases are L2 / shared-memory latency bound"}
 
 
+def _mb_k7(qc, peak, rng, time_call, out):
+    """K7: the reference's per-class segmentation methods on 1400 detection ROIs of 64 frames (~cfg2's ROI table),
+    stats-only outputs as the batched pipeline runs them."""
+    from qcgraft import ffi, synth
+    frames = torch.from_numpy(synth.make_frames(300, BATCH)).cuda()
+    K = 1400
+    w = rng.integers(16, 240, K); h = rng.integers(16, 240, K)
+    x = (rng.random(K) * (IMGSZ - w)).astype(np.int64); y = (rng.random(K) * (IMGSZ - h)).astype(np.int64)
+    img = rng.integers(0, BATCH, K)
+    px = int((w * h).sum())
+    for name, code, iters, marea in (("k7_threshold", ffi.QC_SEG_REF_THRESHOLD, 2, 10), ("k7_adaptive", ffi.QC_SEG_REF_ADAPTIVE, 1, 20)):
+        regs = dict(img=img, x=x, y=y, w=w, h=h, polarity=rng.integers(0, 2, K), thr_scale=0.8, min_area=marea)
+        if code == ffi.QC_SEG_REF_THRESHOLD:
+            regs["max_comp"] = np.full(K, 2)
+        else:
+            regs["max_comp"] = np.minimum(((w + 1) // 2) * ((h + 1) // 2) + 1, 1024)
+        call = lambda i: qc.segment(frames, regs, morph_iters=iters, swap_rb=True, want_mask=False, want_labels=False,
+                                    method=code, want_sums=(code == ffi.QC_SEG_REF_THRESHOLD))
+        call(0); call(1)
+        l0 = qc.launch_count
+        call(2)
+        launches = qc.launch_count - l0
+        med, best = time_call(call, 6)
+        by = px * 3 + K * 64                      # RGB bytes of the ROIs read once + the per-ROI result rows
+        out[f"{name}_1400rois"] = {"bytes": by, "ms": med, "gbs": by / med / 1e6, "frac": by / med / 1e6 / peak,
+                                   "roi_pixels": px, "launches": launches,
+                                   "note": "multi-pass integer / float64 work on small ROIs (blur, histogram, union-find, "
+                                           "flood fill): latency- and issue-bound, the HBM roofline is reported as asked, "
+                                           "it is not what limits these kernels"}
+
+
 _REAL_STDOUT = None
 
 
@@ -324,6 +385,36 @@ def emit(line: dict):
         os.write(1, data)
 
 
+def cfg1_latency(calls: int = 60, warm: int = 8):
+    """BASELINE cfg1: one 640x640 frame through QualityControlDetector.predict (YOLOv8n + ResNet-50), host numpy image
+    in, reference result dict out -- the reference's own timing definition (inference/detector.py:331-374)."""
+    from qcgraft import synth
+    from qcgraft.detector import QualityControlDetector
+    cfg = {"model": {"confidence_threshold": 0.7, "nms_threshold": 0.5},
+           "quality_control": {"defect_classes": ["crack", "scratch", "dent", "discoloration", "contamination"]},
+           "qcgraft": {"yolo_scale": "n", "device": torch.cuda.current_device(), "synthetic_weights": True}}
+    d = QualityControlDetector("synthetic", "synthetic", cfg)
+    d.ensemble_predictor.yolo_detector.model.zero_detect_bias()
+    imgs = [synth.make_frame(7000 + i) for i in range(8)]
+    inj = [l.cuda().to(torch.bfloat16) for l in synth.make_head(7100, 8, IMGSZ, IMGSZ, CANDS_PER_IMAGE)]
+    ts, ndet = [], 0
+    for k in range(warm + calls):
+        i = k % 8
+        t = time.perf_counter()
+        r = d.predict(imgs[i], _inject=[l[i:i + 1] for l in inj])
+        dt = time.perf_counter() - t
+        if "error" in r:
+            return {"error": r["error"]}
+        if k >= warm:
+            ts.append(dt * 1000)
+            ndet += len(r["detections"])
+    ts.sort()
+    return {"calls": len(ts), "median_ms": statistics.median(ts), "p95_ms": ts[int(0.95 * (len(ts) - 1))],
+            "min_ms": ts[0], "max_ms": ts[-1], "images_per_second": 1000 * len(ts) / sum(ts),
+            "detections_per_image_after_rules": ndet / len(ts),
+            "path": "QualityControlDetector.predict (YOLOv8n + ResNet-50, CUDA-graph nets, rule engine on)"}
+
+
 def main():
     _capture_stdout()
     ap = argparse.ArgumentParser()
@@ -331,11 +422,15 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="graft", choices=["graft", "reference"])
+    ap.add_argument("--config", default=None, choices=sorted(CONFIGS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernels", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=32)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "graft" else args.warmup
+    if args.config is None:
+        args.config = "cfg2" if max(args.gpus, 1) == 1 else "cfg5"
+    cfg = CONFIGS[args.config]
 
     from qcgraft import dist as qdist
     if args.impl == "reference":
@@ -350,20 +445,37 @@ def main():
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    pipe = InspectionPipeline("s", NC, device=local_rank, imgsz=IMGSZ)
-    pipe.zero_detect_bias()
-    qc = pipe.qc
     peak, peak_src = measured_peaks()
 
-    # ---- synthetic inputs: 3 rotating batches per rank (236 MB > 126 MB L2) --------------------
+    if args.config == "cfg1":
+        lat = cfg1_latency(max(50, args.steps * 10), max(args.warmup, 8))
+        if rank == 0:
+            line = {"metric": METRIC, "value": lat.get("images_per_second"), "unit": UNIT, "n_gpus": 1,
+                    "steps": lat.get("calls"), "warmup": max(args.warmup, 8),
+                    "ms_per_step": lat.get("median_ms"), "higher_is_better": True, "scaling": "weak",
+                    "vs_baseline": None, "dtype": "bf16 nets / u8+i32+f32+f64 kernels", "data": "synthetic",
+                    "config": {"workload": cfg["name"], "l2": "8 rotating host frames, each uploaded inside predict()"},
+                    "e2e": {"value": lat.get("images_per_second"), "unit": UNIT,
+                            "h2d_bytes_per_step": IMGSZ * IMGSZ * 3, "d2h_bytes_per_step": None},
+                    "cfg1_latency": lat}
+            emit(line)
+        qdist.shutdown()
+        return
+
+    B = cfg["batch"]
+    pipe = InspectionPipeline(cfg["yolo"], NC, device=local_rank, imgsz=IMGSZ)
+    pipe.zero_detect_bias()
+    qc = pipe.qc
+
+    # ---- synthetic inputs: 3 rotating batches per rank (>= 236 MB > 126 MB L2) ------------------
     NB = 3
     host, devb, inj = [], [], []
     for b in range(NB):
-        seed = (rank * NB + b) * BATCH
-        fr = torch.from_numpy(synth.make_frames(seed, BATCH)).pin_memory()
+        seed = (rank * NB + b) * B
+        fr = torch.from_numpy(synth.make_frames(seed, B)).pin_memory()
         host.append(fr)
         devb.append(fr.to(dev))
-        lv = synth.make_head(5000 + seed, BATCH, IMGSZ, IMGSZ, CANDS_PER_IMAGE)
+        lv = synth.make_head(5000 + seed, B, IMGSZ, IMGSZ, CANDS_PER_IMAGE)
         inj.append([l.to(dev, torch.bfloat16) for l in lv])
     spc_total = torch.zeros(9, dtype=torch.float64, device=dev)
 
@@ -379,25 +491,19 @@ def main():
         spc_total.add_(v)
         return r
 
-    def step_resident(i, last=False):
-        h = pipe.run_async(devb[i % NB], inject=inj[i % NB])
-        prev, pending[0] = pending[0], h
-        r = finish(prev) if prev is not None else None
-        if last:
-            r = finish(h)
-            pending[0] = None
-        return r
-
-    def step_e2e(i, last=False):
-        # pinned HOST frames straight into the public call: the pipeline uploads them on its copy stream (H2D of
-        # this step's frames overlaps the previous step's compute) -- the copy is inside the timed region
-        h = pipe.run_async(host[i % NB], inject=inj[i % NB])
-        prev, pending[0] = pending[0], h
-        r = finish(prev) if prev is not None else None
-        if last:
-            r = finish(h)
-            pending[0] = None
-        return r
+    def make_step(src):
+        def step(i, last=False):
+            # resident: frames already in HBM; e2e: pinned HOST frames straight into the public call -- the pipeline
+            # uploads them on its copy stream (H2D of this step's frames overlaps the previous step's compute)
+            h = pipe.run_async(src[i % NB], inject=inj[i % NB])
+            prev, pending[0] = pending[0], h
+            r = finish(prev) if prev is not None else None
+            if last:
+                r = finish(h)
+                pending[0] = None
+            return r
+        return step
+    step_resident, step_e2e = make_step(devb), make_step(host)
 
     def timed(fn, steps, record=False):
         qdist.barrier(); torch.cuda.synchronize()
@@ -426,14 +532,16 @@ def main():
     if rank == 0:
         sampler.start()
     tot_ms, wall_ms, launches, last = timed(step_resident, args.steps, record=True)
-    stage_ms = pipe.stage_ms()
+    # per-STEP milliseconds of every stage (sum of its calls / steps)
+    stage_ms = {k: float(sum(s.elapsed_time(e) for s, e in v)) / args.steps for k, v in pipe.events.items() if v}
+    stage_calls = {k: len(v) / args.steps for k, v in pipe.events.items() if v}
     crops = getattr(pipe, "last_num_crops", 0)
     for i in range(args.warmup):
         step_e2e(i, last=(i == args.warmup - 1))
     e2e_ms, e2e_wall_ms, _, last_e2e = timed(step_e2e, args.steps)
     clocks = sampler.stop() if rank == 0 else None
 
-    imgs_total = world * BATCH * args.steps
+    imgs_total = world * B * args.steps
     # events bracket every step on the launching stream; host-side gaps between steps are inside the
     # bracket of the next step only if the GPU is busy, so use the wall clock when it is larger
     value = imgs_total / (max(tot_ms, wall_ms) / 1000)
@@ -443,46 +551,104 @@ def main():
         qdist.shutdown()
         return
 
-    k1_bytes = BATCH * (IMGSZ * IMGSZ * 3 + 3 * IMGSZ * IMGSZ * 2)
-    k1_ms = stage_ms.get("k1_preprocess")
-    roofline = {"bound": "hbm", "kernel": "k1_pack_stream (K1 preprocess, most bytes of the step)",
-                "achieved": k1_bytes / k1_ms / 1e6 if k1_ms else None, "peak": peak, "unit": "GB/s",
-                "frac": (k1_bytes / k1_ms / 1e6 / peak) if k1_ms else None,
-                # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full
-                # (profiles/r01_f_ncu_full_summary.md: 78.66 MB read + 102.12 MB written inside the kernel)
-                "traffic": 180780032,
-                "peak_source": peak_src, "algorithmic_bytes_per_launch": k1_bytes,
-                "ms_per_launch": k1_ms}
+    # ---- operators of the step: algorithmic bytes from the step's own tables -------------------------------------
+    # (every rotating batch carries the same number of candidates; the last step's ROI table stands for the step)
+    roi_px = (last.roi_box[:, 2] - last.roi_box[:, 0]).astype(np.int64) * (last.roi_box[:, 3] - last.roi_box[:, 1])
+    K = len(roi_px)
+    A = sum((IMGSZ // s_) ** 2 for s_ in (8, 16, 32))
+    adaptive = last.seg_method == ffi.QC_SEG_REF_ADAPTIVE if last.seg_method is not None else np.zeros(K, bool)
+    op_bytes = {
+        "k1_preprocess": B * (IMGSZ * IMGSZ * 3 + 3 * IMGSZ * IMGSZ * 2),
+        "k2_decode_nms": B * ((64 + NC) * A * 2 + 300 * 28 + 4),                  # bf16 head in
+        "k3b_pil_resize": B * (IMGSZ * IMGSZ * 3 + 3 * 224 * 224 * 2),
+        "k3_roi_align": int(roi_px.sum()) * 3 + K * 3 * 224 * 224 * 2,
+        "k7_adaptive": int(roi_px[adaptive].sum()) * 3 + int(adaptive.sum()) * 64,
+        "k7_threshold": int(roi_px[~adaptive].sum()) * 3 + int((~adaptive).sum()) * 64,
+    }
+    operators = {}
+    for k, by in op_bytes.items():
+        ms = stage_ms.get(k)
+        if ms:
+            operators[k] = {"algorithmic_bytes_per_step": by, "ms_per_step": ms, "calls_per_step": stage_calls[k],
+                            "gbs": by / ms / 1e6, "frac": by / ms / 1e6 / peak}
+    own_total = sum(v["ms_per_step"] for v in operators.values())
+    for v in operators.values():
+        v["share_of_own_kernel_time"] = v["ms_per_step"] / own_total if own_total else None
+    dom = max(operators, key=lambda k: operators[k]["ms_per_step"]) if operators else None
+    roofline = None
+    if dom:
+        o = operators[dom]
+        roofline = {"bound": "hbm", "kernel": f"{dom} (dominant own operator: {100 * o['share_of_own_kernel_time']:.0f} % of "
+                    "own-kernel time in the step; one C-ABI call = one launch sequence)",
+                    "achieved": o["gbs"], "peak": peak, "unit": "GB/s", "frac": o["frac"], "traffic": None,
+                    "peak_source": peak_src, "algorithmic_bytes_per_launch": o["algorithmic_bytes_per_step"] / o["calls_per_step"],
+                    "ms_per_launch": o["ms_per_step"] / o["calls_per_step"],
+                    "second": {"kernel": "k1_pack_stream (K1 preprocess, the step's pure streaming kernel)",
+                               **{kk: operators["k1_preprocess"][kk] for kk in ("gbs", "frac", "ms_per_step")},
+                               # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full
+                               # (profiles/r01_f_ncu_full_summary.md)
+                               "traffic": 180780032} if "k1_preprocess" in operators else None}
+    gpu_stage = {"pre": stage_ms.get("k1_preprocess", 0) + stage_ms.get("k3b_pil_resize", 0),
+                 "nets": stage_ms.get("yolo_net", 0) + stage_ms.get("resnet_net", 0),
+                 "decode_nms": stage_ms.get("k2_decode_nms", 0), "roi": stage_ms.get("k3_roi_align", 0),
+                 "seg": stage_ms.get("k7_adaptive", 0) + stage_ms.get("k7_threshold", 0) + stage_ms.get("k4_segment", 0),
+                 "rules": 0.0}
+    stage_split = {"gpu_ms_per_image": {k: v / B for k, v in gpu_stage.items()},
+                   "note": "GPU: CUDA events around each stage in the timed region (K5 SPC reduction and the host rule "
+                           "engine of the drop-in are not in the batched step); CPU: wall time per stage of the port"}
     d2h = int(last.det.nbytes + last.count.nbytes + 72 + (last.roi_probs.nbytes if last.roi_probs is not None else 0)
               + (last.global_probs.nbytes if last.global_probs is not None else 0)
-              + (last.seg_area.nbytes + last.seg_thr.nbytes + last.seg_ncomp.nbytes if last.seg_area is not None else 0))
+              + (last.seg_area.nbytes + last.seg_thr.nbytes + last.seg_ncomp.nbytes + last.seg_sums.nbytes
+                 if last.seg_area is not None else 0))
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": max(tot_ms, wall_ms) / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "bf16 nets / u8+i32+f32 kernels", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "per_gpu_batch": BATCH, "global_batch": BATCH * world,
-                       "l2": "3 rotating resident batches per rank (236 MB > 126 MB L2)",
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16 nets / u8+i32+f32+f64 kernels", "data": "synthetic",
+            "config": {"workload": cfg["name"], "per_gpu_batch": B, "global_batch": B * world,
+                       "l2": f"3 rotating resident batches per rank ({3 * B * IMGSZ * IMGSZ * 3 // 2 ** 20} MiB > 126 MB L2)",
                        "parallelism": f"dp{world}", "detections_per_step": int(last.count.sum()),
-                       "rois_classified_per_step": crops},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": BATCH * IMGSZ * IMGSZ * 3,
+                       "rois_classified_per_step": crops, "segmentation": pipe.seg_mode,
+                       "note": "default workload: cfg2 at N=1, cfg5 (256 frames per GPU) at N>1"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * IMGSZ * IMGSZ * 3,
                     "d2h_bytes_per_step": d2h, "ms_per_step": max(e2e_ms, e2e_wall_ms) / args.steps},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
-            "stage_ms": stage_ms, "device_ms_per_step": tot_ms / args.steps,
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "operators": operators,
+            "stage_ms": stage_ms, "stage_split": stage_split, "device_ms_per_step": tot_ms / args.steps,
             "spc": {k: float(v) for k, v in zip(qdist.SPC_FIELDS, spc_total.cpu().numpy())}}
-    if not args.no_kernels:
+    if not args.no_kernels and world == 1:
         try:
             line["kernels"] = kernel_microbench(qc, peak)
         except Exception as e:   # the headline line must still be printed
             line["kernels"] = {"error": str(e)}
+    if world == 1:
+        try:
+            del devb, host, inj
+            torch.cuda.empty_cache()
+            line["cfg1_latency"] = cfg1_latency()
+        except Exception as e:
+            line["cfg1_latency"] = {"error": str(e)}
     if world == 1 and not args.no_cpu_baseline:
         try:
             torch.set_num_threads(len(os.sched_getaffinity(0)))
         except AttributeError:
             pass
         t0 = time.time()
-        v, ts = cpu_reference_rate(args.cpu_sample, warm=1)
+        v, ts, stg = cpu_reference_rate(args.cpu_sample, warm=1, scale=cfg["yolo"])
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                                "sample": f"{len(ts)} frames of cfg2 (+1 warm-up), sequential predict() loop, "
-                                          f"{time.time() - t0:.1f}s wall, host cpu_count={os.cpu_count()}"}
+                                "sample": f"{len(ts)} frames of {args.config} (+1 warm-up), sequential predict() loop doing the "
+                                          f"reference's work (mock ROI classification), {time.time() - t0:.1f}s wall, "
+                                          f"host cpu_count={os.cpu_count()}"}
+        cpu_ms = {k: 1000 * x for k, x in stg.items()}
+        stage_split["cpu_ms_per_image"] = cpu_ms
+        gpu = stage_split["gpu_ms_per_image"]
+        pp = [k for k in cpu_ms if k != "nets"]
+        g_pp = sum(gpu.get(k, 0.0) for k in pp)
+        stage_split["prepost_cpu_ms_per_image"] = sum(cpu_ms[k] for k in pp)
+        stage_split["prepost_gpu_ms_per_image"] = g_pp
+        stage_split["prepost_ratio"] = (sum(cpu_ms[k] for k in pp) / g_pp) if g_pp else None
+        t0 = time.time()
+        v2, ts2, _ = cpu_reference_rate(max(4, args.cpu_sample // 8), warm=1, scale=cfg["yolo"], classify_rois=True)
+        line["same_work_cpu"] = {"value": v2, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                                 "sample": f"{len(ts2)} frames, as cpu_baseline but with a real roi_align + ResNet-50 pass per "
+                                           f"kept box (the work the GPU pipeline does), {time.time() - t0:.1f}s wall"}
     emit(line)
     qdist.shutdown()
 

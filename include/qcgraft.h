@@ -141,6 +141,12 @@ int qc_roi_align(qc_ctx* ctx, const uint8_t* imgs, int n, int h, int w, int64_t 
                  int32_t row_stride, const float* rois, int K, int out_h, int out_w,
                  int sampling_ratio, int aligned, int swap_rb, const float* norm,
                  int out_dtype, void* dst, void* stream);
+/* Same, with a destination row per ROI: ROI k is written to dst row dst_rows[k] (device int32 [K]; NULL = k), so one
+ * launch can fill the static input buffers of several classifier graphs that sit at fixed places of one arena.     */
+int qc_roi_align_rows(qc_ctx* ctx, const uint8_t* imgs, int n, int h, int w, int64_t img_stride,
+                      int32_t row_stride, const float* rois, const int32_t* dst_rows, int K, int out_h, int out_w,
+                      int sampling_ratio, int aligned, int swap_rb, const float* norm, int out_dtype, void* dst,
+                      void* stream);
 /* norm: device float32 [3][3] rows (div, mean, std) per OUTPUT channel:
  * out = (roi_align_value / div - mean) / std in float32, i.e. /255 then Normalize.
  * dst: [K,3,out_h,out_w] contiguous.                                                    */

@@ -25,8 +25,9 @@ template <typename OutT>
 __global__ void __launch_bounds__(256)
 k3_roi_align(const uint8_t* __restrict__ imgs, int n, int H, int W, long long img_stride, int row_stride,
              const float* __restrict__ rois, int K, int PH, int PW, int sampling_ratio, int aligned, int swap_rb,
-             const float* __restrict__ norm, OutT* __restrict__ dst) {
+             const float* __restrict__ norm, OutT* __restrict__ dst, const int* __restrict__ dst_rows) {
     const int k = blockIdx.y;
+    const long long kd = dst_rows ? dst_rows[k] : k;
     const float* r = rois + (long long)k * 5;
     const int img = (int)r[0];
     const float offset = aligned ? 0.5f : 0.f;
@@ -87,7 +88,7 @@ k3_roi_align(const uint8_t* __restrict__ imgs, int n, int H, int W, long long im
         for (int c = 0; c < 3; ++c) {
             float v = __fdiv_rn(acc[c], count);
             v = __fdiv_rn(__fsub_rn(__fdiv_rn(v, nd[c]), nm[c]), ns[c]);
-            OutT* q = dst + ((long long)k * 3 + c) * total + o;
+            OutT* q = dst + (kd * 3 + c) * total + o;
             if (sizeof(OutT) == 2) *reinterpret_cast<uint16_t*>(q) = qc_f2bf(v);
             else *reinterpret_cast<float*>(q) = v;
         }
@@ -102,7 +103,7 @@ template <typename OutT, int SR>
 __global__ void __launch_bounds__(256)
 k3_roi_sep(const uint8_t* __restrict__ imgs, int n, int H, int W, long long img_stride, int row_stride,
            const float* __restrict__ rois, int K, int PH, int PW, int /*sr_rt*/, int aligned, int swap_rb,
-           const float* __restrict__ norm, OutT* __restrict__ dst, int rows_max) {
+           const float* __restrict__ norm, OutT* __restrict__ dst, int rows_max, const int* __restrict__ dst_rows) {
     constexpr int sr = SR;
     extern __shared__ __align__(16) float k3sm[];
     float* Hs = k3sm;                                        // [rows_max][3][PW]
@@ -111,6 +112,7 @@ k3_roi_sep(const uint8_t* __restrict__ imgs, int n, int H, int W, long long img_
         (reinterpret_cast<uintptr_t>(Hs + (size_t)rows_max * 3 * PW) + 15) & ~(uintptr_t)15);
 
     const int k = blockIdx.y;
+    const long long kd = dst_rows ? dst_rows[k] : k;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float* r = rois + (long long)k * 5;
     const int img = (int)r[0];
@@ -149,7 +151,7 @@ k3_roi_sep(const uint8_t* __restrict__ imgs, int n, int H, int W, long long img_
         return __fdiv_rn(__fsub_rn(__fdiv_rn(__fdiv_rn(acc, count), nd[c]), nm[c]), ns[c]);
     };
     auto store = [&](int c, int o, float v) {
-        OutT* q = dst + ((long long)k * 3 + c) * total + o;
+        OutT* q = dst + (kd * 3 + c) * total + o;
         if (sizeof(OutT) == 2) *reinterpret_cast<uint16_t*>(q) = qc_f2bf(v);
         else *reinterpret_cast<float*>(q) = v;
     };
@@ -290,7 +292,7 @@ k3_roi_sep(const uint8_t* __restrict__ imgs, int n, int H, int W, long long img_
                             }
                         }
                         const float v0 = finish(acc.x, c), v1 = finish(acc.y, c), v2 = finish(acc.z, c), v3 = finish(acc.w, c);
-                        OutT* q4 = dst + ((long long)k * 3 + c) * total + ph * PW + 4 * q;
+                        OutT* q4 = dst + (kd * 3 + c) * total + ph * PW + 4 * q;
                         if (sizeof(OutT) == 2) {
                             const __nv_bfloat162 p0 = __floats2bfloat162_rn(v0, v1), p1 = __floats2bfloat162_rn(v2, v3);
                             *reinterpret_cast<uint2*>(q4) = make_uint2(*reinterpret_cast<const unsigned*>(&p0),
@@ -327,7 +329,7 @@ k3_roi_sep(const uint8_t* __restrict__ imgs, int n, int H, int W, long long img_
                     }
                     const float v0 = finish(s0, c), v1 = finish(s1, c);
                     const int o = ph * PW + pw;
-                    OutT* q = dst + ((long long)k * 3 + c) * total + o;
+                    OutT* q = dst + (kd * 3 + c) * total + o;
                     if (sizeof(OutT) == 2 && two && ((reinterpret_cast<uintptr_t>(q) & 3) == 0)) {
                         *reinterpret_cast<uint32_t*>(q) = (uint32_t)qc_f2bf(v0) | ((uint32_t)qc_f2bf(v1) << 16);
                     } else {
@@ -420,7 +422,7 @@ template <typename OutT>
 __global__ void __launch_bounds__(K3T_THREADS)
 k3_roi_tma(const uint8_t* __restrict__ imgs, int n, int H, int W, long long img_stride, int row_stride,
            const float* __restrict__ rois, int K, int PH, int PW, int sr, int aligned, int swap_rb,
-           const float* __restrict__ norm, OutT* __restrict__ dst, int tma_ok) {
+           const float* __restrict__ norm, OutT* __restrict__ dst, int tma_ok, const int* __restrict__ dst_rows) {
     extern __shared__ __align__(128) unsigned char k3t_sm[];
     float* Hs = reinterpret_cast<float*>(k3t_sm);                                  // [K3T_ROWS][3][PW]
     uint8_t* raw = k3t_sm + (((size_t)K3T_ROWS * 3 * PW * 4 + 127) & ~(size_t)127);   // [K3T_RAW]
@@ -459,7 +461,7 @@ k3_roi_tma(const uint8_t* __restrict__ imgs, int n, int H, int W, long long img_
         const float bin_h = __fdiv_rn(roi_h, (float)PH), bin_w = __fdiv_rn(roi_w, (float)PW);
         const bool img_ok = img >= 0 && img < n;
         const uint8_t* base = imgs + (long long)(img_ok ? img : 0) * img_stride;
-        OutT* dk = dst + (long long)k * 3 * total;
+        OutT* dk = dst + (long long)(dst_rows ? dst_rows[k] : k) * 3 * total;
         const bool geom_ok = img_ok && bin_h >= 0.f && bin_w >= 0.f;
         __syncthreads();                                    // previous ROI is done with every shared table
         // ---- per-ROI tables ---------------------------------------------------------------------------------
@@ -662,9 +664,10 @@ k3_roi_tma(const uint8_t* __restrict__ imgs, int n, int H, int W, long long img_
 
 }  // namespace
 
-extern "C" int qc_roi_align(qc_ctx* ctx, const uint8_t* imgs, int n, int h, int w, int64_t img_stride,
-                            int32_t row_stride, const float* rois, int K, int out_h, int out_w, int sampling_ratio,
-                            int aligned, int swap_rb, const float* norm, int out_dtype, void* dst, void* stream) {
+extern "C" int qc_roi_align_rows(qc_ctx* ctx, const uint8_t* imgs, int n, int h, int w, int64_t img_stride,
+                                 int32_t row_stride, const float* rois, const int32_t* dst_rows, int K, int out_h,
+                                 int out_w, int sampling_ratio, int aligned, int swap_rb, const float* norm,
+                                 int out_dtype, void* dst, void* stream) {
     qc_device_guard dev_guard(ctx);
     if (!ctx) return QC_ERR_INVALID;
     if (K == 0) return QC_OK;
@@ -685,12 +688,12 @@ extern "C" int qc_roi_align(qc_ctx* ctx, const uint8_t* imgs, int n, int h, int 
             if (int rc = qc_prepare(ctx, k3_roi_tma<__nv_bfloat16>, (int)smem, K3T_THREADS, &occ)) return rc;
             k3_roi_tma<__nv_bfloat16><<<std::min(K, ctx->sm_count * std::max(occ, 1)), K3T_THREADS, smem, st>>>(
                 imgs, n, h, w, img_stride, row_stride, rois, K, out_h, out_w, sampling_ratio, aligned, swap_rb, norm,
-                (__nv_bfloat16*)dst, tma_ok);
+                (__nv_bfloat16*)dst, tma_ok, dst_rows);
         } else if (out_dtype == QC_DT_F32) {
             if (int rc = qc_prepare(ctx, k3_roi_tma<float>, (int)smem, K3T_THREADS, &occ)) return rc;
             k3_roi_tma<float><<<std::min(K, ctx->sm_count * std::max(occ, 1)), K3T_THREADS, smem, st>>>(
                 imgs, n, h, w, img_stride, row_stride, rois, K, out_h, out_w, sampling_ratio, aligned, swap_rb, norm,
-                (float*)dst, tma_ok);
+                (float*)dst, tma_ok, dst_rows);
         } else {
             QC_FAIL(ctx, QC_ERR_INVALID, "qc_roi_align: bad out_dtype");
         }
@@ -712,7 +715,7 @@ extern "C" int qc_roi_align(qc_ctx* ctx, const uint8_t* imgs, int n, int h, int 
     do {                                                                                                       \
         if (int rc = qc_prepare(ctx, k3_roi_sep<T, S>, (int)smem, 256, nullptr)) return rc;                    \
         k3_roi_sep<T, S><<<grid, 256, smem, st>>>(imgs, n, h, w, img_stride, row_stride, rois, K, out_h, out_w, \
-                                                  sampling_ratio, aligned, swap_rb, norm, (T*)dst, (int)rows_max); \
+                                                  sampling_ratio, aligned, swap_rb, norm, (T*)dst, (int)rows_max, dst_rows); \
     } while (0)
 #define K3_LAUNCH_SR(T)                                  \
     do {                                                 \
@@ -733,12 +736,19 @@ extern "C" int qc_roi_align(qc_ctx* ctx, const uint8_t* imgs, int n, int h, int 
     dim3 grid((unsigned)((total + 255) / 256), (unsigned)K);
     if (out_dtype == QC_DT_BF16)
         k3_roi_align<__nv_bfloat16><<<grid, 256, 0, st>>>(imgs, n, h, w, img_stride, row_stride, rois, K, out_h, out_w,
-                                                          sampling_ratio, aligned, swap_rb, norm, (__nv_bfloat16*)dst);
+                                                          sampling_ratio, aligned, swap_rb, norm, (__nv_bfloat16*)dst, dst_rows);
     else if (out_dtype == QC_DT_F32)
         k3_roi_align<float><<<grid, 256, 0, st>>>(imgs, n, h, w, img_stride, row_stride, rois, K, out_h, out_w,
-                                                  sampling_ratio, aligned, swap_rb, norm, (float*)dst);
+                                                  sampling_ratio, aligned, swap_rb, norm, (float*)dst, dst_rows);
     else
         QC_FAIL(ctx, QC_ERR_INVALID, "qc_roi_align: bad out_dtype");
     QC_LAUNCHED(ctx);
     return QC_OK;
+}
+
+extern "C" int qc_roi_align(qc_ctx* ctx, const uint8_t* imgs, int n, int h, int w, int64_t img_stride,
+                            int32_t row_stride, const float* rois, int K, int out_h, int out_w, int sampling_ratio,
+                            int aligned, int swap_rb, const float* norm, int out_dtype, void* dst, void* stream) {
+    return qc_roi_align_rows(ctx, imgs, n, h, w, img_stride, row_stride, rois, nullptr, K, out_h, out_w, sampling_ratio,
+                             aligned, swap_rb, norm, out_dtype, dst, stream);
 }

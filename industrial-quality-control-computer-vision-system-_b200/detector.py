@@ -825,13 +825,13 @@ class QualityControlDetector:
             pp = _PassThroughPostProcessor(self.config)
         self.postprocessor = pp
 
-    def predict(self, image: np.ndarray, include_segmentation: bool = True, _head_override=None) -> Dict:
+    def predict(self, image: np.ndarray, include_segmentation: bool = True, _head_override=None, _inject=None) -> Dict:
         start_time = time.time()
         try:
             if not self._validate_image(image):
                 return {"error": "Invalid image input"}
             if self._fused():
-                return self._predict_group([image], include_segmentation, _head_override)[0]
+                return self._predict_group([image], include_segmentation, _head_override, _inject)[0]
             processed_image = self._preprocess_image(image)
             ensemble_results = self.ensemble_predictor.predict(processed_image)
             if "error" in ensemble_results:
@@ -860,7 +860,8 @@ class QualityControlDetector:
                 and ens.yolo_detector.model is not None and ens.resnet_classifier.model is not None
                 and ens.yolo_detector.model is ens.resnet_classifier._pipe)
 
-    def _predict_group(self, images: List[np.ndarray], include_segmentation: bool, head_override=None) -> List[Dict]:
+    def _predict_group(self, images: List[np.ndarray], include_segmentation: bool, head_override=None,
+                       inject=None) -> List[Dict]:
         """Same-shape validated images -> reference result dicts.  One upload of the frames, one pass of
         InspectionPipeline (K1 -> YOLO -> K2 -> K3b/K3 -> ResNet-50 -> K7), one download of the packed results; the
         per-image dictionaries are then built by the same host code the single-stage classes use."""
@@ -881,7 +882,8 @@ class QualityControlDetector:
             frames_np = [_as_rgb3(im) for im in processed]
             shapes = [im.shape for im in processed]
         batch = torch.from_numpy(np.stack(frames_np))
-        res = pipe.run(batch.to(pipe.dev), head_override=head_override, include_segmentation=include_segmentation,
+        res = pipe.run(batch.to(pipe.dev), head_override=head_override, inject=inject,
+                       include_segmentation=include_segmentation,
                        keep_seg_tensors=include_segmentation, processed=not raw_ok)
         n = len(images)
         # ROI rows of every image; packed masks come down once per method group
@@ -941,7 +943,7 @@ class QualityControlDetector:
     def _processed_shape(decoded: np.ndarray) -> tuple:
         return decoded.shape
 
-    def predict_batch(self, images: List[np.ndarray], max_workers: int = 4, _head_override=None) -> List[Dict]:
+    def predict_batch(self, images: List[np.ndarray], max_workers: int = 4, _head_override=None, _inject=None) -> List[Dict]:
         """Same signature / result as inference/detector.py:128-180 (results in input order, ``batch_index`` and
         ``batch_statistics`` on every result).  Instead of ``max_workers`` threads calling predict(), valid images
         are grouped by shape and every group goes through the device pipeline as ONE batch."""
@@ -966,11 +968,14 @@ class QualityControlDetector:
                 for c0 in range(0, len(idx), chunk):
                     part = idx[c0:c0 + chunk]
                     try:
-                        ho = None
+                        ho = ij = None
                         if _head_override is not None:
                             sel = torch.as_tensor(part, device=_head_override[0].device)
                             ho = [l.index_select(0, sel) for l in _head_override]
-                        rs = self._predict_group([images[i] for i in part], True, ho)
+                        if _inject is not None:
+                            sel = torch.as_tensor(part, device=_inject[0].device)
+                            ij = [l.index_select(0, sel) for l in _inject]
+                        rs = self._predict_group([images[i] for i in part], True, ho, ij)
                     except Exception as e:
                         rs = [{"error": str(e)} for _ in part]
                     for i, r in zip(part, rs):

@@ -89,6 +89,9 @@ _SIGS = {
     "qc_roi_align": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int32,
                                C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                C.c_int, C.c_void_p, C.c_void_p]),
+    "qc_roi_align_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int32,
+                                    C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                    C.c_int, C.c_void_p, C.c_void_p]),
     "qc_segment_plan": (C.c_int, [C.POINTER(SegRegion), C.c_int, C.POINTER(SegParams)]),
     "qc_pil_resize_table_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "qc_pil_resize_make_tables": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
@@ -317,10 +320,14 @@ class Context:
     # -- K3 --------------------------------------------------------------------------------
     def roi_align(self, imgs: torch.Tensor, rois: torch.Tensor, out_hw=(224, 224), sampling_ratio: int = 2,
                   aligned: bool = True, swap_rb: bool = False, mean=(0.485, 0.456, 0.406),
-                  std=(0.229, 0.224, 0.225), out_dtype=torch.bfloat16, out: Optional[torch.Tensor] = None):
+                  std=(0.229, 0.224, 0.225), out_dtype=torch.bfloat16, out: Optional[torch.Tensor] = None,
+                  dst_rows: Optional[torch.Tensor] = None):
+        """dst_rows (int32 CUDA [K]): ROI k goes to row dst_rows[k] of ``out`` (default: row k)."""
         assert imgs.is_cuda and imgs.dtype == torch.uint8 and imgs.dim() == 4 and imgs.shape[3] == 3
         assert imgs.stride(3) == 1 and imgs.stride(2) == 3
         assert rois.is_cuda and rois.dtype == torch.float32 and rois.is_contiguous() and rois.shape[-1] == 5
+        if dst_rows is not None:
+            assert out is not None and dst_rows.is_cuda and dst_rows.dtype == torch.int32 and dst_rows.numel() == rois.shape[0]
         K = rois.shape[0]
         key = ("norm", tuple(mean), tuple(std))
         if key not in self._lut_cache:
@@ -333,11 +340,11 @@ class Context:
             return out
         n, h, w = imgs.shape[:3]
         dt = QC_DT_BF16 if out.dtype == torch.bfloat16 else QC_DT_F32
-        rc = self.lib.qc_roi_align(self.h, imgs.data_ptr(), n, h, w, imgs.stride(0) if n > 1 else h * imgs.stride(1),
-                                   imgs.stride(1), rois.data_ptr(), K, out_hw[0], out_hw[1], sampling_ratio,
-                                   int(aligned), int(swap_rb), norm.data_ptr(), dt, out.data_ptr(),
-                                   _stream(imgs.device))
-        self._check(rc, "qc_roi_align")
+        rc = self.lib.qc_roi_align_rows(self.h, imgs.data_ptr(), n, h, w, imgs.stride(0) if n > 1 else h * imgs.stride(1),
+                                        imgs.stride(1), rois.data_ptr(), _ptr(dst_rows), K, out_hw[0], out_hw[1],
+                                        sampling_ratio, int(aligned), int(swap_rb), norm.data_ptr(), dt, out.data_ptr(),
+                                        _stream(imgs.device))
+        self._check(rc, "qc_roi_align_rows")
         return out
 
     # -- K3b -------------------------------------------------------------------------------

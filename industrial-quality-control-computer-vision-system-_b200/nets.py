@@ -298,13 +298,15 @@ def yolo_gflops(scale: str, H: int, W: int) -> float:
 
 
 class GraphedNet:
-    """CUDA-graph replay of a conv net at fixed input shapes (one graph per shape, captured lazily
-    after a cuDNN-autotune warm-up).  The producer kernel writes straight into ``input_buffer(shape)``;
-    ``run(shape)`` replays and returns the static outputs (valid until the next replay)."""
+    """CUDA-graph replay of a conv net at fixed input buffers (one graph per (shape, buffer), captured lazily after a
+    cuDNN-autotune warm-up; all graphs of one net share a memory pool -- they never run concurrently).  The producer
+    kernel writes straight into the input: either ``input_buffer(shape)`` + ``run(shape)``, or any caller-owned view
+    (a slice of an arena) through ``run_on(view)``.  Outputs are valid until the next replay of the same graph."""
 
     def __init__(self, module: nn.Module, device, dtype, channels_last: bool = True):
         self.module, self.device, self.dtype, self.cl = module, device, dtype, channels_last
         self.slots = {}
+        self.pool = None
 
     def input_buffer(self, shape) -> torch.Tensor:
         shape = tuple(int(v) for v in shape)
@@ -318,9 +320,7 @@ class GraphedNet:
         return self.module(x)
 
     @torch.no_grad()
-    def run(self, shape):
-        shape = tuple(int(v) for v in shape)
-        slot = self.slots[shape]
+    def _replay(self, slot):
         if slot["graph"] is None:
             cur = torch.cuda.current_stream(self.device)
             side = torch.cuda.Stream(self.device)
@@ -330,9 +330,23 @@ class GraphedNet:
                     self._fwd(slot["in"])
             cur.wait_stream(side)
             torch.cuda.synchronize(self.device)
+            if self.pool is None:
+                self.pool = torch.cuda.graph_pool_handle()
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            with torch.cuda.graph(g, pool=self.pool):
                 slot["out"] = self._fwd(slot["in"])
             slot["graph"] = g
         slot["graph"].replay()
         return slot["out"]
+
+    def run(self, shape):
+        return self._replay(self.slots[tuple(int(v) for v in shape)])
+
+    def run_on(self, view: torch.Tensor):
+        """Replay with ``view`` (contiguous, fixed address) as the static input."""
+        key = (tuple(view.shape), view.data_ptr())
+        slot = self.slots.get(key)
+        if slot is None:
+            assert view.is_contiguous() and view.dtype == self.dtype
+            slot = self.slots[key] = {"in": view, "graph": None}
+        return self._replay(slot)

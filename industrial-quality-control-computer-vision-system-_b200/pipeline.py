@@ -43,6 +43,40 @@ def chunk_plan(total: int, sizes: Sequence[int]) -> List[tuple]:
     return out
 
 
+def classifier_layout(total: int, sizes: Sequence[int]):
+    """Where the ``total`` classifier rows of a batch live in the input arena, so that every static-shape graph always
+    reads the same place (graphs are keyed by buffer address):
+
+        arena[0 : CH)                 the remainder buckets at fixed offsets: 128 at 0, 64 at 128, 32 at 192, 16 at 224,
+                                      8 at 240 and a second 8 at 248 (chunk_plan uses each size once, 8 at most twice)
+        arena[CH*(j+1) : CH*(j+2))    full chunk j of CH = sizes[0] rows
+
+    Returns (rows, views): rows[r] = arena row of classifier row r (int64 [total]); views = [(arena offset, graph batch
+    size, rows used)] in classifier-row order."""
+    CH = sizes[0]
+    fixed, o = {}, 0
+    for c in sizes[1:]:
+        fixed[c] = o
+        o += c
+    second_small = o                    # the second bucket of the smallest size
+    assert second_small + sizes[-1] <= CH
+    rows = np.empty(total, np.int64)
+    views, r, nfull, small_used = [], 0, 0, 0
+    for cs, used in chunk_plan(total, sizes):
+        if cs == CH:
+            off = CH * (nfull + 1)
+            nfull += 1
+        elif cs == sizes[-1]:
+            off = fixed[cs] if small_used == 0 else second_small
+            small_used += 1
+        else:
+            off = fixed[cs]
+        rows[r:r + used] = off + np.arange(used)
+        views.append((off, cs, used))
+        r += used
+    return rows, views
+
+
 @dataclass
 class BatchResult:
     n: int
@@ -226,49 +260,38 @@ class InspectionPipeline:
 
         # ---- K3b/K3 + ResNet-50: whole-frame classifier (models/resent_model.py:114-130, PIL-exact resize) and
         # ROI hand-off (models/ensemble.py:129-142).  Classifier rows: the n whole frames first, then the K ROIs.
+        # All rows of the batch live in ONE arena [rows,3,224,224] whose static-shape views are the inputs of the
+        # ResNet-50 graphs (classifier_layout); K3 fills it with ONE launch (a destination row per ROI), K3b with one
+        # launch per contiguous span of whole-frame rows.
         n_whole = n if self.classify_global else 0
         n_roi = K if self.classify_rois else 0
         nro = n_whole + n_roi
         self.last_num_crops = nro
         probs = None
         if nro:
-            rois = None
-            if n_roi:
-                r = np.concatenate((roi_img[:, None].astype(np.float32), roi_box.astype(np.float32)), 1)
-                rois = torch.from_numpy(np.ascontiguousarray(r)).to(self.dev, non_blocking=True)
-
+            rows, views = classifier_layout(nro, self.crop_chunks)
+            arena = self._classifier_arena(max(o + c for o, c, _ in views))
             # ResNet sees the caller's channel order (two flips: detector.py:234 + resent_model.py:123)
             rswap = bool(processed)
-            def fill(buf, o, k):
-                """classifier rows [o, o+k) -> buf[:k]"""
-                a = min(o + k, n_whole)
-                if o < a:
+            if n_whole:
+                cut = np.flatnonzero(np.diff(rows[:n_whole]) != 1) + 1          # contiguous spans of arena rows
+                for a0, a1 in zip(np.concatenate(([0], cut)), np.concatenate((cut, [n_whole]))):
                     with self._timed("k3b_pil_resize"):
-                        qc.pil_resize(frames[o:a], swap_rb=rswap, mean=RESNET_MEAN, std=RESNET_STD, out=buf[:a - o])
-                if o + k > a:
-                    lo = max(o, n_whole)
-                    with self._timed("k3_roi_align"):
-                        qc.roi_align(frames, rois[lo - n_whole:o + k - n_whole], swap_rb=rswap, mean=RESNET_MEAN,
-                                     std=RESNET_STD, out=buf[lo - o:k])
-
-            if not self.use_graphs:
-                xin = torch.empty((nro, 3, 224, 224), dtype=self.net_dtype, device=self.dev)
-                fill(xin, 0, nro)
-                with self._timed("resnet_net"):
-                    logits = self.resnet(xin.contiguous(memory_format=torch.channels_last))
-                    probs = torch.softmax(logits.float(), 1)
-            else:
-                # static-shape chunks: K3b/K3 write each chunk straight into the graph's input buffer
-                parts, o = [], 0
-                for cs, k in chunk_plan(nro, self.crop_chunks):
-                    shape = (cs, 3, 224, 224)
-                    buf = self.resnet_g.input_buffer(shape)
-                    fill(buf, o, k)
-                    with self._timed("resnet_net"):
-                        logits = self.resnet_g.run(shape)
-                        parts.append(torch.softmax(logits[:k].float(), 1))
-                    o += k
-                probs = torch.cat(parts)
+                        qc.pil_resize(frames[a0:a1], swap_rb=rswap, mean=RESNET_MEAN, std=RESNET_STD,
+                                      out=arena[int(rows[a0]):int(rows[a0]) + int(a1 - a0)])
+            if n_roi:
+                r = np.concatenate((roi_img[:, None].astype(np.float32), roi_box.astype(np.float32),
+                                    rows[n_whole:, None].astype(np.int32).view(np.float32)), 1)   # one upload: rois + rows
+                rd = torch.from_numpy(np.ascontiguousarray(r)).to(self.dev, non_blocking=True)
+                rois = rd[:, :5].contiguous()
+                drows = rd[:, 5].contiguous().view(torch.int32)
+                with self._timed("k3_roi_align"):
+                    qc.roi_align(frames, rois, swap_rb=rswap, mean=RESNET_MEAN, std=RESNET_STD, out=arena, dst_rows=drows)
+            parts = []
+            with self._timed("resnet_net"):
+                for off, cs, used in views:
+                    parts.append(torch.softmax(self._classify(arena[off:off + cs])[:used].float(), 1))
+            probs = torch.cat(parts) if len(parts) > 1 else parts[0]
 
         # ---- segmentation of every detection ROI (K7 per-class methods, or the K4 composite) ------------------
         seg = None
@@ -333,6 +356,21 @@ class InspectionPipeline:
                                  method=code, want_sums=(code == ffi.QC_SEG_REF_THRESHOLD))
             groups.append(dict(name=name, idx=idx, code=code, iters=iters, seg=seg, cap=cap, regs=regs, swap_rb=swap_rb))
         return groups
+
+    def _classifier_arena(self, rows: int) -> torch.Tensor:
+        """Grow-only [rows,3,224,224] input arena of the classifier (sized in whole chunks, with headroom so that the
+        graphs captured on its views stay valid from batch to batch)."""
+        a = getattr(self, "_arena", None)
+        if a is None or a.shape[0] < rows:
+            CH = self.crop_chunks[0]
+            rows = max(rows, 4 * CH) if a is None else max(rows, 2 * a.shape[0])
+            self._arena = a = torch.zeros((rows, 3, 224, 224), dtype=self.net_dtype, device=self.dev)
+        return a
+
+    def _classify(self, x: torch.Tensor) -> torch.Tensor:
+        if self.use_graphs:
+            return self.resnet_g.run_on(x)
+        return self.resnet(x.contiguous(memory_format=torch.channels_last))
 
     def _upload(self, host_frames: torch.Tensor):
         """uint8 [n,h,w,3] host tensor (pinned for a truly asynchronous copy) -> device staging buffer; the compute

@@ -133,6 +133,26 @@ def test_pil_resize_tables_match_pillow_coefficients():
     assert lib.qc_pil_resize_make_tables(0, 5, 224, 224, t.ctypes.data) != 0
 
 
+def test_classifier_layout_is_a_fixed_place_partition():
+    """Every static-shape classifier graph reads a fixed slice of the arena: rows are unique, views do not overlap, a
+    size always sits at the same offset, and the views cover the rows in classifier order."""
+    from qcgraft.pipeline import classifier_layout, chunk_plan
+    sizes = (256, 128, 64, 32, 16, 8)
+    seen = {}
+    for total in list(range(1, 600)) + [1432, 2047, 4096, 5000]:
+        rows, views = classifier_layout(total, sizes)
+        assert len(set(rows.tolist())) == total and [(c, u) for _, c, u in views] == chunk_plan(total, sizes)
+        iv = sorted((o, o + c) for o, c, _ in views)
+        assert all(a[1] <= b[0] for a, b in zip(iv, iv[1:]))
+        r = 0
+        for off, cs, used in views:
+            assert rows[r:r + used].tolist() == list(range(off, off + used))
+            r += used
+            if cs != 256:
+                seen.setdefault(cs, set()).add(off)
+    assert all(len(v) == (2 if cs == 8 else 1) for cs, v in seen.items()), seen
+
+
 def test_classifier_chunk_plan():
     """Static ResNet batch sizes: every launch but the last is full, the tail rounds up to the smallest graph."""
     from qcgraft.pipeline import chunk_plan
