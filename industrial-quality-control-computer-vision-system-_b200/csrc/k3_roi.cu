@@ -18,6 +18,7 @@
 #include <math.h>
 #include <limits.h>
 #include <algorithm>
+#include <stdlib.h>
 
 namespace {
 
@@ -345,19 +346,21 @@ k3_roi_sep(const uint8_t* __restrict__ imgs, int n, int H, int W, long long img_
 
 
 // ------------------------------------------------------------------------------------------
-// k3_roi_tma (sampling_ratio 1..2, out_w % 4 == 0, out_w <= 224 columns per CTA pass): ONE CTA per ROI walks the
-// ROI's output rows in bands.  Per ROI, once: every thread builds the merged x taps of its output column (<= 4 source
-// pixels with summed weights, kept in registers) and the CTA builds the merged y taps of every output row.  Per band:
+// k3_roi_tma (sampling_ratio 1..2, out_w % 4 == 0, out_w <= 224): persistent CTAs, ONE CTA per ROI at a time, walking
+// the ROI's output rows in bands.  Per ROI, once: every thread builds the merged x taps of its output column (<= 4
+// source pixels with summed weights, kept in registers) and the CTA builds the merged y taps of every output row.
+// Per band (closed-form extent: the y samples are monotone):
 //   (0) the band's source rows are staged as raw bytes in shared memory -- the 16-byte aligned superset of the row
 //       segment the ROI touches, one 1-D TMA bulk copy (cp.async.bulk + mbarrier -> SASS UBLKCP) per row when base
-//       and pitch are 16-byte aligned, plain loads otherwise; the copy of band b+1 is issued as soon as band b's
-//       horizontal pass has consumed the buffer, so it overlaps band b's vertical pass
-//   (1) horizontal pass, thread per output column: <= 4 byte taps x 3 channels from shared memory -> Hs[row][c][col]
-//   (2) vertical pass, thread per (4 columns, row slice), 3 channels: <= 4 LDS.128 + 16 FMAs per 12 outputs,
-//       /255 + Normalize, one 64-bit (bf16x4) or 128-bit (f32x4) store per channel.
+//       and pitch are 16-byte aligned, plain loads otherwise -- and converted ONCE to float (4 bytes per thread-step);
+//       the copy of band b+1 is issued right after, so it overlaps band b's arithmetic
+//   (1) horizontal pass, thread per output column: 3 (or 4) float taps x 3 channels -> Hs[row][c][col]
+//   (2) vertical pass, thread per (4 columns, row slice), 3 channels: 3 (or 4) LDS.128 + 12 (16) FMAs per 4 outputs,
+//       /255 + Normalize as ONE fma (v = acc * 1/(count*div*std) - mean/std), one 64-bit (bf16x4) or 128-bit store.
+// Boxes with samples outside the frame, inverted boxes and rows wider than the staging buffer take the direct form.
 constexpr int K3T_THREADS = 224;
-constexpr int K3T_ROWS = 16;               // source rows per band held as Hs
-constexpr int K3T_RAW = 32 * 1024;         // raw byte staging buffer
+constexpr int K3T_ROWS = 12;               // source rows per band held as Hs
+constexpr int K3T_RAW = 6 * 1024;          // raw byte staging buffer (floats: 4x)
 constexpr int K3T_PH_MAX = 256;
 
 struct K3Taps { int i[4]; float w[4]; int n; };
@@ -371,7 +374,7 @@ __device__ __forceinline__ K3Taps k3_taps(float start, float bin, int p, int sr,
     for (int j = 0; j < 4; ++j) { t.i[j] = 0; t.w[j] = 0.f; }
     for (int is = 0; is < sr; ++is) {
         float v = __fadd_rn(__fadd_rn(start, __fmul_rn((float)p, bin)), __fdiv_rn(__fmul_rn((float)is + 0.5f, bin), (float)sr));
-        if (v < -1.f || v > (float)size || !(v == v)) continue;
+        if (v < -1.f || v > (float)size || !(v == v)) { t.n |= 8; continue; }     // bit 3: a sample fell outside
         if (v <= 0.f) v = 0.f;
         int lo = (int)v, hi;
         if (lo >= size - 1) { hi = lo = size - 1; v = (float)lo; } else hi = lo + 1;
@@ -383,11 +386,11 @@ __device__ __forceinline__ K3Taps k3_taps(float start, float bin, int p, int sr,
             bool merged = false;
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-                if (!merged && j < t.n && t.i[j] == idx[e]) { t.w[j] = __fadd_rn(t.w[j], wt[e]); merged = true; }
+                if (!merged && j < (t.n & 7) && t.i[j] == idx[e]) { t.w[j] = __fadd_rn(t.w[j], wt[e]); merged = true; }
             if (!merged) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
-                    if (j == t.n) { t.i[j] = idx[e]; t.w[j] = wt[e]; }
+                    if (j == (t.n & 7)) { t.i[j] = idx[e]; t.w[j] = wt[e]; }
                 t.n += 1;
             }
         }
@@ -395,59 +398,84 @@ __device__ __forceinline__ K3Taps k3_taps(float start, float bin, int p, int sr,
     return t;
 }
 
-// one output row, 4 columns of one channel, taps straight from global memory (rare slow path)
-__device__ __noinline__ float4 k3_row_direct(const uint8_t* base, int row_stride, int4 yi, float4 yw, int yn, float x1,
-                                             float bin_w, int pw0, int sr, int W, int sc) {
-    float accv[4] = {0.f, 0.f, 0.f, 0.f};
-    const int ia[4] = {yi.x, yi.y, yi.z, yi.w};
-    const float wa[4] = {yw.x, yw.y, yw.z, yw.w};
+// direct form of one ROI (torchvision's loop order verbatim): boxes leaving the frame, inverted boxes, oversized rows
+template <typename OutT>
+__device__ __noinline__ void k3_roi_direct(const uint8_t* base, bool img_ok, int H, int W, int row_stride, float x1, float y1,
+                                           float bin_w, float bin_h, int PH, int PW, int sr, int swap_rb, const float* nd,
+                                           const float* nm, const float* ns, OutT* dk) {
+    const int total = PH * PW;
+    const float count = (float)(sr * sr);
+    for (int o = threadIdx.x; o < total; o += K3T_THREADS) {
+        const int ph = o / PW, pw = o - ph * PW;
+        float acc[3] = {0.f, 0.f, 0.f};
+        if (img_ok) {
+            for (int iy = 0; iy < sr; ++iy) {
+                const float yy = __fadd_rn(__fadd_rn(y1, __fmul_rn((float)ph, bin_h)), __fdiv_rn(__fmul_rn((float)iy + 0.5f, bin_h), (float)sr));
+                for (int ix = 0; ix < sr; ++ix) {
+                    const float xx = __fadd_rn(__fadd_rn(x1, __fmul_rn((float)pw, bin_w)), __fdiv_rn(__fmul_rn((float)ix + 0.5f, bin_w), (float)sr));
+                    float y = yy, x = xx;
+                    if (y < -1.f || y > (float)H || x < -1.f || x > (float)W) continue;
+                    if (y <= 0.f) y = 0.f;
+                    if (x <= 0.f) x = 0.f;
+                    int yl = (int)y, xl = (int)x, yh, xh;
+                    if (yl >= H - 1) { yh = yl = H - 1; y = (float)yl; } else yh = yl + 1;
+                    if (xl >= W - 1) { xh = xl = W - 1; x = (float)xl; } else xh = xl + 1;
+                    const float ly = __fsub_rn(y, (float)yl), lx = __fsub_rn(x, (float)xl);
+                    const float hy = __fsub_rn(1.f, ly), hx = __fsub_rn(1.f, lx);
+                    const float w1 = __fmul_rn(hy, hx), w2 = __fmul_rn(hy, lx), w3 = __fmul_rn(ly, hx), w4 = __fmul_rn(ly, lx);
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-        const K3Taps te = k3_taps(x1, bin_w, pw0 + e, sr, W);
+                    for (int c = 0; c < 3; ++c) {
+                        const int sc = swap_rb ? 2 - c : c;
+                        float v = __fmul_rn(w1, (float)__ldg(base + (long long)yl * row_stride + xl * 3 + sc));
+                        v = __fadd_rn(v, __fmul_rn(w2, (float)__ldg(base + (long long)yl * row_stride + xh * 3 + sc)));
+                        v = __fadd_rn(v, __fmul_rn(w3, (float)__ldg(base + (long long)yh * row_stride + xl * 3 + sc)));
+                        v = __fadd_rn(v, __fmul_rn(w4, (float)__ldg(base + (long long)yh * row_stride + xh * 3 + sc)));
+                        acc[c] = __fadd_rn(acc[c], v);
+                    }
+                }
+            }
+        }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            if (j >= yn) continue;
-            const uint8_t* rowg = base + (long long)ia[j] * row_stride;
-            float hsum = 0.f;
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj)
-                if (jj < te.n) hsum = __fmaf_rn(te.w[jj], (float)__ldg(rowg + 3 * te.i[jj] + sc), hsum);
-            accv[e] = __fmaf_rn(wa[j], hsum, accv[e]);
+        for (int c = 0; c < 3; ++c) {
+            const float v = __fdiv_rn(__fsub_rn(__fdiv_rn(__fdiv_rn(acc[c], count), nd[c]), nm[c]), ns[c]);
+            OutT* q = dk + (long long)c * total + o;
+            if (sizeof(OutT) == 2) *reinterpret_cast<uint16_t*>(q) = qc_f2bf(v);
+            else *reinterpret_cast<float*>(q) = v;
         }
     }
-    return make_float4(accv[0], accv[1], accv[2], accv[3]);
 }
 
 template <typename OutT>
-__global__ void __launch_bounds__(K3T_THREADS)
+__global__ void __launch_bounds__(K3T_THREADS, 3)
 k3_roi_tma(const uint8_t* __restrict__ imgs, int n, int H, int W, long long img_stride, int row_stride,
            const float* __restrict__ rois, int K, int PH, int PW, int sr, int aligned, int swap_rb,
            const float* __restrict__ norm, OutT* __restrict__ dst, int tma_ok, const int* __restrict__ dst_rows) {
     extern __shared__ __align__(128) unsigned char k3t_sm[];
     float* Hs = reinterpret_cast<float*>(k3t_sm);                                  // [K3T_ROWS][3][PW]
-    uint8_t* raw = k3t_sm + (((size_t)K3T_ROWS * 3 * PW * 4 + 127) & ~(size_t)127);   // [K3T_RAW]
-    __shared__ int4 s_yi[K3T_PH_MAX];
+    float* Fb = Hs + (size_t)K3T_ROWS * 3 * PW;                                    // [rows][pitch] bytes as floats
+    uint8_t* raw = reinterpret_cast<uint8_t*>(Fb + K3T_RAW);                       // [K3T_RAW], 16-byte aligned
+    __shared__ int4 s_yo[K3T_PH_MAX];          // y taps of an output row: element offsets row * 3 * PW into Hs
     __shared__ float4 s_yw[K3T_PH_MAX];
     __shared__ short s_ylo[K3T_PH_MAX], s_yhi[K3T_PH_MAX], s_yn[K3T_PH_MAX];
     __shared__ __align__(8) uint64_t s_bar;
     __shared__ int s_xr[2];
     const int tid = threadIdx.x;
     const int total = PH * PW;
-    float nd[3], nm[3], ns[3], ri[3], rs[3];
+    float nd[3], nm[3], ns[3], fa[3], fb[3];
 #pragma unroll
     for (int c = 0; c < 3; ++c) { nd[c] = norm[c * 3 + 0]; nm[c] = norm[c * 3 + 1]; ns[c] = norm[c * 3 + 2]; }
     const float count = (float)(sr * sr);
+    // out = ((acc/count)/div - mean)/std  ==  acc * A - B up to ~6e-7 absolute (inside the 1e-3 / 1-bf16-ulp bars)
 #pragma unroll
-    for (int c = 0; c < 3; ++c) { ri[c] = __fdiv_rn(__fdiv_rn(1.f, count), nd[c]); rs[c] = __fdiv_rn(1.f, ns[c]); }
-    // out = ((acc/count)/div - mean)/std with reciprocal multiplies; where q - mean cancels (|d| < 2^-14, ~0.01 % of
-    // the values) the exact divisions are replayed (see k3_roi_sep)
-    auto finish = [&](float acc, int c) -> float {
-        float d = __fsub_rn(__fmul_rn(acc, ri[c]), nm[c]);
-        if (fabsf(d) < 6.103515625e-5f) d = __fsub_rn(__fdiv_rn(__fdiv_rn(acc, count), nd[c]), nm[c]);
-        return __fmul_rn(d, rs[c]);
-    };
+    for (int c = 0; c < 3; ++c) {
+        fa[c] = __fdiv_rn(1.f, __fmul_rn(__fmul_rn(count, nd[c]), ns[c]));
+        fb[c] = -__fdiv_rn(nm[c], ns[c]);
+    }
     if (tid == 0) { qc_mbar_init(&s_bar, 1); qc_fence_mbar_init(); }
     unsigned parity = 0;
+    const int quads = PW >> 2;
+    const int nsl = K3T_THREADS / quads;             // row slices of the vertical pass
+    const int vq = tid % quads, vsl = tid / quads;
     __syncthreads();
 
     for (int k = blockIdx.x; k < K; k += gridDim.x) {
@@ -461,102 +489,72 @@ k3_roi_tma(const uint8_t* __restrict__ imgs, int n, int H, int W, long long img_
         const float bin_h = __fdiv_rn(roi_h, (float)PH), bin_w = __fdiv_rn(roi_w, (float)PW);
         const bool img_ok = img >= 0 && img < n;
         const uint8_t* base = imgs + (long long)(img_ok ? img : 0) * img_stride;
-        OutT* dk = dst + (long long)(dst_rows ? dst_rows[k] : k) * 3 * total;
-        const bool geom_ok = img_ok && bin_h >= 0.f && bin_w >= 0.f;
+        OutT* const dk = dst + (long long)(dst_rows ? dst_rows[k] : k) * 3 * total;
+        const bool geom_ok = img_ok && bin_h >= 0.f && bin_w >= 0.f && H <= 32767;
         __syncthreads();                                    // previous ROI is done with every shared table
         // ---- per-ROI tables ---------------------------------------------------------------------------------
         K3Taps tx;
         tx.n = 0;
         if (tid < PW) tx = k3_taps(x1, bin_w, tid, sr, W);
         if (tid == 0) { s_xr[0] = INT_MAX; s_xr[1] = -1; }
+        int bad = (tid < PW && ((tx.n & 8) || (tx.n & 7) == 0)) ? 1 : 0;
+        int max_n = tx.n & 7;
         for (int ph = tid; ph < PH; ph += K3T_THREADS) {
             const K3Taps ty = k3_taps(y1, bin_h, ph, sr, H);
-            s_yi[ph] = make_int4(ty.i[0], ty.i[1], ty.i[2], ty.i[3]);
-            s_yw[ph] = make_float4(ty.w[0], ty.w[1], ty.w[2], ty.w[3]);
+            const int yn = ty.n & 7;
+            if ((ty.n & 8) || yn == 0) bad = 1;
+            max_n = max(max_n, yn);
             int lo = INT_MAX, hi = -1;
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-                if (j < ty.n) { lo = min(lo, ty.i[j]); hi = max(hi, ty.i[j]); }
-            s_ylo[ph] = (short)(ty.n ? lo : 0); s_yhi[ph] = (short)(ty.n ? hi : 0); s_yn[ph] = (short)ty.n;
+                if (j < yn) { lo = min(lo, ty.i[j]); hi = max(hi, ty.i[j]); }
+            // unused slots: weight 0 on the row's first tap (always staged)
+            s_yo[ph] = make_int4(ty.i[0] * 3 * PW, (yn > 1 ? ty.i[1] : ty.i[0]) * 3 * PW, (yn > 2 ? ty.i[2] : ty.i[0]) * 3 * PW,
+                                 (yn > 3 ? ty.i[3] : ty.i[0]) * 3 * PW);
+            s_yw[ph] = make_float4(ty.w[0], ty.w[1], ty.w[2], ty.w[3]);
+            s_ylo[ph] = (short)(yn ? lo : 0); s_yhi[ph] = (short)(yn ? hi : 0); s_yn[ph] = (short)yn;
         }
         __syncthreads();
-        if (tid < PW && tx.n) {
+        if (tid < PW && (tx.n & 7)) {
             int lo = tx.i[0], hi = tx.i[0];
 #pragma unroll
             for (int j = 1; j < 4; ++j)
-                if (j < tx.n) { lo = min(lo, tx.i[j]); hi = max(hi, tx.i[j]); }
+                if (j < (tx.n & 7)) { lo = min(lo, tx.i[j]); hi = max(hi, tx.i[j]); }
             atomicMin(&s_xr[0], lo);
             atomicMax(&s_xr[1], hi);
         }
-        __syncthreads();
+        const int any_bad = __syncthreads_or(bad);
+        const int four = __syncthreads_or(max_n > 3);          // some coordinate needs all 4 tap slots
         const int x_lo = s_xr[0], x_hi = s_xr[1];
         // byte window of a source row: 16-byte aligned superset of [3*x_lo, 3*x_hi + 3)
-        int b0 = 0, pitch = 16;
-        bool direct = !geom_ok || x_hi < 0 || H > 32767;
-        if (!direct) {
-            b0 = (3 * x_lo) & ~15;
-            pitch = ((3 * (x_hi + 1) + 15) & ~15) - b0;       // TMA: pitch % 16 == 0 keeps the window inside row_stride
-            if (pitch * 2 > K3T_RAW) direct = true;
-        }
-        if (direct) {
-            // inverted / oversized boxes: the direct form (torchvision's loop order), rare
-            for (int o = tid; o < total; o += K3T_THREADS) {
-                const int ph = o / PW, pw = o - ph * PW;
-                float acc[3] = {0.f, 0.f, 0.f};
-                if (img_ok) {
-                    for (int iy = 0; iy < sr; ++iy) {
-                        const float yy = __fadd_rn(__fadd_rn(y1, __fmul_rn((float)ph, bin_h)), __fdiv_rn(__fmul_rn((float)iy + 0.5f, bin_h), (float)sr));
-                        for (int ix = 0; ix < sr; ++ix) {
-                            const float xx = __fadd_rn(__fadd_rn(x1, __fmul_rn((float)pw, bin_w)), __fdiv_rn(__fmul_rn((float)ix + 0.5f, bin_w), (float)sr));
-                            float y = yy, x = xx;
-                            if (y < -1.f || y > (float)H || x < -1.f || x > (float)W) continue;
-                            if (y <= 0.f) y = 0.f;
-                            if (x <= 0.f) x = 0.f;
-                            int yl = (int)y, xl = (int)x, yh, xh;
-                            if (yl >= H - 1) { yh = yl = H - 1; y = (float)yl; } else yh = yl + 1;
-                            if (xl >= W - 1) { xh = xl = W - 1; x = (float)xl; } else xh = xl + 1;
-                            const float ly = __fsub_rn(y, (float)yl), lx = __fsub_rn(x, (float)xl);
-                            const float hy = __fsub_rn(1.f, ly), hx = __fsub_rn(1.f, lx);
-                            const float w1 = __fmul_rn(hy, hx), w2 = __fmul_rn(hy, lx), w3 = __fmul_rn(ly, hx), w4 = __fmul_rn(ly, lx);
-#pragma unroll
-                            for (int c = 0; c < 3; ++c) {
-                                const int sc = swap_rb ? 2 - c : c;
-                                float v = __fmul_rn(w1, (float)__ldg(base + (long long)yl * row_stride + xl * 3 + sc));
-                                v = __fadd_rn(v, __fmul_rn(w2, (float)__ldg(base + (long long)yl * row_stride + xh * 3 + sc)));
-                                v = __fadd_rn(v, __fmul_rn(w3, (float)__ldg(base + (long long)yh * row_stride + xl * 3 + sc)));
-                                v = __fadd_rn(v, __fmul_rn(w4, (float)__ldg(base + (long long)yh * row_stride + xh * 3 + sc)));
-                                acc[c] = __fadd_rn(acc[c], v);
-                            }
-                        }
-                    }
-                }
-#pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    const float v = __fdiv_rn(__fsub_rn(__fdiv_rn(__fdiv_rn(acc[c], count), nd[c]), nm[c]), ns[c]);
-                    OutT* q = dk + (long long)c * total + o;
-                    if (sizeof(OutT) == 2) *reinterpret_cast<uint16_t*>(q) = qc_f2bf(v);
-                    else *reinterpret_cast<float*>(q) = v;
-                }
-            }
+        const int b0 = (3 * max(x_lo, 0)) & ~15;
+        const int pitch = max(((3 * (x_hi + 1) + 15) & ~15) - b0, 16);
+        const int rows_cap = min(K3T_ROWS, K3T_RAW / pitch);
+        if (!geom_ok || any_bad || x_hi < 0 || rows_cap < 2 || s_yhi[0] - s_ylo[0] + 1 > rows_cap ||
+            s_yhi[PH - 1] - s_ylo[PH - 1] + 1 > rows_cap || __fmul_rn(bin_h, 1.f) > (float)(rows_cap - 2)) {
+            k3_roi_direct<OutT>(base, img_ok, H, W, row_stride, x1, y1, bin_w, bin_h, PH, PW, sr, swap_rb, nd, nm, ns, dk);
             continue;
         }
-        const int rows_cap = min(K3T_ROWS, K3T_RAW / pitch);
-        // band [pa, pb): output rows whose source rows r_lo .. r_hi fit (rows without valid samples cost nothing)
+        // x taps relative to the staged window (float index of the byte): unused slots weight 0 on the first tap
+        int xo[4];
+        float xw[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const bool used = j < (tx.n & 7);
+            xo[j] = 3 * (used ? tx.i[j] : tx.i[0]) - b0;
+            xw[j] = used ? tx.w[j] : 0.f;
+        }
+        // band [pa, pb): closed form from the sample spacing, then trimmed until its source rows fit
         auto band_end = [&](int pa, int& r_lo, int& r_hi) -> int {
-            r_lo = INT_MAX; r_hi = -1;
-            int pb = pa;
-            while (pb < PH) {
-                int lo = r_lo, hi = r_hi;
-                if (s_yn[pb]) { lo = min(lo, (int)s_ylo[pb]); hi = max(hi, (int)s_yhi[pb]); }
-                if (hi >= 0 && hi - lo + 1 > rows_cap) break;
-                r_lo = lo; r_hi = hi;
-                ++pb;
-            }
+            int nb = bin_h > 0.f ? (int)fminf((float)(rows_cap - 2) / bin_h, (float)(PH - pa)) : PH - pa;
+            int pb = pa + max(nb, 1);
+            r_lo = s_ylo[pa];
+            r_hi = s_yhi[pb - 1];
+            while (r_hi - r_lo + 1 > rows_cap && pb > pa + 1) { --pb; r_hi = s_yhi[pb - 1]; }
             return pb;
         };
         const bool use_tma = tma_ok != 0;
         auto stage = [&](int r_lo, int r_hi) {               // rows r_lo..r_hi -> raw[rr * pitch + (byte - b0)]
-            if (r_hi < 0) return;
             const int nrows = r_hi - r_lo + 1;
             if (use_tma) {
                 if (tid == 0) {
@@ -574,78 +572,83 @@ k3_roi_tma(const uint8_t* __restrict__ imgs, int n, int H, int W, long long img_
         };
         int pa = 0, r_lo, r_hi;
         int pb = band_end(pa, r_lo, r_hi);
-        if (pb == pa) {
-            // a single output row needs more source rows than a band holds (extreme down-scaling): not this kernel's
-            // case -- the host only routes sr <= 2, and rows_cap >= 2 holds lo/hi of one sample; two far-apart samples
-            // of one row are handled by widening the band to exactly that row through the generic tap loop below
-            pb = pa + 1; r_lo = s_ylo[pa]; r_hi = s_yhi[pa];
-        }
-        if (r_hi < 0 || r_hi - r_lo + 1 <= rows_cap) stage(r_lo, r_hi);
+        stage(r_lo, r_hi);
         while (pa < PH) {
-            const int nrows = r_hi >= 0 ? r_hi - r_lo + 1 : 0;
-            const bool fits = nrows <= rows_cap;
-            if (nrows && fits) {
-                if (use_tma) { qc_mbar_wait(&s_bar, parity); parity ^= 1u; }
-                else __syncthreads();
-                // (1) horizontal pass: thread = output column
-                if (tid < PW) {
-                    for (int rr = 0; rr < nrows; ++rr) {
-                        const uint8_t* rowp = raw + rr * pitch - b0;
-                        float a0 = 0.f, a1 = 0.f, a2 = 0.f;
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            if (j < tx.n) {
-                                const uint8_t* px = rowp + 3 * tx.i[j];
-                                a0 = __fmaf_rn(tx.w[j], (float)px[0], a0);
-                                a1 = __fmaf_rn(tx.w[j], (float)px[1], a1);
-                                a2 = __fmaf_rn(tx.w[j], (float)px[2], a2);
-                            }
-                        }
-                        float* hrow = Hs + (size_t)rr * 3 * PW;
-                        hrow[(swap_rb ? 2 : 0) * PW + tid] = a0;
-                        hrow[PW + tid] = a1;
-                        hrow[(swap_rb ? 0 : 2) * PW + tid] = a2;
-                    }
-                }
+            const int nrows = r_hi - r_lo + 1;
+            if (use_tma) { qc_mbar_wait(&s_bar, parity); parity ^= 1u; }
+            else __syncthreads();
+            // (0) bytes -> floats, one 32-bit word (4 bytes) per step
+            for (int i = tid; i < (nrows * pitch) >> 2; i += K3T_THREADS) {
+                const unsigned wv = reinterpret_cast<const unsigned*>(raw)[i];
+                reinterpret_cast<float4*>(Fb)[i] = make_float4((float)(wv & 255u), (float)((wv >> 8) & 255u),
+                                                               (float)((wv >> 16) & 255u), (float)(wv >> 24));
             }
-            __syncthreads();                                 // Hs complete, raw consumed
-            // next band: its rows stream in while this band's vertical pass runs
+            __syncthreads();                                 // Fb complete, raw consumed
+            // next band: its rows stream in while this band is computed
             const int npa = pb;
             int nr_lo = 0, nr_hi = -1, npb = npa;
             if (npa < PH) {
                 npb = band_end(npa, nr_lo, nr_hi);
-                if (npb == npa) { npb = npa + 1; nr_lo = s_ylo[npa]; nr_hi = s_yhi[npa]; }
-                if (nr_hi < 0 || nr_hi - nr_lo + 1 <= rows_cap) stage(nr_lo, nr_hi);
+                stage(nr_lo, nr_hi);
             }
-            // (2) vertical pass
-            const int quads = PW >> 2;
-            const int nsl = K3T_THREADS / quads;             // row slices
-            const int q = tid % quads, sl = tid / quads;
-            if (sl < nsl) {
+            // (1) horizontal pass: thread = output column (3 tap slots, 4 only when some column of the ROI needs them)
+            if (tid < PW) {
+                const int c0 = swap_rb ? 2 : 0, c2 = swap_rb ? 0 : 2;
+                float* hrow = Hs + tid;
+                const float* fr = Fb;
+                if (!four) {
+#pragma unroll 2
+                    for (int rr = 0; rr < nrows; ++rr, fr += pitch, hrow += 3 * PW) {
+                        float a0 = __fmul_rn(xw[0], fr[xo[0]]), a1 = __fmul_rn(xw[0], fr[xo[0] + 1]), a2 = __fmul_rn(xw[0], fr[xo[0] + 2]);
+                        a0 = __fmaf_rn(xw[1], fr[xo[1]], a0); a1 = __fmaf_rn(xw[1], fr[xo[1] + 1], a1); a2 = __fmaf_rn(xw[1], fr[xo[1] + 2], a2);
+                        a0 = __fmaf_rn(xw[2], fr[xo[2]], a0); a1 = __fmaf_rn(xw[2], fr[xo[2] + 1], a1); a2 = __fmaf_rn(xw[2], fr[xo[2] + 2], a2);
+                        hrow[c0 * PW] = a0; hrow[PW] = a1; hrow[c2 * PW] = a2;
+                    }
+                } else {
+                    for (int rr = 0; rr < nrows; ++rr, fr += pitch, hrow += 3 * PW) {
+                        float a0 = __fmul_rn(xw[0], fr[xo[0]]), a1 = __fmul_rn(xw[0], fr[xo[0] + 1]), a2 = __fmul_rn(xw[0], fr[xo[0] + 2]);
+                        a0 = __fmaf_rn(xw[1], fr[xo[1]], a0); a1 = __fmaf_rn(xw[1], fr[xo[1] + 1], a1); a2 = __fmaf_rn(xw[1], fr[xo[1] + 2], a2);
+                        a0 = __fmaf_rn(xw[2], fr[xo[2]], a0); a1 = __fmaf_rn(xw[2], fr[xo[2] + 1], a1); a2 = __fmaf_rn(xw[2], fr[xo[2] + 2], a2);
+                        a0 = __fmaf_rn(xw[3], fr[xo[3]], a0); a1 = __fmaf_rn(xw[3], fr[xo[3] + 1], a1); a2 = __fmaf_rn(xw[3], fr[xo[3] + 2], a2);
+                        hrow[c0 * PW] = a0; hrow[PW] = a1; hrow[c2 * PW] = a2;
+                    }
+                }
+            }
+            __syncthreads();                                 // Hs complete
+            // (2) vertical pass: the tap-slot count of the output row picks the loop body (rows between two source
+            // rows -- most rows of an up-scaled box -- need 2 loads + 8 multiply-adds per 4 outputs)
+            if (vsl < nsl) {
                 const int nb = pb - pa;
                 const int per = (nb + nsl - 1) / nsl;
-                const int pe = min(pa + (sl + 1) * per, pb);
-                for (int ph = pa + sl * per; ph < pe; ++ph) {
-                    const int4 yi = s_yi[ph];
+                const int pe = min(pa + (vsl + 1) * per, pb);
+                const float* hb = Hs - r_lo * 3 * PW + 4 * vq;
+                OutT* qrow = dk + (pa + vsl * per) * PW + 4 * vq;
+                for (int ph = pa + vsl * per; ph < pe; ++ph, qrow += PW) {
+                    const int4 yo = s_yo[ph];
                     const float4 yw = s_yw[ph];
-                    const int yn = fits ? s_yn[ph] : 0;
-                    const int ia[4] = {yi.x, yi.y, yi.z, yi.w};
-                    const float wa[4] = {yw.x, yw.y, yw.z, yw.w};
+                    const int yn = s_yn[ph];
 #pragma unroll
                     for (int c = 0; c < 3; ++c) {
-                        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            if (j < yn) {
-                                const float4 a = *reinterpret_cast<const float4*>(Hs + ((size_t)(ia[j] - r_lo) * 3 + c) * PW + 4 * q);
-                                acc.x = __fmaf_rn(wa[j], a.x, acc.x); acc.y = __fmaf_rn(wa[j], a.y, acc.y);
-                                acc.z = __fmaf_rn(wa[j], a.z, acc.z); acc.w = __fmaf_rn(wa[j], a.w, acc.w);
+                        const float* hc = hb + c * PW;
+                        const float4 t0 = *reinterpret_cast<const float4*>(hc + yo.x);
+                        const float4 t1 = *reinterpret_cast<const float4*>(hc + yo.y);
+                        float4 acc;
+                        acc.x = __fmul_rn(yw.x, t0.x); acc.y = __fmul_rn(yw.x, t0.y); acc.z = __fmul_rn(yw.x, t0.z); acc.w = __fmul_rn(yw.x, t0.w);
+                        acc.x = __fmaf_rn(yw.y, t1.x, acc.x); acc.y = __fmaf_rn(yw.y, t1.y, acc.y);
+                        acc.z = __fmaf_rn(yw.y, t1.z, acc.z); acc.w = __fmaf_rn(yw.y, t1.w, acc.w);
+                        if (yn > 2) {
+                            const float4 t2 = *reinterpret_cast<const float4*>(hc + yo.z);
+                            acc.x = __fmaf_rn(yw.z, t2.x, acc.x); acc.y = __fmaf_rn(yw.z, t2.y, acc.y);
+                            acc.z = __fmaf_rn(yw.z, t2.z, acc.z); acc.w = __fmaf_rn(yw.z, t2.w, acc.w);
+                            if (yn > 3) {
+                                const float4 t3 = *reinterpret_cast<const float4*>(hc + yo.w);
+                                acc.x = __fmaf_rn(yw.w, t3.x, acc.x); acc.y = __fmaf_rn(yw.w, t3.y, acc.y);
+                                acc.z = __fmaf_rn(yw.w, t3.z, acc.z); acc.w = __fmaf_rn(yw.w, t3.w, acc.w);
                             }
                         }
-                        if (!fits)   // the row's samples are further apart than a band holds (extreme down-scaling)
-                            acc = k3_row_direct(base, row_stride, yi, yw, s_yn[ph], x1, bin_w, 4 * q, sr, W, swap_rb ? 2 - c : c);
-                        const float v0 = finish(acc.x, c), v1 = finish(acc.y, c), v2 = finish(acc.z, c), v3 = finish(acc.w, c);
-                        OutT* q4 = dk + (long long)c * total + ph * PW + 4 * q;
+                        const float v0 = __fmaf_rn(acc.x, fa[c], fb[c]), v1 = __fmaf_rn(acc.y, fa[c], fb[c]);
+                        const float v2 = __fmaf_rn(acc.z, fa[c], fb[c]), v3 = __fmaf_rn(acc.w, fa[c], fb[c]);
+                        OutT* q4 = qrow + c * total;
                         if (sizeof(OutT) == 2) {
                             const __nv_bfloat162 p0 = __floats2bfloat162_rn(v0, v1), p1 = __floats2bfloat162_rn(v2, v3);
                             *reinterpret_cast<uint2*>(q4) = make_uint2(*reinterpret_cast<const unsigned*>(&p0),
@@ -656,7 +659,7 @@ k3_roi_tma(const uint8_t* __restrict__ imgs, int n, int H, int W, long long img_
                     }
                 }
             }
-            __syncthreads();                                 // Hs free for the next band
+            __syncthreads();                                 // Hs and Fb free for the next band
             pa = npa; pb = npb; r_lo = nr_lo; r_hi = nr_hi;
         }
     }
@@ -679,9 +682,10 @@ extern "C" int qc_roi_align_rows(qc_ctx* ctx, const uint8_t* imgs, int n, int h,
     const int total = out_h * out_w;
     if (sampling_ratio >= 1 && sampling_ratio <= 2 && (out_w & 3) == 0 && out_w <= K3T_THREADS && out_h <= K3T_PH_MAX &&
         K3T_THREADS / (out_w >> 2) >= 1 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0 && h <= 32767) {
-        const size_t smem = (((size_t)K3T_ROWS * 3 * out_w * 4 + 127) & ~(size_t)127) + K3T_RAW;
+        const size_t smem = (size_t)K3T_ROWS * 3 * out_w * 4 + (size_t)K3T_RAW * 4 + K3T_RAW;
         // 1-D TMA bulk copies need 16-byte aligned global addresses: frame base, image pitch and row pitch
-        const int tma_ok = ((reinterpret_cast<uintptr_t>(imgs) & 15) == 0 && (img_stride & 15) == 0 && (row_stride & 15) == 0) ? 1 : 0;
+        const int tma_ok = ((reinterpret_cast<uintptr_t>(imgs) & 15) == 0 && (img_stride & 15) == 0 && (row_stride & 15) == 0 &&
+                            !getenv("QC_K3_NOTMA")) ? 1 : 0;      // (debug switch: plain-load staging)
         int occ = 1;
         const int grid = std::min(K, ctx->sm_count * 8);
         if (out_dtype == QC_DT_BF16) {
