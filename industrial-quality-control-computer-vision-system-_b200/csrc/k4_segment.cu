@@ -80,7 +80,7 @@ SegWs carve(void* base, const qc_seg_params* p, int method = QC_SEG_COMPOSITE) {
     w.hist = (unsigned*)(b + take(R * 256 * 4));
     w.cmp = (int*)(b + take(R * 2 * 4));
     // (+64: ld16_any and the K7 tiles may read a few bytes past the last region)
-    w.gray = (uint8_t*)(b + take(p->channels == 3 ? (size_t)p->total_pixels + 64 : 0));
+    w.gray = (uint8_t*)(b + take((p->channels == 3 || method != QC_SEG_COMPOSITE) ? (size_t)p->total_pixels + 64 : 0));
     w.bits = (unsigned*)(b + take((size_t)p->total_bits_words * 4));
     w.parent = (int*)(b + take((size_t)p->total_blocks * 4));
     w.rank = (int*)(b + take((size_t)p->total_blocks * 4));
@@ -1356,7 +1356,11 @@ int seg_run(qc_ctx* ctx, int method, const uint8_t* imgs, const qc_seg_params* p
     if (p->channels == 3) {
         k4_gray<<<std::min(p->total_bands, sms * 8), K4_THREADS, 0, st>>>(im, regions, R, p->total_bands, w.band_off, w.gray);
         QC_LAUNCHED(ctx);
+    } else if (method != QC_SEG_COMPOSITE) {
+        k7_pack_gray<<<std::min(p->total_bands, sms * 8), K4_THREADS, 0, st>>>(im, regions, R, p->total_bands, w.band_off, w.gray);
+        QC_LAUNCHED(ctx);
     }
+    const uint8_t* gray7 = w.gray;          // K7 reads the region-packed gray copy whatever the input layout
 
     if (method == QC_SEG_COMPOSITE) {
         if (int rc = qc_prepare(ctx, k4_hist, K4_HIST_SMEM, K4_HIST_THREADS, nullptr)) return rc;
@@ -1379,14 +1383,21 @@ int seg_run(qc_ctx* ctx, int method, const uint8_t* imgs, const qc_seg_params* p
         if (bmax > ad.max_block || bmax > ad.pitch)
             QC_FAIL(ctx, QC_ERR_INVALID, "%s: kernel table covers block <= %d, regions need %d", fn, ad.max_block, bmax);
         const int pmax = bmax / 2;
-        const size_t smem_ad = (size_t)((2 * pmax + 1 + 3) & ~3) * 4 + (size_t)(32 + 2 * pmax) * 33 * 4 +
-                               (size_t)(32 + 2 * pmax) * (32 + 2 * pmax);
-        if ((long long)smem_ad + (K4_LOC_MAX + 1) * 4 + 1024 > ctx->max_smem_optin)
-            QC_FAIL(ctx, QC_ERR_UNSUPPORTED, "%s: adaptive block %d needs %zu B of shared memory", fn, bmax, smem_ad);
-        if (int rc = qc_prepare(ctx, k7_adaptive, (int)smem_ad, K4_THREADS, &occ)) return rc;
-        k7_adaptive<<<std::min(p->total_bands, sms * std::max(occ, 1)), K4_THREADS, smem_ad, st>>>(
-            im, regions, R, p->total_bands, w.band_off, w.gray, ad.akern, ad.pitch, ad.c, w.bits2, pmax);
+        // blocks up to 33: the register sliding-window kernel; larger blocks (ROIs with a short side >= 340 px): the
+        // generic tile kernel, launched only when the region table can hold such a region
+        k7_adaptive_small<<<band_grid, K4_THREADS, 0, st>>>(im, regions, R, p->total_bands, w.band_off, gray7, ad.akern,
+                                                            ad.pitch, ad.c, w.bits2);
         QC_LAUNCHED(ctx);
+        if (pmax > K7A_P) {
+            const size_t smem_ad = (size_t)((2 * pmax + 1 + 3) & ~3) * 4 + (size_t)(32 + 2 * pmax) * 33 * 4 +
+                                   (size_t)(32 + 2 * pmax) * (32 + 2 * pmax);
+            if ((long long)smem_ad + (K4_LOC_MAX + 1) * 4 + 1024 > ctx->max_smem_optin)
+                QC_FAIL(ctx, QC_ERR_UNSUPPORTED, "%s: adaptive block %d needs %zu B of shared memory", fn, bmax, smem_ad);
+            if (int rc = qc_prepare(ctx, k7_adaptive, (int)smem_ad, K4_THREADS, &occ)) return rc;
+            k7_adaptive<<<std::min(p->total_bands, sms * std::max(occ, 1)), K4_THREADS, smem_ad, st>>>(
+                im, regions, R, p->total_bands, w.band_off, gray7, ad.akern, ad.pitch, ad.c, w.bits2, pmax, K7A_P);
+            QC_LAUNCHED(ctx);
+        }
         k7_block_out<<<(R + 255) / 256, 256, 0, st>>>(regions, R, o.thr, (long long*)o.sums);
         QC_LAUNCHED(ctx);
         if (int rc = morph(w.bits2, w.bits)) return rc;
@@ -1397,7 +1408,7 @@ int seg_run(qc_ctx* ctx, int method, const uint8_t* imgs, const qc_seg_params* p
     // QC_SEG_REF_THRESHOLD
     k7_init<<<std::max(1, std::min(sms, (R * 4 + 255) / 256)), 256, 0, st>>>(R, w.minmax, (long long*)o.sums);
     QC_LAUNCHED(ctx);
-    k7_blur<<<band_grid, K4_THREADS, 0, st>>>(im, regions, R, p->total_bands, w.band_off, w.gray, w.blurred, w.minmax);
+    k7_blur<<<band_grid, K4_THREADS, 0, st>>>(im, regions, R, p->total_bands, w.band_off, gray7, w.blurred, w.minmax);
     QC_LAUNCHED(ctx);
     k7_hist<<<band_grid, K4_THREADS, 0, st>>>(regions, R, p->total_bands, w.band_off, w.blurred, w.minmax, w.hist);
     QC_LAUNCHED(ctx);
@@ -1411,10 +1422,13 @@ int seg_run(qc_ctx* ctx, int method, const uint8_t* imgs, const qc_seg_params* p
     QC_LAUNCHED(ctx);
     k7_filter<<<band_grid, K4_THREADS, 0, st>>>(regions, R, p->total_bands, w.band_off, w.bits, w.parent, w.rank, w.bits2);
     QC_LAUNCHED(ctx);
-    k7_fill<<<std::min(R, sms * 4), K7_FILL_THREADS, 0, st>>>(regions, R, w.bits2, w.bits3);
+    if (int rc = qc_prepare(ctx, k7_fill, K7_FILL_SMEM_WORDS * 4, K7_FILL_THREADS, &occ)) return rc;
+    // (regions too large for shared memory flood in place in bits3, with their free rows parked in bits -- free until
+    // the morphology pass rewrites it)
+    k7_fill<<<std::min(R, sms * std::max(occ, 1)), K7_FILL_THREADS, K7_FILL_SMEM_WORDS * 4, st>>>(regions, R, w.bits2, w.bits3, w.bits);
     QC_LAUNCHED(ctx);
     if (int rc = morph(w.bits3, w.bits)) return rc;
-    k7_emit<<<band_grid, K4_THREADS, 0, st>>>(im, regions, R, p->total_bands, w.band_off, w.gray, w.bits, o.mask, o.labels,
+    k7_emit<<<band_grid, K4_THREADS, 0, st>>>(im, regions, R, p->total_bands, w.band_off, gray7, w.bits, o.mask, o.labels,
                                               o.stats, (long long*)o.area, (long long*)o.sums);
     QC_LAUNCHED(ctx);
     k7_finish<<<(R + 255) / 256, 256, 0, st>>>(regions, R, o.stats, (const long long*)o.area, o.ncomp, (long long*)o.sums);

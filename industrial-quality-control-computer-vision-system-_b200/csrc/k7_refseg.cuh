@@ -44,7 +44,7 @@ struct K7Gray {
 };
 __device__ __forceinline__ K7Gray k7_gray_of(const Img& im, const qc_seg_region& rg, const uint8_t* gray_ws) {
     K7Gray g;
-    if (im.channels == 3) { g.base = gray_ws + rg.out_offset; g.pitch = rg.w; }
+    if (im.channels == 3 || gray_ws) { g.base = gray_ws + rg.out_offset; g.pitch = rg.w; }   // region-packed gray copy
     else { g.base = im.data + (long long)rg.img * im.img_stride + (long long)rg.y * im.row_stride + rg.x; g.pitch = im.row_stride; }
     return g;
 }
@@ -54,6 +54,25 @@ struct K7Scalars {
     unsigned long long* minmax;   // [R][2] bit patterns of the (non-negative) float64 min / max
     double* thr_adj;              // [R] threshold x class factor
 };
+
+// gray input: region-packed copy of every ROI (the K7 kernels then stream contiguous, padded rows)
+__global__ void __launch_bounds__(K4_THREADS)
+k7_pack_gray(Img im, const qc_seg_region* __restrict__ regs, int R, int total_bands, const int* __restrict__ g_band_off,
+             uint8_t* __restrict__ gray_ws) {
+    __shared__ int s_off[K4_LOC_MAX + 1];
+    const int* off = loc_load(s_off, g_band_off, R);
+    for (int t = blockIdx.x; t < total_bands; t += gridDim.x) {
+        const qc_seg_region rg = regs[loc_find(off, R, t)];
+        const int BR = k4_band_rows(rg.w);
+        const int y0 = (t - rg.band_offset) * BR, y1 = min(y0 + BR, rg.h);
+        const uint8_t* src = im.data + (long long)rg.img * im.img_stride + (long long)rg.y * im.row_stride + rg.x;
+        const int n = (y1 - y0) * rg.w;
+        for (int i = threadIdx.x; i < n; i += K4_THREADS) {
+            const int yy = i / rg.w, x = i - yy * rg.w;
+            gray_ws[rg.out_offset + (long long)(y0 + yy) * rg.w + x] = __ldg(src + (long long)(y0 + yy) * im.row_stride + x);
+        }
+    }
+}
 
 __global__ void k7_init(int R, unsigned long long* __restrict__ minmax, long long* __restrict__ sums) {
     const int gid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
@@ -139,9 +158,11 @@ k7_hist(const qc_seg_region* __restrict__ regs, int R, int total_bands, const in
         const double* __restrict__ blurred, const unsigned long long* __restrict__ minmax,
         unsigned* __restrict__ hist) {
     __shared__ unsigned s_h[256];
+    __shared__ double s_e[257];
     __shared__ int s_off[K4_LOC_MAX + 1];
     const int tid = threadIdx.x;
     const int* off = loc_load(s_off, g_band_off, R);
+    int cur_r = -1;
     for (int t = blockIdx.x; t < total_bands; t += gridDim.x) {
         const int r = loc_find(off, R, t);
         const qc_seg_region rg = regs[r];
@@ -152,19 +173,37 @@ k7_hist(const qc_seg_region* __restrict__ regs, int R, int total_bands, const in
         const int y0 = (t - rg.band_offset) * BR, y1 = min(y0 + BR, rg.h);
         __syncthreads();
         s_h[tid] = 0;
+        if (r != cur_r) {                                  // np.linspace(first, last, 257)
+            const double step = __ddiv_rn(__dsub_rn(last, first), 256.0);
+            for (int i = tid; i < 257; i += K4_THREADS) s_e[i] = k7_edge(i, first, last, step);
+            cur_r = r;
+        }
         __syncthreads();
-        const double denom = __dsub_rn(last, first), step = __ddiv_rn(denom, 256.0);
+        // numpy's bin of x is fixed by the comparisons against the edges (its multiplicative estimate is only ever
+        // corrected by one step down / up); any estimate within a bin of the truth followed by the same corrective
+        // comparisons lands in the same bin
+        const double scale = 256.0 / (last - first);
         const double* p = blurred + rg.out_offset + (long long)y0 * rg.w;
         const int n = (y1 - y0) * rg.w;
-        for (int i = tid; i < n; i += K4_THREADS) {
-            const double x = p[i];
-            // numpy: f_indices = ((a - first) / norm_denom) * n_bins; astype(intp); == n_bins -> -1;
-            // then one corrective step down / up against the linspace edges
-            int idx = (int)__dmul_rn(__ddiv_rn(__dsub_rn(x, first), denom), 256.0);
-            if (idx == 256) idx = 255;
-            if (x < k7_edge(idx, first, last, step)) idx -= 1;
-            if (idx != 255 && x >= k7_edge(idx + 1, first, last, step)) idx += 1;
-            atomicAdd(&s_h[idx], 1u);
+        for (int i0 = 0; i0 < n; i0 += K4_THREADS) {
+            const int i = i0 + tid;
+            int idx = -1;
+            if (i < n) {
+                const double x = p[i];
+                idx = min(max((int)((x - first) * scale), 0), 255);
+                while (idx > 0 && x < s_e[idx]) idx -= 1;
+                while (idx < 255 && x >= s_e[idx + 1]) idx += 1;
+            }
+            // neighbouring pixels of a blurred image mostly share a bin: one shared-memory atomic per run of equal
+            // bins inside the warp instead of one per pixel
+            const int lane = tid & 31;
+            const int prev = __shfl_up_sync(0xffffffffu, idx, 1);
+            const unsigned heads = __ballot_sync(0xffffffffu, lane == 0 || idx != prev);
+            if (idx >= 0 && ((heads >> lane) & 1u)) {
+                const unsigned rest = lane == 31 ? 0u : (heads >> (lane + 1));
+                const int len = rest ? __ffs(rest) : 32 - lane;
+                atomicAdd(&s_h[idx], (unsigned)len);
+            }
         }
         __syncthreads();
         if (s_h[tid]) atomicAdd(&hist[(long long)r * 256 + tid], s_h[tid]);
@@ -253,16 +292,27 @@ k7_cmp(const qc_seg_region* __restrict__ regs, int R, int total_bands, const int
         const int y0 = (t - rg.band_offset) * BR, y1 = min(y0 + BR, rg.h);
         const double T = thr_adj[r];
         const int items = (y1 - y0) * wpr;
-        for (int it = warp; it < items; it += K4_THREADS / 32) {
-            const int yy = it / wpr, wx = it - yy * wpr;
-            const int y = y0 + yy, x = wx * 32 + lane;
-            bool fg = false;
-            if (x < rg.w) {
-                const double v = blurred[rg.out_offset + (long long)y * rg.w + x];
-                fg = rg.polarity ? (v > T) : (v < T);
+        // a warp turns four 32-pixel words per step (four independent loads in flight per lane)
+        for (int it0 = warp * 4; it0 < items; it0 += (K4_THREADS / 32) * 4) {
+            double v[4];
+            bool ok[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int it = it0 + j;
+                const int yy = it / wpr, wx = it - yy * wpr;
+                const int x = wx * 32 + lane;
+                ok[j] = it < items && x < rg.w;
+                v[j] = ok[j] ? blurred[rg.out_offset + (long long)(y0 + yy) * rg.w + x] : 0.0;
             }
-            const unsigned word = __ballot_sync(0xffffffffu, fg);
-            if (lane == 0) bits[rg.bits_offset + (long long)y * wpr + wx] = word;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int it = it0 + j;
+                if (it >= items) break;                    // warp-uniform
+                const bool fg = ok[j] && (rg.polarity ? (v[j] > T) : (v[j] < T));
+                const unsigned word = __ballot_sync(0xffffffffu, fg);
+                const int yy = it / wpr, wx = it - yy * wpr;
+                if (lane == 0) bits[rg.bits_offset + (long long)(y0 + yy) * wpr + wx] = word;
+            }
         }
     }
 }
@@ -287,7 +337,7 @@ __global__ void k7_block_out(const qc_seg_region* __restrict__ regs, int R, int*
 __global__ void __launch_bounds__(K4_THREADS)
 k7_adaptive(Img im, const qc_seg_region* __restrict__ regs, int R, int total_bands,
             const int* __restrict__ g_band_off, const uint8_t* __restrict__ gray_ws, const float* __restrict__ akern,
-            int akern_pitch, int adaptive_c, unsigned* __restrict__ bits, int pmax) {
+            int akern_pitch, int adaptive_c, unsigned* __restrict__ bits, int pmax, int p_skip) {
     extern __shared__ __align__(16) unsigned char k7sm[];
     // layout: float kern[2*pmax+1 rounded up to 4] | float rp[(32+2*pmax)][33] | uint8 src[(32+2*pmax)][(32+2*pmax)]
     const int kmax = (2 * pmax + 1 + 3) & ~3;
@@ -305,6 +355,7 @@ k7_adaptive(Img im, const qc_seg_region* __restrict__ regs, int R, int total_ban
         const int y0 = (t - rg.band_offset) * BR, y1 = min(y0 + BR, rg.h);
         const K7Gray g = k7_gray_of(im, rg, gray_ws);
         const int bs = k7_block_size(rg.w, rg.h), p = bs >> 1;
+        if (p <= p_skip) continue;                      // small blocks: k7_adaptive_small
         const int sw = 32 + 2 * p;
         const int c0 = rg.w & ~7;                       // columns below: both passes fused (cv2's 8-lane vectors)
         const int c1 = c0 + (((rg.w - c0) >> 2) << 2);  // [c0, c1): row pass fused, column pass unfused; then unfused
@@ -355,6 +406,145 @@ k7_adaptive(Img im, const qc_seg_region* __restrict__ regs, int R, int total_ban
                     }
                     const unsigned word = __ballot_sync(0xffffffffu, fg);
                     if (lane == 0 && y < yend) bits[rg.bits_offset + (long long)y * wpr + (tx >> 5)] = word;
+                }
+            }
+        }
+    }
+}
+
+
+// Blocks up to 33 (every ROI whose short side is below 340 px): 32 x 32 tiles with the source tile held as FLOAT
+// (replicate border materialised on both axes), register sliding windows in both passes -- a thread produces 4
+// adjacent outputs along the filter axis, so every staged value is loaded once per 4 outputs -- and the kernel padded
+// with zero taps to a multiple of 4 (fma(x, 0, s) == s, so cv2's sequential sums are reproduced bit for bit).
+constexpr int K7A_P = 16;                    // largest half-block of this path
+constexpr int K7A_FP = 68;                   // float pitch of the source tile (32 + 2*16 + 4)
+constexpr int K7A_ROWS = 32 + 2 * K7A_P;     // source / row-pass rows of a tile
+__global__ void __launch_bounds__(K4_THREADS)
+k7_adaptive_small(Img im, const qc_seg_region* __restrict__ regs, int R, int total_bands,
+                  const int* __restrict__ g_band_off, const uint8_t* __restrict__ gray_ws,
+                  const float* __restrict__ akern, int akern_pitch, int adaptive_c, unsigned* __restrict__ bits) {
+    __shared__ __align__(16) float s_f[K7A_ROWS * K7A_FP + 16];        // source tile, virtual rows ty-p .. ty+31+p
+    __shared__ __align__(16) float s_rp[(K7A_ROWS + 8) * 33];          // row-pass results, 4 zeroed pad rows on each side
+    __shared__ __align__(16) float s_k[40], s_kc[24];                   // taps (zero padded), centre + lower half taps
+    __shared__ int s_off[K4_LOC_MAX + 1];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int* off = loc_load(s_off, g_band_off, R);
+    for (int i = tid; i < (K7A_ROWS + 8) * 33; i += K4_THREADS) s_rp[i] = 0.f;
+    for (int i = tid; i < K7A_ROWS * K7A_FP + 16; i += K4_THREADS) s_f[i] = 0.f;
+    float* const rp = s_rp + 4 * 33;                                     // virtual row 0
+    for (int t = blockIdx.x; t < total_bands; t += gridDim.x) {
+        const int r = loc_find(off, R, t);
+        const qc_seg_region rg = regs[r];
+        const int bs = k7_block_size(rg.w, rg.h), p = bs >> 1;
+        if (p > K7A_P) continue;                                         // large blocks: k7_adaptive
+        const int wpr = wpr_of(rg);
+        const int BR = k4_band_rows(rg.w);
+        const int y0 = (t - rg.band_offset) * BR, y1 = min(y0 + BR, rg.h);
+        const K7Gray g = k7_gray_of(im, rg, gray_ws);
+        const int sw = 32 + 2 * p;
+        const int c0 = rg.w & ~7;                       // columns below: both passes fused (cv2's 8-lane vectors)
+        const int c1 = c0 + (((rg.w - c0) >> 2) << 2);  // [c0, c1): row pass fused, column pass unfused; then unfused
+        const int nk4 = (bs + 3) >> 2, np4 = (p + 3) >> 2;
+        __syncthreads();
+        if (tid < 40) s_k[tid] = tid < bs ? akern[(long long)((bs - 11) >> 1) * akern_pitch + tid] : 0.f;
+        if (tid < 24) s_kc[tid] = tid <= p ? akern[(long long)((bs - 11) >> 1) * akern_pitch + p + tid] : 0.f;
+        for (int ty = y0; ty < y1; ty += 32) {
+            const int yend = min(ty + 32, y1);
+            const int nvr = (yend - ty) + 2 * p;                         // virtual rows ty-p .. yend-1+p
+            for (int tx = 0; tx < rg.w; tx += 32) {
+                __syncthreads();
+                // ---- stage: float source tile, both borders replicated; 4 columns per thread-step
+                const int q4 = (sw + 3) >> 2;
+                for (int i = tid; i < nvr * q4; i += K4_THREADS) {
+                    const int vr = i / q4, cq = i - vr * q4;
+                    const int yy = min(max(ty - p + vr, 0), rg.h - 1);
+                    const uint8_t* gr = g.base + (long long)yy * g.pitch;
+                    const int xb = tx - p + 4 * cq;
+                    float4 v;
+                    v.x = (float)gr[min(max(xb, 0), rg.w - 1)];
+                    v.y = (float)gr[min(max(xb + 1, 0), rg.w - 1)];
+                    v.z = (float)gr[min(max(xb + 2, 0), rg.w - 1)];
+                    v.w = (float)gr[min(max(xb + 3, 0), rg.w - 1)];
+                    *reinterpret_cast<float4*>(s_f + vr * K7A_FP + 4 * cq) = v;
+                }
+                __syncthreads();
+                // ---- row pass: thread = (virtual row, 4 adjacent columns); sequential sum over the taps (cv2's order)
+                for (int i = tid; i < nvr * 8; i += K4_THREADS) {
+                    const int vr = i >> 3, q = i & 7;
+                    const float* fp = s_f + vr * K7A_FP + 4 * q;
+                    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+                    float4 cur = *reinterpret_cast<const float4*>(fp);
+                    if (tx + 4 * q < c1) {
+                        for (int t4 = 0; t4 < nk4; ++t4) {
+                            const float4 nx = *reinterpret_cast<const float4*>(fp + 4 * t4 + 4);
+                            const float4 k = *reinterpret_cast<const float4*>(s_k + 4 * t4);
+                            a0 = __fmaf_rn(cur.x, k.x, a0); a1 = __fmaf_rn(cur.y, k.x, a1); a2 = __fmaf_rn(cur.z, k.x, a2); a3 = __fmaf_rn(cur.w, k.x, a3);
+                            a0 = __fmaf_rn(cur.y, k.y, a0); a1 = __fmaf_rn(cur.z, k.y, a1); a2 = __fmaf_rn(cur.w, k.y, a2); a3 = __fmaf_rn(nx.x, k.y, a3);
+                            a0 = __fmaf_rn(cur.z, k.z, a0); a1 = __fmaf_rn(cur.w, k.z, a1); a2 = __fmaf_rn(nx.x, k.z, a2); a3 = __fmaf_rn(nx.y, k.z, a3);
+                            a0 = __fmaf_rn(cur.w, k.w, a0); a1 = __fmaf_rn(nx.x, k.w, a1); a2 = __fmaf_rn(nx.y, k.w, a2); a3 = __fmaf_rn(nx.z, k.w, a3);
+                            cur = nx;
+                        }
+                    } else {
+                        for (int t4 = 0; t4 < nk4; ++t4) {
+                            const float4 nx = *reinterpret_cast<const float4*>(fp + 4 * t4 + 4);
+                            const float4 k = *reinterpret_cast<const float4*>(s_k + 4 * t4);
+#define K7_MA(acc, x, kk) acc = __fadd_rn(acc, __fmul_rn(x, kk))
+                            K7_MA(a0, cur.x, k.x); K7_MA(a1, cur.y, k.x); K7_MA(a2, cur.z, k.x); K7_MA(a3, cur.w, k.x);
+                            K7_MA(a0, cur.y, k.y); K7_MA(a1, cur.z, k.y); K7_MA(a2, cur.w, k.y); K7_MA(a3, nx.x, k.y);
+                            K7_MA(a0, cur.z, k.z); K7_MA(a1, cur.w, k.z); K7_MA(a2, nx.x, k.z); K7_MA(a3, nx.y, k.z);
+                            K7_MA(a0, cur.w, k.w); K7_MA(a1, nx.x, k.w); K7_MA(a2, nx.y, k.w); K7_MA(a3, nx.z, k.w);
+                            cur = nx;
+                        }
+                    }
+                    float* o = rp + vr * 33 + 4 * q;
+                    o[0] = a0; o[1] = a1; o[2] = a2; o[3] = a3;
+                }
+                __syncthreads();
+                // ---- column pass: thread = (column, 4 adjacent rows), symmetric pairs outwards (cv2's order)
+                {
+                    const int c = lane, vb = 4 * warp + p;                 // virtual row of the thread's first output
+                    const float* cp = rp + c;
+                    float u0 = cp[vb * 33], u1 = cp[(vb + 1) * 33], u2 = cp[(vb + 2) * 33], u3 = cp[(vb + 3) * 33];
+                    float d0 = u0, d1 = u1, d2 = u2;                            // (row vb+3-tb is never a down tap)
+                    const float kc = s_kc[0];
+                    float a0 = __fmul_rn(u0, kc), a1 = __fmul_rn(u1, kc), a2 = __fmul_rn(u2, kc), a3 = __fmul_rn(u3, kc);
+                    const bool fused = tx + c < c0;
+                    for (int t4 = 0; t4 < np4; ++t4) {
+                        const int tb = 4 * t4;
+                        const float4 k = make_float4(s_kc[tb + 1], s_kc[tb + 2], s_kc[tb + 3], s_kc[tb + 4]);
+                        // taps t = tb+1 .. tb+4: the up window slides down one row per tap, the down window up
+                        const float n0 = cp[(vb + 4 + tb) * 33], n1 = cp[(vb + 5 + tb) * 33], n2 = cp[(vb + 6 + tb) * 33], n3 = cp[(vb + 7 + tb) * 33];
+                        const float m0 = cp[(vb - 1 - tb) * 33], m1 = cp[(vb - 2 - tb) * 33], m2 = cp[(vb - 3 - tb) * 33], m3 = cp[(vb - 4 - tb) * 33];
+                        if (fused) {
+#define K7_CF(acc, a, b, kk) acc = __fmaf_rn(__fadd_rn(a, b), kk, acc)
+                            K7_CF(a0, u1, m0, k.x); K7_CF(a1, u2, d0, k.x); K7_CF(a2, u3, d1, k.x); K7_CF(a3, n0, d2, k.x);
+                            K7_CF(a0, u2, m1, k.y); K7_CF(a1, u3, m0, k.y); K7_CF(a2, n0, d0, k.y); K7_CF(a3, n1, d1, k.y);
+                            K7_CF(a0, u3, m2, k.z); K7_CF(a1, n0, m1, k.z); K7_CF(a2, n1, m0, k.z); K7_CF(a3, n2, d0, k.z);
+                            K7_CF(a0, n0, m3, k.w); K7_CF(a1, n1, m2, k.w); K7_CF(a2, n2, m1, k.w); K7_CF(a3, n3, m0, k.w);
+                        } else {
+#define K7_CU(acc, a, b, kk) acc = __fadd_rn(acc, __fmul_rn(kk, __fadd_rn(a, b)))
+                            K7_CU(a0, u1, m0, k.x); K7_CU(a1, u2, d0, k.x); K7_CU(a2, u3, d1, k.x); K7_CU(a3, n0, d2, k.x);
+                            K7_CU(a0, u2, m1, k.y); K7_CU(a1, u3, m0, k.y); K7_CU(a2, n0, d0, k.y); K7_CU(a3, n1, d1, k.y);
+                            K7_CU(a0, u3, m2, k.z); K7_CU(a1, n0, m1, k.z); K7_CU(a2, n1, m0, k.z); K7_CU(a3, n2, d0, k.z);
+                            K7_CU(a0, n0, m3, k.w); K7_CU(a1, n1, m2, k.w); K7_CU(a2, n2, m1, k.w); K7_CU(a3, n3, m0, k.w);
+                        }
+                        u0 = n0; u1 = n1; u2 = n2; u3 = n3;                // rows vb+4+tb .. vb+7+tb
+                        d2 = m1; d1 = m2; d0 = m3;                         // rows vb-4-tb .. vb-2-tb
+                    }
+                    const float acc[4] = {a0, a1, a2, a3};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int y = ty + 4 * warp + j, x = tx + c;
+                        bool fg = false;
+                        if (y < yend && x < rg.w) {
+                            const int mean = min(max(__float2int_rn(acc[j]), 0), 255);     // cvRound + saturate_cast<uchar>
+                            const int d = (int)s_f[(4 * warp + j + p) * K7A_FP + c + p] - mean;
+                            fg = rg.polarity ? (d > -adaptive_c) : (d <= -adaptive_c);
+                        }
+                        const unsigned word = __ballot_sync(0xffffffffu, fg);
+                        if (lane == 0 && y < yend) bits[rg.bits_offset + (long long)y * wpr + (tx >> 5)] = word;
+                    }
                 }
             }
         }
@@ -450,81 +640,93 @@ __device__ __forceinline__ unsigned k7_hfill(unsigned m, unsigned s) {
 }
 
 constexpr int K7_FILL_THREADS = 512;
+constexpr int K7_FILL_SMEM_WORDS = 12 * 1024;          // 48 KB: free + outside bit rows of a region up to ~196 K pixels
+
+// one region; F = free (background) bit rows, O = outside bit rows, both [h][wpr] in shared or global memory
+__device__ __forceinline__ void k7_fill_region(const unsigned* F, volatile unsigned* O, int h, int wpr, int tid) {
+    const int lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = K7_FILL_THREADS / 32;
+    const int S = max(8, (h + NW - 1) / NW);              // rows per strip
+    const int nstrips = (h + S - 1) / S;
+    const int nch = (wpr + 31) >> 5;
+    for (;;) {
+        int changed = 0;
+        for (int st = warp; st < nstrips; st += NW) {
+            const int a = st * S, b = min(a + S, h);
+            for (int dir = 0; dir < 2; ++dir) {
+                for (int k = 0; k < b - a; ++k) {
+                    const int y = dir == 0 ? a + k : b - 1 - k;
+                    const int yn = dir == 0 ? y - 1 : y + 1;              // the row the flood comes from
+                    for (int c = 0; c < nch; ++c) {
+                        const int wx = c * 32 + lane;
+                        const bool valid = wx < wpr;
+                        const unsigned f = valid ? F[y * wpr + wx] : 0u;
+                        const unsigned o = valid ? O[y * wpr + wx] : 0u;
+                        unsigned s = o;
+                        if (valid && yn >= 0 && yn < h) s |= O[yn * wpr + wx] & f;
+                        for (;;) {
+                            s = k7_hfill(f, s);
+                            unsigned l = __shfl_up_sync(0xffffffffu, s, 1) >> 31;
+                            unsigned rt = __shfl_down_sync(0xffffffffu, s, 1) & 1u;
+                            if (lane == 0) l = (valid && wx > 0) ? (O[y * wpr + wx - 1] >> 31) : 0u;
+                            if (lane == 31) rt = (valid && wx + 1 < wpr) ? (O[y * wpr + wx + 1] & 1u) : 0u;
+                            const unsigned ns = s | (f & (l | (rt << 31)));
+                            const bool more = ns != s;
+                            s = ns;
+                            if (!__any_sync(0xffffffffu, more)) break;
+                        }
+                        if (valid && s != o) { O[y * wpr + wx] = s; changed = 1; }
+                        __syncwarp();
+                    }
+                }
+            }
+        }
+        if (!__syncthreads_or(changed)) break;
+    }
+}
+
 __global__ void __launch_bounds__(K7_FILL_THREADS)
 k7_fill(const qc_seg_region* __restrict__ regs, int R, const unsigned* __restrict__ bits_in,
-        unsigned* __restrict__ bits_out) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr int NW = K7_FILL_THREADS / 32;
+        unsigned* __restrict__ bits_out, unsigned* __restrict__ free_ws) {
+    extern __shared__ __align__(16) unsigned k7f_sm[];
+    const int tid = threadIdx.x;
     for (int r = blockIdx.x; r < R; r += gridDim.x) {
         const qc_seg_region rg = regs[r];
-        const int wpr = wpr_of(rg), h = rg.h;
+        const int wpr = wpr_of(rg), h = rg.h, nwords = h * wpr;
         const unsigned tail = (rg.w & 31) ? ((1u << (rg.w & 31)) - 1u) : 0xFFFFFFFFu;   // valid bits of the last word
         const unsigned* B = bits_in + rg.bits_offset;
-        volatile unsigned* O = bits_out + rg.bits_offset;
-        auto freew = [&](int y, int wx) -> unsigned {
-            const unsigned f = ~__ldg(B + (long long)y * wpr + wx);
-            return wx == wpr - 1 ? (f & tail) : f;
-        };
+        unsigned* G = bits_out + rg.bits_offset;
+        const bool in_smem = 2 * nwords <= K7_FILL_SMEM_WORDS;
+        unsigned* F = in_smem ? k7f_sm : free_ws + rg.bits_offset;
+        unsigned* O = in_smem ? k7f_sm + nwords : G;
         __syncthreads();
-        // seeds: the free pixels of the ROI's outer ring
-        for (int i = tid; i < h * wpr; i += K7_FILL_THREADS) {
+        // free pixels; seeds = the free pixels of the ROI's outer ring
+        for (int i = tid; i < nwords; i += K7_FILL_THREADS) {
             const int y = i / wpr, wx = i - y * wpr;
-            const unsigned f = freew(y, wx);
+            unsigned f = ~__ldg(B + i);
+            if (wx == wpr - 1) f &= tail;
             unsigned ring = 0;
             if (y == 0 || y == h - 1) ring = 0xFFFFFFFFu;
             if (wx == 0) ring |= 1u;
             if (wx == wpr - 1) ring |= 1u << ((rg.w - 1) & 31);
+            F[i] = f;
             O[i] = f & ring;
         }
         __syncthreads();
-        const int S = max(8, (h + NW - 1) / NW);              // rows per strip
-        const int nstrips = (h + S - 1) / S;
-        const int nch = (wpr + 31) >> 5;
-        for (;;) {
-            int changed = 0;
-            for (int st = warp; st < nstrips; st += NW) {
-                const int a = st * S, b = min(a + S, h);
-                for (int dir = 0; dir < 2; ++dir) {
-                    for (int k = 0; k < b - a; ++k) {
-                        const int y = dir == 0 ? a + k : b - 1 - k;
-                        const int yn = dir == 0 ? y - 1 : y + 1;              // the row the flood comes from
-                        for (int c = 0; c < nch; ++c) {
-                            const int wx = c * 32 + lane;
-                            const bool valid = wx < wpr;
-                            const unsigned f = valid ? freew(y, wx) : 0u;
-                            const unsigned o = valid ? O[(long long)y * wpr + wx] : 0u;
-                            unsigned s = o;
-                            if (valid && yn >= 0 && yn < h) s |= O[(long long)yn * wpr + wx] & f;
-                            for (;;) {
-                                s = k7_hfill(f, s);
-                                unsigned l = __shfl_up_sync(0xffffffffu, s, 1) >> 31;
-                                unsigned rt = __shfl_down_sync(0xffffffffu, s, 1) & 1u;
-                                if (lane == 0) l = (valid && wx > 0) ? (O[(long long)y * wpr + wx - 1] >> 31) : 0u;
-                                if (lane == 31) rt = (valid && wx + 1 < wpr) ? (O[(long long)y * wpr + wx + 1] & 1u) : 0u;
-                                const unsigned ns = s | (f & (l | (rt << 31)));
-                                const bool more = ns != s;
-                                s = ns;
-                                if (!__any_sync(0xffffffffu, more)) break;
-                            }
-                            if (valid && s != o) { O[(long long)y * wpr + wx] = s; changed = 1; }
-                            __syncwarp();
-                        }
-                    }
-                }
-            }
-            if (!__syncthreads_or(changed)) break;
-        }
+        k7_fill_region(F, O, h, wpr, tid);
         // holes = free pixels the flood never reached: result = ~outside inside the ROI
-        for (int i = tid; i < h * wpr; i += K7_FILL_THREADS) {
+        for (int i = tid; i < nwords; i += K7_FILL_THREADS) {
             const int wx = i % wpr;
             const unsigned o = O[i];
-            O[i] = wx == wpr - 1 ? (~o & tail) : ~o;
+            G[i] = wx == wpr - 1 ? (~o & tail) : ~o;
         }
     }
 }
 
 // ------------------------------------------------------------------------------------------
-// final pass of the threshold method: mask bytes / 0-1 labels, area, extent, confidence sums
+// final pass of the threshold method: mask bytes / 0-1 labels, area, extent, confidence sums.  A thread takes 16
+// pixels: their mask bits, their gray bytes (two aligned 128-bit loads of the region-packed copy) and three byte dot
+// products (dp4a) for sum(gray), sum(gray^2) and sum(gray over the mask).
 __global__ void __launch_bounds__(K4_THREADS)
 k7_emit(Img im, const qc_seg_region* __restrict__ regs, int R, int total_bands, const int* __restrict__ g_band_off,
         const uint8_t* __restrict__ gray_ws, const unsigned* __restrict__ bits, uint8_t* __restrict__ out_mask,
@@ -541,31 +743,49 @@ k7_emit(Img im, const qc_seg_region* __restrict__ regs, int R, int total_bands, 
         const int wpr = wpr_of(rg);
         const int BR = k4_band_rows(rg.w);
         const int y0 = (t - rg.band_offset) * BR, y1 = min(y0 + BR, rg.h);
-        const K7Gray g = k7_gray_of(im, rg, gray_ws);
+        const uint8_t* gbase = gray_ws + rg.out_offset;            // region-packed gray, pitch = w
         const unsigned* B = bits + rg.bits_offset;
-        long long a_fg = 0, s_fg = 0, s_all = 0, s_sq = 0;
+        unsigned a_fg = 0, u_fg = 0, u_all = 0, u_sq = 0;
         int mnx = INT_MAX, mny = INT_MAX, mxx = -1, mxy = -1;
-        const int n = (y1 - y0) * rg.w;
-        for (int i = tid; i < n; i += K4_THREADS) {
-            const int yy = i / rg.w, x = i - yy * rg.w, y = y0 + yy;
-            const unsigned bit = (__ldg(B + (long long)y * wpr + (x >> 5)) >> (x & 31)) & 1u;
-            const long long o = rg.out_offset + (long long)y * rg.w + x;
-            if (out_mask) out_mask[o] = bit ? 255 : 0;
-            if (out_labels) out_labels[o] = (int)bit;
+        const int segs = (rg.w + 15) >> 4;
+        const int items = (y1 - y0) * segs;
+        for (int it = tid; it < items; it += K4_THREADS) {
+            const int yy = it / segs, sg = it - yy * segs, y = y0 + yy, x0 = sg * 16;
+            const int nv = min(16, rg.w - x0);
+            unsigned b16 = (__ldg(B + (long long)y * wpr + (x0 >> 5)) >> (x0 & 31)) & 0xFFFFu;
+            if (nv < 16) b16 &= (1u << nv) - 1u;
             if (sums) {
-                const int v = g.base[(long long)y * g.pitch + x];
-                s_all += v;
-                s_sq += v * v;
-                if (bit) s_fg += v;
+                const uint4 gv = ld16_any(gbase + (long long)y * rg.w + x0);
+                const unsigned gw[4] = {gv.x, gv.y, gv.z, gv.w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int left = nv - 4 * q;                   // valid bytes of this word
+                    if (left <= 0) break;
+                    const unsigned wv = left >= 4 ? gw[q] : (gw[q] & ((1u << (8 * left)) - 1u));
+                    const unsigned m4 = (((b16 >> (4 * q)) & 15u) * 0x00204081u) & 0x01010101u;   // mask bits -> 0/1 bytes
+                    u_all = __dp4a(wv, 0x01010101u, u_all);
+                    u_sq = __dp4a(wv, wv, u_sq);
+                    u_fg = __dp4a(wv, m4, u_fg);
+                }
             }
-            if (bit) {
-                a_fg += 1;
-                mnx = min(mnx, x); mxx = max(mxx, x); mny = min(mny, y); mxy = max(mxy, y);
+            if (b16) {
+                a_fg += __popc(b16);
+                mnx = min(mnx, x0 + __ffs(b16) - 1); mxx = max(mxx, x0 + 31 - __clz(b16));
+                mny = min(mny, y); mxy = max(mxy, y);
+            }
+            if (out_mask || out_labels) {
+                const long long o = rg.out_offset + (long long)y * rg.w + x0;
+                for (int j = 0; j < nv; ++j) {
+                    const unsigned bit = (b16 >> j) & 1u;
+                    if (out_mask) out_mask[o + j] = bit ? 255 : 0;
+                    if (out_labels) out_labels[o + j] = (int)bit;
+                }
             }
         }
+        long long l_fg = a_fg, s_fg = u_fg, s_all = u_all, s_sq = u_sq;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
-            a_fg += __shfl_xor_sync(0xffffffffu, a_fg, o);
+            l_fg += __shfl_xor_sync(0xffffffffu, l_fg, o);
             s_fg += __shfl_xor_sync(0xffffffffu, s_fg, o);
             s_all += __shfl_xor_sync(0xffffffffu, s_all, o);
             s_sq += __shfl_xor_sync(0xffffffffu, s_sq, o);
@@ -576,23 +796,23 @@ k7_emit(Img im, const qc_seg_region* __restrict__ regs, int R, int total_bands, 
         }
         __syncthreads();
         if (lane == 0) {
-            s_acc[warp][0] = a_fg; s_acc[warp][1] = s_fg; s_acc[warp][2] = s_all; s_acc[warp][3] = s_sq;
+            s_acc[warp][0] = l_fg; s_acc[warp][1] = s_fg; s_acc[warp][2] = s_all; s_acc[warp][3] = s_sq;
             s_ext[warp][0] = mnx; s_ext[warp][1] = mny; s_ext[warp][2] = mxx; s_ext[warp][3] = mxy;
         }
         __syncthreads();
         if (tid == 0) {
             for (int k = 1; k < K4_THREADS / 32; ++k) {
-                a_fg += s_acc[k][0]; s_fg += s_acc[k][1]; s_all += s_acc[k][2]; s_sq += s_acc[k][3];
+                l_fg += s_acc[k][0]; s_fg += s_acc[k][1]; s_all += s_acc[k][2]; s_sq += s_acc[k][3];
                 mnx = min(mnx, s_ext[k][0]); mny = min(mny, s_ext[k][1]);
                 mxx = max(mxx, s_ext[k][2]); mxy = max(mxy, s_ext[k][3]);
             }
             typedef unsigned long long ull;
-            if (a_fg) {
-                atomicAdd(reinterpret_cast<ull*>(out_area + r), (ull)a_fg);
+            if (l_fg) {
+                atomicAdd(reinterpret_cast<ull*>(out_area + r), (ull)l_fg);
                 if (rg.max_comp > 1) {
                     int* s = stats + ((long long)rg.stats_offset + 1) * 5;
                     atomicMin(s + 0, mnx); atomicMin(s + 1, mny); atomicMax(s + 2, mxx); atomicMax(s + 3, mxy);
-                    atomicAdd(s + 4, (int)a_fg);
+                    atomicAdd(s + 4, (int)l_fg);
                 }
             }
             if (sums) {
