@@ -426,6 +426,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernels", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=32)
+    ap.add_argument("--kernels-only", default=None, help="comma list (k1,k2,k3,k3b,k4,k6,k7): only the micro-benchmarks")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "graft" else args.warmup
     if args.config is None:
@@ -446,6 +447,12 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     peak, peak_src = measured_peaks()
+
+    if args.kernels_only:
+        qc0 = ffi.Context.current(local_rank)
+        emit({"kernels": kernel_microbench(qc0, peak, set(args.kernels_only.split(","))), "peak": peak})
+        qdist.shutdown()
+        return
 
     if args.config == "cfg1":
         lat = cfg1_latency(max(50, args.steps * 10), max(args.warmup, 8))
@@ -492,10 +499,18 @@ def main():
         return r
 
     def make_step(src):
+        # resident: frames already in HBM; e2e: pinned HOST frames straight into the public call -- the pipeline
+        # uploads them on its copy stream (H2D of the next step's frames overlaps this step's compute).
+        # Two batches are in flight: the detect half (K1 -> YOLOv8 -> K2) of batch i+1 is queued BEFORE the host waits
+        # for batch i's packed detections, so the ROI planning on the host never leaves the GPU idle.
+        state = {"det": None}
+
         def step(i, last=False):
-            # resident: frames already in HBM; e2e: pinned HOST frames straight into the public call -- the pipeline
-            # uploads them on its copy stream (H2D of this step's frames overlaps the previous step's compute)
-            h = pipe.run_async(src[i % NB], inject=inj[i % NB])
+            if state["det"] is None:
+                state["det"] = pipe.submit_detect(src[i % NB], inject=inj[i % NB])
+            cur = state["det"]
+            state["det"] = None if last else pipe.submit_detect(src[(i + 1) % NB], inject=inj[(i + 1) % NB])
+            h = pipe.submit_rest(cur)
             prev, pending[0] = pending[0], h
             r = finish(prev) if prev is not None else None
             if last:

@@ -17,6 +17,7 @@
 // HBM-bound, no tensor cores: algorithmic bytes = h0*w0*3 + 3*H*W*sizeof(out) per image.
 #include "common.cuh"
 #include <math.h>
+#include <algorithm>
 
 namespace {
 
@@ -220,6 +221,146 @@ k1_generic(const uint8_t* __restrict__ src, OutT* __restrict__ dst, const float*
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// k1_resize_tma: the real letterbox / stretch resize with staged source rows.  A CTA takes (image, band of 8 output
+// rows): the <= 16 source rows the band taps are pulled into shared memory by 1-D TMA bulk copies (cp.async.bulk +
+// mbarrier -> SASS UBLKCP; plain loads when base or pitch is not 16-byte aligned), the x coefficient table of the plan
+// (cv2's float64 coordinate maths, evaluated once per CTA instead of twice per output pixel) sits beside them, and a
+// thread produces 8 adjacent output pixels of one row -- exact cv2 INTER_LINEAR integer model, border, LUT -- stored
+// as one 128-bit (bf16) or two 128-bit (f32) streaming stores per plane.
+constexpr int K1R_MAX_THREADS = 512;
+constexpr int K1R_RB = 4;                    // output rows per band (2 source rows each); two bands in flight per CTA
+
+template <typename OutT>
+__global__ void __launch_bounds__(K1R_MAX_THREADS)
+k1_resize_tma(const uint8_t* __restrict__ src, OutT* __restrict__ dst, const float* __restrict__ lut, int n,
+              long long src_img_stride, int src_row_stride, qc_pre_plan pl, int pad_value, int swap_rb, int row_bytes,
+              int tma_ok, int bands_per_img) {
+    extern __shared__ __align__(128) uint8_t k1r_sm[];
+    const int groups = (pl.dst_w + 7) >> 3;
+    uint32_t* lut_s = reinterpret_cast<uint32_t*>(k1r_sm);                       // [3][256]
+    // x table, stored [x & 7][x >> 3] so that the lanes of a warp (adjacent 8-pixel groups) read adjacent entries
+    int4* xtab = reinterpret_cast<int4*>(k1r_sm + 3 * 256 * 4);                  // (3*s0, 3*s1, a0, a1) per output column
+    int4* ytab = xtab + groups * 8;                                              // (s0, s1, a0, a1) per output row; s0 < 0: border
+    uint8_t* rows = reinterpret_cast<uint8_t*>(ytab) + (((size_t)pl.dst_h * 16 + 127) & ~(size_t)127);   // [2][2*K1R_RB][row_bytes]
+    __shared__ __align__(8) uint64_t bar[2];
+    const int tid = threadIdx.x, nt = blockDim.x;
+    if (tid == 0) { qc_mbar_init(&bar[0], 1); qc_mbar_init(&bar[1], 1); qc_fence_mbar_init(); }
+    for (int i = tid; i < 768; i += nt) lut_s[i] = OutPack<OutT>::enc(lut[i]);
+    const bool resize_x = pl.new_w != pl.src_w, resize_y = pl.new_h != pl.src_h;
+    for (int x = tid; x < pl.dst_w; x += nt) {
+        const int rx = x - pl.left;
+        int4 e = make_int4(-1, -1, 0, 0);                                         // border column
+        if (rx >= 0 && rx < pl.new_w) {
+            if (resize_x) { const LinCoef c = lin_coef(rx, pl.new_w, pl.src_w, true); e = make_int4(3 * c.s0, 3 * c.s1, c.a0, c.a1); }
+            else e = make_int4(3 * rx, 3 * rx, 2048, 0);
+        }
+        xtab[(x & 7) * groups + (x >> 3)] = e;
+    }
+    for (int y = tid; y < pl.dst_h; y += nt) {
+        const int ry = y - pl.top;
+        int4 e = make_int4(-1, -1, 2048, 0);                                      // border row
+        if (ry >= 0 && ry < pl.new_h) {
+            if (resize_y) { const LinCoef c = lin_coef(ry, pl.new_h, pl.src_h, false); e = make_int4(c.s0, c.s1, c.a0, c.a1); }
+            else e = make_int4(ry, ry, 2048, 0);
+        }
+        ytab[y] = e;
+    }
+    const long long plane = (long long)pl.dst_h * pl.dst_w;
+    const long long total = (long long)n * bands_per_img;
+    const size_t buf_bytes = (size_t)2 * K1R_RB * row_bytes;
+    // the copies of a band's source rows (TMA: one thread issues them; plain loads happen at use)
+    auto prefetch = [&](long long item, int buf) {
+        if (!tma_ok || tid != 0) return;
+        const int img = (int)(item / bands_per_img), band = (int)(item - (long long)img * bands_per_img);
+        const int y0 = band * K1R_RB, nr = min(K1R_RB, pl.dst_h - y0);
+        const uint8_t* simg = src + (long long)img * src_img_stride;
+        uint8_t* rb = rows + (size_t)buf * buf_bytes;
+        int nvalid = 0;
+        for (int k = 0; k < nr; ++k) nvalid += ytab[y0 + k].x >= 0 ? 2 : 0;
+        if (!nvalid) return;
+        qc_mbar_expect_tx(&bar[buf], (uint32_t)nvalid * (uint32_t)row_bytes);
+        for (int k = 0; k < nr; ++k) {
+            const int4 e = ytab[y0 + k];
+            if (e.x < 0) continue;
+            qc_bulk_g2s(rb + (size_t)(2 * k) * row_bytes, simg + (long long)e.x * src_row_stride, (uint32_t)row_bytes, &bar[buf]);
+            qc_bulk_g2s(rb + (size_t)(2 * k + 1) * row_bytes, simg + (long long)e.y * src_row_stride, (uint32_t)row_bytes, &bar[buf]);
+        }
+    };
+    unsigned par0 = 0u, par1 = 0u;
+    __syncthreads();
+    long long item = blockIdx.x;
+    if (item < total) prefetch(item, 0);
+    for (int it = 0; item < total; ++it, item += gridDim.x) {
+        const int buf = it & 1;
+        const long long next = item + gridDim.x;
+        if (next < total) prefetch(next, buf ^ 1);         // rows of the next band stream in during this band's arithmetic
+        const int img = (int)(item / bands_per_img), band = (int)(item - (long long)img * bands_per_img);
+        const int y0 = band * K1R_RB, y1 = min(y0 + K1R_RB, pl.dst_h);
+        uint8_t* rb = rows + (size_t)buf * buf_bytes;
+        bool any = false;
+        for (int k = 0; k < y1 - y0; ++k) any |= ytab[y0 + k].x >= 0;
+        if (tma_ok) {
+            if (any) {
+                if (buf) { qc_mbar_wait(&bar[1], par1); par1 ^= 1u; } else { qc_mbar_wait(&bar[0], par0); par0 ^= 1u; }
+            }
+        } else if (any) {
+            const uint8_t* simg = src + (long long)img * src_img_stride;
+            const int nb = pl.src_w * 3;
+            for (int i = tid; i < (y1 - y0) * 2 * nb; i += nt) {
+                const int slot = i / nb, j = i - slot * nb;
+                const int4 e = ytab[y0 + (slot >> 1)];
+                const int sr = (slot & 1) ? e.y : e.x;
+                if (sr >= 0) rb[(size_t)slot * row_bytes + j] = __ldg(simg + (long long)sr * src_row_stride + j);
+            }
+            __syncthreads();
+        }
+        // compute: thread = (band row, 8 adjacent output columns)
+        for (int w = tid; w < (y1 - y0) * groups; w += nt) {
+            const int k = w / groups, gx = w - k * groups;
+            const int y = y0 + k, x0 = gx * 8;
+            const int4 ye = ytab[y];
+            const int s0 = ye.x, b0 = ye.z, b1 = ye.w;
+            const uint8_t* r0 = rb + (size_t)(2 * k) * row_bytes;
+            const uint8_t* r1 = r0 + row_bytes;
+            uint32_t vals[3][8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int x = x0 + j;
+                int px[3] = {pad_value, pad_value, pad_value};
+                if (x < pl.dst_w && s0 >= 0) {
+                    const int4 e = xtab[j * groups + gx];
+                    if (e.x >= 0) {
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) {
+                            const int h0 = (int)r0[e.x + c] * e.z + (int)r0[e.y + c] * e.w;
+                            const int h1 = (int)r1[e.x + c] * e.z + (int)r1[e.y + c] * e.w;
+                            px[c] = (resize_x || resize_y) ? ((((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2)
+                                                           : (int)r0[e.x + c];
+                        }
+                    }
+                }
+#pragma unroll
+                for (int oc = 0; oc < 3; ++oc) vals[oc][j] = lut_s[oc * 256 + (px[swap_rb ? 2 - oc : oc] & 255)];
+            }
+#pragma unroll
+            for (int oc = 0; oc < 3; ++oc) {
+                OutT* o = dst + ((long long)img * 3 + oc) * plane + (long long)y * pl.dst_w + x0;
+                const bool full = (x0 + 8 <= pl.dst_w) && ((reinterpret_cast<uintptr_t>(o) & 15) == 0);
+                if (full) {
+                    OutPack<OutT>::store8(o, vals[oc]);
+                } else {
+                    for (int j = 0; j < 8 && x0 + j < pl.dst_w; ++j) {
+                        if (sizeof(OutT) == 2) reinterpret_cast<uint16_t*>(o)[j] = (uint16_t)vals[oc][j];
+                        else reinterpret_cast<uint32_t*>(o)[j] = vals[oc][j];
+                    }
+                }
+            }
+        }
+        __syncthreads();                                   // `buf` may be refilled by the next iteration's prefetch
+    }
+}
+
 inline long long py_round(double v) { return (long long)nearbyint(v); }  // round-half-even == Python round()
 
 }  // namespace
@@ -290,6 +431,30 @@ static int launch_k1(qc_ctx* ctx, const uint8_t* src, int n, int64_t src_img_str
         kern<<<(unsigned)grid, K1_THREADS, smem, st>>>(src, dst, lut, P, src_img_stride, chunks, total);
         QC_LAUNCHED(ctx);
         return QC_OK;
+    }
+    {
+        // staged-row kernel: shared memory = LUT + x table + two bands of 8 source rows
+        const bool tma_ok = (reinterpret_cast<uintptr_t>(src) & 15) == 0 && (src_img_stride & 15) == 0 && (src_row_stride & 15) == 0;
+        const int row_bytes = tma_ok ? ((pl->src_w * 3 + 15) & ~15) : pl->src_w * 3;
+        const int groups = (pl->dst_w + 7) / 8;
+        const size_t smem = 3 * 256 * 4 + (size_t)groups * 8 * 16 + (((size_t)pl->dst_h * 16 + 127) & ~(size_t)127) +
+                            (size_t)2 * 2 * K1R_RB * row_bytes + 16;
+        if ((long long)smem + 2048 <= ctx->max_smem_optin && (!tma_ok || row_bytes <= src_row_stride)) {
+            const int bands = (pl->dst_h + K1R_RB - 1) / K1R_RB;
+            // threads: one pass over the band's (row, 8-pixel group) items when they fit, else equal passes
+            const int items_band = K1R_RB * groups;
+            const int passes = (items_band + 383) / 384;
+            const int threads = std::min(K1R_MAX_THREADS, std::max(128, (((items_band + passes - 1) / passes) + 31) & ~31));
+            int occ = 1;
+            if (int rc = qc_prepare(ctx, k1_resize_tma<OutT>, (int)smem, threads, &occ)) return rc;
+            const long long total = (long long)n * bands;
+            long long g = (long long)ctx->sm_count * std::max(occ, 1);
+            if (g > total) g = total;
+            k1_resize_tma<OutT><<<(unsigned)g, threads, smem, st>>>(src, dst, lut, n, src_img_stride, src_row_stride, *pl,
+                                                                   pad_value, swap_rb, row_bytes, tma_ok ? 1 : 0, bands);
+            QC_LAUNCHED(ctx);
+            return QC_OK;
+        }
     }
     const long long items = (long long)n * pl->dst_h * ((pl->dst_w + 7) / 8);
     long long grid = (items + 255) / 256;

@@ -235,25 +235,50 @@ class InspectionPipeline:
         return img.astype(np.int32), di.astype(np.int32), box[img, di]
 
     @torch.no_grad()
+    def submit_detect(self, frames: torch.Tensor, inject=None, head_override=None, processed: bool = False) -> "DetectHandle":
+        """First half of a batch: (upload) -> K1 -> YOLOv8 -> K2 -> K5, plus the asynchronous device->host copy of the
+        packed detections into pinned memory.  Nothing here waits for the GPU."""
+        qc = self.qc
+        stage_slot = None
+        if not frames.is_cuda:
+            frames, stage_slot = self._upload(frames)
+        det_d, anchor_d, count_d, _ = self.detect(frames, inject, head_override, swap_rb=not processed)
+        spc_d = qc.spc_stats(det_d, count_d)
+        det_h = torch.empty(det_d.shape, dtype=det_d.dtype, pin_memory=True)
+        cnt_h = torch.empty(count_d.shape, dtype=count_d.dtype, pin_memory=True)
+        det_h.copy_(det_d, non_blocking=True)
+        cnt_h.copy_(count_d, non_blocking=True)
+        ready = torch.cuda.Event()
+        ready.record()
+        return DetectHandle(frames, stage_slot, det_h, cnt_h, spc_d, ready, processed)
+
+    @torch.no_grad()
     def run_async(self, frames: torch.Tensor, inject=None, head_override=None, include_segmentation: bool = True,
                   keep_seg_tensors: bool = False, morph_iters: int = 1, min_area: int = 20,
                   processed: bool = False) -> "PendingResult":
         """frames: uint8 [n,h,w,3], CUDA or (pinned) host.  ``processed=False``: the frames are what the caller hands to
         ``QualityControlDetector.predict`` (the reference then flips channels at inference/detector.py:234,
         models/yolo_model.py:80, inside ultralytics, and at models/resent_model.py:123 -- folded into the kernels'
-        swap flags); ``processed=True``: the frames are the output of ``_preprocess_image`` (already flipped once)."""
-        qc = self.qc
+        swap flags); ``processed=True``: the frames are the output of ``_preprocess_image`` (already flipped once).
+        = submit_detect + submit_rest; a caller that keeps several batches in flight calls the two halves itself, the
+        detect half of batch i+1 BEFORE the rest half of batch i, so that the one host wait of a batch (its packed
+        detections, needed to plan the ROI tables) never leaves the GPU without queued work."""
         if self.resnet is None and (self.classify_global or self.classify_rois):
             raise ffi.QcGraftError("ResNet model not loaded")
-        stage_slot = None
-        if not frames.is_cuda:
-            frames, stage_slot = self._upload(frames)
-        n, h, w = frames.shape[:3]
-        det_d, anchor_d, count_d, _ = self.detect(frames, inject, head_override, swap_rb=not processed)
-        spc_d = qc.spc_stats(det_d, count_d)
-        # ---- the one mid-pipeline device->host copy (packed detections) -------------------------
-        det = det_d.cpu().numpy()
-        count = count_d.cpu().numpy()
+        return self.submit_rest(self.submit_detect(frames, inject, head_override, processed), include_segmentation,
+                                keep_seg_tensors, morph_iters, min_area)
+
+    @torch.no_grad()
+    def submit_rest(self, h: "DetectHandle", include_segmentation: bool = True, keep_seg_tensors: bool = False,
+                    morph_iters: int = 1, min_area: int = 20) -> "PendingResult":
+        """Second half: wait for the batch's packed detections (the reference syncs there too,
+        models/yolo_model.py:133-135), plan the ROI tables on the host, then K3b/K3 -> ResNet-50 -> K7."""
+        qc = self.qc
+        frames, stage_slot, processed, spc_d = h.frames, h.stage_slot, h.processed, h.spc_d
+        n = frames.shape[0]
+        h.ready.synchronize()
+        det = h.det_h.numpy()
+        count = h.cnt_h.numpy()
         roi_img, roi_det, roi_box = self.rois_from_detections(det, count)
         K = len(roi_img)
         res = BatchResult(n=n, det=det, count=count, anchor=None, roi_img=roi_img, roi_det=roi_det, roi_box=roi_box)
@@ -395,6 +420,18 @@ class InspectionPipeline:
     def run(self, frames: torch.Tensor, **kw) -> BatchResult:
         """Synchronous form: one batch in, host-side BatchResult out."""
         return self.run_async(frames, **kw).result()
+
+
+@dataclass
+class DetectHandle:
+    """A batch between its two halves (InspectionPipeline.submit_detect / submit_rest)."""
+    frames: torch.Tensor
+    stage_slot: Optional[list]
+    det_h: torch.Tensor
+    cnt_h: torch.Tensor
+    spc_d: torch.Tensor
+    ready: "torch.cuda.Event"
+    processed: bool
 
 
 class PendingResult:
