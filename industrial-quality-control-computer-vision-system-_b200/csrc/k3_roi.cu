@@ -362,6 +362,7 @@ constexpr int K3T_THREADS = 224;
 constexpr int K3T_ROWS = 12;               // source rows per band held as Hs
 constexpr int K3T_RAW = 6 * 1024;          // raw byte staging buffer (floats: 4x)
 constexpr int K3T_PH_MAX = 256;
+constexpr int K3T_SPLIT = 4;                // work items per ROI (quarters of its output rows): balance across CTAs
 
 struct K3Taps { int i[4]; float w[4]; int n; };
 
@@ -402,10 +403,10 @@ __device__ __forceinline__ K3Taps k3_taps(float start, float bin, int p, int sr,
 template <typename OutT>
 __device__ __noinline__ void k3_roi_direct(const uint8_t* base, bool img_ok, int H, int W, int row_stride, float x1, float y1,
                                            float bin_w, float bin_h, int PH, int PW, int sr, int swap_rb, const float* nd,
-                                           const float* nm, const float* ns, OutT* dk) {
+                                           const float* nm, const float* ns, OutT* dk, int ph_lo, int ph_hi) {
     const int total = PH * PW;
     const float count = (float)(sr * sr);
-    for (int o = threadIdx.x; o < total; o += K3T_THREADS) {
+    for (int o = ph_lo * PW + threadIdx.x; o < ph_hi * PW; o += K3T_THREADS) {
         const int ph = o / PW, pw = o - ph * PW;
         float acc[3] = {0.f, 0.f, 0.f};
         if (img_ok) {
@@ -478,7 +479,10 @@ k3_roi_tma(const uint8_t* __restrict__ imgs, int n, int H, int W, long long img_
     const int vq = tid % quads, vsl = tid / quads;
     __syncthreads();
 
-    for (int k = blockIdx.x; k < K; k += gridDim.x) {
+    for (int item = blockIdx.x; item < K * K3T_SPLIT; item += gridDim.x) {
+        const int k = item / K3T_SPLIT, chunk = item - k * K3T_SPLIT;
+        const int ph_lo = chunk * PH / K3T_SPLIT, ph_hi = (chunk + 1) * PH / K3T_SPLIT;      // this item's output rows
+        if (ph_lo >= ph_hi) continue;
         const float* r = rois + (long long)k * 5;
         const int img = (int)r[0];
         const float offset = aligned ? 0.5f : 0.f;
@@ -499,7 +503,7 @@ k3_roi_tma(const uint8_t* __restrict__ imgs, int n, int H, int W, long long img_
         if (tid == 0) { s_xr[0] = INT_MAX; s_xr[1] = -1; }
         int bad = (tid < PW && ((tx.n & 8) || (tx.n & 7) == 0)) ? 1 : 0;
         int max_n = tx.n & 7;
-        for (int ph = tid; ph < PH; ph += K3T_THREADS) {
+        for (int ph = ph_lo + tid; ph < ph_hi; ph += K3T_THREADS) {
             const K3Taps ty = k3_taps(y1, bin_h, ph, sr, H);
             const int yn = ty.n & 7;
             if ((ty.n & 8) || yn == 0) bad = 1;
@@ -529,10 +533,15 @@ k3_roi_tma(const uint8_t* __restrict__ imgs, int n, int H, int W, long long img_
         // byte window of a source row: 16-byte aligned superset of [3*x_lo, 3*x_hi + 3)
         const int b0 = (3 * max(x_lo, 0)) & ~15;
         const int pitch = max(((3 * (x_hi + 1) + 15) & ~15) - b0, 16);
-        const int rows_cap = min(K3T_ROWS, K3T_RAW / pitch);
-        if (!geom_ok || any_bad || x_hi < 0 || rows_cap < 2 || s_yhi[0] - s_ylo[0] + 1 > rows_cap ||
-            s_yhi[PH - 1] - s_ylo[PH - 1] + 1 > rows_cap || __fmul_rn(bin_h, 1.f) > (float)(rows_cap - 2)) {
-            k3_roi_direct<OutT>(base, img_ok, H, W, row_stride, x1, y1, bin_w, bin_h, PH, PW, sr, swap_rb, nd, nm, ns, dk);
+        // narrow windows are converted to float once per band (Fb); rows too wide for that are tapped as bytes from a
+        // staging buffer that then takes the Fb space as well
+        const bool wide = pitch * K3T_ROWS > K3T_RAW;
+        uint8_t* const rawb = wide ? reinterpret_cast<uint8_t*>(Fb) : raw;
+        const int rows_cap = min(K3T_ROWS, (wide ? K3T_RAW * 5 : K3T_RAW) / pitch);
+        if (!geom_ok || any_bad || x_hi < 0 || rows_cap < 4 || s_yhi[ph_lo] - s_ylo[ph_lo] + 1 > rows_cap ||
+            s_yhi[ph_hi - 1] - s_ylo[ph_hi - 1] + 1 > rows_cap || bin_h > (float)(rows_cap - 2)) {
+            k3_roi_direct<OutT>(base, img_ok, H, W, row_stride, x1, y1, bin_w, bin_h, PH, PW, sr, swap_rb, nd, nm, ns, dk,
+                                ph_lo, ph_hi);
             continue;
         }
         // x taps relative to the staged window (float index of the byte): unused slots weight 0 on the first tap
@@ -546,7 +555,7 @@ k3_roi_tma(const uint8_t* __restrict__ imgs, int n, int H, int W, long long img_
         }
         // band [pa, pb): closed form from the sample spacing, then trimmed until its source rows fit
         auto band_end = [&](int pa, int& r_lo, int& r_hi) -> int {
-            int nb = bin_h > 0.f ? (int)fminf((float)(rows_cap - 2) / bin_h, (float)(PH - pa)) : PH - pa;
+            int nb = bin_h > 0.f ? (int)fminf((float)(rows_cap - 2) / bin_h, (float)(ph_hi - pa)) : ph_hi - pa;
             int pb = pa + max(nb, 1);
             r_lo = s_ylo[pa];
             r_hi = s_yhi[pb - 1];
@@ -560,43 +569,53 @@ k3_roi_tma(const uint8_t* __restrict__ imgs, int n, int H, int W, long long img_
                 if (tid == 0) {
                     qc_mbar_expect_tx(&s_bar, (uint32_t)(nrows * pitch));
                     for (int rr = 0; rr < nrows; ++rr)
-                        qc_bulk_g2s(raw + rr * pitch, base + (long long)(r_lo + rr) * row_stride + b0, (uint32_t)pitch, &s_bar);
+                        qc_bulk_g2s(rawb + rr * pitch, base + (long long)(r_lo + rr) * row_stride + b0, (uint32_t)pitch, &s_bar);
                 }
             } else {
                 const int valid = min(pitch, 3 * W - b0);             // never read past the row's pixels
                 for (int i = tid; i < nrows * pitch; i += K3T_THREADS) {
                     const int rr = i / pitch, j = i - rr * pitch;
-                    raw[i] = j < valid ? __ldg(base + (long long)(r_lo + rr) * row_stride + b0 + j) : (uint8_t)0;
+                    rawb[i] = j < valid ? __ldg(base + (long long)(r_lo + rr) * row_stride + b0 + j) : (uint8_t)0;
                 }
             }
         };
-        int pa = 0, r_lo, r_hi;
+        int pa = ph_lo, r_lo, r_hi;
         int pb = band_end(pa, r_lo, r_hi);
         stage(r_lo, r_hi);
-        while (pa < PH) {
+        while (pa < ph_hi) {
             const int nrows = r_hi - r_lo + 1;
             if (use_tma) { qc_mbar_wait(&s_bar, parity); parity ^= 1u; }
             else __syncthreads();
-            // (0) bytes -> floats, one 32-bit word (4 bytes) per step
-            for (int i = tid; i < (nrows * pitch) >> 2; i += K3T_THREADS) {
-                const unsigned wv = reinterpret_cast<const unsigned*>(raw)[i];
-                reinterpret_cast<float4*>(Fb)[i] = make_float4((float)(wv & 255u), (float)((wv >> 8) & 255u),
-                                                               (float)((wv >> 16) & 255u), (float)(wv >> 24));
-            }
-            __syncthreads();                                 // Fb complete, raw consumed
-            // next band: its rows stream in while this band is computed
             const int npa = pb;
             int nr_lo = 0, nr_hi = -1, npb = npa;
-            if (npa < PH) {
-                npb = band_end(npa, nr_lo, nr_hi);
-                stage(nr_lo, nr_hi);
+            if (npa < ph_hi) npb = band_end(npa, nr_lo, nr_hi);
+            if (!wide) {
+                // (0) bytes -> floats, one 32-bit word (4 bytes) per step
+                for (int i = tid; i < (nrows * pitch) >> 2; i += K3T_THREADS) {
+                    const unsigned wv = reinterpret_cast<const unsigned*>(raw)[i];
+                    reinterpret_cast<float4*>(Fb)[i] = make_float4((float)(wv & 255u), (float)((wv >> 8) & 255u),
+                                                                   (float)((wv >> 16) & 255u), (float)(wv >> 24));
+                }
+                __syncthreads();                             // Fb complete, raw consumed
+                if (npa < ph_hi) stage(nr_lo, nr_hi);        // next band streams in while this one is computed
             }
             // (1) horizontal pass: thread = output column (3 tap slots, 4 only when some column of the ROI needs them)
             if (tid < PW) {
                 const int c0 = swap_rb ? 2 : 0, c2 = swap_rb ? 0 : 2;
                 float* hrow = Hs + tid;
-                const float* fr = Fb;
-                if (!four) {
+                if (wide) {
+                    const uint8_t* br = rawb;
+                    for (int rr = 0; rr < nrows; ++rr, br += pitch, hrow += 3 * PW) {
+                        float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const uint8_t* px = br + xo[j];
+                            a0 = __fmaf_rn(xw[j], (float)px[0], a0); a1 = __fmaf_rn(xw[j], (float)px[1], a1); a2 = __fmaf_rn(xw[j], (float)px[2], a2);
+                        }
+                        hrow[c0 * PW] = a0; hrow[PW] = a1; hrow[c2 * PW] = a2;
+                    }
+                } else if (!four) {
+                    const float* fr = Fb;
 #pragma unroll 2
                     for (int rr = 0; rr < nrows; ++rr, fr += pitch, hrow += 3 * PW) {
                         float a0 = __fmul_rn(xw[0], fr[xo[0]]), a1 = __fmul_rn(xw[0], fr[xo[0] + 1]), a2 = __fmul_rn(xw[0], fr[xo[0] + 2]);
@@ -605,6 +624,7 @@ k3_roi_tma(const uint8_t* __restrict__ imgs, int n, int H, int W, long long img_
                         hrow[c0 * PW] = a0; hrow[PW] = a1; hrow[c2 * PW] = a2;
                     }
                 } else {
+                    const float* fr = Fb;
                     for (int rr = 0; rr < nrows; ++rr, fr += pitch, hrow += 3 * PW) {
                         float a0 = __fmul_rn(xw[0], fr[xo[0]]), a1 = __fmul_rn(xw[0], fr[xo[0] + 1]), a2 = __fmul_rn(xw[0], fr[xo[0] + 2]);
                         a0 = __fmaf_rn(xw[1], fr[xo[1]], a0); a1 = __fmaf_rn(xw[1], fr[xo[1] + 1], a1); a2 = __fmaf_rn(xw[1], fr[xo[1] + 2], a2);
@@ -614,7 +634,8 @@ k3_roi_tma(const uint8_t* __restrict__ imgs, int n, int H, int W, long long img_
                     }
                 }
             }
-            __syncthreads();                                 // Hs complete
+            __syncthreads();                                 // Hs complete (wide: the staged bytes are consumed)
+            if (wide && npa < ph_hi) stage(nr_lo, nr_hi);
             // (2) vertical pass: the tap-slot count of the output row picks the loop body (rows between two source
             // rows -- most rows of an up-scaled box -- need 2 loads + 8 multiply-adds per 4 outputs)
             if (vsl < nsl) {
@@ -690,12 +711,12 @@ extern "C" int qc_roi_align_rows(qc_ctx* ctx, const uint8_t* imgs, int n, int h,
         const int grid = std::min(K, ctx->sm_count * 8);
         if (out_dtype == QC_DT_BF16) {
             if (int rc = qc_prepare(ctx, k3_roi_tma<__nv_bfloat16>, (int)smem, K3T_THREADS, &occ)) return rc;
-            k3_roi_tma<__nv_bfloat16><<<std::min(K, ctx->sm_count * std::max(occ, 1)), K3T_THREADS, smem, st>>>(
+            k3_roi_tma<__nv_bfloat16><<<std::min(K * K3T_SPLIT, ctx->sm_count * std::max(occ, 1)), K3T_THREADS, smem, st>>>(
                 imgs, n, h, w, img_stride, row_stride, rois, K, out_h, out_w, sampling_ratio, aligned, swap_rb, norm,
                 (__nv_bfloat16*)dst, tma_ok, dst_rows);
         } else if (out_dtype == QC_DT_F32) {
             if (int rc = qc_prepare(ctx, k3_roi_tma<float>, (int)smem, K3T_THREADS, &occ)) return rc;
-            k3_roi_tma<float><<<std::min(K, ctx->sm_count * std::max(occ, 1)), K3T_THREADS, smem, st>>>(
+            k3_roi_tma<float><<<std::min(K * K3T_SPLIT, ctx->sm_count * std::max(occ, 1)), K3T_THREADS, smem, st>>>(
                 imgs, n, h, w, img_stride, row_stride, rois, K, out_h, out_w, sampling_ratio, aligned, swap_rb, norm,
                 (float*)dst, tma_ok, dst_rows);
         } else {
