@@ -257,6 +257,9 @@ int qc_segment(qc_ctx* ctx, const uint8_t* imgs, const qc_seg_params* p,
  *
  * out_sums (may be NULL): int64 [num_regions][4] = (sum of gray over the mask, sum of gray, sum of gray^2, pixels of
  * the ROI) -- the integers behind inference/segmentation.py:527-555's confidence (means and std of the ROI).
+ * out_contours (may be NULL): int64 [num_regions][4] = (n_axis, n_diag, n_contours, 0) of the final mask's external
+ * contours with cv2.contourArea >= 10 -- inference/segmentation.py:486-525 without tracing a contour: perimeter
+ * (sum of cv2.arcLength) = n_axis + sqrt(2) * n_diag, contour count = n_contours (K8, csrc/k7_refseg.cuh).
  * workspace: qc_segment_ref_workspace_bytes(p, method).                                                    */
 typedef enum { QC_SEG_COMPOSITE = 0, QC_SEG_REF_THRESHOLD = 1, QC_SEG_REF_ADAPTIVE = 2 } qc_seg_method;
 
@@ -266,7 +269,7 @@ int qc_segment_ref(qc_ctx* ctx, int method, const uint8_t* imgs, const qc_seg_pa
                    const qc_seg_region* regions, const float* akern, int akern_pitch, int akern_max_block,
                    int adaptive_c, void* workspace, size_t workspace_bytes, uint8_t* out_mask,
                    int32_t* out_labels, int32_t* out_ncomp, int32_t* out_stats, int32_t* out_thr,
-                   int64_t* out_area, int64_t* out_sums, void* stream);
+                   int64_t* out_area, int64_t* out_sums, int64_t* out_contours, void* stream);
 
 /* ---- SPC per-batch statistics (payload of the one NCCL all-reduce) ---------
  * Device-side reduction of K2's outputs into the 9-vector derived from

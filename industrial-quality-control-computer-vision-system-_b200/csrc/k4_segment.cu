@@ -68,6 +68,8 @@ struct SegWs {
     double* blurred;      // [total_pixels]   sigma=1 float64 image (threshold method)
     unsigned long long* minmax;   // [R][2]
     double* thr_adj;      // [R]
+    unsigned long long* acc_n;    // [total_blocks]  K8 per-root (n_axis | n_diag << 32)
+    long long* acc_x;             // [total_blocks]  K8 per-root sum of cross products
     size_t total;
 };
 
@@ -90,10 +92,12 @@ SegWs carve(void* base, const qc_seg_params* p, int method = QC_SEG_COMPOSITE) {
     w.chunk_off = (int*)(b + take((R + 1) * 4));
     const bool ref = method != QC_SEG_COMPOSITE, thr = method == QC_SEG_REF_THRESHOLD;
     w.bits2 = (unsigned*)(b + take(ref ? (size_t)p->total_bits_words * 4 : 0));
-    w.bits3 = (unsigned*)(b + take(thr ? (size_t)p->total_bits_words * 4 : 0));
+    w.bits3 = (unsigned*)(b + take(ref ? (size_t)p->total_bits_words * 4 : 0));
     w.blurred = (double*)(b + take(thr ? (size_t)p->total_pixels * 8 : 0));
     w.minmax = (unsigned long long*)(b + take(thr ? R * 16 : 0));
     w.thr_adj = (double*)(b + take(thr ? R * 8 : 0));
+    w.acc_n = (unsigned long long*)(b + take(ref ? (size_t)p->total_blocks * 8 : 0));
+    w.acc_x = (long long*)(b + take(ref ? (size_t)p->total_blocks * 8 : 0));
     w.total = off;
     return w;
 }
@@ -945,7 +949,8 @@ __device__ __forceinline__ Cell load_cell(const qc_seg_region& rg, const unsigne
 __global__ void __launch_bounds__(K4_CHUNK)
 k4_compress(const qc_seg_region* __restrict__ regs, int R, int total_chunks, const int* __restrict__ g_chunk_off,
             const unsigned* __restrict__ bits, int* __restrict__ parent, int* __restrict__ chunk_count,
-            int* __restrict__ zero_area) {
+            int* __restrict__ zero_area, unsigned long long* __restrict__ zero_n = nullptr,
+            long long* __restrict__ zero_x = nullptr) {
     __shared__ int s_off[K4_LOC_MAX + 1];
     __shared__ unsigned s_v[K4_CHUNK];          // r0|r1 of every cell of the chunk
     __shared__ int s_base[K4_CHUNK];
@@ -972,6 +977,7 @@ k4_compress(const qc_seg_region* __restrict__ regs, int R, int total_chunks, con
             const int rt = uf_find(parent, g);
             parent[g] = rt;
             if (zero_area) zero_area[g] = 0;
+            if (zero_n) { zero_n[g] = 0ull; zero_x[g] = 0ll; }
             cnt += (rt == g);
         }
 #pragma unroll
@@ -1270,6 +1276,7 @@ namespace {
 
 struct SegOut {
     uint8_t* mask; int32_t* labels; int32_t* ncomp; int32_t* stats; int32_t* thr; int64_t* area; int64_t* sums;
+    int64_t* contours;
 };
 struct SegAdaptive {
     const float* akern; int pitch, max_block, c;
@@ -1322,7 +1329,7 @@ int seg_run(qc_ctx* ctx, int method, const uint8_t* imgs, const qc_seg_params* p
         QC_LAUNCHED(ctx);
         return QC_OK;
     };
-    auto unionfind = [&](const unsigned* bits, int* zero_area) -> int {             // parent[g] = root afterwards
+    auto unionfind = [&](const unsigned* bits, int* zero_area, bool zero_k8 = false) -> int {   // parent[g] = root afterwards
         if (int rc = qc_prepare(ctx, k4_ccl_local, (int)smem_ccl, K4_THREADS, &occ)) return rc;
         k4_ccl_local<<<std::min(p->total_bands, sms * std::max(occ, 1)), K4_THREADS, smem_ccl, st>>>(
             regions, R, p->total_bands, w.band_off, bits, w.parent, band_words, lab_words);
@@ -1330,7 +1337,26 @@ int seg_run(qc_ctx* ctx, int method, const uint8_t* imgs, const qc_seg_params* p
         k4_border<<<band_grid, K4_THREADS, 0, st>>>(regions, R, p->total_bands, w.band_off, bits, w.parent);
         QC_LAUNCHED(ctx);
         k4_compress<<<chunk_grid, K4_CHUNK, 0, st>>>(regions, R, p->total_chunks, w.chunk_off, bits, w.parent,
-                                                     w.chunk_count, zero_area);
+                                                     w.chunk_count, zero_area, zero_k8 ? w.acc_n : nullptr,
+                                                     zero_k8 ? w.acc_x : nullptr);
+        QC_LAUNCHED(ctx);
+        return QC_OK;
+    };
+    auto fill_holes = [&](const unsigned* bits_in, unsigned* bits_out, unsigned* free_ws) -> int {
+        if (int rc = qc_prepare(ctx, k7_fill, K7_FILL_SMEM_WORDS * 4, K7_FILL_THREADS, &occ)) return rc;
+        k7_fill<<<std::min(R, sms * std::max(occ, 1)), K7_FILL_THREADS, K7_FILL_SMEM_WORDS * 4, st>>>(regions, R, bits_in, bits_out, free_ws);
+        QC_LAUNCHED(ctx);
+        return QC_OK;
+    };
+    // K8: contour statistics of the final mask `fbits` (bit rows); scratch: two bit buffers, the union-find arrays
+    auto contour_stats = [&](const unsigned* fbits, unsigned* filled, unsigned* free_ws) -> int {
+        cudaMemsetAsync(o.contours, 0, (size_t)R * 4 * sizeof(int64_t), st);
+        if (int rc = fill_holes(fbits, filled, free_ws)) return rc;
+        if (int rc = unionfind(filled, nullptr, true)) return rc;
+        k8_moves<<<band_grid, K4_THREADS, 0, st>>>(regions, R, p->total_bands, w.band_off, filled, w.parent, w.acc_n, w.acc_x);
+        QC_LAUNCHED(ctx);
+        k8_reduce<<<band_grid, K4_THREADS, 0, st>>>(regions, R, p->total_bands, w.band_off, filled, w.parent, w.acc_n, w.acc_x,
+                                                    (long long*)o.contours);
         QC_LAUNCHED(ctx);
         return QC_OK;
     };
@@ -1402,7 +1428,14 @@ int seg_run(qc_ctx* ctx, int method, const uint8_t* imgs, const qc_seg_params* p
         QC_LAUNCHED(ctx);
         if (int rc = morph(w.bits2, w.bits)) return rc;
         if (int rc = unionfind(w.bits, nullptr)) return rc;
-        return label_tail(w.bits);
+        if (int rc = label_tail(w.bits)) return rc;
+        if (o.contours) {
+            // kept mask (labels + areas are final) -> bits2; filled -> bits3; free rows of oversized regions -> bits
+            k8_kept_bits<<<band_grid, K4_THREADS, 0, st>>>(regions, R, p->total_bands, w.band_off, w.bits, w.parent, o.stats, w.bits2);
+            QC_LAUNCHED(ctx);
+            return contour_stats(w.bits2, w.bits3, w.bits);
+        }
+        return QC_OK;
     }
 
     // QC_SEG_REF_THRESHOLD
@@ -1422,17 +1455,16 @@ int seg_run(qc_ctx* ctx, int method, const uint8_t* imgs, const qc_seg_params* p
     QC_LAUNCHED(ctx);
     k7_filter<<<band_grid, K4_THREADS, 0, st>>>(regions, R, p->total_bands, w.band_off, w.bits, w.parent, w.rank, w.bits2);
     QC_LAUNCHED(ctx);
-    if (int rc = qc_prepare(ctx, k7_fill, K7_FILL_SMEM_WORDS * 4, K7_FILL_THREADS, &occ)) return rc;
     // (regions too large for shared memory flood in place in bits3, with their free rows parked in bits -- free until
     // the morphology pass rewrites it)
-    k7_fill<<<std::min(R, sms * std::max(occ, 1)), K7_FILL_THREADS, K7_FILL_SMEM_WORDS * 4, st>>>(regions, R, w.bits2, w.bits3, w.bits);
-    QC_LAUNCHED(ctx);
+    if (int rc = fill_holes(w.bits2, w.bits3, w.bits)) return rc;
     if (int rc = morph(w.bits3, w.bits)) return rc;
     k7_emit<<<band_grid, K4_THREADS, 0, st>>>(im, regions, R, p->total_bands, w.band_off, gray7, w.bits, o.mask, o.labels,
                                               o.stats, (long long*)o.area, (long long*)o.sums);
     QC_LAUNCHED(ctx);
     k7_finish<<<(R + 255) / 256, 256, 0, st>>>(regions, R, o.stats, (const long long*)o.area, o.ncomp, (long long*)o.sums);
     QC_LAUNCHED(ctx);
+    if (o.contours) return contour_stats(w.bits, w.bits3, w.bits2);      // final mask = bits; bits2 / bits3 are free now
     return QC_OK;
 }
 
@@ -1442,15 +1474,15 @@ extern "C" int qc_segment(qc_ctx* ctx, const uint8_t* imgs, const qc_seg_params*
                           void* workspace, size_t workspace_bytes, uint8_t* out_mask, int32_t* out_labels,
                           int32_t* out_ncomp, int32_t* out_stats, int32_t* out_thr, int64_t* out_area, void* stream) {
     return seg_run(ctx, QC_SEG_COMPOSITE, imgs, p, regions, SegAdaptive{nullptr, 0, 0, 0}, workspace, workspace_bytes,
-                   SegOut{out_mask, out_labels, out_ncomp, out_stats, out_thr, out_area, nullptr}, stream);
+                   SegOut{out_mask, out_labels, out_ncomp, out_stats, out_thr, out_area, nullptr, nullptr}, stream);
 }
 
 extern "C" int qc_segment_ref(qc_ctx* ctx, int method, const uint8_t* imgs, const qc_seg_params* p,
                               const qc_seg_region* regions, const float* akern, int akern_pitch, int akern_max_block,
                               int adaptive_c, void* workspace, size_t workspace_bytes, uint8_t* out_mask,
                               int32_t* out_labels, int32_t* out_ncomp, int32_t* out_stats, int32_t* out_thr,
-                              int64_t* out_area, int64_t* out_sums, void* stream) {
+                              int64_t* out_area, int64_t* out_sums, int64_t* out_contours, void* stream) {
     return seg_run(ctx, method, imgs, p, regions, SegAdaptive{akern, akern_pitch, akern_max_block, adaptive_c},
                    workspace, workspace_bytes,
-                   SegOut{out_mask, out_labels, out_ncomp, out_stats, out_thr, out_area, out_sums}, stream);
+                   SegOut{out_mask, out_labels, out_ncomp, out_stats, out_thr, out_area, out_sums, out_contours}, stream);
 }

@@ -841,3 +841,184 @@ __global__ void k7_finish(const qc_seg_region* __restrict__ regs, int R, int* __
         if (sums) sums[4 * r + 3] = (long long)rg.w * rg.h;
     }
 }
+
+// ------------------------------------------------------------------------------------------
+// K8: contour statistics of the final mask without tracing contours (row a12; inference/segmentation.py:486-525:
+// cv2.findContours(RETR_EXTERNAL, CHAIN_APPROX_SIMPLE), contours with contourArea < 10 dropped, perimeter = sum of
+// arcLength).  The external contours are the outer borders of the 8-connected components of the HOLE-FILLED mask;
+// Suzuki's border following moves between pixel centres and every move appears exactly once in one 2x2 pixel window
+// around a lattice vertex (outside the ROI = 0):
+//     two edge-adjacent foreground pixels -> one axis move;  three foreground pixels -> one diagonal move;
+//     two diagonal foreground pixels -> two diagonal moves (a pinch);  one or four -> none
+// so arcLength = n_axis + sqrt(2) * n_diag and contourArea = |sum of cross products p x p' over the moves| / 2 (moves
+// oriented with the foreground on the right).  Pinned against cv2 on the CPU (oracle/contours.py): counts and areas
+// exact, perimeter to the float32 rounding of cv2's per-segment lengths (< 1e-7 relative).
+//   k8_kept_bits  (adaptive method) kept mask as bit rows from the final labels + per-label areas
+//   k7_fill + K4 union-find on the filled mask (reused)
+//   k8_moves      one thread per 32 lattice vertices: window patterns by bit arithmetic, one atomic per run of moves of
+//                 the same component into (n_axis | n_diag << 32, cross) accumulators on the component's root block
+//   k8_reduce     per region: components with contourArea >= 10 -> (n_axis, n_diag, n_contours)
+__global__ void __launch_bounds__(K4_THREADS)
+k8_kept_bits(const qc_seg_region* __restrict__ regs, int R, int total_bands, const int* __restrict__ g_band_off,
+             const unsigned* __restrict__ bits, const int* __restrict__ label_of_block, const int* __restrict__ stats,
+             unsigned* __restrict__ bits_out) {
+    __shared__ int s_off[K4_LOC_MAX + 1];
+    const int tid = threadIdx.x;
+    const int* off = loc_load(s_off, g_band_off, R);
+    for (int t = blockIdx.x; t < total_bands; t += gridDim.x) {
+        const qc_seg_region rg = regs[loc_find(off, R, t)];
+        const int wpr = wpr_of(rg), bw = bw_of(rg);
+        const int BR = k4_band_rows(rg.w);
+        const int y0 = (t - rg.band_offset) * BR, y1 = min(y0 + BR, rg.h);
+        const int by0 = y0 >> 1, by1 = (y1 + 1) >> 1;
+        const unsigned* B = bits + rg.bits_offset;
+        unsigned* O = bits_out + rg.bits_offset;
+        const int* st = stats + (long long)rg.stats_offset * 5;
+        for (int ci = tid; ci < (by1 - by0) * wpr; ci += K4_THREADS) {
+            const int byy = ci / wpr, wx = ci - byy * wpr, by = by0 + byy;
+            const bool two = 2 * by + 1 < rg.h;
+            const unsigned r0 = __ldg(B + (long long)(2 * by) * wpr + wx);
+            const unsigned r1 = two ? __ldg(B + (long long)(2 * by + 1) * wpr + wx) : 0u;
+            const unsigned v = r0 | r1;
+            unsigned keep = 0;
+            if (v) {
+                const int* prow = label_of_block + rg.blk_offset + (long long)by * bw + wx * 16;
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    if (!((v >> (2 * k)) & 3u)) continue;
+                    const int lab = prow[k];            // components beyond max_comp have no recorded area: kept (as k4_final)
+                    if (lab >= rg.max_comp || st[(long long)lab * 5 + 4] >= rg.min_area) keep |= 3u << (2 * k);
+                }
+            }
+            O[(long long)(2 * by) * wpr + wx] = r0 & keep;
+            if (two) O[(long long)(2 * by + 1) * wpr + wx] = r1 & keep;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(K4_THREADS)
+k8_moves(const qc_seg_region* __restrict__ regs, int R, int total_bands, const int* __restrict__ g_band_off,
+         const unsigned* __restrict__ bits, const int* __restrict__ parent, unsigned long long* __restrict__ acc_n,
+         long long* __restrict__ acc_x) {
+    __shared__ int s_off[K4_LOC_MAX + 1];
+    const int tid = threadIdx.x;
+    const int* off = loc_load(s_off, g_band_off, R);
+    for (int t = blockIdx.x; t < total_bands; t += gridDim.x) {
+        const qc_seg_region rg = regs[loc_find(off, R, t)];
+        const int wpr = wpr_of(rg), bw = bw_of(rg);
+        const int BR = k4_band_rows(rg.w);
+        const int y0 = (t - rg.band_offset) * BR, y1 = min(y0 + BR, rg.h);
+        const unsigned* B = bits + rg.bits_offset;
+        const int* P = parent + rg.blk_offset;
+        // vertex rows vy = y0 .. y1-1 (+ row h for the last band), vertex words 0 .. w/32 (vertex column w included)
+        const int vy1 = y1 == rg.h ? rg.h + 1 : y1;
+        const int vwords = (rg.w >> 5) + 1;
+        auto word = [&](int y, int wx) -> unsigned {
+            return (y < 0 || y >= rg.h || wx < 0 || wx >= wpr) ? 0u : __ldg(B + (long long)y * wpr + wx);
+        };
+        for (int it = tid; it < (vy1 - y0) * vwords; it += K4_THREADS) {
+            const int vyy = it / vwords, wx = it - vyy * vwords, vy = y0 + vyy;
+            const unsigned up = word(vy - 1, wx), dn = word(vy, wx);
+            if (!(up | dn) && !((word(vy - 1, wx - 1) | word(vy, wx - 1)) >> 31)) continue;
+            // bit j <-> vertex column vx = 32*wx + j: a = (vy-1, vx-1), b = (vy-1, vx), c = (vy, vx-1), d = (vy, vx)
+            const unsigned b = up, d = dn;
+            const unsigned a = (up << 1) | (word(vy - 1, wx - 1) >> 31), c = (dn << 1) | (word(vy, wx - 1) >> 31);
+            const unsigned e_cd = ~a & ~b & c & d, e_ab = a & b & ~c & ~d, e_bd = ~a & b & ~c & d, e_ac = a & ~b & c & ~d;
+            const unsigned t_d = a & b & c & ~d, t_a = ~a & b & c & d, t_b = a & ~b & c & d, t_c = a & b & ~c & d;
+            const unsigned p_ad = a & ~b & ~c & d, p_bc = ~a & b & c & ~d;
+            unsigned ev = e_cd | e_ab | e_bd | e_ac | t_d | t_a | t_b | t_c | p_ad | p_bc;
+            int cur = -1;
+            unsigned long long n_acc = 0;
+            long long x_acc = 0;
+            auto flush = [&]() {
+                if (cur >= 0) {
+                    atomicAdd(acc_n + rg.blk_offset + cur, n_acc);
+                    if (x_acc) atomicAdd(reinterpret_cast<unsigned long long*>(acc_x + rg.blk_offset + cur), (unsigned long long)x_acc);
+                }
+            };
+            while (ev) {
+                const int j = __ffs(ev) - 1;
+                ev &= ev - 1;
+                const unsigned m = 1u << j;
+                const long long vx = 32 * wx + j;
+                const long long ax = vx - 1, ay = vy - 1, bx = vx, by_ = vy - 1, cx = vx - 1, cy = vy, dx = vx, dy = vy;
+                long long px, py;                       // a foreground pixel of the window (identifies the component)
+                unsigned long long n;                   // n_axis | n_diag << 32
+                long long cr = 0;
+                if (e_cd & m) { n = 1ull; cr = cx * dy - dx * cy; px = cx; py = cy; }                  // c -> d
+                else if (e_ab & m) { n = 1ull; cr = bx * ay - ax * by_; px = ax; py = ay; }            // b -> a
+                else if (e_bd & m) { n = 1ull; cr = dx * by_ - bx * dy; px = bx; py = by_; }           // d -> b
+                else if (e_ac & m) { n = 1ull; cr = ax * cy - cx * ay; px = ax; py = ay; }             // a -> c
+                else if (t_d & m) { n = 1ull << 32; cr = bx * cy - cx * by_; px = ax; py = ay; }       // b -> c
+                else if (t_a & m) { n = 1ull << 32; cr = cx * by_ - bx * cy; px = bx; py = by_; }      // c -> b
+                else if (t_b & m) { n = 1ull << 32; cr = ax * dy - dx * ay; px = ax; py = ay; }        // a -> d
+                else if (t_c & m) { n = 1ull << 32; cr = dx * ay - ax * dy; px = ax; py = ay; }        // d -> a
+                else if (p_ad & m) { n = 2ull << 32; px = ax; py = ay; }                               // a <-> d
+                else { n = 2ull << 32; px = bx; py = by_; }                                            // b <-> c
+                const int root = P[(py >> 1) * bw + (px >> 1)] - rg.blk_offset;
+                if (root != cur) { flush(); cur = root; n_acc = 0; x_acc = 0; }
+                n_acc += n;
+                x_acc += cr;
+            }
+            flush();
+        }
+    }
+}
+
+__global__ void __launch_bounds__(K4_THREADS)
+k8_reduce(const qc_seg_region* __restrict__ regs, int R, int total_bands, const int* __restrict__ g_band_off,
+          const unsigned* __restrict__ bits, const int* __restrict__ parent, const unsigned long long* __restrict__ acc_n,
+          const long long* __restrict__ acc_x, long long* __restrict__ out_contours) {
+    __shared__ int s_off[K4_LOC_MAX + 1];
+    __shared__ long long s_acc[K4_THREADS / 32][3];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int* off = loc_load(s_off, g_band_off, R);
+    for (int t = blockIdx.x; t < total_bands; t += gridDim.x) {
+        const int r = loc_find(off, R, t);
+        const qc_seg_region rg = regs[r];
+        const int wpr = wpr_of(rg), bw = bw_of(rg);
+        const int BR = k4_band_rows(rg.w);
+        const int y0 = (t - rg.band_offset) * BR, y1 = min(y0 + BR, rg.h);
+        const int by0 = y0 >> 1, by1 = (y1 + 1) >> 1;
+        const unsigned* B = bits + rg.bits_offset;
+        long long n_axis = 0, n_diag = 0, n_cont = 0;
+        for (int ci = tid; ci < (by1 - by0) * wpr; ci += K4_THREADS) {
+            const int byy = ci / wpr, wx = ci - byy * wpr, by = by0 + byy;
+            const unsigned r0 = __ldg(B + (long long)(2 * by) * wpr + wx);
+            const unsigned r1 = (2 * by + 1 < rg.h) ? __ldg(B + (long long)(2 * by + 1) * wpr + wx) : 0u;
+            unsigned v = r0 | r1;
+            v = (v | (v >> 1)) & 0x55555555u;
+            while (v) {
+                const int k = (__ffs(v) - 1) >> 1;
+                v &= v - 1;
+                const int g = rg.blk_offset + by * bw + wx * 16 + k;
+                if (parent[g] != g) continue;                       // component roots only
+                const long long x2 = acc_x[g];
+                if ((x2 < 0 ? -x2 : x2) >= 2 * 10) {                // contourArea = |cross| / 2 >= 10  (:498-500)
+                    const unsigned long long nn = acc_n[g];
+                    n_axis += (long long)(nn & 0xFFFFFFFFull);
+                    n_diag += (long long)(nn >> 32);
+                    n_cont += 1;
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            n_axis += __shfl_xor_sync(0xffffffffu, n_axis, o);
+            n_diag += __shfl_xor_sync(0xffffffffu, n_diag, o);
+            n_cont += __shfl_xor_sync(0xffffffffu, n_cont, o);
+        }
+        __syncthreads();
+        if (lane == 0) { s_acc[warp][0] = n_axis; s_acc[warp][1] = n_diag; s_acc[warp][2] = n_cont; }
+        __syncthreads();
+        if (tid == 0) {
+            for (int k = 1; k < K4_THREADS / 32; ++k) { n_axis += s_acc[k][0]; n_diag += s_acc[k][1]; n_cont += s_acc[k][2]; }
+            typedef unsigned long long ull;
+            if (n_cont) {
+                atomicAdd(reinterpret_cast<ull*>(out_contours + 4 * r + 0), (ull)n_axis);
+                atomicAdd(reinterpret_cast<ull*>(out_contours + 4 * r + 1), (ull)n_diag);
+                atomicAdd(reinterpret_cast<ull*>(out_contours + 4 * r + 2), (ull)n_cont);
+            }
+        }
+    }
+}

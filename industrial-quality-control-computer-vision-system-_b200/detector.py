@@ -522,6 +522,52 @@ class _LazyFullMask:
         return np.asarray(self)[k]
 
 
+class _LazyContours:
+    """The contour list of one region (inference/segmentation.py:102-110).  Its LENGTH comes from the device (K8 counts
+    the external contours with contourArea >= 10 without tracing them); the point arrays are traced by cv2 on the
+    ROI-sized mask only when somebody reads them."""
+
+    def __init__(self, local, x1, y1, count):
+        self._local, self._x1, self._y1, self._n, self._items = local, x1, y1, int(count), None
+
+    def _get(self):
+        if self._items is None:
+            cs, _ = cv2.findContours(np.ascontiguousarray(self._local), cv2.RETR_EXTERNAL, cv2.CHAIN_APPROX_SIMPLE)
+            out = []
+            for c in cs:
+                if cv2.contourArea(c) >= 10:                                    # :498-500
+                    g = c.copy(); g[:, 0, 0] += self._x1; g[:, 0, 1] += self._y1
+                    out.append(g)
+            self._items = out
+        return self._items
+
+    def __len__(self):
+        return self._n
+
+    def __iter__(self):
+        return iter(self._get())
+
+    def __getitem__(self, i):
+        return self._get()[i]
+
+
+class _LazyConcat:
+    """``segmentation_results['contours']``: all regions' contours in order (:131), traced on first use."""
+
+    def __init__(self, parts):
+        self._parts = parts
+
+    def __len__(self):
+        return sum(len(p) for p in self._parts)
+
+    def __iter__(self):
+        for p in self._parts:
+            yield from p
+
+    def __getitem__(self, i):
+        return list(self)[i]
+
+
 class ImageSegmentator:
     """inference/segmentation.py:21 -- the reference's per-class methods on device (K7, csrc/k7_refseg.cuh):
 
@@ -576,7 +622,7 @@ class ImageSegmentator:
             H, W = img.shape[:2]
             sel = self._select(detections, H, W)
             frames = _frames if _frames is not None else torch.from_numpy(img[None]).to(dev)
-            local_masks, areas, sums = {}, {}, {}
+            local_masks, areas, sums, cstats = {}, {}, {}, {}
             for method, code, iters in (("adaptive", ffi.QC_SEG_REF_ADAPTIVE, 1), ("threshold", ffi.QC_SEG_REF_THRESHOLD, 2)):
                 grp = [k for k, s_ in enumerate(sel) if (s_[5] == "adaptive") == (method == "adaptive")]
                 if not grp:
@@ -592,40 +638,57 @@ class ImageSegmentator:
                     regs["thr_scale"] = [self.THRESHOLD_FACTORS.get(c, 1.0) for c in cls]
                     regs["max_comp"] = [2] * len(grp)
                 res = qc.segment(frames, regs, morph_iters=iters, want_labels=False, swap_rb=False, method=code,
-                                 want_sums=(method == "threshold"))
+                                 want_sums=(method == "threshold"), want_contours=True)
                 mask_all = res["mask"].cpu().numpy()
                 area = res["area"].cpu().numpy()
                 sm = res["sums"].cpu().numpy() if res["sums"] is not None else None
+                ct = res["contours"].cpu().numpy()
                 for j, k in enumerate(grp):
                     _, x1, y1, x2, y2, _m = sel[k]
                     o = int(res["regions"][j].out_offset)
                     local_masks[k] = mask_all[o:o + (x2 - x1) * (y2 - y1)].reshape(y2 - y1, x2 - x1)
                     areas[k] = int(area[j])
                     sums[k] = sm[j] if sm is not None else None
-            return self._assemble(img, detections, sel, local_masks, areas, sums)
+                    cstats[k] = ct[j]
+            return self._assemble(img, detections, sel, local_masks, areas, sums, cstats=cstats)
         except Exception as e:
             logger.error(f"Error in defect segmentation: {str(e)}")
             return {"error": str(e)}
 
-    def _assemble(self, img: np.ndarray, detections: List[Dict], sel, local_masks, areas, sums, bgr: bool = False) -> Dict:
+    def _assemble(self, img: np.ndarray, detections: List[Dict], sel, local_masks, areas, sums, bgr: bool = False,
+                  cstats=None) -> Dict:
         """The reference's result dictionary (:113-138) from the device outputs of every selected ROI.  ``img`` is the
-        frame the masks were computed on (``bgr``: in the caller's channel order, i.e. before detector.py:234)."""
+        frame the masks were computed on (``bgr``: in the caller's channel order, i.e. before detector.py:234).
+        ``cstats[k]`` = K8's (n_axis, n_diag, n_contours): perimeter, compactness and the contour count come from the
+        device and the contour point arrays are traced lazily; without it cv2 traces every mask here."""
         out = {"segmented_regions": [], "masks": [], "contours": [], "area_analysis": {},
                "total_defect_area": 0, "defect_density": 0.0}
         H, W = img.shape[:2]
         total_image_area = H * W
         total_defect_area = 0
-        gray = None
+        parts = []
         for k, (i, x1, y1, x2, y2, method) in enumerate(sel):
             d = detections[i]
             local = local_masks[k]
             defect_area = areas[k]
             total_defect_area += defect_area
-            contours = self._find_contours(local)
-            gcontours = []
-            for c in contours:
-                g = c.copy(); g[:, 0, 0] += x1; g[:, 0, 1] += y1
-                gcontours.append(g)
+            if cstats is not None:
+                n_axis, n_diag, n_cont = (int(v) for v in cstats[k][:3])
+                gcontours = _LazyContours(local, x1, y1, n_cont)
+                perimeter = n_axis + float(np.sqrt(2.0)) * n_diag                # sum of cv2.arcLength, :508-513
+                if n_cont == 0 or defect_area == 0 or perimeter == 0:            # :515-525
+                    compactness = 0.0
+                else:
+                    compactness = min((4 * np.pi * defect_area) / (perimeter ** 2), 1.0)
+            else:
+                contours = self._find_contours(local)
+                gcontours = []
+                for c in contours:
+                    g = c.copy(); g[:, 0, 0] += x1; g[:, 0, 1] += y1
+                    gcontours.append(g)
+                perimeter = self._calculate_perimeter(contours)
+                compactness = self._calculate_compactness(defect_area, contours)
+            parts.append(gcontours)
             gmask = _LazyFullMask((H, W), y1, x1, local)
             if method == "adaptive":
                 roi = img[y1:y2, x1:x2]
@@ -638,11 +701,10 @@ class ImageSegmentator:
                 "detection_id": i, "defect_class": d["class"], "confidence": d.get("confidence", 0.0),
                 "bbox": d["bbox"], "mask": gmask, "local_mask": local, "contours": gcontours,
                 "area_pixels": defect_area, "area_percentage": (defect_area / total_image_area) * 100,
-                "perimeter": self._calculate_perimeter(contours),
-                "compactness": self._calculate_compactness(defect_area, contours),
+                "perimeter": perimeter, "compactness": compactness,
                 "segmentation_method": method, "confidence_score": conf})
             out["masks"].append(gmask)
-            out["contours"].extend(gcontours)
+        out["contours"] = _LazyConcat(parts) if cstats is not None else [c for p_ in parts for c in p_]
         out["total_defect_area"] = total_defect_area
         out["defect_density"] = (total_defect_area / total_image_area) * 100
         out["area_analysis"] = self._analyze_defect_areas(out["segmented_regions"])
@@ -915,7 +977,7 @@ class QualityControlDetector:
                     continue
                 segmentation_results = {}
                 if include_segmentation and dets:
-                    sel, lm, ar, sm = [], {}, {}, {}
+                    sel, lm, ar, sm, cs_ = [], {}, {}, {}, {}
                     for k in ks:
                         x1, y1, x2, y2 = (int(v) for v in res.roi_box[k])
                         code = int(res.seg_method[k])
@@ -924,8 +986,9 @@ class QualityControlDetector:
                         j = len(sel)
                         sel.append((int(res.roi_det[k]), x1, y1, x2, y2, name))
                         lm[j], ar[j], sm[j] = masks_host[int(k)], int(res.seg_area[k]), res.seg_sums[k]
+                        cs_[j] = res.seg_contours[k]
                         assert (code == ffi.QC_SEG_REF_ADAPTIVE) == (name == "adaptive")
-                    segmentation_results = seg._assemble(frames_np[i], dets, sel, lm, ar, sm, bgr=raw_ok)
+                    segmentation_results = seg._assemble(frames_np[i], dets, sel, lm, ar, sm, bgr=raw_ok, cstats=cs_)
                 final = self.postprocessor.process_results(ensemble_results, segmentation_results, shape)
                 dt = per_image + 0.0
                 self._update_performance_stats(dt)

@@ -103,7 +103,7 @@ _SIGS = {
     "qc_segment_ref_workspace_bytes": (C.c_size_t, [C.POINTER(SegParams), C.c_int]),
     "qc_segment_ref": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(SegParams), C.c_void_p, C.c_void_p, C.c_int,
                                  C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p,
-                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "qc_spc_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "qc_rules_cluster": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                    C.c_double, C.c_void_p, C.c_void_p]),
@@ -439,7 +439,7 @@ class Context:
 
     def segment(self, imgs: torch.Tensor, regions, morph_iters: int = 1, want_mask: bool = True,
                 want_labels: bool = True, swap_rb: bool = False, method: int = QC_SEG_COMPOSITE,
-                adaptive_c: int = 2, want_sums: bool = False):
+                adaptive_c: int = 2, want_sums: bool = False, want_contours: bool = False):
         """imgs: uint8 CUDA [n,h,w] (gray) or [n,h,w,3] (RGB).  Returns dict of device tensors + the plan.
         method: QC_SEG_COMPOSITE (K4: Otsu -> morphology -> CCL), QC_SEG_REF_THRESHOLD / QC_SEG_REF_ADAPTIVE (K7: the
         reference's _threshold_segmentation / _adaptive_segmentation, see include/qcgraft.h)."""
@@ -457,7 +457,8 @@ class Context:
                         stats=torch.zeros((0, 5), dtype=torch.int32, device=dev),
                         thr=torch.zeros(0, dtype=torch.int32, device=dev),
                         area=torch.zeros(0, dtype=torch.int64, device=dev),
-                        sums=torch.zeros((0, 4), dtype=torch.int64, device=dev))
+                        sums=torch.zeros((0, 4), dtype=torch.int64, device=dev),
+                        contours=torch.zeros((0, 4), dtype=torch.int64, device=dev))
         regs_dev = torch.from_numpy(arr[:R].view(np.uint8).reshape(-1)).to(dev, non_blocking=False)
         mask = torch.empty(p.total_pixels, dtype=torch.uint8, device=dev) if want_mask else None
         labels = torch.empty(p.total_pixels, dtype=torch.int32, device=dev) if want_labels else None
@@ -465,7 +466,7 @@ class Context:
         stats = torch.empty((p.total_stats_rows, 5), dtype=torch.int32, device=dev)
         thr = torch.empty(R, dtype=torch.int32, device=dev)
         area = torch.empty(R, dtype=torch.int64, device=dev)
-        sums = None
+        sums = contours = None
         if method == QC_SEG_COMPOSITE:
             need = self.lib.qc_segment_workspace_bytes(C.byref(p))
             ws = self.workspace("seg", need)
@@ -475,6 +476,7 @@ class Context:
             self._check(rc, "qc_segment")
         else:
             sums = torch.empty((R, 4), dtype=torch.int64, device=dev) if want_sums else None
+            contours = torch.empty((R, 4), dtype=torch.int64, device=dev) if want_contours else None
             ak, pitch, maxb = (None, 0, 0)
             if method == QC_SEG_REF_ADAPTIVE:
                 ak, pitch, maxb = self.adaptive_kernel_table(max(11, min(p.max_region_w, p.max_region_h) // 10) | 1)
@@ -483,10 +485,10 @@ class Context:
             rc = self.lib.qc_segment_ref(self.h, method, imgs.data_ptr(), C.byref(p), regs_dev.data_ptr(), _ptr(ak), pitch,
                                          maxb, adaptive_c, ws.data_ptr(), ws.numel(), _ptr(mask), _ptr(labels),
                                          ncomp.data_ptr(), stats.data_ptr(), thr.data_ptr(), area.data_ptr(), _ptr(sums),
-                                         _stream(dev))
+                                         _ptr(contours), _stream(dev))
             self._check(rc, "qc_segment_ref")
         return dict(regions=arr, params=p, regs_dev=regs_dev, mask=mask, labels=labels, ncomp=ncomp, stats=stats,
-                    thr=thr, area=area, sums=sums)
+                    thr=thr, area=area, sums=sums, contours=contours)
 
     # -- SPC -------------------------------------------------------------------------------
     # -- K6 --------------------------------------------------------------------------------

@@ -93,6 +93,7 @@ class BatchResult:
     seg_ncomp: Optional[np.ndarray] = None      # [K]
     seg_method: Optional[np.ndarray] = None     # [K] ffi.QC_SEG_* the ROI went through
     seg_sums: Optional[np.ndarray] = None       # [K,4] int64 confidence sums (threshold method rows)
+    seg_contours: Optional[np.ndarray] = None   # [K,4] int64 (n_axis, n_diag, n_contours, 0): perimeter = n_axis + sqrt(2) n_diag
     spc: Optional[np.ndarray] = None            # [9] float64
     seg: Optional[dict] = None                  # device tensors of K4 (mask/labels/stats) when requested
     timings_ms: dict = field(default_factory=dict)
@@ -125,6 +126,7 @@ class InspectionPipeline:
         # chain (Otsu -> 3x3 morphology -> CCL) for every class
         assert seg_mode in ("reference", "composite")
         self.seg_mode = seg_mode
+        self.seg_contours = True             # K8: perimeter / contour count of every ROI mask on the device
         self.record = False          # bench.py: CUDA-event pairs around every stage
         self.events = {}
         # host frames: H2D on a copy stream into one of two staging buffers, so the copy of batch i+1 overlaps the
@@ -336,7 +338,7 @@ class InspectionPipeline:
             host["probs"] = stage(probs)
         if seg is not None:
             for gi, g in enumerate(seg):
-                for k in ("area", "thr", "ncomp", "sums"):
+                for k in ("area", "thr", "ncomp", "sums", "contours"):
                     if g["seg"].get(k) is not None:
                         host[f"{k}{gi}"] = stage(g["seg"][k])
         done = torch.cuda.Event()
@@ -378,7 +380,8 @@ class InspectionPipeline:
             # gray is read as the reference does AFTER inference/detector.py:234 swapped the channels
             with self._timed(name):
                 seg = qc.segment(frames, regs, morph_iters=iters, swap_rb=swap_rb, want_mask=keep, want_labels=keep,
-                                 method=code, want_sums=(code == ffi.QC_SEG_REF_THRESHOLD))
+                                 method=code, want_sums=(code == ffi.QC_SEG_REF_THRESHOLD),
+                                 want_contours=(code != ffi.QC_SEG_COMPOSITE and self.seg_contours))
             groups.append(dict(name=name, idx=idx, code=code, iters=iters, seg=seg, cap=cap, regs=regs, swap_rb=swap_rb))
         return groups
 
@@ -463,6 +466,7 @@ class PendingResult:
             res.seg_ncomp = np.zeros(K, np.int32)
             res.seg_method = np.zeros(K, np.int32)
             res.seg_sums = np.zeros((K, 4), np.int64)
+            res.seg_contours = np.zeros((K, 4), np.int64)
             for gi, g in enumerate(m["seg"]):
                 idx = g["idx"]
                 area = self.host[f"area{gi}"].numpy().copy()
@@ -480,6 +484,8 @@ class PendingResult:
                 res.seg_method[idx] = g["code"]
                 if f"sums{gi}" in self.host:
                     res.seg_sums[idx] = self.host[f"sums{gi}"].numpy()
+                if f"contours{gi}" in self.host:
+                    res.seg_contours[idx] = self.host[f"contours{gi}"].numpy()
             if m["keep"]:
                 res.seg = m["seg"]
         self.frames = None

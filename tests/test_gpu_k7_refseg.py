@@ -16,7 +16,7 @@ import pytest
 import torch
 
 from gpu_common import qc  # noqa: F401
-from oracle import refseg as R, segment as oseg
+from oracle import refseg as R, segment as oseg, contours as ocont
 from qcgraft import ffi, synth
 
 pytestmark = pytest.mark.gpu
@@ -45,13 +45,23 @@ def _frame(seed, H, W, gray=True):
     return cv2.cvtColor(f, cv2.COLOR_RGB2GRAY) if gray else f
 
 
+def _check_contours(res, i, mask):
+    """K8 (n_axis, n_diag, n_contours) of region i vs cv2.findContours / contourArea / arcLength on the same mask
+    (inference/segmentation.py:486-525): contour count exact, perimeter to the float32 rounding of cv2's segments."""
+    per, n, _areas = ocont.contour_stats(mask)
+    n_axis, n_diag, n_cont, _ = (int(v) for v in res["contours"][i].cpu().numpy())
+    assert n_cont == n, f"region {i}: {n_cont} contours vs cv2 {n}"
+    got = n_axis + np.sqrt(2.0) * n_diag
+    assert abs(got - per) <= 1e-6 * max(1.0, per), f"region {i}: perimeter {got} vs cv2 {per}"
+
+
 def _run_threshold(qc, img, regs, classes):
     rr = []
     for r, c in zip(regs, classes):
         rr.append(dict(r, polarity=0 if c in R.DARK_CLASSES else 1, thr_scale=R.THRESHOLD_FACTORS.get(c, 1.0),
                        min_area=10, max_comp=2))
     res = qc.segment(torch.from_numpy(img[None]).cuda(), rr, morph_iters=2, method=ffi.QC_SEG_REF_THRESHOLD,
-                     want_sums=True)
+                     want_sums=True, want_contours=True)
     torch.cuda.synchronize()
     return res
 
@@ -80,6 +90,7 @@ def _check_threshold(res, i, img, reg, cls):
     assert list(s) == [int(r64[m > 0].sum()), int(r64.sum()), int((r64 * r64).sum()), roi.size]
     from qcgraft.detector import ImageSegmentator
     assert abs(ImageSegmentator._threshold_confidence(s, area) - conf) <= 1e-9
+    _check_contours(res, i, m)
 
 
 def test_threshold_method_random_rois(qc):
@@ -140,7 +151,8 @@ def test_threshold_method_large_regions(qc):
 
 def _run_adaptive(qc, img, regs, classes, max_comp=None):
     rr = [dict(r, polarity=0 if c in R.DARK_CLASSES else 1, min_area=20) for r, c in zip(regs, classes)]
-    res = qc.segment(torch.from_numpy(img[None]).cuda(), rr, morph_iters=1, method=ffi.QC_SEG_REF_ADAPTIVE)
+    res = qc.segment(torch.from_numpy(img[None]).cuda(), rr, morph_iters=1, method=ffi.QC_SEG_REF_ADAPTIVE,
+                     want_contours=True)
     torch.cuda.synchronize()
     return res
 
@@ -164,6 +176,7 @@ def _check_adaptive(res, i, img, reg, cls, budget=0):
         keep[0] = False
         labf = np.where(keep[lab], lab, 0)
         assert np.array_equal(res["labels"][o:o + w * h].view(h, w).cpu().numpy(), labf)
+        _check_contours(res, i, m)
     return bad
 
 
@@ -224,11 +237,36 @@ def test_dropin_segment_defects_matches_reference_golden(qc):
             assert r["area_pixels"] == g["area_pixels"], (fi, g["id"])
             assert r["segmentation_method"] == g["method"], (fi, g["id"])
             assert abs(r["confidence_score"] - g["confidence_score"]) <= 1e-9, (fi, g["id"])
-            assert abs(r["perimeter"] - g["perimeter"]) <= 1e-9 * max(1.0, g["perimeter"])
-            assert abs(r["compactness"] - g["compactness"]) <= 1e-9
+            # perimeter = n_axis + sqrt(2) n_diag from K8; cv2 sums float32 segment lengths: <= 1e-7 relative apart
+            assert abs(r["perimeter"] - g["perimeter"]) <= 1e-6 * max(1.0, g["perimeter"])
+            assert abs(r["compactness"] - g["compactness"]) <= 1e-6
             assert len(r["contours"]) == g["n_contours"]
             assert np.array_equal(np.asarray(r["mask"])[b["y1"]:b["y1"] + h, b["x1"]:b["x1"] + w] > 0, gm > 0)
             n += 1
         ref_ids = [g["id"] for g in g_rows if g["method"] != "threshold_fallback"]
         assert sum(got[i]["area_pixels"] for i in ref_ids) == gold["frames"][fi]["total_defect_area"]
     assert n == gold["n_rois"] >= 20
+
+
+def test_contour_statistics_on_structured_masks(qc):
+    """K8 on shapes that stress border following: one-pixel lines, diagonal chains (pinches), rings with nested
+    components (RETR_EXTERNAL ignores what sits in a hole), shapes touching every ROI border, checkerboards."""
+    H = W = 200
+    img = np.full((H, W), 60, np.uint8)
+    yy, xx = np.mgrid[0:H, 0:W]
+    img[20, 10:190] = 230; img[30:180, 15] = 230                          # 1-px lines
+    img[(yy - xx == 20) & (yy > 40) & (yy < 160)] = 230                   # diagonal chain
+    d = np.maximum(np.abs(yy - 110), np.abs(xx - 120))
+    img[(d >= 40) & (d < 46)] = 230; img[(d >= 15) & (d < 25)] = 230      # ring with a ring inside its hole
+    img[105:116, 115:126] = 230                                           # ... and a blob inside that
+    img[0:8, 60:140] = 230; img[H - 6:, 30:90] = 230; img[70:130, W - 5:] = 230
+    img[160:190, 150:190][((yy[160:190, 150:190] // 2) + (xx[160:190, 150:190] // 2)) % 2 == 0] = 230
+    regs = [dict(img=0, x=0, y=0, w=W, h=H), dict(img=0, x=5, y=5, w=190, h=150), dict(img=0, x=60, y=50, w=120, h=121),
+            dict(img=0, x=140, y=150, w=60, h=50), dict(img=0, x=0, y=0, w=33, h=200)]
+    # composite-free check of the statistics: the adaptive / threshold methods produce the masks, cv2 the reference
+    res = _run_threshold(qc, img, regs, ["x"] * len(regs))
+    for i, r in enumerate(regs):
+        _check_threshold(res, i, img, r, "x")
+    res = _run_adaptive(qc, img, regs, ["other"] * len(regs))
+    for i, r in enumerate(regs):
+        _check_adaptive(res, i, img, r, "other")
