@@ -255,8 +255,10 @@ int qc_segment(qc_ctx* ctx, const uint8_t* imgs, const qc_seg_params* p,
  *     block size bs, row pitch akern_pitch floats, rows up to akern_max_block (the caller fills it with cv2's own
  *     numbers, like the K1 LUT; only needed for QC_SEG_REF_ADAPTIVE).
  *
- * out_sums (may be NULL): int64 [num_regions][4] = (sum of gray over the mask, sum of gray, sum of gray^2, pixels of
- * the ROI) -- the integers behind inference/segmentation.py:527-555's confidence (means and std of the ROI).
+ * out_sums (may be NULL): int64 [num_regions][4].  QC_SEG_REF_THRESHOLD: (sum of gray over the mask, sum of gray, sum of
+ * gray^2, pixels of the ROI) -- the integers behind inference/segmentation.py:527-555's confidence (means and std of the
+ * ROI).  QC_SEG_REF_ADAPTIVE: (Canny edge pixels on the mask, Canny edge pixels, 0, pixels of the ROI) with
+ * cv2.Canny(roi, 50, 150) computed on device bit for bit (K9) -- the integers behind :557-578's edge-overlap confidence.
  * out_contours (may be NULL): int64 [num_regions][4] = (n_axis, n_diag, n_contours, 0) of the final mask's external
  * contours with cv2.contourArea >= 10 -- inference/segmentation.py:486-525 without tracing a contour: perimeter
  * (sum of cv2.arcLength) = n_axis + sqrt(2) * n_diag, contour count = n_contours (K8, csrc/k7_refseg.cuh).

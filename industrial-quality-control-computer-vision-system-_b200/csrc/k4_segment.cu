@@ -1429,11 +1429,23 @@ int seg_run(qc_ctx* ctx, int method, const uint8_t* imgs, const qc_seg_params* p
         if (int rc = morph(w.bits2, w.bits)) return rc;
         if (int rc = unionfind(w.bits, nullptr)) return rc;
         if (int rc = label_tail(w.bits)) return rc;
-        if (o.contours) {
-            // kept mask (labels + areas are final) -> bits2; filled -> bits3; free rows of oversized regions -> bits
+        if (o.contours || o.sums) {
+            // kept mask (labels + areas are final) -> bits2
             k8_kept_bits<<<band_grid, K4_THREADS, 0, st>>>(regions, R, p->total_bands, w.band_off, w.bits, w.parent, o.stats, w.bits2);
             QC_LAUNCHED(ctx);
-            return contour_stats(w.bits2, w.bits3, w.bits);
+        }
+        if (o.contours)        // filled -> bits3; free rows of oversized regions -> bits
+            if (int rc = contour_stats(w.bits2, w.bits3, w.bits)) return rc;
+        if (o.sums) {
+            // K9: Canny(50, 150) edges and their overlap with the kept mask (:557-578); candidates -> bits, strong -> bits3
+            k9_canny_nms<<<band_grid, K4_THREADS, 0, st>>>(regions, R, p->total_bands, w.band_off, gray7, 50, 150, w.bits, w.bits3);
+            QC_LAUNCHED(ctx);
+            if (int rc = unionfind(w.bits, w.rank)) return rc;                 // w.rank = "component holds a strong pixel"
+            k9_mark<<<band_grid, K4_THREADS, 0, st>>>(regions, R, p->total_bands, w.band_off, w.bits3, w.parent, w.rank);
+            QC_LAUNCHED(ctx);
+            k9_overlap<<<band_grid, K4_THREADS, 0, st>>>(regions, R, p->total_bands, w.band_off, w.bits, w.bits2, w.parent, w.rank,
+                                                         (long long*)o.sums);
+            QC_LAUNCHED(ctx);
         }
         return QC_OK;
     }

@@ -1022,3 +1022,167 @@ k8_reduce(const qc_seg_region* __restrict__ regs, int R, int total_bands, const 
         }
     }
 }
+
+// ------------------------------------------------------------------------------------------
+// K9: cv2.Canny(roi, low, high) (aperture 3, L1 gradient) on every ROI and its overlap with the ROI's final mask -- the
+// integers behind _calculate_adaptive_confidence (inference/segmentation.py:557-578).  All integer arithmetic, pinned bit
+// for bit against cv2 (oracle/canny.py):
+//   k9_canny_nms  32x32 tiles: 3x3 Sobel (replicate border), mag = |dx| + |dy| (zero outside the ROI), non-maximum
+//                 suppression along the quantised gradient direction (cv2's Q15 tangents) -> candidate / strong bit rows
+//   K4 union-find on the candidate rows (8-connectivity); k9_mark flags the components that hold a strong pixel
+//   k9_overlap    edges = candidates of flagged components (hysteresis); per region (edges AND mask, edges) counts
+constexpr int K9_TG22 = 13573;               // tan(22.5 deg) in Q15
+
+__global__ void __launch_bounds__(K4_THREADS)
+k9_canny_nms(const qc_seg_region* __restrict__ regs, int R, int total_bands, const int* __restrict__ g_band_off,
+             const uint8_t* __restrict__ gray_ws, int low, int high, unsigned* __restrict__ cand_bits,
+             unsigned* __restrict__ strong_bits) {
+    __shared__ uint8_t s_g[36][40];
+    __shared__ short2 s_d[34][34];
+    __shared__ int s_m[34][35];
+    __shared__ int s_off[K4_LOC_MAX + 1];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int* off = loc_load(s_off, g_band_off, R);
+    for (int t = blockIdx.x; t < total_bands; t += gridDim.x) {
+        const qc_seg_region rg = regs[loc_find(off, R, t)];
+        const int wpr = wpr_of(rg);
+        const int BR = k4_band_rows(rg.w);
+        const int y0 = (t - rg.band_offset) * BR, y1 = min(y0 + BR, rg.h);
+        const uint8_t* g = gray_ws + rg.out_offset;
+        for (int ty = y0; ty < y1; ty += 32) {
+            const int yend = min(ty + 32, y1);
+            for (int tx = 0; tx < rg.w; tx += 32) {
+                __syncthreads();
+                for (int i = tid; i < 36 * 36; i += K4_THREADS) {           // gray tile, 2-pixel halo, replicate border
+                    const int rr = i / 36, cc = i - rr * 36;
+                    const int yy = min(max(ty - 2 + rr, 0), rg.h - 1), xx = min(max(tx - 2 + cc, 0), rg.w - 1);
+                    s_g[rr][cc] = g[(long long)yy * rg.w + xx];
+                }
+                __syncthreads();
+                for (int i = tid; i < 34 * 34; i += K4_THREADS) {           // Sobel + magnitude, 1-pixel halo
+                    const int rr = i / 34, cc = i - rr * 34;
+                    const int y = ty - 1 + rr, x = tx - 1 + cc;
+                    int dx = 0, dy = 0, m = 0;
+                    if (y >= 0 && y < rg.h && x >= 0 && x < rg.w) {
+                        const int a = s_g[rr][cc], b = s_g[rr][cc + 1], c = s_g[rr][cc + 2];
+                        const int d = s_g[rr + 1][cc], f = s_g[rr + 1][cc + 2];
+                        const int gg = s_g[rr + 2][cc], hh = s_g[rr + 2][cc + 1], ii = s_g[rr + 2][cc + 2];
+                        dx = (c + 2 * f + ii) - (a + 2 * d + gg);
+                        dy = (gg + 2 * hh + ii) - (a + 2 * b + c);
+                        m = abs(dx) + abs(dy);
+                    }
+                    s_d[rr][cc] = make_short2((short)dx, (short)dy);
+                    s_m[rr][cc] = m;
+                }
+                __syncthreads();
+                for (int rr = warp; rr < 32; rr += K4_THREADS / 32) {        // non-maximum suppression
+                    const int y = ty + rr, x = tx + lane;
+                    bool cand = false, strong = false;
+                    if (y < yend && x < rg.w) {
+                        const int m = s_m[rr + 1][lane + 1];
+                        if (m > low) {
+                            const short2 d = s_d[rr + 1][lane + 1];
+                            const long long ax = abs((int)d.x), ay = (long long)abs((int)d.y) << 15;
+                            const long long tg22x = ax * K9_TG22;
+                            if (ay < tg22x) cand = m > s_m[rr + 1][lane] && m >= s_m[rr + 1][lane + 2];
+                            else if (ay > tg22x + (ax << 16)) cand = m > s_m[rr][lane + 1] && m >= s_m[rr + 2][lane + 1];
+                            else {
+                                const int sgn = ((d.x ^ d.y) < 0) ? -1 : 1;
+                                cand = m > s_m[rr][lane + 1 - sgn] && m > s_m[rr + 2][lane + 1 + sgn];
+                            }
+                            strong = cand && m > high;
+                        }
+                    }
+                    const unsigned cw = __ballot_sync(0xffffffffu, cand), sw = __ballot_sync(0xffffffffu, strong);
+                    if (lane == 0 && y < yend) {
+                        cand_bits[rg.bits_offset + (long long)y * wpr + (tx >> 5)] = cw;
+                        strong_bits[rg.bits_offset + (long long)y * wpr + (tx >> 5)] = sw;
+                    }
+                }
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(K4_THREADS)
+k9_mark(const qc_seg_region* __restrict__ regs, int R, int total_bands, const int* __restrict__ g_band_off,
+        const unsigned* __restrict__ strong_bits, const int* __restrict__ parent, int* __restrict__ flag) {
+    __shared__ int s_off[K4_LOC_MAX + 1];
+    const int tid = threadIdx.x;
+    const int* off = loc_load(s_off, g_band_off, R);
+    for (int t = blockIdx.x; t < total_bands; t += gridDim.x) {
+        const qc_seg_region rg = regs[loc_find(off, R, t)];
+        const int wpr = wpr_of(rg), bw = bw_of(rg);
+        const int BR = k4_band_rows(rg.w);
+        const int y0 = (t - rg.band_offset) * BR, y1 = min(y0 + BR, rg.h);
+        const int by0 = y0 >> 1, by1 = (y1 + 1) >> 1;
+        const unsigned* S = strong_bits + rg.bits_offset;
+        for (int ci = tid; ci < (by1 - by0) * wpr; ci += K4_THREADS) {
+            const int byy = ci / wpr, wx = ci - byy * wpr, by = by0 + byy;
+            unsigned v = __ldg(S + (long long)(2 * by) * wpr + wx);
+            if (2 * by + 1 < rg.h) v |= __ldg(S + (long long)(2 * by + 1) * wpr + wx);
+            v = (v | (v >> 1)) & 0x55555555u;
+            while (v) {
+                const int k = (__ffs(v) - 1) >> 1;
+                v &= v - 1;
+                flag[parent[rg.blk_offset + by * bw + wx * 16 + k]] = 1;      // (every writer stores the same value)
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(K4_THREADS)
+k9_overlap(const qc_seg_region* __restrict__ regs, int R, int total_bands, const int* __restrict__ g_band_off,
+           const unsigned* __restrict__ cand_bits, const unsigned* __restrict__ mask_bits, const int* __restrict__ parent,
+           const int* __restrict__ flag, long long* __restrict__ sums) {
+    __shared__ int s_off[K4_LOC_MAX + 1];
+    __shared__ int s_acc[K4_THREADS / 32][2];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int* off = loc_load(s_off, g_band_off, R);
+    for (int t = blockIdx.x; t < total_bands; t += gridDim.x) {
+        const int r = loc_find(off, R, t);
+        const qc_seg_region rg = regs[r];
+        const int wpr = wpr_of(rg), bw = bw_of(rg);
+        const int BR = k4_band_rows(rg.w);
+        const int y0 = (t - rg.band_offset) * BR, y1 = min(y0 + BR, rg.h);
+        const int by0 = y0 >> 1, by1 = (y1 + 1) >> 1;
+        const unsigned* Cb = cand_bits + rg.bits_offset;
+        const unsigned* Mb = mask_bits + rg.bits_offset;
+        int n_edge = 0, n_both = 0;
+        for (int ci = tid; ci < (by1 - by0) * wpr; ci += K4_THREADS) {
+            const int byy = ci / wpr, wx = ci - byy * wpr, by = by0 + byy;
+            const bool two = 2 * by + 1 < rg.h;
+            const unsigned c0 = __ldg(Cb + (long long)(2 * by) * wpr + wx);
+            const unsigned c1 = two ? __ldg(Cb + (long long)(2 * by + 1) * wpr + wx) : 0u;
+            unsigned v = c0 | c1;
+            if (!v) continue;
+            v = (v | (v >> 1)) & 0x55555555u;
+            unsigned keep = 0;
+            while (v) {
+                const int k = (__ffs(v) - 1) >> 1;
+                v &= v - 1;
+                if (flag[parent[rg.blk_offset + by * bw + wx * 16 + k]]) keep |= 3u << (2 * k);
+            }
+            const unsigned e0 = c0 & keep, e1 = c1 & keep;
+            n_edge += __popc(e0) + __popc(e1);
+            n_both += __popc(e0 & __ldg(Mb + (long long)(2 * by) * wpr + wx));
+            if (two) n_both += __popc(e1 & __ldg(Mb + (long long)(2 * by + 1) * wpr + wx));
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            n_edge += __shfl_xor_sync(0xffffffffu, n_edge, o);
+            n_both += __shfl_xor_sync(0xffffffffu, n_both, o);
+        }
+        __syncthreads();
+        if (lane == 0) { s_acc[warp][0] = n_edge; s_acc[warp][1] = n_both; }
+        __syncthreads();
+        if (tid == 0) {
+            for (int k = 1; k < K4_THREADS / 32; ++k) { n_edge += s_acc[k][0]; n_both += s_acc[k][1]; }
+            typedef unsigned long long ull;
+            if (n_edge) {
+                atomicAdd(reinterpret_cast<ull*>(sums + 4 * r + 0), (ull)n_both);
+                atomicAdd(reinterpret_cast<ull*>(sums + 4 * r + 1), (ull)n_edge);
+            }
+        }
+    }
+}

@@ -638,7 +638,7 @@ class ImageSegmentator:
                     regs["thr_scale"] = [self.THRESHOLD_FACTORS.get(c, 1.0) for c in cls]
                     regs["max_comp"] = [2] * len(grp)
                 res = qc.segment(frames, regs, morph_iters=iters, want_labels=False, swap_rb=False, method=code,
-                                 want_sums=(method == "threshold"), want_contours=True)
+                                 want_sums=True, want_contours=True)
                 mask_all = res["mask"].cpu().numpy()
                 area = res["area"].cpu().numpy()
                 sm = res["sums"].cpu().numpy() if res["sums"] is not None else None
@@ -690,7 +690,9 @@ class ImageSegmentator:
                 compactness = self._calculate_compactness(defect_area, contours)
             parts.append(gcontours)
             gmask = _LazyFullMask((H, W), y1, x1, local)
-            if method == "adaptive":
+            if method == "adaptive" and sums.get(k) is not None:
+                conf = self._adaptive_confidence_from_counts(sums[k], defect_area)      # K9: Canny overlap on device
+            elif method == "adaptive":
                 roi = img[y1:y2, x1:x2]
                 if roi.ndim == 3:            # gray of the ROI == ROI of the gray frame (per-pixel transform)
                     roi = cv2.cvtColor(np.ascontiguousarray(roi), cv2.COLOR_BGR2GRAY if bgr else cv2.COLOR_RGB2GRAY)
@@ -720,6 +722,16 @@ class ImageSegmentator:
         fg_mean, bg_mean = s_fg / area, (s_all - s_fg) / (n - area)
         std = float(np.sqrt(n * s_sq - s_all * s_all) / n)
         return float(min(abs(fg_mean - bg_mean) / (std + 1e-6) / 3.0, 1.0))
+
+    @staticmethod
+    def _adaptive_confidence_from_counts(counts, area: int) -> float:
+        """inference/segmentation.py:557-578 from K9's integers (Canny edge pixels on the mask, Canny edge pixels, -,
+        pixels of the ROI)."""
+        n_both, _n_edge, _, size = (int(v) for v in counts)
+        ratio = area / size
+        if ratio < 0.01 or ratio > 0.8:
+            return 0.3
+        return float(min(0.5 + 0.5 * (n_both / area), 1.0))
 
     @staticmethod
     def _adaptive_confidence(roi: np.ndarray, local: np.ndarray, area: int) -> float:

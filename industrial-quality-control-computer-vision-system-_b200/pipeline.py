@@ -92,7 +92,7 @@ class BatchResult:
     seg_thr: Optional[np.ndarray] = None        # [K] Otsu threshold / Otsu bin (threshold method) / block size (adaptive)
     seg_ncomp: Optional[np.ndarray] = None      # [K]
     seg_method: Optional[np.ndarray] = None     # [K] ffi.QC_SEG_* the ROI went through
-    seg_sums: Optional[np.ndarray] = None       # [K,4] int64 confidence sums (threshold method rows)
+    seg_sums: Optional[np.ndarray] = None       # [K,4] int64 confidence integers (threshold: gray sums; adaptive: Canny overlap)
     seg_contours: Optional[np.ndarray] = None   # [K,4] int64 (n_axis, n_diag, n_contours, 0): perimeter = n_axis + sqrt(2) n_diag
     spc: Optional[np.ndarray] = None            # [9] float64
     seg: Optional[dict] = None                  # device tensors of K4 (mask/labels/stats) when requested
@@ -380,7 +380,7 @@ class InspectionPipeline:
             # gray is read as the reference does AFTER inference/detector.py:234 swapped the channels
             with self._timed(name):
                 seg = qc.segment(frames, regs, morph_iters=iters, swap_rb=swap_rb, want_mask=keep, want_labels=keep,
-                                 method=code, want_sums=(code == ffi.QC_SEG_REF_THRESHOLD),
+                                 method=code, want_sums=(code != ffi.QC_SEG_COMPOSITE),
                                  want_contours=(code != ffi.QC_SEG_COMPOSITE and self.seg_contours))
             groups.append(dict(name=name, idx=idx, code=code, iters=iters, seg=seg, cap=cap, regs=regs, swap_rb=swap_rb))
         return groups

@@ -152,7 +152,7 @@ def test_threshold_method_large_regions(qc):
 def _run_adaptive(qc, img, regs, classes, max_comp=None):
     rr = [dict(r, polarity=0 if c in R.DARK_CLASSES else 1, min_area=20) for r, c in zip(regs, classes)]
     res = qc.segment(torch.from_numpy(img[None]).cuda(), rr, morph_iters=1, method=ffi.QC_SEG_REF_ADAPTIVE,
-                     want_contours=True)
+                     want_contours=True, want_sums=True)
     torch.cuda.synchronize()
     return res
 
@@ -177,6 +177,12 @@ def _check_adaptive(res, i, img, reg, cls, budget=0):
         labf = np.where(keep[lab], lab, 0)
         assert np.array_equal(res["labels"][o:o + w * h].view(h, w).cpu().numpy(), labf)
         _check_contours(res, i, m)
+        # K9: cv2.Canny(roi, 50, 150) and its overlap with the mask, bit for bit; the confidence of :557-578
+        edges = cv2.Canny(np.ascontiguousarray(roi), 50, 150)
+        sm = [int(v) for v in res["sums"][i].cpu().numpy()]
+        assert sm == [int(((edges > 0) & (m > 0)).sum()), int((edges > 0).sum()), 0, roi.size], f"region {i}: Canny counts {sm}"
+        from qcgraft.detector import ImageSegmentator
+        assert abs(ImageSegmentator._adaptive_confidence_from_counts(sm, int((m > 0).sum())) - conf) <= 1e-12
     return bad
 
 

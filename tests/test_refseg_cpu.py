@@ -110,3 +110,46 @@ def test_oracle_reproduces_reference_segment_defects(restated):
             assert r["n_contours"] == g["n_contours"]
             n += 1
     assert n == GOLD["n_rois"] >= 20
+
+
+def test_contour_statistics_restated_equal_cv2():
+    """oracle/contours.py: perimeter / contour count / contourArea from 2x2 window moves of the hole-filled mask ==
+    cv2.findContours(RETR_EXTERNAL) + contourArea + arcLength (inference/segmentation.py:486-525)."""
+    from oracle import contours as C
+    rng = np.random.default_rng(3)
+    for t in range(160):
+        h, w = int(rng.integers(1, 70)), int(rng.integers(1, 70))
+        kind = t % 4
+        if kind == 0:
+            m = rng.random((h, w)) < rng.uniform(0.05, 0.9)
+        elif kind == 1:
+            m = np.zeros((h, w), bool)
+            for _ in range(8):
+                y, x = rng.integers(0, h), rng.integers(0, w)
+                m[y:y + rng.integers(1, 20), x:x + rng.integers(1, 20)] = True
+            for _ in range(4):
+                y, x = rng.integers(0, h), rng.integers(0, w)
+                m[y:y + rng.integers(1, 8), x:x + rng.integers(1, 8)] = False
+        elif kind == 2:
+            yy, xx = np.mgrid[0:h, 0:w]
+            m = (yy + xx) % int(rng.integers(2, 6)) == 0
+        else:
+            m = cv2.morphologyEx((rng.random((h, w)) < 0.5).astype(np.uint8), cv2.MORPH_OPEN, np.ones((3, 3), np.uint8)) > 0
+        a, b = C.contour_stats(m), C.contour_stats_restated(m)
+        assert a[1] == b[1] and a[2] == b[2], t
+        assert abs(a[0] - b[0]) <= 1e-6 * max(1.0, a[0]), t
+
+
+def test_canny_restated_equals_cv2():
+    """oracle/canny.py == cv2.Canny(roi, 50, 150) bit for bit, on strided ROI views like the reference passes."""
+    from oracle import canny as K
+    rng = np.random.default_rng(4)
+    for t in range(90):
+        g = _rand_roi(rng, t, 1, 150)
+        h, w = g.shape
+        big = rng.integers(0, 256, (h + 5, w + 6)).astype(np.uint8)
+        big[2:2 + h, 3:3 + w] = g
+        roi = big[2:2 + h, 3:3 + w]
+        assert np.array_equal(cv2.Canny(roi, 50, 150), K.canny_restated(np.ascontiguousarray(roi))), t
+        m, conf, _ = R.adaptive_segmentation(roi, "crack")
+        assert K.adaptive_confidence_restated(np.ascontiguousarray(roi), m) == conf
