@@ -556,6 +556,21 @@ def main():
     e2e_ms, e2e_wall_ms, _, last_e2e = timed(step_e2e, args.steps)
     clocks = sampler.stop() if rank == 0 else None
 
+    # ---- per-kernel durations of the same step, from CUDA events the library records around its own launches
+    # (qc_profile_enable); a separate short pass so that the event records stay out of the timed regions ---------
+    PROF_STEPS = 3
+    qc.profile(True)
+    for i in range(PROF_STEPS):
+        step_resident(i, last=(i == PROF_STEPS - 1))
+    torch.cuda.synchronize()
+    prof = qc.profile_collect()
+    qc.profile(False)
+    kernel_times = {}
+    for name, ms in prof:
+        k = kernel_times.setdefault(name, {"ms_per_step": 0.0, "launches_per_step": 0.0})
+        k["ms_per_step"] += ms / PROF_STEPS
+        k["launches_per_step"] += 1.0 / PROF_STEPS
+
     imgs_total = world * B * args.steps
     # events bracket every step on the launching stream; host-side gaps between steps are inside the
     # bracket of the next step only if the GPU is busy, so use the wall clock when it is larger
@@ -590,19 +605,55 @@ def main():
     for v in operators.values():
         v["share_of_own_kernel_time"] = v["ms_per_step"] / own_total if own_total else None
     dom = max(operators, key=lambda k: operators[k]["ms_per_step"]) if operators else None
+    # per-kernel table (live CUDA events inside the library): algorithmic bytes of the kernels that can lead it
+    thr_px, adp_px = int(roi_px[~adaptive].sum()), int(roi_px[adaptive].sum())
+    k3_kernels = [k for k in kernel_times if k.startswith("k3_roi")]
+    kern_bytes = {
+        "k1_pack_stream": op_bytes["k1_preprocess"], "k1_resize_tma": op_bytes["k1_preprocess"],
+        "k3b_resize": op_bytes["k3b_pil_resize"],
+        "k7_blur": thr_px * (1 + 8),                       # u8 gray in, f64 blurred out
+        "k7_hist": thr_px * 8, "k7_cmp": thr_px * 8 + thr_px // 8,
+        "k7_pack_gray": int(roi_px.sum()) * (3 + 1),       # RGB in, gray out
+        "k7_adaptive_small": adp_px + adp_px // 8, "k9_canny_nms": adp_px + adp_px // 4,
+        "k7_fill": (2 * thr_px + adp_px) // 4,             # bit masks in and out, all calls of the step
+        "k4_ccl_local": (2 * thr_px + 3 * adp_px) // 8 + (2 * thr_px + 3 * adp_px),   # bits in, one int32 per 2x2 block out
+    }
+    if len(k3_kernels) == 1:
+        kern_bytes[k3_kernels[0]] = op_bytes["k3_roi_align"]
+    k_total = sum(v["ms_per_step"] for v in kernel_times.values())
+    for name, v in kernel_times.items():
+        v["share_of_own_kernel_time"] = v["ms_per_step"] / k_total if k_total else None
+        by = kern_bytes.get(name)
+        if by and v["ms_per_step"] > 0:
+            v["algorithmic_bytes_per_step"] = by
+            v["gbs"] = by / v["ms_per_step"] / 1e6
+            v["frac"] = v["gbs"] / peak
+    kernel_times = dict(sorted(kernel_times.items(), key=lambda kv: -kv[1]["ms_per_step"]))
+    kdom = next(iter(kernel_times), None)
     roofline = None
+    if kdom and "gbs" in kernel_times[kdom]:
+        kv = kernel_times[kdom]
+        roofline = {"bound": "hbm", "kernel": f"{kdom} (largest single kernel of the step: "
+                    f"{100 * kv['share_of_own_kernel_time']:.0f} % of own-kernel time, CUDA events around every launch "
+                    "inside the library)",
+                    "achieved": kv["gbs"], "peak": peak, "unit": "GB/s", "frac": kv["frac"], "traffic": None,
+                    "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": kv["algorithmic_bytes_per_step"] / kv["launches_per_step"],
+                    "ms_per_launch": kv["ms_per_step"] / kv["launches_per_step"]}
     if dom:
         o = operators[dom]
-        roofline = {"bound": "hbm", "kernel": f"{dom} (dominant own operator: {100 * o['share_of_own_kernel_time']:.0f} % of "
-                    "own-kernel time in the step; one C-ABI call = one launch sequence)",
-                    "achieved": o["gbs"], "peak": peak, "unit": "GB/s", "frac": o["frac"], "traffic": None,
-                    "peak_source": peak_src, "algorithmic_bytes_per_launch": o["algorithmic_bytes_per_step"] / o["calls_per_step"],
-                    "ms_per_launch": o["ms_per_step"] / o["calls_per_step"],
+        roofline = roofline or {"bound": "hbm", "peak": peak, "unit": "GB/s", "traffic": None, "peak_source": peak_src,
+                                "kernel": dom, "achieved": o["gbs"], "frac": o["frac"]}
+        roofline.update({
+                    "dominant_operator": {"operator": f"{dom} (one C-ABI call = one launch sequence; "
+                                          f"{100 * o['share_of_own_kernel_time']:.0f} % of own-operator time)",
+                                          "gbs": o["gbs"], "frac": o["frac"], "ms_per_call": o["ms_per_step"] / o["calls_per_step"],
+                                          "algorithmic_bytes_per_call": o["algorithmic_bytes_per_step"] / o["calls_per_step"]},
                     "second": {"kernel": "k1_pack_stream (K1 preprocess, the step's pure streaming kernel)",
                                **{kk: operators["k1_preprocess"][kk] for kk in ("gbs", "frac", "ms_per_step")},
                                # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full
                                # (profiles/r01_f_ncu_full_summary.md)
-                               "traffic": 180780032} if "k1_preprocess" in operators else None}
+                               "traffic": 180780032} if "k1_preprocess" in operators else None})
     gpu_stage = {"pre": stage_ms.get("k1_preprocess", 0) + stage_ms.get("k3b_pil_resize", 0),
                  "nets": stage_ms.get("yolo_net", 0) + stage_ms.get("resnet_net", 0),
                  "decode_nms": stage_ms.get("k2_decode_nms", 0), "roi": stage_ms.get("k3_roi_align", 0),
@@ -626,6 +677,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * IMGSZ * IMGSZ * 3,
                     "d2h_bytes_per_step": d2h, "ms_per_step": max(e2e_ms, e2e_wall_ms) / args.steps},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "operators": operators,
+            "kernel_times": kernel_times,
             "stage_ms": stage_ms, "stage_split": stage_split, "device_ms_per_step": tot_ms / args.steps,
             "spc": {k: float(v) for k, v in zip(qdist.SPC_FIELDS, spc_total.cpu().numpy())}}
     if not args.no_kernels and world == 1:

@@ -14,8 +14,9 @@
  *     reference's {"error": str} convention, inference/detector.py:124-126).
  *   - all data pointers are DEVICE pointers owned by the caller; the library
  *     allocates nothing on the data path, never synchronises the stream and
- *     never touches host memory.  Scratch space comes from the caller via the
- *     *_workspace_bytes() queries.
+ *     never touches host memory (one documented exception: qc_jpeg_decode reads the
+ *     compressed byte streams where they are, on the host).  Scratch space comes from
+ *     the caller via the *_workspace_bytes() queries.
  *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).
  *   - no CPU fallback exists: every entry point launches sm_100a kernels.
  */
@@ -47,8 +48,17 @@ const char* qc_version(void);
 int qc_sm_count(const qc_ctx* ctx);
 /* number of kernels this ctx has launched since creation (bench.py "gpu_launches") */
 int64_t qc_launch_count(const qc_ctx* ctx);
+
+/* Optional per-kernel timing (measurement only; off by default).  While enabled every entry point records one CUDA
+ * event on the caller's stream at entry and one after each kernel it launches (up to 4096 per collection; stream
+ * capture must not be active).  qc_profile_collect() waits for the recorded events, writes the kernels' names (static
+ * strings) and durations in launch order into names[0..cap) / ms[0..cap), clears the list and returns the number of
+ * kernels recorded.  A kernel's duration runs from the previous event on its stream to its own, so it includes the
+ * launch gap in front of it -- microseconds for back-to-back launches. */
+int qc_profile_enable(qc_ctx* ctx, int on);
+int qc_profile_collect(qc_ctx* ctx, const char** names, float* ms, int cap);
 /* sizeof() of the ABI structs, for bindings to self-check their layout:
- * 0 qc_pre_plan, 1 qc_yolo_params, 2 qc_seg_region, 3 qc_seg_params */
+ * 0 qc_pre_plan, 1 qc_yolo_params, 2 qc_seg_region, 3 qc_seg_params, 4 qc_jpeg_info */
 size_t qc_sizeof(int which);
 
 /* ---- K1: letterbox / stretch resize + normalise + NCHW pack -------------
@@ -293,6 +303,44 @@ int qc_spc_stats(qc_ctx* ctx, const float* det, const int32_t* count, int n, int
 int qc_rules_cluster(qc_ctx* ctx, const int32_t* box, const int32_t* cls, const uint8_t* keep,
                      const int32_t* count, int n, int cap, double overlap_threshold, int32_t* out_label,
                      void* stream);
+
+/* ---- K10: batched baseline-JPEG decode (row f4, input side) ---------------------------------
+ * Replaces: cv2.imdecode(buf, cv2.IMREAD_COLOR) at inference/detector.py:214,229 and
+ * models/yolo_model.py:74-76 (the 1-D uint8 upload buffer of app.py:190-194), plus -- with rgb=1 --
+ * the cv2.cvtColor(BGR2RGB) that follows it (inference/detector.py:233-234).  Output bytes are
+ * identical to cv2's (libjpeg-turbo 3.x defaults: islow IDCT, fancy upsampling, integer colour
+ * tables).  THE ONE EXCEPTION to the "device pointers only" convention: the JPEG byte streams,
+ * `infos`, `dst_offsets`, `dst_row_strides` and `host_staging` are HOST memory; the Huffman stage
+ * runs on `host_threads` host threads inside the call (it is serial per restart interval), then one
+ * cudaMemcpyAsync moves the coefficient blocks and two kernels rebuild the pixels.  `host_staging`
+ * (pinned for an asynchronous copy) must stay untouched until the stream has passed the copy.
+ * Supported: 8-bit sequential Huffman (SOF0/SOF1), grayscale or YCbCr 4:4:4 / 4:2:2 / 4:2:0, one
+ * interleaved scan, restart intervals.  Anything else (progressive, arithmetic, CMYK / RGB-coded,
+ * other samplings, EXIF orientation != 1) -> QC_ERR_UNSUPPORTED; the library has no other decoder.
+ */
+typedef enum { QC_JPEG_GRAY = 0, QC_JPEG_444 = 1, QC_JPEG_422 = 2, QC_JPEG_420 = 3 } qc_jpeg_subsampling;
+typedef struct {
+    int32_t width, height;
+    int32_t components;        /* 1 or 3 (the decoded frame always has 3 channels, like IMREAD_COLOR) */
+    int32_t subsampling;       /* qc_jpeg_subsampling */
+    int32_t restart_interval;  /* MCUs between RSTn markers, 0 = none */
+    int32_t reserved;
+    int64_t blocks;            /* 8x8 coefficient blocks incl. MCU padding (sizes staging / workspace) */
+} qc_jpeg_info;
+/* host only; ctx may be NULL (then no message is kept) */
+int qc_jpeg_info_host(qc_ctx* ctx, const uint8_t* data, size_t len, qc_jpeg_info* info);
+/* host only: the entropy stage of ONE image on its own -- coefs[blocks*64] int16 in natural (row-major) order, not
+ * dequantised, laid out [component][block row][block column][64] over the MCU-padded planes (Y has
+ * mcus_x*h_samp x mcus_y*v_samp blocks); quant[components*64] in natural order.  What qc_jpeg_decode stages. */
+int qc_jpeg_entropy_host(qc_ctx* ctx, const uint8_t* data, size_t len, int16_t* coefs, uint16_t* quant);
+size_t qc_jpeg_staging_bytes(const qc_jpeg_info* infos, int n);     /* host staging buffer            */
+size_t qc_jpeg_workspace_bytes(const qc_jpeg_info* infos, int n);   /* device workspace               */
+/* image i is written as packed 3-byte pixels at dst + dst_offsets[i] with dst_row_strides[i] bytes per
+ * row (>= 3*width): BGR like cv2.imdecode, or RGB when rgb != 0 */
+int qc_jpeg_decode(qc_ctx* ctx, const uint8_t* const* jpegs, const size_t* lens, int n,
+                   const qc_jpeg_info* infos, int host_threads, void* host_staging, size_t staging_bytes,
+                   void* workspace, size_t workspace_bytes, uint8_t* dst, const int64_t* dst_offsets,
+                   const int32_t* dst_row_strides, int rgb, void* stream);
 
 #ifdef __cplusplus
 }

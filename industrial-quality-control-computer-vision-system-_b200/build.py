@@ -10,7 +10,7 @@ CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_DIR = os.path.join(PKG_DIR, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libqcgraft.so")
 
-SOURCES = ["api.cu", "k1_preprocess.cu", "k2_yolo.cu", "k3_roi.cu", "k3b_resize.cu", "k4_segment.cu", "k5_spc.cu", "k6_rules.cu"]
+SOURCES = ["api.cu", "k1_preprocess.cu", "k2_yolo.cu", "k3_roi.cu", "k3b_resize.cu", "k4_segment.cu", "k5_spc.cu", "k6_rules.cu", "k10_jpeg.cu"]
 # -fmad=false: the parity-critical float paths must not be contracted into FMAs (the reference's
 # CPU libraries are not); these kernels are memory-bound so nothing is lost.
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

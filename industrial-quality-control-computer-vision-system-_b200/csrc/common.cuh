@@ -9,13 +9,30 @@
 #include "../../include/qcgraft.h"
 
 struct qc_attr_entry { const void* func; int smem; int occ; int threads; int device; };
+// optional per-kernel timing (qc_profile_enable): one event after every launch and one at every API entry, all on the
+// caller's stream; qc_profile_collect() turns consecutive events into per-kernel durations
+struct qc_prof_rec { const char* name; cudaEvent_t ev; };
+constexpr int QC_PROF_MAX = 4096;
 struct qc_ctx {
     int device;
     int sm_count;
     int max_smem_optin;
     std::atomic<long long> launches;
     char err[512];
+    bool prof = false;
+    int prof_n = 0;
+    qc_prof_rec* prof_recs = nullptr;
 };
+static inline void qc_prof_mark(qc_ctx* ctx, const char* name, cudaStream_t st) {
+    if (!ctx || !ctx->prof || !ctx->prof_recs || ctx->prof_n >= QC_PROF_MAX) return;
+    qc_prof_rec& r = ctx->prof_recs[ctx->prof_n];
+    if (!r.ev && cudaEventCreate(&r.ev) != cudaSuccess) return;
+    r.name = name;
+    cudaEventRecord(r.ev, st);
+    ctx->prof_n += 1;
+}
+// at the top of every kernel-launching entry point (name == nullptr marks a boundary, not a kernel)
+#define QC_ENTER(ctx, stream) qc_prof_mark((ctx), nullptr, (cudaStream_t)(stream))
 
 #define QC_FAIL(ctx, code, ...)                                   \
     do {                                                          \
@@ -32,10 +49,11 @@ struct qc_ctx {
     } while (0)
 
 // every kernel launch goes through this so qc_launch_count() is honest
-#define QC_LAUNCHED(ctx)                                                                \
+#define QC_LAUNCHED_AS(ctx, name, st)                                                   \
     do {                                                                                \
         (ctx)->launches.fetch_add(1, std::memory_order_relaxed);                        \
         QC_CUDA(ctx, cudaGetLastError());                                               \
+        if ((ctx)->prof) qc_prof_mark((ctx), (name), (cudaStream_t)(st));               \
     } while (0)
 
 // Every entry point that launches kernels runs under this guard: the kernels, the stream and the pointers belong to

@@ -417,7 +417,7 @@ static int launch_k1(qc_ctx* ctx, const uint8_t* src, int n, int64_t src_img_str
         long long grid = (long long)ctx->sm_count * occ;
         if (grid > total) grid = total;
         kern<<<(unsigned)grid, K1_THREADS, smem, st>>>(src, dst, lut, P, src_img_stride, chunks, total);
-        QC_LAUNCHED(ctx);
+        QC_LAUNCHED_AS(ctx, "k1_pack_stream", st);
         return QC_OK;
     }
     if (identity && packed) {   // per-channel LUT (mean/std normalisation): three lane-private tables
@@ -429,7 +429,7 @@ static int launch_k1(qc_ctx* ctx, const uint8_t* src, int n, int64_t src_img_str
         long long grid = ctx->sm_count;
         if (grid > total) grid = total;
         kern<<<(unsigned)grid, K1_THREADS, smem, st>>>(src, dst, lut, P, src_img_stride, chunks, total);
-        QC_LAUNCHED(ctx);
+        QC_LAUNCHED_AS(ctx, "k1_pack_stream", st);
         return QC_OK;
     }
     {
@@ -452,7 +452,7 @@ static int launch_k1(qc_ctx* ctx, const uint8_t* src, int n, int64_t src_img_str
             if (g > total) g = total;
             k1_resize_tma<OutT><<<(unsigned)g, threads, smem, st>>>(src, dst, lut, n, src_img_stride, src_row_stride, *pl,
                                                                    pad_value, swap_rb, row_bytes, tma_ok ? 1 : 0, bands);
-            QC_LAUNCHED(ctx);
+            QC_LAUNCHED_AS(ctx, "k1_resize_tma", st);
             return QC_OK;
         }
     }
@@ -463,7 +463,7 @@ static int launch_k1(qc_ctx* ctx, const uint8_t* src, int n, int64_t src_img_str
     if (grid < 1) grid = 1;
     k1_generic<OutT><<<(unsigned)grid, 256, 0, st>>>(src, dst, lut, n, src_img_stride, src_row_stride, *pl,
                                                      pad_value, swap_rb);
-    QC_LAUNCHED(ctx);
+    QC_LAUNCHED_AS(ctx, "k1_generic", st);
     return QC_OK;
 }
 
@@ -472,6 +472,7 @@ extern "C" int qc_preprocess(qc_ctx* ctx, const uint8_t* src, int n, int64_t src
                              int flags, int out_dtype, void* dst, void* stream) {
     qc_device_guard dev_guard(ctx);
     if (!ctx) return QC_ERR_INVALID;
+    QC_ENTER(ctx, stream);
     if (!src || !plan || !lut || !dst || n < 0) QC_FAIL(ctx, QC_ERR_INVALID, "qc_preprocess: null/invalid argument");
     if (n == 0) return QC_OK;
     if (plan->src_h <= 0 || plan->src_w <= 0 || plan->dst_h <= 0 || plan->dst_w <= 0 || plan->new_h <= 0 ||

@@ -841,7 +841,7 @@ int launch_nms(qc_ctx* ctx, const NmsArgs& a, int n, const Ws& w, float* out_det
     if (int rc = qc_prepare(ctx, k2_nms, (int)smem, K2_NMS_THREADS, nullptr)) return rc;
     k2_nms<<<n, K2_NMS_THREADS, smem, st>>>(a, w.key, w.box, w.count, w.gkeys, w.gvals, w.gsorted, out_det, out_idx,
                                             out_count, out_ncand);
-    QC_LAUNCHED(ctx);
+    QC_LAUNCHED_AS(ctx, "k2_nms", st);
     return QC_OK;
 }
 
@@ -862,6 +862,7 @@ extern "C" int qc_yolo_decode_nms(qc_ctx* ctx, const void* const* levels, const 
                                   int32_t* out_ncand, void* stream) {
     qc_device_guard dev_guard(ctx);
     if (!ctx) return QC_ERR_INVALID;
+    QC_ENTER(ctx, stream);
     if (!levels || !p || !out_det || !out_anchor || !out_count)
         QC_FAIL(ctx, QC_ERR_INVALID, "qc_yolo_decode_nms: null argument");
     if (p->n == 0) return QC_OK;
@@ -920,7 +921,7 @@ extern "C" int qc_yolo_decode_nms(qc_ctx* ctx, const void* const* levels, const 
         if (bf) k2_filter<true, K2_NC_MAX><<<gf, 256, 0, st>>>(lt, p->nc, p->reg_max, conf, logit_lo, cap, vec_ok, w.key, w.count);
         else k2_filter<false, K2_NC_MAX><<<gf, 256, 0, st>>>(lt, p->nc, p->reg_max, conf, logit_lo, cap, vec_ok, w.key, w.count);
     }
-    QC_LAUNCHED(ctx);
+    QC_LAUNCHED_AS(ctx, "k2_filter", st);
 
     dim3 gd(32, (unsigned)p->n);
     if (p->reg_max == 16) {
@@ -930,7 +931,7 @@ extern "C" int qc_yolo_decode_nms(qc_ctx* ctx, const void* const* levels, const 
         if (bf) k2_decode<true, 0><<<gd, 256, 0, st>>>(lt, p->reg_max, cap, w.key, w.count, w.box);
         else k2_decode<false, 0><<<gd, 256, 0, st>>>(lt, p->reg_max, cap, w.key, w.count, w.box);
     }
-    QC_LAUNCHED(ctx);
+    QC_LAUNCHED_AS(ctx, "k2_decode", st);
 
     NmsArgs a;
     a.cap = cap; a.max_det = p->max_det; a.max_nms = p->max_nms; a.max_wh = p->max_wh; a.iou_thres = p->iou_thres;
@@ -952,7 +953,7 @@ extern "C" int qc_yolo_decode_nms(qc_ctx* ctx, const void* const* levels, const 
             k2_nms_class<<<dim3((unsigned)p->nc, (unsigned)p->n), K2C_THREADS, smem, st>>>(
                 a, p->nc, w.key, w.box, w.count, w.gkeys, w.gvals, w.gsorted, w.gmall, w.kept_key, w.kept_box,
                 w.kept_count, w.ticket, out_det, out_anchor, out_count, out_ncand);
-            QC_LAUNCHED(ctx);
+            QC_LAUNCHED_AS(ctx, "k2_nms_class", st);
             return QC_OK;
         }
     }
@@ -964,6 +965,7 @@ extern "C" int qc_nms(qc_ctx* ctx, const float* boxes, const float* scores, cons
                       size_t workspace_bytes, int32_t* out_keep, int32_t* out_count, void* stream) {
     qc_device_guard dev_guard(ctx);
     if (!ctx) return QC_ERR_INVALID;
+    QC_ENTER(ctx, stream);
     if (!boxes || !scores || !cls || !counts || !out_keep || !out_count || cap <= 0 || max_det <= 0 || n < 0)
         QC_FAIL(ctx, QC_ERR_INVALID, "qc_nms: bad argument");
     if (n == 0) return QC_OK;
@@ -974,7 +976,7 @@ extern "C" int qc_nms(qc_ctx* ctx, const float* boxes, const float* scores, cons
     cudaStream_t st = (cudaStream_t)stream;
     dim3 g((unsigned)std::min((cap + 255) / 256, 32), (unsigned)n);
     k2_make_keys<<<g, 256, 0, st>>>(scores, cls, counts, cap, w.key, w.count);
-    QC_LAUNCHED(ctx);
+    QC_LAUNCHED_AS(ctx, "k2_make_keys", st);
     w.box = const_cast<float4*>(reinterpret_cast<const float4*>(boxes));
     NmsArgs a;
     a.cap = cap; a.max_det = max_det; a.max_nms = cap; a.max_wh = max_wh; a.iou_thres = iou_thres;

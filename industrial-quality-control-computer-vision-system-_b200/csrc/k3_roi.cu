@@ -694,6 +694,7 @@ extern "C" int qc_roi_align_rows(qc_ctx* ctx, const uint8_t* imgs, int n, int h,
                                  int out_dtype, void* dst, void* stream) {
     qc_device_guard dev_guard(ctx);
     if (!ctx) return QC_ERR_INVALID;
+    QC_ENTER(ctx, stream);
     if (K == 0) return QC_OK;
     if (!imgs || !rois || !norm || !dst || n <= 0 || h <= 0 || w <= 0 || K < 0 || out_h <= 0 || out_w <= 0 ||
         row_stride < w * 3)
@@ -723,7 +724,7 @@ extern "C" int qc_roi_align_rows(qc_ctx* ctx, const uint8_t* imgs, int n, int h,
             QC_FAIL(ctx, QC_ERR_INVALID, "qc_roi_align: bad out_dtype");
         }
         (void)grid;
-        QC_LAUNCHED(ctx);
+        QC_LAUNCHED_AS(ctx, "k3_roi_tma", st);
         return QC_OK;
     }
     if (sampling_ratio >= 1 && sampling_ratio <= K3_SR_MAX) {
@@ -754,7 +755,7 @@ extern "C" int qc_roi_align_rows(qc_ctx* ctx, const uint8_t* imgs, int n, int h,
             if (out_dtype == QC_DT_BF16) K3_LAUNCH_SR(__nv_bfloat16);
             else if (out_dtype == QC_DT_F32) K3_LAUNCH_SR(float);
             else QC_FAIL(ctx, QC_ERR_INVALID, "qc_roi_align: bad out_dtype");
-            QC_LAUNCHED(ctx);
+            QC_LAUNCHED_AS(ctx, "k3_roi_sep", st);
             return QC_OK;
         }
     }
@@ -767,7 +768,7 @@ extern "C" int qc_roi_align_rows(qc_ctx* ctx, const uint8_t* imgs, int n, int h,
                                                   sampling_ratio, aligned, swap_rb, norm, (float*)dst, dst_rows);
     else
         QC_FAIL(ctx, QC_ERR_INVALID, "qc_roi_align: bad out_dtype");
-    QC_LAUNCHED(ctx);
+    QC_LAUNCHED_AS(ctx, "k3_roi_align", st);
     return QC_OK;
 }
 

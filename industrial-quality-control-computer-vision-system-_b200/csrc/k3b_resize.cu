@@ -285,6 +285,7 @@ extern "C" int qc_pil_resize(qc_ctx* ctx, const uint8_t* imgs, int n, int h, int
                              const float* norm, int out_dtype, void* dst, void* stream) {
     qc_device_guard dev_guard(ctx);
     if (!ctx) return QC_ERR_INVALID;
+    QC_ENTER(ctx, stream);
     if (n == 0) return QC_OK;
     if (!imgs || !dev_tables || !host_tables || !norm || !dst || n < 0 || h <= 0 || w <= 0 || row_stride < w * 3)
         QC_FAIL(ctx, QC_ERR_INVALID, "qc_pil_resize: bad argument");
@@ -321,6 +322,6 @@ extern "C" int qc_pil_resize(qc_ctx* ctx, const uint8_t* imgs, int n, int h, int
     if (out_dtype == QC_DT_BF16) K3B_LAUNCH_NG(__nv_bfloat16);
     else if (out_dtype == QC_DT_F32) K3B_LAUNCH_NG(float);
     else QC_FAIL(ctx, QC_ERR_INVALID, "qc_pil_resize: bad out_dtype");
-    QC_LAUNCHED(ctx);
+    QC_LAUNCHED_AS(ctx, "k3b_resize", st);
     return QC_OK;
 }

@@ -1287,6 +1287,7 @@ int seg_run(qc_ctx* ctx, int method, const uint8_t* imgs, const qc_seg_params* p
     const char* fn = method == QC_SEG_COMPOSITE ? "qc_segment" : "qc_segment_ref";
     if (!ctx) return QC_ERR_INVALID;
     qc_device_guard dev_guard(ctx);
+    QC_ENTER(ctx, stream);
     if (!p) QC_FAIL(ctx, QC_ERR_INVALID, "%s: null params", fn);
     if (method < QC_SEG_COMPOSITE || method > QC_SEG_REF_ADAPTIVE) QC_FAIL(ctx, QC_ERR_INVALID, "%s: bad method %d", fn, method);
     if (p->num_regions == 0) return QC_OK;
@@ -1326,26 +1327,26 @@ int seg_run(qc_ctx* ctx, int method, const uint8_t* imgs, const qc_seg_params* p
         if (int rc = qc_prepare(ctx, k4_mask, (int)smem_mask, K4_THREADS, &occ)) return rc;
         k4_mask<<<std::min(p->total_bands, sms * std::max(occ, 1)), K4_THREADS, smem_mask, st>>>(
             im, regions, R, p->total_bands, w.band_off, p->morph_iters, w.cmp, w.gray, bits_out, buf_words, bits_in);
-        QC_LAUNCHED(ctx);
+        QC_LAUNCHED_AS(ctx, "k4_mask", st);
         return QC_OK;
     };
     auto unionfind = [&](const unsigned* bits, int* zero_area, bool zero_k8 = false) -> int {   // parent[g] = root afterwards
         if (int rc = qc_prepare(ctx, k4_ccl_local, (int)smem_ccl, K4_THREADS, &occ)) return rc;
         k4_ccl_local<<<std::min(p->total_bands, sms * std::max(occ, 1)), K4_THREADS, smem_ccl, st>>>(
             regions, R, p->total_bands, w.band_off, bits, w.parent, band_words, lab_words);
-        QC_LAUNCHED(ctx);
+        QC_LAUNCHED_AS(ctx, "k4_ccl_local", st);
         k4_border<<<band_grid, K4_THREADS, 0, st>>>(regions, R, p->total_bands, w.band_off, bits, w.parent);
-        QC_LAUNCHED(ctx);
+        QC_LAUNCHED_AS(ctx, "k4_border", st);
         k4_compress<<<chunk_grid, K4_CHUNK, 0, st>>>(regions, R, p->total_chunks, w.chunk_off, bits, w.parent,
                                                      w.chunk_count, zero_area, zero_k8 ? w.acc_n : nullptr,
                                                      zero_k8 ? w.acc_x : nullptr);
-        QC_LAUNCHED(ctx);
+        QC_LAUNCHED_AS(ctx, "k4_compress", st);
         return QC_OK;
     };
     auto fill_holes = [&](const unsigned* bits_in, unsigned* bits_out, unsigned* free_ws) -> int {
         if (int rc = qc_prepare(ctx, k7_fill, K7_FILL_SMEM_WORDS * 4, K7_FILL_THREADS, &occ)) return rc;
         k7_fill<<<std::min(R, sms * std::max(occ, 1)), K7_FILL_THREADS, K7_FILL_SMEM_WORDS * 4, st>>>(regions, R, bits_in, bits_out, free_ws);
-        QC_LAUNCHED(ctx);
+        QC_LAUNCHED_AS(ctx, "k7_fill", st);
         return QC_OK;
     };
     // K8: contour statistics of the final mask `fbits` (bit rows); scratch: two bit buffers, the union-find arrays
@@ -1354,37 +1355,37 @@ int seg_run(qc_ctx* ctx, int method, const uint8_t* imgs, const qc_seg_params* p
         if (int rc = fill_holes(fbits, filled, free_ws)) return rc;
         if (int rc = unionfind(filled, nullptr, true)) return rc;
         k8_moves<<<band_grid, K4_THREADS, 0, st>>>(regions, R, p->total_bands, w.band_off, filled, w.parent, w.acc_n, w.acc_x);
-        QC_LAUNCHED(ctx);
+        QC_LAUNCHED_AS(ctx, "k8_moves", st);
         k8_reduce<<<band_grid, K4_THREADS, 0, st>>>(regions, R, p->total_bands, w.band_off, filled, w.parent, w.acc_n, w.acc_x,
                                                     (long long*)o.contours);
-        QC_LAUNCHED(ctx);
+        QC_LAUNCHED_AS(ctx, "k8_reduce", st);
         return QC_OK;
     };
     auto label_tail = [&](const unsigned* bits) -> int {                            // cv2 numbering, stats, outputs
         k4_scan<<<std::min(R, sms * 2), 1024, 0, st>>>(regions, R, w.chunk_count, w.chunk_base, o.ncomp);
-        QC_LAUNCHED(ctx);
+        QC_LAUNCHED_AS(ctx, "k4_scan", st);
         k4_rank<<<chunk_grid, K4_CHUNK, 0, st>>>(regions, R, p->total_chunks, w.chunk_off, bits, w.parent, w.chunk_base,
                                                  w.rank);
-        QC_LAUNCHED(ctx);
+        QC_LAUNCHED_AS(ctx, "k4_rank", st);
         k4_stats<<<band_grid, K4_THREADS, 0, st>>>(regions, R, p->total_bands, w.band_off, bits, w.parent, w.rank,
                                                    o.stats);
-        QC_LAUNCHED(ctx);
+        QC_LAUNCHED_AS(ctx, "k4_stats", st);
         k4_final<<<band_grid, K4_THREADS, 0, st>>>(regions, R, p->total_bands, w.band_off, bits, w.parent, o.stats,
                                                    o.ncomp, o.mask, o.labels, (long long*)o.area);
-        QC_LAUNCHED(ctx);
+        QC_LAUNCHED_AS(ctx, "k4_final", st);
         return QC_OK;
     };
 
     k4_init<<<std::min(sms * 4, std::max(1, (p->total_stats_rows + 255) / 256)), 256, 0, st>>>(
         regions, R, w.hist, o.stats, (long long*)o.area, p->total_stats_rows, w.band_off, w.chunk_off,
         p->total_bands, p->total_chunks);
-    QC_LAUNCHED(ctx);
+    QC_LAUNCHED_AS(ctx, "k4_init", st);
     if (p->channels == 3) {
         k4_gray<<<std::min(p->total_bands, sms * 8), K4_THREADS, 0, st>>>(im, regions, R, p->total_bands, w.band_off, w.gray);
-        QC_LAUNCHED(ctx);
+        QC_LAUNCHED_AS(ctx, "k4_gray", st);
     } else if (method != QC_SEG_COMPOSITE) {
         k7_pack_gray<<<std::min(p->total_bands, sms * 8), K4_THREADS, 0, st>>>(im, regions, R, p->total_bands, w.band_off, w.gray);
-        QC_LAUNCHED(ctx);
+        QC_LAUNCHED_AS(ctx, "k7_pack_gray", st);
     }
     const uint8_t* gray7 = w.gray;          // K7 reads the region-packed gray copy whatever the input layout
 
@@ -1394,10 +1395,10 @@ int seg_run(qc_ctx* ctx, int method, const uint8_t* imgs, const qc_seg_params* p
         const int items = p->total_bands * K4_HIST_SPLIT;
         k4_hist<<<std::min((items + nw - 1) / nw, sms), K4_HIST_THREADS, K4_HIST_SMEM, st>>>(
             im, regions, R, p->total_bands, w.band_off, w.hist, w.gray);
-        QC_LAUNCHED(ctx);
+        QC_LAUNCHED_AS(ctx, "k4_hist", st);
         k4_otsu<<<std::min((R + K4_OTSU_WARPS - 1) / K4_OTSU_WARPS, sms * 8), K4_OTSU_WARPS * 32, 0, st>>>(
             regions, R, w.hist, w.cmp, o.thr);
-        QC_LAUNCHED(ctx);
+        QC_LAUNCHED_AS(ctx, "k4_otsu", st);
         if (int rc = morph(nullptr, w.bits)) return rc;
         if (int rc = unionfind(w.bits, nullptr)) return rc;
         return label_tail(w.bits);
@@ -1413,7 +1414,7 @@ int seg_run(qc_ctx* ctx, int method, const uint8_t* imgs, const qc_seg_params* p
         // generic tile kernel, launched only when the region table can hold such a region
         k7_adaptive_small<<<band_grid, K4_THREADS, 0, st>>>(im, regions, R, p->total_bands, w.band_off, gray7, ad.akern,
                                                             ad.pitch, ad.c, w.bits2);
-        QC_LAUNCHED(ctx);
+        QC_LAUNCHED_AS(ctx, "k7_adaptive_small", st);
         if (pmax > K7A_P) {
             const size_t smem_ad = (size_t)((2 * pmax + 1 + 3) & ~3) * 4 + (size_t)(32 + 2 * pmax) * 33 * 4 +
                                    (size_t)(32 + 2 * pmax) * (32 + 2 * pmax);
@@ -1422,60 +1423,60 @@ int seg_run(qc_ctx* ctx, int method, const uint8_t* imgs, const qc_seg_params* p
             if (int rc = qc_prepare(ctx, k7_adaptive, (int)smem_ad, K4_THREADS, &occ)) return rc;
             k7_adaptive<<<std::min(p->total_bands, sms * std::max(occ, 1)), K4_THREADS, smem_ad, st>>>(
                 im, regions, R, p->total_bands, w.band_off, gray7, ad.akern, ad.pitch, ad.c, w.bits2, pmax, K7A_P);
-            QC_LAUNCHED(ctx);
+            QC_LAUNCHED_AS(ctx, "k7_adaptive", st);
         }
         k7_block_out<<<(R + 255) / 256, 256, 0, st>>>(regions, R, o.thr, (long long*)o.sums);
-        QC_LAUNCHED(ctx);
+        QC_LAUNCHED_AS(ctx, "k7_block_out", st);
         if (int rc = morph(w.bits2, w.bits)) return rc;
         if (int rc = unionfind(w.bits, nullptr)) return rc;
         if (int rc = label_tail(w.bits)) return rc;
         if (o.contours || o.sums) {
             // kept mask (labels + areas are final) -> bits2
             k8_kept_bits<<<band_grid, K4_THREADS, 0, st>>>(regions, R, p->total_bands, w.band_off, w.bits, w.parent, o.stats, w.bits2);
-            QC_LAUNCHED(ctx);
+            QC_LAUNCHED_AS(ctx, "k8_kept_bits", st);
         }
         if (o.contours)        // filled -> bits3; free rows of oversized regions -> bits
             if (int rc = contour_stats(w.bits2, w.bits3, w.bits)) return rc;
         if (o.sums) {
             // K9: Canny(50, 150) edges and their overlap with the kept mask (:557-578); candidates -> bits, strong -> bits3
             k9_canny_nms<<<band_grid, K4_THREADS, 0, st>>>(regions, R, p->total_bands, w.band_off, gray7, 50, 150, w.bits, w.bits3);
-            QC_LAUNCHED(ctx);
+            QC_LAUNCHED_AS(ctx, "k9_canny_nms", st);
             if (int rc = unionfind(w.bits, w.rank)) return rc;                 // w.rank = "component holds a strong pixel"
             k9_mark<<<band_grid, K4_THREADS, 0, st>>>(regions, R, p->total_bands, w.band_off, w.bits3, w.parent, w.rank);
-            QC_LAUNCHED(ctx);
+            QC_LAUNCHED_AS(ctx, "k9_mark", st);
             k9_overlap<<<band_grid, K4_THREADS, 0, st>>>(regions, R, p->total_bands, w.band_off, w.bits, w.bits2, w.parent, w.rank,
                                                          (long long*)o.sums);
-            QC_LAUNCHED(ctx);
+            QC_LAUNCHED_AS(ctx, "k9_overlap", st);
         }
         return QC_OK;
     }
 
     // QC_SEG_REF_THRESHOLD
     k7_init<<<std::max(1, std::min(sms, (R * 4 + 255) / 256)), 256, 0, st>>>(R, w.minmax, (long long*)o.sums);
-    QC_LAUNCHED(ctx);
+    QC_LAUNCHED_AS(ctx, "k7_init", st);
     k7_blur<<<band_grid, K4_THREADS, 0, st>>>(im, regions, R, p->total_bands, w.band_off, gray7, w.blurred, w.minmax);
-    QC_LAUNCHED(ctx);
+    QC_LAUNCHED_AS(ctx, "k7_blur", st);
     k7_hist<<<band_grid, K4_THREADS, 0, st>>>(regions, R, p->total_bands, w.band_off, w.blurred, w.minmax, w.hist);
-    QC_LAUNCHED(ctx);
+    QC_LAUNCHED_AS(ctx, "k7_hist", st);
     k7_otsu<<<std::min((R + K7_OTSU_WARPS - 1) / K7_OTSU_WARPS, sms * 8), K7_OTSU_WARPS * 32, 0, st>>>(
         regions, R, w.hist, w.minmax, w.thr_adj, o.thr);
-    QC_LAUNCHED(ctx);
+    QC_LAUNCHED_AS(ctx, "k7_otsu", st);
     k7_cmp<<<band_grid, K4_THREADS, 0, st>>>(regions, R, p->total_bands, w.band_off, w.blurred, w.thr_adj, w.bits);
-    QC_LAUNCHED(ctx);
+    QC_LAUNCHED_AS(ctx, "k7_cmp", st);
     if (int rc = unionfind(w.bits, w.rank)) return rc;                             // w.rank doubles as the area table
     k7_area<<<band_grid, K4_THREADS, 0, st>>>(regions, R, p->total_bands, w.band_off, w.bits, w.parent, w.rank);
-    QC_LAUNCHED(ctx);
+    QC_LAUNCHED_AS(ctx, "k7_area", st);
     k7_filter<<<band_grid, K4_THREADS, 0, st>>>(regions, R, p->total_bands, w.band_off, w.bits, w.parent, w.rank, w.bits2);
-    QC_LAUNCHED(ctx);
+    QC_LAUNCHED_AS(ctx, "k7_filter", st);
     // (regions too large for shared memory flood in place in bits3, with their free rows parked in bits -- free until
     // the morphology pass rewrites it)
     if (int rc = fill_holes(w.bits2, w.bits3, w.bits)) return rc;
     if (int rc = morph(w.bits3, w.bits)) return rc;
     k7_emit<<<band_grid, K4_THREADS, 0, st>>>(im, regions, R, p->total_bands, w.band_off, gray7, w.bits, o.mask, o.labels,
                                               o.stats, (long long*)o.area, (long long*)o.sums);
-    QC_LAUNCHED(ctx);
+    QC_LAUNCHED_AS(ctx, "k7_emit", st);
     k7_finish<<<(R + 255) / 256, 256, 0, st>>>(regions, R, o.stats, (const long long*)o.area, o.ncomp, (long long*)o.sums);
-    QC_LAUNCHED(ctx);
+    QC_LAUNCHED_AS(ctx, "k7_finish", st);
     if (o.contours) return contour_stats(w.bits, w.bits3, w.bits2);      // final mask = bits; bits2 / bits3 are free now
     return QC_OK;
 }

@@ -66,8 +66,9 @@ extern "C" int qc_spc_stats(qc_ctx* ctx, const float* det, const int32_t* count,
                             void* stream) {
     qc_device_guard dev_guard(ctx);
     if (!ctx) return QC_ERR_INVALID;
+    QC_ENTER(ctx, stream);
     if (!det || !count || !out9 || n < 0 || max_det <= 0) QC_FAIL(ctx, QC_ERR_INVALID, "qc_spc_stats: bad argument");
     k5_spc<<<1, K5_THREADS, 0, (cudaStream_t)stream>>>(det, count, n, max_det, out9);
-    QC_LAUNCHED(ctx);
+    QC_LAUNCHED_AS(ctx, "k5_spc", stream);
     return QC_OK;
 }

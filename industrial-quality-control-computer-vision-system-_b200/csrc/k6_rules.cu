@@ -115,6 +115,7 @@ extern "C" int qc_rules_cluster(qc_ctx* ctx, const int32_t* box, const int32_t* 
                                 void* stream) {
     qc_device_guard dev_guard(ctx);
     if (!ctx) return QC_ERR_INVALID;
+    QC_ENTER(ctx, stream);
     if (n == 0) return QC_OK;
     if (!box || !cls || !count || !out_label || n < 0 || cap <= 0)
         QC_FAIL(ctx, QC_ERR_INVALID, "qc_rules_cluster: bad argument");
@@ -124,6 +125,6 @@ extern "C" int qc_rules_cluster(qc_ctx* ctx, const int32_t* box, const int32_t* 
     if (int rc = qc_prepare(ctx, k6_cluster, (int)smem, K6_THREADS, nullptr)) return rc;
     // the reference compares `1.0 - iou` against `eps = 1.0 - overlap_threshold` (both float64)
     k6_cluster<<<n, K6_THREADS, smem, (cudaStream_t)stream>>>(box, cls, keep, count, cap, 1.0 - overlap_threshold, out_label);
-    QC_LAUNCHED(ctx);
+    QC_LAUNCHED_AS(ctx, "k6_cluster", stream);
     return QC_OK;
 }

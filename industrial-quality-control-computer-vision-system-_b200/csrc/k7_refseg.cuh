@@ -642,42 +642,46 @@ __device__ __forceinline__ unsigned k7_hfill(unsigned m, unsigned s) {
 constexpr int K7_FILL_THREADS = 512;
 constexpr int K7_FILL_SMEM_WORDS = 12 * 1024;          // 48 KB: free + outside bit rows of a region up to ~196 K pixels
 
-// one region; F = free (background) bit rows, O = outside bit rows, both [h][wpr] in shared or global memory
+// one region; F = free (background) bit rows, O = outside bit rows, both [h][wpr] in shared or global memory.
+// A strip of rows is swept by a GROUP of G lanes (one lane per 32-pixel word; G = 4, 8, 16 or 32 >= words per row), so a
+// warp sweeps 32/G strips at once and the 16 warps of the CTA cover the region with strips of very few rows: an
+// iteration is only a handful of dependent row steps.
 __device__ __forceinline__ void k7_fill_region(const unsigned* F, volatile unsigned* O, int h, int wpr, int tid) {
     const int lane = tid & 31, warp = tid >> 5;
     constexpr int NW = K7_FILL_THREADS / 32;
-    const int S = max(8, (h + NW - 1) / NW);              // rows per strip
-    const int nstrips = (h + S - 1) / S;
-    const int nch = (wpr + 31) >> 5;
+    const int G = wpr <= 4 ? 4 : wpr <= 8 ? 8 : wpr <= 16 ? 16 : 32;
+    const int spw = 32 / G;                                // strips per warp
+    const int S = max(1, (h + NW * spw - 1) / (NW * spw)); // rows per strip
+    const int nch = (wpr + 31) >> 5;                       // 32-word chunks per row (> 1 only for rows wider than 1024 px)
+    const int gl = lane & (G - 1);                         // lane inside its group = word inside the chunk
+    const int a = (warp * spw + lane / G) * S, b = min(a + S, h);
     for (;;) {
         int changed = 0;
-        for (int st = warp; st < nstrips; st += NW) {
-            const int a = st * S, b = min(a + S, h);
-            for (int dir = 0; dir < 2; ++dir) {
-                for (int k = 0; k < b - a; ++k) {
-                    const int y = dir == 0 ? a + k : b - 1 - k;
-                    const int yn = dir == 0 ? y - 1 : y + 1;              // the row the flood comes from
-                    for (int c = 0; c < nch; ++c) {
-                        const int wx = c * 32 + lane;
-                        const bool valid = wx < wpr;
-                        const unsigned f = valid ? F[y * wpr + wx] : 0u;
-                        const unsigned o = valid ? O[y * wpr + wx] : 0u;
-                        unsigned s = o;
-                        if (valid && yn >= 0 && yn < h) s |= O[yn * wpr + wx] & f;
-                        for (;;) {
-                            s = k7_hfill(f, s);
-                            unsigned l = __shfl_up_sync(0xffffffffu, s, 1) >> 31;
-                            unsigned rt = __shfl_down_sync(0xffffffffu, s, 1) & 1u;
-                            if (lane == 0) l = (valid && wx > 0) ? (O[y * wpr + wx - 1] >> 31) : 0u;
-                            if (lane == 31) rt = (valid && wx + 1 < wpr) ? (O[y * wpr + wx + 1] & 1u) : 0u;
-                            const unsigned ns = s | (f & (l | (rt << 31)));
-                            const bool more = ns != s;
-                            s = ns;
-                            if (!__any_sync(0xffffffffu, more)) break;
-                        }
-                        if (valid && s != o) { O[y * wpr + wx] = s; changed = 1; }
-                        __syncwarp();
+        for (int dir = 0; dir < 2; ++dir) {
+            for (int k = 0; k < S; ++k) {
+                const int y = dir == 0 ? a + k : b - 1 - k;
+                const bool row_ok = a + k < b;
+                const int yn = dir == 0 ? y - 1 : y + 1;               // the row the flood comes from
+                for (int c = 0; c < nch; ++c) {
+                    const int wx = c * 32 + gl;
+                    const bool valid = row_ok && wx < wpr;
+                    const unsigned f = valid ? F[y * wpr + wx] : 0u;
+                    const unsigned o = valid ? O[y * wpr + wx] : 0u;
+                    unsigned s = o;
+                    if (valid && yn >= 0 && yn < h) s |= O[yn * wpr + wx] & f;
+                    for (;;) {
+                        s = k7_hfill(f, s);
+                        unsigned l = __shfl_up_sync(0xffffffffu, s, 1, G) >> 31;
+                        unsigned rt = __shfl_down_sync(0xffffffffu, s, 1, G) & 1u;
+                        if (gl == 0) l = (valid && wx > 0) ? (O[y * wpr + wx - 1] >> 31) : 0u;
+                        if (gl == G - 1) rt = (valid && wx + 1 < wpr) ? (O[y * wpr + wx + 1] & 1u) : 0u;
+                        const unsigned ns = s | (f & (l | (rt << 31)));
+                        const bool more = ns != s;
+                        s = ns;
+                        if (!__any_sync(0xffffffffu, more)) break;
                     }
+                    if (valid && s != o) { O[y * wpr + wx] = s; changed = 1; }
+                    __syncwarp();
                 }
             }
         }

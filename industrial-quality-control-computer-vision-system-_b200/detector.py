@@ -94,6 +94,19 @@ def _decode(image: np.ndarray) -> np.ndarray:
     return image
 
 
+def _jpeg_info(image, device: int = 0):
+    """qc_jpeg_info of an encoded upload (the 1-D uint8 buffer of app.py:190-194) when K10 decodes it on the device
+    (baseline JPEG), else None: other encodings -- PNG, progressive JPEG, ... -- keep the reference's own host call,
+    cv2.imdecode, like before."""
+    if not (isinstance(image, np.ndarray) and image.ndim == 1 and image.dtype == np.uint8 and image.size >= 4
+            and image[0] == 0xFF and image[1] == 0xD8):
+        return None
+    try:
+        return ffi.Context.current(device).jpeg_info(image)
+    except ffi.QcGraftError:
+        return None
+
+
 def _as_rgb3(image: np.ndarray) -> np.ndarray:
     if image.ndim == 2:
         image = np.repeat(image[:, :, None], 3, 2)
@@ -884,6 +897,9 @@ class QualityControlDetector:
         self.segmentator = None
         self.postprocessor = None
         self.performance_stats = {"total_predictions": 0, "total_time": 0.0, "average_time": 0.0}
+        # encoded uploads: how many were decoded by K10 on the device / by cv2.imdecode on the host (non-JPEG,
+        # progressive, ...: the reference's own call)
+        self.decode_stats = {"device_jpeg": 0, "host_imdecode": 0}
         self.initialize_components(yolo_weights, resnet_weights)
 
     def initialize_components(self, yolo_weights: str, resnet_weights: str):
@@ -946,17 +962,28 @@ class QualityControlDetector:
         pipe.conf, pipe.iou = ydet.confidence_threshold, ydet.nms_threshold
         pre = self.config.get("preprocessing", {}) if isinstance(self.config, dict) else {}
         raw_ok = not ("resize" in pre or pre.get("denoise", False) or pre.get("enhance_contrast", False))
-        decoded = [_decode(im) for im in images]
-        if raw_ok:
-            # no optional host preprocessing: the three channel flips are folded into the kernels' swap flags
-            frames_np = [_as_rgb3(im) for im in decoded]
-            shapes = [self._processed_shape(im) for im in decoded]
+        dev_index = pipe.dev.index or 0
+        infos = [_jpeg_info(im, dev_index) for im in images] if raw_ok else [None]
+        if all(i is not None for i in infos):
+            # encoded uploads: K10 decodes the whole group on the device (bit-exact with cv2.imdecode); no decoded
+            # frame ever exists on the host, so the assembly below only gets the frame's shape
+            batch_dev = pipe.qc.jpeg_decode(images, rgb=False, infos=infos)
+            shapes = [(i.height, i.width, 3) for i in infos]
+            frames_np = [np.broadcast_to(np.uint8(0), sh) for sh in shapes]
+            self.decode_stats["device_jpeg"] += len(images)
         else:
-            processed = [self._preprocess_image(im) for im in images]
-            frames_np = [_as_rgb3(im) for im in processed]
-            shapes = [im.shape for im in processed]
-        batch = torch.from_numpy(np.stack(frames_np))
-        res = pipe.run(batch.to(pipe.dev), head_override=head_override, inject=inject,
+            self.decode_stats["host_imdecode"] += sum(1 for im in images if isinstance(im, np.ndarray) and im.ndim == 1)
+            decoded = [_decode(im) for im in images]
+            if raw_ok:
+                # no optional host preprocessing: the three channel flips are folded into the kernels' swap flags
+                frames_np = [_as_rgb3(im) for im in decoded]
+                shapes = [self._processed_shape(im) for im in decoded]
+            else:
+                processed = [self._preprocess_image(im) for im in images]
+                frames_np = [_as_rgb3(im) for im in processed]
+                shapes = [im.shape for im in processed]
+            batch_dev = torch.from_numpy(np.stack(frames_np)).to(pipe.dev)
+        res = pipe.run(batch_dev, head_override=head_override, inject=inject,
                        include_segmentation=include_segmentation,
                        keep_seg_tensors=include_segmentation, processed=not raw_ok)
         n = len(images)
@@ -1034,8 +1061,9 @@ class QualityControlDetector:
                     results[i] = self.predict(img)
                 else:
                     try:
-                        d = _decode(img)
-                        groups.setdefault(tuple(d.shape), []).append(i)
+                        info = _jpeg_info(img, int(_qcfg(self.config).get("device", 0)))
+                        shape = (info.height, info.width, 3) if info is not None else tuple(_decode(img).shape)
+                        groups.setdefault(shape, []).append(i)
                     except Exception as e:
                         results[i] = {"error": str(e)}
             chunk = int(_qcfg(self.config).get("max_batch", 64))
@@ -1090,6 +1118,8 @@ class QualityControlDetector:
         if image is None or not isinstance(image, np.ndarray):
             return False
         if image.ndim == 1:
+            if self._fused() and _jpeg_info(image, int(_qcfg(self.config).get("device", 0))) is not None:
+                return True                      # a stream K10 decodes: the header parse is the validation
             try:
                 return cv2.imdecode(image, cv2.IMREAD_COLOR) is not None
             except Exception:
@@ -1116,8 +1146,12 @@ class QualityControlDetector:
 
     def _get_image_metadata(self, image: np.ndarray) -> Dict:
         if image.ndim == 1:
-            decoded = cv2.imdecode(image, cv2.IMREAD_COLOR)
-            shape = decoded.shape if decoded is not None else (0, 0, 0)
+            info = _jpeg_info(image, int(_qcfg(self.config).get("device", 0))) if self._fused() else None
+            if info is not None:
+                shape = (info.height, info.width, 3)
+            else:
+                decoded = cv2.imdecode(image, cv2.IMREAD_COLOR)
+                shape = decoded.shape if decoded is not None else (0, 0, 0)
         else:
             shape = image.shape
         return {"original_shape": shape, "channels": shape[2] if len(shape) > 2 else 1,

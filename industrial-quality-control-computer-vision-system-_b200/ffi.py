@@ -62,6 +62,13 @@ class SegParams(C.Structure):
                 ("total_chunks", C.c_int32), ("max_region_w", C.c_int32), ("max_region_h", C.c_int32)]
 
 
+class JpegInfo(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("components", C.c_int32), ("subsampling", C.c_int32),
+                ("restart_interval", C.c_int32), ("reserved", C.c_int32), ("blocks", C.c_int64)]
+
+
+QC_JPEG_GRAY, QC_JPEG_444, QC_JPEG_422, QC_JPEG_420 = 0, 1, 2, 3
+
 SEG_REGION_DTYPE = np.dtype([("img", "i4"), ("x", "i4"), ("y", "i4"), ("w", "i4"), ("h", "i4"),
                              ("polarity", "i4"), ("min_area", "i4"), ("max_comp", "i4"), ("thr_scale", "f8"),
                              ("out_offset", "i8"), ("stats_offset", "i4"), ("band_offset", "i4"),
@@ -76,6 +83,15 @@ _SIGS = {
     "qc_sm_count": (C.c_int, [C.c_void_p]),
     "qc_launch_count": (C.c_int64, [C.c_void_p]),
     "qc_sizeof": (C.c_size_t, [C.c_int]),
+    "qc_jpeg_info_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(JpegInfo)]),
+    "qc_jpeg_entropy_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
+    "qc_jpeg_staging_bytes": (C.c_size_t, [C.POINTER(JpegInfo), C.c_int]),
+    "qc_jpeg_workspace_bytes": (C.c_size_t, [C.POINTER(JpegInfo), C.c_int]),
+    "qc_jpeg_decode": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.c_int, C.POINTER(JpegInfo),
+                                 C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p,
+                                 C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.c_int, C.c_void_p]),
+    "qc_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
+    "qc_profile_collect": (C.c_int, [C.c_void_p, C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.c_int]),
     "qc_pre_make_plan": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(PrePlan)]),
     "qc_preprocess": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int32, C.POINTER(PrePlan),
                                 C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
@@ -201,6 +217,17 @@ class Context:
     @property
     def sm_count(self) -> int:
         return int(self.lib.qc_sm_count(self.h))
+
+    def profile(self, on: bool) -> None:
+        """Per-kernel CUDA-event timing inside the library (measurement only; see include/qcgraft.h)."""
+        self._check(self.lib.qc_profile_enable(self.h, int(bool(on))), "qc_profile_enable")
+
+    def profile_collect(self, cap: int = 4096):
+        """[(kernel name, ms)] in launch order since the last collection; waits for the recorded events."""
+        names = (C.c_char_p * cap)()
+        ms = (C.c_float * cap)()
+        n = min(int(self.lib.qc_profile_collect(self.h, names, ms, cap)), cap)
+        return [(names[i].decode(), float(ms[i])) for i in range(n)]
 
     def workspace(self, key: str, nbytes: int) -> torch.Tensor:
         """Grow-only cached scratch buffer (caller-owned memory as far as the C ABI goes)."""
@@ -507,6 +534,57 @@ class Context:
                                        _stream(box.device))
         self._check(rc, "qc_rules_cluster")
         return out
+
+    # -- K10 -------------------------------------------------------------------------------
+    def jpeg_info(self, buf: np.ndarray) -> JpegInfo:
+        """Header of one encoded stream (host only).  Raises QcGraftError for anything K10 does not decode."""
+        buf = np.ascontiguousarray(np.frombuffer(buf, np.uint8) if isinstance(buf, (bytes, bytearray)) else buf, np.uint8)
+        info = JpegInfo()
+        self._check(self.lib.qc_jpeg_info_host(self.h, buf.ctypes.data, buf.size, C.byref(info)), "qc_jpeg_info_host")
+        return info
+
+    def jpeg_decode(self, bufs, rgb: bool = False, threads: Optional[int] = None, infos=None):
+        """cv2.imdecode(buf, IMREAD_COLOR) for a batch of baseline JPEG streams (1-D uint8 arrays or bytes), bit for
+        bit; rgb=True also folds the reference's BGR2RGB in.  Returns one uint8 CUDA tensor [n,h,w,3] when all
+        frames have the same size, else a list of [h,w,3] tensors (views of one buffer)."""
+        arrs = [np.ascontiguousarray(np.frombuffer(b, np.uint8) if isinstance(b, (bytes, bytearray)) else b, np.uint8)
+                for b in bufs]
+        n = len(arrs)
+        if n == 0:
+            return []
+        if infos is None:
+            infos = [self.jpeg_info(a) for a in arrs]
+        cinfo = (JpegInfo * n)(*infos)
+        nstage = int(self.lib.qc_jpeg_staging_bytes(cinfo, n))
+        nws = int(self.lib.qc_jpeg_workspace_bytes(cinfo, n))
+        ev = getattr(self, "_jpeg_event", None)
+        if ev is not None:
+            ev.synchronize()                               # the previous call's upload has left the staging buffer
+        st = getattr(self, "_jpeg_staging", None)
+        if st is None or st.numel() < nstage:
+            st = self._jpeg_staging = torch.empty(nstage, dtype=torch.uint8).pin_memory()
+        ws = self.workspace("jpeg", nws)
+        sizes = [(i.height, i.width) for i in infos]
+        offs, o = [], 0
+        for h, w in sizes:
+            offs.append(o)
+            o += h * w * 3
+        dst = torch.empty(o, dtype=torch.uint8, device=self.device)
+        ptrs = (C.c_void_p * n)(*[a.ctypes.data for a in arrs])
+        lens = (C.c_size_t * n)(*[a.size for a in arrs])
+        coffs = (C.c_int64 * n)(*offs)
+        cstr = (C.c_int32 * n)(*[3 * w for _, w in sizes])
+        if threads is None:
+            threads = max(1, min(n, (os.cpu_count() or 1), 32))
+        rc = self.lib.qc_jpeg_decode(self.h, ptrs, lens, n, cinfo, int(threads), st.data_ptr(), st.numel(),
+                                     ws.data_ptr(), ws.numel(), dst.data_ptr(), coffs, cstr, int(bool(rgb)),
+                                     _stream(self.device))
+        self._check(rc, "qc_jpeg_decode")
+        self._jpeg_event = torch.cuda.Event()
+        self._jpeg_event.record(torch.cuda.current_stream(self.device))
+        if len(set(sizes)) == 1:
+            return dst.view(n, sizes[0][0], sizes[0][1], 3)
+        return [dst[o_:o_ + h * w * 3].view(h, w, 3) for o_, (h, w) in zip(offs, sizes)]
 
     def spc_stats(self, det: torch.Tensor, count: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         n, md = det.shape[0], det.shape[1]

@@ -19,8 +19,9 @@ for name, code, iters, marea in (("threshold", ffi.QC_SEG_REF_THRESHOLD, 2, 10),
         continue
     regs = dict(img=img, x=x, y=y, w=w, h=h, polarity=rng.integers(0, 2, K), thr_scale=0.8, min_area=marea)
     regs["max_comp"] = np.full(K, 2) if name == "threshold" else np.minimum(((w + 1) // 2) * ((h + 1) // 2) + 1, 1024)
+    full = os.environ.get("K7_FULL", "1") == "1"      # with K8 contour statistics and K9 Canny confidence, as the pipeline runs it
     call = lambda: qc.segment(frames, regs, morph_iters=iters, swap_rb=True, want_mask=False, want_labels=False,
-                              method=code, want_sums=(name == "threshold"))
+                              method=code, want_sums=full or name == "threshold", want_contours=full)
     for _ in range(3):
         res = call()
     torch.cuda.synchronize()
