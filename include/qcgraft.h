@@ -58,7 +58,8 @@ int64_t qc_launch_count(const qc_ctx* ctx);
 int qc_profile_enable(qc_ctx* ctx, int on);
 int qc_profile_collect(qc_ctx* ctx, const char** names, float* ms, int cap);
 /* sizeof() of the ABI structs, for bindings to self-check their layout:
- * 0 qc_pre_plan, 1 qc_yolo_params, 2 qc_seg_region, 3 qc_seg_params, 4 qc_jpeg_info */
+ * 0 qc_pre_plan, 1 qc_yolo_params, 2 qc_seg_region, 3 qc_seg_params, 4 qc_jpeg_info,
+ * 5 qc_rules_row, 6 qc_rules_refined, 7 qc_rules_out */
 size_t qc_sizeof(int which);
 
 /* ---- K1: letterbox / stretch resize + normalise + NCHW pack -------------
@@ -303,6 +304,45 @@ int qc_spc_stats(qc_ctx* ctx, const float* det, const int32_t* count, int n, int
 int qc_rules_cluster(qc_ctx* ctx, const int32_t* box, const int32_t* cls, const uint8_t* keep,
                      const int32_t* count, int n, int cap, double overlap_threshold, int32_t* out_label,
                      void* stream);
+
+/* ---- K6 (whole chain): refine -> filter -> merge -> validate of the post-NMS rule engine (row f1) ----
+ * Replaces the detection chain of PostProcessor.process_results, inference/postprocess.py:64-81:
+ * _refine_detections :111-184 (+ _refine_bbox_from_mask :764-812, _refine_severity :814-840),
+ * _filter_detections :186-231, _merge_overlapping_detections :233-303, _merge_detection_cluster
+ * :305-358, _validate_detections :360-410, _calculate_validation_score :412-464 -- for a batch of
+ * images, one table of `cap` rows per image.  float64 results are bit-identical with the reference's
+ * Python / numpy arithmetic (np.mean in pairwise order, IEEE divisions).
+ *   rows[n][cap]         input: what the detector, the ensemble and the segmentation produced per detection
+ *   count[n], shapes[n][2] = (height, width) of each image
+ *   elongated_classes    bit c set = class id c is one of the reference's ('crack', 'scratch') (:833)
+ *   out_refined[n][cap]  per input row: refined bbox / severity / area and whether the filter kept it
+ *   out_rows[n][cap]     the merged list in the reference's order (out_count[n] rows); flags bit 1 =
+ *                        validation_score > 0.3 (the row survives), bit 0 = area_consistency_warning
+ *   out_member[n][cap]   per input row: index of the out row it went into, -1 = filtered out
+ */
+typedef struct {
+    int32_t x1, y1, x2, y2;    /* detection bbox (ints of models/yolo_model.py:139)                    */
+    int32_t cls, severity;     /* class id; 1 minor, 2 major, 3 critical                               */
+    int32_t has_seg, reserved;
+    int32_t ext[4];            /* mask extent y_min, y_max, x_min, x_max in frame coordinates; ext[0] < 0 = empty mask */
+    int64_t area_pixels;       /* segmentation area (has_seg)                                          */
+    double conf;               /* ensemble_confidence                                                  */
+    double seg_conf, area_pct, compactness;
+} qc_rules_row;
+typedef struct {
+    int32_t x1, y1, x2, y2, severity, kept;
+    int64_t area_pixels;
+} qc_rules_refined;
+typedef struct {
+    int32_t base, merged_from; /* input row whose other fields the row inherits; number of members      */
+    int32_t x1, y1, x2, y2, severity, flags;
+    int64_t area_pixels;
+    double conf, validation_score;
+} qc_rules_out;
+int qc_rules_apply(qc_ctx* ctx, const qc_rules_row* rows, const int32_t* count, const int32_t* shapes, int n,
+                   int cap, double min_conf, double max_area_pct, uint64_t elongated_classes,
+                   double overlap_threshold, qc_rules_refined* out_refined, qc_rules_out* out_rows,
+                   int32_t* out_member, int32_t* out_count, void* stream);
 
 /* ---- K10: batched baseline-JPEG decode (row f4, input side) ---------------------------------
  * Replaces: cv2.imdecode(buf, cv2.IMREAD_COLOR) at inference/detector.py:214,229 and

@@ -87,6 +87,9 @@ size_t qc_sizeof(int which) {
         case 2: return sizeof(qc_seg_region);
         case 3: return sizeof(qc_seg_params);
         case 4: return sizeof(qc_jpeg_info);
+        case 5: return sizeof(qc_rules_row);
+        case 6: return sizeof(qc_rules_refined);
+        case 7: return sizeof(qc_rules_out);
         default: return 0;
     }
 }

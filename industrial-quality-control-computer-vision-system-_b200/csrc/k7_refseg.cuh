@@ -640,7 +640,7 @@ __device__ __forceinline__ unsigned k7_hfill(unsigned m, unsigned s) {
 }
 
 constexpr int K7_FILL_THREADS = 512;
-constexpr int K7_FILL_SMEM_WORDS = 12 * 1024;          // 48 KB: free + outside bit rows of a region up to ~196 K pixels
+constexpr int K7_FILL_SMEM_WORDS = 25 * 1024;          // 100 KB per CTA, two CTAs per SM
 
 // one region; F = free (background) bit rows, O = outside bit rows, both [h][wpr] in shared or global memory.
 // A strip of rows is swept by a GROUP of G lanes (one lane per 32-pixel word; G = 4, 8, 16 or 32 >= words per row), so a
@@ -689,36 +689,145 @@ __device__ __forceinline__ void k7_fill_region(const unsigned* F, volatile unsig
     }
 }
 
-__global__ void __launch_bounds__(K7_FILL_THREADS)
+// The flood as a union-find over horizontal runs (the normal path; the sweeps above are the fallback for a region whose
+// runs do not fit the CTA's shared memory).  Sweeps need one iteration per change of direction of the background's
+// paths -- hundreds on a textured ROI -- while the union-find does a fixed amount of work:
+//   nodes   = maximal horizontal runs of free pixels (a run may span words), numbered 1.. in raster order through a
+//             CTA-wide prefix sum of the per-word run starts; node 0 = "outside"
+//   unions  = one per maximal interval of F[y] & F[y-1] (two runs overlap in exactly one interval: 4-connectivity),
+//             found as the start bits of that AND; runs touching the ROI's outer ring are united with node 0
+//   output  = every run whose root is not 0 is a hole: result = ~outside inside the ROI.
+__device__ __forceinline__ unsigned k7_run_starts(const unsigned* F, int i, int wx) {
+    const unsigned f = F[i];
+    return f & ~((f << 1) | (wx > 0 ? F[i - 1] >> 31 : 0u));
+}
+
+__global__ void __launch_bounds__(K7_FILL_THREADS, 2)
 k7_fill(const qc_seg_region* __restrict__ regs, int R, const unsigned* __restrict__ bits_in,
         unsigned* __restrict__ bits_out, unsigned* __restrict__ free_ws) {
     extern __shared__ __align__(16) unsigned k7f_sm[];
-    const int tid = threadIdx.x;
+    __shared__ int s_warp[K7_FILL_THREADS / 32];
+    __shared__ int s_total;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int r = blockIdx.x; r < R; r += gridDim.x) {
         const qc_seg_region rg = regs[r];
         const int wpr = wpr_of(rg), h = rg.h, nwords = h * wpr;
         const unsigned tail = (rg.w & 31) ? ((1u << (rg.w & 31)) - 1u) : 0xFFFFFFFFu;   // valid bits of the last word
         const unsigned* B = bits_in + rg.bits_offset;
         unsigned* G = bits_out + rg.bits_offset;
-        const bool in_smem = 2 * nwords <= K7_FILL_SMEM_WORDS;
-        unsigned* F = in_smem ? k7f_sm : free_ws + rg.bits_offset;
-        unsigned* O = in_smem ? k7f_sm + nwords : G;
+        const bool f_smem = 2 * nwords <= K7_FILL_SMEM_WORDS;
+        unsigned* F = f_smem ? k7f_sm : free_ws + rg.bits_offset;
         __syncthreads();
-        // free pixels; seeds = the free pixels of the ROI's outer ring
         for (int i = tid; i < nwords; i += K7_FILL_THREADS) {
-            const int y = i / wpr, wx = i - y * wpr;
+            const int wx = i % wpr;
             unsigned f = ~__ldg(B + i);
             if (wx == wpr - 1) f &= tail;
+            F[i] = f;
+        }
+        __syncthreads();
+        // ---- run numbering: exclusive prefix of the run starts over the words in raster order -----------------
+        bool uf = f_smem;
+        int* base = reinterpret_cast<int*>(k7f_sm + nwords);
+        int* parent = base + nwords;
+        const int cap = K7_FILL_SMEM_WORDS - 2 * nwords;                  // nodes the rest of the buffer holds
+        if (uf) {
+            const int per = (nwords + K7_FILL_THREADS - 1) / K7_FILL_THREADS;
+            const int i0 = min(tid * per, nwords), i1 = min(i0 + per, nwords);
+            int mine = 0;
+            for (int i = i0; i < i1; ++i) mine += __popc(k7_run_starts(F, i, i % wpr));
+            int inc = mine;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, inc, d);
+                if (lane >= d) inc += v;
+            }
+            if (lane == 31) s_warp[warp] = inc;
+            __syncthreads();
+            if (warp == 0) {
+                int v = lane < K7_FILL_THREADS / 32 ? s_warp[lane] : 0, w = v;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int u = __shfl_up_sync(0xffffffffu, w, d);
+                    if (lane >= d) w += u;
+                }
+                if (lane < K7_FILL_THREADS / 32) s_warp[lane] = w - v;
+                if (lane == 31) s_total = w;
+            }
+            __syncthreads();
+            int run = s_warp[warp] + inc - mine;
+            for (int i = i0; i < i1; ++i) {
+                base[i] = run;
+                run += __popc(k7_run_starts(F, i, i % wpr));
+            }
+            uf = s_total + 1 <= cap;                                       // block-uniform
+        }
+        if (uf) {
+            const int nodes = s_total + 1;
+            for (int i = tid; i < nodes; i += K7_FILL_THREADS) parent[i] = i;
+            __syncthreads();
+            for (int i = tid; i < nwords; i += K7_FILL_THREADS) {
+                const int y = i / wpr, wx = i - y * wpr;
+                const unsigned f = F[i];
+                if (!f) continue;
+                const unsigned st = k7_run_starts(F, i, wx);
+                const int b0 = base[i];
+                // runs on the ROI's outer ring are outside
+                unsigned ring = (y == 0 || y == h - 1) ? (st | (f & 1u)) : 0u;      // every run of the row (f&1: one continuing into this word)
+                if (wx == 0) ring |= f & 1u;
+                if (wx == wpr - 1) ring |= f & (1u << ((rg.w - 1) & 31));
+                while (ring) {
+                    const int c = __ffs(ring) - 1;
+                    ring &= ring - 1;
+                    suf_union(parent, b0 + __popc(st & ((2u << c) - 1u)), 0);
+                }
+                if (y == 0) continue;
+                const unsigned fa = F[i - wpr];
+                const unsigned both = f & fa;
+                if (!both) continue;
+                const unsigned prev = wx > 0 ? ((F[i - 1] & F[i - 1 - wpr]) >> 31) : 0u;
+                unsigned sb = both & ~((both << 1) | prev);
+                const unsigned sta = k7_run_starts(F, i - wpr, wx);
+                const int ba = base[i - wpr];
+                while (sb) {
+                    const int c = __ffs(sb) - 1;
+                    sb &= sb - 1;
+                    const unsigned le = (2u << c) - 1u;
+                    suf_union(parent, b0 + __popc(st & le), ba + __popc(sta & le));
+                }
+            }
+            __syncthreads();
+            for (int i = tid; i < nwords; i += K7_FILL_THREADS) {
+                const int wx = i % wpr;
+                const unsigned f = F[i];
+                const unsigned st = k7_run_starts(F, i, wx);
+                const int b0 = base[i];
+                unsigned heads = st | (f & 1u);                           // first bit of every run piece inside this word
+                unsigned out = 0;
+                while (heads) {
+                    const int c = __ffs(heads) - 1;
+                    heads &= heads - 1;
+                    if (suf_find(parent, b0 + __popc(st & ((2u << c) - 1u))) == 0) {
+                        const unsigned t = f >> c;
+                        out |= (t & ~(t + 1u)) << c;                      // the run's pixels in this word
+                    }
+                }
+                G[i] = wx == wpr - 1 ? (~out & tail) : ~out;
+            }
+            continue;
+        }
+        // ---- fallback: sweeps, outside rows in the rest of the shared buffer or in the output itself ------------
+        unsigned* O = f_smem ? k7f_sm + nwords : G;
+        __syncthreads();
+        for (int i = tid; i < nwords; i += K7_FILL_THREADS) {
+            const int y = i / wpr, wx = i - y * wpr;
             unsigned ring = 0;
             if (y == 0 || y == h - 1) ring = 0xFFFFFFFFu;
             if (wx == 0) ring |= 1u;
             if (wx == wpr - 1) ring |= 1u << ((rg.w - 1) & 31);
-            F[i] = f;
-            O[i] = f & ring;
+            O[i] = F[i] & ring;
         }
         __syncthreads();
         k7_fill_region(F, O, h, wpr, tid);
-        // holes = free pixels the flood never reached: result = ~outside inside the ROI
         for (int i = tid; i < nwords; i += K7_FILL_THREADS) {
             const int wx = i % wpr;
             const unsigned o = O[i];

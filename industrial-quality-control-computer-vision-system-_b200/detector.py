@@ -835,8 +835,17 @@ class RulesPostProcessor(_PassThroughPostProcessor):
 
     def __init__(self, config):
         super().__init__(config)
-        from .rules import DetectionRules
-        self.rules = DetectionRules(config)
+        self.rules = self._make_rules()
+
+    def _make_rules(self):
+        """K6 on the device (``qc_rules_apply``) is the default wherever a GPU is present;
+        ``config['qcgraft']['rules_on_device'] = False`` selects the host tables of qcgraft/rules.py, which produce the
+        same dictionaries (they are what the CPU tests pin against the reference's PostProcessor)."""
+        from .rules import DetectionRules, DeviceDetectionRules
+        q = _qcfg(self.config)
+        if q.get("rules_on_device", torch.cuda.is_available()):
+            return DeviceDetectionRules(self.config, int(q.get("device", 0)))
+        return DetectionRules(self.config)
 
     def _generate_recommendations(self, detections, quality, risk) -> List[str]:
         rec = []
@@ -864,7 +873,22 @@ class RulesPostProcessor(_PassThroughPostProcessor):
             rec.append("High defect density - review entire manufacturing process")
         return rec
 
-    def process_results(self, ensemble_results, segmentation_results, image_shape):
+    def process_results_many(self, items) -> List[Dict]:
+        """process_results for every (ensemble_results, segmentation_results, image_shape) of a batch; with the device
+        rules the detection chains of all images run in ONE kernel launch."""
+        chains: List[Optional[List[Dict]]] = [None] * len(items)
+        if hasattr(self.rules, "process_many"):
+            try:
+                idx = [i for i, it in enumerate(items) if it[0].get("detections")]
+                done = self.rules.process_many([(items[i][0]["detections"], items[i][1] or {}, items[i][2]) for i in idx])
+                for i, d in zip(idx, done):
+                    chains[i] = d
+            except Exception as e:
+                logger.error(f"Error in batched post-processing: {str(e)}")
+                return [{"error": str(e)} for _ in items]
+        return [self.process_results(*it, _chain=chains[i]) for i, it in enumerate(items)]
+
+    def process_results(self, ensemble_results, segmentation_results, image_shape, _chain=None):
         try:
             from datetime import datetime
             meta = {"processing_timestamp": datetime.now().isoformat(), "image_shape": image_shape,
@@ -873,7 +897,7 @@ class RulesPostProcessor(_PassThroughPostProcessor):
             if not raw:                                                  # early return of :62-64
                 return {"detections": [], "quality_assessment": self.rules._assess_quality([], {}),
                         "risk_analysis": {}, "recommendations": [], "metadata": dict(meta, total_detections=0)}
-            dets = self.rules.process(raw, segmentation_results or {}, image_shape)
+            dets = _chain if _chain is not None else self.rules.process(raw, segmentation_results or {}, image_shape)
             quality = self.rules._assess_quality(dets, segmentation_results or {})
             risk = self.rules._analyze_risks(dets, quality)
             rec = self._generate_recommendations(dets, quality, risk)
@@ -885,7 +909,7 @@ class RulesPostProcessor(_PassThroughPostProcessor):
 
     def update_config(self, new_config):
         super().update_config(new_config)
-        self.rules = type(self.rules)(self.config)
+        self.rules = self._make_rules()
 
 
 class QualityControlDetector:
@@ -997,7 +1021,7 @@ class QualityControlDetector:
                     o = int(r.out_offset)
                     masks_host[int(k)] = m[o:o + int(r.w) * int(r.h)].reshape(int(r.h), int(r.w))
         per_image = (time.time() - t0) / n
-        out = []
+        out, pending = [], []
         for i in range(n):
             try:
                 rows = res.det[i, :int(res.count[i])]
@@ -1028,17 +1052,27 @@ class QualityControlDetector:
                         cs_[j] = res.seg_contours[k]
                         assert (code == ffi.QC_SEG_REF_ADAPTIVE) == (name == "adaptive")
                     segmentation_results = seg._assemble(frames_np[i], dets, sel, lm, ar, sm, bgr=raw_ok, cstats=cs_)
-                final = self.postprocessor.process_results(ensemble_results, segmentation_results, shape)
-                dt = per_image + 0.0
-                self._update_performance_stats(dt)
-                final.update({"total_inference_time_ms": dt * 1000,
-                              "processing_pipeline": "ensemble + segmentation + postprocess",
-                              "image_metadata": self._get_image_metadata(images[i])})
-                out.append(final)
+                out.append(None)
+                pending.append((i, (ensemble_results, segmentation_results, shape)))
             except Exception as e:
                 logger.error(f"Error in QC prediction: {str(e)}")
                 out.append({"error": str(e)})
-            per_image = (time.time() - t0) / n
+        # the post-NMS rule chains of the whole group: one K6 launch with the default post-processor
+        try:
+            if hasattr(self.postprocessor, "process_results_many"):
+                finals = self.postprocessor.process_results_many([it for _, it in pending])
+            else:
+                finals = [self.postprocessor.process_results(*it) for _, it in pending]
+        except Exception as e:
+            logger.error(f"Error in QC prediction: {str(e)}")
+            finals = [{"error": str(e)} for _ in pending]
+        per_image = (time.time() - t0) / n
+        for (i, _), final in zip(pending, finals):
+            self._update_performance_stats(per_image)
+            final.update({"total_inference_time_ms": per_image * 1000,
+                          "processing_pipeline": "ensemble + segmentation + postprocess",
+                          "image_metadata": self._get_image_metadata(images[i])})
+            out[i] = final
         return out
 
     @staticmethod

@@ -69,6 +69,16 @@ class JpegInfo(C.Structure):
 
 QC_JPEG_GRAY, QC_JPEG_444, QC_JPEG_422, QC_JPEG_420 = 0, 1, 2, 3
 
+# K6 whole-chain tables (qc_rules_row / qc_rules_refined / qc_rules_out of include/qcgraft.h)
+RULES_ROW_DTYPE = np.dtype([("x1", "i4"), ("y1", "i4"), ("x2", "i4"), ("y2", "i4"), ("cls", "i4"), ("severity", "i4"),
+                            ("has_seg", "i4"), ("reserved", "i4"), ("ext", "i4", (4,)), ("area_pixels", "i8"),
+                            ("conf", "f8"), ("seg_conf", "f8"), ("area_pct", "f8"), ("compactness", "f8")], align=True)
+RULES_REFINED_DTYPE = np.dtype([("x1", "i4"), ("y1", "i4"), ("x2", "i4"), ("y2", "i4"), ("severity", "i4"), ("kept", "i4"),
+                                ("area_pixels", "i8")], align=True)
+RULES_OUT_DTYPE = np.dtype([("base", "i4"), ("merged_from", "i4"), ("x1", "i4"), ("y1", "i4"), ("x2", "i4"), ("y2", "i4"),
+                            ("severity", "i4"), ("flags", "i4"), ("area_pixels", "i8"), ("conf", "f8"),
+                            ("validation_score", "f8")], align=True)
+
 SEG_REGION_DTYPE = np.dtype([("img", "i4"), ("x", "i4"), ("y", "i4"), ("w", "i4"), ("h", "i4"),
                              ("polarity", "i4"), ("min_area", "i4"), ("max_comp", "i4"), ("thr_scale", "f8"),
                              ("out_offset", "i8"), ("stats_offset", "i4"), ("band_offset", "i4"),
@@ -83,6 +93,8 @@ _SIGS = {
     "qc_sm_count": (C.c_int, [C.c_void_p]),
     "qc_launch_count": (C.c_int64, [C.c_void_p]),
     "qc_sizeof": (C.c_size_t, [C.c_int]),
+    "qc_rules_apply": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double,
+                                 C.c_uint64, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "qc_jpeg_info_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(JpegInfo)]),
     "qc_jpeg_entropy_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
     "qc_jpeg_staging_bytes": (C.c_size_t, [C.POINTER(JpegInfo), C.c_int]),
@@ -534,6 +546,36 @@ class Context:
                                        _stream(box.device))
         self._check(rc, "qc_rules_cluster")
         return out
+
+    def rules_apply(self, rows: np.ndarray, count: np.ndarray, shapes: np.ndarray, min_conf: float = 0.5,
+                    max_area_pct: float = 50.0, elongated_classes: int = 0, overlap_threshold: float = 0.3) -> dict:
+        """The whole post-NMS detection chain (refine -> filter -> merge -> validate) of a batch on the device.
+        rows: RULES_ROW_DTYPE [n, cap]; count int32 [n]; shapes int32 [n, 2] = (height, width).  One upload, one
+        launch, one download; returns host arrays {refined, rows, member, count}."""
+        assert rows.dtype == RULES_ROW_DTYPE and rows.ndim == 2
+        n, cap = rows.shape
+        count = np.ascontiguousarray(count, np.int32)
+        shapes = np.ascontiguousarray(shapes, np.int32).reshape(n, 2)
+        nb_rows, nb_ref, nb_out = n * cap * RULES_ROW_DTYPE.itemsize, n * cap * RULES_REFINED_DTYPE.itemsize, \
+            n * cap * RULES_OUT_DTYPE.itemsize
+        # one packed upload (rows | count | shapes) and one packed download (refined | out rows | member | count)
+        up = np.empty(nb_rows + 4 * n + 8 * n, np.uint8)
+        up[:nb_rows] = np.ascontiguousarray(rows).view(np.uint8).reshape(-1)
+        up[nb_rows:nb_rows + 4 * n] = count.view(np.uint8)
+        up[nb_rows + 4 * n:] = shapes.view(np.uint8).reshape(-1)
+        d_in = torch.from_numpy(up).to(self.device)
+        d_out = torch.empty(nb_ref + nb_out + 4 * n * cap + 4 * n, dtype=torch.uint8, device=self.device)
+        p_in, p_out = d_in.data_ptr(), d_out.data_ptr()
+        rc = self.lib.qc_rules_apply(self.h, p_in, p_in + nb_rows, p_in + nb_rows + 4 * n, n, cap, float(min_conf),
+                                     float(max_area_pct), int(elongated_classes), float(overlap_threshold),
+                                     p_out, p_out + nb_ref, p_out + nb_ref + nb_out,
+                                     p_out + nb_ref + nb_out + 4 * n * cap, _stream(self.device))
+        self._check(rc, "qc_rules_apply")
+        host = d_out.cpu().numpy()
+        return {"refined": host[:nb_ref].view(RULES_REFINED_DTYPE).reshape(n, cap),
+                "rows": host[nb_ref:nb_ref + nb_out].view(RULES_OUT_DTYPE).reshape(n, cap),
+                "member": host[nb_ref + nb_out:nb_ref + nb_out + 4 * n * cap].view(np.int32).reshape(n, cap),
+                "count": host[nb_ref + nb_out + 4 * n * cap:].view(np.int32)}
 
     # -- K10 -------------------------------------------------------------------------------
     def jpeg_info(self, buf: np.ndarray) -> JpegInfo:

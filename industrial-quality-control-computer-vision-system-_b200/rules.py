@@ -380,3 +380,126 @@ class DetectionRules:
     def process(self, raw_detections: Sequence[Dict], segmentation_results: Dict, image_shape: Tuple) -> List[Dict]:
         refined = self._refine_detections(raw_detections, segmentation_results, image_shape)
         return self._validate_detections(self._merge_overlapping_detections(self._filter_detections(refined)), image_shape)
+
+
+# ---------------------------------------------------------------------------------------------------
+class DeviceDetectionRules(DetectionRules):
+    """The same chain with every number computed by K6 on the device (``qc_rules_apply``: refine, filter, cluster,
+    merge, validate for a whole batch in one launch); the host only packs the detections of the batch into one table
+    and turns the returned rows back into the reference's dictionaries.  Results are identical to
+    ``DetectionRules.process`` -- and through it to the reference's PostProcessor (tests/test_gpu_rules.py)."""
+
+    SEV_NAMES = {1: "minor", 2: "major", 3: "critical"}
+
+    def __init__(self, config: Optional[Dict] = None, device: int = 0):
+        super().__init__(config)
+        self.device = device
+
+    def process(self, raw_detections, segmentation_results, image_shape):
+        return self.process_many([(raw_detections, segmentation_results, image_shape)])[0]
+
+    def process_many(self, items) -> List[List[Dict]]:
+        """items: [(raw_detections, segmentation_results, image_shape)] -> the validated detection list of each."""
+        from . import ffi
+        n = len(items)
+        out: List[Optional[List[Dict]]] = [None] * n
+        cap = max([len(it[0]) for it in items] + [1])
+        rows = np.zeros((n, cap), ffi.RULES_ROW_DTYPE)
+        rows["ext"] = -1
+        count = np.zeros(n, np.int32)
+        shapes = np.ones((n, 2), np.int32)
+        class_ids: Dict[str, int] = {}
+        prepared = []
+        for a, (raw, seg, shape) in enumerate(items):
+            regions = {}
+            for r in (seg or {}).get("segmented_regions", []):
+                regions.setdefault(r.get("detection_id"), r)
+            ok = len(raw) > 0
+            exts = []
+            for i, det in enumerate(raw):
+                sev = SEVERITY_ORDER.get(det.get("severity", "minor"))
+                cid = class_ids.setdefault(det["class"], len(class_ids))
+                bb = det["bbox"]
+                if sev is None or cid >= 64 or bb["width"] != bb["x2"] - bb["x1"] or bb["height"] != bb["y2"] - bb["y1"]:
+                    ok = False                           # a table the kernel does not model: the host form below
+                    break
+                row = rows[a, i]
+                row["x1"], row["y1"], row["x2"], row["y2"] = bb["x1"], bb["y1"], bb["x2"], bb["y2"]
+                row["cls"], row["severity"] = cid, sev
+                row["conf"] = float(_conf_of(det)) if ("ensemble_confidence" in det or "confidence" in det) else 0.0
+                r = regions.get(i)
+                ext = None
+                if r:
+                    row["has_seg"] = 1
+                    row["seg_conf"] = r.get("confidence_score", 0.0)
+                    row["area_pixels"] = r.get("area_pixels", 0)
+                    row["area_pct"] = r.get("area_percentage", 0.0)
+                    row["compactness"] = r.get("compactness", 0.0)
+                    ext = self.mask_extent(r.get("mask"))
+                    if ext is not None:
+                        row["ext"] = [int(v) for v in ext]
+                exts.append(ext)
+            if not ok:
+                out[a] = super().process(raw, seg, shape) if raw else []
+                prepared.append(None)
+                continue
+            count[a] = len(raw)
+            shapes[a] = shape[0], shape[1]
+            prepared.append((regions, exts))
+        if not any(p is not None for p in prepared):
+            return out
+        elong = sum(1 << cid for name, cid in class_ids.items() if name in ("crack", "scratch"))
+        res = ffi.Context.current(self.device).rules_apply(
+            rows, count, shapes, self.quality_thresholds.get("confidence_threshold", 0.5),
+            self.quality_thresholds.get("area_threshold_percent", 50.0), elong, OVERLAP_THRESHOLD)
+        for a, (raw, seg, shape) in enumerate(items):
+            if prepared[a] is None:
+                continue
+            regions, exts = prepared[a]
+            refined = []
+            for i, det in enumerate(raw):                       # the dictionaries of _refine_detections (:111-184)
+                d = det.copy()
+                rf = res["refined"][a, i]
+                r = regions.get(i)
+                if r:
+                    d.update({"segmentation_confidence": r.get("confidence_score", 0.0), "area_pixels": r.get("area_pixels", 0),
+                              "area_percentage": r.get("area_percentage", 0.0), "perimeter": r.get("perimeter", 0.0),
+                              "compactness": r.get("compactness", 0.0), "contour_count": len(r.get("contours", [])),
+                              "has_segmentation": True})
+                    if exts[i] is not None:
+                        d["bbox"] = _bbox_dict(int(rf["x1"]), int(rf["y1"]), int(rf["x2"]), int(rf["y2"]))
+                else:
+                    d.update({"segmentation_confidence": 0.0, "area_pixels": int(rf["area_pixels"]), "area_percentage": 0.0,
+                              "perimeter": 0.0, "compactness": 0.0, "contour_count": 0, "has_segmentation": False})
+                d["final_severity"] = self.SEV_NAMES[int(rf["severity"])]
+                bb = d["bbox"]
+                d.update({"aspect_ratio": bb["width"] / max(bb["height"], 1), "bbox_area": bb["width"] * bb["height"],
+                          "normalized_position": {"x": bb["center_x"] / 1000, "y": bb["center_y"] / 1000}})
+                refined.append(d)
+            member = res["member"][a, :len(raw)]
+            final = []
+            for j in range(int(res["count"][a])):
+                o = res["rows"][a, j]
+                d = refined[int(o["base"])]
+                if o["merged_from"] > 1:                        # _merge_detection_cluster (:305-358)
+                    idx = np.nonzero(member == j)[0]
+                    confs = [_conf_of(refined[i]) if ("ensemble_confidence" in refined[i] or "confidence" in refined[i]) else 0
+                             for i in idx]
+                    d = d.copy()
+                    d["bbox"] = {}
+                    d["ensemble_confidence"] = np.float64(o["conf"])
+                    d["confidence"] = np.float64(o["conf"])
+                    d["final_severity"] = self.SEV_NAMES[int(o["severity"])]
+                    d["merged_from"] = int(o["merged_from"])
+                    d["original_confidences"] = confs
+                x1, y1, x2, y2 = int(o["x1"]), int(o["y1"]), int(o["x2"]), int(o["y2"])
+                d["bbox"].update(_bbox_dict(x1, y1, x2, y2))    # _validate_detections clamps in place (:376-386)
+                if o["merged_from"] > 1 or (o["flags"] & 1):
+                    d["area_pixels"] = int(o["area_pixels"])
+                if o["flags"] & 1:
+                    d["area_consistency_warning"] = True
+                d["validation_score"] = float(o["validation_score"])
+                if o["flags"] & 2:
+                    final.append(d)
+            out[a] = final
+        return out

@@ -85,3 +85,60 @@ def test_golden_cases_through_device_labels(qc):
                                torch.tensor([k], dtype=torch.int32).cuda()).cpu().numpy()[0]
         merged = r._merge_overlapping_detections(filtered, labels=lab)
         assert json.loads(json.dumps(jsonable(merged))) == gold[name]["merged"], name
+
+
+def _load_gold():
+    import gzip, json, os, sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, os.path.join(here, "golden"))
+    with gzip.open(os.path.join(here, "golden", "rules_golden.json.gz"), "rt") as f:
+        return json.load(f)
+
+
+def test_whole_chain_on_device_matches_reference_golden(qc):
+    """qc_rules_apply (refine -> filter -> merge -> validate in one launch) through DeviceDetectionRules == the
+    reference's PostProcessor output, every key and every float64 bit (inference/postprocess.py:64-81)."""
+    import json
+    from rules_cases import CASES, build_case, jsonable
+    from qcgraft.rules import DeviceDetectionRules
+    gold = _load_gold()
+    for name in sorted(CASES):
+        dets, seg, shape, cfg = build_case(**CASES[name])
+        out = DeviceDetectionRules(cfg).process(dets, seg, shape)
+        assert json.loads(json.dumps(jsonable(out))) == gold[name]["validated"], name
+    # all cases as ONE batch (different image shapes, thresholds of the first config): same rows per image
+    names = [n for n in sorted(CASES) if "thresholds" not in CASES[n]]
+    built = [build_case(**CASES[n]) for n in names]
+    outs = DeviceDetectionRules(built[0][3]).process_many([(d, s, sh) for d, s, sh, _ in built])
+    for n, o in zip(names, outs):
+        assert json.loads(json.dumps(jsonable(o))) == gold[n]["validated"], n
+
+
+def test_whole_chain_on_device_equals_host_tables_on_random_batches(qc):
+    """Seeded stress against the host form (itself pinned to the reference): up to 300 detections per image, big
+    clusters (np.mean's pairwise order beyond 8 and beyond 128 members), slivers, edge boxes, no-mask rows."""
+    import json
+    from rules_cases import build_case, jsonable
+    from qcgraft.rules import DetectionRules, DeviceDetectionRules
+    specs = [dict(seed=100 + i, k=int(k), shape=shape, cluster=c, seg_frac=sf, one_class=oc, slivers=sl, edges=ed)
+             for i, (k, shape, c, sf, oc, sl, ed) in enumerate([
+                 (300, (2400, 2400, 3), 0.0, 0.0, True, False, False),    # mostly isolated boxes of one class: one cluster of > 128
+                 (300, (640, 640, 3), 0.9, 0.5, False, False, False),
+                 (200, (1080, 1920, 3), 0.95, 0.7, True, False, True),
+                 (120, (333, 500, 3), 0.5, 0.4, False, True, True),
+                 (17, (64, 64, 3), 0.3, 1.0, False, False, True),
+                 (1, (640, 640, 3), 0.0, 0.0, False, False, False),
+                 (0, (640, 640, 3), 0.0, 0.0, False, False, False),
+                 (64, (640, 640, 3), 0.7, 0.9, False, True, False)])]
+    ref = []
+    for s in specs:
+        d, seg, shape, cfg = build_case(**s)
+        ref.append(json.loads(json.dumps(jsonable(DetectionRules(cfg).process(d, seg, shape)))))
+    built = [build_case(**s) for s in specs]
+    got = DeviceDetectionRules(built[0][3]).process_many([(d, s, sh) for d, s, sh, _ in built])
+    merged_sizes = []
+    for s, r, g in zip(specs, ref, got):
+        g = json.loads(json.dumps(jsonable(g)))
+        assert g == r, s
+        merged_sizes += [d.get("merged_from", 1) for d in r]
+    assert max(merged_sizes) > 128 and any(8 < m <= 128 for m in merged_sizes)

@@ -149,6 +149,20 @@ def test_threshold_method_large_regions(qc):
         _check_threshold(res, i, img, r, ["discoloration", "x"][i])
 
 
+def test_threshold_method_noise_rois_many_background_runs(qc):
+    """White-noise ROIs: tens of thousands of background runs with maze-like 4-connected paths.  The small ones go
+    through the run union-find of the flood, the 420x430 one has more runs than the CTA's node table holds and takes
+    the sweep fallback."""
+    rng = np.random.default_rng(12)
+    img = rng.integers(0, 256, (480, 480)).astype(np.uint8)
+    regs = [dict(img=0, x=10, y=20, w=420, h=430), dict(img=0, x=0, y=0, w=200, h=190), dict(img=0, x=100, y=50, w=97, h=301),
+            dict(img=0, x=300, y=300, w=33, h=31), dict(img=0, x=5, y=400, w=470, h=70)]
+    cls = ["discoloration", "x", "dent", "discoloration", "x"]
+    res = _run_threshold(qc, img, regs, cls)
+    for i, r in enumerate(regs):
+        _check_threshold(res, i, img, r, cls[i])
+
+
 def _run_adaptive(qc, img, regs, classes, max_comp=None):
     rr = [dict(r, polarity=0 if c in R.DARK_CLASSES else 1, min_area=20) for r, c in zip(regs, classes)]
     res = qc.segment(torch.from_numpy(img[None]).cuda(), rr, morph_iters=1, method=ffi.QC_SEG_REF_ADAPTIVE,
