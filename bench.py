@@ -224,7 +224,52 @@ def kernel_microbench(qc, peak, only=None):
         _mb_k6(qc, peak, rng, time_call, out)
     if want("k7"):
         _mb_k7(qc, peak, rng, time_call, out)
+    if want("k10"):
+        _mb_k10(qc, peak, rng, time_call, out)
     return out
+
+
+def _mb_k10(qc, peak, rng, time_call, out):
+    """K10: 64 baseline JPEG uploads (640x640, 4:2:0, quality 90) -> packed BGR frames on the device, the
+    cv2.imdecode of inference/detector.py:229 for a batch; next to it cv2.imdecode itself on one host core."""
+    import cv2
+    from qcgraft import synth
+    frames = synth.make_frames(4000, BATCH)
+    streams = [cv2.imencode(".jpg", np.ascontiguousarray(f[..., ::-1]), [cv2.IMWRITE_JPEG_QUALITY, 90])[1] for f in frames]
+    infos = [qc.jpeg_info(b) for b in streams]
+    got = qc.jpeg_decode(streams, infos=infos)
+    ok = all(np.array_equal(got[i].cpu().numpy(), cv2.imdecode(streams[i], cv2.IMREAD_COLOR)) for i in (0, BATCH // 2, BATCH - 1))
+    t0 = time.perf_counter()
+    for b in streams[:16]:
+        cv2.imdecode(b, cv2.IMREAD_COLOR)
+    cpu_ms_per_image = (time.perf_counter() - t0) * 1000 / 16
+    walls = []
+    for _ in range(5):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        qc.jpeg_decode(streams, infos=infos)
+        torch.cuda.synchronize()
+        walls.append((time.perf_counter() - t0) * 1000)
+    qc.profile(True)
+    qc.jpeg_decode(streams, infos=infos)
+    torch.cuda.synchronize()
+    kern = {}
+    for name, ms in qc.profile_collect():
+        kern[name] = kern.get(name, 0.0) + ms
+    qc.profile(False)
+    comp = sum(int(b.size) for b in streams)
+    blocks = sum(int(i.blocks) for i in infos)
+    dev_bytes = blocks * 64 * 2 + blocks * 64 * 2 + BATCH * IMGSZ * IMGSZ * 3      # coefficients in, planes out+in, frames out
+    dev_ms = sum(v for k, v in kern.items() if k != "k10_h2d_copy")
+    out["k10_jpeg_decode_64x640"] = {
+        "images": BATCH, "compressed_bytes": comp, "bit_exact_vs_cv2": bool(ok),
+        "ms_call_wall": sorted(walls)[len(walls) // 2], "images_per_s": BATCH / (sorted(walls)[len(walls) // 2] / 1000),
+        "host_threads": max(1, min(BATCH, os.cpu_count() or 1, 32)),
+        "device_kernels_ms": kern, "bytes": dev_bytes, "ms": dev_ms, "gbs": dev_bytes / dev_ms / 1e6 if dev_ms else None,
+        "frac": dev_bytes / dev_ms / 1e6 / peak if dev_ms else None,
+        "cv2_imdecode_ms_per_image_one_core": cpu_ms_per_image,
+        "note": "wall time of the whole call: Huffman stage on the host threads + one H2D copy of the coefficient blocks + "
+                "k10_idct + k10_color; gbs/frac are the two kernels alone (their first event also spans the H2D copy)"}
 
 
 def _mb_k1(qc, peak, rng, time_call, out):
@@ -311,6 +356,27 @@ def _mb_k6(qc, peak, rng, time_call, out):
     qc.rules_cluster(b, c, cnt)
     med, best = time_call(lambda i: qc.rules_cluster(b, c, cnt), 8)
     by = n * cap * (16 + 4 + 4 + 4)
+    # the whole chain (refine -> filter -> cluster -> merge -> validate) on the same boxes, one launch
+    from qcgraft import ffi as _ffi
+    rows = np.zeros((n, cap), _ffi.RULES_ROW_DTYPE)
+    rows["x1"], rows["y1"], rows["x2"], rows["y2"] = box[..., 0], box[..., 1], box[..., 2], box[..., 3]
+    rows["cls"] = c.cpu().numpy()
+    rows["severity"] = rng.integers(1, 4, (n, cap))
+    rows["conf"] = rng.uniform(0.4, 0.99, (n, cap))
+    rows["ext"] = -1
+    shp = np.tile(np.array([[IMGSZ, IMGSZ]], np.int32), (n, 1))
+    cn = np.full(n, cap, np.int32)
+    qc.rules_apply(rows, cn, shp)
+    t0 = time.perf_counter()
+    for _ in range(5):
+        qc.rules_apply(rows, cn, shp)
+    wall = (time.perf_counter() - t0) * 1000 / 5
+    qc.profile(True)
+    qc.rules_apply(rows, cn, shp)
+    chain_ms = sum(ms for name, ms in qc.profile_collect() if name == "k6_chain")
+    qc.profile(False)
+    out["k6_rules_chain_64x300"] = {"ms": chain_ms, "ms_call_wall_with_copies": wall, "bytes": n * cap * (88 + 32 + 56 + 4),
+                                    "note": "one CTA per image, float64 rule arithmetic; latency-bound"}
     out["k6_rules_cluster_64x300"] = {"bytes": by, "ms": med, "gbs": by / med / 1e6, "frac": by / med / 1e6 / peak,
                                       "note": "quadratic pair test + shared-memory union-find per image: latency-bound, "
                                               "the bytes are negligible"}

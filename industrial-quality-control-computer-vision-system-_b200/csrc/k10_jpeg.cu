@@ -336,8 +336,7 @@ int entropy_decode(const uint8_t* d, size_t len, const Header& H, const Geometry
                                 k += 16;
                                 continue;
                             }
-                            k += r;
-                            br.fill();
+                            k += r;                    // fill() left >= 33 bits: 16 for the code, 15 for the value
                             blk[k10_natural[k]] = (int16_t)receive_extend(br, s);
                             ++k;
                         }
@@ -657,7 +656,9 @@ extern "C" int qc_jpeg_decode(qc_ctx* ctx, const uint8_t* const* jpegs, const si
     }
     // ---- device: one upload, IDCT, colour ----------------------------------------------------------
     uint8_t* ws = static_cast<uint8_t*>(workspace);
+    QC_ENTER(ctx, stream);                 // profiling boundary: the host stage above is not device time
     QC_CUDA(ctx, cudaMemcpyAsync(ws, hs, L.off_coef + (size_t)cb * sizeof(int16_t), cudaMemcpyHostToDevice, st));
+    if (ctx->prof) qc_prof_mark(ctx, "k10_h2d_copy", st);      // listed next to the kernels; not a launch
     const K10Img* dimg = reinterpret_cast<const K10Img*>(ws + L.off_img);
     {
         dim3 grid((unsigned)((max_blocks + K10_IDCT_THREADS - 1) / K10_IDCT_THREADS), (unsigned)(3 * n));

@@ -91,14 +91,20 @@ void axis_coeffs(int in_size, int out_size, int ksize, int* bounds, int* kk) {
 // staged row: 3*w data bytes + 16 B alignment slack + the words the zero-coefficient taps of the last group may reach
 __host__ __device__ inline int k3b_row_buf(int src_w, int ng) { return (src_w * 3 + 32 + 12 * ng + 15) & ~15; }
 
+// byte `shift/8` of four coefficients, packed for dp4a
+__device__ __forceinline__ unsigned k3b_pack(const int (&k)[4], int shift) {
+    return ((unsigned)(k[0] >> shift) & 255u) | (((unsigned)(k[1] >> shift) & 255u) << 8) |
+           (((unsigned)(k[2] >> shift) & 255u) << 16) | (((unsigned)(k[3] >> shift) & 255u) << 24);
+}
+
 template <typename OutT, int NG>              // NG: 4-tap groups per output column (0 = runtime, coefficients in smem)
 __global__ void __launch_bounds__(K3B_THREADS)
 k3b_resize(const uint8_t* __restrict__ imgs, long long img_stride, int row_stride, const int* __restrict__ tab,
-           int swap_rb, const float* __restrict__ norm, OutT* __restrict__ dst, int stage_rows, int ng_rt) {
+           int swap_rb, const float* __restrict__ norm, OutT* __restrict__ dst, int stage_rows, int ng_rt,
+           int band_rows, int max_src_rows) {
     extern __shared__ __align__(16) uint8_t k3b_sm[];
     __shared__ float s_lut[3][256];
     const int src_w = tab[1], dst_h = tab[2], dst_w = tab[3], kx = tab[4], ky = tab[5];
-    const int band_rows = tab[6], max_src_rows = tab[7];
     const int* __restrict__ bx = tab + K3B_HDR;
     const int* __restrict__ kkx = bx + dst_w * 2;
     const int* __restrict__ by = kkx + dst_w * kx;
@@ -119,9 +125,15 @@ k3b_resize(const uint8_t* __restrict__ imgs, long long img_stride, int row_strid
         s_lut[c][v] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)v, norm[c * 3 + 0]), norm[c * 3 + 1]), norm[c * 3 + 2]);
     }
     if (NG == 0) {
-        for (int i = tid; i < dst_w * ng * 4; i += K3B_THREADS) {
-            const int ox = i / (ng * 4), x = i - ox * ng * 4;
-            kx_s[i] = x < kx ? __ldg(kkx + ox * kx + x) : 0;
+        // per (column, 4-tap group): the three byte planes of the four coefficients (see below), one pad word
+        for (int i = tid; i < dst_w * ng; i += K3B_THREADS) {
+            const int ox = i / ng, g = i - ox * ng;
+            int k[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) k[t] = 4 * g + t < kx ? __ldg(kkx + ox * kx + 4 * g + t) : 0;
+            uint4 pk;
+            pk.x = k3b_pack(k, 0); pk.y = k3b_pack(k, 8); pk.z = k3b_pack(k, 16); pk.w = 0u;
+            reinterpret_cast<uint4*>(kx_s)[i] = pk;
         }
     }
     // source rows this band taps (bounds are monotone in the output index)
@@ -167,17 +179,26 @@ k3b_resize(const uint8_t* __restrict__ imgs, long long img_stride, int row_strid
         __syncthreads();                                   // stage sti landed (and tables / LUT written)
         for (int ox = tid; ox < dst_w; ox += K3B_THREADS) {
             const int x0 = bx[ox * 2];
-            int kreg[NG ? NG * 4 : 1];
+            // Coefficients are non-negative 22-bit integers: k = b0 + 256 b1 + 65536 b2.  With the four taps' bytes of one
+            // plane packed in a word, a channel's four products are ONE dp4a per plane (3 per channel and group
+            // instead of 4 multiply-adds plus the byte extracts); the planes are recombined by shifts at the end --
+            // the same integer sum, in a different order.
+            unsigned kb[NG ? NG : 1][3];
             if (NG) {
 #pragma unroll
-                for (int x = 0; x < NG * 4; ++x) kreg[x] = x < kx ? __ldg(kkx + ox * kx + x) : 0;
+                for (int g = 0; g < NG; ++g) {
+                    int k[4];
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) k[t] = 4 * g + t < kx ? __ldg(kkx + ox * kx + 4 * g + t) : 0;
+                    kb[g][0] = k3b_pack(k, 0); kb[g][1] = k3b_pack(k, 8); kb[g][2] = k3b_pack(k, 16);
+                }
             }
             for (int rr = 0; rr < nr; ++rr) {
                 const uint8_t* p = ibase + (long long)(sy0 + r0 + rr) * row_stride;
                 const int s = (int)(reinterpret_cast<uintptr_t>(p) & 15) + x0 * 3;      // window start in the staged row
                 const unsigned* wp = reinterpret_cast<const unsigned*>(cur + (size_t)rr * row_buf) + (s >> 2);
                 const unsigned sh = (unsigned)(s & 3) * 8u;
-                int a0 = 1 << (K3B_PREC - 1), a1 = a0, a2 = a0;
+                unsigned acc[3][3] = {{0u, 0u, 0u}, {0u, 0u, 0u}, {0u, 0u, 0u}};        // [channel][byte plane]
                 unsigned wprev = wp[0];
 #pragma unroll
                 for (int g = 0; g < (NG ? NG : 1); ++g) {
@@ -186,17 +207,24 @@ k3b_resize(const uint8_t* __restrict__ imgs, long long img_stride, int row_strid
                         const unsigned A0 = __funnelshift_r(wprev, w1, sh), A1 = __funnelshift_r(w1, w2, sh),
                                        A2 = __funnelshift_r(w2, w3, sh);
                         wprev = w3;
-                        int k0, k1, k2, k3;
-                        if (NG) { k0 = kreg[4 * g]; k1 = kreg[4 * g + 1]; k2 = kreg[4 * g + 2]; k3 = kreg[4 * g + 3]; }
+                        unsigned k0, k1, k2;
+                        if (NG) { k0 = kb[g][0]; k1 = kb[g][1]; k2 = kb[g][2]; }
                         else {
-                            const int4 kv = *reinterpret_cast<const int4*>(kx_s + (ox * ng + gg) * 4);
-                            k0 = kv.x; k1 = kv.y; k2 = kv.z; k3 = kv.w;
+                            const uint4 kv = *reinterpret_cast<const uint4*>(kx_s + (ox * ng + gg) * 4);
+                            k0 = kv.x; k1 = kv.y; k2 = kv.z;
                         }
-                        a0 += (int)(A0 & 255u) * k0 + (int)(A0 >> 24) * k1 + (int)((A1 >> 16) & 255u) * k2 + (int)((A2 >> 8) & 255u) * k3;
-                        a1 += (int)((A0 >> 8) & 255u) * k0 + (int)(A1 & 255u) * k1 + (int)(A1 >> 24) * k2 + (int)((A2 >> 16) & 255u) * k3;
-                        a2 += (int)((A0 >> 16) & 255u) * k0 + (int)((A1 >> 8) & 255u) * k1 + (int)(A2 & 255u) * k2 + (int)(A2 >> 24) * k3;
+                        // 12 bytes = 4 RGB pixels: channel c of pixel t is byte 3t + c
+                        const unsigned c0 = __byte_perm(__byte_perm(A0, A1, 0x0630), A2, 0x5210);   // bytes 0,3,6,9
+                        const unsigned c1 = __byte_perm(__byte_perm(A0, A1, 0x0741), A2, 0x6210);   // bytes 1,4,7,10
+                        const unsigned c2 = __byte_perm(__byte_perm(A0, A1, 0x0052), A2, 0x7410);   // bytes 2,5,8,11
+                        acc[0][0] = __dp4a(c0, k0, acc[0][0]); acc[0][1] = __dp4a(c0, k1, acc[0][1]); acc[0][2] = __dp4a(c0, k2, acc[0][2]);
+                        acc[1][0] = __dp4a(c1, k0, acc[1][0]); acc[1][1] = __dp4a(c1, k1, acc[1][1]); acc[1][2] = __dp4a(c1, k2, acc[1][2]);
+                        acc[2][0] = __dp4a(c2, k0, acc[2][0]); acc[2][1] = __dp4a(c2, k1, acc[2][1]); acc[2][2] = __dp4a(c2, k2, acc[2][2]);
                     }
                 }
+                const int a0 = (1 << (K3B_PREC - 1)) + (int)(acc[0][0] + (acc[0][1] << 8) + (acc[0][2] << 16));
+                const int a1 = (1 << (K3B_PREC - 1)) + (int)(acc[1][0] + (acc[1][1] << 8) + (acc[1][2] << 16));
+                const int a2 = (1 << (K3B_PREC - 1)) + (int)(acc[2][0] + (acc[2][1] << 8) + (acc[2][2] << 16));
                 uint8_t* t = tile + (size_t)(r0 + rr) * 3 * pitch + ox;
                 t[0] = (uint8_t)min(max(a0 >> K3B_PREC, 0), 255);
                 t[pitch] = (uint8_t)min(max(a1 >> K3B_PREC, 0), 255);
@@ -291,27 +319,48 @@ extern "C" int qc_pil_resize(qc_ctx* ctx, const uint8_t* imgs, int n, int h, int
         QC_FAIL(ctx, QC_ERR_INVALID, "qc_pil_resize: bad argument");
     if (host_tables[0] != h || host_tables[1] != w) QC_FAIL(ctx, QC_ERR_INVALID, "qc_pil_resize: tables are for %dx%d", host_tables[0], host_tables[1]);
     if (n > 65535) QC_FAIL(ctx, QC_ERR_UNSUPPORTED, "qc_pil_resize: n > 65535 (split the call)");
-    const int dst_h = host_tables[2], dst_w = host_tables[3], kx = host_tables[4], band = host_tables[6],
-              max_rows = host_tables[7];
+    const int dst_h = host_tables[2], dst_w = host_tables[3], kx = host_tables[4], ky = host_tables[5];
     const int pitch = (dst_w + 3) & ~3;
     const int ng = (kx + 3) / 4;
     const int row_buf = k3b_row_buf(w, ng);
-    const size_t tile_bytes = ((size_t)max_rows * 3 * pitch + 15) & ~(size_t)15;
     const size_t coef_bytes = ng <= 2 ? 0 : (size_t)dst_w * ng * 16;
-    // rows per staging buffer (two buffers): 4 unless the frame is so wide that the budget only allows fewer
-    int stage_rows = 4;
-    while (stage_rows > 1 && tile_bytes + (size_t)2 * stage_rows * row_buf + coef_bytes + 4096 > (size_t)ctx->max_smem_optin / 2)
-        stage_rows >>= 1;
-    const size_t smem = tile_bytes + (size_t)2 * stage_rows * row_buf + coef_bytes;
-    if ((long long)smem + 4096 > ctx->max_smem_optin)
-        QC_FAIL(ctx, QC_ERR_UNSUPPORTED, "qc_pil_resize: %dx%d -> %dx%d needs %zu B of shared memory", h, w, dst_h, dst_w, smem);
+    // Output rows per CTA, chosen per launch: a band costs its tapped source rows (horizontal pass) plus its own rows
+    // (vertical pass), and the grid should fill whole waves of the CTAs that fit an SM at that band's tile size.
+    Tables tl = layout(h, w, dst_h, dst_w);
+    const int* by = host_tables + tl.off_by;
+    int band = 0, max_rows = 0, stage_rows = 4;
+    size_t smem = 0;
+    double best_cost = 0.0;
+    (void)ky;
+    for (int b = 4; b <= std::min(dst_h, 48); ++b) {
+        int mr = 0;
+        for (int o0 = 0; o0 < dst_h; o0 += b) {
+            const int o1 = std::min(o0 + b, dst_h) - 1;
+            mr = std::max(mr, by[o1 * 2] + by[o1 * 2 + 1] - by[o0 * 2]);
+        }
+        const size_t tile_b = ((size_t)mr * 3 * pitch + 15) & ~(size_t)15;
+        int sr = 4;
+        while (sr > 1 && tile_b + (size_t)2 * sr * row_buf + coef_bytes + 4096 > (size_t)ctx->max_smem_optin / 2) sr >>= 1;
+        const size_t sm = tile_b + (size_t)2 * sr * row_buf + coef_bytes;
+        if ((long long)sm + 4096 > ctx->max_smem_optin) continue;
+        const int occ = (int)std::max<size_t>(1, std::min<size_t>(2048 / K3B_THREADS, (size_t)(228 * 1024) / (sm + 1024)));
+        const long long ctas = (long long)((dst_h + b - 1) / b) * n;
+        const long long waves = (ctas + (long long)occ * ctx->sm_count - 1) / ((long long)occ * ctx->sm_count);
+        // per-CTA work ~ source rows filtered horizontally + a third of that per output row of the vertical pass
+        // (the SM is issue-bound: CTAs resident together share it, so a wave takes occ times one CTA's work; below
+        // three resident CTAs the staging latency is no longer hidden)
+        const double cost = (double)waves * occ * ((double)mr + 0.35 * b + 6.0) * (occ >= 3 ? 1.0 : 1.3);
+        if (band == 0 || cost < best_cost) { band = b; max_rows = mr; stage_rows = sr; smem = sm; best_cost = cost; }
+    }
+    if (band == 0)
+        QC_FAIL(ctx, QC_ERR_UNSUPPORTED, "qc_pil_resize: %dx%d -> %dx%d does not fit shared memory", h, w, dst_h, dst_w);
     cudaStream_t st = (cudaStream_t)stream;
     dim3 grid((unsigned)((dst_h + band - 1) / band), (unsigned)n);
 #define K3B_LAUNCH(T, G)                                                                                          \
     do {                                                                                                          \
         if (int rc = qc_prepare(ctx, k3b_resize<T, G>, (int)smem, K3B_THREADS, nullptr)) return rc;               \
         k3b_resize<T, G><<<grid, K3B_THREADS, smem, st>>>(imgs, img_stride, row_stride, dev_tables, swap_rb, norm, \
-                                                          (T*)dst, stage_rows, ng);                               \
+                                                          (T*)dst, stage_rows, ng, band, max_rows);               \
     } while (0)
 #define K3B_LAUNCH_NG(T)                          \
     do {                                          \
