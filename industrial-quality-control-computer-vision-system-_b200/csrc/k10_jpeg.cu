@@ -441,37 +441,60 @@ k10_idct(const K10Img* __restrict__ imgs, const uint16_t* __restrict__ quant, co
     }
 }
 
-// jdsample.c: value of the upsampled chroma plane at (oy, ox)
-__device__ __forceinline__ int k10_chroma(const uint8_t* __restrict__ pl, int pitch, int dw, int dh, int mode, int oy, int ox) {
-    if (mode == QC_JPEG_444) return pl[(long long)oy * pitch + ox];
-    const int c = ox >> 1;
-    if (mode == QC_JPEG_422) {
-        const uint8_t* row = pl + (long long)oy * pitch;
-        if (dw <= 2) return row[c];                                              // h2v1_upsample (replication)
-        const int cur = row[c];
-        if (ox & 1) return c == dw - 1 ? cur : (3 * cur + row[c + 1] + 2) >> 2;   // h2v1_fancy_upsample
-        return c == 0 ? cur : (3 * cur + row[c - 1] + 1) >> 2;
+// jdsample.c: the upsampled chroma values of 8 consecutive pixels x0..x0+7 (x0 a multiple of 8) of row oy.  The four
+// chroma samples under them come in as one aligned word per contributing row, the two neighbours as single bytes.
+__device__ __forceinline__ void k10_chroma8(const uint8_t* __restrict__ pl, int pitch, int dw, int dh, int mode, int oy,
+                                            int x0, int (&out)[8]) {
+    if (mode == QC_JPEG_444) {
+        const uint2 v = *reinterpret_cast<const uint2*>(pl + (long long)oy * pitch + x0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { out[j] = (v.x >> (8 * j)) & 255u; out[4 + j] = (v.y >> (8 * j)) & 255u; }
+        return;
     }
-    const int r0 = oy >> 1;
-    if (dw <= 2) return pl[(long long)r0 * pitch + c];                           // h2v2_upsample (replication)
-    // h2v2_fancy_upsample: nearer row weighs 3, the other 1; context rows replicate the first / last real row
-    const int r1 = (oy & 1) ? min(r0 + 1, dh - 1) : max(r0 - 1, 0);
+    const int c0 = x0 >> 1;                                   // a multiple of 4: aligned in the MCU-padded plane
+    const int r0 = mode == QC_JPEG_422 ? oy : oy >> 1;
     const uint8_t* a = pl + (long long)r0 * pitch;
-    const uint8_t* b = pl + (long long)r1 * pitch;
-    const int cur = 3 * a[c] + b[c];
-    if (ox & 1) {
-        if (c == dw - 1) return (cur * 4 + 7) >> 4;
-        return (cur * 3 + 3 * a[c + 1] + b[c + 1] + 7) >> 4;
+    const unsigned wa = *reinterpret_cast<const unsigned*>(a + c0);
+    if (dw <= 2) {                                            // h2v1_upsample / h2v2_upsample: plain replication
+#pragma unroll
+        for (int j = 0; j < 8; ++j) out[j] = (wa >> (8 * (j >> 1))) & 255u;
+        return;
     }
-    if (c == 0) return (cur * 4 + 8) >> 4;
-    return (cur * 3 + 3 * a[c - 1] + b[c - 1] + 8) >> 4;
+    const int cl = max(c0 - 1, 0), cr = min(c0 + 4, dw - 1);  // neighbours (clamped: the edge formulas ignore them)
+    int v[6];
+    if (mode == QC_JPEG_422) {                                // h2v1_fancy_upsample on the samples themselves
+        v[0] = a[cl]; v[5] = a[cr];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[1 + j] = (wa >> (8 * j)) & 255u;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int c = c0 + j, cur = v[1 + j];
+            out[2 * j] = c == 0 ? cur : (3 * cur + v[j] + 1) >> 2;
+            out[2 * j + 1] = c >= dw - 1 ? cur : (3 * cur + v[2 + j] + 2) >> 2;
+        }
+        return;
+    }
+    // h2v2_fancy_upsample: column sums 3*near + far of the two contributing rows (context rows replicate the first /
+    // last real row), then the same 3:1 blend horizontally with roundings 8 and 7
+    const int r1 = (oy & 1) ? min(r0 + 1, dh - 1) : max(r0 - 1, 0);
+    const uint8_t* b = pl + (long long)r1 * pitch;
+    const unsigned wb = *reinterpret_cast<const unsigned*>(b + c0);
+    v[0] = 3 * a[cl] + b[cl]; v[5] = 3 * a[cr] + b[cr];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[1 + j] = 3 * (int)((wa >> (8 * j)) & 255u) + (int)((wb >> (8 * j)) & 255u);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int c = c0 + j, cur = v[1 + j];
+        out[2 * j] = c == 0 ? (cur * 4 + 8) >> 4 : (cur * 3 + v[j] + 8) >> 4;
+        out[2 * j + 1] = c >= dw - 1 ? (cur * 4 + 7) >> 4 : (cur * 3 + v[2 + j] + 7) >> 4;
+    }
 }
 
-// upsample + jdcolor.c ycc_rgb_convert (+ gray_rgb_convert), 4 pixels = 3 words per thread
+// upsample + jdcolor.c ycc_rgb_convert (+ gray_rgb_convert), 8 pixels = 6 words per thread
 __global__ void __launch_bounds__(K10_COLOR_THREADS)
 k10_color(const K10Img* __restrict__ imgs, const uint8_t* __restrict__ planes, uint8_t* __restrict__ dst, int rgb) {
     const K10Img& I = imgs[blockIdx.y];
-    const int wq = (I.w + 3) >> 2;
+    const int wq = (I.w + 7) >> 3;
     const long long items = (long long)I.h * wq;
     const int p0 = I.bw[0] * 8, p1 = I.nc == 3 ? I.bw[1] * 8 : 0;
     const uint8_t* Y = planes + I.plane_off[0];
@@ -479,33 +502,36 @@ k10_color(const K10Img* __restrict__ imgs, const uint8_t* __restrict__ planes, u
     const uint8_t* Cr = planes + I.plane_off[2];
     for (long long it = (long long)blockIdx.x * K10_COLOR_THREADS + threadIdx.x; it < items;
          it += (long long)gridDim.x * K10_COLOR_THREADS) {
-        const int y = (int)(it / wq), x0 = (int)(it - (long long)y * wq) * 4;
-        const unsigned yw = *reinterpret_cast<const unsigned*>(Y + (long long)y * p0 + x0);   // plane pitch is a multiple of 8
-        uint8_t px[12];
+        const int y = (int)(it / wq), x0 = (int)(it - (long long)y * wq) * 8;
+        const uint2 yw = *reinterpret_cast<const uint2*>(Y + (long long)y * p0 + x0);       // plane pitch is a multiple of 8
+        int cb[8], cr[8];
+        if (I.nc == 3) {
+            k10_chroma8(Cb, p1, I.dw, I.dh, I.mode, y, x0, cb);
+            k10_chroma8(Cr, p1, I.dw, I.dh, I.mode, y, x0, cr);
+        }
+        unsigned px[6] = {0u, 0u, 0u, 0u, 0u, 0u};
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int x = min(x0 + j, I.w - 1);
-            const int yy = (int)((yw >> (8 * (x - x0))) & 255u);
+        for (int j = 0; j < 8; ++j) {
+            const int yy = (int)(((j < 4 ? yw.x : yw.y) >> (8 * (j & 3))) & 255u);
             int r = yy, g = yy, b = yy;
             if (I.nc == 3) {
-                const int cb = k10_chroma(Cb, p1, I.dw, I.dh, I.mode, y, x) - 128;
-                const int cr = k10_chroma(Cr, p1, I.dw, I.dh, I.mode, y, x) - 128;
-                r = yy + ((91881 * cr + 32768) >> 16);
-                b = yy + ((116130 * cb + 32768) >> 16);
-                g = yy + ((-22554 * cb + 32768 - 46802 * cr) >> 16);
-                r = min(max(r, 0), 255); g = min(max(g, 0), 255); b = min(max(b, 0), 255);
+                const int u = cb[j] - 128, v = cr[j] - 128;
+                r = min(max(yy + ((91881 * v + 32768) >> 16), 0), 255);
+                b = min(max(yy + ((116130 * u + 32768) >> 16), 0), 255);
+                g = min(max(yy + ((-22554 * u + 32768 - 46802 * v) >> 16), 0), 255);
             }
-            px[3 * j] = (uint8_t)(rgb ? r : b); px[3 * j + 1] = (uint8_t)g; px[3 * j + 2] = (uint8_t)(rgb ? b : r);
+            const unsigned c3[3] = {(unsigned)(rgb ? r : b), (unsigned)g, (unsigned)(rgb ? b : r)};
+#pragma unroll
+            for (int c = 0; c < 3; ++c) px[(3 * j + c) >> 2] |= c3[c] << (8 * ((3 * j + c) & 3));
         }
         uint8_t* o = dst + I.dst_off + (long long)y * I.dst_stride + 3ll * x0;
-        if (x0 + 4 <= I.w && ((reinterpret_cast<uintptr_t>(o) & 3) == 0)) {
+        if (x0 + 8 <= I.w && ((reinterpret_cast<uintptr_t>(o) & 3) == 0)) {
             unsigned* o4 = reinterpret_cast<unsigned*>(o);
-            o4[0] = px[0] | (px[1] << 8) | (px[2] << 16) | ((unsigned)px[3] << 24);
-            o4[1] = px[4] | (px[5] << 8) | (px[6] << 16) | ((unsigned)px[7] << 24);
-            o4[2] = px[8] | (px[9] << 8) | (px[10] << 16) | ((unsigned)px[11] << 24);
+#pragma unroll
+            for (int k = 0; k < 6; ++k) o4[k] = px[k];
         } else {
-            const int nv = min(4, I.w - x0) * 3;
-            for (int j = 0; j < nv; ++j) o[j] = px[j];
+            const int nv = min(8, I.w - x0) * 3;
+            for (int j = 0; j < nv; ++j) o[j] = (uint8_t)(px[j >> 2] >> (8 * (j & 3)));
         }
     }
 }
@@ -627,38 +653,50 @@ extern "C" int qc_jpeg_decode(qc_ctx* ctx, const uint8_t* const* jpegs, const si
         const int hm = H.nc == 3 ? H.hs[0] : 1, vm = H.nc == 3 ? H.vs[0] : 1;
         I.dw = (H.w + hm - 1) / hm; I.dh = (H.h + vm - 1) / vm;
         I.dst_stride = dst_row_strides[i]; I.dst_off = dst_offsets[i];
-        max_items = std::max(max_items, (long long)H.h * ((H.w + 3) / 4));
+        max_items = std::max(max_items, (long long)H.h * ((H.w + 7) / 8));
     }
-    // ---- host: entropy decode, one image per task ------------------------------------------------
+    // ---- host: entropy decode, one image per task; every finished image's coefficient blocks are sent to the device at
+    // once (from the thread that decoded it), so the copies overlap the Huffman work of the other images ----------------
+    uint8_t* ws = static_cast<uint8_t*>(workspace);
+    QC_ENTER(ctx, stream);
+    QC_CUDA(ctx, cudaMemcpyAsync(ws, hs, L.off_coef, cudaMemcpyHostToDevice, st));          // image table + quantisers
     std::atomic<int> next{0}, failed{-1};
     std::vector<char> msgs((size_t)n * 128, 0);
     std::vector<int> rcs((size_t)n, 0);
-    auto work = [&]() {
+    const int device = ctx->device;
+    auto work = [&](bool set_device) {
+        if (set_device) cudaSetDevice(device);
         for (;;) {
             const int i = next.fetch_add(1);
             if (i >= n) break;
             rcs[i] = entropy_decode(jpegs[i], lens[i], hdr[i], geo[i], hcoef + coef_base[i], &msgs[(size_t)i * 128], 128);
+            if (rcs[i] == QC_OK) {
+                const size_t off = L.off_coef + (size_t)coef_base[i] * sizeof(int16_t);
+                const cudaError_t e = cudaMemcpyAsync(ws + off, hs + off, (size_t)geo[i].blocks * 64 * sizeof(int16_t),
+                                                      cudaMemcpyHostToDevice, st);
+                if (e != cudaSuccess) {
+                    rcs[i] = QC_ERR_CUDA;
+                    snprintf(&msgs[(size_t)i * 128], 128, "cudaMemcpyAsync: %s", cudaGetErrorString(e));
+                }
+            }
             if (rcs[i] != QC_OK) { int e = -1; failed.compare_exchange_strong(e, i); }
         }
     };
     const int nt = std::max(1, std::min(host_threads > 0 ? host_threads : 1, n));
-    if (nt == 1) work();
+    if (nt == 1) work(false);
     else {
         std::vector<std::thread> th;
         th.reserve((size_t)nt - 1);
-        for (int t = 1; t < nt; ++t) th.emplace_back(work);
-        work();
+        for (int t = 1; t < nt; ++t) th.emplace_back(work, true);
+        work(false);
         for (auto& t : th) t.join();
     }
     if (failed.load() >= 0) {
         const int i = failed.load();
         QC_FAIL(ctx, rcs[i], "qc_jpeg_decode: image %d: %s", i, &msgs[(size_t)i * 128]);
     }
-    // ---- device: one upload, IDCT, colour ----------------------------------------------------------
-    uint8_t* ws = static_cast<uint8_t*>(workspace);
-    QC_ENTER(ctx, stream);                 // profiling boundary: the host stage above is not device time
-    QC_CUDA(ctx, cudaMemcpyAsync(ws, hs, L.off_coef + (size_t)cb * sizeof(int16_t), cudaMemcpyHostToDevice, st));
-    if (ctx->prof) qc_prof_mark(ctx, "k10_h2d_copy", st);      // listed next to the kernels; not a launch
+    // ---- device: IDCT, colour (the stream already holds every copy) ---------------------------------
+    QC_ENTER(ctx, stream);                 // profiling boundary: the host stage above is not kernel time
     const K10Img* dimg = reinterpret_cast<const K10Img*>(ws + L.off_img);
     {
         dim3 grid((unsigned)((max_blocks + K10_IDCT_THREADS - 1) / K10_IDCT_THREADS), (unsigned)(3 * n));

@@ -164,6 +164,21 @@ k3b_resize(const uint8_t* __restrict__ imgs, long long img_stride, int row_strid
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
+    // Coefficients are non-negative 22-bit integers: k = b0 + 256 b1 + 65536 b2.  With the four taps' bytes of one
+    // plane packed in a word, a channel's four products are ONE dp4a per plane (3 per channel and group instead of 4
+    // multiply-adds plus the byte extracts); the planes are recombined by shifts at the end -- the same integer sum, in
+    // a different order.  A thread keeps the packed planes of its output column for the whole band.
+    unsigned kb[NG ? NG : 1][3];
+    auto load_kb = [&](int ox) {
+#pragma unroll
+        for (int g = 0; g < (NG ? NG : 1); ++g) {
+            int k[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) k[t] = (ox < dst_w && 4 * g + t < kx) ? __ldg(kkx + ox * kx + 4 * g + t) : 0;
+            kb[g][0] = k3b_pack(k, 0); kb[g][1] = k3b_pack(k, 8); kb[g][2] = k3b_pack(k, 16);
+        }
+    };
+    if (NG) load_kb(tid);
     const int nstage = (nsrc + stage_rows - 1) / stage_rows;
     issue_stage(0, stage);
     for (int sti = 0; sti < nstage; ++sti) {
@@ -179,20 +194,7 @@ k3b_resize(const uint8_t* __restrict__ imgs, long long img_stride, int row_strid
         __syncthreads();                                   // stage sti landed (and tables / LUT written)
         for (int ox = tid; ox < dst_w; ox += K3B_THREADS) {
             const int x0 = bx[ox * 2];
-            // Coefficients are non-negative 22-bit integers: k = b0 + 256 b1 + 65536 b2.  With the four taps' bytes of one
-            // plane packed in a word, a channel's four products are ONE dp4a per plane (3 per channel and group
-            // instead of 4 multiply-adds plus the byte extracts); the planes are recombined by shifts at the end --
-            // the same integer sum, in a different order.
-            unsigned kb[NG ? NG : 1][3];
-            if (NG) {
-#pragma unroll
-                for (int g = 0; g < NG; ++g) {
-                    int k[4];
-#pragma unroll
-                    for (int t = 0; t < 4; ++t) k[t] = 4 * g + t < kx ? __ldg(kkx + ox * kx + 4 * g + t) : 0;
-                    kb[g][0] = k3b_pack(k, 0); kb[g][1] = k3b_pack(k, 8); kb[g][2] = k3b_pack(k, 16);
-                }
-            }
+            if (NG && dst_w > K3B_THREADS) load_kb(ox);        // only when the output is wider than the CTA
             for (int rr = 0; rr < nr; ++rr) {
                 const uint8_t* p = ibase + (long long)(sy0 + r0 + rr) * row_stride;
                 const int s = (int)(reinterpret_cast<uintptr_t>(p) & 15) + x0 * 3;      // window start in the staged row

@@ -44,3 +44,17 @@ def test_pitched_rows_and_odd_output(qc):
     out = qc.pil_resize(view, out_hw=(97, 131), out_dtype=torch.float32).cpu().numpy()
     for i in range(3):
         assert np.array_equal(out[i], opr.resnet_input(big[i, 10:290, 7:407], (97, 131)))
+
+
+@pytest.mark.parametrize("hw,out_hw", [((640, 640), (300, 320)), ((480, 900), (256, 600)), ((97, 1200), (224, 257))])
+def test_outputs_wider_than_one_cta(qc, hw, out_hw):
+    """Output rows wider than the 256 threads of a CTA (a thread then owns several columns and reloads its packed
+    coefficients per column), against Pillow itself."""
+    from PIL import Image
+    rng = np.random.default_rng(hw[1])
+    imgs = rng.integers(0, 256, (2,) + hw + (3,), dtype=np.uint8)
+    out = qc.pil_resize(torch.from_numpy(imgs).cuda(), out_hw=out_hw, out_dtype=torch.float32).cpu().numpy()
+    for i in range(2):
+        assert np.array_equal(out[i], opr.resnet_input(imgs[i], out_hw)), (hw, out_hw)
+        pil = np.asarray(Image.fromarray(imgs[i]).resize((out_hw[1], out_hw[0]), Image.BILINEAR))
+        assert np.array_equal(opr.pil_resize_bilinear(imgs[i], out_hw), pil)
