@@ -38,6 +38,9 @@ struct HuffTable {
     int maxcode[18];                  // largest code of each length, -1 if none
     int valoff[18];                   // index of the first symbol of a length minus its first code
     uint8_t vals[256];
+    // AC tables only: when a code and the value bits that follow it fit the look-ahead together, one lookup yields
+    // (value << 8) | (run << 4) | total bits; 0 = take the two-step path
+    int16_t fast[1 << K10_LOOK];
 };
 
 struct Header {
@@ -75,6 +78,16 @@ bool build_huff(HuffTable& t, const uint8_t counts[16], const uint8_t* vals, int
         code <<= 1;
     }
     t.maxcode[17] = 0x7fffffff;
+    for (int i = 0; i < (1 << K10_LOOK); ++i) {
+        t.fast[i] = 0;
+        const unsigned e = t.lut[i];
+        if (!e) continue;
+        const int len = (int)(e >> 8), run = (int)((e >> 4) & 15u), mag = (int)(e & 15u);
+        if (mag == 0 || len + mag > K10_LOOK) continue;
+        int v = ((i << len) & ((1 << K10_LOOK) - 1)) >> (K10_LOOK - mag);
+        if (v < (1 << (mag - 1))) v = v - (1 << mag) + 1;
+        if (v >= -128 && v <= 127) t.fast[i] = (int16_t)(v * 256 + run * 16 + len + mag);
+    }
     t.present = true;
     return true;
 }
@@ -240,21 +253,12 @@ Geometry geometry(const Header& H) {
 }
 
 // ---- entropy stage (host) ------------------------------------------------------------------------------------------
+#define K10_INLINE __attribute__((always_inline)) inline
 struct BitReader {
     const uint8_t* p; const uint8_t* end;
     uint64_t acc = 0; int cnt = 0; bool marker = false;
-    inline void fill() {
-        if (cnt > 32) return;
-        if (!marker && p + 4 <= end) {                            // four bytes at once when none of them is 0xFF
-            unsigned v;
-            memcpy(&v, p, 4);
-            if ((v & 0xffu) != 0xffu && ((v >> 8) & 0xffu) != 0xffu && ((v >> 16) & 0xffu) != 0xffu && (v >> 24) != 0xffu) {
-                acc = (acc << 32) | __builtin_bswap32(v);
-                cnt += 32;
-                p += 4;
-                return;
-            }
-        }
+    // slow refill: byte by byte, un-stuffing 0xFF00 and stopping at a marker (then zeros are fed, like libjpeg)
+    __attribute__((noinline)) void fill_slow() {
         while (cnt <= 56) {
             unsigned b = 0;
             if (!marker && p < end) {
@@ -262,20 +266,38 @@ struct BitReader {
                 if (b == 0xFF) {
                     const unsigned b2 = p < end ? *p : 0xD9u;
                     if (b2 == 0) ++p;
-                    else { marker = true; --p; b = 0; }       // leave p on the 0xFF of the marker; feed zeros
+                    else { marker = true; --p; b = 0; }       // leave p on the 0xFF of the marker
                 }
             }
             acc = (acc << 8) | b;
             cnt += 8;
         }
     }
-    inline unsigned peek(int n) const { return (unsigned)((acc >> (cnt - n)) & ((1u << n) - 1u)); }
+    // at least 33 valid bits afterwards: 16 for a code and 15 for the value that follows it
+    K10_INLINE void fill() {
+        if (cnt > 32) return;
+        if (!marker && p + 4 <= end) {                            // four bytes at once when none of them is 0xFF
+            unsigned v;
+            memcpy(&v, p, 4);
+            if (!has_ff(v)) {
+                acc = (acc << 32) | __builtin_bswap32(v);
+                cnt += 32;
+                p += 4;
+                return;
+            }
+        }
+        fill_slow();
+    }
+    static K10_INLINE bool has_ff(unsigned v) {
+        return (v & 0xffu) == 0xffu || ((v >> 8) & 0xffu) == 0xffu || ((v >> 16) & 0xffu) == 0xffu || (v >> 24) == 0xffu;
+    }
+    K10_INLINE unsigned peek(int n) const { return (unsigned)((acc >> (cnt - n)) & ((1u << n) - 1u)); }
 };
 
-inline int huff_decode(BitReader& br, const HuffTable& t) {
+K10_INLINE int huff_decode(BitReader& br, const HuffTable& t) {
     br.fill();
     const unsigned e = t.lut[br.peek(K10_LOOK)];
-    if (e) { br.cnt -= (int)(e >> 8); return (int)(e & 255u); }
+    if (__builtin_expect(e != 0, 1)) { br.cnt -= (int)(e >> 8); return (int)(e & 255u); }
     int l = K10_LOOK + 1;
     int code = (int)br.peek(l);
     while (l <= 16 && code > t.maxcode[l]) { ++l; code = (int)br.peek(l); }
@@ -284,7 +306,7 @@ inline int huff_decode(BitReader& br, const HuffTable& t) {
     return t.vals[(t.valoff[l] + code) & 255];
 }
 
-inline int receive_extend(BitReader& br, int s) {
+K10_INLINE int receive_extend(BitReader& br, int s) {
     const int v = (int)br.peek(s);
     br.cnt -= s;
     return v < (1 << (s - 1)) ? v - (1 << s) + 1 : v;
@@ -327,6 +349,15 @@ int entropy_decode(const uint8_t* d, size_t len, const Header& H, const Geometry
                         if (s) pred[c] += receive_extend(br, s);
                         blk[0] = (int16_t)pred[c];
                         for (int k = 1; k < 64;) {
+                            br.fill();
+                            const int f = act.fast[br.peek(K10_LOOK)];
+                            if (f) {                         // short code + short value: one lookup
+                                k += (f >> 4) & 15;
+                                br.cnt -= f & 15;
+                                blk[k10_natural[k]] = (int16_t)(f >> 8);
+                                ++k;
+                                continue;
+                            }
                             const int rs = huff_decode(br, act);
                             if (rs < 0) K10_BAD(QC_ERR_INVALID, "jpeg: corrupt AC code");
                             const int r = rs >> 4;
