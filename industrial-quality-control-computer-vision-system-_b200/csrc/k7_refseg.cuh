@@ -105,29 +105,55 @@ k7_blur(Img im, const qc_seg_region* __restrict__ regs, int R, int total_bands, 
         for (int ty = y0; ty < y1; ty += 32) {
             for (int tx = 0; tx < rg.w; tx += 32) {
                 __syncthreads();
-                for (int i = tid; i < 40 * 40; i += K4_THREADS) {
-                    const int rr = i / 40, cc = i - rr * 40;
-                    const int yy = min(max(ty - 4 + rr, 0), rg.h - 1), xx = min(max(tx - 4 + cc, 0), rg.w - 1);
-                    s_src[rr][cc] = __dmul_rn((double)g.base[(long long)yy * g.pitch + xx], K7_INV255);
+                // source tile with 'nearest' borders: 4 columns per thread-step -- inside the row one (unaligned)
+                // 32-bit read as two aligned words + a funnel shift, single clamped bytes only at the ROI's edges
+                for (int i = tid; i < 40 * 10; i += K4_THREADS) {
+                    const int rr = i / 10, cw = i - rr * 10;
+                    const int yy = min(max(ty - 4 + rr, 0), rg.h - 1), x0 = tx - 4 + 4 * cw;
+                    const uint8_t* rowp = g.base + (long long)yy * g.pitch;
+                    unsigned wv;
+                    if (x0 >= 0 && x0 + 3 < rg.w) {
+                        const uintptr_t a = reinterpret_cast<uintptr_t>(rowp + x0);
+                        const unsigned* q = reinterpret_cast<const unsigned*>(a & ~(uintptr_t)3);
+                        wv = __funnelshift_r(__ldg(q), __ldg(q + 1), (unsigned)(a & 3) * 8u);    // q+1: inside the padded workspace
+                    } else {
+                        wv = 0u;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) wv |= (unsigned)rowp[min(max(x0 + j, 0), rg.w - 1)] << (8 * j);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        s_src[rr][4 * cw + j] = __dmul_rn((double)((wv >> (8 * j)) & 255u), K7_INV255);
                 }
                 __syncthreads();
-                for (int i = tid; i < 32 * 40; i += K4_THREADS) {          // axis 0 first
-                    const int rr = i / 40, cc = i - rr * 40;
-                    s_v[rr][cc] = k7_tap9(s_src[rr + 4][cc], s_src[rr][cc], s_src[rr + 8][cc], s_src[rr + 1][cc],
-                                          s_src[rr + 7][cc], s_src[rr + 2][cc], s_src[rr + 6][cc], s_src[rr + 3][cc],
-                                          s_src[rr + 5][cc]);
+                // Register sliding windows: a thread produces 4 adjacent outputs along the filter axis from 12 staged
+                // values (3 loads per output instead of 9; the kernel is bound by 64-bit shared-memory loads).
+                for (int i = tid; i < 8 * 40; i += K4_THREADS) {           // axis 0 first: lanes = columns
+                    const int rg4 = i / 40, cc = i - rg4 * 40;
+                    double v[12];
+#pragma unroll
+                    for (int k = 0; k < 12; ++k) v[k] = s_src[4 * rg4 + k][cc];
+#pragma unroll
+                    for (int o = 0; o < 4; ++o)
+                        s_v[4 * rg4 + o][cc] = k7_tap9(v[o + 4], v[o], v[o + 8], v[o + 1], v[o + 7], v[o + 2], v[o + 6], v[o + 3], v[o + 5]);
                 }
                 __syncthreads();
-                for (int i = tid; i < 32 * 32; i += K4_THREADS) {          // then axis 1
-                    const int rr = i >> 5, cc = i & 31;
-                    const int y = ty + rr, x = tx + cc;
-                    if (y < y1 && x < rg.w) {
-                        const double o = k7_tap9(s_v[rr][cc + 4], s_v[rr][cc], s_v[rr][cc + 8], s_v[rr][cc + 1],
-                                                 s_v[rr][cc + 7], s_v[rr][cc + 2], s_v[rr][cc + 6], s_v[rr][cc + 3],
-                                                 s_v[rr][cc + 5]);
-                        blurred[rg.out_offset + (long long)y * rg.w + x] = o;
-                        mn = fmin(mn, o);
-                        mx = fmax(mx, o);
+                for (int i = tid; i < 32 * 8; i += K4_THREADS) {           // then axis 1: lanes = rows (pitch 41: no bank conflicts)
+                    const int rr = i & 31, cg = i >> 5;
+                    const int y = ty + rr, x = tx + 4 * cg;
+                    if (y >= y1 || x >= rg.w) continue;
+                    double v[12];
+#pragma unroll
+                    for (int k = 0; k < 12; ++k) v[k] = s_v[rr][4 * cg + k];
+                    double* q = blurred + rg.out_offset + (long long)y * rg.w + x;
+#pragma unroll
+                    for (int o = 0; o < 4; ++o) {
+                        if (x + o < rg.w) {
+                            const double r9 = k7_tap9(v[o + 4], v[o], v[o + 8], v[o + 1], v[o + 7], v[o + 2], v[o + 6], v[o + 3], v[o + 5]);
+                            q[o] = r9;
+                            mn = fmin(mn, r9);
+                            mx = fmax(mx, r9);
+                        }
                     }
                 }
             }
@@ -185,24 +211,34 @@ k7_hist(const qc_seg_region* __restrict__ regs, int R, int total_bands, const in
         const double scale = 256.0 / (last - first);
         const double* p = blurred + rg.out_offset + (long long)y0 * rg.w;
         const int n = (y1 - y0) * rg.w;
-        for (int i0 = 0; i0 < n; i0 += K4_THREADS) {
-            const int i = i0 + tid;
-            int idx = -1;
-            if (i < n) {
-                const double x = p[i];
-                idx = min(max((int)((x - first) * scale), 0), 255);
-                while (idx > 0 && x < s_e[idx]) idx -= 1;
-                while (idx < 255 && x >= s_e[idx + 1]) idx += 1;
+        const int lane = tid & 31;
+        for (int i0 = 0; i0 < n; i0 += 4 * K4_THREADS) {
+            double xv[4];                                  // four loads in flight per thread: the pass is latency-bound
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + u * K4_THREADS + tid;
+                xv[u] = i < n ? p[i] : 0.0;
             }
-            // neighbouring pixels of a blurred image mostly share a bin: one shared-memory atomic per run of equal
-            // bins inside the warp instead of one per pixel
-            const int lane = tid & 31;
-            const int prev = __shfl_up_sync(0xffffffffu, idx, 1);
-            const unsigned heads = __ballot_sync(0xffffffffu, lane == 0 || idx != prev);
-            if (idx >= 0 && ((heads >> lane) & 1u)) {
-                const unsigned rest = lane == 31 ? 0u : (heads >> (lane + 1));
-                const int len = rest ? __ffs(rest) : 32 - lane;
-                atomicAdd(&s_h[idx], (unsigned)len);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (i0 + u * K4_THREADS >= n) break;       // block-uniform
+                const int i = i0 + u * K4_THREADS + tid;
+                int idx = -1;
+                if (i < n) {
+                    const double x = xv[u];
+                    idx = min(max((int)((x - first) * scale), 0), 255);
+                    while (idx > 0 && x < s_e[idx]) idx -= 1;
+                    while (idx < 255 && x >= s_e[idx + 1]) idx += 1;
+                }
+                // neighbouring pixels of a blurred image mostly share a bin: one shared-memory atomic per run of
+                // equal bins inside the warp instead of one per pixel
+                const int prev = __shfl_up_sync(0xffffffffu, idx, 1);
+                const unsigned heads = __ballot_sync(0xffffffffu, lane == 0 || idx != prev);
+                if (idx >= 0 && ((heads >> lane) & 1u)) {
+                    const unsigned rest = lane == 31 ? 0u : (heads >> (lane + 1));
+                    const int len = rest ? __ffs(rest) : 32 - lane;
+                    atomicAdd(&s_h[idx], (unsigned)len);
+                }
             }
         }
         __syncthreads();

@@ -1,25 +1,38 @@
 #!/usr/bin/env python
-"""Summarise an .ncu-rep per CUDA source line: share of executed warp instructions and stall samples.
-usage: tools/ncu_lines.py rep.ncu-rep [topN]"""
-import csv, subprocess, sys
-rep = sys.argv[1]; top = int(sys.argv[2]) if len(sys.argv) > 2 else 30
+"""Per CUDA source line of an .ncu-rep (compiled with -lineinfo, captured with --import-source on): share of executed
+warp instructions and of the stall samples, summed over the SASS of the line and over the captured launches.
+usage: tools/ncu_lines.py rep.ncu-rep [topN] [kernel-substring]"""
+import collections
+import csv
+import subprocess
+import sys
+
+rep = sys.argv[1]
+top = int(sys.argv[2]) if len(sys.argv) > 2 else 20
+only = sys.argv[3] if len(sys.argv) > 3 else ""
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"],
                      capture_output=True, text=True).stdout
-rows = list(csv.reader(out.splitlines()))
-hdr = None; funcs = {}; cur = None
-for x in rows:
+cur, hdr, agg = None, None, {}
+for x in csv.reader(out.splitlines()):
     if len(x) >= 2 and x[0] == "Function Name":
-        cur = x[1].split("(")[0]; funcs.setdefault(cur, []); continue
+        cur = x[1].split("(")[0][:60]
+        continue
     if len(x) > 7 and x[0] == "Line No":
-        hdr = x; continue
+        hdr = x
+        continue
     if hdr and cur and len(x) >= 8 and x[0] not in ("", "Line No"):
         try:
-            funcs[cur].append((float(x[7]), int(x[6] or 0), x[0], x[1].strip()[:110]))
+            a = agg.setdefault(cur, collections.OrderedDict())
+            v = a.setdefault((x[0], x[1].strip()[:110]), [0.0, 0])
+            v[0] += float(x[7])
+            v[1] += int(x[6] or 0)
         except ValueError:
             pass
-for fn, lines in funcs.items():
-    tot = sum(l[0] for l in lines) or 1; ts = sum(l[1] for l in lines) or 1
-    lines.sort(reverse=True)
-    print(f"== {fn}: total warp-instructions {tot:.0f}, samples {ts}")
-    for v, smp, n, s in lines[:top]:
-        print(f"{v / tot * 100:5.1f}% inst  {smp / ts * 100:5.1f}% smp  L{n:>4s}  {s}")
+for fn, a in agg.items():
+    if only not in fn:
+        continue
+    tot = sum(v[0] for v in a.values()) or 1
+    ts = sum(v[1] for v in a.values()) or 1
+    print(f"== {fn}: warp-instructions {tot:.0f}, stall samples {ts}")
+    for (ln, src), v in sorted(a.items(), key=lambda kv: -kv[1][1])[:top]:
+        print(f"{100 * v[0] / tot:5.1f}% inst {100 * v[1] / ts:5.1f}% smp  L{ln:>4s}  {src}")
