@@ -70,6 +70,7 @@ struct SegWs {
     double* thr_adj;      // [R]
     unsigned long long* acc_n;    // [total_blocks]  K8 per-root (n_axis | n_diag << 32)
     long long* acc_x;             // [total_blocks]  K8 per-root sum of cross products
+    int* queue;                   // [16] work counters of the kernels that hand regions out dynamically (zeroed per call)
     size_t total;
 };
 
@@ -98,6 +99,7 @@ SegWs carve(void* base, const qc_seg_params* p, int method = QC_SEG_COMPOSITE) {
     w.thr_adj = (double*)(b + take(thr ? R * 8 : 0));
     w.acc_n = (unsigned long long*)(b + take(ref ? (size_t)p->total_blocks * 8 : 0));
     w.acc_x = (long long*)(b + take(ref ? (size_t)p->total_blocks * 8 : 0));
+    w.queue = (int*)(b + take(64));
     w.total = off;
     return w;
 }
@@ -1343,9 +1345,13 @@ int seg_run(qc_ctx* ctx, int method, const uint8_t* imgs, const qc_seg_params* p
         QC_LAUNCHED_AS(ctx, "k4_compress", st);
         return QC_OK;
     };
+    int queue_used = 0;
+    QC_CUDA(ctx, cudaMemsetAsync(w.queue, 0, 64, st));
     auto fill_holes = [&](const unsigned* bits_in, unsigned* bits_out, unsigned* free_ws) -> int {
         if (int rc = qc_prepare(ctx, k7_fill, K7_FILL_SMEM_WORDS * 4, K7_FILL_THREADS, &occ)) return rc;
-        k7_fill<<<std::min(R, sms * std::max(occ, 1)), K7_FILL_THREADS, K7_FILL_SMEM_WORDS * 4, st>>>(regions, R, bits_in, bits_out, free_ws);
+        if (queue_used >= 16) QC_FAIL(ctx, QC_ERR_INVALID, "%s: out of work counters", fn);
+        k7_fill<<<std::min(R, sms * std::max(occ, 1)), K7_FILL_THREADS, K7_FILL_SMEM_WORDS * 4, st>>>(regions, R, bits_in, bits_out, free_ws,
+                                                                                                    w.queue + queue_used++);
         QC_LAUNCHED_AS(ctx, "k7_fill", st);
         return QC_OK;
     };

@@ -740,12 +740,19 @@ __device__ __forceinline__ unsigned k7_run_starts(const unsigned* F, int i, int 
 
 __global__ void __launch_bounds__(K7_FILL_THREADS, 2)
 k7_fill(const qc_seg_region* __restrict__ regs, int R, const unsigned* __restrict__ bits_in,
-        unsigned* __restrict__ bits_out, unsigned* __restrict__ free_ws) {
+        unsigned* __restrict__ bits_out, unsigned* __restrict__ free_ws, int* __restrict__ queue) {
     extern __shared__ __align__(16) unsigned k7f_sm[];
     __shared__ int s_warp[K7_FILL_THREADS / 32];
-    __shared__ int s_total;
+    __shared__ int s_total, s_next;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int r = blockIdx.x; r < R; r += gridDim.x) {
+    // regions differ 50x in size and a CTA only gets a handful of them: a shared counter hands them out one at a time
+    // (a static round-robin left the slowest CTA with more than twice the mean work)
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_next = atomicAdd(queue, 1);
+        __syncthreads();
+        const int r = s_next;
+        if (r >= R) break;
         const qc_seg_region rg = regs[r];
         const int wpr = wpr_of(rg), h = rg.h, nwords = h * wpr;
         const unsigned tail = (rg.w & 31) ? ((1u << (rg.w & 31)) - 1u) : 0xFFFFFFFFu;   // valid bits of the last word
