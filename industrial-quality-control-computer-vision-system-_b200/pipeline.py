@@ -132,6 +132,9 @@ class InspectionPipeline:
         # host frames: H2D on a copy stream into one of two staging buffers, so the copy of batch i+1 overlaps the
         # compute of batch i (run_async is called before the previous batch is finalised)
         self.copy_stream = torch.cuda.Stream(self.dev)
+        # the segmentation of a batch runs on its own stream, underneath the classifier (submit_rest)
+        self.seg_stream = torch.cuda.Stream(self.dev)
+        self.overlap_seg = True
         self._stage = {}             # (shape) -> [buffers, free events, next index]
 
     def install_yolo(self, module, source: str):
@@ -290,6 +293,23 @@ class InspectionPipeline:
         # All rows of the batch live in ONE arena [rows,3,224,224] whose static-shape views are the inputs of the
         # ResNet-50 graphs (classifier_layout); K3 fills it with ONE launch (a destination row per ROI), K3b with one
         # launch per contiguous span of whole-frame rows.
+        # The segmentation needs the frames and the kept boxes only -- not the classifier -- and its kernels are
+        # latency-bound chains on small ROIs: it is queued FIRST, on its own stream, so that it runs underneath the
+        # ResNet-50 graphs instead of after them (joined again before the result copies).
+        seg, seg_done = None, None
+        if include_segmentation and K:
+            cls = det[roi_img, roi_det, 5].astype(np.int32)
+            side = self.seg_stream if self.overlap_seg else torch.cuda.current_stream(self.dev)
+            if self.overlap_seg:
+                side.wait_event(h.ready)           # K2 of THIS batch (and everything before it) is done
+            with torch.cuda.stream(side):
+                seg = self._segment_rois(frames, roi_img, roi_box, cls, keep_seg_tensors, morph_iters, min_area,
+                                         swap_rb=not processed)
+                if self.overlap_seg:
+                    seg_done = torch.cuda.Event()
+                    seg_done.record(side)
+            self.last_seg_pixels = int(sum(int(g["seg"]["params"].total_pixels) for g in seg))
+
         n_whole = n if self.classify_global else 0
         n_roi = K if self.classify_rois else 0
         nro = n_whole + n_roi
@@ -320,13 +340,8 @@ class InspectionPipeline:
                     parts.append(torch.softmax(self._classify(arena[off:off + cs])[:used].float(), 1))
             probs = torch.cat(parts) if len(parts) > 1 else parts[0]
 
-        # ---- segmentation of every detection ROI (K7 per-class methods, or the K4 composite) ------------------
-        seg = None
-        if include_segmentation and K:
-            cls = det[roi_img, roi_det, 5].astype(np.int32)
-            seg = self._segment_rois(frames, roi_img, roi_box, cls, keep_seg_tensors, morph_iters, min_area,
-                                     swap_rb=not processed)
-            self.last_seg_pixels = int(sum(int(g["seg"]["params"].total_pixels) for g in seg))
+        if seg_done is not None:
+            torch.cuda.current_stream(self.dev).wait_event(seg_done)
 
         # ---- final device->host reads: asynchronous copies into pinned buffers, finalised by .result() ------
         def stage(t):
@@ -475,9 +490,12 @@ class PendingResult:
                     over = np.nonzero(ncomp > g["cap"])[0]
                     if len(over):   # components beyond the reservation escaped the min-area filter: redo exactly
                         sub = {k: (v[over] if isinstance(v, np.ndarray) else v) for k, v in g["regs"].items() if k != "max_comp"}
-                        seg2 = pipe.qc.segment(self.frames, sub, morph_iters=g["iters"], swap_rb=g["swap_rb"], want_mask=False,
-                                               want_labels=False, method=g["code"])
-                        area[over] = seg2["area"].cpu().numpy()
+                        # on the segmentation stream: its cached workspaces may be in use by the next batch there
+                        side = pipe.seg_stream if pipe.overlap_seg else torch.cuda.current_stream(pipe.dev)
+                        with torch.cuda.stream(side):
+                            seg2 = pipe.qc.segment(self.frames, sub, morph_iters=g["iters"], swap_rb=g["swap_rb"], want_mask=False,
+                                                   want_labels=False, method=g["code"])
+                            area[over] = seg2["area"].cpu().numpy()
                 res.seg_area[idx] = area
                 res.seg_thr[idx] = self.host[f"thr{gi}"].numpy()
                 res.seg_ncomp[idx] = ncomp
