@@ -37,5 +37,31 @@ qc.segment(big, [dict(img=0, x=0, y=0, w=1100, h=300)], morph_iters=1)
 # K5
 det = torch.rand(2, 8, 6).cuda() * 100
 qc.spc_stats(det, torch.tensor([3, 8], dtype=torch.int32).cuda())
+# K7 / K8 / K9 (reference segmentation methods: run union-find fill, sweeps fallback on a noise ROI, adaptive + Canny)
+gn = torch.from_numpy(rng.integers(0, 256, (1, 300, 310), dtype=np.uint8)).cuda()
+for code, iters, marea in ((ffi.QC_SEG_REF_THRESHOLD, 2, 10), (ffi.QC_SEG_REF_ADAPTIVE, 1, 20)):
+    regs = [dict(img=0, x=0, y=0, w=203, h=130, polarity=1, min_area=marea), dict(img=1, x=7, y=9, w=65, h=33, polarity=0, min_area=marea),
+            dict(img=0, x=100, y=50, w=33, h=70, polarity=1, min_area=marea)]
+    if code == ffi.QC_SEG_REF_THRESHOLD:
+        for r in regs:
+            r["max_comp"] = 2
+    qc.segment(g, regs, morph_iters=iters, method=code, want_sums=True, want_contours=True)
+    rn = [dict(img=0, x=3, y=2, w=301, h=290, polarity=1, min_area=marea)]
+    if code == ffi.QC_SEG_REF_THRESHOLD:
+        rn[0]["max_comp"] = 2
+    qc.segment(gn, rn, morph_iters=iters, method=code, want_sums=True, want_contours=True)
+# K6 (clustering alone + the whole chain)
+rows = np.zeros((2, 40), ffi.RULES_ROW_DTYPE)
+xy = rng.integers(0, 250, (2, 40, 2)); wh = rng.integers(4, 60, (2, 40, 2))
+rows["x1"], rows["y1"], rows["x2"], rows["y2"] = xy[..., 0], xy[..., 1], xy[..., 0] + wh[..., 0], xy[..., 1] + wh[..., 1]
+rows["cls"] = rng.integers(0, 3, (2, 40)); rows["severity"] = rng.integers(1, 4, (2, 40)); rows["conf"] = rng.uniform(0.3, 1, (2, 40))
+rows["ext"] = -1
+qc.rules_apply(rows, np.array([40, 17], np.int32), np.array([[320, 320], [300, 310]], np.int32))
+# K10 (4:2:0 with restart intervals, 4:4:4 odd size, gray)
+import cv2
+streams = [cv2.imencode(".jpg", np.ascontiguousarray(imgs[0][..., ::-1]), [cv2.IMWRITE_JPEG_QUALITY, 80, cv2.IMWRITE_JPEG_RST_INTERVAL, 3])[1],
+           cv2.imencode(".jpg", np.ascontiguousarray(imgs[1][:77, :131, ::-1]), [cv2.IMWRITE_JPEG_QUALITY, 95, cv2.IMWRITE_JPEG_SAMPLING_FACTOR, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444])[1],
+           cv2.imencode(".jpg", imgs[0][:50, :9, 0])[1]]
+qc.jpeg_decode(streams)
 torch.cuda.synchronize()
 print("sanitize_case done, launches:", qc.launch_count)
