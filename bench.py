@@ -697,7 +697,14 @@ def main():
         "k7_fill": (2 * thr_px + adp_px) // 4,             # bit masks in and out, all calls of the step
         "k4_ccl_local": (2 * thr_px + 3 * adp_px) // 8 + (2 * thr_px + 3 * adp_px),   # bits in, one int32 per 2x2 block out
     }
-    if len(k3_kernels) == 1:
+    # K3 = k3_roi_win (every ROI whose taps fit three-pixel windows: bins <= 1.95) + k3_roi_tma (the rest; a scan that
+    # finds nothing when no box is wider / taller than 436 px): the bytes go to the kernel that did the work
+    if "k3_roi_win" in k3_kernels:
+        big = (last.roi_box[:, 2] - last.roi_box[:, 0] > 436) | (last.roi_box[:, 3] - last.roi_box[:, 1] > 436)
+        kern_bytes["k3_roi_win"] = int(roi_px[~big].sum()) * 3 + int((~big).sum()) * 3 * 224 * 224 * 2
+        if big.any():
+            kern_bytes["k3_roi_tma"] = int(roi_px[big].sum()) * 3 + int(big.sum()) * 3 * 224 * 224 * 2
+    elif len(k3_kernels) == 1:
         kern_bytes[k3_kernels[0]] = op_bytes["k3_roi_align"]
     k_total = sum(v["ms_per_step"] for v in kernel_times.values())
     for name, v in kernel_times.items():

@@ -28,11 +28,25 @@ int qc_create(int device, qc_ctx** out) {
         delete c;
         return QC_ERR_UNSUPPORTED;
     }
+    {
+        qc_device_guard dev_guard(c);
+        if (cudaMalloc(&c->sched, (size_t)QC_SCHED_SLOTS * 32 * sizeof(int)) != cudaSuccess ||
+            cudaMemset(c->sched, 0, (size_t)QC_SCHED_SLOTS * 32 * sizeof(int)) != cudaSuccess) {
+            cudaGetLastError();
+            if (c->sched) cudaFree(c->sched);
+            delete c;
+            return QC_ERR_CUDA;
+        }
+    }
     *out = c;
     return QC_OK;
 }
 
 void qc_destroy(qc_ctx* ctx) {
+    if (ctx && ctx->sched) {
+        qc_device_guard dev_guard(ctx);
+        cudaFree(ctx->sched);
+    }
     if (ctx && ctx->prof_recs) {
         for (int i = 0; i < QC_PROF_MAX; ++i)
             if (ctx->prof_recs[i].ev) cudaEventDestroy(ctx->prof_recs[i].ev);

@@ -22,7 +22,12 @@ struct qc_ctx {
     bool prof = false;
     int prof_n = 0;
     qc_prof_rec* prof_recs = nullptr;
+    // ring of zero-initialised work counters (one 128-byte line each) for kernels that hand out work items dynamically;
+    // a call takes the next line and resets it on its own stream before the launch
+    int* sched = nullptr;
+    std::atomic<unsigned> sched_i{0};
 };
+constexpr int QC_SCHED_SLOTS = 64;
 static inline void qc_prof_mark(qc_ctx* ctx, const char* name, cudaStream_t st) {
     if (!ctx || !ctx->prof || !ctx->prof_recs || ctx->prof_n >= QC_PROF_MAX) return;
     qc_prof_rec& r = ctx->prof_recs[ctx->prof_n];

@@ -363,6 +363,7 @@ constexpr int K3T_ROWS = 12;               // source rows per band held as Hs
 constexpr int K3T_RAW = 6 * 1024;          // raw byte staging buffer (floats: 4x)
 constexpr int K3T_PH_MAX = 256;
 constexpr int K3T_SPLIT = 4;                // work items per ROI (quarters of its output rows): balance across CTAs
+constexpr int K3T_SCAN = 8;                 // ROIs a CTA examines per round in leftover mode
 
 struct K3Taps { int i[4]; float w[4]; int n; };
 
@@ -403,10 +404,11 @@ __device__ __forceinline__ K3Taps k3_taps(float start, float bin, int p, int sr,
 template <typename OutT>
 __device__ __noinline__ void k3_roi_direct(const uint8_t* base, bool img_ok, int H, int W, int row_stride, float x1, float y1,
                                            float bin_w, float bin_h, int PH, int PW, int sr, int swap_rb, const float* nd,
-                                           const float* nm, const float* ns, OutT* dk, int ph_lo, int ph_hi) {
+                                           const float* nm, const float* ns, OutT* dk, int ph_lo, int ph_hi,
+                                           int nthreads = K3T_THREADS) {
     const int total = PH * PW;
     const float count = (float)(sr * sr);
-    for (int o = ph_lo * PW + threadIdx.x; o < ph_hi * PW; o += K3T_THREADS) {
+    for (int o = ph_lo * PW + threadIdx.x; o < ph_hi * PW; o += nthreads) {
         const int ph = o / PW, pw = o - ph * PW;
         float acc[3] = {0.f, 0.f, 0.f};
         if (img_ok) {
@@ -446,11 +448,378 @@ __device__ __noinline__ void k3_roi_direct(const uint8_t* base, bool img_ok, int
     }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// k3_roi_win: the common case -- every sample inside the frame and bins <= 1.95 source pixels, i.e. the merged taps of
+// an output coordinate lie in a window of THREE consecutive source pixels (two samples at most ~0.98 apart).  Both
+// passes then run in registers with fixed-size windows and no intermediate image in shared memory:
+//   work item = (ROI, slice of its output rows), one 64-thread CTA at a time (persistent, ~8 CTAs per SM);
+//   thread    = two pairs of adjacent output columns (2t, 2t+1, 2t+PW/2, 2t+PW/2+1); x windows (first source pixel + 3
+//               weights per column) live in registers;
+//   per band of source rows: one TMA bulk copy per row (16-byte aligned superset of the tapped segment) -> bytes
+//               converted ONCE to float4 pixels already scaled by 1/(count*div*std) (swap_rb folded in);
+//   per source row: horizontal pass = 3 LDS.128 + 9 FMA per column into a rotating three-row register window;
+//               every output row whose last tapped source row this is gets emitted straight from the window:
+//               out = B + w0*row[-2] + w1*row[-1] + w2*row[0]  (B = -mean/std; no separate normalisation pass),
+//               bf16x2 / float2 stores (a warp writes 128 / 256 contiguous bytes per channel and pair).
+// Compared with k3_roi_tma (Hs in shared memory): ~3x less shared-memory traffic, no barriers inside a band.
+// Everything else (boxes leaving the frame, larger bins) is left to k3_roi_tma, which skips what this kernel took;
+// both evaluate the same scalar predicate k3_geom().fast.
+constexpr int K3W_F_BYTES = 20 * 1024;         // float4 pixels of one band
+constexpr int K3W_RAW_BYTES = 4 * 1024;        // staged bytes of one band
+constexpr int K3W_ROWS = 9;                    // source rows per band (a multiple of 3; fewer for wide boxes)
+constexpr int K3W_PH_MAX = 128;                // output rows per work item
+constexpr int K3W_SRC_MAX = 272;               // source rows per work item (128 * 1.95 + slack)
+constexpr float K3W_BIN_MAX = 1.95f;
+constexpr int K3W_THREADS = 64;
+
+struct K3Geom {
+    int img, x_lo, x_hi, b0, pitch;
+    float x1, y1, bin_w, bin_h;
+    bool img_ok, fast;
+};
+
+// torchvision's sample position, same operation order; `isr` = 1/sr when sr is a power of two (division by 1, 2 or 4
+// is an exact multiplication), 0 otherwise
+__device__ __forceinline__ float k3_sample(float start, float bin, int p, int is, int sr, float isr) {
+    const float t = __fmul_rn((float)is + 0.5f, bin);
+    const float d = isr != 0.f ? __fmul_rn(t, isr) : __fdiv_rn(t, (float)sr);
+    return __fadd_rn(__fadd_rn(start, __fmul_rn((float)p, bin)), d);
+}
+__device__ __forceinline__ float k3_isr(int sr) { return sr == 1 ? 1.f : (sr == 2 ? 0.5f : (sr == 4 ? 0.25f : 0.f)); }
+
+__device__ __forceinline__ K3Geom k3_geom(const float* __restrict__ r, int n, int H, int W, int PH, int PW, int sr, int aligned) {
+    K3Geom g;
+    const float isr = k3_isr(sr);
+    g.img = (int)r[0];
+    const float offset = aligned ? 0.5f : 0.f;
+    g.x1 = __fsub_rn(r[1], offset); g.y1 = __fsub_rn(r[2], offset);
+    const float x2 = __fsub_rn(r[3], offset), y2 = __fsub_rn(r[4], offset);
+    float roi_w = __fsub_rn(x2, g.x1), roi_h = __fsub_rn(y2, g.y1);
+    if (!aligned) { roi_w = fmaxf(roi_w, 1.f); roi_h = fmaxf(roi_h, 1.f); }
+    g.bin_h = __fdiv_rn(roi_h, (float)PH); g.bin_w = __fdiv_rn(roi_w, (float)PW);
+    g.img_ok = g.img >= 0 && g.img < n;
+    // the samples are monotone in (p, is) for bin >= 0: first and last bound all of them
+    const float fx = k3_sample(g.x1, g.bin_w, 0, 0, sr, isr), lx = k3_sample(g.x1, g.bin_w, PW - 1, sr - 1, sr, isr);
+    const float fy = k3_sample(g.y1, g.bin_h, 0, 0, sr, isr), ly = k3_sample(g.y1, g.bin_h, PH - 1, sr - 1, sr, isr);
+    g.fast = g.img_ok && g.bin_w >= 0.f && g.bin_w <= K3W_BIN_MAX && g.bin_h >= 0.f && g.bin_h <= K3W_BIN_MAX &&
+             fx >= -1.f && lx <= (float)W && fy >= -1.f && ly <= (float)H;
+    g.x_lo = min((int)fmaxf(fx, 0.f), W - 1);
+    g.x_hi = min((int)fmaxf(lx, 0.f) + 1, W - 1);
+    g.b0 = (3 * g.x_lo) & ~15;
+    g.pitch = ((3 * (g.x_hi + 1) + 15) & ~15) - g.b0;
+    // three source rows of the band must fit: staged bytes and float4 pixels (row pitch rounded up to 4 pixels)
+    g.fast = g.fast && g.x_hi >= g.x_lo && g.pitch * 3 <= K3W_RAW_BYTES && ((g.x_hi - g.x_lo + 6) & ~3) * 48 <= K3W_F_BYTES;
+    return g;
+}
+
+// window form of the merged taps of one output coordinate (sr <= 2, all samples known to be in range): first source
+// index and the summed weights at offsets 0..2; `wide` is set if a tap falls outside the three-pixel window (never
+// for bins <= 1.95 -- checked, not assumed)
+__device__ __forceinline__ void k3_window(float start, float bin, int p, int sr, float isr, int size, int& first, int& last,
+                                          float& w0, float& w1, float& w2, bool& wide) {
+    float v = k3_sample(start, bin, p, 0, sr, isr);
+    if (v <= 0.f) v = 0.f;
+    int lo = (int)v, hi;
+    if (lo >= size - 1) { hi = lo = size - 1; v = (float)lo; } else hi = lo + 1;
+    float l = __fsub_rn(v, (float)lo);
+    first = lo; last = hi;
+    w0 = __fsub_rn(1.f, l);
+    w1 = hi > lo ? l : 0.f;
+    if (hi == lo) w0 = __fadd_rn(w0, l);
+    w2 = 0.f;
+    if (sr > 1) {
+        v = k3_sample(start, bin, p, 1, sr, isr);
+        if (v <= 0.f) v = 0.f;
+        lo = (int)v;
+        if (lo >= size - 1) { hi = lo = size - 1; v = (float)lo; } else hi = lo + 1;
+        l = __fsub_rn(v, (float)lo);
+        const float h = __fsub_rn(1.f, l);
+        const int dl = lo - first, dh = hi - first;
+        if (dl < 0 || dh > 2) wide = true;
+        last = hi;
+        w0 = __fadd_rn(w0, dl == 0 ? h : 0.f);
+        w1 = __fadd_rn(w1, (dl == 1 ? h : 0.f));
+        w1 = __fadd_rn(w1, (dh == 1 ? l : 0.f));
+        w2 = __fadd_rn(w2, (dl == 2 ? h : 0.f));
+        w2 = __fadd_rn(w2, (dh == 2 ? l : 0.f));
+        if (dh == 0) w0 = __fadd_rn(w0, l);
+    }
+}
+
+// packed two-lane float32 arithmetic (sm_100 FFMA2 / FMUL2: one issue slot for two multiply-adds)
+__device__ __forceinline__ float2 k3_fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ float2 k3_mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 k3_lo(const float4& v) { return make_float2(v.x, v.y); }
+__device__ __forceinline__ float2 k3_hi(const float4& v) { return make_float2(v.z, v.w); }
+__device__ __forceinline__ float2 k3_dup(float v) { return make_float2(v, v); }
+
+// one output row from the register window: rows A (r-2, only if THREE), B (r-1), C (r)
+template <typename OutT, bool THREE, int CPW, int CPH>
+__device__ __forceinline__ void k3w_emit(const float2 (&A)[4][2], const float2 (&B)[4][2], const float2 (&C)[4][2], const float4 wv,
+                                         const float2 (&fb2)[2], OutT* q, long long total, int half) {
+    float2 o[4][2];
+    const float2 w0 = k3_dup(wv.x), w1 = k3_dup(wv.y), w2 = k3_dup(wv.z);
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            o[j][e] = k3_fma2(w1, B[j][e], k3_fma2(w2, C[j][e], fb2[e]));
+            if (THREE) o[j][e] = k3_fma2(w0, A[j][e], o[j][e]);
+        }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const float v0 = c == 0 ? o[2 * e][0].x : (c == 1 ? o[2 * e][0].y : o[2 * e][1].x);
+            const float v1 = c == 0 ? o[2 * e + 1][0].x : (c == 1 ? o[2 * e + 1][0].y : o[2 * e + 1][1].x);
+            OutT* qe = q + c * total + (CPW ? e * (CPW / 2) : e * half);
+            if (sizeof(OutT) == 2) {
+                const __nv_bfloat162 a = __floats2bfloat162_rn(v0, v1);
+                *reinterpret_cast<unsigned*>(qe) = *reinterpret_cast<const unsigned*>(&a);
+            } else {
+                *reinterpret_cast<float2*>(qe) = make_float2(v0, v1);
+            }
+        }
+    }
+}
+
+// One source row: horizontal pass into window slot SLOT (channel pairs (c0,c1), (c2,-) per column: the float4 pixel
+// splits into two FFMA2 operands), then the output rows whose last tapped source row this is: `info` = n3 | n2 << 8,
+// at most one three-row output (the one straddling source row r-1) followed by n2 two-row outputs.  CPW / CPH > 0: the
+// output shape is a compile-time constant, so every store address is the running row pointer + an immediate.
+template <typename OutT, int SLOT, int CPW, int CPH>
+__device__ __forceinline__ void k3w_row(float2 (&win)[3][4][2], const float4* __restrict__ frow, const int (&xo)[4],
+                                        const float (&xw)[4][3], const int*& infop, int& info, const float4*& wvp, float4& wv,
+                                        const float2 (&fb2)[2], OutT*& q, int total_rt, int PW_rt) {
+    const int PW = CPW ? CPW : PW_rt;
+    const long long total = CPW ? (long long)CPW * CPH : (long long)total_rt;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float4 p0 = frow[xo[j]], p1 = frow[xo[j] + 1], p2 = frow[xo[j] + 2];
+        const float2 w0 = k3_dup(xw[j][0]), w1 = k3_dup(xw[j][1]), w2 = k3_dup(xw[j][2]);
+        win[SLOT][j][0] = k3_fma2(w2, k3_lo(p2), k3_fma2(w1, k3_lo(p1), k3_mul2(w0, k3_lo(p0))));
+        win[SLOT][j][1] = k3_fma2(w2, k3_hi(p2), k3_fma2(w1, k3_hi(p1), k3_mul2(w0, k3_hi(p0))));
+    }
+    constexpr int S1 = (SLOT + 1) % 3, S2 = (SLOT + 2) % 3;        // rows r-2, r-1 (row r is SLOT)
+    const int n3 = info & 255, n2 = info >> 8;
+    info = *++infop;                                                // next source row's counts (sentinel behind the last)
+    for (int e = 0; e < n3; ++e) {
+        k3w_emit<OutT, true, CPW, CPH>(win[S1], win[S2], win[SLOT], wv, fb2, q, total, PW >> 1);
+        wv = *++wvp;                                                // next output row's weights (sentinel behind the last)
+        q += PW;
+    }
+    for (int e = 0; e < n2; ++e) {
+        k3w_emit<OutT, false, CPW, CPH>(win[S1], win[S2], win[SLOT], wv, fb2, q, total, PW >> 1);
+        wv = *++wvp;
+        q += PW;
+    }
+}
+
+__device__ __forceinline__ float k3_bytef(unsigned v, int k) { return (float)((v >> (8 * k)) & 255u); }
+
+template <typename OutT, int CPW, int CPH>
+__global__ void __launch_bounds__(K3W_THREADS, 8)
+k3_roi_win(const uint8_t* __restrict__ imgs, int n, int H, int W, long long img_stride, int row_stride,
+           const float* __restrict__ rois, int K, int PH_rt, int PW_rt, int sr, int aligned, int swap_rb,
+           const float* __restrict__ norm, OutT* __restrict__ dst, int tma_ok, const int* __restrict__ dst_rows, int split_log2,
+           int* __restrict__ sched) {
+    constexpr int THREADS = K3W_THREADS;
+    extern __shared__ __align__(128) unsigned char k3w_sm[];
+    float4* F = reinterpret_cast<float4*>(k3w_sm);                       // [rows][fp4] scaled float pixels
+    uint8_t* raw = k3w_sm + K3W_F_BYTES;                                 // [rows][pitch] (+16 bytes of slack)
+    __shared__ float4 s_wv[K3W_PH_MAX + 1];       // per output row of the item: weights of source rows last-2, last-1, last
+    __shared__ int s_info[K3W_SRC_MAX + 1];       // per source row of the item: n3 | n2 << 8 output rows ending there
+    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ int s_next;
+    const int PH = CPH ? CPH : PH_rt, PW = CPW ? CPW : PW_rt;
+    const int tid = threadIdx.x;
+    const int total = PH * PW;
+    const int half = PW >> 1, npair = PW >> 2;                        // threads that own columns
+    const bool active = tid < npair;
+    const float isr = k3_isr(sr);
+    float fa[3];
+    float2 fb2[2];
+    {
+        // out = ((acc/count)/div - mean)/std == acc * A - mean/std up to ~6e-7 absolute; A is folded into the staged pixels
+        const float count = (float)(sr * sr);
+        float fb[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            fa[c] = __fdiv_rn(1.f, __fmul_rn(__fmul_rn(count, norm[c * 3 + 0]), norm[c * 3 + 2]));
+            fb[c] = -__fdiv_rn(norm[c * 3 + 1], norm[c * 3 + 2]);
+        }
+        fb2[0] = make_float2(fb[0], fb[1]);
+        fb2[1] = make_float2(fb[2], 0.f);
+    }
+    if (tid == 0) { qc_mbar_init(&s_bar, 1); qc_fence_mbar_init(); }
+    unsigned parity = 0;
+    __syncthreads();
+
+    // work items = (ROI, slice of output rows), handed out through a global counter (boxes differ 10x in source area)
+    const int n_items = K << split_log2;
+    int item = blockIdx.x;
+    while (item < n_items) {
+        const int k = item >> split_log2, chunk = item - (k << split_log2);
+        const int ph_lo = (chunk * PH) >> split_log2, ph_hi = ((chunk + 1) * PH) >> split_log2;
+        const int nout = ph_hi - ph_lo;
+        const K3Geom g = k3_geom(rois + (long long)k * 5, n, H, W, PH, PW, sr, aligned);
+        // first source row of the item == first tap of output row ph_lo (same expression as k3_window)
+        const int r_first = min((int)fmaxf(k3_sample(g.y1, g.bin_h, ph_lo, 0, sr, isr), 0.f), H - 1);
+        const int nsrc_max = min(K3W_SRC_MAX, (int)((float)nout * g.bin_h) + 4);
+        __syncthreads();                                             // previous item is done with every shared table
+        if (tid == 0) s_next = (int)gridDim.x + atomicAdd(sched, 1);
+        for (int i = tid; i <= nsrc_max; i += THREADS) s_info[i] = 0;
+        __syncthreads();
+        if (!g.fast || nout <= 0) {
+            item = s_next;
+            continue;
+        }
+        const uint8_t* base = imgs + (long long)g.img * img_stride;
+        OutT* const dk = dst + (long long)(dst_rows ? dst_rows[k] : k) * 3 * total;
+        // ---- per-item tables -----------------------------------------------------------------------------------
+        bool wide = false;
+        int xo[4];
+        float xw[4][3];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int col = 2 * tid + (j >> 1) * half + (j & 1);
+            int first = g.x_lo, last;
+            xw[j][0] = xw[j][1] = xw[j][2] = 0.f;
+            if (active) k3_window(g.x1, g.bin_w, col, sr, isr, W, first, last, xw[j][0], xw[j][1], xw[j][2], wide);
+            xo[j] = first - g.x_lo;
+            if (xo[j] < 0 || first > g.x_hi) wide = true;
+        }
+        for (int i = tid; i <= nout; i += THREADS) {
+            if (i == nout) {                                         // sentinel (read ahead, never used)
+                s_wv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                continue;
+            }
+            int first, last;
+            float w0, w1, w2;
+            k3_window(g.y1, g.bin_h, ph_lo + i, sr, isr, H, first, last, w0, w1, w2, wide);
+            // re-base the weights on the LAST tapped row: slots = rows last-2, last-1, last
+            const int sh = 2 - (last - first);                       // 0, 1 or 2 leading empty slots
+            const float a0 = sh == 0 ? w0 : 0.f;
+            const float a1 = sh == 0 ? w1 : (sh == 1 ? w0 : 0.f);
+            const float a2 = sh == 0 ? w2 : (sh == 1 ? w1 : w0);
+            s_wv[i] = make_float4(a0, a1, a2, 0.f);
+            const int ri = last - r_first;
+            if (ri < 0 || ri >= nsrc_max) wide = true;
+            else atomicAdd(&s_info[ri], sh == 0 ? 1 : 256);
+        }
+        const int any_wide = __syncthreads_or(wide ? 1 : 0);
+        if (any_wide) {                                              // not reachable for bins <= 1.95; kept as a guard
+            float nd[3], nm[3], ns[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) { nd[c] = norm[c * 3 + 0]; nm[c] = norm[c * 3 + 1]; ns[c] = norm[c * 3 + 2]; }
+            k3_roi_direct<OutT>(base, true, H, W, row_stride, g.x1, g.y1, g.bin_w, g.bin_h, PH, PW, sr, swap_rb, nd, nm, ns, dk,
+                                ph_lo, ph_hi, THREADS);
+            item = s_next;
+            continue;
+        }
+        // last source row of the item = last tap of its last output row (monotone); the rows in between are all staged
+        int r_last;
+        {
+            int f, l;
+            float t0, t1, t2;
+            bool dummy = false;
+            k3_window(g.y1, g.bin_h, ph_hi - 1, sr, isr, H, f, l, t0, t1, t2, dummy);
+            r_last = l;
+        }
+        const int fpitch = g.x_hi - g.x_lo + 3;                      // + the two pixels a window may reach past x_hi
+        const int fp4 = (fpitch + 3) & ~3, g4 = fp4 >> 2;            // F row pitch in pixels / in 4-pixel groups
+        const int rows_cap = max(3, min(min(K3W_ROWS, K3W_RAW_BYTES / g.pitch), K3W_F_BYTES / (fp4 * 16)) / 3 * 3);
+        const int bofs = 3 * g.x_lo - g.b0;                          // byte of pixel x_lo inside a staged row
+        auto stage = [&](int r0, int r1) {
+            const int nrows = r1 - r0 + 1;
+            if (tma_ok) {
+                if (tid == 0) {
+                    qc_fence_proxy_async();
+                    qc_mbar_expect_tx(&s_bar, (uint32_t)(nrows * g.pitch));
+                    for (int rr = 0; rr < nrows; ++rr)
+                        qc_bulk_g2s(raw + rr * g.pitch, base + (long long)(r0 + rr) * row_stride + g.b0, (uint32_t)g.pitch, &s_bar);
+                }
+            } else {
+                const int valid = min(g.pitch, 3 * W - g.b0);        // never read past the row's pixels
+                for (int i = tid; i < nrows * g.pitch; i += THREADS) {
+                    const int rr = i / g.pitch, j = i - rr * g.pitch;
+                    raw[i] = j < valid ? __ldg(base + (long long)(r0 + rr) * row_stride + g.b0 + j) : (uint8_t)0;
+                }
+            }
+        };
+        float2 win[3][4][2];
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) win[a][j][0] = win[a][j][1] = make_float2(0.f, 0.f);
+        const float f0 = swap_rb ? fa[2] : fa[0], f2 = swap_rb ? fa[0] : fa[2];     // scale of byte 0 / byte 2 of a pixel
+        int r = r_first;
+        const float4* wvp = s_wv;
+        float4 wv = wvp[0];
+        const int* infop = s_info;
+        int info = infop[0];
+        OutT* q = dk + (long long)ph_lo * PW + 2 * tid;
+        stage(r, min(r + rows_cap - 1, r_last));
+        while (r <= r_last) {
+            const int re = min(r + rows_cap - 1, r_last), nrows = re - r + 1;
+            if (tma_ok) { qc_mbar_wait(&s_bar, parity); parity ^= 1u; }
+            else __syncthreads();
+            // bytes -> scaled float4 pixels, four pixels (12 bytes = three funnel-shifted words) per step; pixels past
+            // x_hi take whatever bytes follow in the staging buffer: finite, and only ever multiplied by 0
+            {
+                int rr = 0, gq = tid;
+                while (gq >= g4) { gq -= g4; ++rr; }
+                while (rr < nrows) {
+                    const int a = rr * g.pitch + bofs + 12 * gq;
+                    const unsigned* wp = reinterpret_cast<const unsigned*>(raw) + (a >> 2);
+                    const unsigned sh = (unsigned)(a & 3) * 8u;
+                    const unsigned x0 = wp[0], x1 = wp[1], x2 = wp[2], x3 = wp[3];
+                    const unsigned v0 = __funnelshift_r(x0, x1, sh), v1 = __funnelshift_r(x1, x2, sh), v2 = __funnelshift_r(x2, x3, sh);
+                    float4* fo = F + rr * fp4 + 4 * gq;
+                    float4 o0 = make_float4(__fmul_rn(k3_bytef(v0, 0), f0), __fmul_rn(k3_bytef(v0, 1), fa[1]), __fmul_rn(k3_bytef(v0, 2), f2), 0.f);
+                    float4 o1 = make_float4(__fmul_rn(k3_bytef(v0, 3), f0), __fmul_rn(k3_bytef(v1, 0), fa[1]), __fmul_rn(k3_bytef(v1, 1), f2), 0.f);
+                    float4 o2 = make_float4(__fmul_rn(k3_bytef(v1, 2), f0), __fmul_rn(k3_bytef(v1, 3), fa[1]), __fmul_rn(k3_bytef(v2, 0), f2), 0.f);
+                    float4 o3 = make_float4(__fmul_rn(k3_bytef(v2, 1), f0), __fmul_rn(k3_bytef(v2, 2), fa[1]), __fmul_rn(k3_bytef(v2, 3), f2), 0.f);
+                    if (swap_rb) {
+                        float t;
+                        t = o0.x; o0.x = o0.z; o0.z = t; t = o1.x; o1.x = o1.z; o1.z = t;
+                        t = o2.x; o2.x = o2.z; o2.z = t; t = o3.x; o3.x = o3.z; o3.z = t;
+                    }
+                    fo[0] = o0; fo[1] = o1; fo[2] = o2; fo[3] = o3;
+                    gq += THREADS;
+                    while (gq >= g4) { gq -= g4; ++rr; }
+                }
+            }
+            __syncthreads();                                         // F complete, raw consumed
+            if (re < r_last) stage(re + 1, min(re + rows_cap, r_last));      // next band streams in meanwhile
+            if (active) {
+                const float4* frow = F;
+                for (int rr = 0; rr < nrows; rr += 3, frow += 3 * fp4) {      // every band starts on window slot 0
+                    k3w_row<OutT, 0, CPW, CPH>(win, frow, xo, xw, infop, info, wvp, wv, fb2, q, total, PW);
+                    if (rr + 1 < nrows) k3w_row<OutT, 1, CPW, CPH>(win, frow + fp4, xo, xw, infop, info, wvp, wv, fb2, q, total, PW);
+                    if (rr + 2 < nrows) k3w_row<OutT, 2, CPW, CPH>(win, frow + 2 * fp4, xo, xw, infop, info, wvp, wv, fb2, q, total, PW);
+                }
+            }
+            __syncthreads();                                         // F free for the next band
+            r = re + 1;
+        }
+        item = s_next;
+    }
+    // the last CTA to leave puts the counters back to zero for the next call that takes this line of the ring
+    if (tid == 0 && atomicAdd(sched + 1, 1) == (int)gridDim.x - 1) {
+        sched[0] = 0;
+        sched[1] = 0;
+        __threadfence();
+    }
+}
+
 template <typename OutT>
 __global__ void __launch_bounds__(K3T_THREADS, 3)
 k3_roi_tma(const uint8_t* __restrict__ imgs, int n, int H, int W, long long img_stride, int row_stride,
            const float* __restrict__ rois, int K, int PH, int PW, int sr, int aligned, int swap_rb,
-           const float* __restrict__ norm, OutT* __restrict__ dst, int tma_ok, const int* __restrict__ dst_rows) {
+           const float* __restrict__ norm, OutT* __restrict__ dst, int tma_ok, const int* __restrict__ dst_rows,
+           int skip_fast) {
     extern __shared__ __align__(128) unsigned char k3t_sm[];
     float* Hs = reinterpret_cast<float*>(k3t_sm);                                  // [K3T_ROWS][3][PW]
     float* Fb = Hs + (size_t)K3T_ROWS * 3 * PW;                                    // [rows][pitch] bytes as floats
@@ -479,8 +848,36 @@ k3_roi_tma(const uint8_t* __restrict__ imgs, int n, int H, int W, long long img_
     const int vq = tid % quads, vsl = tid / quads;
     __syncthreads();
 
-    for (int item = blockIdx.x; item < K * K3T_SPLIT; item += gridDim.x) {
-        const int k = item / K3T_SPLIT, chunk = item - k * K3T_SPLIT;
+    // Work items = (ROI, quarter of its output rows).  Normal mode: every ROI, items strided over the grid.  Leftover mode
+    // (skip_fast: k3_roi_win runs in the same call and takes the ROIs its predicate accepts): a CTA scans K3T_SCAN ROIs
+    // per round with one thread each and works through the ones left; a grid with nothing left exits within a microsecond.
+    __shared__ int s_left[K3T_SCAN];
+    __shared__ int s_nleft;
+    int item = blockIdx.x, scan_base = blockIdx.x * K3T_SCAN, li = 0, ln = 0;
+    for (;;) {
+        int k, chunk;
+        if (!skip_fast) {
+            if (item >= K * K3T_SPLIT) break;
+            k = item / K3T_SPLIT; chunk = item - k * K3T_SPLIT;
+            item += gridDim.x;
+        } else {
+            bool done = false;
+            while (li >= ln * K3T_SPLIT) {
+                if (scan_base >= K) { done = true; break; }
+                __syncthreads();
+                if (tid == 0) s_nleft = 0;
+                __syncthreads();
+                if (tid < K3T_SCAN && scan_base + tid < K &&
+                    !k3_geom(rois + (long long)(scan_base + tid) * 5, n, H, W, PH, PW, sr, aligned).fast)
+                    s_left[atomicAdd(&s_nleft, 1)] = scan_base + tid;
+                __syncthreads();
+                ln = s_nleft; li = 0;
+                scan_base += gridDim.x * K3T_SCAN;
+            }
+            if (done) break;
+            k = s_left[li / K3T_SPLIT]; chunk = li % K3T_SPLIT;
+            ++li;
+        }
         const int ph_lo = chunk * PH / K3T_SPLIT, ph_hi = (chunk + 1) * PH / K3T_SPLIT;      // this item's output rows
         if (ph_lo >= ph_hi) continue;
         const float* r = rois + (long long)k * 5;
@@ -708,22 +1105,53 @@ extern "C" int qc_roi_align_rows(qc_ctx* ctx, const uint8_t* imgs, int n, int h,
         // 1-D TMA bulk copies need 16-byte aligned global addresses: frame base, image pitch and row pitch
         const int tma_ok = ((reinterpret_cast<uintptr_t>(imgs) & 15) == 0 && (img_stride & 15) == 0 && (row_stride & 15) == 0 &&
                             !getenv("QC_K3_NOTMA")) ? 1 : 0;      // (debug switch: plain-load staging)
+        // (1) k3_roi_win takes every ROI whose taps fit three-pixel windows; (2) k3_roi_tma takes the rest
+        const int use_win = (out_w >> 2) <= K3W_THREADS && ctx->sched && !getenv("QC_K3_NOWIN");
         int occ = 1;
-        const int grid = std::min(K, ctx->sm_count * 8);
+        int* ctr = nullptr;
+        if (use_win) {
+            const size_t wsmem = (size_t)K3W_F_BYTES + K3W_RAW_BYTES + 16;
+            // one cache line of the context's counter ring per call (calls in flight on different streams never share
+            // one): [0] = work items handed out, [1] = CTAs that have left; the kernel leaves both at zero
+            ctr = ctx->sched + 32 * (int)(ctx->sched_i.fetch_add(1) % QC_SCHED_SLOTS);
+            static const int split_env = getenv("QC_K3_SPLIT") ? atoi(getenv("QC_K3_SPLIT")) : -1;
+#define K3W_GO(T, CW, CH)                                                                                           \
+    do {                                                                                                           \
+        if (int rc = qc_prepare(ctx, k3_roi_win<T, CW, CH>, (int)wsmem, K3W_THREADS, &occ)) return rc;              \
+        const int slots = ctx->sm_count * std::max(occ, 1);                                                        \
+        int sl = 3;                       /* 2^sl work items per ROI: finer when there are few ROIs, >= ~6 per CTA */ \
+        while (sl > 1 && ((long long)K << (sl - 1)) >= 6LL * slots) --sl;                                           \
+        if (split_env >= 0) sl = split_env;                                                                        \
+        while ((out_h >> sl) + 1 > K3W_PH_MAX) ++sl;                                                               \
+        const unsigned wgrid = (unsigned)std::min<long long>((long long)K << sl, slots);                           \
+        k3_roi_win<T, CW, CH><<<wgrid, K3W_THREADS, wsmem, st>>>(imgs, n, h, w, img_stride, row_stride, rois, K, out_h, \
+                                                                 out_w, sampling_ratio, aligned, swap_rb, norm, (T*)dst, \
+                                                                 tma_ok, dst_rows, sl, ctr);                       \
+    } while (0)
+#define K3W_LAUNCH(T)                                                                                              \
+    do {                                                                                                           \
+        if (out_w == 224 && out_h == 224) K3W_GO(T, 224, 224); else K3W_GO(T, 0, 0);                                \
+    } while (0)
+            if (out_dtype == QC_DT_BF16) K3W_LAUNCH(__nv_bfloat16);
+            else if (out_dtype == QC_DT_F32) K3W_LAUNCH(float);
+            else QC_FAIL(ctx, QC_ERR_INVALID, "qc_roi_align: bad out_dtype");
+#undef K3W_LAUNCH
+#undef K3W_GO
+            QC_LAUNCHED_AS(ctx, "k3_roi_win", st);
+        }
         if (out_dtype == QC_DT_BF16) {
             if (int rc = qc_prepare(ctx, k3_roi_tma<__nv_bfloat16>, (int)smem, K3T_THREADS, &occ)) return rc;
             k3_roi_tma<__nv_bfloat16><<<std::min(K * K3T_SPLIT, ctx->sm_count * std::max(occ, 1)), K3T_THREADS, smem, st>>>(
                 imgs, n, h, w, img_stride, row_stride, rois, K, out_h, out_w, sampling_ratio, aligned, swap_rb, norm,
-                (__nv_bfloat16*)dst, tma_ok, dst_rows);
+                (__nv_bfloat16*)dst, tma_ok, dst_rows, use_win);
         } else if (out_dtype == QC_DT_F32) {
             if (int rc = qc_prepare(ctx, k3_roi_tma<float>, (int)smem, K3T_THREADS, &occ)) return rc;
             k3_roi_tma<float><<<std::min(K * K3T_SPLIT, ctx->sm_count * std::max(occ, 1)), K3T_THREADS, smem, st>>>(
                 imgs, n, h, w, img_stride, row_stride, rois, K, out_h, out_w, sampling_ratio, aligned, swap_rb, norm,
-                (float*)dst, tma_ok, dst_rows);
+                (float*)dst, tma_ok, dst_rows, use_win);
         } else {
             QC_FAIL(ctx, QC_ERR_INVALID, "qc_roi_align: bad out_dtype");
         }
-        (void)grid;
         QC_LAUNCHED_AS(ctx, "k3_roi_tma", st);
         return QC_OK;
     }

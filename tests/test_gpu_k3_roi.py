@@ -64,7 +64,8 @@ def _check(qc, imgs_t, imgs_np, rois, **kw):
     out16 = qc.roi_align(imgs_t, torch.from_numpy(rois).cuda(), **kw)
     # bf16: within 1 ulp of the RNE-rounded reference.  Where (v/255 - mean)/std cancels to |v| < 2^-10 a bf16 ulp
     # (< 8e-6) is finer than float32 accumulation-order noise (~3e-7 absolute); there the absolute bar applies, 16x
-    # tighter than the float32 one.  Such elements are counted and must stay below 1e-5 of the outputs.
+    # tighter than the float32 one.  Such elements are counted and must stay below 2e-5 of the outputs (the window
+    # kernel scales the staged pixels by 1/(count*div*std) before the two passes: one more rounding per tap).
     def key(t_):
         i = t_.detach().cpu().contiguous().view(torch.int16).to(torch.int32) & 0xFFFF
         return torch.where(i >= 0x8000, 0x8000 - i, i)
@@ -72,7 +73,7 @@ def _check(qc, imgs_t, imgs_np, rois, **kw):
     far = (key(out16) - key(r16)).abs() > 1
     if far.any():
         assert (ref[far].abs() < 2 ** -10).all() and (out16.cpu().float()[far] - ref[far]).abs().max() <= 2 ** -14
-        assert int(far.sum()) <= 1e-5 * far.numel() + 2, int(far.sum())
+        assert int(far.sum()) <= 2e-5 * far.numel() + 2, int(far.sum())
 
 
 def test_roi_align_staged_path_geometries(qc):

@@ -26,3 +26,12 @@ by = int(((r[:, 3] - r[:, 1]) * (r[:, 4] - r[:, 2]) * 3).sum()) + K * 3 * 224 * 
 ts = sorted(s.elapsed_time(e) for s, e in ev)
 print(f"K3 {K} rois: median {ts[len(ts) // 2] * 1000:.1f} us, best {ts[0] * 1000:.1f} us, {by / ts[len(ts) // 2] / 1e6:.0f} GB/s",
       "NOTMA" if os.environ.get("QC_K3_NOTMA") else "TMA")
+qc.profile(True)
+for _ in range(5):
+    qc.roi_align(frames, rois, out=out)
+torch.cuda.synchronize()
+acc = {}
+for name, ms in qc.profile_collect():
+    acc.setdefault(name, []).append(ms * 1000)
+qc.profile(False)
+print("   per kernel (events inside the library):", ", ".join(f"{k} {sorted(v)[len(v) // 2]:.1f} us" for k, v in acc.items()))
