@@ -363,7 +363,8 @@ constexpr int K3T_ROWS = 12;               // source rows per band held as Hs
 constexpr int K3T_RAW = 6 * 1024;          // raw byte staging buffer (floats: 4x)
 constexpr int K3T_PH_MAX = 256;
 constexpr int K3T_SPLIT = 4;                // work items per ROI (quarters of its output rows): balance across CTAs
-constexpr int K3T_SCAN = 8;                 // ROIs a CTA examines per round in leftover mode
+constexpr int K3T_SPLIT_LEFT = 16;          // ... in leftover mode
+constexpr int K3T_LEFT_MAX = 1024;          // ROIs of one leftover list (leftover mode works through the table in passes)
 
 struct K3Taps { int i[4]; float w[4]; int n; };
 
@@ -471,7 +472,6 @@ constexpr int K3W_ROWS = 9;                    // source rows per band (a multip
 constexpr int K3W_PH_MAX = 128;                // output rows per work item
 constexpr int K3W_SRC_MAX = 272;               // source rows per work item (128 * 1.95 + slack)
 constexpr float K3W_BIN_MAX = 1.95f;
-constexpr int K3W_THREADS = 64;
 
 struct K3Geom {
     int img, x_lo, x_hi, b0, pitch;
@@ -554,14 +554,18 @@ __device__ __forceinline__ float2 k3_lo(const float4& v) { return make_float2(v.
 __device__ __forceinline__ float2 k3_hi(const float4& v) { return make_float2(v.z, v.w); }
 __device__ __forceinline__ float2 k3_dup(float v) { return make_float2(v, v); }
 
+// F rows are swizzled in groups of four pixels (slot = p ^ ((p >> 3) & 3)): the conversion's four float4 stores per
+// thread (64 bytes apart between lanes) and the horizontal pass's loads at even pixel strides spread over all banks
+__device__ __forceinline__ int k3_swz(int p) { return p ^ ((p >> 3) & 3); }
+
 // one output row from the register window: rows A (r-2, only if THREE), B (r-1), C (r)
-template <typename OutT, bool THREE, int CPW, int CPH>
-__device__ __forceinline__ void k3w_emit(const float2 (&A)[4][2], const float2 (&B)[4][2], const float2 (&C)[4][2], const float4 wv,
+template <typename OutT, bool THREE, int CPW, int CPH, int NC>
+__device__ __forceinline__ void k3w_emit(const float2 (&A)[NC][2], const float2 (&B)[NC][2], const float2 (&C)[NC][2], const float4 wv,
                                          const float2 (&fb2)[2], OutT* q, long long total, int half) {
-    float2 o[4][2];
+    float2 o[NC][2];
     const float2 w0 = k3_dup(wv.x), w1 = k3_dup(wv.y), w2 = k3_dup(wv.z);
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
+    for (int j = 0; j < NC; ++j)
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
             o[j][e] = k3_fma2(w1, B[j][e], k3_fma2(w2, C[j][e], fb2[e]));
@@ -570,7 +574,7 @@ __device__ __forceinline__ void k3w_emit(const float2 (&A)[4][2], const float2 (
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
+        for (int e = 0; e < NC / 2; ++e) {
             const float v0 = c == 0 ? o[2 * e][0].x : (c == 1 ? o[2 * e][0].y : o[2 * e][1].x);
             const float v1 = c == 0 ? o[2 * e + 1][0].x : (c == 1 ? o[2 * e + 1][0].y : o[2 * e + 1][1].x);
             OutT* qe = q + c * total + (CPW ? e * (CPW / 2) : e * half);
@@ -588,15 +592,15 @@ __device__ __forceinline__ void k3w_emit(const float2 (&A)[4][2], const float2 (
 // splits into two FFMA2 operands), then the output rows whose last tapped source row this is: `info` = n3 | n2 << 8,
 // at most one three-row output (the one straddling source row r-1) followed by n2 two-row outputs.  CPW / CPH > 0: the
 // output shape is a compile-time constant, so every store address is the running row pointer + an immediate.
-template <typename OutT, int SLOT, int CPW, int CPH>
-__device__ __forceinline__ void k3w_row(float2 (&win)[3][4][2], const float4* __restrict__ frow, const int (&xo)[4],
-                                        const float (&xw)[4][3], const int*& infop, int& info, const float4*& wvp, float4& wv,
+template <typename OutT, int SLOT, int CPW, int CPH, int NC>
+__device__ __forceinline__ void k3w_row(float2 (&win)[3][NC][2], const float4* __restrict__ frow, const int (&xo)[NC][3],
+                                        const float (&xw)[NC][3], const int*& infop, int& info, const float4*& wvp, float4& wv,
                                         const float2 (&fb2)[2], OutT*& q, int total_rt, int PW_rt) {
     const int PW = CPW ? CPW : PW_rt;
     const long long total = CPW ? (long long)CPW * CPH : (long long)total_rt;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const float4 p0 = frow[xo[j]], p1 = frow[xo[j] + 1], p2 = frow[xo[j] + 2];
+    for (int j = 0; j < NC; ++j) {
+        const float4 p0 = frow[xo[j][0]], p1 = frow[xo[j][1]], p2 = frow[xo[j][2]];
         const float2 w0 = k3_dup(xw[j][0]), w1 = k3_dup(xw[j][1]), w2 = k3_dup(xw[j][2]);
         win[SLOT][j][0] = k3_fma2(w2, k3_lo(p2), k3_fma2(w1, k3_lo(p1), k3_mul2(w0, k3_lo(p0))));
         win[SLOT][j][1] = k3_fma2(w2, k3_hi(p2), k3_fma2(w1, k3_hi(p1), k3_mul2(w0, k3_hi(p0))));
@@ -605,12 +609,12 @@ __device__ __forceinline__ void k3w_row(float2 (&win)[3][4][2], const float4* __
     const int n3 = info & 255, n2 = info >> 8;
     info = *++infop;                                                // next source row's counts (sentinel behind the last)
     for (int e = 0; e < n3; ++e) {
-        k3w_emit<OutT, true, CPW, CPH>(win[S1], win[S2], win[SLOT], wv, fb2, q, total, PW >> 1);
+        k3w_emit<OutT, true, CPW, CPH, NC>(win[S1], win[S2], win[SLOT], wv, fb2, q, total, PW >> 1);
         wv = *++wvp;                                                // next output row's weights (sentinel behind the last)
         q += PW;
     }
     for (int e = 0; e < n2; ++e) {
-        k3w_emit<OutT, false, CPW, CPH>(win[S1], win[S2], win[SLOT], wv, fb2, q, total, PW >> 1);
+        k3w_emit<OutT, false, CPW, CPH, NC>(win[S1], win[S2], win[SLOT], wv, fb2, q, total, PW >> 1);
         wv = *++wvp;
         q += PW;
     }
@@ -618,13 +622,15 @@ __device__ __forceinline__ void k3w_row(float2 (&win)[3][4][2], const float4* __
 
 __device__ __forceinline__ float k3_bytef(unsigned v, int k) { return (float)((v >> (8 * k)) & 255u); }
 
-template <typename OutT, int CPW, int CPH>
-__global__ void __launch_bounds__(K3W_THREADS, 8)
+// NC = output columns per thread: 4 (two pairs half a row apart, 64-thread CTAs) or 2 (one pair, 128-thread CTAs: twice
+// the warps per work item for the same staging buffers)
+template <typename OutT, int CPW, int CPH, int NC>
+__global__ void __launch_bounds__(256 / NC, NC == 4 ? 8 : 5)
 k3_roi_win(const uint8_t* __restrict__ imgs, int n, int H, int W, long long img_stride, int row_stride,
            const float* __restrict__ rois, int K, int PH_rt, int PW_rt, int sr, int aligned, int swap_rb,
            const float* __restrict__ norm, OutT* __restrict__ dst, int tma_ok, const int* __restrict__ dst_rows, int split_log2,
            int* __restrict__ sched) {
-    constexpr int THREADS = K3W_THREADS;
+    constexpr int THREADS = 256 / NC;
     extern __shared__ __align__(128) unsigned char k3w_sm[];
     float4* F = reinterpret_cast<float4*>(k3w_sm);                       // [rows][fp4] scaled float pixels
     uint8_t* raw = k3w_sm + K3W_F_BYTES;                                 // [rows][pitch] (+16 bytes of slack)
@@ -635,7 +641,7 @@ k3_roi_win(const uint8_t* __restrict__ imgs, int n, int H, int W, long long img_
     const int PH = CPH ? CPH : PH_rt, PW = CPW ? CPW : PW_rt;
     const int tid = threadIdx.x;
     const int total = PH * PW;
-    const int half = PW >> 1, npair = PW >> 2;                        // threads that own columns
+    const int half = PW >> 1, npair = PW / NC;                        // threads that own columns
     const bool active = tid < npair;
     const float isr = k3_isr(sr);
     float fa[3];
@@ -679,16 +685,18 @@ k3_roi_win(const uint8_t* __restrict__ imgs, int n, int H, int W, long long img_
         OutT* const dk = dst + (long long)(dst_rows ? dst_rows[k] : k) * 3 * total;
         // ---- per-item tables -----------------------------------------------------------------------------------
         bool wide = false;
-        int xo[4];
-        float xw[4][3];
+        int xo[NC][3];                                               // swizzled F slots of the column's three pixels
+        float xw[NC][3];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < NC; ++j) {
             const int col = 2 * tid + (j >> 1) * half + (j & 1);
             int first = g.x_lo, last;
             xw[j][0] = xw[j][1] = xw[j][2] = 0.f;
             if (active) k3_window(g.x1, g.bin_w, col, sr, isr, W, first, last, xw[j][0], xw[j][1], xw[j][2], wide);
-            xo[j] = first - g.x_lo;
-            if (xo[j] < 0 || first > g.x_hi) wide = true;
+            const int o = first - g.x_lo;
+            if (o < 0 || first > g.x_hi) wide = true;
+#pragma unroll
+            for (int d = 0; d < 3; ++d) xo[j][d] = k3_swz(o + d);
         }
         for (int i = tid; i <= nout; i += THREADS) {
             if (i == nout) {                                         // sentinel (read ahead, never used)
@@ -734,11 +742,14 @@ k3_roi_win(const uint8_t* __restrict__ imgs, int n, int H, int W, long long img_
         auto stage = [&](int r0, int r1) {
             const int nrows = r1 - r0 + 1;
             if (tma_ok) {
-                if (tid == 0) {
-                    qc_fence_proxy_async();
-                    qc_mbar_expect_tx(&s_bar, (uint32_t)(nrows * g.pitch));
-                    for (int rr = 0; rr < nrows; ++rr)
-                        qc_bulk_g2s(raw + rr * g.pitch, base + (long long)(r0 + rr) * row_stride + g.b0, (uint32_t)g.pitch, &s_bar);
+                if (tid < 32) {                                      // lane rr issues the copy of row rr (nrows <= 9)
+                    if (tid == 0) {
+                        qc_fence_proxy_async();
+                        qc_mbar_expect_tx(&s_bar, (uint32_t)(nrows * g.pitch));
+                    }
+                    __syncwarp();
+                    if (tid < nrows)
+                        qc_bulk_g2s(raw + tid * g.pitch, base + (long long)(r0 + tid) * row_stride + g.b0, (uint32_t)g.pitch, &s_bar);
                 }
             } else {
                 const int valid = min(g.pitch, 3 * W - g.b0);        // never read past the row's pixels
@@ -748,11 +759,11 @@ k3_roi_win(const uint8_t* __restrict__ imgs, int n, int H, int W, long long img_
                 }
             }
         };
-        float2 win[3][4][2];
+        float2 win[3][NC][2];
 #pragma unroll
         for (int a = 0; a < 3; ++a)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) win[a][j][0] = win[a][j][1] = make_float2(0.f, 0.f);
+            for (int j = 0; j < NC; ++j) win[a][j][0] = win[a][j][1] = make_float2(0.f, 0.f);
         const float f0 = swap_rb ? fa[2] : fa[0], f2 = swap_rb ? fa[0] : fa[2];     // scale of byte 0 / byte 2 of a pixel
         int r = r_first;
         const float4* wvp = s_wv;
@@ -786,7 +797,8 @@ k3_roi_win(const uint8_t* __restrict__ imgs, int n, int H, int W, long long img_
                         t = o0.x; o0.x = o0.z; o0.z = t; t = o1.x; o1.x = o1.z; o1.z = t;
                         t = o2.x; o2.x = o2.z; o2.z = t; t = o3.x; o3.x = o3.z; o3.z = t;
                     }
-                    fo[0] = o0; fo[1] = o1; fo[2] = o2; fo[3] = o3;
+                    const int sw = (gq >> 1) & 3;                    // k3_swz of pixels 4*gq .. 4*gq+3
+                    fo[sw] = o0; fo[1 ^ sw] = o1; fo[2 ^ sw] = o2; fo[3 ^ sw] = o3;
                     gq += THREADS;
                     while (gq >= g4) { gq -= g4; ++rr; }
                 }
@@ -796,9 +808,9 @@ k3_roi_win(const uint8_t* __restrict__ imgs, int n, int H, int W, long long img_
             if (active) {
                 const float4* frow = F;
                 for (int rr = 0; rr < nrows; rr += 3, frow += 3 * fp4) {      // every band starts on window slot 0
-                    k3w_row<OutT, 0, CPW, CPH>(win, frow, xo, xw, infop, info, wvp, wv, fb2, q, total, PW);
-                    if (rr + 1 < nrows) k3w_row<OutT, 1, CPW, CPH>(win, frow + fp4, xo, xw, infop, info, wvp, wv, fb2, q, total, PW);
-                    if (rr + 2 < nrows) k3w_row<OutT, 2, CPW, CPH>(win, frow + 2 * fp4, xo, xw, infop, info, wvp, wv, fb2, q, total, PW);
+                    k3w_row<OutT, 0, CPW, CPH, NC>(win, frow, xo, xw, infop, info, wvp, wv, fb2, q, total, PW);
+                    if (rr + 1 < nrows) k3w_row<OutT, 1, CPW, CPH, NC>(win, frow + fp4, xo, xw, infop, info, wvp, wv, fb2, q, total, PW);
+                    if (rr + 2 < nrows) k3w_row<OutT, 2, CPW, CPH, NC>(win, frow + 2 * fp4, xo, xw, infop, info, wvp, wv, fb2, q, total, PW);
                 }
             }
             __syncthreads();                                         // F free for the next band
@@ -848,37 +860,51 @@ k3_roi_tma(const uint8_t* __restrict__ imgs, int n, int H, int W, long long img_
     const int vq = tid % quads, vsl = tid / quads;
     __syncthreads();
 
-    // Work items = (ROI, quarter of its output rows).  Normal mode: every ROI, items strided over the grid.  Leftover mode
-    // (skip_fast: k3_roi_win runs in the same call and takes the ROIs its predicate accepts): a CTA scans K3T_SCAN ROIs
-    // per round with one thread each and works through the ones left; a grid with nothing left exits within a microsecond.
-    __shared__ int s_left[K3T_SCAN];
-    __shared__ int s_nleft;
-    int item = blockIdx.x, scan_base = blockIdx.x * K3T_SCAN, li = 0, ln = 0;
+    // Work items = (ROI, quarter of its output rows), strided over the grid.  Normal mode: every ROI.  Leftover mode
+    // (skip_fast: k3_roi_win runs in the same call and takes the ROIs its predicate accepts): every CTA scans the ROI
+    // table (one thread per ROI, K3T_THREADS per round) and compacts the ROIs left IN ORDER, so all CTAs hold the same
+    // list and stride over its items; a table with nothing left costs a microsecond.
+    __shared__ int s_left[K3T_LEFT_MAX];
+    __shared__ int s_wcnt[K3T_THREADS / 32];
+    // leftover mode: the boxes left are the big ones (down-scaled, up to the whole frame): finer items
+    const int nsplit = skip_fast ? K3T_SPLIT_LEFT : K3T_SPLIT;
+    int item = blockIdx.x, scan_k = 0, ln = 0;          // leftover mode: `item` indexes the current list
     for (;;) {
         int k, chunk;
         if (!skip_fast) {
-            if (item >= K * K3T_SPLIT) break;
-            k = item / K3T_SPLIT; chunk = item - k * K3T_SPLIT;
+            if (item >= K * nsplit) break;
+            k = item / nsplit; chunk = item - k * nsplit;
             item += gridDim.x;
         } else {
             bool done = false;
-            while (li >= ln * K3T_SPLIT) {
-                if (scan_base >= K) { done = true; break; }
-                __syncthreads();
-                if (tid == 0) s_nleft = 0;
-                __syncthreads();
-                if (tid < K3T_SCAN && scan_base + tid < K &&
-                    !k3_geom(rois + (long long)(scan_base + tid) * 5, n, H, W, PH, PW, sr, aligned).fast)
-                    s_left[atomicAdd(&s_nleft, 1)] = scan_base + tid;
-                __syncthreads();
-                ln = s_nleft; li = 0;
-                scan_base += gridDim.x * K3T_SCAN;
+            while (item >= ln * nsplit) {
+                if (scan_k >= K) { done = true; break; }
+                item -= ln * nsplit;                            // position in the next list
+                ln = 0;
+                __syncthreads();                                    // the previous list is consumed
+                while (scan_k < K && ln + K3T_THREADS <= K3T_LEFT_MAX) {
+                    const int kk = scan_k + tid;
+                    const bool left = kk < K && !k3_geom(rois + (long long)kk * 5, n, H, W, PH, PW, sr, aligned).fast;
+                    const unsigned bal = __ballot_sync(0xffffffffu, left);
+                    if ((tid & 31) == 0) s_wcnt[tid >> 5] = __popc(bal);
+                    __syncthreads();
+                    int before = ln, tot = 0;
+#pragma unroll
+                    for (int wi = 0; wi < K3T_THREADS / 32; ++wi) {
+                        if (wi < (tid >> 5)) before += s_wcnt[wi];
+                        tot += s_wcnt[wi];
+                    }
+                    if (left) s_left[before + __popc(bal & ((1u << (tid & 31)) - 1u))] = kk;
+                    __syncthreads();
+                    ln += tot;
+                    scan_k += K3T_THREADS;
+                }
             }
             if (done) break;
-            k = s_left[li / K3T_SPLIT]; chunk = li % K3T_SPLIT;
-            ++li;
+            k = s_left[item / nsplit]; chunk = item % nsplit;
+            item += gridDim.x;
         }
-        const int ph_lo = chunk * PH / K3T_SPLIT, ph_hi = (chunk + 1) * PH / K3T_SPLIT;      // this item's output rows
+        const int ph_lo = chunk * PH / nsplit, ph_hi = (chunk + 1) * PH / nsplit;      // this item's output rows
         if (ph_lo >= ph_hi) continue;
         const float* r = rois + (long long)k * 5;
         const int img = (int)r[0];
@@ -1106,7 +1132,7 @@ extern "C" int qc_roi_align_rows(qc_ctx* ctx, const uint8_t* imgs, int n, int h,
         const int tma_ok = ((reinterpret_cast<uintptr_t>(imgs) & 15) == 0 && (img_stride & 15) == 0 && (row_stride & 15) == 0 &&
                             !getenv("QC_K3_NOTMA")) ? 1 : 0;      // (debug switch: plain-load staging)
         // (1) k3_roi_win takes every ROI whose taps fit three-pixel windows; (2) k3_roi_tma takes the rest
-        const int use_win = (out_w >> 2) <= K3W_THREADS && ctx->sched && !getenv("QC_K3_NOWIN");
+        const int use_win = (out_w >> 2) <= 64 && ctx->sched && !getenv("QC_K3_NOWIN");
         int occ = 1;
         int* ctr = nullptr;
         if (use_win) {
@@ -1115,22 +1141,25 @@ extern "C" int qc_roi_align_rows(qc_ctx* ctx, const uint8_t* imgs, int n, int h,
             // one): [0] = work items handed out, [1] = CTAs that have left; the kernel leaves both at zero
             ctr = ctx->sched + 32 * (int)(ctx->sched_i.fetch_add(1) % QC_SCHED_SLOTS);
             static const int split_env = getenv("QC_K3_SPLIT") ? atoi(getenv("QC_K3_SPLIT")) : -1;
-#define K3W_GO(T, CW, CH)                                                                                           \
+            static const int nc_env = getenv("QC_K3_NC") ? atoi(getenv("QC_K3_NC")) : 4;
+#define K3W_GO(T, CW, CH, NC)                                                                                       \
     do {                                                                                                           \
-        if (int rc = qc_prepare(ctx, k3_roi_win<T, CW, CH>, (int)wsmem, K3W_THREADS, &occ)) return rc;              \
+        constexpr int K3W_TH = 256 / NC;                                                                           \
+        if (int rc = qc_prepare(ctx, k3_roi_win<T, CW, CH, NC>, (int)wsmem, K3W_TH, &occ)) return rc;               \
         const int slots = ctx->sm_count * std::max(occ, 1);                                                        \
         int sl = 3;                       /* 2^sl work items per ROI: finer when there are few ROIs, >= ~6 per CTA */ \
         while (sl > 1 && ((long long)K << (sl - 1)) >= 6LL * slots) --sl;                                           \
         if (split_env >= 0) sl = split_env;                                                                        \
         while ((out_h >> sl) + 1 > K3W_PH_MAX) ++sl;                                                               \
         const unsigned wgrid = (unsigned)std::min<long long>((long long)K << sl, slots);                           \
-        k3_roi_win<T, CW, CH><<<wgrid, K3W_THREADS, wsmem, st>>>(imgs, n, h, w, img_stride, row_stride, rois, K, out_h, \
-                                                                 out_w, sampling_ratio, aligned, swap_rb, norm, (T*)dst, \
-                                                                 tma_ok, dst_rows, sl, ctr);                       \
+        k3_roi_win<T, CW, CH, NC><<<wgrid, K3W_TH, wsmem, st>>>(imgs, n, h, w, img_stride, row_stride, rois, K, out_h,  \
+                                                                out_w, sampling_ratio, aligned, swap_rb, norm, (T*)dst, \
+                                                                tma_ok, dst_rows, sl, ctr);                        \
     } while (0)
 #define K3W_LAUNCH(T)                                                                                              \
     do {                                                                                                           \
-        if (out_w == 224 && out_h == 224) K3W_GO(T, 224, 224); else K3W_GO(T, 0, 0);                                \
+        if (out_w == 224 && out_h == 224) { if (nc_env == 2) K3W_GO(T, 224, 224, 2); else K3W_GO(T, 224, 224, 4); }  \
+        else K3W_GO(T, 0, 0, 4);                                                                                   \
     } while (0)
             if (out_dtype == QC_DT_BF16) K3W_LAUNCH(__nv_bfloat16);
             else if (out_dtype == QC_DT_F32) K3W_LAUNCH(float);

@@ -12,7 +12,14 @@ K = int(os.environ.get("K3_ROIS", 512))
 r = np.zeros((K, 5), np.float32)
 r[:, 0] = rng.integers(0, 16, K)
 r[:, 1] = rng.integers(0, 500, K); r[:, 2] = rng.integers(0, 500, K)
-r[:, 3] = r[:, 1] + rng.integers(40, 120, K); r[:, 4] = r[:, 2] + rng.integers(40, 120, K)
+if os.environ.get("K3_MIX"):
+    # the bench step's box sizes: sides (l + r) * stride with l, r in 0.5..7.5 cells, strides 8 / 16 / 32 at 0.6 / 0.3 / 0.1
+    st = rng.choice([8, 16, 32], K, p=[0.6, 0.3, 0.1])
+    bw = ((rng.integers(1, 8, K) + rng.integers(1, 8, K)) * st).clip(8, 600); bh = ((rng.integers(1, 8, K) + rng.integers(1, 8, K)) * st).clip(8, 600)
+    r[:, 1] = (rng.random(K) * (640 - bw)).astype(np.int32); r[:, 2] = (rng.random(K) * (640 - bh)).astype(np.int32)
+    r[:, 3] = r[:, 1] + bw; r[:, 4] = r[:, 2] + bh
+else:
+    r[:, 3] = r[:, 1] + rng.integers(40, 120, K); r[:, 4] = r[:, 2] + rng.integers(40, 120, K)
 rois = torch.from_numpy(r).cuda()
 out = torch.empty((K, 3, 224, 224), dtype=torch.bfloat16, device="cuda")
 for _ in range(3):
