@@ -454,18 +454,23 @@ __device__ __noinline__ void k3_roi_direct(const uint8_t* base, bool img_ok, int
 // k3_roi_win: the common case -- every sample inside the frame and bins <= 1.95 source pixels, i.e. the merged taps of
 // an output coordinate lie in a window of THREE consecutive source pixels (two samples at most ~0.98 apart).  Both
 // passes then run in registers with fixed-size windows and no intermediate image in shared memory:
-//   work item = (ROI, slice of its output rows), one 64-thread CTA at a time (persistent, ~8 CTAs per SM);
-//   thread    = two pairs of adjacent output columns (2t, 2t+1, 2t+PW/2, 2t+PW/2+1); x windows (first source pixel + 3
+//   work item = (ROI, 1/2^sl of its output rows), handed to 64-thread CTAs (8 per SM) through a global counter -- the
+//               boxes of a batch differ 10x in source area; the last CTA to leave zeroes the counter again;
+//   thread    = two pairs of adjacent output columns (2t, 2t+1, 2t+PW/2, 2t+PW/2+1); x windows (three F slots + three
 //               weights per column) live in registers;
-//   per band of source rows: one TMA bulk copy per row (16-byte aligned superset of the tapped segment) -> bytes
-//               converted ONCE to float4 pixels already scaled by 1/(count*div*std) (swap_rb folded in);
-//   per source row: horizontal pass = 3 LDS.128 + 9 FMA per column into a rotating three-row register window;
-//               every output row whose last tapped source row this is gets emitted straight from the window:
+//   per band of <= 9 source rows: one TMA bulk copy per row (16-byte aligned superset of the tapped segment, lane rr
+//               issues row rr) -> bytes converted ONCE, four pixels per step, to float4 pixels already scaled by
+//               1/(count*div*std) (swap_rb folded in); F rows are XOR-swizzled in groups of four pixels;
+//   per source row: horizontal pass = 3 LDS.128 + 6 FFMA2 per column (sm_100 packed fp32: the float4 pixel is two
+//               channel pairs) into a rotating three-row register window; then the output rows whose LAST tapped
+//               source row this is -- at most one three-row output (the one straddling r-1) and n two-row outputs, the
+//               counts tabulated per source row -- straight from the window:
 //               out = B + w0*row[-2] + w1*row[-1] + w2*row[0]  (B = -mean/std; no separate normalisation pass),
-//               bf16x2 / float2 stores (a warp writes 128 / 256 contiguous bytes per channel and pair).
-// Compared with k3_roi_tma (Hs in shared memory): ~3x less shared-memory traffic, no barriers inside a band.
-// Everything else (boxes leaving the frame, larger bins) is left to k3_roi_tma, which skips what this kernel took;
-// both evaluate the same scalar predicate k3_geom().fast.
+//               bf16x2 / float2 stores at immediate offsets from one running pointer (224x224 is a compile-time shape);
+//               a warp writes 128 / 256 contiguous bytes per channel and pair.
+// Everything else (boxes leaving the frame, larger bins) is left to k3_roi_tma, which in the same call scans the table
+// for what this kernel's scalar predicate k3_geom().fast rejects (nothing left: a microsecond).
+// 512 boxes of ~80x80: 135.7 us (round 1, k3_roi_sep) -> 89 us (k3_roi_tma) -> 64 us; 1400 such boxes 142 us = 3.1 TB/s.
 constexpr int K3W_F_BYTES = 20 * 1024;         // float4 pixels of one band
 constexpr int K3W_RAW_BYTES = 4 * 1024;        // staged bytes of one band
 constexpr int K3W_ROWS = 9;                    // source rows per band (a multiple of 3; fewer for wide boxes)
@@ -1141,7 +1146,6 @@ extern "C" int qc_roi_align_rows(qc_ctx* ctx, const uint8_t* imgs, int n, int h,
             // one): [0] = work items handed out, [1] = CTAs that have left; the kernel leaves both at zero
             ctr = ctx->sched + 32 * (int)(ctx->sched_i.fetch_add(1) % QC_SCHED_SLOTS);
             static const int split_env = getenv("QC_K3_SPLIT") ? atoi(getenv("QC_K3_SPLIT")) : -1;
-            static const int nc_env = getenv("QC_K3_NC") ? atoi(getenv("QC_K3_NC")) : 4;
 #define K3W_GO(T, CW, CH, NC)                                                                                       \
     do {                                                                                                           \
         constexpr int K3W_TH = 256 / NC;                                                                           \
@@ -1158,7 +1162,7 @@ extern "C" int qc_roi_align_rows(qc_ctx* ctx, const uint8_t* imgs, int n, int h,
     } while (0)
 #define K3W_LAUNCH(T)                                                                                              \
     do {                                                                                                           \
-        if (out_w == 224 && out_h == 224) { if (nc_env == 2) K3W_GO(T, 224, 224, 2); else K3W_GO(T, 224, 224, 4); }  \
+        if (out_w == 224 && out_h == 224) K3W_GO(T, 224, 224, 4);  /* (2 columns per thread: 10 % slower) */        \
         else K3W_GO(T, 0, 0, 4);                                                                                   \
     } while (0)
             if (out_dtype == QC_DT_BF16) K3W_LAUNCH(__nv_bfloat16);
