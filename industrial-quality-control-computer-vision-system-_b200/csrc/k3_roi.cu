@@ -638,7 +638,7 @@ k3_roi_win(const uint8_t* __restrict__ imgs, int n, int H, int W, long long img_
     constexpr int THREADS = 256 / NC;
     extern __shared__ __align__(128) unsigned char k3w_sm[];
     float4* F = reinterpret_cast<float4*>(k3w_sm);                       // [rows][fp4] scaled float pixels
-    uint8_t* raw = k3w_sm + K3W_F_BYTES;                                 // [rows][pitch] (+16 bytes of slack)
+    uint8_t* raw = k3w_sm + K3W_F_BYTES;                                 // [rows][pitch] (+32 bytes of slack)
     __shared__ float4 s_wv[K3W_PH_MAX + 1];       // per output row of the item: weights of source rows last-2, last-1, last
     __shared__ int s_info[K3W_SRC_MAX + 1];       // per source row of the item: n3 | n2 << 8 output rows ending there
     __shared__ __align__(8) uint64_t s_bar;
@@ -1141,7 +1141,7 @@ extern "C" int qc_roi_align_rows(qc_ctx* ctx, const uint8_t* imgs, int n, int h,
         int occ = 1;
         int* ctr = nullptr;
         if (use_win) {
-            const size_t wsmem = (size_t)K3W_F_BYTES + K3W_RAW_BYTES + 16;
+            const size_t wsmem = (size_t)K3W_F_BYTES + K3W_RAW_BYTES + 32;     // the four-pixel conversion reads <= 19 bytes past a row
             // one cache line of the context's counter ring per call (calls in flight on different streams never share
             // one): [0] = work items handed out, [1] = CTAs that have left; the kernel leaves both at zero
             ctr = ctx->sched + 32 * (int)(ctx->sched_i.fetch_add(1) % QC_SCHED_SLOTS);

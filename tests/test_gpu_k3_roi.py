@@ -119,3 +119,34 @@ def test_roi_align_large_frames(qc):
     rois[2] = [0, 0, 1000, 2048, 1040]
     rois[3] = [0, 5, 5, 1500, 1800]
     _check(qc, torch.from_numpy(imgs).cuda(), imgs, rois)
+
+
+def test_roi_align_window_and_leftover_kernels_share_a_call(qc):
+    """One call = k3_roi_win (bins <= 1.95) + k3_roi_tma over what is left: 1250 boxes of which ~1100 are wider or taller
+    than 437 px (more than one 1024-entry leftover list), the rest small, scattered destination rows; bins on both
+    sides of the 1.95 bound, boxes on the frame border."""
+    from qcgraft import synth
+    rng = np.random.default_rng(26)
+    imgs = synth.make_frames(44, 2)
+    t = torch.from_numpy(imgs).cuda()
+    K = 1250
+    r = np.zeros((K, 5), np.float32)
+    r[:, 0] = rng.integers(0, 2, K)
+    big = rng.random(K) < 0.88
+    w = np.where(big, rng.integers(438, 641, K), rng.integers(3, 437, K))
+    h = np.where(rng.random(K) < 0.5, rng.integers(3, 437, K), rng.integers(3, 641, K))
+    r[:, 1] = (rng.random(K) * (640 - w + 1)).astype(np.int32); r[:, 2] = (rng.random(K) * (640 - h + 1)).astype(np.int32)
+    r[:, 3] = r[:, 1] + w; r[:, 4] = r[:, 2] + h
+    r[5] = [0, 0, 0, 436.8, 436.8]             # bin 1.95 exactly on the bound
+    r[6] = [1, 203.2, 203.2, 640, 640]
+    r[7] = [0, 0, 0, 437, 437]
+    rows = rng.permutation(K + 50)[:K].astype(np.int32)
+    out = torch.zeros((K + 50, 3, 224, 224), dtype=torch.float32, device="cuda")
+    qc.roi_align(t, torch.from_numpy(r).cuda(), out=out, dst_rows=torch.from_numpy(rows).cuda())
+    got = out.cpu()
+    for a in range(0, K, 250):
+        ref = oroi.roi_align_normalize(imgs, r[a:a + 250])
+        d = (got[rows[a:a + 250]] - ref).abs().flatten(1).max(1).values
+        assert d.max() <= 1e-3, f"roi {a + int(d.argmax())}: {d.max()}"
+    untouched = np.setdiff1d(np.arange(K + 50), rows)
+    assert float(got[untouched].abs().max()) == 0.0
