@@ -40,7 +40,9 @@ typedef enum {
     QC_ERR_UNSUPPORTED = -4
 } qc_status;
 
-/* ---- context ------------------------------------------------------------ */
+/* ---- context ------------------------------------------------------------
+ * qc_create allocates 8 KB of device memory on `device` (a ring of zeroed work counters for the kernels that hand
+ * out work items dynamically; a call takes the next 128-byte line and leaves it at zero); qc_destroy frees it.     */
 int qc_create(int device, qc_ctx** out);
 void qc_destroy(qc_ctx* ctx);
 const char* qc_last_error(const qc_ctx* ctx);
@@ -147,7 +149,10 @@ int qc_nms(qc_ctx* ctx, const float* boxes, const float* scores, const int32_t* 
  * Implements the hand-off models/ensemble.py:129-142,181-195 only mocks: each kept box is
  * cropped/resampled to [3,out_h,out_w] with torchvision.ops.roi_align semantics
  * (spatial_scale=1) and normalised through the same LUT mechanism as K1.
- * imgs: n images uint8 HWC; rois: device float32 [K][5] = (img, x1, y1, x2, y2).        */
+ * imgs: n images uint8 HWC; rois: device float32 [K][5] = (img, x1, y1, x2, y2).
+ * sampling_ratio 1..2, out_w % 4 == 0, out_w <= 224: two launches per call -- k3_roi_win (boxes whose bins are <= 1.95
+ * source pixels with every sample inside the frame) and k3_roi_tma (whatever is left); other shapes: k3_roi_sep /
+ * k3_roi_align.  Results do not depend on which kernel took a box beyond float32 rounding (<= 1e-3 absolute).      */
 int qc_roi_align(qc_ctx* ctx, const uint8_t* imgs, int n, int h, int w, int64_t img_stride,
                  int32_t row_stride, const float* rois, int K, int out_h, int out_w,
                  int sampling_ratio, int aligned, int swap_rb, const float* norm,
