@@ -725,7 +725,14 @@ def main():
         roofline = {"bound": "hbm", "kernel": f"{kdom} (longest single kernel launch of the step: "
                     f"{100 * kv['share_of_own_kernel_time']:.0f} % of own-kernel time, CUDA events around every launch "
                     "inside the library; kernel_times lists every kernel)",
-                    "achieved": kv["gbs"], "peak": peak, "unit": "GB/s", "frac": kv["frac"], "traffic": None,
+                    "achieved": kv["gbs"], "peak": peak, "unit": "GB/s", "frac": kv["frac"],
+                    # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch, ncu --set full
+                    # (profiles/r02_ncu_full_summary.md): k3_roi_win on 1400 boxes of the step's size distribution
+                    # (tools/k3_case.py K3_MIX=1; 479 MB algorithmic there: 37.6 MB read = the tapped row segments once,
+                    # 369.7 MB of the 421 MB of outputs written back by kernel end, the rest still in L2)
+                    "traffic": 407300000 if kdom == "k3_roi_win" else None,
+                    "traffic_note": "ncu capture of tools/k3_case.py K3_MIX=1 K3_ROIS=1400 (same kernel, same box-size "
+                                    "distribution, 479 MB algorithmic): no re-reads" if kdom == "k3_roi_win" else None,
                     "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": kv["algorithmic_bytes_per_step"] / kv["launches_per_step"],
                     "ms_per_launch": kv["ms_per_step"] / kv["launches_per_step"]}
