@@ -150,3 +150,16 @@ def test_roi_align_window_and_leftover_kernels_share_a_call(qc):
         assert d.max() <= 1e-3, f"roi {a + int(d.argmax())}: {d.max()}"
     untouched = np.setdiff1d(np.arange(K + 50), rows)
     assert float(got[untouched].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("hw,aligned,sr", [((112, 112), False, 2), ((56, 64), True, 2), ((224, 224), True, 1), ((96, 32), False, 1)])
+def test_roi_align_window_kernel_other_shapes(qc, hw, aligned, sr):
+    """The run-time-shape instance of k3_roi_win (out_w % 4 == 0, not 224x224), aligned=True, sampling_ratio 1 and 2."""
+    from qcgraft import synth
+    rng = np.random.default_rng(27)
+    imgs = synth.make_frames(45, 2)
+    rois = _rois(rng, 2, 640, 640, 80)
+    rois[0] = [0, 0, 0, 640, 640]
+    rois[1] = [1, 600, 600, 640, 640]
+    rois[2] = [0, 10.25, 20.5, 90.75, 61.5]
+    _check(qc, torch.from_numpy(imgs).cuda(), imgs, rois, out_hw=hw, aligned=aligned, sampling_ratio=sr)
