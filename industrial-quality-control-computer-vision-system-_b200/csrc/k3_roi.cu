@@ -1151,8 +1151,10 @@ extern "C" int qc_roi_align_rows(qc_ctx* ctx, const uint8_t* imgs, int n, int h,
         constexpr int K3W_TH = 256 / NC;                                                                           \
         if (int rc = qc_prepare(ctx, k3_roi_win<T, CW, CH, NC>, (int)wsmem, K3W_TH, &occ)) return rc;               \
         const int slots = ctx->sm_count * std::max(occ, 1);                                                        \
-        int sl = 3;                       /* 2^sl work items per ROI: finer when there are few ROIs, >= ~6 per CTA */ \
-        while (sl > 1 && ((long long)K << (sl - 1)) >= 6LL * slots) --sl;                                           \
+        /* 2^sl work items per box: 8, or 4 once there are ~9 quarter-boxes per resident CTA (measured on the bench  \
+           step's box sizes: 1400 boxes 250 / 228 us at sl = 2 / 3, 3000 boxes equal, 5441 boxes 597 / 629 us; halves    \
+           of boxes lose to the big boxes' imbalance at every size) */                                             \
+        int sl = ((long long)K << 2) >= 9LL * slots ? 2 : 3;                                                        \
         if (split_env >= 0) sl = split_env;                                                                        \
         while ((out_h >> sl) + 1 > K3W_PH_MAX) ++sl;                                                               \
         const unsigned wgrid = (unsigned)std::min<long long>((long long)K << sl, slots);                           \
