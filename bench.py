@@ -28,6 +28,7 @@ One JSON line on stdout (rank 0):
   kernels      per-kernel achieved GB/s on their own BASELINE configs (K1 cfg2, K2 cfg3, K3, K3b, K4 cfg4, K7),
                measured after the timed region with L2-defeating rotation
   cfg1_latency batch-1 latency of QualityControlDetector.predict (N=1 only)
+  dropin_batch images/s of QualityControlDetector.predict_batch (host numpy frames -> reference result dictionaries, N=1 only)
   cpu_baseline the oracle port of the reference CPU path on the host cores (bounded sample): the reference's work
                (mock ROI classification, models/ensemble.py:181-195); `same_work_cpu` = with a real ResNet-50 pass per ROI
 --impl reference times only that CPU path (rank 0; other ranks exit).
@@ -481,6 +482,38 @@ def cfg1_latency(calls: int = 60, warm: int = 8):
             "path": "QualityControlDetector.predict (YOLOv8n + ResNet-50, CUDA-graph nets, rule engine on)"}
 
 
+def dropin_batch_rate(scale: str, batch: int = 64, calls: int = 4, warm: int = 2):
+    """The same workload through the reference's OWN call signature: QualityControlDetector.predict_batch(list of host
+    numpy frames) -> list of reference result dictionaries (inference/detector.py:128-180), i.e. host frames in,
+    detections / classification / segmentation / rule engine / quality grade dictionaries out."""
+    from qcgraft import synth
+    from qcgraft.detector import QualityControlDetector
+    cfg = {"model": {"confidence_threshold": 0.7, "nms_threshold": 0.5},
+           "quality_control": {"defect_classes": ["crack", "scratch", "dent", "discoloration", "contamination"]},
+           "qcgraft": {"yolo_scale": scale, "device": torch.cuda.current_device(), "synthetic_weights": True,
+                       "max_batch": batch}}
+    d = QualityControlDetector("synthetic", "synthetic", cfg)
+    d.ensemble_predictor.yolo_detector.model.zero_detect_bias()
+    imgs = [synth.make_frame(8000 + i) for i in range(batch)]
+    inj = [l.cuda().to(torch.bfloat16) for l in synth.make_head(8100, batch, IMGSZ, IMGSZ, CANDS_PER_IMAGE)]
+    ts, ndet = [], 0
+    for k in range(warm + calls):
+        t = time.perf_counter()
+        rs = d.predict_batch(imgs, _inject=inj)
+        dt = time.perf_counter() - t
+        bad = [r["error"] for r in rs if "error" in r]
+        if bad:
+            return {"error": bad[0]}
+        if k >= warm:
+            ts.append(dt)
+            ndet += sum(len(r["detections"]) for r in rs)
+    return {"value": batch * len(ts) / sum(ts), "unit": UNIT, "batch": batch, "calls": len(ts),
+            "ms_per_call_min": 1000 * min(ts), "ms_per_call_max": 1000 * max(ts),
+            "detections_per_image_after_rules": ndet / (batch * len(ts)),
+            "path": "QualityControlDetector.predict_batch: host numpy frames -> reference result dictionaries "
+                    "(one device batch per call, rule chain on the device, dictionaries assembled on the host)"}
+
+
 def main():
     _capture_stdout()
     ap = argparse.ArgumentParser()
@@ -790,6 +823,11 @@ def main():
             line["cfg1_latency"] = cfg1_latency()
         except Exception as e:
             line["cfg1_latency"] = {"error": str(e)}
+        try:
+            torch.cuda.empty_cache()
+            line["dropin_batch"] = dropin_batch_rate(cfg["yolo"], B if B <= 64 else 64)
+        except Exception as e:
+            line["dropin_batch"] = {"error": str(e)}
     if world == 1 and not args.no_cpu_baseline:
         try:
             torch.set_num_threads(len(os.sched_getaffinity(0)))

@@ -1006,7 +1006,19 @@ class QualityControlDetector:
                 processed = [self._preprocess_image(im) for im in images]
                 frames_np = [_as_rgb3(im) for im in processed]
                 shapes = [im.shape for im in processed]
-            batch_dev = torch.from_numpy(np.stack(frames_np)).to(pipe.dev)
+            # one pinned staging tensor per batch shape (kept: page-locking costs milliseconds): the frames are copied
+            # into it once and the pipeline uploads it asynchronously on its copy stream
+            key = (len(frames_np),) + tuple(frames_np[0].shape)
+            cache = self.__dict__.setdefault("_stage_cache", {})
+            stage = cache.get(key)
+            if stage is None:
+                if len(cache) >= 4:
+                    cache.clear()
+                stage = cache[key] = torch.empty(key, dtype=torch.uint8, pin_memory=True)
+            view = stage.numpy()
+            for i, f in enumerate(frames_np):
+                np.copyto(view[i], f)
+            batch_dev = stage
         res = pipe.run(batch_dev, head_override=head_override, inject=inject,
                        include_segmentation=include_segmentation,
                        keep_seg_tensors=include_segmentation, processed=not raw_ok)

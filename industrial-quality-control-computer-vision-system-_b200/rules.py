@@ -415,7 +415,8 @@ class DeviceDetectionRules(DetectionRules):
             for r in (seg or {}).get("segmented_regions", []):
                 regions.setdefault(r.get("detection_id"), r)
             ok = len(raw) > 0
-            exts = []
+            exts, tups = [], []
+            no_ext = (-1, -1, -1, -1)
             for i, det in enumerate(raw):
                 sev = SEVERITY_ORDER.get(det.get("severity", "minor"))
                 cid = class_ids.setdefault(det["class"], len(class_ids))
@@ -423,26 +424,24 @@ class DeviceDetectionRules(DetectionRules):
                 if sev is None or cid >= 64 or bb["width"] != bb["x2"] - bb["x1"] or bb["height"] != bb["y2"] - bb["y1"]:
                     ok = False                           # a table the kernel does not model: the host form below
                     break
-                row = rows[a, i]
-                row["x1"], row["y1"], row["x2"], row["y2"] = bb["x1"], bb["y1"], bb["x2"], bb["y2"]
-                row["cls"], row["severity"] = cid, sev
-                row["conf"] = float(_conf_of(det)) if ("ensemble_confidence" in det or "confidence" in det) else 0.0
+                conf = float(_conf_of(det)) if ("ensemble_confidence" in det or "confidence" in det) else 0.0
                 r = regions.get(i)
                 ext = None
                 if r:
-                    row["has_seg"] = 1
-                    row["seg_conf"] = r.get("confidence_score", 0.0)
-                    row["area_pixels"] = r.get("area_pixels", 0)
-                    row["area_pct"] = r.get("area_percentage", 0.0)
-                    row["compactness"] = r.get("compactness", 0.0)
                     ext = self.mask_extent(r.get("mask"))
-                    if ext is not None:
-                        row["ext"] = [int(v) for v in ext]
+                    # one tuple per row in RULES_ROW_DTYPE's field order (a single structured assignment per image)
+                    tups.append((bb["x1"], bb["y1"], bb["x2"], bb["y2"], cid, sev, 1, 0,
+                                 tuple(int(v) for v in ext) if ext is not None else no_ext, r.get("area_pixels", 0), conf,
+                                 r.get("confidence_score", 0.0), r.get("area_percentage", 0.0), r.get("compactness", 0.0)))
+                else:
+                    tups.append((bb["x1"], bb["y1"], bb["x2"], bb["y2"], cid, sev, 0, 0, no_ext, 0, conf, 0.0, 0.0, 0.0))
                 exts.append(ext)
             if not ok:
                 out[a] = super().process(raw, seg, shape) if raw else []
                 prepared.append(None)
                 continue
+            if tups:
+                rows[a, :len(tups)] = np.array(tups, dtype=ffi.RULES_ROW_DTYPE)
             count[a] = len(raw)
             shapes[a] = shape[0], shape[1]
             prepared.append((regions, exts))
@@ -457,9 +456,12 @@ class DeviceDetectionRules(DetectionRules):
                 continue
             regions, exts = prepared[a]
             refined = []
+            # plain tuples instead of numpy records: (x1, y1, x2, y2, severity, kept, area_pixels)
+            ref_l = res["refined"][a, :len(raw)].tolist()
             for i, det in enumerate(raw):                       # the dictionaries of _refine_detections (:111-184)
                 d = det.copy()
-                rf = res["refined"][a, i]
+                t = ref_l[i]
+                rf = {"x1": t[0], "y1": t[1], "x2": t[2], "y2": t[3], "severity": t[4], "area_pixels": t[6]}
                 r = regions.get(i)
                 if r:
                     d.update({"segmentation_confidence": r.get("confidence_score", 0.0), "area_pixels": r.get("area_pixels", 0),
@@ -478,8 +480,9 @@ class DeviceDetectionRules(DetectionRules):
                 refined.append(d)
             member = res["member"][a, :len(raw)]
             final = []
-            for j in range(int(res["count"][a])):
-                o = res["rows"][a, j]
+            keys = ("base", "merged_from", "x1", "y1", "x2", "y2", "severity", "flags", "area_pixels", "conf", "validation_score")
+            for j, t in enumerate(res["rows"][a, :int(res["count"][a])].tolist()):
+                o = dict(zip(keys, t))
                 d = refined[int(o["base"])]
                 if o["merged_from"] > 1:                        # _merge_detection_cluster (:305-358)
                     idx = np.nonzero(member == j)[0]
