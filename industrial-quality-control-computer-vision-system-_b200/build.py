@@ -14,7 +14,7 @@ SOURCES = ["api.cu", "k1_preprocess.cu", "k2_yolo.cu", "k3_roi.cu", "k3b_resize.
 # -fmad=false: the parity-critical float paths must not be contracted into FMAs (the reference's
 # CPU libraries are not); these kernels are memory-bound so nothing is lost.
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-fmad=false", "-Xcompiler", "-fPIC"]
+              "-fmad=false", "-Xcompiler", "-fPIC"] + os.environ.get("QC_NVCC_EXTRA", "").split()
 
 
 def _nvcc() -> str:

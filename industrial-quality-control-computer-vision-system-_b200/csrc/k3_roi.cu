@@ -553,8 +553,16 @@ __device__ __forceinline__ void k3_window(float start, float bin, int p, int sr,
 }
 
 // packed two-lane float32 arithmetic (sm_100 FFMA2 / FMUL2: one issue slot for two multiply-adds)
+#ifdef K3_SCALAR_FMA
+__device__ __forceinline__ float2 k3_fma2(float2 a, float2 b, float2 c) { return make_float2(__fmaf_rn(a.x, b.x, c.x), __fmaf_rn(a.y, b.y, c.y)); }
+#else
 __device__ __forceinline__ float2 k3_fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+#endif
+#ifdef K3_SCALAR_FMA
+__device__ __forceinline__ float2 k3_mul2(float2 a, float2 b) { return make_float2(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y)); }
+#else
 __device__ __forceinline__ float2 k3_mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
+#endif
 __device__ __forceinline__ float2 k3_lo(const float4& v) { return make_float2(v.x, v.y); }
 __device__ __forceinline__ float2 k3_hi(const float4& v) { return make_float2(v.z, v.w); }
 __device__ __forceinline__ float2 k3_dup(float v) { return make_float2(v, v); }
