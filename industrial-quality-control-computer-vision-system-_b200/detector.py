@@ -524,7 +524,13 @@ class _LazyFullMask:
     def extent(self):
         """(y_min, y_max, x_min, x_max) of mask > 0 in frame coordinates, or None -- what
         inference/postprocess.py:784-790 reads off the full-frame mask, without materialising it."""
-        m = self._local > 0
+        loc = self._local
+        if loc.dtype == np.uint8 and loc.ndim == 2 and loc.flags.c_contiguous:
+            x, y, w, h = cv2.boundingRect(loc)                     # bounding box of the non-zero pixels
+            if w == 0 or h == 0:
+                return None
+            return y + self._y1, y + h - 1 + self._y1, x + self._x1, x + w - 1 + self._x1
+        m = loc > 0
         rows = np.flatnonzero(m.any(1))
         if rows.size == 0:
             return None
@@ -1028,12 +1034,19 @@ class QualityControlDetector:
         if res.seg is not None:
             for g in res.seg:
                 m = g["seg"]["mask"].cpu().numpy()
-                for j, k in enumerate(g["idx"]):
-                    r = g["seg"]["regions"][j]
-                    o = int(r.out_offset)
-                    masks_host[int(k)] = m[o:o + int(r.w) * int(r.h)].reshape(int(r.h), int(r.w))
+                regs = g["seg"]["regions"]
+                offs, ws, hs = regs["out_offset"].tolist(), regs["w"].tolist(), regs["h"].tolist()
+                for j, k in enumerate(np.asarray(g["idx"]).tolist()):
+                    o = offs[j]
+                    masks_host[k] = m[o:o + ws[j] * hs[j]].reshape(hs[j], ws[j])
         per_image = (time.time() - t0) / n
         out, pending = [], []
+        # plain Python numbers for the per-ROI scalars (numpy scalar indexing costs ~100 ns a piece, x 10 per ROI)
+        roi_det_l, roi_box_l = res.roi_det.tolist(), res.roi_box.tolist()
+        seg_method_l = res.seg_method.tolist() if getattr(res, "seg_method", None) is not None else None
+        seg_area_l = res.seg_area.tolist() if getattr(res, "seg_area", None) is not None else None
+        seg_sums_l = res.seg_sums.tolist() if getattr(res, "seg_sums", None) is not None else None
+        seg_cont_l = res.seg_contours.tolist() if getattr(res, "seg_contours", None) is not None else None
         for i in range(n):
             try:
                 rows = res.det[i, :int(res.count[i])]
@@ -1043,8 +1056,8 @@ class QualityControlDetector:
                                 "image_shape": tuple(shape[:2]), "total_detections": len(dets)}
                 resnet_results = rcls._result(res.global_probs[i])
                 resnet_results["inference_time_ms"] = per_image * 1000
-                ks = np.nonzero(res.roi_img == i)[0]
-                roi_probs = {int(res.roi_det[k]): res.roi_probs[k] for k in ks} if res.roi_probs is not None else {}
+                ks = np.nonzero(res.roi_img == i)[0].tolist()
+                roi_probs = {roi_det_l[k]: res.roi_probs[k] for k in ks} if res.roi_probs is not None else {}
                 ensemble_results = ens._combine_predictions(yolo_results, resnet_results, shape, None, _roi_probs=roi_probs)
                 ensemble_results["total_inference_time_ms"] = per_image * 1000
                 if "error" in ensemble_results:
@@ -1054,14 +1067,14 @@ class QualityControlDetector:
                 if include_segmentation and dets:
                     sel, lm, ar, sm, cs_ = [], {}, {}, {}, {}
                     for k in ks:
-                        x1, y1, x2, y2 = (int(v) for v in res.roi_box[k])
-                        code = int(res.seg_method[k])
-                        name = seg._select_segmentation_method(dets[int(res.roi_det[k])]["class"])
+                        x1, y1, x2, y2 = roi_box_l[k]
+                        code = seg_method_l[k]
+                        name = seg._select_segmentation_method(dets[roi_det_l[k]]["class"])
                         name = name if name in ("adaptive", "threshold") else "threshold_fallback"
                         j = len(sel)
-                        sel.append((int(res.roi_det[k]), x1, y1, x2, y2, name))
-                        lm[j], ar[j], sm[j] = masks_host[int(k)], int(res.seg_area[k]), res.seg_sums[k]
-                        cs_[j] = res.seg_contours[k]
+                        sel.append((roi_det_l[k], x1, y1, x2, y2, name))
+                        lm[j], ar[j], sm[j] = masks_host[k], seg_area_l[k], seg_sums_l[k]
+                        cs_[j] = seg_cont_l[k]
                         assert (code == ffi.QC_SEG_REF_ADAPTIVE) == (name == "adaptive")
                     segmentation_results = seg._assemble(frames_np[i], dets, sel, lm, ar, sm, bgr=raw_ok, cstats=cs_)
                 out.append(None)
@@ -1078,6 +1091,13 @@ class QualityControlDetector:
         except Exception as e:
             logger.error(f"Error in QC prediction: {str(e)}")
             finals = [{"error": str(e)} for _ in pending]
+        if not self.__dict__.get("_gc_frozen") and _qcfg(self.config).get("gc_freeze", True):
+            # The nets, CUDA graphs and plans built by the first pass are long-lived: move them out of the collector's
+            # reach once, or every few calls a full collection walks ~10^5 objects (80 ms on a 64-frame batch call).
+            import gc
+            gc.collect()
+            gc.freeze()
+            self._gc_frozen = True
         per_image = (time.time() - t0) / n
         for (i, _), final in zip(pending, finals):
             self._update_performance_stats(per_image)
