@@ -396,7 +396,7 @@ def _mb_k4(qc, peak, rng, time_call, out):
     by = 16 * 6 * 2048 * 2048 + 20 * ncomp
     out["k4_segment_cfg4"] = {"bytes": by, "ms": med, "gbs": by / med / 1e6, "frac": by / med / 1e6 / peak,
                               "components": ncomp,
-                              "note": "11 launches; union-find merge/rank phases are L2 / shared-memory latency bound"}
+                              "note": "10 launches; union-find merge/rank phases are L2 / shared-memory latency bound"}
 
 
 def _mb_k7(qc, peak, rng, time_call, out):

@@ -23,8 +23,7 @@
 //                first-contact links + pointer jumping, unions only for the remaining contacts
 //   k4_border    unions across band borders (atomicMin in L2, roots = min block index)
 //   k4_compress  path compression + per-1024-block root counts
-//   k4_scan      exclusive scan of the counts per region -> chunk bases, ncomp
-//   k4_rank      root -> label (1-based rank in block-raster order)
+//   k4_rank      root -> label (1-based rank in block-raster order; sums the earlier chunks' root counts itself), ncomp
 //   k4_stats     parent -> label in place; per-label area / bbox via run-aggregated atomics
 //   k4_final     int32 labels + u8 mask (min-area filter applied), kept area (from the stats rows alone when no
 //                pixel output is wanted), bbox -> (x,y,w,h)
@@ -990,56 +989,26 @@ k4_compress(const qc_seg_region* __restrict__ regs, int R, int total_chunks, con
     }
 }
 
-__global__ void __launch_bounds__(1024)
-k4_scan(const qc_seg_region* __restrict__ regs, int R, const int* __restrict__ chunk_count,
-        int* __restrict__ chunk_base, int* __restrict__ out_ncomp) {
-    __shared__ int s_w[32];
-    __shared__ int s_carry;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int r = blockIdx.x; r < R; r += gridDim.x) {
-        const int c0 = regs[r].chunk_offset;
-        const int ncell = bh_of(regs[r]) * wpr_of(regs[r]);
-        const int nc = (ncell + K4_CHUNK - 1) / K4_CHUNK;
-        __syncthreads();
-        if (tid == 0) s_carry = 0;
-        __syncthreads();
-        for (int i0 = 0; i0 < nc; i0 += 1024) {
-            const int i = i0 + tid;
-            const int v = i < nc ? chunk_count[c0 + i] : 0;
-            int x = v;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
-            if (lane == 31) s_w[warp] = x;
-            __syncthreads();
-            if (warp == 0) {
-                int w = s_w[lane];
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += y; }
-                s_w[lane] = w;
-            }
-            __syncthreads();
-            const int incl = x + (warp ? s_w[warp - 1] : 0);
-            const int carry = s_carry;
-            if (i < nc) chunk_base[c0 + i] = carry + incl - v;
-            __syncthreads();
-            if (tid == 1023) s_carry = carry + incl;
-            __syncthreads();
-        }
-        if (tid == 0) out_ncomp[r] = s_carry + 1;     // labels incl. background, like cv2
-    }
-}
-
+// root -> label.  The number of labels before a chunk = the sum of the root counts of the region's earlier chunks
+// (k4_compress wrote them): every CTA adds those up itself -- at most a few hundred integers from L2 -- instead of
+// a separate scan kernel; the CTA of a region's last chunk also writes ncomp.
 __global__ void __launch_bounds__(K4_CHUNK)
 k4_rank(const qc_seg_region* __restrict__ regs, int R, int total_chunks, const int* __restrict__ g_chunk_off,
-        const unsigned* __restrict__ bits, const int* __restrict__ parent, const int* __restrict__ chunk_base,
-        int* __restrict__ rank) {
+        const unsigned* __restrict__ bits, const int* __restrict__ parent, const int* __restrict__ chunk_count,
+        int* __restrict__ rank, int* __restrict__ out_ncomp) {
     __shared__ int s_off[K4_LOC_MAX + 1];
     __shared__ int s_cnt[K4_CHUNK / 32];
+    __shared__ int s_pre[K4_CHUNK / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int* off = loc_load(s_off, g_chunk_off, R);
     for (int c = blockIdx.x; c < total_chunks; c += gridDim.x) {
         const int r = loc_find(off, R, c);
         const qc_seg_region rg = regs[r];
+        // labels of the region's earlier chunks
+        int pre = 0;
+        for (int i = rg.chunk_offset + tid; i < c; i += K4_CHUNK) pre += __ldg(chunk_count + i);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) pre += __shfl_xor_sync(0xffffffffu, pre, o);
         const Cell ce = load_cell(rg, bits, (c - rg.chunk_offset) * K4_CHUNK + tid);
         unsigned rootmask = 0;                                   // bit k: block k of the cell is a root
         unsigned m = ((ce.r0 | ce.r1) | ((ce.r0 | ce.r1) >> 1)) & 0x55555555u;
@@ -1054,16 +1023,20 @@ k4_rank(const qc_seg_region* __restrict__ regs, int R, int total_chunks, const i
         for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
         __syncthreads();
         if (lane == 31) s_cnt[warp] = x;
+        if (lane == 0) s_pre[warp] = pre;
         __syncthreads();
-        int prev = 0;
+        int prev = 0, base = 0, tot = 0;
 #pragma unroll
-        for (int k = 0; k < K4_CHUNK / 32; ++k) prev += (k < warp) ? s_cnt[k] : 0;
-        int next = chunk_base[c] + prev + x - cnt;               // labels before this cell
+        for (int k = 0; k < K4_CHUNK / 32; ++k) { prev += (k < warp) ? s_cnt[k] : 0; base += s_pre[k]; tot += s_cnt[k]; }
+        int next = base + prev + x - cnt;                        // labels before this cell
         while (rootmask) {
             const int k = __ffs(rootmask) - 1;
             rootmask &= rootmask - 1;
             rank[ce.base + k] = ++next;
         }
+        const int ncell = bh_of(rg) * wpr_of(rg);
+        if (tid == 0 && c == rg.chunk_offset + (ncell + K4_CHUNK - 1) / K4_CHUNK - 1)
+            out_ncomp[r] = base + tot + 1;                       // labels incl. background, like cv2
     }
 }
 
@@ -1368,10 +1341,8 @@ int seg_run(qc_ctx* ctx, int method, const uint8_t* imgs, const qc_seg_params* p
         return QC_OK;
     };
     auto label_tail = [&](const unsigned* bits) -> int {                            // cv2 numbering, stats, outputs
-        k4_scan<<<std::min(R, sms * 2), 1024, 0, st>>>(regions, R, w.chunk_count, w.chunk_base, o.ncomp);
-        QC_LAUNCHED_AS(ctx, "k4_scan", st);
-        k4_rank<<<chunk_grid, K4_CHUNK, 0, st>>>(regions, R, p->total_chunks, w.chunk_off, bits, w.parent, w.chunk_base,
-                                                 w.rank);
+        k4_rank<<<chunk_grid, K4_CHUNK, 0, st>>>(regions, R, p->total_chunks, w.chunk_off, bits, w.parent, w.chunk_count,
+                                                 w.rank, o.ncomp);
         QC_LAUNCHED_AS(ctx, "k4_rank", st);
         k4_stats<<<band_grid, K4_THREADS, 0, st>>>(regions, R, p->total_bands, w.band_off, bits, w.parent, w.rank,
                                                    o.stats);
