@@ -235,8 +235,8 @@ size_t qc_segment_workspace_bytes(const qc_seg_params* p);
  * (small) components are zeroed but the numbering is NOT compacted.
  * out_ncomp [num_regions]: number of labels incl. background (cv2's return value).
  * out_stats [total_stats_rows][5] int32 rows (x,y,w,h,area) at stats_offset + label
- * (label >= 1; row 0 of each region is zero); labels >= max_comp are counted but not
- * recorded (and never removed by min_area).  out_thr [num_regions] int32 Otsu threshold;
+ * (label >= 1; row 0 of each region is zero; rows at and past out_ncomp are not written); labels >= max_comp are
+ * counted but not recorded (and never removed by min_area).  out_thr [num_regions] int32 Otsu threshold;
  * out_area [num_regions] int64 kept foreground pixels (== np.sum(mask>0)).
  * out_mask / out_labels may be NULL to skip those writes.                               */
 int qc_segment(qc_ctx* ctx, const uint8_t* imgs, const qc_seg_params* p,

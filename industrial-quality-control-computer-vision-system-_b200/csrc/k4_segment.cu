@@ -143,6 +143,7 @@ __global__ void k4_init(const qc_seg_region* __restrict__ regs, int R, unsigned*
     for (int i = gid; i < R * 256; i += gsz) hist[i] = 0;
     for (int i = gid; i < R; i += gsz) out_area[i] = 0;
     // rows of (minx, miny, maxx, maxy, area) = (INT_MAX, INT_MAX, -1, -1, 0), written as one coalesced int stream
+    // (total_stats_rows == 0 when the labelling tail initialises the rows it hands out itself: k4_rank)
     const long long nints = (long long)total_stats_rows * 5;
     for (long long i = gid; i < nints; i += gsz) {
         const int c = (int)(i % 5);
@@ -995,7 +996,7 @@ k4_compress(const qc_seg_region* __restrict__ regs, int R, int total_chunks, con
 __global__ void __launch_bounds__(K4_CHUNK)
 k4_rank(const qc_seg_region* __restrict__ regs, int R, int total_chunks, const int* __restrict__ g_chunk_off,
         const unsigned* __restrict__ bits, const int* __restrict__ parent, const int* __restrict__ chunk_count,
-        int* __restrict__ rank, int* __restrict__ out_ncomp) {
+        int* __restrict__ rank, int* __restrict__ out_ncomp, int* __restrict__ stats) {
     __shared__ int s_off[K4_LOC_MAX + 1];
     __shared__ int s_cnt[K4_CHUNK / 32];
     __shared__ int s_pre[K4_CHUNK / 32];
@@ -1033,6 +1034,10 @@ k4_rank(const qc_seg_region* __restrict__ regs, int R, int total_chunks, const i
             const int k = __ffs(rootmask) - 1;
             rootmask &= rootmask - 1;
             rank[ce.base + k] = ++next;
+            if (next < rg.max_comp) {                            // the label's stats row: (minx, miny, maxx, maxy, area)
+                int* st = stats + ((long long)rg.stats_offset + next) * 5;
+                st[0] = INT_MAX; st[1] = INT_MAX; st[2] = -1; st[3] = -1; st[4] = 0;
+            }
         }
         const int ncell = bh_of(rg) * wpr_of(rg);
         if (tid == 0 && c == rg.chunk_offset + (ncell + K4_CHUNK - 1) / K4_CHUNK - 1)
@@ -1342,7 +1347,7 @@ int seg_run(qc_ctx* ctx, int method, const uint8_t* imgs, const qc_seg_params* p
     };
     auto label_tail = [&](const unsigned* bits) -> int {                            // cv2 numbering, stats, outputs
         k4_rank<<<chunk_grid, K4_CHUNK, 0, st>>>(regions, R, p->total_chunks, w.chunk_off, bits, w.parent, w.chunk_count,
-                                                 w.rank, o.ncomp);
+                                                 w.rank, o.ncomp, o.stats);
         QC_LAUNCHED_AS(ctx, "k4_rank", st);
         k4_stats<<<band_grid, K4_THREADS, 0, st>>>(regions, R, p->total_bands, w.band_off, bits, w.parent, w.rank,
                                                    o.stats);
@@ -1353,8 +1358,11 @@ int seg_run(qc_ctx* ctx, int method, const uint8_t* imgs, const qc_seg_params* p
         return QC_OK;
     };
 
-    k4_init<<<std::min(sms * 4, std::max(1, (p->total_stats_rows + 255) / 256)), 256, 0, st>>>(
-        regions, R, w.hist, o.stats, (long long*)o.area, p->total_stats_rows, w.band_off, w.chunk_off,
+    // stats rows: the labelling tail (composite, adaptive) initialises the rows of the labels it hands out; the threshold
+    // method's two rows per region are written by k7_emit / k7_finish from initialised sentinels
+    const int init_rows = method == QC_SEG_REF_THRESHOLD ? p->total_stats_rows : 0;
+    k4_init<<<std::min(sms * 4, std::max(1, (std::max(init_rows, R * 64) + 255) / 256)), 256, 0, st>>>(
+        regions, R, w.hist, o.stats, (long long*)o.area, init_rows, w.band_off, w.chunk_off,
         p->total_bands, p->total_chunks);
     QC_LAUNCHED_AS(ctx, "k4_init", st);
     if (p->channels == 3) {
