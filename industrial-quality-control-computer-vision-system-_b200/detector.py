@@ -1025,60 +1025,79 @@ class QualityControlDetector:
             for i, f in enumerate(frames_np):
                 np.copyto(view[i], f)
             batch_dev = stage
-        res = pipe.run(batch_dev, head_override=head_override, inject=inject,
-                       include_segmentation=include_segmentation,
-                       keep_seg_tensors=include_segmentation, processed=not raw_ok)
+        pend = pipe.run_async(batch_dev, head_override=head_override, inject=inject,
+                              include_segmentation=include_segmentation,
+                              keep_seg_tensors=include_segmentation, processed=not raw_ok)
         n = len(images)
-        # ROI rows of every image; packed masks come down once per method group
+        # ---- phase 1, while the classifier graphs are still running: the detections are on the host already (the
+        # pipeline planned its ROI tables from them), the segmentation finishes early on its own stream
+        res = pend.res
+        roi_det_l, roi_box_l = res.roi_det.tolist(), res.roi_box.tolist()
+        ks_of = [np.nonzero(res.roi_img == i)[0].tolist() for i in range(n)]
+        dets_of, errs = [None] * n, [None] * n
+        for i in range(n):
+            try:
+                dets_of[i] = ydet._parse_results(res.det[i, :int(res.count[i])], shapes[i])
+            except Exception as e:
+                errs[i] = e
+        res = pend.seg_result()
+        # ROI rows of every image; the packed masks of a method group came down in one (pinned, asynchronous) copy
         masks_host = {}
         if res.seg is not None:
             for g in res.seg:
-                m = g["seg"]["mask"].cpu().numpy()
+                m = g["mask_host"] if "mask_host" in g else g["seg"]["mask"].cpu().numpy()
                 regs = g["seg"]["regions"]
                 offs, ws, hs = regs["out_offset"].tolist(), regs["w"].tolist(), regs["h"].tolist()
                 for j, k in enumerate(np.asarray(g["idx"]).tolist()):
                     o = offs[j]
                     masks_host[k] = m[o:o + ws[j] * hs[j]].reshape(hs[j], ws[j])
-        per_image = (time.time() - t0) / n
-        out, pending = [], []
         # plain Python numbers for the per-ROI scalars (numpy scalar indexing costs ~100 ns a piece, x 10 per ROI)
-        roi_det_l, roi_box_l = res.roi_det.tolist(), res.roi_box.tolist()
         seg_method_l = res.seg_method.tolist() if getattr(res, "seg_method", None) is not None else None
         seg_area_l = res.seg_area.tolist() if getattr(res, "seg_area", None) is not None else None
         seg_sums_l = res.seg_sums.tolist() if getattr(res, "seg_sums", None) is not None else None
         seg_cont_l = res.seg_contours.tolist() if getattr(res, "seg_contours", None) is not None else None
+        segs_of = [{} for _ in range(n)]
+        for i in range(n):
+            dets = dets_of[i]
+            if errs[i] is not None or not (include_segmentation and dets):
+                continue
+            try:
+                sel, lm, ar, sm, cs_ = [], {}, {}, {}, {}
+                for k in ks_of[i]:
+                    x1, y1, x2, y2 = roi_box_l[k]
+                    code = seg_method_l[k]
+                    name = seg._select_segmentation_method(dets[roi_det_l[k]]["class"])
+                    name = name if name in ("adaptive", "threshold") else "threshold_fallback"
+                    j = len(sel)
+                    sel.append((roi_det_l[k], x1, y1, x2, y2, name))
+                    lm[j], ar[j], sm[j] = masks_host[k], seg_area_l[k], seg_sums_l[k]
+                    cs_[j] = seg_cont_l[k]
+                    assert (code == ffi.QC_SEG_REF_ADAPTIVE) == (name == "adaptive")
+                segs_of[i] = seg._assemble(frames_np[i], dets, sel, lm, ar, sm, bgr=raw_ok, cstats=cs_)
+            except Exception as e:
+                errs[i] = e
+        # ---- phase 2: everything else of the batch (classifier probabilities, SPC vector)
+        res = pend.result()
+        per_image = (time.time() - t0) / n
+        out, pending = [], []
         for i in range(n):
             try:
-                rows = res.det[i, :int(res.count[i])]
+                if errs[i] is not None:
+                    raise errs[i]
                 shape = shapes[i]
-                dets = ydet._parse_results(rows, shape)
+                dets = dets_of[i]
                 yolo_results = {"detections": dets, "inference_time_ms": per_image * 1000,
                                 "image_shape": tuple(shape[:2]), "total_detections": len(dets)}
                 resnet_results = rcls._result(res.global_probs[i])
                 resnet_results["inference_time_ms"] = per_image * 1000
-                ks = np.nonzero(res.roi_img == i)[0].tolist()
-                roi_probs = {roi_det_l[k]: res.roi_probs[k] for k in ks} if res.roi_probs is not None else {}
+                roi_probs = {roi_det_l[k]: res.roi_probs[k] for k in ks_of[i]} if res.roi_probs is not None else {}
                 ensemble_results = ens._combine_predictions(yolo_results, resnet_results, shape, None, _roi_probs=roi_probs)
                 ensemble_results["total_inference_time_ms"] = per_image * 1000
                 if "error" in ensemble_results:
                     out.append(ensemble_results)
                     continue
-                segmentation_results = {}
-                if include_segmentation and dets:
-                    sel, lm, ar, sm, cs_ = [], {}, {}, {}, {}
-                    for k in ks:
-                        x1, y1, x2, y2 = roi_box_l[k]
-                        code = seg_method_l[k]
-                        name = seg._select_segmentation_method(dets[roi_det_l[k]]["class"])
-                        name = name if name in ("adaptive", "threshold") else "threshold_fallback"
-                        j = len(sel)
-                        sel.append((roi_det_l[k], x1, y1, x2, y2, name))
-                        lm[j], ar[j], sm[j] = masks_host[k], seg_area_l[k], seg_sums_l[k]
-                        cs_[j] = seg_cont_l[k]
-                        assert (code == ffi.QC_SEG_REF_ADAPTIVE) == (name == "adaptive")
-                    segmentation_results = seg._assemble(frames_np[i], dets, sel, lm, ar, sm, bgr=raw_ok, cstats=cs_)
                 out.append(None)
-                pending.append((i, (ensemble_results, segmentation_results, shape)))
+                pending.append((i, (ensemble_results, segs_of[i], shape)))
             except Exception as e:
                 logger.error(f"Error in QC prediction: {str(e)}")
                 out.append({"error": str(e)})

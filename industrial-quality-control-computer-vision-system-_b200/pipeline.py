@@ -296,7 +296,7 @@ class InspectionPipeline:
         # The segmentation needs the frames and the kept boxes only -- not the classifier -- and its kernels are
         # latency-bound chains on small ROIs: it is queued FIRST, on its own stream, so that it runs underneath the
         # ResNet-50 graphs instead of after them (joined again before the result copies).
-        seg, seg_done = None, None
+        seg, seg_done, seg_ready, seg_host = None, None, None, {}
         if include_segmentation and K:
             cls = det[roi_img, roi_det, 5].astype(np.int32)
             side = self.seg_stream if self.overlap_seg else torch.cuda.current_stream(self.dev)
@@ -305,9 +305,20 @@ class InspectionPipeline:
             with torch.cuda.stream(side):
                 seg = self._segment_rois(frames, roi_img, roi_box, cls, keep_seg_tensors, morph_iters, min_area,
                                          swap_rb=not processed)
+                # the segmentation's results go to pinned host memory right behind its kernels, on its own stream, with
+                # their own event: a caller that assembles per-region dictionaries can start on them while the
+                # classifier graphs are still running (PendingResult.seg_result)
+                for gi, g in enumerate(seg):
+                    for k in ("area", "thr", "ncomp", "sums", "contours") + (("mask",) if keep_seg_tensors else ()):
+                        if g["seg"].get(k) is not None:
+                            t = g["seg"][k]
+                            hbuf = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+                            hbuf.copy_(t, non_blocking=True)
+                            seg_host[f"{k}{gi}"] = hbuf
+                seg_ready = torch.cuda.Event()
+                seg_ready.record(side)
                 if self.overlap_seg:
-                    seg_done = torch.cuda.Event()
-                    seg_done.record(side)
+                    seg_done = seg_ready
             self.last_seg_pixels = int(sum(int(g["seg"]["params"].total_pixels) for g in seg))
 
         n_whole = n if self.classify_global else 0
@@ -351,16 +362,12 @@ class InspectionPipeline:
         host = {"spc": stage(spc_d)}
         if probs is not None:
             host["probs"] = stage(probs)
-        if seg is not None:
-            for gi, g in enumerate(seg):
-                for k in ("area", "thr", "ncomp", "sums", "contours"):
-                    if g["seg"].get(k) is not None:
-                        host[f"{k}{gi}"] = stage(g["seg"][k])
+        host.update(seg_host)
         done = torch.cuda.Event()
         done.record()
         if stage_slot is not None:
             stage_slot[1] = done         # the staging buffer may be overwritten once this batch's kernels are done
-        return PendingResult(self, res, frames, host, done, dict(K=K, n=n, seg=seg, keep=keep_seg_tensors))
+        return PendingResult(self, res, frames, host, done, dict(K=K, n=n, seg=seg, keep=keep_seg_tensors), seg_ready)
 
     def _segment_rois(self, frames, roi_img, roi_box, cls, keep: bool, morph_iters: int = 1, min_area: int = 20,
                       swap_rb: bool = True):
@@ -456,13 +463,59 @@ class PendingResult:
     """Handle of a batch whose result copies are still in flight; ``result()`` waits for them.  Letting the host
     run ahead (submit batch i+1, then finalise batch i) keeps the GPU busy between steps."""
 
-    def __init__(self, pipe, res, frames, host, done, meta):
+    def __init__(self, pipe, res, frames, host, done, meta, seg_ready=None):
         self.pipe, self.res, self.frames, self.host, self.done, self.meta = pipe, res, frames, host, done, meta
+        self.seg_ready = seg_ready
         self._final = None
+        self._seg_final = False
+
+    def seg_result(self) -> BatchResult:
+        """Waits for the segmentation alone (it runs on its own stream underneath the classifier) and fills the
+        ``seg_*`` fields of the batch result; ``result()`` later adds the classifier's part."""
+        res, m, pipe = self.res, self.meta, self.pipe
+        if self._seg_final or m["seg"] is None:
+            return res
+        (self.seg_ready or self.done).synchronize()
+        K = m["K"]
+        res.seg_area = np.zeros(K, np.int64)
+        res.seg_thr = np.zeros(K, np.int32)
+        res.seg_ncomp = np.zeros(K, np.int32)
+        res.seg_method = np.zeros(K, np.int32)
+        res.seg_sums = np.zeros((K, 4), np.int64)
+        res.seg_contours = np.zeros((K, 4), np.int64)
+        for gi, g in enumerate(m["seg"]):
+            idx = g["idx"]
+            area = self.host[f"area{gi}"].numpy().copy()
+            ncomp = self.host[f"ncomp{gi}"].numpy()
+            if g["cap"] is not None:
+                over = np.nonzero(ncomp > g["cap"])[0]
+                if len(over):   # components beyond the reservation escaped the min-area filter: redo exactly
+                    sub = {k: (v[over] if isinstance(v, np.ndarray) else v) for k, v in g["regs"].items() if k != "max_comp"}
+                    # on the segmentation stream: its cached workspaces may be in use by the next batch there
+                    side = pipe.seg_stream if pipe.overlap_seg else torch.cuda.current_stream(pipe.dev)
+                    with torch.cuda.stream(side):
+                        seg2 = pipe.qc.segment(self.frames, sub, morph_iters=g["iters"], swap_rb=g["swap_rb"], want_mask=False,
+                                               want_labels=False, method=g["code"])
+                        area[over] = seg2["area"].cpu().numpy()
+            res.seg_area[idx] = area
+            res.seg_thr[idx] = self.host[f"thr{gi}"].numpy()
+            res.seg_ncomp[idx] = ncomp
+            res.seg_method[idx] = g["code"]
+            if f"sums{gi}" in self.host:
+                res.seg_sums[idx] = self.host[f"sums{gi}"].numpy()
+            if f"contours{gi}" in self.host:
+                res.seg_contours[idx] = self.host[f"contours{gi}"].numpy()
+            if f"mask{gi}" in self.host:
+                g["mask_host"] = self.host[f"mask{gi}"].numpy()      # packed mask bytes of the group, already on the host
+        if m["keep"]:
+            res.seg = m["seg"]
+        self._seg_final = True
+        return res
 
     def result(self) -> BatchResult:
         if self._final is not None:
             return self._final
+        self.seg_result()
         self.done.synchronize()
         res, m, pipe = self.res, self.meta, self.pipe
         n, K = m["n"], m["K"]
@@ -475,37 +528,6 @@ class PendingResult:
                 o = n
             if pipe.classify_rois and K:
                 res.roi_probs = pr[o:o + K].copy()
-        if m["seg"] is not None:
-            res.seg_area = np.zeros(K, np.int64)
-            res.seg_thr = np.zeros(K, np.int32)
-            res.seg_ncomp = np.zeros(K, np.int32)
-            res.seg_method = np.zeros(K, np.int32)
-            res.seg_sums = np.zeros((K, 4), np.int64)
-            res.seg_contours = np.zeros((K, 4), np.int64)
-            for gi, g in enumerate(m["seg"]):
-                idx = g["idx"]
-                area = self.host[f"area{gi}"].numpy().copy()
-                ncomp = self.host[f"ncomp{gi}"].numpy()
-                if g["cap"] is not None:
-                    over = np.nonzero(ncomp > g["cap"])[0]
-                    if len(over):   # components beyond the reservation escaped the min-area filter: redo exactly
-                        sub = {k: (v[over] if isinstance(v, np.ndarray) else v) for k, v in g["regs"].items() if k != "max_comp"}
-                        # on the segmentation stream: its cached workspaces may be in use by the next batch there
-                        side = pipe.seg_stream if pipe.overlap_seg else torch.cuda.current_stream(pipe.dev)
-                        with torch.cuda.stream(side):
-                            seg2 = pipe.qc.segment(self.frames, sub, morph_iters=g["iters"], swap_rb=g["swap_rb"], want_mask=False,
-                                                   want_labels=False, method=g["code"])
-                            area[over] = seg2["area"].cpu().numpy()
-                res.seg_area[idx] = area
-                res.seg_thr[idx] = self.host[f"thr{gi}"].numpy()
-                res.seg_ncomp[idx] = ncomp
-                res.seg_method[idx] = g["code"]
-                if f"sums{gi}" in self.host:
-                    res.seg_sums[idx] = self.host[f"sums{gi}"].numpy()
-                if f"contours{gi}" in self.host:
-                    res.seg_contours[idx] = self.host[f"contours{gi}"].numpy()
-            if m["keep"]:
-                res.seg = m["seg"]
         self.frames = None
         self._final = res
         return res
