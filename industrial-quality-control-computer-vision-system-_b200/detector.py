@@ -524,6 +524,12 @@ class _LazyFullMask:
     def extent(self):
         """(y_min, y_max, x_min, x_max) of mask > 0 in frame coordinates, or None -- what
         inference/postprocess.py:784-790 reads off the full-frame mask, without materialising it."""
+        if "_ext" in self.__dict__:
+            return self._ext
+        self._ext = self._extent()
+        return self._ext
+
+    def _extent(self):
         loc = self._local
         if loc.dtype == np.uint8 and loc.ndim == 2 and loc.flags.c_contiguous:
             x, y, w, h = cv2.boundingRect(loc)                     # bounding box of the non-zero pixels
@@ -1074,6 +1080,8 @@ class QualityControlDetector:
                     cs_[j] = seg_cont_l[k]
                     assert (code == ffi.QC_SEG_REF_ADAPTIVE) == (name == "adaptive")
                 segs_of[i] = seg._assemble(frames_np[i], dets, sel, lm, ar, sm, bgr=raw_ok, cstats=cs_)
+                for r in segs_of[i]["segmented_regions"]:          # the rule chain's mask extents (memoised), off the tail
+                    r["mask"].extent()
             except Exception as e:
                 errs[i] = e
         # ---- phase 2: everything else of the batch (classifier probabilities, SPC vector)
