@@ -152,7 +152,9 @@ int qc_nms(qc_ctx* ctx, const float* boxes, const float* scores, const int32_t* 
  * imgs: n images uint8 HWC; rois: device float32 [K][5] = (img, x1, y1, x2, y2).
  * sampling_ratio 1..2, out_w % 4 == 0, out_w <= 224: two launches per call -- k3_roi_win (boxes whose bins are <= 1.95
  * source pixels with every sample inside the frame) and k3_roi_tma (whatever is left); other shapes: k3_roi_sep /
- * k3_roi_align.  Results do not depend on which kernel took a box beyond float32 rounding (<= 1e-3 absolute).      */
+ * k3_roi_align.  Results do not depend on which kernel took a box beyond float32 rounding (<= 1e-3 absolute).
+ * Work items are handed out in table order: when the boxes differ much in size, list the biggest first (with
+ * qc_roi_align_rows every ROI carries its destination row, so the order of the table is free).                     */
 int qc_roi_align(qc_ctx* ctx, const uint8_t* imgs, int n, int h, int w, int64_t img_stride,
                  int32_t row_stride, const float* rois, int K, int out_h, int out_w,
                  int sampling_ratio, int aligned, int swap_rb, const float* norm,

@@ -340,6 +340,11 @@ class InspectionPipeline:
             if n_roi:
                 r = np.concatenate((roi_img[:, None].astype(np.float32), roi_box.astype(np.float32),
                                     rows[n_whole:, None].astype(np.int32).view(np.float32)), 1)   # one upload: rois + rows
+                # K3 hands its work items out in table order and the boxes of a batch differ 100x in area: biggest
+                # first, so that no CTA starts a 400-pixel box when the others are finishing (-17 % on this batch);
+                # every ROI carries its destination row, so the order of the table is free
+                area = (roi_box[:, 2] - roi_box[:, 0]).astype(np.int64) * (roi_box[:, 3] - roi_box[:, 1])
+                r = r[np.argsort(-area, kind="stable")]
                 rd = torch.from_numpy(np.ascontiguousarray(r)).to(self.dev, non_blocking=True)
                 rois = rd[:, :5].contiguous()
                 drows = rd[:, 5].contiguous().view(torch.int32)
@@ -386,6 +391,9 @@ class InspectionPipeline:
         for name, idx, code, iters, marea in specs:
             if len(idx) == 0:
                 continue
+            # biggest regions first: k7_fill hands regions out through a work counter, the band kernels stride over the
+            # table -- either way the long regions should not be the last ones to start (results are scattered back by idx)
+            idx = idx[np.argsort(-(w[idx].astype(np.int64) * h[idx]), kind="stable")]
             regs = dict(img=roi_img[idx], x=roi_box[idx, 0], y=roi_box[idx, 1], w=w[idx], h=h[idx],
                         polarity=(~np.isin(cls[idx], DARK_CLASSES)).astype(np.int32), thr_scale=1.0, min_area=marea)
             cap = None

@@ -20,6 +20,8 @@ if os.environ.get("K3_MIX"):
     r[:, 3] = r[:, 1] + bw; r[:, 4] = r[:, 2] + bh
 else:
     r[:, 3] = r[:, 1] + rng.integers(40, 120, K); r[:, 4] = r[:, 2] + rng.integers(40, 120, K)
+if os.environ.get("K3_SORT"):          # biggest boxes first (the work items are handed out in table order)
+    r = r[np.argsort(-(r[:, 3] - r[:, 1]) * (r[:, 4] - r[:, 2]), kind="stable")]
 rois = torch.from_numpy(r).cuda()
 out = torch.empty((K, 3, 224, 224), dtype=torch.bfloat16, device="cuda")
 for _ in range(3):
