@@ -1159,10 +1159,12 @@ extern "C" int qc_roi_align_rows(qc_ctx* ctx, const uint8_t* imgs, int n, int h,
         constexpr int K3W_TH = 256 / NC;                                                                           \
         if (int rc = qc_prepare(ctx, k3_roi_win<T, CW, CH, NC>, (int)wsmem, K3W_TH, &occ)) return rc;               \
         const int slots = ctx->sm_count * std::max(occ, 1);                                                        \
-        /* 2^sl work items per box: 8, or 4 once there are ~9 quarter-boxes per resident CTA (measured on the bench  \
-           step's box sizes: 1400 boxes 250 / 228 us at sl = 2 / 3, 3000 boxes equal, 5441 boxes 597 / 629 us; halves    \
-           of boxes lose to the big boxes' imbalance at every size) */                                             \
-        int sl = ((long long)K << 2) >= 9LL * slots ? 2 : 3;                                                        \
+        /* 2^sl work items per box: 8, 4 from one box per resident CTA on, 2 from four on.  Measured on the bench      \
+           step's box sizes with the table sorted biggest first (sl = 1 / 2 / 3): 1400 boxes 222 / 164 / 166 us,         \
+           5441 boxes 524 / 550 / 611 us; unsorted 1400: 331 / 250 / 228, 5441: 656 / 597 / 629 */                      \
+        int sl = 3;                                                                                                \
+        if ((long long)K >= (long long)slots) sl = 2;                                                               \
+        if ((long long)K >= 4LL * slots) sl = 1;                                                                    \
         if (split_env >= 0) sl = split_env;                                                                        \
         while ((out_h >> sl) + 1 > K3W_PH_MAX) ++sl;                                                               \
         const unsigned wgrid = (unsigned)std::min<long long>((long long)K << sl, slots);                           \
