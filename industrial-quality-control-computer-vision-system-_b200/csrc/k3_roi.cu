@@ -1158,7 +1158,8 @@ extern "C" int qc_roi_align_rows(qc_ctx* ctx, const uint8_t* imgs, int n, int h,
     do {                                                                                                           \
         constexpr int K3W_TH = 256 / NC;                                                                           \
         if (int rc = qc_prepare(ctx, k3_roi_win<T, CW, CH, NC>, (int)wsmem, K3W_TH, &occ)) return rc;               \
-        const int slots = ctx->sm_count * std::max(occ, 1);                                                        \
+        static const int ctas_env = getenv("QC_K3_CTAS") ? atoi(getenv("QC_K3_CTAS")) : 0;                          \
+        const int slots = ctx->sm_count * (ctas_env > 0 ? std::min(std::max(occ, 1), ctas_env) : std::max(occ, 1)); \
         /* 2^sl work items per box: 8, 4 from one box per resident CTA on, 2 from four on.  Measured on the bench      \
            step's box sizes with the table sorted biggest first (sl = 1 / 2 / 3): 1400 boxes 222 / 164 / 166 us,         \
            5441 boxes 524 / 550 / 611 us; unsorted 1400: 331 / 250 / 228, 5441: 656 / 597 / 629 */                      \
